@@ -1,0 +1,206 @@
+/* neo_b200.h -- C ABI of the B200-native FFT / partitioned-convolution backend for neo-sonar/neo-dsp.
+ *
+ * The reference has no FFI: its backend seam is a compile-time alias over C++ "plan" / "convolver" duck types
+ * (src/neo/fft/fft.hpp:36-52, src/neo/fft/rfft.hpp:15-23, src/neo/convolution/dense_convolver.hpp:20-41).
+ * This header is what one more backend behind those aliases binds to; the C++ facade that satisfies the duck types
+ * on top of it is include/neo_b200.hpp, and INTEGRATION.md shows the alias branches a maintainer adds.
+ *
+ * Conventions
+ *   - complex data is interleaved [re, im] (layout of std::complex<T> and neo::scalar_complex<T>,
+ *     src/neo/complex/scalar_complex.hpp:113);
+ *   - `dtype` names the REAL element type (NEO_B200_F32 / NEO_B200_F64);
+ *   - transforms are UNNORMALISED in both directions, like every reference plan (c2c_dit2_plan.hpp:84-95,
+ *     fallback_rfft_plan.hpp:39-55); forward is exp(-2 pi i nk/N) (fft/direction.hpp:8-12);
+ *   - `memspace` says where in/out live: HOST buffers are staged through pinned memory and the call returns when the
+ *     result is in `out`; DEVICE buffers are used in place, the work is enqueued on the handle's stream and the
+ *     call returns immediately (use *_synchronize or the stream);
+ *   - every function returns a neo_b200_status (0 = ok); neo_b200_last_error() gives the message of the last
+ *     failure on the calling thread. The C++ facade turns failures of create/set_filter into std::runtime_error,
+ *     which is what the reference throws from plan construction (c2c_dit2_plan.hpp:98-104, backend/ipp.hpp:30-51);
+ *   - handles are not re-entrant; distinct handles are independent (the reference's plans hold mutable scratch too);
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute entry point fails with
+ *     NEO_B200_ERR_CUDA.
+ */
+#ifndef NEO_B200_H
+#define NEO_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+    #define NEO_B200_API __declspec(dllexport)
+#else
+    #define NEO_B200_API __attribute__((visibility("default")))
+#endif
+
+typedef enum neo_b200_status
+{
+    NEO_B200_OK              = 0,
+    NEO_B200_ERR_INVALID     = 1, /* bad argument (null handle, extent mismatch, ...) */
+    NEO_B200_ERR_UNSUPPORTED = 2, /* e.g. order > max_order: the reference throws std::runtime_error here */
+    NEO_B200_ERR_CUDA        = 3, /* CUDA runtime failure / no device */
+    NEO_B200_ERR_ALLOC       = 4
+} neo_b200_status;
+
+typedef enum neo_b200_dtype
+{
+    NEO_B200_F32 = 0,
+    NEO_B200_F64 = 1
+} neo_b200_dtype;
+
+/* src/neo/fft/direction.hpp:8-12 */
+typedef enum neo_b200_direction
+{
+    NEO_B200_FORWARD  = -1,
+    NEO_B200_BACKWARD = 1
+} neo_b200_direction;
+
+typedef enum neo_b200_memspace
+{
+    NEO_B200_HOST   = 0,
+    NEO_B200_DEVICE = 1
+} neo_b200_memspace;
+
+/* ---- library ------------------------------------------------------------------------------------------------- */
+NEO_B200_API const char* neo_b200_last_error(void);
+NEO_B200_API const char* neo_b200_version(void);
+NEO_B200_API int neo_b200_device_count(void);                /* number of CUDA devices, 0 when none */
+NEO_B200_API int neo_b200_set_device(int device);            /* device used by handles created afterwards on this thread */
+NEO_B200_API int neo_b200_kernel_launches(uint64_t* count);  /* kernels launched by this library since load */
+
+/* ---- c2c plan: replaces neo::fft::fft_plan<Complex> == c2c_dit2_plan (fft/reference/c2c_dit2_plan.hpp:22-104) ---- */
+typedef struct neo_b200_fft_plan neo_b200_fft_plan;
+
+/* ctor `Plan(from_order, order)` (c2c_dit2_plan.hpp:55-56). order > max_order -> NEO_B200_ERR_UNSUPPORTED. */
+NEO_B200_API int neo_b200_fft_plan_create(neo_b200_fft_plan** plan, size_t order, int dtype);
+NEO_B200_API void neo_b200_fft_plan_destroy(neo_b200_fft_plan* plan);
+NEO_B200_API size_t neo_b200_fft_plan_order(neo_b200_fft_plan const* plan); /* c2c_dit2_plan.hpp:71-75 */
+NEO_B200_API size_t neo_b200_fft_plan_size(neo_b200_fft_plan const* plan);  /* c2c_dit2_plan.hpp:77-81 */
+NEO_B200_API size_t neo_b200_fft_max_order(void);                           /* c2c_dit2_plan.hpp:59-62: 27 */
+
+/* `plan(x, dir)` (c2c_dit2_plan.hpp:84-95) on `batch` contiguous transforms [batch][size]; in == out is in place,
+ * otherwise out-of-place (the optional 3-argument overload looked up by fft/fft.hpp:65,84). */
+NEO_B200_API int neo_b200_fft_exec(neo_b200_fft_plan* plan, void const* in, void* out, size_t batch, int direction, int memspace);
+
+/* one transform over a strided rank-1 view (strides in complex elements; layout_stride mdspan, fft_test.cpp:114-128);
+ * HOST memory only: staged through a contiguous buffer like backend/ipp.hpp:150-158 */
+NEO_B200_API int neo_b200_fft_exec_strided(
+    neo_b200_fft_plan* plan, void const* in, ptrdiff_t in_stride, void* out, ptrdiff_t out_stride, int direction);
+
+NEO_B200_API int neo_b200_fft_plan_set_stream(neo_b200_fft_plan* plan, void* cuda_stream);
+NEO_B200_API int neo_b200_fft_plan_synchronize(neo_b200_fft_plan* plan);
+
+/* ---- rfft plan: replaces neo::fft::rfft_plan<Float, Complex> == fallback_rfft_plan
+ *      (fft/fallback/fallback_rfft_plan.hpp:15-61) ---------------------------------------------------------------- */
+typedef struct neo_b200_rfft_plan neo_b200_rfft_plan;
+
+NEO_B200_API int neo_b200_rfft_plan_create(neo_b200_rfft_plan** plan, size_t order, int dtype);
+NEO_B200_API void neo_b200_rfft_plan_destroy(neo_b200_rfft_plan* plan);
+NEO_B200_API size_t neo_b200_rfft_plan_order(neo_b200_rfft_plan const* plan);
+NEO_B200_API size_t neo_b200_rfft_plan_size(neo_b200_rfft_plan const* plan);
+
+/* r2c `plan(real_in, complex_out)` (fallback_rfft_plan.hpp:28-36): in [batch][N] reals -> out [batch][N/2+1] complex */
+NEO_B200_API int neo_b200_rfft_exec(neo_b200_rfft_plan* plan, void const* in, void* out, size_t batch, int memspace);
+
+/* c2r `plan(complex_in, real_out)` (fallback_rfft_plan.hpp:39-55): in [batch][in_row_len] complex of which the
+ * first N/2+1 per row are used (callers may hand N-long rows, overlap_save.hpp:57,107) -> out [batch][N] reals.
+ * UNNORMALISED; the imaginary parts of bins 0 and N/2 do not influence the result (the reference takes .real()). */
+NEO_B200_API int neo_b200_irfft_exec(
+    neo_b200_rfft_plan* plan, void const* in, size_t in_row_len, void* out, size_t batch, int memspace);
+
+NEO_B200_API int neo_b200_rfft_plan_set_stream(neo_b200_rfft_plan* plan, void* cuda_stream);
+NEO_B200_API int neo_b200_rfft_plan_synchronize(neo_b200_rfft_plan* plan);
+
+/* ---- index tables: bit-exact with the reference ------------------------------------------------------------------ */
+/* bitrevorder_plan's table (fft/reference/bitrevorder.hpp:65-75): out[i] = reverse_bits(i, order), 2^order entries */
+NEO_B200_API int neo_b200_bitrev_table(size_t order, uint32_t* out);
+/* permutation applied by digitrevorder_plan<radix> (fft/reference/digitrevorder.hpp:13-48) to iota(size) */
+NEO_B200_API int neo_b200_digitrev_perm(size_t radix, size_t size, uint32_t* out);
+/* fdl_index (convolution/fdl_index.hpp:24-36): for each of `calls` blocks the write position and the `parts`
+ * (fdl row, filter row) pairs; evaluated with the indexer the MAC kernel uses. pairs: [calls][parts][2] */
+NEO_B200_API int neo_b200_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, uint32_t* pairs);
+/* number of partitions of an L-tap impulse response at block size B (fft/stft.hpp:21-25, overlap 0): ceil(L/B) */
+NEO_B200_API size_t neo_b200_num_partitions(size_t taps, size_t block);
+/* fft/order.hpp:33-39 */
+NEO_B200_API size_t neo_b200_next_order(size_t size);
+
+/* ---- filter preparation: replaces neo::convolution::uniform_partition (convolution/uniform_partition.hpp:13-26 ->
+ *      fft/stft.hpp:58-99) ------------------------------------------------------------------------------------------ */
+/* ir [channels][taps] reals -> out [channels][P][block+1] complex, P = neo_b200_num_partitions(taps, block); unscaled.
+ * block must be a power of two (overlap_save.hpp:53 vs stft.hpp:104 agree only then) and taps >= block. */
+NEO_B200_API int neo_b200_uniform_partition(
+    void const* ir, size_t channels, size_t taps, size_t block, void* out, int dtype, int memspace);
+
+/* ---- partitioned convolver: replaces neo::convolution::upols_convolver / upola_convolver
+ *      (convolution/uniform_partitioned_convolver.hpp:14-65, dense_convolver.hpp:20-41), one handle = a bank of
+ *      channels ------------------------------------------------------------------------------------------------------ */
+typedef struct neo_b200_conv neo_b200_conv;
+
+typedef enum neo_b200_conv_kind
+{
+    NEO_B200_UPOLS = 0, /* overlap-save  (convolution/overlap_save.hpp:85-112) */
+    NEO_B200_UPOLA = 1  /* overlap-add   (convolution/overlap_add.hpp:78-107)  */
+} neo_b200_conv_kind;
+
+typedef enum neo_b200_conv_topology
+{
+    NEO_B200_DIAGONAL = 0, /* channel c is convolved with its own filter c: a bank of independent reference convolvers */
+    NEO_B200_MATRIX   = 1  /* out[o] = sum_i in[i] * h[o][i]: every (o,i) pair is one reference convolver, summed per o */
+} neo_b200_conv_topology;
+
+typedef struct neo_b200_conv_config
+{
+    int kind;           /* neo_b200_conv_kind */
+    int dtype;          /* neo_b200_dtype */
+    int topology;       /* neo_b200_conv_topology */
+    size_t outputs;     /* output channels */
+    size_t inputs;      /* input channels (== outputs for DIAGONAL) */
+    size_t block;       /* B, power of two >= 2 */
+    size_t partitions;  /* P of the WHOLE filter */
+    size_t max_blocks;  /* largest number of blocks T handed to one process call (>= 1) */
+    /* partition sharding of long impulse responses across devices: this handle holds partitions
+     * [partition_begin, partition_end) of every filter and yields PARTIAL spectra. 0,0 = all partitions. */
+    size_t partition_begin;
+    size_t partition_end;
+} neo_b200_conv_config;
+
+NEO_B200_API int neo_b200_conv_create(neo_b200_conv** conv, neo_b200_conv_config const* config);
+NEO_B200_API void neo_b200_conv_destroy(neo_b200_conv* conv);
+
+/* `convolver.filter(partitions)` (uniform_partitioned_convolver.hpp:38-45): deep-copies H and zeroes all state
+ * (window, FDL, write position). H: DIAGONAL [outputs][P][block+1], MATRIX [outputs][inputs][P][block+1] complex,
+ * P = config.partitions; a sharded handle reads only its own partition range from it. */
+NEO_B200_API int neo_b200_conv_set_filter(neo_b200_conv* conv, void const* H, int memspace);
+/* same, starting from time-domain impulse responses [filters][taps] (uniform_partition fused in, on the device) */
+NEO_B200_API int neo_b200_conv_set_impulse(neo_b200_conv* conv, void const* ir, size_t taps, int memspace);
+/* zero window / FDL / write position, keep the filter */
+NEO_B200_API int neo_b200_conv_reset(neo_b200_conv* conv);
+
+/* `convolver(block)` (uniform_partitioned_convolver.hpp:48-65) for every channel of the bank, `blocks` consecutive
+ * blocks per call: in [inputs][blocks*B] -> out [outputs][blocks*B] reals; in == out allowed for DIAGONAL (the
+ * reference is in place). blocks == 1 is the reference's streaming call; blocks > 1 gives identical results to
+ * `blocks` successive calls but reuses each filter partition across the blocks. */
+NEO_B200_API int neo_b200_conv_process(neo_b200_conv* conv, void const* in, void* out, size_t blocks, int memspace);
+
+/* split form for partition-sharded handles: forward = window + r2c + FDL insert + spectral MAC -> partial spectra
+ * [outputs][blocks][B] complex in an internal packed layout (device pointer below; sum across shards elementwise);
+ * inverse = c2r + overlap handling of (already summed) spectra for outputs [first, first+count). */
+NEO_B200_API int neo_b200_conv_forward(neo_b200_conv* conv, void const* in, size_t blocks, int memspace);
+NEO_B200_API int neo_b200_conv_spectra(neo_b200_conv* conv, void** device_ptr, size_t* bytes_per_output_block);
+NEO_B200_API int neo_b200_conv_inverse(
+    neo_b200_conv* conv, void const* spectra_device, void* out, size_t first, size_t count, size_t blocks, int memspace);
+
+NEO_B200_API int neo_b200_conv_set_stream(neo_b200_conv* conv, void* cuda_stream);
+NEO_B200_API int neo_b200_conv_synchronize(neo_b200_conv* conv);
+/* bytes of device memory held by the handle (filter + FDL + scratch) */
+NEO_B200_API size_t neo_b200_conv_device_bytes(neo_b200_conv const* conv);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* NEO_B200_H */

@@ -1,0 +1,525 @@
+"""neo_b200 -- host-side Python mirror of the reference's front end over the C ABI (include/neo_b200.h).
+
+The reference's Python package is a thin pybind11 layer (extra/python/src/main.cpp:130-198, extra/python/src/neo/fft/__init__.py:20-29):
+``neo.fft.fft(x, n, norm)``, ``neo.fft.ifft``, ``neo.convolve(in1, in2, mode, method)``. The same names live here, plus the plan /
+convolver objects the C++ drivers use (Plan(order) + call on spans; Convolver.filter(H) + call on a block), batched.
+
+Everything computes on the GPU through ``libneo_b200.so``. There is NO CPU fallback: if the library is missing or no CUDA
+device is usable, importing works but every compute call raises ``RuntimeError``.
+
+numpy arrays are HOST buffers (copied to the device and back inside the call, synchronous like the reference);
+objects with ``data_ptr()`` / ``__cuda_array_interface__`` (torch CUDA tensors) are DEVICE buffers used in place, the work
+is enqueued on the handle's stream.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Any
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIBRARY_PATH = os.path.join(_HERE, "libneo_b200.so")
+
+F32, F64 = 0, 1
+FORWARD, BACKWARD = -1, 1
+HOST, DEVICE = 0, 1
+UPOLS, UPOLA = 0, 1
+DIAGONAL, MATRIX = 0, 1
+
+_vp, _sz, _i = C.c_void_p, C.c_size_t, C.c_int
+
+
+class ConvConfig(C.Structure):
+    _fields_ = [
+        ("kind", _i),
+        ("dtype", _i),
+        ("topology", _i),
+        ("outputs", _sz),
+        ("inputs", _sz),
+        ("block", _sz),
+        ("partitions", _sz),
+        ("max_blocks", _sz),
+        ("partition_begin", _sz),
+        ("partition_end", _sz),
+    ]
+
+
+# name -> (restype, argtypes): exactly the entry points include/neo_b200.h declares
+SIGNATURES = {
+    "neo_b200_last_error": (C.c_char_p, []),
+    "neo_b200_version": (C.c_char_p, []),
+    "neo_b200_device_count": (_i, []),
+    "neo_b200_set_device": (_i, [_i]),
+    "neo_b200_kernel_launches": (_i, [C.POINTER(C.c_uint64)]),
+    "neo_b200_fft_plan_create": (_i, [C.POINTER(_vp), _sz, _i]),
+    "neo_b200_fft_plan_destroy": (None, [_vp]),
+    "neo_b200_fft_plan_order": (_sz, [_vp]),
+    "neo_b200_fft_plan_size": (_sz, [_vp]),
+    "neo_b200_fft_max_order": (_sz, []),
+    "neo_b200_fft_exec": (_i, [_vp, _vp, _vp, _sz, _i, _i]),
+    "neo_b200_fft_exec_strided": (_i, [_vp, _vp, C.c_ssize_t, _vp, C.c_ssize_t, _i]),
+    "neo_b200_fft_plan_set_stream": (_i, [_vp, _vp]),
+    "neo_b200_fft_plan_synchronize": (_i, [_vp]),
+    "neo_b200_rfft_plan_create": (_i, [C.POINTER(_vp), _sz, _i]),
+    "neo_b200_rfft_plan_destroy": (None, [_vp]),
+    "neo_b200_rfft_plan_order": (_sz, [_vp]),
+    "neo_b200_rfft_plan_size": (_sz, [_vp]),
+    "neo_b200_rfft_exec": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "neo_b200_irfft_exec": (_i, [_vp, _vp, _sz, _vp, _sz, _i]),
+    "neo_b200_rfft_plan_set_stream": (_i, [_vp, _vp]),
+    "neo_b200_rfft_plan_synchronize": (_i, [_vp]),
+    "neo_b200_bitrev_table": (_i, [_sz, _vp]),
+    "neo_b200_digitrev_perm": (_i, [_sz, _sz, _vp]),
+    "neo_b200_fdl_index_sequence": (_i, [_sz, _sz, _vp, _vp]),
+    "neo_b200_num_partitions": (_sz, [_sz, _sz]),
+    "neo_b200_next_order": (_sz, [_sz]),
+    "neo_b200_uniform_partition": (_i, [_vp, _sz, _sz, _sz, _vp, _i, _i]),
+    "neo_b200_conv_create": (_i, [C.POINTER(_vp), C.POINTER(ConvConfig)]),
+    "neo_b200_conv_destroy": (None, [_vp]),
+    "neo_b200_conv_set_filter": (_i, [_vp, _vp, _i]),
+    "neo_b200_conv_set_impulse": (_i, [_vp, _vp, _sz, _i]),
+    "neo_b200_conv_reset": (_i, [_vp]),
+    "neo_b200_conv_process": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "neo_b200_conv_forward": (_i, [_vp, _vp, _sz, _i]),
+    "neo_b200_conv_spectra": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
+    "neo_b200_conv_inverse": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _i]),
+    "neo_b200_conv_set_stream": (_i, [_vp, _vp]),
+    "neo_b200_conv_synchronize": (_i, [_vp]),
+    "neo_b200_conv_device_bytes": (_sz, [_vp]),
+}
+
+_lib = None
+
+
+def library() -> C.CDLL:
+    """The C-ABI library; raises if it has not been built (no fallback of any kind)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIBRARY_PATH):
+            raise RuntimeError(
+                f"{LIBRARY_PATH} is missing: build it with `make -C neo-dsp_b200` (or __graft_entry__.build()); "
+                "neo_b200 has no CPU fallback"
+            )
+        lib = C.CDLL(LIBRARY_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def _check(status: int) -> None:
+    if status != 0:
+        raise RuntimeError(library().neo_b200_last_error().decode())
+
+
+def kernel_launches() -> int:
+    n = C.c_uint64(0)
+    _check(library().neo_b200_kernel_launches(C.byref(n)))
+    return int(n.value)
+
+
+def device_count() -> int:
+    return int(library().neo_b200_device_count())
+
+
+def set_device(index: int) -> None:
+    _check(library().neo_b200_set_device(index))
+
+
+# ---- buffers ---------------------------------------------------------------------------------------------------------
+_REAL_OF = {"complex64": "float32", "complex128": "float64", "float32": "float32", "float64": "float64"}
+_DTYPE_CODE = {"float32": F32, "float64": F64}
+
+
+def _is_device(a: Any) -> bool:
+    return hasattr(a, "data_ptr") and getattr(a, "is_cuda", False)
+
+
+def _dtype_name(a: Any) -> str:
+    return str(a.dtype).replace("torch.", "")
+
+
+def _ptr(a: Any) -> int:
+    if _is_device(a):
+        if not a.is_contiguous():
+            raise ValueError("device buffers must be contiguous")
+        return int(a.data_ptr())
+    if not isinstance(a, np.ndarray) or not a.flags.c_contiguous:
+        raise ValueError("host buffers must be C-contiguous numpy arrays")
+    return int(a.ctypes.data)
+
+
+def _space(a: Any) -> int:
+    return DEVICE if _is_device(a) else HOST
+
+
+def _empty_like_kind(a: Any, shape, dtype_name: str):
+    if _is_device(a):
+        import torch
+
+        return torch.empty(shape, dtype=getattr(torch, dtype_name), device=a.device)
+    return np.empty(shape, dtype=dtype_name)
+
+
+def _stream_ptr(stream: Any) -> int:
+    return int(getattr(stream, "cuda_stream", stream) or 0)
+
+
+# ---- plans -----------------------------------------------------------------------------------------------------------
+class FFTPlan:
+    """neo::fft::fft_plan<Complex>{from_order, order} (fft/reference/c2c_dit2_plan.hpp:22-104), batched over leading axes."""
+
+    def __init__(self, order: int, dtype="complex64"):
+        self.real = _REAL_OF[str(np.dtype(dtype))]
+        self.complex = "complex64" if self.real == "float32" else "complex128"
+        self._h = _vp()
+        _check(library().neo_b200_fft_plan_create(C.byref(self._h), order, _DTYPE_CODE[self.real]))
+
+    @staticmethod
+    def max_order() -> int:
+        return int(library().neo_b200_fft_max_order())
+
+    @staticmethod
+    def max_size() -> int:
+        return 1 << FFTPlan.max_order()
+
+    def order(self) -> int:
+        return int(library().neo_b200_fft_plan_order(self._h))
+
+    def size(self) -> int:
+        return int(library().neo_b200_fft_plan_size(self._h))
+
+    def set_stream(self, stream) -> None:
+        _check(library().neo_b200_fft_plan_set_stream(self._h, _stream_ptr(stream)))
+
+    def synchronize(self) -> None:
+        _check(library().neo_b200_fft_plan_synchronize(self._h))
+
+    def __call__(self, x, direction: int = FORWARD, out=None):
+        """plan(x, dir): in place when `out` is None (like the reference), else out-of-place. x[..., size]."""
+        if _dtype_name(x) != self.complex or x.shape[-1] != self.size():
+            raise ValueError(f"expected {self.complex}[..., {self.size()}]")
+        out = x if out is None else out
+        batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
+        _check(library().neo_b200_fft_exec(self._h, _ptr(x), _ptr(out), batch, direction, _space(x)))
+        return out
+
+    def strided(self, x: np.ndarray, direction: int = FORWARD) -> None:
+        """In-place transform of a strided rank-1 numpy view (layout_stride mdspan, fft_test.cpp:114-128)."""
+        if x.ndim != 1 or x.shape[0] != self.size() or str(x.dtype) != self.complex:
+            raise ValueError("expected a rank-1 complex view of plan size")
+        stride = x.strides[0] // x.itemsize
+        _check(library().neo_b200_fft_exec_strided(self._h, x.ctypes.data, stride, x.ctypes.data, stride, direction))
+
+    def close(self) -> None:
+        if self._h:
+            library().neo_b200_fft_plan_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class RFFTPlan:
+    """neo::fft::rfft_plan<Float>{from_order, order} (fft/fallback/fallback_rfft_plan.hpp:15-61), batched."""
+
+    def __init__(self, order: int, dtype="float32"):
+        self.real = _REAL_OF[str(np.dtype(dtype))]
+        self.complex = "complex64" if self.real == "float32" else "complex128"
+        self._h = _vp()
+        _check(library().neo_b200_rfft_plan_create(C.byref(self._h), order, _DTYPE_CODE[self.real]))
+
+    def order(self) -> int:
+        return int(library().neo_b200_rfft_plan_order(self._h))
+
+    def size(self) -> int:
+        return int(library().neo_b200_rfft_plan_size(self._h))
+
+    def set_stream(self, stream) -> None:
+        _check(library().neo_b200_rfft_plan_set_stream(self._h, _stream_ptr(stream)))
+
+    def synchronize(self) -> None:
+        _check(library().neo_b200_rfft_plan_synchronize(self._h))
+
+    def rfft(self, x, out=None):
+        """x[..., N] real -> [..., N/2+1] complex."""
+        n = self.size()
+        if _dtype_name(x) != self.real or x.shape[-1] != n:
+            raise ValueError(f"expected {self.real}[..., {n}]")
+        if out is None:
+            out = _empty_like_kind(x, tuple(x.shape[:-1]) + (n // 2 + 1,), self.complex)
+        batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
+        _check(library().neo_b200_rfft_exec(self._h, _ptr(x), _ptr(out), batch, _space(x)))
+        return out
+
+    def irfft(self, x, out=None):
+        """x[..., >= N/2+1] complex -> [..., N] real, UNNORMALISED (fallback_rfft_plan.hpp:39-55)."""
+        n = self.size()
+        if _dtype_name(x) != self.complex or x.shape[-1] < n // 2 + 1:
+            raise ValueError(f"expected {self.complex}[..., >= {n // 2 + 1}]")
+        if out is None:
+            out = _empty_like_kind(x, tuple(x.shape[:-1]) + (n,), self.real)
+        batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
+        _check(library().neo_b200_irfft_exec(self._h, _ptr(x), x.shape[-1], _ptr(out), batch, _space(x)))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            library().neo_b200_rfft_plan_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- index tables (bit-exact contract) ----------------------------------------------------------------------------------
+def bitrev_table(order: int) -> np.ndarray:
+    out = np.zeros(1 << order, dtype=np.uint32)
+    _check(library().neo_b200_bitrev_table(order, out.ctypes.data))
+    return out
+
+
+def digitrev_perm(radix: int, size: int) -> np.ndarray:
+    out = np.zeros(size, dtype=np.uint32)
+    _check(library().neo_b200_digitrev_perm(radix, size, out.ctypes.data))
+    return out
+
+
+def fdl_index_sequence(parts: int, calls: int):
+    wp = np.zeros(calls, dtype=np.uint32)
+    pairs = np.zeros((calls, parts, 2), dtype=np.uint32)
+    _check(library().neo_b200_fdl_index_sequence(parts, calls, wp.ctypes.data, pairs.ctypes.data))
+    return wp, pairs
+
+
+def num_partitions(taps: int, block: int) -> int:
+    return int(library().neo_b200_num_partitions(taps, block))
+
+
+def next_order(size: int) -> int:
+    return int(library().neo_b200_next_order(size))
+
+
+# ---- filter preparation + convolver bank -----------------------------------------------------------------------------------
+def uniform_partition(ir, block: int):
+    """neo::convolution::uniform_partition (convolution/uniform_partition.hpp:13-26): ir[C][L] -> H[C][P][block+1]."""
+    if ir.ndim != 2:
+        raise ValueError("impulse response must be [channels][taps]")
+    real = _dtype_name(ir)
+    ch, taps = int(ir.shape[0]), int(ir.shape[1])
+    parts = num_partitions(taps, block)
+    out = _empty_like_kind(ir, (ch, parts, block + 1), "complex64" if real == "float32" else "complex128")
+    _check(library().neo_b200_uniform_partition(_ptr(ir), ch, taps, block, _ptr(out), _DTYPE_CODE[real], _space(ir)))
+    return out
+
+
+class Convolver:
+    """A bank of neo::convolution::upols_convolver / upola_convolver instances
+    (convolution/uniform_partitioned_convolver.hpp:14-65): `filter(H)` then call on blocks.
+
+    H: DIAGONAL [C][P][B+1] (channel c has its own filter), MATRIX [O][I][P][B+1].
+    """
+
+    def __init__(self, kind: int = UPOLS, dtype="float32", topology: int = DIAGONAL, max_blocks: int = 1,
+                 partition_range: tuple[int, int] | None = None):
+        self.kind, self.topology, self.max_blocks = kind, topology, max_blocks
+        self.real = _REAL_OF[str(np.dtype(dtype))]
+        self.partition_range = partition_range
+        self._h = _vp()
+        self.cfg = None
+        self._stream = None
+
+    def _create(self, outputs, inputs, block, partitions):
+        self.close()
+        lo, hi = self.partition_range or (0, 0)
+        self.cfg = ConvConfig(self.kind, _DTYPE_CODE[self.real], self.topology, outputs, inputs, block, partitions,
+                              self.max_blocks, lo, hi)
+        _check(library().neo_b200_conv_create(C.byref(self._h), C.byref(self.cfg)))
+        if self._stream is not None:
+            _check(library().neo_b200_conv_set_stream(self._h, self._stream))
+
+    def filter(self, H) -> None:
+        """convolver.filter(partitions) (uniform_partitioned_convolver.hpp:38-45): deep copy, state zeroed."""
+        want = 3 if self.topology == DIAGONAL else 4
+        if H.ndim != want:
+            raise ValueError(f"filter must have {want} dimensions for this topology")
+        if _dtype_name(H) != ("complex64" if self.real == "float32" else "complex128"):
+            raise ValueError("filter dtype does not match the convolver")
+        outputs = int(H.shape[0])
+        inputs = outputs if self.topology == DIAGONAL else int(H.shape[1])
+        partitions, bins = int(H.shape[-2]), int(H.shape[-1])
+        self._create(outputs, inputs, bins - 1, partitions)
+        _check(library().neo_b200_conv_set_filter(self._h, _ptr(H), _space(H)))
+
+    def impulse(self, ir, block: int) -> None:
+        """filter(uniform_partition(ir, block)) without materialising H on the host. ir: [C][L] or [O][I][L]."""
+        want = 2 if self.topology == DIAGONAL else 3
+        if ir.ndim != want or _dtype_name(ir) != self.real:
+            raise ValueError("impulse response shape/dtype mismatch")
+        outputs = int(ir.shape[0])
+        inputs = outputs if self.topology == DIAGONAL else int(ir.shape[1])
+        taps = int(ir.shape[-1])
+        self._create(outputs, inputs, block, num_partitions(taps, block))
+        _check(library().neo_b200_conv_set_impulse(self._h, _ptr(ir), taps, _space(ir)))
+
+    def set_stream(self, stream) -> None:
+        self._stream = _stream_ptr(stream)
+        if self._h:
+            _check(library().neo_b200_conv_set_stream(self._h, self._stream))
+
+    def synchronize(self) -> None:
+        _check(library().neo_b200_conv_synchronize(self._h))
+
+    def reset(self) -> None:
+        _check(library().neo_b200_conv_reset(self._h))
+
+    def device_bytes(self) -> int:
+        return int(library().neo_b200_conv_device_bytes(self._h))
+
+    def __call__(self, x, out=None):
+        """convolver(block) for every channel: x[inputs][T*B] processed as T blocks; in place when out is None
+        (diagonal only, like the reference)."""
+        block = int(self.cfg.block)
+        if x.ndim != 2 or x.shape[0] != self.cfg.inputs or x.shape[1] % block != 0 or _dtype_name(x) != self.real:
+            raise ValueError(f"expected {self.real}[{self.cfg.inputs}][T*{block}]")
+        if out is None:
+            out = x if self.topology == DIAGONAL else _empty_like_kind(x, (int(self.cfg.outputs), x.shape[1]), self.real)
+        _check(library().neo_b200_conv_process(self._h, _ptr(x), _ptr(out), x.shape[1] // block, _space(x)))
+        return out
+
+    # split form used around the cross-device reduction of partition-sharded handles
+    def forward(self, x) -> None:
+        block = int(self.cfg.block)
+        _check(library().neo_b200_conv_forward(self._h, _ptr(x), x.shape[1] // block, _space(x)))
+
+    def spectra_ptr(self) -> tuple[int, int]:
+        p, n = _vp(), _sz(0)
+        _check(library().neo_b200_conv_spectra(self._h, C.byref(p), C.byref(n)))
+        return int(p.value), int(n.value)
+
+    def spectra_tensor(self, blocks: int):
+        """torch view [outputs][blocks][2B] (float32 pairs) of the partial spectra produced by forward()."""
+        import torch
+
+        ptr, _ = self.spectra_ptr()
+        n = int(self.cfg.outputs) * blocks * int(self.cfg.block) * 2
+        dt = np.float32 if self.real == "float32" else np.float64
+
+        class _Raw:
+            __cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(dt).str, "data": (ptr, False), "version": 3}
+
+        return torch.as_tensor(_Raw(), device=f"cuda:{torch.cuda.current_device()}").view(int(self.cfg.outputs), blocks, -1)
+
+    def inverse(self, spectra, out, first: int, count: int, blocks: int) -> None:
+        sp = spectra if isinstance(spectra, int) else _ptr(spectra)
+        _check(library().neo_b200_conv_inverse(self._h, sp, _ptr(out), first, count, blocks, _space(out)))
+
+    def close(self) -> None:
+        if self._h:
+            library().neo_b200_conv_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+# ---- free functions with the reference's Python names (extra/python/src/neo/fft/__init__.py:20-29) -----------------------
+def _norm_factor(norm: str, n: int, forward: bool) -> float:
+    # extra/python/src/main.cpp:150-162
+    if norm == "backward":
+        return 1.0 if forward else 1.0 / n
+    if norm == "ortho":
+        return 1.0 / np.sqrt(n)
+    if norm == "forward":
+        return 1.0 / n if forward else 1.0
+    raise RuntimeError(f"unsupported norm '{norm}'")
+
+
+def _c2c(x, n, norm, direction):
+    x = np.asarray(x)
+    if x.dtype not in (np.complex64, np.complex128):
+        x = x.astype(np.complex128 if x.dtype == np.float64 else np.complex64)
+    n = x.shape[-1] if n is None else n
+    if n & (n - 1) != 0 or n == 0:
+        raise RuntimeError("only power-of-two sizes are supported")  # main.cpp:137-139
+    if x.shape[-1] != n:
+        buf = np.zeros(x.shape[:-1] + (n,), dtype=x.dtype)
+        m = min(n, x.shape[-1])
+        buf[..., :m] = x[..., :m]
+        x = buf
+    else:
+        x = np.ascontiguousarray(x).copy()
+    plan = FFTPlan(n.bit_length() - 1, x.dtype)
+    plan(x, direction)
+    plan.close()
+    scale = _norm_factor(norm, n, direction == FORWARD)
+    return x if scale == 1.0 else (x * x.real.dtype.type(scale)).astype(x.dtype)
+
+
+def fft(x, n=None, norm="backward"):
+    return _c2c(x, n, norm, FORWARD)
+
+
+def ifft(x, n=None, norm="backward"):
+    return _c2c(x, n, norm, BACKWARD)
+
+
+def rfft(x):
+    x = np.ascontiguousarray(x)
+    plan = RFFTPlan(int(x.shape[-1]).bit_length() - 1, x.dtype)
+    out = plan.rfft(x)
+    plan.close()
+    return out
+
+
+def irfft(x, n: int):
+    x = np.ascontiguousarray(x)
+    plan = RFFTPlan(int(n).bit_length() - 1, _REAL_OF[str(x.dtype)])
+    out = plan.irfft(x)
+    plan.close()
+    return out
+
+
+def convolve(in1, in2, mode: str = "full", method: str = "upols", block: int | None = None):
+    """neo.convolve (extra/python/src/main.cpp:171-198): full linear convolution of two 1-D signals. The reference binds
+    method="direct"/"fft"; the partitioned methods of convolution/method.hpp:8-17 ("upols", "upola") are what runs here."""
+    if mode != "full":
+        raise RuntimeError(f"unsupported mode '{mode}'")  # main.cpp:197, asserted by extra/python/test/test.py:36-40
+    if method not in ("upols", "upola", "ols", "ola", "fft", "auto"):
+        raise RuntimeError(f"unsupported method '{method}'")
+    sig = np.ascontiguousarray(in1, dtype=np.float32)
+    ir = np.ascontiguousarray(in2, dtype=np.float32)
+    if sig.ndim != 1 or ir.ndim != 1:
+        raise RuntimeError("unsupported ndim")  # main.cpp:126
+    if sig.size == 0 or ir.size == 0:
+        return np.zeros(0, dtype=np.float32)
+    if block is None:
+        block = max(2, min(4096, 1 << max(1, (ir.size - 1).bit_length())))
+    total = sig.size + ir.size - 1
+    taps = max(ir.size, block)
+    ir_p = np.zeros((1, taps), dtype=np.float32)
+    ir_p[0, : ir.size] = ir
+    blocks = -(-total // block)
+    x = np.zeros((1, blocks * block), dtype=np.float32)
+    x[0, : sig.size] = sig
+    conv = Convolver(UPOLA if method in ("upola", "ola") else UPOLS, "float32", DIAGONAL, max_blocks=min(blocks, 64))
+    conv.impulse(ir_p, block)
+    step = conv.max_blocks * block
+    for s in range(0, x.shape[1], step):
+        chunk = np.ascontiguousarray(x[:, s : s + step])
+        conv(chunk)
+        x[:, s : s + step] = chunk
+    conv.close()
+    return x[0, :total].copy()

@@ -1,0 +1,639 @@
+// conv.cu -- C ABI of the partitioned convolver bank, uniform_partition and the index tables (include/neo_b200.h).
+// Drop-in for neo::convolution::upols_convolver / upola_convolver
+// (src/neo/convolution/uniform_partitioned_convolver.hpp:14-65, dense_convolver.hpp:20-25) and
+// neo::convolution::uniform_partition (uniform_partition.hpp:13-26).
+#include "conv_kernels.cuh"
+
+#include <algorithm>
+#include <memory>
+
+namespace neo_b200 {
+
+__global__ void fdl_index_kernel(unsigned parts, unsigned calls, unsigned* write_pos, unsigned* pairs)
+{
+    // one thread per (call, segment): the ring position advances by one per call (fdl_index.hpp:33-35)
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= size_t(parts) * calls) { return; }
+    unsigned const call    = unsigned(i / parts);
+    unsigned const segment = unsigned(i - size_t(call) * parts);
+    unsigned const wp      = call % parts;
+    if (segment == 0) { write_pos[call] = wp; }
+    pairs[2 * i + 0] = segment;
+    pairs[2 * i + 1] = fdl_filter_index(wp, segment, parts);
+}
+
+__global__ void bitrev_table_kernel(unsigned order, unsigned* out)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= (size_t(1) << order)) { return; }
+    out[i] = order == 0 ? 0U : (__brev(unsigned(i)) >> (32U - order));
+}
+
+// digitrevorder_plan<R>::make (fft/reference/digitrevorder.hpp:27-45) walks a carry chain; entry i is the base-R digit
+// reversal of i for i < size-1 and 0 for the last entry. Applying the plan to iota (swap when i < lut[i]) yields the
+// permutation below: perm[i] = digitrev(i), and position size-1 stays in place because its lut entry is 0.
+__global__ void digitrev_perm_kernel(unsigned radix, unsigned digits, unsigned size, unsigned* out)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= size) { return; }
+    unsigned v = unsigned(i), r = 0;
+    for (unsigned d = 0; d < digits; ++d) {
+        r = r * radix + v % radix;
+        v /= radix;
+    }
+    out[i] = r;
+}
+
+namespace {
+
+template<typename T>
+struct conv_engine
+{
+    neo_b200_conv_config cfg{};
+    int logb{0};
+    int m{0};           // B
+    int parts{0};       // local partitions
+    int ring{0};
+    int sources{1};
+    int splits{1};
+    size_t filters{0};  // outputs * sources
+    size_t write_pos{0};
+    bool has_filter{false};
+    int tail_flip{0};
+
+    fft_tables<T> tables;
+    device_buffer filter, fdl, prev, tail[2], acc, ola_y, stage_in, stage_out, stage_filter;
+
+    size_t device_bytes() const
+    {
+        return filter.bytes + fdl.bytes + prev.bytes + tail[0].bytes + tail[1].bytes + acc.bytes + ola_y.bytes + stage_in.bytes
+             + stage_out.bytes + stage_filter.bytes;
+    }
+
+    int init(neo_b200_conv_config const& c, cudaStream_t stream)
+    {
+        cfg     = c;
+        m       = int(c.block);
+        logb    = int(log2_exact(c.block));
+        parts   = int(c.partition_end - c.partition_begin);
+        ring    = int(c.partition_end + c.max_blocks - 1);
+        sources = c.topology == NEO_B200_MATRIX ? int(c.inputs) : 1;
+        filters = c.outputs * size_t(sources);
+        NEO_TRY(tables.build(logb, true, stream));
+
+        size_t const csz = sizeof(cx<T>);
+        NEO_TRY(filter.reserve(filters * parts * m * csz));
+        NEO_TRY(fdl.reserve(c.inputs * size_t(ring) * m * csz));
+        NEO_TRY(prev.reserve(c.inputs * m * sizeof(T)));
+        if (c.kind == NEO_B200_UPOLA) {
+            NEO_TRY(tail[0].reserve(c.outputs * m * sizeof(T)));
+            NEO_TRY(tail[1].reserve(c.outputs * m * sizeof(T)));
+            NEO_TRY(ola_y.reserve(c.outputs * c.max_blocks * 2 * m * sizeof(T)));
+        }
+        // split the partition loop when (bins x outputs) alone cannot fill the GPU: ~4 CTAs per SM wanted
+        int sms = 148;
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        size_t const ctas_xy = size_t((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads) * c.outputs;
+        size_t const work    = size_t(sources) * parts;
+        size_t want          = (size_t(sms) * 4 + ctas_xy - 1) / ctas_xy;
+        want                 = std::min(want, std::max<size_t>(1, work / 8));
+        splits               = int(std::max<size_t>(1, std::min<size_t>(want, 64)));
+        NEO_TRY(acc.reserve(size_t(splits) * c.outputs * c.max_blocks * m * csz));
+        return clear_state(stream);
+    }
+
+    int clear_state(cudaStream_t stream)
+    {
+        NEO_CUDA_TRY(cudaMemsetAsync(fdl.ptr, 0, fdl.bytes, stream));
+        NEO_CUDA_TRY(cudaMemsetAsync(prev.ptr, 0, prev.bytes, stream));
+        if (tail[0].ptr != nullptr) {
+            NEO_CUDA_TRY(cudaMemsetAsync(tail[0].ptr, 0, tail[0].bytes, stream));
+            NEO_CUDA_TRY(cudaMemsetAsync(tail[1].ptr, 0, tail[1].bytes, stream));
+        }
+        write_pos = 0;
+        tail_flip = 0;
+        return NEO_B200_OK;
+    }
+
+    // H in the reference layout [filters][P][B+1]; device pointer
+    int pack_filter(cx<T> const* h_dev, size_t first_filter, size_t count, size_t src_parts, int part0, cudaStream_t stream)
+    {
+        size_t const rows = count * parts;
+        for (size_t r0 = 0; r0 < rows; r0 += 65535) {  // gridDim.y <= 65535
+            dim3 const grid(unsigned((m + 255) / 256), unsigned(std::min<size_t>(65535, rows - r0)));
+            pack_filter_kernel<T><<<grid, 256, 0, stream>>>(h_dev, filter.template as<cx<T>>() + first_filter * parts * m, src_parts, part0,
+                                                            parts, m, r0);
+            NEO_TRY(check_launch("pack_filter_kernel"));
+        }
+        return NEO_B200_OK;
+    }
+
+    int set_filter(void const* h, int memspace, cudaStream_t stream)
+    {
+        size_t const p_total = cfg.partitions;
+        size_t const k       = size_t(m) + 1;
+        size_t const csz     = sizeof(cx<T>);
+        if (memspace == NEO_B200_DEVICE) {
+            NEO_TRY(pack_filter(static_cast<cx<T> const*>(h), 0, filters, p_total, int(cfg.partition_begin), stream));
+        } else {
+            // stage only this handle's partition range of each filter, a few hundred MB at a time
+            size_t const row_bytes = size_t(parts) * k * csz;
+            size_t const chunk     = std::max<size_t>(1, std::min(filters, (size_t(256) << 20) / row_bytes));
+            NEO_TRY(stage_filter.reserve(chunk * row_bytes));
+            char const* src = static_cast<char const*>(h) + cfg.partition_begin * k * csz;
+            for (size_t f = 0; f < filters; f += chunk) {
+                size_t const n = std::min(chunk, filters - f);
+                NEO_CUDA_TRY(cudaMemcpy2DAsync(stage_filter.ptr, row_bytes, src + f * p_total * k * csz, p_total * k * csz, row_bytes, n,
+                                               cudaMemcpyHostToDevice, stream));
+                NEO_TRY(pack_filter(stage_filter.template as<cx<T>>(), f, n, size_t(parts), 0, stream));
+                NEO_CUDA_TRY(cudaStreamSynchronize(stream));  // staging buffer is reused
+            }
+        }
+        has_filter = true;
+        return clear_state(stream);
+    }
+
+    int partition_into(T const* ir_dev, size_t taps, size_t first_filter, size_t count, cudaStream_t stream)
+    {
+        int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_DISPATCH_LOGM(T, logb, {
+            if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
+                partition_r2c_io<T, LOGM> io{ir_dev, taps, int(cfg.partition_begin), parts,
+                                             filter.template as<cx<T>>() + first_filter * parts * m, 1};
+                status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), count * parts, stream);
+            }
+        });
+        return status;
+    }
+
+    int set_impulse(void const* ir, size_t taps, int memspace, cudaStream_t stream)
+    {
+        if (memspace == NEO_B200_DEVICE) {
+            NEO_TRY(partition_into(static_cast<T const*>(ir), taps, 0, filters, stream));
+        } else {
+            size_t const row_bytes = taps * sizeof(T);
+            size_t const chunk     = std::max<size_t>(1, std::min(filters, (size_t(256) << 20) / row_bytes));
+            NEO_TRY(stage_filter.reserve(chunk * row_bytes));
+            for (size_t f = 0; f < filters; f += chunk) {
+                size_t const n = std::min(chunk, filters - f);
+                NEO_CUDA_TRY(cudaMemcpyAsync(stage_filter.ptr, static_cast<char const*>(ir) + f * row_bytes, n * row_bytes,
+                                             cudaMemcpyHostToDevice, stream));
+                NEO_TRY(partition_into(stage_filter.template as<T>(), taps, f, n, stream));
+                NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+            }
+        }
+        has_filter = true;
+        return clear_state(stream);
+    }
+
+    // window + r2c + FDL insert + MAC for `blocks` blocks; in is a device pointer [inputs][in_stride]
+    int forward(T const* in, size_t in_stride, size_t blocks, cudaStream_t stream)
+    {
+        int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_DISPATCH_LOGM(T, logb, {
+            if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
+                conv_r2c_io<T, LOGM> io{in, in_stride, prev.template as<T>(), fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
+                                        cfg.kind == NEO_B200_UPOLA ? 1 : 0};
+                status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), cfg.inputs * blocks, stream);
+            }
+        });
+        if (status != NEO_B200_OK) { return status == NEO_B200_ERR_UNSUPPORTED ? fail(status, "block size %d not supported", m) : status; }
+        if (cfg.kind == NEO_B200_UPOLS) {
+            // the last block becomes the left half of the next call's first window (overlap_save.hpp:94-95)
+            NEO_CUDA_TRY(cudaMemcpy2DAsync(prev.ptr, m * sizeof(T), in + (blocks - 1) * m, in_stride * sizeof(T), m * sizeof(T), cfg.inputs,
+                                           cudaMemcpyDeviceToDevice, stream));
+        }
+
+        mac_geom g{};
+        g.m         = m;
+        g.ring      = ring;
+        g.parts     = parts;
+        g.age0      = int(cfg.partition_begin);
+        g.sources   = sources;
+        g.diagonal  = cfg.topology == NEO_B200_DIAGONAL ? 1 : 0;
+        g.blocks    = int(blocks);
+        g.splits    = splits;
+        g.acc_plane = cfg.outputs * blocks * size_t(m);
+
+        size_t tau = 0;
+        while (tau < blocks) {
+            size_t const left = blocks - tau;
+            g.tau0            = int(tau);
+            g.wp              = int((write_pos + tau) % size_t(ring));
+            int const tb      = left >= 16 && sizeof(T) == 4 ? 16 : left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
+            NEO_TRY(launch_mac(tb, g, stream));
+            tau += size_t(tb);
+        }
+        write_pos = (write_pos + blocks) % size_t(ring);
+        return NEO_B200_OK;
+    }
+
+    int launch_mac(int tb, mac_geom const& g, cudaStream_t stream)
+    {
+        auto const* x = fdl.template as<cx<T>>();
+        auto const* h = filter.template as<cx<T>>();
+        auto* a       = acc.template as<cx<T>>();
+        if (tb == 1) {
+            dim3 const grid(unsigned((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads), unsigned(cfg.outputs), unsigned(splits));
+            fdl_mac_stream_kernel<T><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
+            return check_launch("fdl_mac_stream_kernel");
+        }
+        dim3 const grid(unsigned((m + k_mac_threads - 1) / k_mac_threads), unsigned(cfg.outputs), unsigned(splits));
+        switch (tb) {
+            case 2: fdl_mac_toeplitz_kernel<T, 2><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g); break;
+            case 4: fdl_mac_toeplitz_kernel<T, 4><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g); break;
+            case 8: fdl_mac_toeplitz_kernel<T, 8><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g); break;
+            default:
+                if constexpr (sizeof(T) == 4) { fdl_mac_toeplitz_kernel<T, 16><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g); }
+                break;
+        }
+        return check_launch("fdl_mac_toeplitz_kernel");
+    }
+
+    // c2r + scale + overlap handling of spectra [count][blocks][B] (S partial planes `plane` apart) into out [count][out_stride]
+    int inverse(cx<T> const* spectra, size_t plane, int nsplits, T* out, size_t out_stride, size_t first, size_t count, size_t blocks,
+                cudaStream_t stream)
+    {
+        bool const ola = cfg.kind == NEO_B200_UPOLA;
+        T* const dst   = ola ? ola_y.template as<T>() : out;
+        int status     = NEO_B200_ERR_UNSUPPORTED;
+        NEO_DISPATCH_LOGM(T, logb, {
+            if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
+                conv_c2r_io<T, LOGM> io{spectra, plane, nsplits, int(blocks), dst, out_stride, T(1) / T(2 * m), ola ? 1 : 0};
+                status = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
+            }
+        });
+        if (status != NEO_B200_OK) { return status; }
+        if (ola) {
+            dim3 const grid(unsigned((m + 255) / 256), unsigned(blocks), unsigned(count));
+            ola_combine_kernel<T><<<grid, 256, 0, stream>>>(ola_y.template as<T>(), tail[tail_flip].template as<T>(),
+                                                            tail[tail_flip ^ 1].template as<T>(), out, out_stride, m, int(blocks), first);
+            NEO_TRY(check_launch("ola_combine_kernel"));
+        }
+        return NEO_B200_OK;
+    }
+
+    int reduce_planes(size_t blocks, cudaStream_t stream)
+    {
+        if (splits <= 1) { return NEO_B200_OK; }
+        size_t const plane = cfg.outputs * blocks * size_t(m);
+        sum_planes_kernel<T><<<unsigned((plane + 255) / 256), 256, 0, stream>>>(acc.template as<cx<T>>(), plane, splits);
+        return check_launch("sum_planes_kernel");
+    }
+};
+
+int validate(neo_b200_conv_config& c)
+{
+    if (c.kind != NEO_B200_UPOLS && c.kind != NEO_B200_UPOLA) { return fail(NEO_B200_ERR_INVALID, "bad kind %d", c.kind); }
+    if (c.dtype != NEO_B200_F32 && c.dtype != NEO_B200_F64) { return fail(NEO_B200_ERR_INVALID, "bad dtype %d", c.dtype); }
+    if (c.topology != NEO_B200_DIAGONAL && c.topology != NEO_B200_MATRIX) { return fail(NEO_B200_ERR_INVALID, "bad topology %d", c.topology); }
+    if (c.outputs == 0) { return fail(NEO_B200_ERR_INVALID, "outputs must be > 0"); }
+    if (c.topology == NEO_B200_DIAGONAL) {
+        if (c.inputs == 0) { c.inputs = c.outputs; }
+        if (c.inputs != c.outputs) { return fail(NEO_B200_ERR_INVALID, "diagonal topology needs inputs == outputs"); }
+    } else if (c.inputs == 0) {
+        return fail(NEO_B200_ERR_INVALID, "inputs must be > 0");
+    }
+    // overlap_save sizes its rfft as bit_ceil(2B-1) (overlap_save.hpp:53), uniform_partition as 2B (stft.hpp:104):
+    // they agree only for power-of-two B, which is also what every reference test uses
+    if (!is_pow2(c.block) || c.block < 2) { return fail(NEO_B200_ERR_INVALID, "block size must be a power of two >= 2, got %zu", c.block); }
+    if (c.partitions == 0) { return fail(NEO_B200_ERR_INVALID, "partitions must be > 0"); }
+    if (c.max_blocks == 0) { c.max_blocks = 1; }
+    if (c.partition_begin == 0 && c.partition_end == 0) { c.partition_end = c.partitions; }
+    if (c.partition_begin >= c.partition_end || c.partition_end > c.partitions) {
+        return fail(NEO_B200_ERR_INVALID, "bad partition range [%zu, %zu) of %zu", c.partition_begin, c.partition_end, c.partitions);
+    }
+    if (c.partition_end + c.max_blocks > (size_t(1) << 30) || c.outputs > 65535) { return fail(NEO_B200_ERR_INVALID, "configuration too large"); }
+    return NEO_B200_OK;
+}
+
+}  // namespace
+}  // namespace neo_b200
+
+using namespace neo_b200;
+
+struct neo_b200_conv
+{
+    neo_b200_conv_config cfg;
+    int device;
+    stream_ref stream;
+    conv_engine<float> f32;
+    conv_engine<double> f64;
+    bool sharded;
+};
+
+#define NEO_CONV_ENGINE(conv, CALL) ((conv)->cfg.dtype == NEO_B200_F32 ? (conv)->f32.CALL : (conv)->f64.CALL)
+
+extern "C" {
+
+int neo_b200_conv_create(neo_b200_conv** conv, neo_b200_conv_config const* config)
+{
+    if (conv == nullptr || config == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    *conv = nullptr;
+    neo_b200_conv_config c = *config;
+    NEO_TRY(validate(c));
+    size_t const logb = log2_exact(c.block);
+    if (int(logb) > (c.dtype == NEO_B200_F32 ? max_cta_logm<float>() : max_cta_logm<double>())) {
+        return fail(NEO_B200_ERR_UNSUPPORTED, "block size %zu exceeds the single-CTA transform range", c.block);
+    }
+    NEO_TRY(require_device());
+    auto p = std::unique_ptr<neo_b200_conv>(new (std::nothrow) neo_b200_conv{});
+    if (!p) { return fail(NEO_B200_ERR_ALLOC, "out of host memory"); }
+    p->cfg     = c;
+    p->sharded = !(c.partition_begin == 0 && c.partition_end == c.partitions);
+    NEO_CUDA_TRY(cudaGetDevice(&p->device));
+    NEO_TRY(p->stream.create());
+    NEO_TRY(NEO_CONV_ENGINE(p, init(c, p->stream.stream)));
+    NEO_CUDA_TRY(cudaStreamSynchronize(p->stream.stream));
+    *conv = p.release();
+    return NEO_B200_OK;
+}
+
+void neo_b200_conv_destroy(neo_b200_conv* conv)
+{
+    if (conv == nullptr) { return; }
+    cudaStreamSynchronize(conv->stream.stream);
+    delete conv;
+}
+
+int neo_b200_conv_set_filter(neo_b200_conv* conv, void const* H, int memspace)
+{
+    if (conv == nullptr || H == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    NEO_CUDA_TRY(cudaSetDevice(conv->device));
+    NEO_TRY(NEO_CONV_ENGINE(conv, set_filter(H, memspace, conv->stream.stream)));
+    NEO_CUDA_TRY(cudaStreamSynchronize(conv->stream.stream));
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_set_impulse(neo_b200_conv* conv, void const* ir, size_t taps, int memspace)
+{
+    if (conv == nullptr || ir == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    // stft would underflow L-B for L < B (fft/stft.hpp:24); the frame count must match the configured partitions
+    if (taps < conv->cfg.block) { return fail(NEO_B200_ERR_INVALID, "impulse response shorter than one block"); }
+    if (neo_b200_num_partitions(taps, conv->cfg.block) != conv->cfg.partitions) {
+        return fail(NEO_B200_ERR_INVALID, "taps=%zu gives %zu partitions, handle was created for %zu", taps,
+                    neo_b200_num_partitions(taps, conv->cfg.block), conv->cfg.partitions);
+    }
+    NEO_CUDA_TRY(cudaSetDevice(conv->device));
+    NEO_TRY(NEO_CONV_ENGINE(conv, set_impulse(ir, taps, memspace, conv->stream.stream)));
+    NEO_CUDA_TRY(cudaStreamSynchronize(conv->stream.stream));
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_reset(neo_b200_conv* conv)
+{
+    if (conv == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    NEO_CUDA_TRY(cudaSetDevice(conv->device));
+    return NEO_CONV_ENGINE(conv, clear_state(conv->stream.stream));
+}
+
+extern "C++" template<typename T>
+int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, void* out, size_t blocks, int memspace)
+{
+    cudaStream_t const s = conv->stream.stream;
+    size_t const stride  = blocks * e.m;
+    T const* din         = static_cast<T const*>(in);
+    T* dout              = static_cast<T*>(out);
+    if (memspace == NEO_B200_HOST) {
+        NEO_TRY(e.stage_in.reserve(conv->cfg.inputs * stride * sizeof(T)));
+        NEO_TRY(e.stage_out.reserve(conv->cfg.outputs * stride * sizeof(T)));
+        NEO_CUDA_TRY(cudaMemcpyAsync(e.stage_in.ptr, in, conv->cfg.inputs * stride * sizeof(T), cudaMemcpyHostToDevice, s));
+        din  = e.stage_in.template as<T>();
+        dout = e.stage_out.template as<T>();
+    }
+    NEO_TRY(e.forward(din, stride, blocks, s));
+    NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), conv->cfg.outputs * blocks * size_t(e.m), e.splits, dout, stride, 0, conv->cfg.outputs,
+                      blocks, s));
+    if (conv->cfg.kind == NEO_B200_UPOLA) { e.tail_flip ^= 1; }
+    if (memspace == NEO_B200_HOST) {
+        NEO_CUDA_TRY(cudaMemcpyAsync(out, dout, conv->cfg.outputs * stride * sizeof(T), cudaMemcpyDeviceToHost, s));
+        NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return NEO_B200_OK;
+}
+
+static int conv_check_call(neo_b200_conv* conv, size_t blocks)
+{
+    if (conv == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    bool const ready = conv->cfg.dtype == NEO_B200_F32 ? conv->f32.has_filter : conv->f64.has_filter;
+    if (!ready) { return fail(NEO_B200_ERR_INVALID, "no filter set"); }
+    if (blocks == 0 || blocks > conv->cfg.max_blocks) {
+        return fail(NEO_B200_ERR_INVALID, "blocks=%zu outside [1, max_blocks=%zu]", blocks, conv->cfg.max_blocks);
+    }
+    NEO_CUDA_TRY(cudaSetDevice(conv->device));
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_process(neo_b200_conv* conv, void const* in, void* out, size_t blocks, int memspace)
+{
+    NEO_TRY(conv_check_call(conv, blocks));
+    if (in == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null buffer"); }
+    if (conv->sharded) { return fail(NEO_B200_ERR_INVALID, "partition-sharded handle: use conv_forward / conv_inverse around the reduction"); }
+    if (in == out && conv->cfg.topology != NEO_B200_DIAGONAL) { return fail(NEO_B200_ERR_INVALID, "in-place needs the diagonal topology"); }
+    if (conv->cfg.dtype == NEO_B200_F32) { return conv_process_impl<float>(conv, conv->f32, in, out, blocks, memspace); }
+    return conv_process_impl<double>(conv, conv->f64, in, out, blocks, memspace);
+}
+
+extern "C++" template<typename T>
+int conv_forward_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, size_t blocks, int memspace)
+{
+    cudaStream_t const s = conv->stream.stream;
+    size_t const stride  = blocks * e.m;
+    T const* din         = static_cast<T const*>(in);
+    if (memspace == NEO_B200_HOST) {
+        NEO_TRY(e.stage_in.reserve(conv->cfg.inputs * stride * sizeof(T)));
+        NEO_CUDA_TRY(cudaMemcpyAsync(e.stage_in.ptr, in, conv->cfg.inputs * stride * sizeof(T), cudaMemcpyHostToDevice, s));
+        din = e.stage_in.template as<T>();
+    }
+    NEO_TRY(e.forward(din, stride, blocks, s));
+    return e.reduce_planes(blocks, s);
+}
+
+int neo_b200_conv_forward(neo_b200_conv* conv, void const* in, size_t blocks, int memspace)
+{
+    NEO_TRY(conv_check_call(conv, blocks));
+    if (in == nullptr) { return fail(NEO_B200_ERR_INVALID, "null buffer"); }
+    if (conv->cfg.dtype == NEO_B200_F32) { return conv_forward_impl<float>(conv, conv->f32, in, blocks, memspace); }
+    return conv_forward_impl<double>(conv, conv->f64, in, blocks, memspace);
+}
+
+int neo_b200_conv_spectra(neo_b200_conv* conv, void** device_ptr, size_t* bytes_per_output_block)
+{
+    if (conv == nullptr || device_ptr == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    *device_ptr = conv->cfg.dtype == NEO_B200_F32 ? conv->f32.acc.ptr : conv->f64.acc.ptr;
+    if (bytes_per_output_block != nullptr) { *bytes_per_output_block = conv->cfg.block * 2 * elem_size(conv->cfg.dtype); }
+    return NEO_B200_OK;
+}
+
+extern "C++" template<typename T>
+int conv_inverse_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* spectra, void* out, size_t first, size_t count,
+                             size_t blocks, int memspace)
+{
+    cudaStream_t const s = conv->stream.stream;
+    size_t const stride  = blocks * e.m;
+    T* dout              = static_cast<T*>(out);
+    if (memspace == NEO_B200_HOST) {
+        NEO_TRY(e.stage_out.reserve(count * stride * sizeof(T)));
+        dout = e.stage_out.template as<T>();
+    }
+    NEO_TRY(e.inverse(static_cast<cx<T> const*>(spectra), 0, 1, dout, stride, first, count, blocks, s));
+    if (conv->cfg.kind == NEO_B200_UPOLA) { e.tail_flip ^= 1; }
+    if (memspace == NEO_B200_HOST) {
+        NEO_CUDA_TRY(cudaMemcpyAsync(out, dout, count * stride * sizeof(T), cudaMemcpyDeviceToHost, s));
+        NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_inverse(neo_b200_conv* conv, void const* spectra_device, void* out, size_t first, size_t count, size_t blocks, int memspace)
+{
+    NEO_TRY(conv_check_call(conv, blocks));
+    if (spectra_device == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null buffer"); }
+    if (first + count > conv->cfg.outputs) { return fail(NEO_B200_ERR_INVALID, "output range [%zu, %zu) outside the bank", first, first + count); }
+    if (count == 0) { return NEO_B200_OK; }
+    if (conv->cfg.dtype == NEO_B200_F32) { return conv_inverse_impl<float>(conv, conv->f32, spectra_device, out, first, count, blocks, memspace); }
+    return conv_inverse_impl<double>(conv, conv->f64, spectra_device, out, first, count, blocks, memspace);
+}
+
+int neo_b200_conv_set_stream(neo_b200_conv* conv, void* cuda_stream)
+{
+    if (conv == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    conv->stream.adopt(cuda_stream);
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_synchronize(neo_b200_conv* conv)
+{
+    if (conv == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    NEO_CUDA_TRY(cudaStreamSynchronize(conv->stream.stream));
+    return NEO_B200_OK;
+}
+
+size_t neo_b200_conv_device_bytes(neo_b200_conv const* conv)
+{
+    if (conv == nullptr) { return 0; }
+    return conv->cfg.dtype == NEO_B200_F32 ? conv->f32.device_bytes() : conv->f64.device_bytes();
+}
+
+// ---- filter preparation -------------------------------------------------------------------------------------------------------
+size_t neo_b200_num_partitions(size_t taps, size_t block)
+{
+    // num_sftf_frames(signal, frame, overlap=0) = idiv(signal - frame, frame) + 1 (fft/stft.hpp:21-25, math/idiv.hpp:11-14)
+    if (block == 0 || taps < block) { return 0; }
+    return (taps - block + block - 1) / block + 1;
+}
+
+extern "C++" template<typename T>
+int uniform_partition_impl(void const* ir, size_t channels, size_t taps, size_t block, void* out, int memspace)
+{
+    int const logb = int(log2_exact(block));
+    if (logb > max_cta_logm<T>()) { return fail(NEO_B200_ERR_UNSUPPORTED, "block size %zu exceeds the single-CTA transform range", block); }
+    size_t const parts = neo_b200_num_partitions(taps, block);
+    stream_ref stream;
+    NEO_TRY(stream.create());
+    cudaStream_t const s = stream.stream;
+    fft_tables<T> tables;
+    NEO_TRY(tables.build(logb, true, s));
+    device_buffer d_in, d_out;
+    T const* src  = static_cast<T const*>(ir);
+    cx<T>* dst    = static_cast<cx<T>*>(out);
+    size_t const out_row = parts * (block + 1) * sizeof(cx<T>);
+    size_t chunk         = channels;
+    if (memspace == NEO_B200_HOST) {
+        chunk = std::max<size_t>(1, std::min(channels, (size_t(256) << 20) / out_row));
+        NEO_TRY(d_in.reserve(chunk * taps * sizeof(T)));
+        NEO_TRY(d_out.reserve(chunk * out_row));
+    }
+    for (size_t c = 0; c < channels; c += chunk) {
+        size_t const n = std::min(chunk, channels - c);
+        T const* in_dev = src + c * taps;
+        cx<T>* out_dev  = dst + c * parts * (block + 1);
+        if (memspace == NEO_B200_HOST) {
+            NEO_CUDA_TRY(cudaMemcpyAsync(d_in.ptr, src + c * taps, n * taps * sizeof(T), cudaMemcpyHostToDevice, s));
+            in_dev  = d_in.template as<T>();
+            out_dev = d_out.template as<cx<T>>();
+        }
+        int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_DISPATCH_LOGM(T, logb, {
+            if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
+                partition_r2c_io<T, LOGM> io{in_dev, taps, 0, int(parts), out_dev, 0};
+                status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), n * parts, s);
+            }
+        });
+        if (status != NEO_B200_OK) { return status; }
+        if (memspace == NEO_B200_HOST) {
+            NEO_CUDA_TRY(cudaMemcpyAsync(reinterpret_cast<char*>(dst) + c * out_row, d_out.ptr, n * out_row, cudaMemcpyDeviceToHost, s));
+        }
+        NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return NEO_B200_OK;
+}
+
+int neo_b200_uniform_partition(void const* ir, size_t channels, size_t taps, size_t block, void* out, int dtype, int memspace)
+{
+    if (ir == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (!is_pow2(block) || block < 2) { return fail(NEO_B200_ERR_INVALID, "block size must be a power of two >= 2"); }
+    if (taps < block) { return fail(NEO_B200_ERR_INVALID, "impulse response shorter than one block"); }
+    if (channels == 0) { return NEO_B200_OK; }
+    NEO_TRY(require_device());
+    if (dtype == NEO_B200_F32) { return uniform_partition_impl<float>(ir, channels, taps, block, out, memspace); }
+    if (dtype == NEO_B200_F64) { return uniform_partition_impl<double>(ir, channels, taps, block, out, memspace); }
+    return fail(NEO_B200_ERR_INVALID, "bad dtype %d", dtype);
+}
+
+// ---- index tables -----------------------------------------------------------------------------------------------------------------
+static int table_to_host(device_buffer& buf, uint32_t* out, size_t count)
+{
+    NEO_CUDA_TRY(cudaMemcpy(out, buf.ptr, count * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return NEO_B200_OK;
+}
+
+int neo_b200_bitrev_table(size_t order, uint32_t* out)
+{
+    if (out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (order > 30) { return fail(NEO_B200_ERR_UNSUPPORTED, "order %zu too large", order); }
+    NEO_TRY(require_device());
+    size_t const n = size_t(1) << order;
+    device_buffer buf;
+    NEO_TRY(buf.reserve(n * sizeof(uint32_t)));
+    bitrev_table_kernel<<<unsigned((n + 255) / 256), 256>>>(unsigned(order), buf.as<unsigned>());
+    NEO_TRY(check_launch("bitrev_table_kernel"));
+    return table_to_host(buf, out, n);
+}
+
+int neo_b200_digitrev_perm(size_t radix, size_t size, uint32_t* out)
+{
+    if (out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (radix < 2 || size == 0) { return fail(NEO_B200_ERR_INVALID, "bad radix/size"); }
+    size_t digits = 0, pow = 1;
+    while (pow < size) {
+        pow *= radix;
+        ++digits;
+    }
+    if (pow != size) { return fail(NEO_B200_ERR_INVALID, "size %zu is not a power of radix %zu", size, radix); }
+    NEO_TRY(require_device());
+    device_buffer buf;
+    NEO_TRY(buf.reserve(size * sizeof(uint32_t)));
+    digitrev_perm_kernel<<<unsigned((size + 255) / 256), 256>>>(unsigned(radix), unsigned(digits), unsigned(size), buf.as<unsigned>());
+    NEO_TRY(check_launch("digitrev_perm_kernel"));
+    return table_to_host(buf, out, size);
+}
+
+int neo_b200_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, uint32_t* pairs)
+{
+    if (write_pos == nullptr || pairs == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (parts == 0 || calls == 0) { return NEO_B200_OK; }
+    NEO_TRY(require_device());
+    device_buffer wp, pr;
+    NEO_TRY(wp.reserve(calls * sizeof(uint32_t)));
+    NEO_TRY(pr.reserve(parts * calls * 2 * sizeof(uint32_t)));
+    size_t const n = parts * calls;
+    fdl_index_kernel<<<unsigned((n + 255) / 256), 256>>>(unsigned(parts), unsigned(calls), wp.as<unsigned>(), pr.as<unsigned>());
+    NEO_TRY(check_launch("fdl_index_kernel"));
+    NEO_TRY(table_to_host(wp, write_pos, calls));
+    return table_to_host(pr, pairs, n * 2);
+}
+
+}  // extern "C"

@@ -1,0 +1,418 @@
+// conv_kernels.cuh -- device side of the uniformly partitioned convolver bank.
+//
+// Reference per block and channel (src/neo/convolution/uniform_partitioned_convolver.hpp:48-65, overlap_save.hpp:85-112):
+//   slide window, rfft(2B), FDL insert, clear accumulator, P x multiply_add(fdl[s], H[(w+P-s)%P]), irfft, scale, keep last B.
+// Here, per call of T blocks over a bank of channels, three kernels:
+//   r2c_kernel<conv_r2c_io>   window assembly + r2c + FDL insert fused        (K3, K5, K6 of SURVEY 2a)
+//   fdl_mac_*                 the spectral multiply-accumulate                 (K7, K8)
+//   c2r_kernel<conv_c2r_io>   partial-sum gather + c2r + 1/N scale + discard   (K4, K9, K10)
+//
+// HBM layout (all complex rows are B = N/2 elements: bin 0 carries (Re X[0], Re X[B]) because both are real):
+//   fdl    [inputs][R][B]             ring of spectra, R = partition_end + max_blocks - 1 slots, slot(n) = n mod R
+//   filter [outputs*sources][Pl][B]   Pl local partitions, sources = 1 (diagonal) or inputs (matrix)
+//   acc    [S][outputs][T][B]         S partial planes (split over partitions so small banks still fill the GPU)
+#pragma once
+
+#include "fft_kernels.cuh"
+
+namespace neo_b200 {
+
+// fdl_index (src/neo/convolution/fdl_index.hpp:28-31): the filter row paired with FDL row `segment` when the newest
+// spectrum sits in row `write_pos` of a P-row ring. The MAC kernels pair rows by age = (write_pos - segment) mod P,
+// which is this value; neo_b200_fdl_index_sequence evaluates the same function on the device.
+__host__ __device__ __forceinline__ unsigned fdl_filter_index(unsigned write_pos, unsigned segment, unsigned parts)
+{
+    return (write_pos + parts - segment) % parts;
+}
+
+struct mac_geom
+{
+    int m;             // complex elements per row (= B)
+    int ring;          // R
+    int parts;         // Pl, partitions held by this handle
+    int age0;          // age of the first local partition (= partition_begin)
+    int sources;       // FDL channels summed per output
+    int diagonal;      // 1: source channel = output channel
+    int wp;            // ring slot of the first block of this launch
+    int blocks;        // T of the whole call (row stride of acc)
+    int tau0;          // first block of this launch inside the call
+    int splits;        // S
+    size_t acc_plane;  // elements per partial plane
+};
+
+// ---- T = 1: pure stream. Every filter and FDL element is used exactly once -> HBM roofline. -------------------------------
+// thread = VEC adjacent bins (16 bytes), 8 rows in flight per thread.
+template<typename T>
+struct mac_vec;
+template<>
+struct mac_vec<float>
+{
+    using type               = float4;
+    static constexpr int VEC = 2;
+    static __device__ __forceinline__ void cfma(float4& a, float4 const x, float4 const h)
+    {
+        a.x = fmaf(x.x, h.x, a.x);
+        a.x = fmaf(-x.y, h.y, a.x);
+        a.y = fmaf(x.x, h.y, a.y);
+        a.y = fmaf(x.y, h.x, a.y);
+        a.z = fmaf(x.z, h.z, a.z);
+        a.z = fmaf(-x.w, h.w, a.z);
+        a.w = fmaf(x.z, h.w, a.w);
+        a.w = fmaf(x.w, h.z, a.w);
+    }
+    // packed bin 0 = (Re X0, Re XB): two independent real products
+    static __device__ __forceinline__ void cfma_edge(float4& a, float4 const x, float4 const h)
+    {
+        a.x = fmaf(x.x, h.x, a.x);
+        a.y = fmaf(x.y, h.y, a.y);
+        a.z = fmaf(x.z, h.z, a.z);
+        a.z = fmaf(-x.w, h.w, a.z);
+        a.w = fmaf(x.z, h.w, a.w);
+        a.w = fmaf(x.w, h.z, a.w);
+    }
+    static __device__ __forceinline__ float4 zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template<>
+struct mac_vec<double>
+{
+    using type               = double2;
+    static constexpr int VEC = 1;
+    static __device__ __forceinline__ void cfma(double2& a, double2 const x, double2 const h)
+    {
+        a.x = ::fma(x.x, h.x, a.x);
+        a.x = ::fma(-x.y, h.y, a.x);
+        a.y = ::fma(x.x, h.y, a.y);
+        a.y = ::fma(x.y, h.x, a.y);
+    }
+    static __device__ __forceinline__ void cfma_edge(double2& a, double2 const x, double2 const h)
+    {
+        a.x = ::fma(x.x, h.x, a.x);
+        a.y = ::fma(x.y, h.y, a.y);
+    }
+    static __device__ __forceinline__ double2 zero() { return make_double2(0.0, 0.0); }
+};
+
+template<typename V>
+__device__ __forceinline__ V ld_stream(V const* p)
+{
+    return __ldcs(p);  // read-once data: evict-first
+}
+
+constexpr int k_mac_threads = 128;
+constexpr int k_mac_unroll  = 8;
+
+template<typename T>
+__global__ void __launch_bounds__(k_mac_threads)
+    fdl_mac_stream_kernel(cx<T> const* __restrict__ fdl, cx<T> const* __restrict__ filter, cx<T>* __restrict__ acc, mac_geom g)
+{
+    using MV          = mac_vec<T>;
+    using V           = typename MV::type;
+    int const col     = blockIdx.x * k_mac_threads + threadIdx.x;  // in units of V
+    int const out     = blockIdx.y;
+    int const split   = blockIdx.z;
+    int const row_vec = g.m / MV::VEC;
+    if (col >= row_vec) { return; }
+
+    int const total = g.sources * g.parts;  // virtual partitions of this output
+    int const v0    = int((long long)total * split / g.splits);
+    int const v1    = int((long long)total * (split + 1) / g.splits);
+
+    V a = MV::zero();
+    bool const edge = (col == 0);  // this thread owns the packed bin 0
+
+    V const* const frow = reinterpret_cast<V const*>(filter) + size_t(out) * g.sources * g.parts * row_vec + col;
+    V const* const xrow = reinterpret_cast<V const*>(fdl) + col;
+
+    for (int v = v0; v < v1; v += k_mac_unroll) {
+        V x[k_mac_unroll], h[k_mac_unroll];
+#pragma unroll
+        for (int u = 0; u < k_mac_unroll; ++u) {
+            int const vp = v + u;
+            if (vp < v1) {
+                int const src = vp / g.parts;
+                int const p   = vp - src * g.parts;
+                int slot      = g.wp - g.age0 - p;
+                slot          = slot % g.ring;
+                slot += slot < 0 ? g.ring : 0;
+                int const ch = g.diagonal ? out : src;
+                h[u]         = ld_stream(frow + size_t(vp) * row_vec);
+                x[u]         = ld_stream(xrow + (size_t(ch) * g.ring + slot) * row_vec);
+            } else {
+                h[u] = MV::zero();
+                x[u] = MV::zero();
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < k_mac_unroll; ++u) {
+            if (edge) { MV::cfma_edge(a, x[u], h[u]); }
+            else { MV::cfma(a, x[u], h[u]); }
+        }
+    }
+    reinterpret_cast<V*>(acc)[size_t(split) * (g.acc_plane / MV::VEC) + (size_t(out) * g.blocks + g.tau0) * row_vec + col] = a;
+}
+
+// ---- T = TB > 1: Toeplitz form. acc[tau] += H[p] * X(tau - age0 - p); each H[p] is reused TB times from registers and
+// each spectrum up to TB times, so bytes per block drop ~TB-fold until FP32 FMA throughput binds. thread = one bin. ------------
+template<typename T, int TB>
+__global__ void __launch_bounds__(k_mac_threads)
+    fdl_mac_toeplitz_kernel(cx<T> const* __restrict__ fdl, cx<T> const* __restrict__ filter, cx<T>* __restrict__ acc, mac_geom g)
+{
+    using C         = cx<T>;
+    int const k     = blockIdx.x * k_mac_threads + threadIdx.x;
+    int const out   = blockIdx.y;
+    int const split = blockIdx.z;
+    if (k >= g.m) { return; }
+    bool const edge = (k == 0);
+
+    int const chunks_per_src = (g.parts + TB - 1) / TB;
+    int const total          = g.sources * chunks_per_src;
+    int const c0             = int((long long)total * split / g.splits);
+    int const c1             = int((long long)total * (split + 1) / g.splits);
+
+    C a[TB];
+#pragma unroll
+    for (int i = 0; i < TB; ++i) { a[i] = mk<T>(0, 0); }
+
+    C win[2 * TB - 1];
+    int prev_src = -1;
+    int slot_lo  = 0;  // ring slot of win[0]
+    size_t xbase = 0;
+
+    for (int c = c0; c < c1; ++c) {
+        int const src = c / chunks_per_src;
+        int const p0  = (c - src * chunks_per_src) * TB;
+        if (src != prev_src) {
+            // fresh window: pretend a previous chunk at p0 - TB left its lower TB-1 entries behind
+            int const ch = g.diagonal ? out : src;
+            xbase        = size_t(ch) * g.ring * g.m + k;
+            int base     = g.wp - g.age0 - p0 + 1;  // d of win[0] of that virtual previous chunk: -(age0 + p0 - TB) - (TB-1)
+            base         = base % g.ring;
+            base += base < 0 ? g.ring : 0;
+            slot_lo = base;
+            int s   = base;
+#pragma unroll
+            for (int i = 0; i < TB - 1; ++i) {
+                win[i] = fdl[xbase + size_t(s) * g.m];
+                s      = (s + 1 == g.ring) ? 0 : s + 1;
+            }
+            prev_src = src;
+        }
+        // shift: entries [0, TB-1) become [TB, 2TB-1); then load TB older spectra below them
+#pragma unroll
+        for (int i = TB - 2; i >= 0; --i) { win[i + TB] = win[i]; }
+        slot_lo -= TB;
+        slot_lo += slot_lo < 0 ? g.ring : 0;
+        {
+            int s = slot_lo;
+#pragma unroll
+            for (int i = 0; i < TB; ++i) {
+                win[i] = fdl[xbase + size_t(s) * g.m];
+                s      = (s + 1 == g.ring) ? 0 : s + 1;
+            }
+        }
+        C const* hrow = filter + ((size_t(out) * g.sources + src) * g.parts + p0) * g.m + k;
+#pragma unroll
+        for (int pp = 0; pp < TB; ++pp) {
+            if (p0 + pp < g.parts) {
+                C const h = __ldcs(hrow + size_t(pp) * g.m);
+#pragma unroll
+                for (int tau = 0; tau < TB; ++tau) {
+                    C const x = win[tau - pp + TB - 1];
+                    if (edge) {
+                        a[tau].x = fma(x.x, h.x, a[tau].x);
+                        a[tau].y = fma(x.y, h.y, a[tau].y);
+                    } else {
+                        a[tau].x = fma(x.x, h.x, a[tau].x);
+                        a[tau].x = fma(-x.y, h.y, a[tau].x);
+                        a[tau].y = fma(x.x, h.y, a[tau].y);
+                        a[tau].y = fma(x.y, h.x, a[tau].y);
+                    }
+                }
+            }
+        }
+    }
+    C* dst = acc + size_t(split) * g.acc_plane + (size_t(out) * g.blocks + g.tau0) * g.m + k;
+#pragma unroll
+    for (int tau = 0; tau < TB; ++tau) { dst[size_t(tau) * g.m] = a[tau]; }
+}
+
+// sum the S partial planes into plane 0 (only needed before handing spectra to a collective)
+template<typename T>
+__global__ void __launch_bounds__(256) sum_planes_kernel(cx<T>* acc, size_t plane, int splits)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= plane) { return; }
+    cx<T> s = acc[i];
+    for (int p = 1; p < splits; ++p) { s = cadd(s, acc[size_t(p) * plane + i]); }
+    acc[i] = s;
+}
+
+// ---- forward side: window assembly + r2c + FDL insert ---------------------------------------------------------------------------
+template<typename T, int LOGM>
+struct conv_r2c_io
+{
+    using C = cx<T>;
+    T const* in;       // [inputs][in_stride] reals, block tau at offset tau*B
+    size_t in_stride;  // reals between channels
+    T const* prev;     // [inputs][B] last block of the previous call (overlap-save)
+    C* fdl;
+    int ring, wp, blocks;
+    int overlap_add;   // 0: window = [previous block | block]   1: window = [block | zeros]  (overlap_add.hpp:88-90)
+
+    struct row_state
+    {
+        C const* lo;
+        C const* hi;
+        C* dst;
+    };
+    __device__ __forceinline__ row_state open(size_t b) const
+    {
+        constexpr size_t B = size_t(1) << LOGM;
+        size_t const ch    = b / blocks;
+        int const tau      = int(b - ch * blocks);
+        T const* cur       = in + ch * in_stride + size_t(tau) * B;
+        int slot           = wp + tau;
+        slot -= slot >= ring ? ring : 0;
+        C* dst = fdl + (ch * ring + slot) * B;
+        if (overlap_add) { return {reinterpret_cast<C const*>(cur), nullptr, dst}; }
+        T const* before = tau == 0 ? prev + ch * B : cur - B;
+        return {reinterpret_cast<C const*>(before), reinterpret_cast<C const*>(cur), dst};
+    }
+    __device__ __forceinline__ C load(row_state const& r, int j) const
+    {
+        constexpr int H = (1 << LOGM) / 2;  // complex pairs per block
+        if (j < H) { return r.lo[j]; }
+        return r.hi != nullptr ? r.hi[j - H] : mk<T>(0, 0);
+    }
+    __device__ __forceinline__ void store(row_state const& r, int k, C x) const { r.dst[k] = x; }
+    __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const { r.dst[0] = mk<T>(dc, nyq); }
+};
+
+// ---- inverse side: partial-plane gather + c2r + scale + overlap-save discard -------------------------------------------------
+template<typename T, int LOGM>
+struct conv_c2r_io
+{
+    using C = cx<T>;
+    C const* acc;       // [splits][count][blocks][B], row 0 = first output channel handled
+    size_t acc_plane;
+    int splits, blocks;
+    T* out;             // overlap-save: [count][out_stride] reals;  overlap-add: scratch [count][blocks][2B]
+    size_t out_stride;
+    T scale;            // 1 / (2B)  (overlap_save.hpp:108)
+    int overlap_add;
+
+    struct row_state
+    {
+        C const* src;
+        C* dst;
+    };
+    __device__ __forceinline__ row_state open(size_t b) const
+    {
+        constexpr size_t B = size_t(1) << LOGM;
+        size_t const ch    = b / blocks;
+        size_t const tau   = b - ch * blocks;
+        C const* src       = acc + (ch * blocks + tau) * B;
+        T* dst             = overlap_add ? out + (ch * blocks + tau) * 2 * B : out + ch * out_stride + tau * B;
+        return {src, reinterpret_cast<C*>(dst)};
+    }
+    __device__ __forceinline__ C load(row_state const& r, int k) const
+    {
+        C s = r.src[k];
+        for (int p = 1; p < splits; ++p) { s = cadd(s, r.src[size_t(p) * acc_plane + k]); }
+        return s;
+    }
+    __device__ __forceinline__ C load_edges(row_state const& r) const { return load(r, 0); }
+    __device__ __forceinline__ void store(row_state const& r, int j, C z) const
+    {
+        constexpr int H = (1 << LOGM) / 2;
+        z.x *= scale;
+        z.y *= scale;
+        if (overlap_add) {
+            r.dst[j] = z;  // all 2B samples; combined with the saved tail afterwards
+        } else if (j >= H) {
+            r.dst[j - H] = z;  // keep samples [B, 2B) (overlap_save.hpp:111)
+        }
+    }
+};
+
+// overlap-add epilogue (overlap_add.hpp:103-106): out = y[0..B) + tail, tail' = y[B..2B) of the last block
+template<typename T>
+__global__ void __launch_bounds__(256)
+    ola_combine_kernel(T const* __restrict__ y, T const* __restrict__ tail_in, T* __restrict__ tail_out, T* __restrict__ out,
+                       size_t out_stride, int block, int blocks, size_t first)
+{
+    size_t const ch  = blockIdx.z;
+    int const tau    = blockIdx.y;
+    int const i      = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= block) { return; }
+    T const* yrow  = y + (ch * blocks + tau) * 2 * size_t(block);
+    T const before = tau == 0 ? tail_in[(first + ch) * block + i] : yrow[i - block];  // y[tau-1][B + i]
+    out[ch * out_stride + size_t(tau) * block + i] = yrow[i] + before;
+    if (tau == blocks - 1) { tail_out[(first + ch) * block + i] = yrow[block + i]; }
+}
+
+// ---- filter preparation ----------------------------------------------------------------------------------------------------------
+// uniform_partition (convolution/uniform_partition.hpp:13-26 -> fft/stft.hpp:78-96): frame p of filter f, zero padded to 2B
+template<typename T, int LOGM>
+struct partition_r2c_io
+{
+    using C = cx<T>;
+    T const* ir;         // [filters][taps]
+    size_t taps;
+    int part0, parts;    // partitions [part0, part0 + parts) are produced
+    C* out;
+    int packed;          // 1: convolver layout [f][parts][B] (bin 0 packed), 0: reference layout [f][parts][B+1]
+
+    struct row_state
+    {
+        T const* src;
+        long count;
+        C* dst;
+    };
+    __device__ __forceinline__ row_state open(size_t b) const
+    {
+        constexpr size_t B = size_t(1) << LOGM;
+        size_t const f     = b / parts;
+        size_t const p     = part0 + (b - f * parts);
+        long const left    = long(taps) - long(p * B);
+        long const count   = left < long(B) ? left : long(B);
+        return {ir + f * taps + p * B, count, out + b * (packed ? B : B + 1)};
+    }
+    __device__ __forceinline__ C load(row_state const& r, int j) const
+    {
+        long const i = 2L * j;
+        return mk<T>(i < r.count ? r.src[i] : T(0), i + 1 < r.count ? r.src[i + 1] : T(0));
+    }
+    __device__ __forceinline__ void store(row_state const& r, int k, C x) const { r.dst[k] = x; }
+    __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const
+    {
+        if (packed) {
+            r.dst[0] = mk<T>(dc, nyq);
+        } else {
+            r.dst[0]         = mk<T>(dc, T(0));
+            r.dst[1 << LOGM] = mk<T>(nyq, T(0));
+        }
+    }
+};
+
+// reference layout H[f][P][B+1] -> convolver layout [f][parts][B] for partitions [part0, part0+parts)
+template<typename T>
+__global__ void __launch_bounds__(256)
+    pack_filter_kernel(cx<T> const* __restrict__ h, cx<T>* __restrict__ packed, size_t src_parts, int part0, int parts, int block,
+                       size_t row0)
+{
+    size_t const row = row0 + blockIdx.y;  // f * parts + p
+    int const k      = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= block) { return; }
+    size_t const f   = row / parts;
+    size_t const p   = part0 + (row - f * parts);
+    cx<T> const* src = h + (f * src_parts + p) * (size_t(block) + 1);
+    cx<T> v          = src[k];
+    if (k == 0) { v.y = src[block].x; }
+    packed[row * block + k] = v;
+}
+
+__global__ void fdl_index_kernel(unsigned parts, unsigned calls, unsigned* write_pos, unsigned* pairs);
+__global__ void bitrev_table_kernel(unsigned order, unsigned* out);
+
+}  // namespace neo_b200

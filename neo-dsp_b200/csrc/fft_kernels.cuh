@@ -1,0 +1,342 @@
+// fft_kernels.cuh -- batched single-pass FFT kernels built on cta_fft: one transform (or G small ones) per CTA,
+// one HBM read and one HBM write per datum. The load/store sides are policy objects so the convolver can fuse its
+// window / FDL-insert / overlap-discard steps into the same kernels.
+#pragma once
+
+#include "common.hpp"
+#include "fft_core.cuh"
+
+#include <vector>
+
+namespace neo_b200 {
+
+// largest single-CTA transform (complex points, log2). Above it the four-step path in fft_large.cuh takes over.
+template<typename T>
+constexpr int max_cta_logm()
+{
+    return sizeof(T) == 4 ? 13 : 12;
+}
+
+template<typename T, int LOGM>
+struct fft_cfg
+{
+    using F                      = cta_fft<T, LOGM, -1>;
+    static constexpr int E       = F::E;
+    static constexpr int TN      = F::TN;
+    static constexpr int M       = F::M;
+    static constexpr int G       = TN >= 64 ? 1 : 64 / TN;  // transforms per CTA
+    static constexpr int THREADS = TN * G;
+    static constexpr int TILE    = F::TILE;
+    static constexpr size_t SMEM = size_t(G) * TILE * sizeof(cx<T>);
+};
+
+// ---- twiddle tables (host, computed in double, rounded once) --------------------------------------------------------
+template<typename T>
+std::vector<cx<T>> make_stage_twiddles(int logm)
+{
+    int const loge = pick_loge<T>(logm);
+    std::vector<cx<T>> lut(static_cast<size_t>(fft_twiddle_count(logm, loge)) + 1);
+    if (loge == 0) { return lut; }
+    int const r0 = fft_first_logr(logm, loge);
+    int logns    = r0 > 0 ? r0 : loge;
+    size_t off   = 0;
+    int const r  = 1 << loge;
+    while (logns < logm) {
+        long const ns    = 1L << logns;
+        double const den = static_cast<double>(ns) * r;
+        for (int q = 1; q < r; ++q) {
+            for (long k = 0; k < ns; ++k) {
+                double const a             = -2.0 * 3.14159265358979323846264338327950288 * double(q) * double(k) / den;
+                lut[off + (q - 1) * ns + k] = mk<T>(T(std::cos(a)), T(std::sin(a)));
+            }
+        }
+        off += static_cast<size_t>(r - 1) * ns;
+        logns += loge;
+    }
+    return lut;
+}
+
+// W[k] = exp(-2 pi i k / (2M)), k < M: the real<->complex split twiddles
+template<typename T>
+std::vector<cx<T>> make_split_twiddles(int logm)
+{
+    size_t const m = size_t(1) << logm;
+    std::vector<cx<T>> lut(m);
+    for (size_t k = 0; k < m; ++k) {
+        double const a = -3.14159265358979323846264338327950288 * double(k) / double(m);
+        lut[k]         = mk<T>(T(std::cos(a)), T(std::sin(a)));
+    }
+    return lut;
+}
+
+// ---- c2c -------------------------------------------------------------------------------------------------------------
+template<typename T, int LOGM, int DIR>
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
+    c2c_kernel(cx<T> const* __restrict__ in, cx<T>* __restrict__ out, cx<T> const* __restrict__ tw, size_t batch)
+{
+    using cfg = fft_cfg<T, LOGM>;
+    using F   = cta_fft<T, LOGM, DIR>;
+    using C   = cx<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* sm = reinterpret_cast<C*>(smem_raw);
+
+    int const g     = threadIdx.x / cfg::TN;
+    int const t     = threadIdx.x % cfg::TN;
+    size_t const b  = size_t(blockIdx.x) * cfg::G + g;
+    bool const live = b < batch;
+
+    C v[cfg::E];
+    C const* src = in + b * cfg::M;
+#pragma unroll
+    for (int e = 0; e < cfg::E; ++e) { v[e] = live ? src[t + e * cfg::TN] : mk<T>(0, 0); }
+
+    F::run(v, sm + g * cfg::TILE, tw, t);
+
+    if (live) {
+        C* dst = out + b * cfg::M;
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) { dst[t + e * cfg::TN] = v[e]; }
+    }
+}
+
+// ---- r2c: IO policy provides load(b, j) -> z[j] and the spectrum stores ------------------------------------------------
+template<typename T, int LOGM, class IO>
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
+    r2c_kernel(IO io, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ rtw, size_t batch)
+{
+    using cfg = fft_cfg<T, LOGM>;
+    using F   = cta_fft<T, LOGM, -1>;
+    using C   = cx<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* sm = reinterpret_cast<C*>(smem_raw) + (threadIdx.x / cfg::TN) * cfg::TILE;
+
+    int const g     = threadIdx.x / cfg::TN;
+    int const t     = threadIdx.x % cfg::TN;
+    size_t const b  = size_t(blockIdx.x) * cfg::G + g;
+    bool const live = b < batch;
+
+    C v[cfg::E];
+    typename IO::row_state row = io.open(live ? b : 0);
+#pragma unroll
+    for (int e = 0; e < cfg::E; ++e) { v[e] = live ? io.load(row, t + e * cfg::TN) : mk<T>(0, 0); }
+
+    F::run(v, sm, tw, t);
+
+    if constexpr (LOGM > 0) {
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) { sm[padded<T>(t + e * cfg::TN)] = v[e]; }
+        __syncthreads();
+    }
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) {
+            int const k = t + e * cfg::TN;
+            if (k == 0) {
+                io.store_edges(row, v[e].x + v[e].y, v[e].x - v[e].y);
+            } else {
+                C const zp = sm[padded<T>(cfg::M - k)];
+                io.store(row, k, r2c_post(v[e], zp, __ldg(rtw + k)));
+            }
+        }
+    }
+}
+
+// ---- c2r: IO policy provides the spectrum loads and store(b, j, z[j]) -----------------------------------------------------
+template<typename T, int LOGM, class IO>
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
+    c2r_kernel(IO io, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ rtw, size_t batch)
+{
+    using cfg = fft_cfg<T, LOGM>;
+    using F   = cta_fft<T, LOGM, +1>;
+    using C   = cx<T>;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    C* sm = reinterpret_cast<C*>(smem_raw) + (threadIdx.x / cfg::TN) * cfg::TILE;
+
+    int const g     = threadIdx.x / cfg::TN;
+    int const t     = threadIdx.x % cfg::TN;
+    size_t const b  = size_t(blockIdx.x) * cfg::G + g;
+    bool const live = b < batch;
+
+    C v[cfg::E];
+    typename IO::row_state row = io.open(live ? b : 0);
+#pragma unroll
+    for (int e = 0; e < cfg::E; ++e) {
+        int const k = t + e * cfg::TN;
+        if (!live) {
+            v[e] = mk<T>(0, 0);
+        } else if (k == 0) {
+            v[e] = io.load_edges(row);  // (Re X[0], Re X[M])
+        } else {
+            v[e] = io.load(row, k);
+        }
+    }
+    if constexpr (LOGM > 0) {
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) { sm[padded<T>(t + e * cfg::TN)] = v[e]; }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) {
+            int const k = t + e * cfg::TN;
+            if (k == 0) {
+                v[e] = mk<T>(v[e].x + v[e].y, v[e].x - v[e].y);
+            } else {
+                C const xp = sm[padded<T>(cfg::M - k)];
+                v[e]       = c2r_pre(v[e], xp, __ldg(rtw + k));
+            }
+        }
+        __syncthreads();
+    } else {
+        v[0] = mk<T>(v[0].x + v[0].y, v[0].x - v[0].y);
+    }
+
+    F::run(v, sm, tw, t);
+
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) { io.store(row, t + e * cfg::TN, v[e]); }
+    }
+}
+
+// ---- plain batched IO policies (the rfft plan) ---------------------------------------------------------------------------
+template<typename T, int LOGM>
+struct r2c_plain_io
+{
+    using C = cx<T>;
+    T const* in;  // [batch][2M]
+    C* out;       // [batch][M+1]
+    struct row_state
+    {
+        C const* src;
+        C* dst;
+    };
+    __device__ __forceinline__ row_state open(size_t b) const
+    {
+        return {reinterpret_cast<C const*>(in) + b * (size_t(1) << LOGM), out + b * ((size_t(1) << LOGM) + 1)};
+    }
+    __device__ __forceinline__ C load(row_state const& r, int j) const { return r.src[j]; }
+    __device__ __forceinline__ void store(row_state const& r, int k, C x) const { r.dst[k] = x; }
+    __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const
+    {
+        r.dst[0]         = mk<T>(dc, T(0));
+        r.dst[1 << LOGM] = mk<T>(nyq, T(0));
+    }
+};
+
+template<typename T, int LOGM>
+struct c2r_plain_io
+{
+    using C = cx<T>;
+    C const* in;     // [batch][row_len], first M+1 used
+    T* out;          // [batch][2M]
+    size_t row_len;
+    struct row_state
+    {
+        C const* src;
+        C* dst;
+    };
+    __device__ __forceinline__ row_state open(size_t b) const
+    {
+        return {in + b * row_len, reinterpret_cast<C*>(out) + b * (size_t(1) << LOGM)};
+    }
+    __device__ __forceinline__ C load(row_state const& r, int k) const { return r.src[k]; }
+    __device__ __forceinline__ C load_edges(row_state const& r) const
+    {
+        return mk<T>(r.src[0].x, r.src[1 << LOGM].x);
+    }
+    __device__ __forceinline__ void store(row_state const& r, int j, C z) const { r.dst[j] = z; }
+};
+
+// ---- launch helpers ----------------------------------------------------------------------------------------------------------
+template<typename Kernel>
+int enable_smem(Kernel kernel, size_t bytes)
+{
+    if (bytes > 48 * 1024) {
+        NEO_CUDA_TRY(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
+    }
+    return NEO_B200_OK;
+}
+
+template<typename T, int LOGM, class IO>
+int launch_r2c(IO const& io, cx<T> const* tw, cx<T> const* rtw, size_t batch, cudaStream_t stream)
+{
+    using cfg = fft_cfg<T, LOGM>;
+    if (batch == 0) { return NEO_B200_OK; }
+    auto kernel = r2c_kernel<T, LOGM, IO>;
+    NEO_TRY(enable_smem(kernel, cfg::SMEM));
+    size_t const grid = (batch + cfg::G - 1) / cfg::G;
+    kernel<<<static_cast<unsigned>(grid), cfg::THREADS, cfg::SMEM, stream>>>(io, tw, rtw, batch);
+    return check_launch("r2c_kernel");
+}
+
+template<typename T, int LOGM, class IO>
+int launch_c2r(IO const& io, cx<T> const* tw, cx<T> const* rtw, size_t batch, cudaStream_t stream)
+{
+    using cfg = fft_cfg<T, LOGM>;
+    if (batch == 0) { return NEO_B200_OK; }
+    auto kernel = c2r_kernel<T, LOGM, IO>;
+    NEO_TRY(enable_smem(kernel, cfg::SMEM));
+    size_t const grid = (batch + cfg::G - 1) / cfg::G;
+    kernel<<<static_cast<unsigned>(grid), cfg::THREADS, cfg::SMEM, stream>>>(io, tw, rtw, batch);
+    return check_launch("c2r_kernel");
+}
+
+template<typename T, int LOGM, int DIR>
+int launch_c2c(cx<T> const* in, cx<T>* out, cx<T> const* tw, size_t batch, cudaStream_t stream)
+{
+    using cfg = fft_cfg<T, LOGM>;
+    if (batch == 0) { return NEO_B200_OK; }
+    auto kernel = c2c_kernel<T, LOGM, DIR>;
+    NEO_TRY(enable_smem(kernel, cfg::SMEM));
+    size_t const grid = (batch + cfg::G - 1) / cfg::G;
+    kernel<<<static_cast<unsigned>(grid), cfg::THREADS, cfg::SMEM, stream>>>(in, out, tw, batch);
+    return check_launch("c2c_kernel");
+}
+
+// device-resident twiddle tables of one transform size
+template<typename T>
+struct fft_tables
+{
+    int logm{-1};
+    device_buffer stage;  // cta_fft stage twiddles
+    device_buffer split;  // real<->complex split twiddles (only when requested)
+
+    int build(int logm_, bool with_split, cudaStream_t stream)
+    {
+        logm          = logm_;
+        auto const tw = make_stage_twiddles<T>(logm);
+        NEO_TRY(stage.reserve(tw.size() * sizeof(cx<T>)));
+        NEO_CUDA_TRY(cudaMemcpyAsync(stage.ptr, tw.data(), tw.size() * sizeof(cx<T>), cudaMemcpyHostToDevice, stream));
+        if (with_split) {
+            auto const sp = make_split_twiddles<T>(logm);
+            NEO_TRY(split.reserve(sp.size() * sizeof(cx<T>)));
+            NEO_CUDA_TRY(cudaMemcpyAsync(split.ptr, sp.data(), sp.size() * sizeof(cx<T>), cudaMemcpyHostToDevice, stream));
+        }
+        NEO_CUDA_TRY(cudaStreamSynchronize(stream));  // host vectors die here
+        return NEO_B200_OK;
+    }
+
+    cx<T> const* tw() const { return stage.template as<cx<T>>(); }
+    cx<T> const* rtw() const { return split.template as<cx<T>>(); }
+};
+
+// switch over the compile-time transform size
+#define NEO_DISPATCH_LOGM(T, logm, ...) \
+    switch (logm) { \
+        case 0: { constexpr int LOGM = 0; __VA_ARGS__; } break; \
+        case 1: { constexpr int LOGM = 1; __VA_ARGS__; } break; \
+        case 2: { constexpr int LOGM = 2; __VA_ARGS__; } break; \
+        case 3: { constexpr int LOGM = 3; __VA_ARGS__; } break; \
+        case 4: { constexpr int LOGM = 4; __VA_ARGS__; } break; \
+        case 5: { constexpr int LOGM = 5; __VA_ARGS__; } break; \
+        case 6: { constexpr int LOGM = 6; __VA_ARGS__; } break; \
+        case 7: { constexpr int LOGM = 7; __VA_ARGS__; } break; \
+        case 8: { constexpr int LOGM = 8; __VA_ARGS__; } break; \
+        case 9: { constexpr int LOGM = 9; __VA_ARGS__; } break; \
+        case 10: { constexpr int LOGM = 10; __VA_ARGS__; } break; \
+        case 11: { constexpr int LOGM = 11; __VA_ARGS__; } break; \
+        case 12: { constexpr int LOGM = 12; __VA_ARGS__; } break; \
+        case 13: { constexpr int LOGM = 13; __VA_ARGS__; } break; \
+        default: break; \
+    }
+
+}  // namespace neo_b200

@@ -1,0 +1,263 @@
+"""TEST INFRASTRUCTURE ONLY: ctypes access to the two CPU checkers.
+
+* ``oracle()``  -> liboracle.so       plain-C restatement (oracle/neo_oracle.c), built by ``make -C oracle oracle``
+* ``ref()``     -> _ref/libneo_ref.so  the unmodified reference headers compiled in place (oracle/ref_wrapper.cpp);
+                                       ``None`` when the prebuilt library is absent (it cannot be rebuilt on the GPU box).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import functools
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+ORACLE_SO = os.path.join(_HERE, "liboracle.so")
+REF_SO = os.path.join(_HERE, "_ref", "libneo_ref.so")
+
+_vp, _sz, _i, _u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32
+
+
+def build(force: bool = False) -> None:
+    """(Re)build the checkers. `_ref` only where /root/reference exists."""
+    if force or not os.path.exists(ORACLE_SO) or os.path.getmtime(ORACLE_SO) < max(
+        os.path.getmtime(os.path.join(_HERE, f)) for f in ("neo_oracle.c", "neo_oracle_impl.inc", "neo_oracle.h")
+    ):
+        subprocess.run(["make", "-C", _HERE, "-B", "oracle"], check=True, capture_output=True)
+    if os.path.isdir("/root/reference/src/neo"):
+        stale = (not os.path.exists(REF_SO)) or os.path.getmtime(REF_SO) < os.path.getmtime(
+            os.path.join(_HERE, "ref_wrapper.cpp")
+        )
+        if force or stale:
+            subprocess.run(["make", "-C", _HERE, "-B", "_ref/libneo_ref.so"], check=True, capture_output=True)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(_vp)
+
+
+_SUF = {np.dtype(np.float32): "f32", np.dtype(np.float64): "f64"}
+_CPLX = {np.dtype(np.float32): np.complex64, np.dtype(np.float64): np.complex128}
+_REAL = {np.dtype(np.complex64): np.float32, np.dtype(np.complex128): np.float64}
+
+
+class _Checker:
+    """Common numpy-level API over either library (prefix 'oracle_' or 'ref_')."""
+
+    def __init__(self, path: str, prefix: str):
+        self.lib = C.CDLL(path)
+        self.prefix = prefix
+        self.path = path
+
+    def _fn(self, name, restype=None, argtypes=None):
+        f = getattr(self.lib, self.prefix + name)
+        f.restype = restype
+        if argtypes is not None:
+            f.argtypes = argtypes
+        return f
+
+    # ---- integer tables -------------------------------------------------------------------------
+    def bitrev_table(self, order: int) -> np.ndarray:
+        out = np.zeros(1 << order, dtype=np.uint32)
+        self._fn("bitrev_table", None, [_sz, _vp])(order, _ptr(out))
+        return out
+
+    def digitrev_perm(self, radix: int, size: int) -> np.ndarray:
+        out = np.zeros(size, dtype=np.uint32)
+        self._fn("digitrev_perm", None, [_sz, _sz, _vp])(radix, size, _ptr(out))
+        return out
+
+    def fdl_index_sequence(self, parts: int, calls: int):
+        wp = np.zeros(calls, dtype=np.uint32)
+        pairs = np.zeros((calls, parts, 2), dtype=np.uint32)
+        self._fn("fdl_index_sequence", None, [_sz, _sz, _vp, _vp])(parts, calls, _ptr(wp), _ptr(pairs))
+        return wp, pairs
+
+    def num_stft_frames(self, signal: int, frame: int, overlap: int) -> int:
+        return int(self._fn("num_stft_frames", _sz, [_sz, _sz, _sz])(signal, frame, overlap))
+
+    def next_order(self, n: int) -> int:
+        return int(self._fn("next_order", _sz, [_sz])(n))
+
+    # ---- plans ------------------------------------------------------------------------------------
+    def twiddle_lut(self, size: int, direction: int, dtype=np.float32) -> np.ndarray:
+        dtype = np.dtype(dtype)
+        out = np.zeros(size, dtype=dtype)  # size/2 complex
+        self._fn("twiddle_lut_" + _SUF[dtype], None, [_sz, _i, _vp])(size, direction, _ptr(out))
+        return out.view(_CPLX[dtype])
+
+    def fft(self, x: np.ndarray, direction: int = -1) -> np.ndarray:
+        """c2c of the last axis (any batch shape), unnormalised; returns a new array. Raises on order > 27."""
+        x = np.ascontiguousarray(x)
+        real = np.dtype(_REAL[x.dtype])
+        n = x.shape[-1]
+        order = int(n).bit_length() - 1
+        assert 1 << order == n
+        out = x.reshape(-1, n).copy()
+        fn = self._fn("fft_c2c_" + _SUF[real], _i, [_sz, _vp, _i])
+        for row in out:
+            if fn(order, _ptr(row), direction) != 0:
+                raise RuntimeError(f"unsupported order {order}")
+        return out.reshape(x.shape)
+
+    def fft_status(self, order: int) -> int:
+        """0 if a c2c plan of this order can be built (runs a transform only for small orders)."""
+        if order > 27:
+            buf = np.zeros(4, dtype=np.float32)
+            return int(self._fn("fft_c2c_f32", _i, [_sz, _vp, _i])(order, _ptr(buf), -1))
+        return 0
+
+    def rfft(self, x: np.ndarray) -> np.ndarray:
+        x = np.ascontiguousarray(x)
+        n = x.shape[-1]
+        order = int(n).bit_length() - 1
+        assert 1 << order == n
+        rows = x.reshape(-1, n)
+        out = np.zeros((rows.shape[0], n // 2 + 1), dtype=_CPLX[x.dtype])
+        fn = self._fn("rfft_" + _SUF[x.dtype], None, [_sz, _vp, _vp])
+        for r, o in zip(rows, out):
+            fn(order, _ptr(r), _ptr(o))
+        return out.reshape(x.shape[:-1] + (n // 2 + 1,))
+
+    def irfft(self, x: np.ndarray, n: int) -> np.ndarray:
+        """c2r, UNNORMALISED (fallback_rfft_plan.hpp:39-55). x[..., n/2+1] (or [..., n])."""
+        x = np.ascontiguousarray(x)
+        real = np.dtype(_REAL[x.dtype])
+        order = int(n).bit_length() - 1
+        rows = x.reshape(-1, x.shape[-1])
+        out = np.zeros((rows.shape[0], n), dtype=real)
+        fn = self._fn("irfft_" + _SUF[real], None, [_sz, _vp, _sz, _vp])
+        for r, o in zip(rows, out):
+            fn(order, _ptr(r), x.shape[-1], _ptr(o))
+        return out.reshape(x.shape[:-1] + (n,))
+
+    def multiply_add(self, x, y, z):
+        x, y, z = (np.ascontiguousarray(a) for a in (x, y, z))
+        out = np.zeros_like(x)
+        name = "multiply_add_" + ("c64" if self.prefix == "ref_" else "f32")
+        assert x.dtype == np.complex64
+        self._fn(name, None, [_vp, _vp, _vp, _vp, _sz])(_ptr(x), _ptr(y), _ptr(z), _ptr(out), x.size)
+        return out
+
+    # ---- inputs -------------------------------------------------------------------------------------
+    def noise(self, n: int, seed: int, dtype=np.float32) -> np.ndarray:
+        """generate_noise_signal (testing/testing.hpp:37-72). Complex dtypes draw re then im."""
+        dtype = np.dtype(dtype)
+        if dtype.kind == "c":
+            return self.noise(2 * n, seed, _REAL[dtype]).view(dtype)
+        out = np.zeros(n, dtype=dtype)
+        self._fn("noise_" + _SUF[dtype], None, [_sz, _u32, _vp])(n, seed, _ptr(out))
+        return out
+
+    def normalize_impulse(self, ir: np.ndarray) -> np.ndarray:
+        ir = np.ascontiguousarray(ir, dtype=np.float32).copy()
+        ch, ln = ir.shape
+        self._fn("normalize_impulse_f32", None, [_vp, _sz, _sz])(_ptr(ir), ch, ln)
+        return ir
+
+    # ---- filter preparation + convolvers ------------------------------------------------------------
+    def uniform_partition(self, ir: np.ndarray, block: int) -> np.ndarray:
+        """ir[C][L] -> H[C][P][B+1] (convolution/uniform_partition.hpp:13-26)."""
+        ir = np.ascontiguousarray(ir)
+        ch, ln = ir.shape
+        fn = self._fn("uniform_partition_" + _SUF[ir.dtype], _sz, [_vp, _sz, _sz, _sz, _vp])
+        parts = int(fn(_ptr(ir), ch, ln, block, None))
+        out = np.zeros((ch, parts, block + 1), dtype=_CPLX[ir.dtype])
+        fn(_ptr(ir), ch, ln, block, _ptr(out))
+        return out
+
+    def convolver(self, kind: int, dtype=np.float32) -> "_Convolver":
+        return _Convolver(self, kind, np.dtype(dtype))
+
+    def convolve_blocks(self, kind: int, H: np.ndarray, signal: np.ndarray, chunk: int | None = None) -> np.ndarray:
+        """Run one convolver per channel over signal[C][n] (n multiple of B) and return the output.
+        H: [C][P][K] (own filter per channel)."""
+        real = np.dtype(_REAL[H.dtype])
+        signal = np.ascontiguousarray(signal, dtype=real)
+        out = signal.copy()
+        block = H.shape[-1] - 1
+        step = chunk or block
+        for c in range(signal.shape[0]):
+            conv = self.convolver(kind, real)
+            conv.filter(H[c])
+            for s in range(0, signal.shape[1], step):
+                conv.process(out[c, s : s + step])
+            conv.close()
+        return out
+
+
+class _Convolver:
+    def __init__(self, chk: _Checker, kind: int, dtype: np.dtype):
+        self.chk, self.suf = chk, _SUF[dtype]
+        self.dtype = dtype
+        self.h = chk._fn("conv_create_" + self.suf, _vp, [_i])(kind)
+
+    def filter(self, H: np.ndarray) -> None:
+        H = np.ascontiguousarray(H, dtype=_CPLX[self.dtype])
+        self.chk._fn("conv_filter_" + self.suf, None, [_vp, _vp, _sz, _sz])(self.h, _ptr(H), H.shape[0], H.shape[1])
+
+    def process(self, block: np.ndarray) -> None:
+        assert block.dtype == self.dtype and block.flags.c_contiguous
+        self.chk._fn("conv_process_" + self.suf, None, [_vp, _vp, _sz])(self.h, _ptr(block), block.size)
+
+    def close(self) -> None:
+        if self.h:
+            self.chk._fn("conv_destroy_" + self.suf, None, [_vp])(self.h)
+            self.h = None
+
+
+class _Oracle(_Checker):
+    def direct_convolve(self, signal: np.ndarray, ir: np.ndarray, out_len: int) -> np.ndarray:
+        signal, ir = np.ascontiguousarray(signal), np.ascontiguousarray(ir, dtype=signal.dtype)
+        out = np.zeros(out_len, dtype=signal.dtype)
+        self._fn("direct_convolve_" + _SUF[signal.dtype], None, [_vp, _sz, _vp, _sz, _vp, _sz])(
+            _ptr(signal), signal.size, _ptr(ir), ir.size, _ptr(out), out_len
+        )
+        return out
+
+    def digitrev_lut(self, radix: int, size: int) -> np.ndarray:
+        out = np.zeros(size, dtype=np.uint32)
+        self._fn("digitrev_lut", None, [_sz, _sz, _vp])(radix, size, _ptr(out))
+        return out
+
+
+class _Ref(_Checker):
+    def fft_max_order(self) -> int:
+        return int(self._fn("fft_max_order", _sz, [])())
+
+    def overlap_identity(self, add: bool, block: int, filter_size: int, signal: np.ndarray) -> np.ndarray:
+        sig = np.ascontiguousarray(signal, dtype=np.float32).copy()
+        self._fn("overlap_identity_f32", None, [_i, _sz, _sz, _vp, _sz])(
+            int(add), block, filter_size, _ptr(sig), sig.size // block
+        )
+        return sig
+
+    def conv_bench(self, kind, filters, filter_stride, signal, threads) -> float:
+        """signal[C][nblocks*B] processed in place; returns seconds of the block loop."""
+        parts, bins = filters.shape[-2], filters.shape[-1]
+        ch = signal.shape[0]
+        nblocks = signal.shape[1] // (bins - 1)
+        fn = self._fn("conv_bench_f32", C.c_double, [_i, _vp, _sz, _sz, _sz, _vp, _sz, _sz, _sz])
+        return float(fn(kind, _ptr(filters), filter_stride, parts, bins, _ptr(signal), ch, nblocks, threads))
+
+    def rfft_bench(self, order: int, data: np.ndarray, threads: int) -> float:
+        fn = self._fn("rfft_bench_f32", C.c_double, [_sz, _vp, _sz, _sz])
+        return float(fn(order, _ptr(data), data.shape[0], threads))
+
+
+@functools.lru_cache(maxsize=None)
+def oracle() -> _Oracle:
+    if not os.path.exists(ORACLE_SO):
+        build()
+    return _Oracle(ORACLE_SO, "oracle_")
+
+
+@functools.lru_cache(maxsize=None)
+def ref() -> _Ref | None:
+    if not os.path.exists(REF_SO):
+        return None
+    return _Ref(REF_SO, "ref_")

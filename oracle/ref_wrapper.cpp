@@ -1,0 +1,354 @@
+// TEST INFRASTRUCTURE ONLY. Not part of the product; never linked by libneo_b200.so.
+//
+// C entry points around the UNMODIFIED reference headers, compiled where they lie
+// (/root/reference/src, see oracle/Makefile) into oracle/_ref/libneo_ref.so.
+// It is the strongest checker we have: the reference's own `fft_plan`,
+// `rfft_plan`, `uniform_partition` and `up{ols,ola}_convolver` running on the CPU.
+// It is also the `--impl reference` / `cpu_baseline.kind == "reference"` arm of bench.py
+// (threaded over channels, one convolver per channel as extra/cli/src/convolver.cpp:37-40 does).
+//
+// No xsimd (not installable offline): NEO_HAS_XSIMD is undefined, so the reference
+// drops to its scalar loops (algorithm/multiply_add.hpp:298-300) = "neo's own fallback".
+
+#include <neo/algorithm.hpp>
+#include <neo/convolution.hpp>
+#include <neo/fft.hpp>
+#include <neo/testing/testing.hpp>
+
+#include <atomic>
+#include <chrono>
+#include <complex>
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <thread>
+#include <variant>
+#include <vector>
+
+namespace {
+
+template<typename T>
+using vec_view = stdex::mdspan<T, stdex::dextents<std::size_t, 1>>;
+template<typename T>
+using mat_view = stdex::mdspan<T, stdex::dextents<std::size_t, 2>>;
+
+template<typename Float>
+auto c2c(std::size_t order, Float* inout, int direction) -> int
+{
+    using Complex = std::complex<Float>;
+    try {
+        auto plan = neo::fft::fft_plan<Complex>{neo::fft::from_order, order};
+        auto x    = vec_view<Complex>{reinterpret_cast<Complex*>(inout), plan.size()};
+        plan(x, direction < 0 ? neo::fft::direction::forward : neo::fft::direction::backward);
+    } catch (std::exception const&) {
+        return 1;
+    }
+    return 0;
+}
+
+template<typename Float>
+auto r2c(std::size_t order, Float const* in, Float* out) -> void
+{
+    using Complex = std::complex<Float>;
+    auto plan     = neo::fft::rfft_plan<Float, Complex>{neo::fft::from_order, order};
+    auto x        = vec_view<Float const>{in, plan.size()};
+    auto y        = vec_view<Complex>{reinterpret_cast<Complex*>(out), plan.size() / 2 + 1};
+    neo::fft::rfft(plan, x, y);
+}
+
+template<typename Float>
+auto c2r(std::size_t order, Float const* in, std::size_t in_len, Float* out) -> void
+{
+    using Complex = std::complex<Float>;
+    auto plan     = neo::fft::rfft_plan<Float, Complex>{neo::fft::from_order, order};
+    auto x        = vec_view<Complex const>{reinterpret_cast<Complex const*>(in), in_len};
+    auto y        = vec_view<Float>{out, plan.size()};
+    neo::fft::irfft(plan, x, y);
+}
+
+template<typename Float>
+struct convolver_box
+{
+    using Complex = std::complex<Float>;
+    std::variant<
+        neo::convolution::upols_convolver<Complex>,
+        neo::convolution::upola_convolver<Complex>,
+        neo::convolution::split_upols_convolver<Complex>,
+        neo::convolution::split_upola_convolver<Complex>,
+        neo::convolution::upola_convolver_v2<Complex>>
+        impl;
+
+    explicit convolver_box(int kind)
+    {
+        switch (kind) {
+            case 0: impl.template emplace<0>(); break;
+            case 1: impl.template emplace<1>(); break;
+            case 2: impl.template emplace<2>(); break;
+            case 3: impl.template emplace<3>(); break;
+            default: impl.template emplace<4>(); break;
+        }
+    }
+
+    auto filter(Float const* h, std::size_t parts, std::size_t bins) -> void
+    {
+        auto view = mat_view<Complex const>{reinterpret_cast<Complex const*>(h), parts, bins};
+        std::visit([&](auto& c) { c.filter(view); }, impl);
+    }
+
+    auto process(Float* block, std::size_t n) -> void
+    {
+        auto view = vec_view<Float>{block, n};
+        std::visit([&](auto& c) { c(view); }, impl);
+    }
+};
+
+}  // namespace
+
+extern "C" {
+
+// ---- plans ---------------------------------------------------------------------------
+int ref_fft_c2c_f32(std::size_t order, float* inout, int direction) { return c2c<float>(order, inout, direction); }
+int ref_fft_c2c_f64(std::size_t order, double* inout, int direction) { return c2c<double>(order, inout, direction); }
+void ref_rfft_f32(std::size_t order, float const* in, float* out) { r2c<float>(order, in, out); }
+void ref_rfft_f64(std::size_t order, double const* in, double* out) { r2c<double>(order, in, out); }
+void ref_irfft_f32(std::size_t order, float const* in, std::size_t n, float* out) { c2r<float>(order, in, n, out); }
+void ref_irfft_f64(std::size_t order, double const* in, std::size_t n, double* out) { c2r<double>(order, in, n, out); }
+
+std::size_t ref_fft_max_order() { return neo::fft::fft_plan<std::complex<float>>::max_order(); }
+std::size_t ref_next_order(std::size_t n) { return neo::fft::next_order(n); }
+
+// ---- integer tables (bit-exact contract) ------------------------------------------------
+// bitrevorder_plan keeps its table private (fft/reference/bitrevorder.hpp:77); applying the
+// involution to iota reads it back exactly.
+void ref_bitrev_table(std::size_t order, std::uint32_t* out)
+{
+    auto const n = std::size_t(1) << order;
+    auto plan    = neo::fft::bitrevorder_plan{order};
+    auto buf     = std::vector<std::complex<double>>(n);
+    for (std::size_t i = 0; i < n; ++i) { buf[i] = double(i); }
+    plan(vec_view<std::complex<double>>{buf.data(), n});
+    for (std::size_t i = 0; i < n; ++i) { out[i] = static_cast<std::uint32_t>(buf[i].real()); }
+}
+
+// permutation produced by digitrevorder_plan<Radix> (fft/reference/digitrevorder.hpp:13-48)
+void ref_digitrev_perm(std::size_t radix, std::size_t size, std::uint32_t* out)
+{
+    auto buf = std::vector<std::complex<double>>(size);
+    for (std::size_t i = 0; i < size; ++i) { buf[i] = double(i); }
+    auto view = vec_view<std::complex<double>>{buf.data(), size};
+    switch (radix) {
+        case 2: neo::fft::digitrevorder_plan<2>{size}(view); break;
+        case 3: neo::fft::digitrevorder_plan<3>{size}(view); break;
+        case 4: neo::fft::digitrevorder_plan<4>{size}(view); break;
+        case 5: neo::fft::digitrevorder_plan<5>{size}(view); break;
+        case 8: neo::fft::digitrevorder_plan<8>{size}(view); break;
+        default: break;
+    }
+    for (std::size_t i = 0; i < size; ++i) { out[i] = static_cast<std::uint32_t>(buf[i].real()); }
+}
+
+// twiddle LUT exactly as the plan builds it (fft/twiddle.hpp:47-52), interleaved re/im
+void ref_twiddle_lut_f32(std::size_t size, int direction, float* out)
+{
+    auto lut = neo::fft::make_twiddle_lut_radix2<std::complex<float>>(
+        size,
+        direction < 0 ? neo::fft::direction::forward : neo::fft::direction::backward
+    );
+    std::memcpy(out, lut.data(), sizeof(float) * size);
+}
+
+void ref_twiddle_lut_f64(std::size_t size, int direction, double* out)
+{
+    auto lut = neo::fft::make_twiddle_lut_radix2<std::complex<double>>(
+        size,
+        direction < 0 ? neo::fft::direction::forward : neo::fft::direction::backward
+    );
+    std::memcpy(out, lut.data(), sizeof(double) * size);
+}
+
+// fdl_index sequence: for each of `calls` invocations records write_pos and the P (fdl,filter) pairs
+void ref_fdl_index_sequence(std::size_t parts, std::size_t calls, std::uint32_t* write_pos, std::uint32_t* pairs)
+{
+    auto idx = neo::convolution::fdl_index<std::size_t>{parts};
+    for (std::size_t c = 0; c < calls; ++c) {
+        auto n = std::size_t(0);
+        idx(
+            [&](std::size_t w) { write_pos[c] = static_cast<std::uint32_t>(w); },
+            [&](std::size_t fdl, std::size_t filt) {
+                pairs[(c * parts + n) * 2 + 0] = static_cast<std::uint32_t>(fdl);
+                pairs[(c * parts + n) * 2 + 1] = static_cast<std::uint32_t>(filt);
+                ++n;
+            }
+        );
+    }
+}
+
+std::size_t ref_num_stft_frames(std::size_t signal, std::size_t frame, std::size_t overlap)
+{
+    return neo::fft::detail::num_sftf_frames(signal, frame, overlap);
+}
+
+// ---- inputs ------------------------------------------------------------------------------
+void ref_noise_f32(std::size_t n, std::uint32_t seed, float* out)
+{
+    auto sig = neo::generate_noise_signal<float>(n, seed);
+    std::memcpy(out, sig.data(), sizeof(float) * n);
+}
+
+void ref_noise_f64(std::size_t n, std::uint32_t seed, double* out)
+{
+    auto sig = neo::generate_noise_signal<double>(n, seed);
+    std::memcpy(out, sig.data(), sizeof(double) * n);
+}
+
+void ref_noise_c64(std::size_t n, std::uint32_t seed, float* out)
+{
+    auto sig = neo::generate_noise_signal<std::complex<float>>(n, seed);
+    std::memcpy(out, sig.data(), sizeof(float) * 2 * n);
+}
+
+void ref_noise_c128(std::size_t n, std::uint32_t seed, double* out)
+{
+    auto sig = neo::generate_noise_signal<std::complex<double>>(n, seed);
+    std::memcpy(out, sig.data(), sizeof(double) * 2 * n);
+}
+
+void ref_normalize_impulse_f32(float* ir, std::size_t channels, std::size_t len)
+{
+    neo::convolution::normalize_impulse(mat_view<float>{ir, channels, len});
+}
+
+// ---- elementwise -------------------------------------------------------------------------
+void ref_multiply_add_c64(float const* x, float const* y, float const* z, float* out, std::size_t n)
+{
+    using C = std::complex<float>;
+    neo::multiply_add(
+        vec_view<C const>{reinterpret_cast<C const*>(x), n},
+        vec_view<C const>{reinterpret_cast<C const*>(y), n},
+        vec_view<C const>{reinterpret_cast<C const*>(z), n},
+        vec_view<C>{reinterpret_cast<C*>(out), n}
+    );
+}
+
+// ---- filter preparation -------------------------------------------------------------------
+// uniform_partition (convolution/uniform_partition.hpp:13-26): out is [C][P][B+1] complex, returns P
+std::size_t ref_uniform_partition_f32(float const* ir, std::size_t channels, std::size_t len, std::size_t block, float* out)
+{
+    auto parts = neo::convolution::uniform_partition(mat_view<float const>{ir, channels, len}, block);
+    if (out != nullptr) { std::memcpy(out, parts.data(), sizeof(float) * 2 * parts.size()); }
+    return parts.extent(1);
+}
+
+std::size_t
+ref_uniform_partition_f64(double const* ir, std::size_t channels, std::size_t len, std::size_t block, double* out)
+{
+    auto parts = neo::convolution::uniform_partition(mat_view<double const>{ir, channels, len}, block);
+    if (out != nullptr) { std::memcpy(out, parts.data(), sizeof(double) * 2 * parts.size()); }
+    return parts.extent(1);
+}
+
+// ---- overlap policies with the identity callback (convolution/overlap_test.cpp:21-64) -----------
+void ref_overlap_identity_f32(int add, std::size_t block, std::size_t filter_size, float* signal, std::size_t nblocks)
+{
+    using C = std::complex<float>;
+    auto run = [&](auto policy) {
+        for (std::size_t b = 0; b < nblocks; ++b) {
+            policy(vec_view<float>{signal + b * block, block}, [](auto) {});
+        }
+    };
+    if (add != 0) {
+        run(neo::convolution::overlap_add<C>{block, filter_size});
+    } else {
+        run(neo::convolution::overlap_save<C>{block, filter_size});
+    }
+}
+
+// ---- convolvers ----------------------------------------------------------------------------
+// kind: 0 upols, 1 upola, 2 split_upols, 3 split_upola, 4 upola_v2 (convolution/dense_convolver.hpp:20-41)
+void* ref_conv_create_f32(int kind) { return new convolver_box<float>{kind}; }
+void* ref_conv_create_f64(int kind) { return new convolver_box<double>{kind}; }
+void ref_conv_destroy_f32(void* h) { delete static_cast<convolver_box<float>*>(h); }
+void ref_conv_destroy_f64(void* h) { delete static_cast<convolver_box<double>*>(h); }
+void ref_conv_filter_f32(void* h, float const* f, std::size_t parts, std::size_t bins)
+{
+    static_cast<convolver_box<float>*>(h)->filter(f, parts, bins);
+}
+void ref_conv_filter_f64(void* h, double const* f, std::size_t parts, std::size_t bins)
+{
+    static_cast<convolver_box<double>*>(h)->filter(f, parts, bins);
+}
+void ref_conv_process_f32(void* h, float* block, std::size_t n) { static_cast<convolver_box<float>*>(h)->process(block, n); }
+void ref_conv_process_f64(void* h, double* block, std::size_t n)
+{
+    static_cast<convolver_box<double>*>(h)->process(block, n);
+}
+
+// ---- timed CPU baselines (bench.py cpu_baseline / --impl reference) ------------------------------
+// `channels` independent convolvers (own filter each, filter[c] = H + c*filter_stride complex elements; stride 0
+// shares one filter so the sample fits host RAM), spread over `threads` std::threads.
+// Every channel processes `nblocks` blocks of B = bins-1 samples in place in signal[c][nblocks*B].
+// Returns seconds spent in the block loop only (filter setup excluded, as convolution.cpp:26-40 excludes it).
+double ref_conv_bench_f32(
+    int kind,
+    float const* filters,
+    std::size_t filter_stride,
+    std::size_t parts,
+    std::size_t bins,
+    float* signal,
+    std::size_t channels,
+    std::size_t nblocks,
+    std::size_t threads
+)
+{
+    auto const block = bins - 1;
+    auto boxes       = std::vector<std::unique_ptr<convolver_box<float>>>(channels);
+
+    auto for_channels = [&](auto fn) {
+        auto next = std::atomic<std::size_t>{0};
+        auto pool = std::vector<std::thread>{};
+        for (std::size_t t = 0; t < threads; ++t) {
+            pool.emplace_back([&] {
+                for (auto c = next.fetch_add(1); c < channels; c = next.fetch_add(1)) { fn(c); }
+            });
+        }
+        for (auto& t : pool) { t.join(); }
+    };
+
+    for_channels([&](std::size_t c) {
+        boxes[c] = std::make_unique<convolver_box<float>>(kind);
+        boxes[c]->filter(filters + c * filter_stride * 2, parts, bins);
+    });
+
+    auto const start = std::chrono::steady_clock::now();
+    for_channels([&](std::size_t c) {
+        for (std::size_t b = 0; b < nblocks; ++b) { boxes[c]->process(signal + (c * nblocks + b) * block, block); }
+    });
+    auto const stop = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(stop - start).count();
+}
+
+// batched rfft+irfft round trips, batch split over threads, one plan per thread
+double ref_rfft_bench_f32(std::size_t order, float* data, std::size_t batch, std::size_t threads)
+{
+    using C       = std::complex<float>;
+    auto const n  = std::size_t(1) << order;
+    auto next     = std::atomic<std::size_t>{0};
+    auto pool     = std::vector<std::thread>{};
+    auto const t0 = std::chrono::steady_clock::now();
+    for (std::size_t t = 0; t < threads; ++t) {
+        pool.emplace_back([&] {
+            auto plan = neo::fft::rfft_plan<float, C>{neo::fft::from_order, order};
+            auto spec = std::vector<C>(n);
+            for (auto b = next.fetch_add(1); b < batch; b = next.fetch_add(1)) {
+                auto x = vec_view<float>{data + b * n, n};
+                neo::fft::rfft(plan, x, vec_view<C>{spec.data(), n});
+                neo::fft::irfft(plan, vec_view<C>{spec.data(), n}, x);
+            }
+        });
+    }
+    for (auto& t : pool) { t.join(); }
+    auto const t1 = std::chrono::steady_clock::now();
+    return std::chrono::duration<double>(t1 - t0).count();
+}
+
+}  // extern "C"

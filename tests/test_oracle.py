@@ -1,0 +1,208 @@
+"""CPU: pins the oracle (oracle/neo_oracle.c) against the reference's own known-answer tests, against golden vectors
+produced by the unmodified reference (tests/golden/neo_ref_golden.npz, oracle/make_golden.py) and, where the prebuilt
+oracle/_ref library is present, against the reference side by side."""
+import numpy as np
+import pytest
+
+from conftest import rel_l2
+
+KINDS = ("upols", "upola", "split_upols", "split_upola", "upola_v2")
+
+
+# ---- integers: bit-exact ---------------------------------------------------------------------------------------------
+def test_bitrev_table_golden(orc, golden):
+    for order in range(0, 11):
+        assert np.array_equal(orc.bitrev_table(order), golden[f"bitrev/{order}"])
+    # order 4
+    assert orc.bitrev_table(4).tolist() == [0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15]
+
+
+def test_digitrev_golden(orc, golden):
+    for key in [k for k in golden.files if k.startswith("digitrev/")]:
+        _, radix, size = key.split("/")
+        assert np.array_equal(orc.digitrev_perm(int(radix), int(size)), golden[key]), key
+    # the reference's LUT quirk: the last entry stays 0 (digitrevorder.hpp:34)
+    assert orc.digitrev_lut(4, 16)[-1] == 0 and orc.digitrev_lut(4, 16)[1] == 4
+
+
+def test_fdl_index_sequence(orc, golden):
+    # convolution/fdl_index_test.cpp:13-65, P = 3
+    wp, pairs = orc.fdl_index_sequence(3, 6)
+    assert wp.tolist() == [0, 1, 2, 0, 1, 2]
+    assert pairs[0].tolist() == [[0, 0], [1, 2], [2, 1]]
+    assert pairs[1].tolist() == [[0, 1], [1, 0], [2, 2]]
+    assert pairs[2].tolist() == [[0, 2], [1, 1], [2, 0]]
+    for parts in (1, 2, 3, 4, 7):
+        wp, pairs = orc.fdl_index_sequence(parts, 2 * parts + 3)
+        assert np.array_equal(wp, golden[f"fdl_index/{parts}/write_pos"])
+        assert np.array_equal(pairs, golden[f"fdl_index/{parts}/pairs"])
+
+
+def test_frame_counts_and_orders(orc, golden):
+    # fft/stft_test.cpp:8-13
+    assert orc.num_stft_frames(1024, 128, 0) == 8
+    assert orc.num_stft_frames(1024, 256, 128) == 8
+    for args, want in zip(golden["stft_frames/args"], golden["stft_frames/out"]):
+        assert orc.num_stft_frames(*[int(a) for a in args]) == int(want)
+    for n, want in zip(golden["next_order/args"], golden["next_order/out"]):
+        assert orc.next_order(int(n)) == int(want)
+    assert int(golden["fft_max_order"][0]) == 27
+    assert int(golden["fft_status_28"][0]) != 0 and orc.fft_status(28) != 0  # ctor throws past max_order
+    assert orc.fft_status(27) == 0
+
+
+# ---- inputs -------------------------------------------------------------------------------------------------------------
+def test_noise_matches_reference_generator(orc, golden):
+    for seed in (1, 2, 11, 13):
+        assert np.array_equal(orc.noise(96, seed, np.float32), golden[f"noise/f32/{seed}"])
+        assert np.array_equal(orc.noise(96, seed, np.float64), golden[f"noise/f64/{seed}"])
+    assert np.array_equal(orc.noise(48, 1, np.complex64), golden["noise/c64/1"])
+
+
+def test_twiddle_luts(orc, golden):
+    for size in (2, 4, 16, 256):
+        for d, name in ((-1, "fwd"), (1, "bwd")):
+            assert np.array_equal(orc.twiddle_lut(size, d, np.float32), golden[f"twiddle/f32/{size}/{name}"])
+            assert np.array_equal(orc.twiddle_lut(size, d, np.float64), golden[f"twiddle/f64/{size}/{name}"])
+
+
+# ---- known answers of the reference's own tests ----------------------------------------------------------------------------
+def test_kat_c2c_1234(orc, golden):
+    # fft/rfft_test.cpp:170-186: FFT([1,2,3,4]) = [10, -2+2i, -2, -2-2i]
+    got = orc.fft(np.array([1, 2, 3, 4], dtype=np.complex64), -1)
+    assert np.allclose(got, [10, -2 + 2j, -2, -2 - 2j], atol=1e-6)
+    assert np.allclose(got, golden["kat/c2c_1234"], atol=0)
+
+
+def test_kat_delta_all_ones(orc, golden):
+    # fft/rfft_test.cpp:132-168, fft/dft_test.cpp:31-46
+    for n in (2, 16, 128):
+        x = np.zeros(n, dtype=np.complex128)
+        x[0] = 1
+        assert np.allclose(orc.fft(x, -1), np.ones(n))
+        assert np.allclose(orc.fft(x, +1), np.ones(n))
+    assert np.array_equal(orc.fft(np.eye(1, 16, 0, dtype=np.complex64)[0], -1), golden["kat/c2c_delta16"])
+
+
+def test_kat_dct2_through_fft(orc):
+    # fft/dct_test.cpp:23-39 pins fft_plan at N=8 through the DCT-II of [1..8] against scipy's values.
+    # DCT-II via one N-point c2c (Makhoul): v = even samples then reversed odd samples, X = 2 Re(W4N^k FFT(v))
+    x = np.arange(1, 9, dtype=np.float64)
+    v = np.concatenate([x[0::2], x[1::2][::-1]]).astype(np.complex128)
+    V = orc.fft(v, -1)
+    k = np.arange(8)
+    dct = 2 * np.real(np.exp(-1j * np.pi * k / 16) * V)
+    want = [72.0, -25.76929209, 0.0, -2.6938192, 0.0, -0.80361161, 0.0, -0.20280929]
+    assert np.allclose(dct, want, atol=1e-6)
+
+
+def test_kat_multiply_add(orc, golden):
+    # algorithm/multiply_add_test.cpp:52-95: (1+2i)(3+4i)+(5+6i) = 0+16i, sizes 2/33/128
+    for n in (2, 33, 128):
+        x, y, z = (np.full(n, v, dtype=np.complex64) for v in (1 + 2j, 3 + 4j, 5 + 6j))
+        assert np.array_equal(orc.multiply_add(x, y, z), np.full(n, 16j, dtype=np.complex64))
+    assert np.array_equal(golden["kat/multiply_add"], np.full(33, 16j, dtype=np.complex64))
+
+
+# ---- transforms vs golden ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,real,cplx,tol", [("f32", np.float32, np.complex64, 0.0), ("f64", np.float64, np.complex128, 4e-16)])
+def test_transforms_match_reference_golden(orc, golden, tag, real, cplx, tol):
+    # f32: bit-exact. f64: the reference build contracts a*b+c into FMA (-march=x86-64-v3), the oracle does not.
+    for order in (1, 2, 3, 4, 5, 8, 10, 11):
+        n = 1 << order
+        x = orc.noise(n, 1, cplx)
+        assert rel_l2(orc.fft(x, -1), golden[f"c2c/{tag}/{order}/fwd"]) <= tol
+        assert rel_l2(orc.fft(x, +1), golden[f"c2c/{tag}/{order}/bwd"]) <= tol
+        xr = orc.noise(n, 2, real)
+        spec = orc.rfft(xr)
+        assert rel_l2(spec, golden[f"r2c/{tag}/{order}"]) <= tol
+        assert rel_l2(orc.irfft(golden[f"r2c/{tag}/{order}"], n), golden[f"c2r/{tag}/{order}"]) <= tol
+    junk = orc.noise(64, 5, cplx)
+    assert rel_l2(orc.irfft(junk[:33], 64), golden[f"c2r_junk/{tag}/half"]) <= tol
+    assert rel_l2(orc.irfft(junk, 64), golden[f"c2r_junk/{tag}/full"]) <= tol
+    # c2r ignores Im X[0], Im X[N/2] and everything past N/2 (fallback_rfft_plan.hpp:44-54)
+    assert np.array_equal(golden[f"c2r_junk/{tag}/half"], golden[f"c2r_junk/{tag}/full"])
+
+
+def test_transforms_against_numpy(orc):
+    for order in (1, 3, 6, 9, 12):
+        n = 1 << order
+        x = orc.noise(n, 1, np.complex128)
+        assert rel_l2(orc.fft(x, -1), np.fft.fft(x)) < 1e-14
+        assert rel_l2(orc.fft(x, +1), np.fft.ifft(x) * n) < 1e-14
+        xr = orc.noise(n, 2, np.float64)
+        assert rel_l2(orc.rfft(xr), np.fft.rfft(xr)) < 1e-14
+        assert rel_l2(orc.irfft(np.fft.rfft(xr), n), xr * n) < 1e-14  # unnormalised round trip gains N
+    # rfft(a), rfft(b) == deinterleave(fft(a + ib)) (fft/rfft_test.cpp:80-126)
+    a, b = orc.noise(256, 3, np.float64), orc.noise(256, 4, np.float64)
+    z = orc.fft(a + 1j * b, -1)
+    zc = np.conj(np.roll(z[::-1], 1))
+    assert np.allclose(orc.rfft(a), ((z + zc) / 2)[:129]) and np.allclose(orc.rfft(b), ((z - zc) / 2j)[:129])
+
+
+# ---- filter preparation + convolvers vs golden ---------------------------------------------------------------------------------
+@pytest.mark.parametrize("tag,tol", [("f32", 0.0), ("f64", 1e-15)])
+def test_partition_and_convolvers_match_reference_golden(orc, golden, tag, tol):
+    B, L, NB = (int(v) for v in golden["conv/block"])
+    ir, sig, H = golden[f"conv/{tag}/ir"], golden[f"conv/{tag}/signal"], golden[f"conv/{tag}/H"]
+    assert H.shape == (2, -(-L // B), B + 1)  # convolution/uniform_partition_test.cpp:8-38: [C][ceil(L/B)][B+1]
+    assert rel_l2(orc.uniform_partition(ir, B), H) <= tol
+    for kind, name in enumerate(KINDS):
+        # split_* keep SoA planes; same arithmetic order, so the oracle (one AoS implementation) must match both
+        tol_k = max(tol, 2e-7) if name.startswith("split") else tol
+        assert rel_l2(orc.convolve_blocks(kind, H, sig), golden[f"conv/{tag}/{name}"]) <= tol_k, name
+    assert rel_l2(orc.convolve_blocks(4, H, sig, chunk=96), golden[f"conv/{tag}/upola_v2_chunk96"]) <= tol
+
+
+def test_uniform_partition_shapes(orc):
+    # convolution/uniform_partition_test.cpp:8-38
+    for L in (4096, 4095):
+        H = orc.uniform_partition(np.zeros((2, L), dtype=np.float32), 128)
+        assert H.shape == (2, 32, 129)
+
+
+def test_upols_equals_direct_convolution(orc):
+    # the gap SURVEY section 4 names: non-trivial IR vs direct convolution
+    B, L, NB = 128, 1000, 24
+    ir = orc.normalize_impulse(orc.noise(L, 11, np.float32)[None, :])
+    sig = orc.noise(B * NB, 13, np.float32)[None, :]
+    H = orc.uniform_partition(ir, B)
+    want = orc.direct_convolve(sig[0], ir[0], B * NB)
+    for kind in (0, 1, 4):
+        assert rel_l2(orc.convolve_blocks(kind, H, sig)[0], want) < 2e-6
+
+
+def test_identity_filter_passes_signal(orc):
+    # convolution/uniform_partitioned_convolver_test.cpp:35-75: partition 0 all-ones, 3 partitions, 20 blocks
+    for B in (128, 256):
+        H = np.zeros((1, 3, B + 1), dtype=np.complex64)
+        H[0, 0, :] = 1
+        sig = orc.noise(B * 20, 7, np.float32)[None, :]
+        for kind in range(5):
+            assert np.allclose(orc.convolve_blocks(kind, H, sig), sig, atol=1e-5)
+
+
+def test_overlap_policies_identity(golden):
+    # convolution/overlap_test.cpp:21-64 through the reference itself
+    assert np.allclose(golden["overlap/save"], golden["overlap/signal"], atol=1e-5)
+    assert np.allclose(golden["overlap/add"], golden["overlap/signal"], atol=1e-5)
+
+
+# ---- side by side with the compiled reference, when it travelled ------------------------------------------------------------------
+def test_oracle_vs_compiled_reference(orc, ref):
+    if ref is None:
+        pytest.skip("oracle/_ref/libneo_ref.so not present")
+    for order in range(0, 13):
+        assert np.array_equal(orc.bitrev_table(order), ref.bitrev_table(order))
+    for order in (1, 4, 9, 13):
+        x = orc.noise(1 << order, 21, np.complex64)
+        assert np.array_equal(orc.fft(x, -1), ref.fft(x, -1))
+        xr = orc.noise(1 << order, 22, np.float32)
+        assert np.array_equal(orc.rfft(xr), ref.rfft(xr))
+    ir = orc.normalize_impulse(np.stack([orc.noise(700, 31 + c, np.float32) for c in range(2)]))
+    assert np.array_equal(ir, ref.normalize_impulse(np.stack([orc.noise(700, 31 + c, np.float32) for c in range(2)])))
+    H = orc.uniform_partition(ir, 64)
+    assert np.array_equal(H, ref.uniform_partition(ir, 64))
+    sig = np.stack([orc.noise(64 * 16, 41 + c, np.float32) for c in range(2)])
+    for kind in (0, 1, 4):
+        assert np.array_equal(orc.convolve_blocks(kind, H, sig), ref.convolve_blocks(kind, H, sig))
