@@ -1,0 +1,62 @@
+"""CPU: the C-ABI library loads, exports every symbol include/neo_b200.h declares, and -- with no GPU -- refuses to
+compute instead of falling back to anything."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from conftest import ROOT
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "neo_b200.h")).read()
+    return sorted(set(re.findall(r"NEO_B200_API[^;]*?\b(neo_b200_\w+)\s*\(", text)))
+
+
+def test_header_and_binding_agree(pkg):
+    names = declared_symbols()
+    assert len(names) >= 38
+    assert sorted(pkg.SIGNATURES) == names
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = ctypes.CDLL(pkg.LIBRARY_PATH)
+    for name in declared_symbols():
+        assert hasattr(lib, name), name
+
+
+def test_integer_helpers_need_no_device(pkg):
+    assert pkg.FFTPlan.max_order() == 27  # c2c_dit2_plan.hpp:59-62
+    assert pkg.num_partitions(4096, 128) == 32 and pkg.num_partitions(4095, 128) == 32  # uniform_partition_test.cpp
+    assert pkg.num_partitions(1 << 20, 1024) == 1024
+    assert [pkg.next_order(n) for n in (1, 2, 3, 1023, 1024, 1025)] == [0, 1, 2, 10, 10, 11]
+    assert pkg.library().neo_b200_version().startswith(b"neo_b200")
+
+
+def test_order_past_max_is_unsupported_like_the_reference(pkg):
+    # fft_test.cpp:62-67 expects a throw for next_order(max_size()+1)
+    with pytest.raises(RuntimeError, match="unsupported order"):
+        pkg.FFTPlan(pkg.FFTPlan.max_order() + 1)
+    with pytest.raises(RuntimeError, match="unsupported order"):
+        pkg.RFFTPlan(28)
+
+
+def test_no_cpu_fallback(pkg):
+    if pkg.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    for make in (lambda: pkg.FFTPlan(4), lambda: pkg.RFFTPlan(4), lambda: pkg.bitrev_table(4)):
+        with pytest.raises(RuntimeError, match="no CPU fallback"):
+            make()
+
+
+def test_product_never_touches_the_oracle():
+    for base, _, files in os.walk(os.path.join(ROOT, "neo-dsp_b200")):
+        if os.sep + "build" in base:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")) or f == "Makefile":
+                text = open(os.path.join(base, f)).read()
+                assert "oracle" not in text.lower() or f == "__init__.py" and "pyoracle" not in text, f
+    text = open(os.path.join(ROOT, "include", "neo_b200.h")).read()
+    assert "oracle" not in text.lower()

@@ -1,0 +1,263 @@
+"""GPU: parity of the CUDA partitioned-convolver bank with the oracle (= the reference's upols/upola convolvers, one per
+channel) through the C ABI, block by block including the zero-history warm-up blocks."""
+import numpy as np
+import pytest
+
+from conftest import TOL, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def make_case(orc, channels, taps, block, nblocks, real=np.float32, seed=0):
+    ir = np.stack([orc.noise(taps, 11 + seed + c, real) for c in range(channels)])
+    if real == np.float32:
+        ir = orc.normalize_impulse(ir)
+    else:
+        ir = ir / np.sqrt((ir**2).sum(axis=1).max())
+    sig = np.stack([orc.noise(block * nblocks, 13 + seed + c, real) for c in range(channels)])
+    return ir, sig
+
+
+def run_bank(conv, sig, block, pattern):
+    """feed sig[C][n] through the bank with the given sequence of blocks-per-call"""
+    out = sig.copy()
+    pos = 0
+    i = 0
+    while pos < sig.shape[1]:
+        t = min(pattern[i % len(pattern)], (sig.shape[1] - pos) // block)
+        chunk = np.ascontiguousarray(out[:, pos : pos + t * block])
+        conv(chunk)
+        out[:, pos : pos + t * block] = chunk
+        pos += t * block
+        i += 1
+    return out
+
+
+@pytest.mark.parametrize("name,kind", [("upols", 0), ("upola", 1)])
+@pytest.mark.parametrize("tag,real", [("f32", np.float32), ("f64", np.float64)])
+def test_golden_vectors_from_the_reference(gpu, golden, name, kind, tag, real):
+    B, L, NB = (int(v) for v in golden["conv/block"])
+    H, sig, want = golden[f"conv/{tag}/H"], golden[f"conv/{tag}/signal"], golden[f"conv/{tag}/{name}"]
+    for pattern in ([1], [2], [3, 1], [12]):
+        conv = gpu.Convolver(kind, real, gpu.DIAGONAL, max_blocks=max(pattern))
+        conv.filter(H)
+        got = run_bank(conv, sig, B, pattern)
+        assert rel_l2(got, want) <= TOL[np.dtype(real).name], pattern
+        conv.close()
+    # split_* aliases and upola_v2 (block-sized calls) compute the same thing (dense_convolver.hpp:28-41)
+    assert rel_l2(golden[f"conv/{tag}/split_{name}"], want) <= 1e-6
+    if kind == 1:
+        assert rel_l2(golden[f"conv/{tag}/upola_v2"], want) <= 1e-6
+
+
+@pytest.mark.parametrize("block,taps,channels,nblocks", [
+    (2, 7, 3, 9), (8, 8, 2, 6), (16, 100, 3, 40), (128, 1000, 3, 24), (512, 512 * 17, 2, 40), (1024, 1024 * 33 - 5, 2, 45),
+    (4096, 4096 * 3, 1, 7),
+])
+def test_upols_matches_oracle_streaming_and_batched(gpu, orc, block, taps, channels, nblocks):
+    ir, sig = make_case(orc, channels, taps, block, nblocks)
+    H = orc.uniform_partition(ir, block)
+    want = orc.convolve_blocks(0, H, sig)
+    for pattern in ([1], [1, 2, 5, 16, 7, 1, 3], [32]):
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, max_blocks=32)
+        conv.filter(H)
+        got = run_bank(conv, sig, block, pattern)
+        assert rel_l2(got, want) <= 1e-5, (pattern, rel_l2(got, want))
+        conv.close()
+    # against direct convolution too (the gap SURVEY section 4 names)
+    direct = np.stack([orc.direct_convolve(sig[c], ir[c], sig.shape[1]) for c in range(channels)])
+    assert rel_l2(got, direct) <= 1e-5
+
+
+@pytest.mark.parametrize("block,taps", [(16, 100), (256, 256 * 9 - 3)])
+def test_upola_and_f64(gpu, orc, block, taps):
+    for real in (np.float32, np.float64):
+        ir, sig = make_case(orc, 2, taps, block, 20, real)
+        H = orc.uniform_partition(ir, block)
+        for kind in (0, 1):
+            want = orc.convolve_blocks(kind, H, sig)
+            for pattern in ([1], [4, 1, 8]):
+                conv = gpu.Convolver(kind, real, gpu.DIAGONAL, max_blocks=8)
+                conv.filter(H)
+                assert rel_l2(run_bank(conv, sig, block, pattern), want) <= TOL[np.dtype(real).name], (real, kind, pattern)
+                conv.close()
+
+
+def test_identity_filter_passes_signal(gpu, orc):
+    # convolution/uniform_partitioned_convolver_test.cpp:35-75
+    for block in (128, 256, 512, 1024):
+        H = np.zeros((1, 3, block + 1), dtype=np.complex64)
+        H[0, 0, :] = 1
+        sig = orc.noise(block * 20, 7, np.float32)[None, :]
+        for kind in (gpu.UPOLS, gpu.UPOLA):
+            conv = gpu.Convolver(kind, np.float32)
+            conv.filter(H)
+            assert np.allclose(run_bank(conv, sig, block, [1]), sig, atol=1e-5)
+            conv.close()
+
+
+def test_uniform_partition_matches_oracle(gpu, orc, golden):
+    B, L, _ = (int(v) for v in golden["conv/block"])
+    for tag, real in (("f32", np.float32), ("f64", np.float64)):
+        got = gpu.uniform_partition(golden[f"conv/{tag}/ir"], B)
+        assert got.shape == golden[f"conv/{tag}/H"].shape
+        assert rel_l2(got, golden[f"conv/{tag}/H"]) <= TOL[np.dtype(real).name]
+    for L in (4096, 4095):  # convolution/uniform_partition_test.cpp:8-38
+        ir = np.stack([orc.noise(L, 3 + c, np.float32) for c in range(2)])
+        got = gpu.uniform_partition(ir, 128)
+        assert got.shape == (2, 32, 129)
+        assert rel_l2(got, orc.uniform_partition(ir, 128)) <= 1e-5
+    with pytest.raises(RuntimeError):
+        gpu.uniform_partition(np.zeros((1, 100), dtype=np.float32), 128)  # L < B underflows in the reference
+    with pytest.raises(RuntimeError):
+        gpu.uniform_partition(np.zeros((1, 300), dtype=np.float32), 96)   # B must be a power of two
+
+
+def test_impulse_entry_equals_filter_entry(gpu, orc):
+    ir, sig = make_case(orc, 3, 700, 64, 16)
+    a = gpu.Convolver(gpu.UPOLS, np.float32, max_blocks=4)
+    a.filter(orc.uniform_partition(ir, 64))
+    b = gpu.Convolver(gpu.UPOLS, np.float32, max_blocks=4)
+    b.impulse(ir, 64)
+    ya, yb = run_bank(a, sig, 64, [4]), run_bank(b, sig, 64, [4])
+    assert rel_l2(yb, ya) <= 2e-6
+
+
+def test_filter_swap_and_reset(gpu, orc):
+    ir, sig = make_case(orc, 2, 500, 32, 10)
+    ir2, _ = make_case(orc, 2, 300, 32, 10, seed=50)
+    H, H2 = orc.uniform_partition(ir, 32), orc.uniform_partition(ir2, 32)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32)
+    conv.filter(H)
+    first = run_bank(conv, sig, 32, [1])
+    conv.reset()
+    assert np.array_equal(run_bank(conv, sig, 32, [1]), first)  # reset restores the zero-history state exactly
+    conv.filter(H2)  # filter() may be called again to swap IRs; all state is re-created (uniform_partitioned_convolver.hpp:38-45)
+    assert rel_l2(run_bank(conv, sig, 32, [1]), orc.convolve_blocks(0, H2, sig)) <= 1e-5
+
+
+def test_matrix_topology_equals_sum_of_reference_convolvers(gpu, orc):
+    # 3 inputs x 2 outputs: every (o, i) pair is one reference convolver, outputs summed per o
+    O, I, B, L, NB = 2, 3, 64, 64 * 9, 14
+    ir = np.stack([np.stack([orc.noise(L, 100 + 10 * o + i, np.float32) for i in range(I)]) for o in range(O)])
+    ir /= np.sqrt((ir**2).sum(axis=2).max())
+    sig = np.stack([orc.noise(B * NB, 13 + i, np.float32) for i in range(I)])
+    want = np.zeros((O, B * NB), dtype=np.float64)
+    for o in range(O):
+        H = orc.uniform_partition(ir[o], B)
+        want[o] = orc.convolve_blocks(0, H, sig).astype(np.float64).sum(axis=0)
+    Hm = np.stack([orc.uniform_partition(ir[o], B) for o in range(O)])
+    for pattern in ([1], [2, 4, 1]):
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.MATRIX, max_blocks=4)
+        conv.filter(Hm)
+        got = np.zeros((O, B * NB), dtype=np.float32)
+        pos, i = 0, 0
+        while pos < B * NB:
+            t = min(pattern[i % len(pattern)], NB - pos // B)
+            got[:, pos : pos + t * B] = conv(np.ascontiguousarray(sig[:, pos : pos + t * B]))
+            pos += t * B
+            i += 1
+        assert rel_l2(got, want) <= 1e-5, pattern
+        conv.close()
+
+
+def test_partition_sharded_handles_sum_to_the_whole(gpu, orc):
+    # one long IR split over "devices": partial spectra add up; inverse runs on the sum (last row)
+    import torch
+
+    C, B, P, NB, T = 4, 128, 12, 18, 3
+    ir, sig = make_case(orc, C, B * P - 17, B, NB)
+    H = orc.uniform_partition(ir, B)
+    want = orc.convolve_blocks(0, H, sig)
+    shards = [(0, 5), (5, 6), (6, 12)]
+    convs = []
+    for lo, hi in shards:
+        c = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, max_blocks=T, partition_range=(lo, hi))
+        c.filter(H)
+        convs.append(c)
+    got = np.zeros_like(sig)
+    for pos in range(0, NB, T):
+        x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + T) * B])).cuda()
+        total = None
+        for c in convs:
+            c.forward(x)
+            c.synchronize()
+            part = c.spectra_tensor(T).clone()
+            total = part if total is None else total + part
+        y = torch.empty_like(x)
+        # the channel range is split too: outputs [0,1) on "rank" 0, [1,4) on "rank" 2
+        convs[0].inverse(total[0:1].contiguous(), y[0:1], 0, 1, T)
+        convs[2].inverse(total[1:4].contiguous(), y[1:4], 1, 3, T)
+        convs[0].synchronize()
+        convs[2].synchronize()
+        got[:, pos * B : (pos + T) * B] = y.cpu().numpy()
+    assert rel_l2(got, want) <= 1e-5
+    with pytest.raises(RuntimeError):
+        convs[0](np.zeros((C, B), dtype=np.float32))  # a sharded handle has no complete process()
+
+
+def test_small_bank_splits_partitions_across_ctas(gpu, orc):
+    # 1 channel x 256 partitions: the partition loop is split over CTAs and partial planes are summed in the c2r load
+    ir, sig = make_case(orc, 1, 256 * 256, 256, 12)
+    H = orc.uniform_partition(ir, 256)
+    want = orc.convolve_blocks(0, H, sig)
+    for pattern in ([1], [4]):
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, max_blocks=4)
+        conv.filter(H)
+        assert rel_l2(run_bank(conv, sig, 256, pattern), want) <= 1e-5
+        conv.close()
+
+
+def test_full_size_partitions_north_star_shape(gpu, orc):
+    # BASELINE config 5 geometry (B=1024, 2^20 taps -> P=1024, K=1025) on a 2-channel slice, full oracle parity,
+    # plus a size-independent property on more channels: an IR that is a unit impulse at tap d delays the input by d.
+    B, L, NB = 1024, 1 << 20, 12
+    ir, sig = make_case(orc, 2, L, B, NB)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, max_blocks=4)
+    conv.impulse(ir, B)
+    got = run_bank(conv, sig, B, [1, 4, 2])
+    want = orc.convolve_blocks(0, orc.uniform_partition(ir, B), sig)
+    assert rel_l2(got, want) <= 1e-5
+    conv.close()
+
+    C = 16
+    delays = [(c * 65521 + 3) % (NB * B // 2) for c in range(C)]
+    ird = np.zeros((C, L), dtype=np.float32)
+    for c, d in enumerate(delays):
+        ird[c, d] = 1
+    sigd = np.stack([orc.noise(B * NB, 200 + c, np.float32) for c in range(C)])
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, max_blocks=12)
+    conv.impulse(ird, B)
+    out = run_bank(conv, sigd, B, [12])
+    for c, d in enumerate(delays):
+        expect = np.concatenate([np.zeros(d, dtype=np.float32), sigd[c, : B * NB - d]])
+        assert np.allclose(out[c], expect, atol=2e-5), c
+
+
+def test_error_contract(gpu, orc):
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, max_blocks=2)
+    with pytest.raises(RuntimeError):
+        conv.filter(np.zeros((1, 3, 97), dtype=np.complex64))  # B = 96 is not a power of two
+    H = np.zeros((2, 3, 65), dtype=np.complex64)
+    conv.filter(H)
+    with pytest.raises(ValueError):
+        conv(np.zeros((2, 100), dtype=np.float32))  # not a whole number of blocks
+    with pytest.raises(RuntimeError):
+        conv(np.zeros((2, 64 * 3), dtype=np.float32))  # more blocks than max_blocks
+    assert conv.device_bytes() > 0
+
+
+def test_python_convolve_front_end(gpu, orc):
+    # extra/python/test/test.py:25-40: delta patch returns the signal; unsupported modes raise RuntimeError
+    sig = orc.noise(1000, 5, np.float32)
+    for method in ("upols", "upola"):
+        out = gpu.convolve(sig, np.array([1.0], dtype=np.float32), method=method)
+        assert out.shape == (1000,) and np.allclose(out, sig, atol=1e-5)
+        ir = orc.noise(300, 6, np.float32)
+        full = gpu.convolve(sig, ir, method=method)
+        assert full.shape == (1299,)
+        assert rel_l2(full, np.convolve(sig.astype(np.float64), ir.astype(np.float64))) < 1e-5
+    for mode in ("valid", "same"):
+        with pytest.raises(RuntimeError):
+            gpu.convolve(sig, sig, mode=mode)
+    assert gpu.convolve(np.zeros(0, dtype=np.float32), sig).size == 0  # empty-input edge case (direct_convolve_test.cpp)

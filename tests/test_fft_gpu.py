@@ -1,0 +1,202 @@
+"""GPU: parity of the CUDA FFT plans with the oracle (= the reference's fallback plans) through the C ABI.
+Tolerances are north_star's: relative L2 <= 1e-5 (float32), <= 1e-12 (float64)."""
+import numpy as np
+import pytest
+
+from conftest import TOL, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+CASES = [(np.float32, np.complex64), (np.float64, np.complex128)]
+
+
+@pytest.mark.parametrize("real,cplx", CASES)
+def test_c2c_matches_oracle_every_order(gpu, orc, real, cplx):
+    tol = TOL[np.dtype(real).name]
+    for order in range(0, 15):  # order 0 is the identity (the reference itself is undefined there, see oracle dit2_v3)
+        n = 1 << order
+        batch = 5 if order < 12 else 2
+        x = np.stack([orc.noise(n, 1 + b, cplx) for b in range(batch)])
+        plan = gpu.FFTPlan(order, cplx)
+        assert plan.size() == n and plan.order() == order
+        for direction in (gpu.FORWARD, gpu.BACKWARD):
+            got = plan(x.copy(), direction)
+            assert rel_l2(got, orc.fft(x, direction)) <= tol, (order, direction)
+        out = np.zeros_like(x)
+        plan(x, gpu.FORWARD, out=out)  # out-of-place overload (fft/fft.hpp:63-71)
+        assert rel_l2(out, orc.fft(x, -1)) <= tol
+        plan.close()
+
+
+@pytest.mark.parametrize("real,cplx", CASES)
+def test_rfft_irfft_match_oracle_every_order(gpu, orc, real, cplx):
+    tol = TOL[np.dtype(real).name]
+    for order in range(1, 16):
+        n = 1 << order
+        batch = 5 if order < 12 else 2
+        x = np.stack([orc.noise(n, 2 + b, real) for b in range(batch)])
+        plan = gpu.RFFTPlan(order, real)
+        want = orc.rfft(x)
+        spec = plan.rfft(x)
+        assert spec.shape == (batch, n // 2 + 1)
+        assert rel_l2(spec, want) <= tol, order
+        assert rel_l2(plan.irfft(want), orc.irfft(want, n)) <= tol, order
+        plan.close()
+
+
+def test_golden_vectors_from_the_reference(gpu, golden):
+    for tag, real, cplx in (("f32", np.float32, np.complex64), ("f64", np.float64, np.complex128)):
+        tol = TOL[np.dtype(real).name]
+        for order in (1, 2, 3, 4, 5, 8, 10, 11):
+            n = 1 << order
+            from oracle import pyoracle
+
+            x = pyoracle.oracle().noise(n, 1, cplx)
+            plan = gpu.FFTPlan(order, cplx)
+            assert rel_l2(plan(x.copy(), -1), golden[f"c2c/{tag}/{order}/fwd"]) <= tol
+            assert rel_l2(plan(x.copy(), +1), golden[f"c2c/{tag}/{order}/bwd"]) <= tol
+            plan.close()
+            rp = gpu.RFFTPlan(order, real)
+            xr = pyoracle.oracle().noise(n, 2, real)
+            assert rel_l2(rp.rfft(xr[None, :])[0], golden[f"r2c/{tag}/{order}"]) <= tol
+            assert rel_l2(rp.irfft(golden[f"r2c/{tag}/{order}"][None, :].copy())[0], golden[f"c2r/{tag}/{order}"]) <= tol
+            rp.close()
+        # c2r semantics on junk spectra: Im X[0] / Im X[N/2] ignored, N-long rows accepted
+        rp = gpu.RFFTPlan(6, real)
+        junk = pyoracle.oracle().noise(64, 5, cplx)
+        assert rel_l2(rp.irfft(junk[None, :33].copy())[0], golden[f"c2r_junk/{tag}/half"]) <= tol
+        assert rel_l2(rp.irfft(junk[None, :].copy())[0], golden[f"c2r_junk/{tag}/full"]) <= tol
+        rp.close()
+
+
+def test_known_answers(gpu):
+    # fft/rfft_test.cpp:170-186
+    plan = gpu.FFTPlan(2, np.complex64)
+    got = plan(np.array([1, 2, 3, 4], dtype=np.complex64), gpu.FORWARD)
+    assert np.allclose(got, [10, -2 + 2j, -2, -2 - 2j], atol=1e-6)
+    # delta -> all ones, both directions (rfft_test.cpp:132-168, dft_test.cpp:31-46; extra/python/test/test.py:12-19)
+    for order in (1, 2, 5, 9, 12):
+        for cplx in (np.complex64, np.complex128):
+            x = np.zeros(1 << order, dtype=cplx)
+            x[0] = 1
+            p = gpu.FFTPlan(order, cplx)
+            assert np.allclose(p(x.copy(), gpu.FORWARD), 1) and np.allclose(p(x.copy(), gpu.BACKWARD), 1)
+            y = p(p(x.copy(), gpu.FORWARD), gpu.BACKWARD) / x.size
+            assert np.allclose(y, x, atol=1e-6)
+            p.close()
+    # DCT-II of [1..8] through the c2c plan (fft/dct_test.cpp:23-39)
+    x = np.arange(1, 9, dtype=np.float64)
+    v = np.concatenate([x[0::2], x[1::2][::-1]]).astype(np.complex128)
+    p = gpu.FFTPlan(3, np.complex128)
+    V = p(v, gpu.FORWARD)
+    dct = 2 * np.real(np.exp(-1j * np.pi * np.arange(8) / 16) * V)
+    assert np.allclose(dct, [72.0, -25.76929209, 0.0, -2.6938192, 0.0, -0.80361161, 0.0, -0.20280929], atol=1e-6)
+
+
+def test_plan_contract(gpu):
+    # fft_test.cpp:53-130: size/order, throw past max_size, round trips in place / out of place / strided view
+    assert gpu.FFTPlan.max_order() == 27 and gpu.FFTPlan.max_size() == 1 << 27
+    with pytest.raises(RuntimeError):
+        gpu.FFTPlan(gpu.next_order(gpu.FFTPlan.max_size() + 1))
+    from oracle import pyoracle
+
+    orc = pyoracle.oracle()
+    for order in range(2, 15):
+        for cplx, atol in ((np.complex64, 1e-5), (np.complex128, 1e-9)):  # algorithm/allclose.hpp:36-40
+            n = 1 << order
+            x = orc.noise(n, 99, cplx)
+            p = gpu.FFTPlan(order, cplx)
+            y = p(p(x.copy(), gpu.FORWARD), gpu.BACKWARD) / n
+            assert np.allclose(y, x, atol=atol)
+            mat = np.zeros((n, 2), dtype=cplx)  # stride-2 column view of a layout_left matrix (fft_test.cpp:114-128)
+            mat[:, 1] = x
+            p.strided(mat[:, 1], gpu.FORWARD)
+            assert rel_l2(mat[:, 1], orc.fft(x, -1)) <= TOL[np.dtype(cplx).name]
+            assert np.all(mat[:, 0] == 0)
+            p.close()
+
+
+def test_rfft_deinterleave_relation(gpu, orc):
+    # fft/rfft_test.cpp:80-126: rfft(a), rfft(b) == deinterleave(fft(a + ib))
+    for order in (4, 9, 13):
+        n = 1 << order
+        a, b = orc.noise(n, 3, np.float32), orc.noise(n, 4, np.float32)
+        z = gpu.FFTPlan(order, np.complex64)((a + 1j * b).astype(np.complex64), gpu.FORWARD).astype(np.complex128)
+        zc = np.conj(np.roll(z[::-1], 1))
+        rp = gpu.RFFTPlan(order, np.float32)
+        assert rel_l2(rp.rfft(a[None])[0], ((z + zc) / 2)[: n // 2 + 1]) < 1e-5
+        assert rel_l2(rp.rfft(b[None])[0], ((z - zc) / 2j)[: n // 2 + 1]) < 1e-5
+
+
+def test_large_and_ragged_batches(gpu, orc):
+    # batch not a multiple of the transforms-per-CTA packing, and > 65535 transforms
+    for order, batch in ((3, 7), (5, 33), (7, 70001)):
+        n = 1 << order
+        x = orc.noise(n * batch, 5, np.float32).reshape(batch, n)
+        rp = gpu.RFFTPlan(order, np.float32)
+        spec = rp.rfft(x)
+        ref = np.fft.rfft(x.astype(np.float64), axis=1)
+        assert rel_l2(spec, ref) < 1e-6
+        assert rel_l2(rp.irfft(spec), x.astype(np.float64) * n) < 1e-6
+        rp.close()
+
+
+@pytest.mark.parametrize("order", [16, 18, 20])
+def test_long_transforms_four_step(gpu, orc, order):
+    # beyond the oracle's comfortable range for exhaustive checks: one oracle comparison + size-independent properties
+    n = 1 << order
+    x = orc.noise(n, 7, np.complex64)
+    p = gpu.FFTPlan(order, np.complex64)
+    X = p(x.copy(), gpu.FORWARD)
+    assert rel_l2(X, orc.fft(x, -1)) <= 1e-5
+    assert rel_l2(p(X.copy(), gpu.BACKWARD) / n, x) <= 1e-5          # round trip
+    assert abs(np.vdot(X, X).real / n - np.vdot(x, x).real) / np.vdot(x, x).real < 1e-5  # Parseval
+    y = orc.noise(n, 8, np.complex64)
+    lin = p((2 * x + 3j * y).astype(np.complex64), gpu.FORWARD)
+    assert rel_l2(lin, 2 * X.astype(np.complex128) + 3j * p(y.copy(), gpu.FORWARD).astype(np.complex128)) <= 1e-5
+    p.close()
+    xr = orc.noise(n, 9, np.float32)
+    rp = gpu.RFFTPlan(order, np.float32)
+    S = rp.rfft(xr[None])
+    assert rel_l2(S[0], orc.rfft(xr)) <= 1e-5
+    assert rel_l2(rp.irfft(S)[0] / n, xr) <= 1e-5
+    rp.close()
+
+
+def test_long_transform_f64(gpu, orc):
+    order = 15
+    x = orc.noise(1 << order, 7, np.complex128)
+    p = gpu.FFTPlan(order, np.complex128)
+    assert rel_l2(p(x.copy(), gpu.FORWARD), orc.fft(x, -1)) <= 1e-12
+    xr = orc.noise(1 << order, 9, np.float64)
+    rp = gpu.RFFTPlan(order, np.float64)
+    S = rp.rfft(xr[None])
+    assert rel_l2(S[0], orc.rfft(xr)) <= 1e-12
+    assert rel_l2(rp.irfft(S)[0], orc.irfft(orc.rfft(xr), 1 << order)) <= 1e-12
+
+
+def test_device_buffers_and_streams(gpu, orc):
+    import torch
+
+    x = np.stack([orc.noise(4096, 2 + b, np.float32) for b in range(16)])
+    rp = gpu.RFFTPlan(12, np.float32)
+    rp.set_stream(torch.cuda.current_stream())
+    dx = torch.from_numpy(x).cuda()
+    dspec = rp.rfft(dx)
+    torch.cuda.synchronize()
+    assert rel_l2(dspec.cpu().numpy(), orc.rfft(x)) <= 1e-5
+    back = rp.irfft(dspec)
+    torch.cuda.synchronize()
+    assert rel_l2(back.cpu().numpy() / 4096, x) <= 1e-5
+
+
+def test_python_front_end(gpu):
+    # extra/python/test/test.py:12-19
+    for n in (4, 64, 4096):
+        for dt in (np.complex64, np.complex128):
+            x = np.zeros(n, dtype=dt)
+            x[0] = 1
+            y = gpu.ifft(gpu.fft(x))
+            assert y.shape == (n,) and np.allclose(y, x, atol=1e-6)
+    with pytest.raises(RuntimeError):
+        gpu.fft(np.zeros(12, dtype=np.complex64))  # non power of two (main.cpp:137-139)
