@@ -196,6 +196,11 @@ NEO_B200_API int neo_b200_conv_inverse(
 
 NEO_B200_API int neo_b200_conv_set_stream(neo_b200_conv* conv, void* cuda_stream);
 NEO_B200_API int neo_b200_conv_synchronize(neo_b200_conv* conv);
+/* per-phase device time, measured with CUDA events on the handle's stream while enabled: phase_ms[3] = window+r2c+FDL
+ * insert, spectral MAC, c2r+overlap (summed since the last read; the read synchronises the stream);
+ * mac_launches = MAC kernel launches in that span. Measurement aid for benchmarks, no effect on results. */
+NEO_B200_API int neo_b200_conv_profile_enable(neo_b200_conv* conv, int enable);
+NEO_B200_API int neo_b200_conv_profile_read(neo_b200_conv* conv, double* phase_ms, uint64_t* mac_launches);
 /* bytes of device memory held by the handle (filter + FDL + scratch) */
 NEO_B200_API size_t neo_b200_conv_device_bytes(neo_b200_conv const* conv);
 

@@ -87,6 +87,8 @@ SIGNATURES = {
     "neo_b200_conv_inverse": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _i]),
     "neo_b200_conv_set_stream": (_i, [_vp, _vp]),
     "neo_b200_conv_synchronize": (_i, [_vp]),
+    "neo_b200_conv_profile_enable": (_i, [_vp, _i]),
+    "neo_b200_conv_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "neo_b200_conv_device_bytes": (_sz, [_vp]),
 }
 
@@ -340,6 +342,7 @@ class Convolver:
 
     def _create(self, outputs, inputs, block, partitions):
         self.close()
+        self._spectra_view = None
         lo, hi = self.partition_range or (0, 0)
         self.cfg = ConvConfig(self.kind, _DTYPE_CODE[self.real], self.topology, outputs, inputs, block, partitions,
                               self.max_blocks, lo, hi)
@@ -382,6 +385,16 @@ class Convolver:
     def reset(self) -> None:
         _check(library().neo_b200_conv_reset(self._h))
 
+    def profile(self, enable: bool) -> None:
+        _check(library().neo_b200_conv_profile_enable(self._h, int(enable)))
+
+    def profile_read(self):
+        """(ms_r2c, ms_mac, ms_c2r, mac_launches) since the last read; synchronises the stream."""
+        ms = (C.c_double * 3)()
+        n = C.c_uint64(0)
+        _check(library().neo_b200_conv_profile_read(self._h, ms, C.byref(n)))
+        return float(ms[0]), float(ms[1]), float(ms[2]), int(n.value)
+
     def device_bytes(self) -> int:
         return int(library().neo_b200_conv_device_bytes(self._h))
 
@@ -410,6 +423,9 @@ class Convolver:
         """torch view [outputs][blocks][2B] (float32 pairs) of the partial spectra produced by forward()."""
         import torch
 
+        cached = getattr(self, "_spectra_view", None)
+        if cached is not None and cached[0] == blocks:
+            return cached[1]
         ptr, _ = self.spectra_ptr()
         n = int(self.cfg.outputs) * blocks * int(self.cfg.block) * 2
         dt = np.float32 if self.real == "float32" else np.float64
@@ -417,7 +433,9 @@ class Convolver:
         class _Raw:
             __cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(dt).str, "data": (ptr, False), "version": 3}
 
-        return torch.as_tensor(_Raw(), device=f"cuda:{torch.cuda.current_device()}").view(int(self.cfg.outputs), blocks, -1)
+        view = torch.as_tensor(_Raw(), device=f"cuda:{torch.cuda.current_device()}").view(int(self.cfg.outputs), blocks, -1)
+        self._spectra_view = (blocks, view)
+        return view
 
     def inverse(self, spectra, out, first: int, count: int, blocks: int) -> None:
         sp = spectra if isinstance(spectra, int) else _ptr(spectra)

@@ -6,6 +6,7 @@
 
 #include <algorithm>
 #include <memory>
+#include <vector>
 
 namespace neo_b200 {
 
@@ -63,6 +64,52 @@ struct conv_engine
 
     fft_tables<T> tables;
     device_buffer filter, fdl, prev, tail[2], acc, ola_y, stage_in, stage_out, stage_filter;
+
+    // optional per-phase timing with CUDA events on the handle's stream (bench.py's roofline numbers)
+    struct span
+    {
+        cudaEvent_t begin, end;
+    };
+    bool profiling{false};
+    std::vector<span> spans[3];  // 0 r2c + FDL insert, 1 MAC, 2 c2r
+    std::uint64_t mac_launches{0};
+
+    int mark_begin(int phase, cudaStream_t stream)
+    {
+        if (!profiling) { return NEO_B200_OK; }
+        span s{};
+        NEO_CUDA_TRY(cudaEventCreate(&s.begin));
+        NEO_CUDA_TRY(cudaEventCreate(&s.end));
+        NEO_CUDA_TRY(cudaEventRecord(s.begin, stream));
+        spans[phase].push_back(s);
+        return NEO_B200_OK;
+    }
+
+    int mark_end(int phase, cudaStream_t stream)
+    {
+        if (!profiling) { return NEO_B200_OK; }
+        NEO_CUDA_TRY(cudaEventRecord(spans[phase].back().end, stream));
+        return NEO_B200_OK;
+    }
+
+    int read_profile(double* ms, std::uint64_t* launches, cudaStream_t stream)
+    {
+        NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+        for (int p = 0; p < 3; ++p) {
+            ms[p] = 0.0;
+            for (auto& s : spans[p]) {
+                float t = 0.f;
+                NEO_CUDA_TRY(cudaEventElapsedTime(&t, s.begin, s.end));
+                ms[p] += double(t);
+                cudaEventDestroy(s.begin);
+                cudaEventDestroy(s.end);
+            }
+            spans[p].clear();
+        }
+        *launches    = mac_launches;
+        mac_launches = 0;
+        return NEO_B200_OK;
+    }
 
     size_t device_bytes() const
     {
@@ -192,6 +239,7 @@ struct conv_engine
     int forward(T const* in, size_t in_stride, size_t blocks, cudaStream_t stream)
     {
         int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_TRY(mark_begin(0, stream));
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
                 conv_r2c_io<T, LOGM> io{in, in_stride, prev.template as<T>(), fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
@@ -205,6 +253,7 @@ struct conv_engine
             NEO_CUDA_TRY(cudaMemcpy2DAsync(prev.ptr, m * sizeof(T), in + (blocks - 1) * m, in_stride * sizeof(T), m * sizeof(T), cfg.inputs,
                                            cudaMemcpyDeviceToDevice, stream));
         }
+        NEO_TRY(mark_end(0, stream));
 
         mac_geom g{};
         g.m         = m;
@@ -218,14 +267,17 @@ struct conv_engine
         g.acc_plane = cfg.outputs * blocks * size_t(m);
 
         size_t tau = 0;
+        NEO_TRY(mark_begin(1, stream));
         while (tau < blocks) {
             size_t const left = blocks - tau;
             g.tau0            = int(tau);
             g.wp              = int((write_pos + tau) % size_t(ring));
             int const tb      = left >= 16 && sizeof(T) == 4 ? 16 : left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
             NEO_TRY(launch_mac(tb, g, stream));
+            ++mac_launches;
             tau += size_t(tb);
         }
+        NEO_TRY(mark_end(1, stream));
         write_pos = (write_pos + blocks) % size_t(ring);
         return NEO_B200_OK;
     }
@@ -259,6 +311,7 @@ struct conv_engine
         bool const ola = cfg.kind == NEO_B200_UPOLA;
         T* const dst   = ola ? ola_y.template as<T>() : out;
         int status     = NEO_B200_ERR_UNSUPPORTED;
+        NEO_TRY(mark_begin(2, stream));
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
                 conv_c2r_io<T, LOGM> io{spectra, plane, nsplits, int(blocks), dst, out_stride, T(1) / T(2 * m), ola ? 1 : 0};
@@ -272,6 +325,7 @@ struct conv_engine
                                                             tail[tail_flip ^ 1].template as<T>(), out, out_stride, m, int(blocks), first);
             NEO_TRY(check_launch("ola_combine_kernel"));
         }
+        NEO_TRY(mark_end(2, stream));
         return NEO_B200_OK;
     }
 
@@ -509,6 +563,19 @@ int neo_b200_conv_synchronize(neo_b200_conv* conv)
     if (conv == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
     NEO_CUDA_TRY(cudaStreamSynchronize(conv->stream.stream));
     return NEO_B200_OK;
+}
+
+int neo_b200_conv_profile_enable(neo_b200_conv* conv, int enable)
+{
+    if (conv == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    conv->f32.profiling = conv->f64.profiling = (enable != 0);
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_profile_read(neo_b200_conv* conv, double* phase_ms, uint64_t* mac_launches)
+{
+    if (conv == nullptr || phase_ms == nullptr || mac_launches == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    return NEO_CONV_ENGINE(conv, read_profile(phase_ms, mac_launches, conv->stream.stream));
 }
 
 size_t neo_b200_conv_device_bytes(neo_b200_conv const* conv)
