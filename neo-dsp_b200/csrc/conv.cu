@@ -57,6 +57,7 @@ struct conv_engine
     int ring{0};
     int sources{1};
     int splits{1};
+    int logw{0}, nt{1};  // tile-major row layout
     size_t filters{0};  // outputs * sources
     size_t write_pos{0};
     bool has_filter{false};
@@ -126,6 +127,8 @@ struct conv_engine
         ring    = int(c.partition_end + c.max_blocks - 1);
         sources = c.topology == NEO_B200_MATRIX ? int(c.inputs) : 1;
         filters = c.outputs * size_t(sources);
+        logw    = std::min(logb, int(log2_exact(size_t(tile_width<T>()))));
+        nt      = m >> logw;
         NEO_TRY(tables.build(logb, true, stream));
 
         size_t const csz = sizeof(cx<T>);
@@ -171,7 +174,7 @@ struct conv_engine
         for (size_t r0 = 0; r0 < rows; r0 += 65535) {  // gridDim.y <= 65535
             dim3 const grid(unsigned((m + 255) / 256), unsigned(std::min<size_t>(65535, rows - r0)));
             pack_filter_kernel<T><<<grid, 256, 0, stream>>>(h_dev, filter.template as<cx<T>>() + first_filter * parts * m, src_parts, part0,
-                                                            parts, m, r0);
+                                                            parts, m, r0, logw, nt);
             NEO_TRY(check_launch("pack_filter_kernel"));
         }
         return NEO_B200_OK;
@@ -208,7 +211,7 @@ struct conv_engine
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
                 partition_r2c_io<T, LOGM> io{ir_dev, taps, int(cfg.partition_begin), parts,
-                                             filter.template as<cx<T>>() + first_filter * parts * m, 1};
+                                             filter.template as<cx<T>>() + first_filter * parts * m, 1, logw, nt};
                 status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), count * parts, stream);
             }
         });
@@ -243,7 +246,7 @@ struct conv_engine
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
                 conv_r2c_io<T, LOGM> io{in, in_stride, prev.template as<T>(), fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
-                                        cfg.kind == NEO_B200_UPOLA ? 1 : 0};
+                                        cfg.kind == NEO_B200_UPOLA ? 1 : 0, logw, nt};
                 status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), cfg.inputs * blocks, stream);
             }
         });
@@ -257,6 +260,8 @@ struct conv_engine
 
         mac_geom g{};
         g.m         = m;
+        g.logw      = logw;
+        g.nt        = nt;
         g.ring      = ring;
         g.parts     = parts;
         g.age0      = int(cfg.partition_begin);
@@ -272,7 +277,8 @@ struct conv_engine
             size_t const left = blocks - tau;
             g.tau0            = int(tau);
             g.wp              = int((write_pos + tau) % size_t(ring));
-            int const tb      = left >= 16 && sizeof(T) == 4 ? 16 : left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
+            bool const tma    = sizeof(T) == 4 && m >= 128;  // float rows of whole 1 KB tiles: TMA-staged kernel
+            int const tb      = left >= 32 && tma ? 32 : left >= 16 && sizeof(T) == 4 ? 16 : left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
             NEO_TRY(launch_mac(tb, g, stream));
             ++mac_launches;
             tau += size_t(tb);
@@ -292,6 +298,14 @@ struct conv_engine
             fdl_mac_stream_kernel<T><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
             return check_launch("fdl_mac_stream_kernel");
         }
+        if constexpr (sizeof(T) == 4) {
+            if (m >= 128 && tb >= 8) {
+                dim3 const tgrid(unsigned(nt), unsigned(cfg.outputs), unsigned(splits));
+                if (tb == 32) { return launch_tma<32, 8, 3>(tgrid, x, h, a, g, stream); }
+                if (tb == 16) { return launch_tma<16, 8, 3>(tgrid, x, h, a, g, stream); }
+                return launch_tma<8, 8, 3>(tgrid, x, h, a, g, stream);
+            }
+        }
         dim3 const grid(unsigned((m + k_mac_threads - 1) / k_mac_threads), unsigned(cfg.outputs), unsigned(splits));
         switch (tb) {
             case 2: fdl_mac_toeplitz_kernel<T, 2><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g); break;
@@ -302,6 +316,22 @@ struct conv_engine
                 break;
         }
         return check_launch("fdl_mac_toeplitz_kernel");
+    }
+
+    template<int TB, int CH, int STAGES>
+    int launch_tma(dim3 grid, float2 const* x, float2 const* h, float2* a, mac_geom const& g, cudaStream_t stream)
+    {
+        using tc = mac_tma_cfg<TB, CH, STAGES>;
+        if (g.parts % CH == 0) {
+            auto kernel = fdl_mac_tma_kernel<TB, CH, STAGES, false>;
+            NEO_TRY(enable_smem(kernel, tc::SMEM));
+            kernel<<<grid, 128, tc::SMEM, stream>>>(x, h, a, g);
+        } else {
+            auto kernel = fdl_mac_tma_kernel<TB, CH, STAGES, true>;
+            NEO_TRY(enable_smem(kernel, tc::SMEM));
+            kernel<<<grid, 128, tc::SMEM, stream>>>(x, h, a, g);
+        }
+        return check_launch("fdl_mac_tma_kernel");
     }
 
     // c2r + scale + overlap handling of spectra [count][blocks][B] (S partial planes `plane` apart) into out [count][out_stride]

@@ -7,10 +7,12 @@
 //   fdl_mac_*                 the spectral multiply-accumulate                 (K7, K8)
 //   c2r_kernel<conv_c2r_io>   partial-sum gather + c2r + 1/N scale + discard   (K4, K9, K10)
 //
-// HBM layout (all complex rows are B = N/2 elements: bin 0 carries (Re X[0], Re X[B]) because both are real):
-//   fdl    [inputs][R][B]             ring of spectra, R = partition_end + max_blocks - 1 slots, slot(n) = n mod R
-//   filter [outputs*sources][Pl][B]   Pl local partitions, sources = 1 (diagonal) or inputs (matrix)
-//   acc    [S][outputs][T][B]         S partial planes (split over partitions so small banks still fill the GPU)
+// HBM layout. Every spectrum row is B = N/2 complex elements: bin 0 carries (Re X[0], Re X[B]) because both are real.
+// FDL and filter rows are cut into tiles of W elements (1 KB) and stored tile-major, so that the rows one CTA walks
+// (one tile column of one channel) are contiguous and a pipeline stage is ONE bulk copy:
+//   fdl    [inputs][B/W][R][W]             ring of spectra, R = partition_end + max_blocks - 1 slots, slot(n) = n mod R
+//   filter [outputs*sources][B/W][Pl][W]   Pl local partitions, sources = 1 (diagonal) or inputs (matrix)
+//   acc    [S][outputs][T][B]              S partial planes (split over partitions so small banks still fill the GPU)
 #pragma once
 
 #include "fft_kernels.cuh"
@@ -25,9 +27,24 @@ __host__ __device__ __forceinline__ unsigned fdl_filter_index(unsigned write_pos
     return (write_pos + parts - segment) % parts;
 }
 
+// complex elements per 1 KB tile
+template<typename T>
+__host__ __device__ constexpr int tile_width()
+{
+    return 1024 / int(sizeof(cx<T>));
+}
+
+// element offset of (chan, row, k) in a tile-major array with `rows` rows per channel
+__host__ __device__ __forceinline__ size_t tiled_offset(size_t chan, int nt, int logw, size_t rows, size_t row, int k)
+{
+    return (((chan * nt + size_t(k >> logw)) * rows + row) << logw) + size_t(k & ((1 << logw) - 1));
+}
+
 struct mac_geom
 {
     int m;             // complex elements per row (= B)
+    int logw;          // log2 of the tile width W = min(B, tile_width)
+    int nt;            // tiles per row = B / W
     int ring;          // R
     int parts;         // Pl, partitions held by this handle
     int age0;          // age of the first local partition (= partition_begin)
@@ -120,8 +137,13 @@ __global__ void __launch_bounds__(k_mac_threads)
     V a = MV::zero();
     bool const edge = (col == 0);  // this thread owns the packed bin 0
 
-    V const* const frow = reinterpret_cast<V const*>(filter) + size_t(out) * g.sources * g.parts * row_vec + col;
-    V const* const xrow = reinterpret_cast<V const*>(fdl) + col;
+    // tile-major addressing in units of V (VEC elements)
+    int const k0       = col * MV::VEC;
+    int const tile     = k0 >> g.logw;
+    int const tile_vec = (1 << g.logw) / MV::VEC;
+    int const within   = (k0 & ((1 << g.logw) - 1)) / MV::VEC;
+    V const* const fbase = reinterpret_cast<V const*>(filter) + within;
+    V const* const xbase = reinterpret_cast<V const*>(fdl) + within;
 
     for (int v = v0; v < v1; v += k_mac_unroll) {
         V x[k_mac_unroll], h[k_mac_unroll];
@@ -135,8 +157,9 @@ __global__ void __launch_bounds__(k_mac_threads)
                 slot          = slot % g.ring;
                 slot += slot < 0 ? g.ring : 0;
                 int const ch = g.diagonal ? out : src;
-                h[u]         = ld_stream(frow + size_t(vp) * row_vec);
-                x[u]         = ld_stream(xrow + (size_t(ch) * g.ring + slot) * row_vec);
+                size_t const filt = size_t(out) * g.sources + src;
+                h[u]              = ld_stream(fbase + ((filt * g.nt + tile) * g.parts + p) * tile_vec);
+                x[u]              = ld_stream(xbase + ((size_t(ch) * g.nt + tile) * g.ring + slot) * tile_vec);
             } else {
                 h[u] = MV::zero();
                 x[u] = MV::zero();
@@ -184,7 +207,7 @@ __global__ void __launch_bounds__(k_mac_threads)
         if (src != prev_src) {
             // fresh window: pretend a previous chunk at p0 - TB left its lower TB-1 entries behind
             int const ch = g.diagonal ? out : src;
-            xbase        = size_t(ch) * g.ring * g.m + k;
+            xbase        = tiled_offset(size_t(ch), g.nt, g.logw, size_t(g.ring), 0, k);
             int base     = g.wp - g.age0 - p0 + 1;  // d of win[0] of that virtual previous chunk: -(age0 + p0 - TB) - (TB-1)
             base         = base % g.ring;
             base += base < 0 ? g.ring : 0;
@@ -192,7 +215,7 @@ __global__ void __launch_bounds__(k_mac_threads)
             int s   = base;
 #pragma unroll
             for (int i = 0; i < TB - 1; ++i) {
-                win[i] = fdl[xbase + size_t(s) * g.m];
+                win[i] = fdl[xbase + (size_t(s) << g.logw)];
                 s      = (s + 1 == g.ring) ? 0 : s + 1;
             }
             prev_src = src;
@@ -206,15 +229,15 @@ __global__ void __launch_bounds__(k_mac_threads)
             int s = slot_lo;
 #pragma unroll
             for (int i = 0; i < TB; ++i) {
-                win[i] = fdl[xbase + size_t(s) * g.m];
+                win[i] = fdl[xbase + (size_t(s) << g.logw)];
                 s      = (s + 1 == g.ring) ? 0 : s + 1;
             }
         }
-        C const* hrow = filter + ((size_t(out) * g.sources + src) * g.parts + p0) * g.m + k;
+        C const* hrow = filter + tiled_offset(size_t(out) * g.sources + src, g.nt, g.logw, size_t(g.parts), size_t(p0), k);
 #pragma unroll
         for (int pp = 0; pp < TB; ++pp) {
             if (p0 + pp < g.parts) {
-                C const h = __ldcs(hrow + size_t(pp) * g.m);
+                C const h = __ldcs(hrow + (size_t(pp) << g.logw));
 #pragma unroll
                 for (int tau = 0; tau < TB; ++tau) {
                     C const x = win[tau - pp + TB - 1];
@@ -232,6 +255,220 @@ __global__ void __launch_bounds__(k_mac_threads)
         }
     }
     C* dst = acc + size_t(split) * g.acc_plane + (size_t(out) * g.blocks + g.tau0) * g.m + k;
+#pragma unroll
+    for (int tau = 0; tau < TB; ++tau) { dst[size_t(tau) * g.m] = a[tau]; }
+}
+
+// ---- the same Toeplitz MAC for float32 rows of at least one full tile, fed by TMA -------------------------------------------------
+// CTA = 128 threads = one tile column (128 bins, 1 KB per row) of one output. The partition loop advances CH rows per
+// pipeline stage; thanks to the tile-major layout the CH filter rows are one contiguous CH KB block and so are the CH FDL
+// rows (two blocks where the ring wraps), fetched with cp.async.bulk into shared memory and signalled through an mbarrier.
+// STAGES-1 stages are in flight while the FMAs of the current one issue: the loads never sit in registers, so the kernel
+// is bound by FP32 issue (TB large) or HBM (TB small) instead of load latency.
+namespace tma {
+
+__device__ __forceinline__ unsigned smem_addr(void const* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(void* bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_expect_tx(void* bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+
+__device__ __forceinline__ bool mbar_try_wait(void* bar, unsigned parity)
+{
+    unsigned ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_addr(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+
+__device__ __forceinline__ void mbar_wait(void* bar, unsigned parity)
+{
+    while (!mbar_try_wait(bar, parity)) {}
+}
+
+// global -> shared bulk copy (TMA, SASS UBLKCP); bytes and both addresses are multiples of 16
+__device__ __forceinline__ void bulk_g2s(void* dst, void const* src, unsigned bytes, void* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_addr(dst)),
+                 "l"(src), "r"(bytes), "r"(smem_addr(bar))
+                 : "memory");
+}
+
+}  // namespace tma
+
+template<int TB, int CH, int STAGES>
+struct mac_tma_cfg
+{
+    static constexpr int W         = 128;                       // bins per CTA = one float2 tile
+    static constexpr int WARPS     = 4;
+    static constexpr int STAGE_EL  = 2 * CH * W;                // float2 elements per stage: CH filter rows + CH FDL rows
+    static constexpr size_t SMEM   = size_t(STAGES) * STAGE_EL * sizeof(float2) + STAGES * (sizeof(unsigned long long) + sizeof(int));
+};
+
+// RAGGED: the partition count is not a multiple of CH, the last chunk of every source is predicated.
+template<int TB, int CH, int STAGES, bool RAGGED>
+__global__ void __launch_bounds__(128)
+    fdl_mac_tma_kernel(float2 const* __restrict__ fdl, float2 const* __restrict__ filter, float2* __restrict__ acc, mac_geom g)
+{
+    using cfg = mac_tma_cfg<TB, CH, STAGES>;
+    constexpr int W = cfg::W;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float2* const stage_mem        = reinterpret_cast<float2*>(smem_raw);
+    unsigned long long* const full = reinterpret_cast<unsigned long long*>(smem_raw + size_t(STAGES) * cfg::STAGE_EL * sizeof(float2));
+    int* const done                = reinterpret_cast<int*>(full + STAGES);  // warps finished with the stage
+
+    int const tid   = threadIdx.x;
+    int const lane  = tid & 31;
+    int const tile  = blockIdx.x;
+    int const out   = blockIdx.y;
+    int const split = blockIdx.z;
+    bool const edge = (tile == 0 && tid == 0);  // packed bin 0: (Re X0, Re XB) are two real products
+
+    int const chunks_per_src = (g.parts + CH - 1) / CH;
+    int const total          = g.sources * chunks_per_src;
+    int const c0             = int((long long)total * split / g.splits);
+    int const c1             = int((long long)total * (split + 1) / g.splits);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tma::mbar_init(&full[s], 1);
+            done[s] = 0;
+        }
+        tma::fence_mbar_init();
+    }
+    __syncthreads();
+
+    // fill stage (c - c0) % STAGES with chunk c: one bulk copy of filter rows, one (two at the ring wrap) of FDL rows
+    auto issue = [&](int c) {
+        int const src   = c / chunks_per_src;
+        int const p0    = (c - src * chunks_per_src) * CH;
+        int const ch    = g.diagonal ? out : src;
+        int const st    = (c - c0) % STAGES;
+        float2* const h = stage_mem + size_t(st) * cfg::STAGE_EL;
+        float2* const x = h + CH * W;
+        int const hrows = RAGGED ? min(CH, g.parts - p0) : CH;
+        // FDL rows: the CH spectra just older than the previous chunk's, ascending ring slots starting at `lo`
+        int lo = g.wp - g.age0 - p0 - CH + 1;
+        lo %= g.ring;
+        lo += lo < 0 ? g.ring : 0;
+        int const first = min(CH, g.ring - lo);
+        tma::mbar_expect_tx(&full[st], unsigned((hrows + CH) * W * sizeof(float2)));
+        tma::bulk_g2s(h, filter + ((((size_t(out) * g.sources + src) * g.nt + tile) * g.parts + p0) << 7), unsigned(hrows * W * sizeof(float2)),
+                      &full[st]);
+        float2 const* const xrows = fdl + (((size_t(ch) * g.nt + tile) * g.ring) << 7);
+        tma::bulk_g2s(x, xrows + (size_t(lo) << 7), unsigned(first * W * sizeof(float2)), &full[st]);
+        if (first < CH) { tma::bulk_g2s(x + first * W, xrows, unsigned((CH - first) * W * sizeof(float2)), &full[st]); }
+    };
+
+    if (tid == 0) {
+        for (int c = c0; c < c1 && c < c0 + STAGES; ++c) { issue(c); }
+    }
+
+    float2 a[TB];
+#pragma unroll
+    for (int i = 0; i < TB; ++i) { a[i] = make_float2(0.f, 0.f); }
+    float2 win[TB + CH - 1];  // win[i] = X(d0 + i), d0 = -(age0 + p0) - CH + 1 for the chunk being consumed
+
+    int src = c0 / chunks_per_src;
+    int p0  = (c0 - src * chunks_per_src) * CH;
+    bool fresh = true;
+    int st = 0;
+    unsigned parity = 0;
+
+    for (int c = c0; c < c1; ++c) {
+        if (fresh) {
+            // the TB-1 spectra newer than X(-(age0+p0)), straight from global memory (once per source)
+            int const ch = g.diagonal ? out : src;
+            float2 const* const xcol = fdl + (((size_t(ch) * g.nt + tile) * g.ring) << 7) + tid;
+            int s = g.wp - g.age0 - p0 + 1;
+            s %= g.ring;
+            s += s < 0 ? g.ring : 0;
+#pragma unroll
+            for (int i = 0; i < TB - 1; ++i) {
+                win[i] = xcol[size_t(s) << 7];
+                s      = (s + 1 == g.ring) ? 0 : s + 1;
+            }
+            fresh = false;
+        }
+#pragma unroll
+        for (int i = TB - 2; i >= 0; --i) { win[i + CH] = win[i]; }
+
+        tma::mbar_wait(&full[st], parity);
+        float2 const* const h = stage_mem + size_t(st) * cfg::STAGE_EL + tid;
+        float2 const* const x = h + CH * W;
+#pragma unroll
+        for (int i = 0; i < CH; ++i) { win[i] = x[i * W]; }
+
+        if (!edge) {
+#pragma unroll
+            for (int pp = 0; pp < CH; ++pp) {
+                if (!RAGGED || p0 + pp < g.parts) {
+                    float2 const hv = h[pp * W];
+#pragma unroll
+                    for (int tau = 0; tau < TB; ++tau) {
+                        float2 const xv = win[tau - pp + CH - 1];
+                        a[tau].x = fmaf(xv.x, hv.x, a[tau].x);
+                        a[tau].x = fmaf(-xv.y, hv.y, a[tau].x);
+                        a[tau].y = fmaf(xv.x, hv.y, a[tau].y);
+                        a[tau].y = fmaf(xv.y, hv.x, a[tau].y);
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int pp = 0; pp < CH; ++pp) {
+                if (!RAGGED || p0 + pp < g.parts) {
+                    float2 const hv = h[pp * W];
+#pragma unroll
+                    for (int tau = 0; tau < TB; ++tau) {
+                        float2 const xv = win[tau - pp + CH - 1];
+                        a[tau].x = fmaf(xv.x, hv.x, a[tau].x);
+                        a[tau].y = fmaf(xv.y, hv.y, a[tau].y);
+                    }
+                }
+            }
+        }
+
+        // release the stage without a CTA barrier: the last of the four warps to finish refills it
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            int const before = atomicAdd(&done[st], 1);
+            if (before == cfg::WARPS - 1) {
+                done[st] = 0;
+                if (c + STAGES < c1) { issue(c + STAGES); }
+            }
+        }
+        __syncwarp();
+
+        p0 += CH;
+        if (p0 >= g.parts) {
+            p0 = 0;
+            ++src;
+            fresh = true;
+        }
+        if (++st == STAGES) {
+            st = 0;
+            parity ^= 1U;
+        }
+    }
+
+    float2* dst = acc + size_t(split) * g.acc_plane + (size_t(out) * g.blocks + g.tau0) * g.m + tile * W + tid;
 #pragma unroll
     for (int tau = 0; tau < TB; ++tau) { dst[size_t(tau) * g.m] = a[tau]; }
 }
@@ -258,12 +495,13 @@ struct conv_r2c_io
     C* fdl;
     int ring, wp, blocks;
     int overlap_add;   // 0: window = [previous block | block]   1: window = [block | zeros]  (overlap_add.hpp:88-90)
+    int logw, nt;      // tile-major FDL layout
 
     struct row_state
     {
         C const* lo;
         C const* hi;
-        C* dst;
+        C* dst;        // element (tile 0, slot, 0); tiles are ring << logw apart
     };
     __device__ __forceinline__ row_state open(size_t b) const
     {
@@ -273,7 +511,7 @@ struct conv_r2c_io
         T const* cur       = in + ch * in_stride + size_t(tau) * B;
         int slot           = wp + tau;
         slot -= slot >= ring ? ring : 0;
-        C* dst = fdl + (ch * ring + slot) * B;
+        C* dst = fdl + tiled_offset(ch, nt, logw, size_t(ring), size_t(slot), 0);
         if (overlap_add) { return {reinterpret_cast<C const*>(cur), nullptr, dst}; }
         T const* before = tau == 0 ? prev + ch * B : cur - B;
         return {reinterpret_cast<C const*>(before), reinterpret_cast<C const*>(cur), dst};
@@ -284,7 +522,10 @@ struct conv_r2c_io
         if (j < H) { return r.lo[j]; }
         return r.hi != nullptr ? r.hi[j - H] : mk<T>(0, 0);
     }
-    __device__ __forceinline__ void store(row_state const& r, int k, C x) const { r.dst[k] = x; }
+    __device__ __forceinline__ void store(row_state const& r, int k, C x) const
+    {
+        r.dst[((size_t(k >> logw) * ring) << logw) + (k & ((1 << logw) - 1))] = x;
+    }
     __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const { r.dst[0] = mk<T>(dc, nyq); }
 };
 
@@ -361,7 +602,8 @@ struct partition_r2c_io
     size_t taps;
     int part0, parts;    // partitions [part0, part0 + parts) are produced
     C* out;
-    int packed;          // 1: convolver layout [f][parts][B] (bin 0 packed), 0: reference layout [f][parts][B+1]
+    int packed;          // 1: convolver layout [f][B/W][parts][W] (bin 0 packed), 0: reference layout [f][parts][B+1]
+    int logw, nt;
 
     struct row_state
     {
@@ -376,14 +618,19 @@ struct partition_r2c_io
         size_t const p     = part0 + (b - f * parts);
         long const left    = long(taps) - long(p * B);
         long const count   = left < long(B) ? left : long(B);
-        return {ir + f * taps + p * B, count, out + b * (packed ? B : B + 1)};
+        C* dst = packed ? out + tiled_offset(f, nt, logw, size_t(parts), b - f * parts, 0) : out + b * (B + 1);
+        return {ir + f * taps + p * B, count, dst};
     }
     __device__ __forceinline__ C load(row_state const& r, int j) const
     {
         long const i = 2L * j;
         return mk<T>(i < r.count ? r.src[i] : T(0), i + 1 < r.count ? r.src[i + 1] : T(0));
     }
-    __device__ __forceinline__ void store(row_state const& r, int k, C x) const { r.dst[k] = x; }
+    __device__ __forceinline__ void store(row_state const& r, int k, C x) const
+    {
+        if (packed) { r.dst[((size_t(k >> logw) * parts) << logw) + (k & ((1 << logw) - 1))] = x; }
+        else { r.dst[k] = x; }
+    }
     __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const
     {
         if (packed) {
@@ -399,7 +646,7 @@ struct partition_r2c_io
 template<typename T>
 __global__ void __launch_bounds__(256)
     pack_filter_kernel(cx<T> const* __restrict__ h, cx<T>* __restrict__ packed, size_t src_parts, int part0, int parts, int block,
-                       size_t row0)
+                       size_t row0, int logw, int nt)
 {
     size_t const row = row0 + blockIdx.y;  // f * parts + p
     int const k      = blockIdx.x * blockDim.x + threadIdx.x;
@@ -409,7 +656,7 @@ __global__ void __launch_bounds__(256)
     cx<T> const* src = h + (f * src_parts + p) * (size_t(block) + 1);
     cx<T> v          = src[k];
     if (k == 0) { v.y = src[block].x; }
-    packed[row * block + k] = v;
+    packed[tiled_offset(f, nt, logw, size_t(parts), row - f * parts, k)] = v;
 }
 
 __global__ void fdl_index_kernel(unsigned parts, unsigned calls, unsigned* write_pos, unsigned* pairs);
