@@ -82,7 +82,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def __enter__(self):
         if self.nv is not None:
@@ -373,7 +373,7 @@ def run_ours(args):
         with open(tpath) as f:
             traffic = json.load(f).get(f"fdl_mac_T{T}_G{world}")
     roofline = {
-        "kernel": "fdl_mac_stream_kernel<float>" if T == 1 else f"fdl_mac_toeplitz_kernel<float,{T}>",
+        "kernel": "fdl_mac_stream_kernel<float>" if T == 1 else f"fdl_mac_tma_kernel<{T if T in (8, 16, 32) else 'mixed'},8,3>",
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
@@ -448,7 +448,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--blocks", type=int, default=16, help="blocks per call T (1 = the reference's streaming call)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])

@@ -1,0 +1,345 @@
+// neo_b200.hpp -- C++ facade over the C ABI (neo_b200.h) that satisfies the reference's plan / convolver duck types, so the
+// B200 backend can sit behind neo's compile-time aliases exactly like its IPP / MKL / vDSP backends do
+// (src/neo/fft/fft.hpp:36-52, src/neo/fft/rfft.hpp:15-23, src/neo/convolution/dense_convolver.hpp:20-25).
+//
+// The classes are templates over "any rank-1 / rank-2 view with the mdspan interface" (data_handle(), extent(i), stride(i)):
+// Kokkos::mdspan (what neo uses), std::mdspan and cuda::std::mdspan all qualify, and so does the tiny span in the tests.
+// Contiguous views go straight to the library; strided ones are staged through a contiguous buffer, the pattern of
+// src/neo/fft/backend/ipp.hpp:150-158. Construction failures throw std::runtime_error like c2c_dit2_plan.hpp:98-104.
+//
+// Host code only: no CUDA headers are needed to compile against this file.
+#pragma once
+
+#include "neo_b200.h"
+
+#include <complex>
+#include <cstddef>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <utility>
+#include <vector>
+
+namespace neo::b200 {
+
+namespace detail {
+
+template<typename Float>
+inline constexpr int dtype_of = std::is_same_v<Float, double> ? NEO_B200_F64 : NEO_B200_F32;
+
+inline auto check(int status) -> void
+{
+    if (status != NEO_B200_OK) { throw std::runtime_error{std::string{"neo_b200: "} + neo_b200_last_error()}; }
+}
+
+// neo::fft::direction is `enum struct direction : int { forward = -1, backward = 1 }` (fft/direction.hpp:8-12); any enum or
+// integer with those values is accepted so that this header does not depend on neo's.
+template<typename Direction>
+constexpr auto direction_value(Direction dir) noexcept -> int
+{
+    return static_cast<int>(dir) < 0 ? NEO_B200_FORWARD : NEO_B200_BACKWARD;
+}
+
+template<typename Complex>
+using real_of = typename Complex::value_type;
+
+template<typename View>
+using element_of = std::remove_cv_t<typename View::element_type>;
+
+template<typename View>
+auto is_contiguous(View const& v) noexcept -> bool
+{
+    return v.extent(0) <= 1 || v.stride(0) == 1;
+}
+
+}  // namespace detail
+
+/// neo::fft::from_order_tag look-alike (fft/order.hpp:17-25); any tag type is accepted by the constructors.
+struct from_order_tag
+{
+    explicit from_order_tag() = default;
+};
+inline constexpr auto from_order = from_order_tag{};
+
+/// Drop-in for neo::fft::fft_plan<Complex> (fft/reference/c2c_dit2_plan.hpp:22-104): in-place `plan(x, dir)`, unnormalised,
+/// plus the optional out-of-place overload that fft/fft.hpp:63-71 looks for. Complex = std::complex<T> or
+/// neo::scalar_complex<T> (both interleaved [re, im]).
+template<typename Complex>
+struct fft_plan
+{
+    using value_type = Complex;
+    using size_type  = std::size_t;
+    using real_type  = detail::real_of<Complex>;
+
+    template<typename Tag>
+    fft_plan(Tag /*from_order*/, size_type order)
+    {
+        detail::check(neo_b200_fft_plan_create(&_plan, order, detail::dtype_of<real_type>));
+    }
+
+    fft_plan(fft_plan const&)                    = delete;
+    auto operator=(fft_plan const&) -> fft_plan& = delete;
+    fft_plan(fft_plan&& other) noexcept : _plan{std::exchange(other._plan, nullptr)}, _staging{std::move(other._staging)} {}
+    auto operator=(fft_plan&& other) noexcept -> fft_plan&
+    {
+        std::swap(_plan, other._plan);
+        std::swap(_staging, other._staging);
+        return *this;
+    }
+    ~fft_plan() { neo_b200_fft_plan_destroy(_plan); }
+
+    [[nodiscard]] static constexpr auto max_order() noexcept -> size_type { return 27; }  // c2c_dit2_plan.hpp:59-62
+    [[nodiscard]] static constexpr auto max_size() noexcept -> size_type { return size_type(1) << max_order(); }
+
+    [[nodiscard]] auto order() const noexcept -> size_type { return neo_b200_fft_plan_order(_plan); }
+    [[nodiscard]] auto size() const noexcept -> size_type { return neo_b200_fft_plan_size(_plan); }
+
+    template<typename Vec, typename Direction>
+    auto operator()(Vec x, Direction dir) -> void
+    {
+        static_assert(std::is_same_v<detail::element_of<Vec>, Complex>);
+        auto const d = detail::direction_value(dir);
+        if (detail::is_contiguous(x)) {
+            detail::check(neo_b200_fft_exec(_plan, x.data_handle(), x.data_handle(), 1, d, NEO_B200_HOST));
+        } else {
+            auto const s = static_cast<std::ptrdiff_t>(x.stride(0));
+            detail::check(neo_b200_fft_exec_strided(_plan, x.data_handle(), s, x.data_handle(), s, d));
+        }
+    }
+
+    template<typename InVec, typename OutVec, typename Direction>
+    auto operator()(InVec in, OutVec out, Direction dir) -> void
+    {
+        auto const d = detail::direction_value(dir);
+        if (detail::is_contiguous(in) && detail::is_contiguous(out)) {
+            detail::check(neo_b200_fft_exec(_plan, in.data_handle(), out.data_handle(), 1, d, NEO_B200_HOST));
+        } else {
+            detail::check(neo_b200_fft_exec_strided(_plan, in.data_handle(), static_cast<std::ptrdiff_t>(in.stride(0)),
+                                                    out.data_handle(), static_cast<std::ptrdiff_t>(out.stride(0)), d));
+        }
+    }
+
+    /// batched extension: `batch` contiguous transforms [batch][size()], host or device memory
+    auto batched(Complex const* in, Complex* out, size_type batch, int direction, int memspace = NEO_B200_HOST) -> void
+    {
+        detail::check(neo_b200_fft_exec(_plan, in, out, batch, direction, memspace));
+    }
+
+private:
+    neo_b200_fft_plan* _plan{nullptr};
+    std::vector<Complex> _staging;
+};
+
+/// Drop-in for neo::fft::rfft_plan<Float, Complex> (fft/fallback/fallback_rfft_plan.hpp:15-61): two call operators told apart
+/// by element type, real -> complex (N/2+1 bins written) and complex -> real (unnormalised).
+template<typename Float, typename Complex = std::complex<Float>>
+struct rfft_plan
+{
+    using real_type    = Float;
+    using complex_type = Complex;
+    using size_type    = std::size_t;
+
+    template<typename Tag>
+    rfft_plan(Tag /*from_order*/, size_type order)
+    {
+        detail::check(neo_b200_rfft_plan_create(&_plan, order, detail::dtype_of<Float>));
+    }
+
+    rfft_plan(rfft_plan const&)                    = delete;
+    auto operator=(rfft_plan const&) -> rfft_plan& = delete;
+    rfft_plan(rfft_plan&& other) noexcept
+        : _plan{std::exchange(other._plan, nullptr)}
+        , _real{std::move(other._real)}
+        , _cplx{std::move(other._cplx)}
+    {}
+    auto operator=(rfft_plan&& other) noexcept -> rfft_plan&
+    {
+        std::swap(_plan, other._plan);
+        std::swap(_real, other._real);
+        std::swap(_cplx, other._cplx);
+        return *this;
+    }
+    ~rfft_plan() { neo_b200_rfft_plan_destroy(_plan); }
+
+    [[nodiscard]] auto order() const noexcept -> size_type { return neo_b200_rfft_plan_order(_plan); }
+    [[nodiscard]] auto size() const noexcept -> size_type { return neo_b200_rfft_plan_size(_plan); }
+
+    template<typename InVec, typename OutVec>
+        requires(std::is_same_v<detail::element_of<InVec>, Float> && std::is_same_v<detail::element_of<OutVec>, Complex>)
+    auto operator()(InVec in, OutVec out) -> void
+    {
+        auto const n    = size();
+        auto const bins = n / 2 + 1;
+        Float const* src = in.data_handle();
+        if (!detail::is_contiguous(in)) {
+            _real.resize(n);
+            for (size_type i = 0; i < n; ++i) { _real[i] = in[i]; }
+            src = _real.data();
+        }
+        if (detail::is_contiguous(out)) {
+            detail::check(neo_b200_rfft_exec(_plan, src, out.data_handle(), 1, NEO_B200_HOST));
+        } else {
+            _cplx.resize(bins);
+            detail::check(neo_b200_rfft_exec(_plan, src, _cplx.data(), 1, NEO_B200_HOST));
+            for (size_type i = 0; i < bins; ++i) { out[i] = _cplx[i]; }
+        }
+    }
+
+    template<typename InVec, typename OutVec>
+        requires(std::is_same_v<detail::element_of<InVec>, Complex> && std::is_same_v<detail::element_of<OutVec>, Float>)
+    auto operator()(InVec in, OutVec out) -> void
+    {
+        auto const n    = size();
+        auto const bins = n / 2 + 1;
+        Complex const* src = in.data_handle();
+        auto row          = static_cast<size_type>(in.extent(0));  // callers may hand N bins (overlap_save.hpp:57,107)
+        if (!detail::is_contiguous(in)) {
+            _cplx.resize(bins);
+            for (size_type i = 0; i < bins; ++i) { _cplx[i] = in[i]; }
+            src = _cplx.data();
+            row = bins;
+        }
+        if (detail::is_contiguous(out)) {
+            detail::check(neo_b200_irfft_exec(_plan, src, row, out.data_handle(), 1, NEO_B200_HOST));
+        } else {
+            _real.resize(n);
+            detail::check(neo_b200_irfft_exec(_plan, src, row, _real.data(), 1, NEO_B200_HOST));
+            for (size_type i = 0; i < n; ++i) { out[i] = _real[i]; }
+        }
+    }
+
+    /// batched extensions: [batch][N] reals <-> [batch][N/2+1] complex, host or device memory
+    auto rfft_batched(Float const* in, Complex* out, size_type batch, int memspace = NEO_B200_HOST) -> void
+    {
+        detail::check(neo_b200_rfft_exec(_plan, in, out, batch, memspace));
+    }
+    auto irfft_batched(Complex const* in, size_type row_len, Float* out, size_type batch, int memspace = NEO_B200_HOST) -> void
+    {
+        detail::check(neo_b200_irfft_exec(_plan, in, row_len, out, batch, memspace));
+    }
+
+private:
+    neo_b200_rfft_plan* _plan{nullptr};
+    std::vector<Float> _real;
+    std::vector<Complex> _cplx;
+};
+
+/// neo::convolution::uniform_partition (convolution/uniform_partition.hpp:13-26): ir[C][L] -> [C][P][B+1] into `out`
+template<typename Float>
+inline auto uniform_partition(Float const* ir, std::size_t channels, std::size_t taps, std::size_t block, std::complex<Float>* out)
+    -> std::size_t
+{
+    detail::check(neo_b200_uniform_partition(ir, channels, taps, block, out, detail::dtype_of<Float>, NEO_B200_HOST));
+    return neo_b200_num_partitions(taps, block);
+}
+
+/// A bank of partitioned convolvers: what one GPU handle really is. `filter` takes H[outputs][P][B+1]
+/// (or [outputs][inputs][P][B+1] for the matrix topology); `process` runs T blocks for every channel.
+template<typename Float, int Kind>
+struct convolver_bank
+{
+    using real_type    = Float;
+    using complex_type = std::complex<Float>;
+    using size_type    = std::size_t;
+
+    convolver_bank() = default;
+    convolver_bank(convolver_bank const&)                    = delete;
+    auto operator=(convolver_bank const&) -> convolver_bank& = delete;
+    convolver_bank(convolver_bank&& other) noexcept : _conv{std::exchange(other._conv, nullptr)}, _cfg{other._cfg} {}
+    auto operator=(convolver_bank&& other) noexcept -> convolver_bank&
+    {
+        std::swap(_conv, other._conv);
+        std::swap(_cfg, other._cfg);
+        return *this;
+    }
+    ~convolver_bank() { neo_b200_conv_destroy(_conv); }
+
+    auto filter(complex_type const* h, size_type outputs, size_type inputs, size_type partitions, size_type bins, int topology,
+                size_type max_blocks = 1, int memspace = NEO_B200_HOST) -> void
+    {
+        neo_b200_conv_destroy(std::exchange(_conv, nullptr));
+        _cfg            = neo_b200_conv_config{};
+        _cfg.kind       = Kind;
+        _cfg.dtype      = detail::dtype_of<Float>;
+        _cfg.topology   = topology;
+        _cfg.outputs    = outputs;
+        _cfg.inputs     = inputs;
+        _cfg.block      = bins - 1;
+        _cfg.partitions = partitions;
+        _cfg.max_blocks = max_blocks;
+        detail::check(neo_b200_conv_create(&_conv, &_cfg));
+        detail::check(neo_b200_conv_set_filter(_conv, h, memspace));
+    }
+
+    auto process(Float const* in, Float* out, size_type blocks, int memspace = NEO_B200_HOST) -> void
+    {
+        detail::check(neo_b200_conv_process(_conv, in, out, blocks, memspace));
+    }
+
+    [[nodiscard]] auto block_size() const noexcept -> size_type { return _cfg.block; }
+    [[nodiscard]] auto handle() const noexcept -> neo_b200_conv* { return _conv; }
+
+private:
+    neo_b200_conv* _conv{nullptr};
+    neo_b200_conv_config _cfg{};
+};
+
+/// Drop-in for neo::convolution::upols_convolver<Complex> / upola_convolver<Complex>
+/// (convolution/uniform_partitioned_convolver.hpp:14-65): default constructible, `filter(H[P][K])` deep-copies the
+/// partitions and resets all state, `operator()(block[B])` processes one block in place. One instance = one channel, as in
+/// extra/cli/src/convolver.cpp:37-50; use convolver_bank to run many channels per call.
+template<typename Complex, int Kind>
+struct uniform_partitioned_convolver
+{
+    using value_type = Complex;
+    using real_type  = detail::real_of<Complex>;
+
+    uniform_partitioned_convolver() = default;
+
+    template<typename Mat, typename... Ignored>
+    auto filter(Mat h, Ignored... /*args*/) -> void
+    {
+        static_assert(std::is_same_v<detail::element_of<Mat>, Complex>);
+        auto const parts = static_cast<std::size_t>(h.extent(0));
+        auto const bins  = static_cast<std::size_t>(h.extent(1));
+        auto const* ptr  = reinterpret_cast<std::complex<real_type> const*>(h.data_handle());
+        if (h.stride(1) != 1 || static_cast<std::size_t>(h.stride(0)) != bins) {
+            _copy.resize(parts * bins);
+            for (std::size_t p = 0; p < parts; ++p) {
+                for (std::size_t k = 0; k < bins; ++k) {
+                    auto const v        = h(p, k);
+                    _copy[p * bins + k] = {v.real(), v.imag()};
+                }
+            }
+            ptr = _copy.data();
+        }
+        _bank.filter(ptr, 1, 1, parts, bins, NEO_B200_DIAGONAL);
+    }
+
+    template<typename Vec>
+    auto operator()(Vec block) -> void
+    {
+        static_assert(std::is_same_v<detail::element_of<Vec>, real_type>);
+        auto const n = static_cast<std::size_t>(block.extent(0));
+        if (detail::is_contiguous(block)) {
+            _bank.process(block.data_handle(), block.data_handle(), 1);
+        } else {
+            _tmp.resize(n);
+            for (std::size_t i = 0; i < n; ++i) { _tmp[i] = block[i]; }
+            _bank.process(_tmp.data(), _tmp.data(), 1);
+            for (std::size_t i = 0; i < n; ++i) { block[i] = _tmp[i]; }
+        }
+    }
+
+private:
+    convolver_bank<real_type, Kind> _bank;
+    std::vector<std::complex<real_type>> _copy;
+    std::vector<real_type> _tmp;
+};
+
+template<typename Complex>
+using upols_convolver = uniform_partitioned_convolver<Complex, NEO_B200_UPOLS>;
+template<typename Complex>
+using upola_convolver = uniform_partitioned_convolver<Complex, NEO_B200_UPOLA>;
+
+}  // namespace neo::b200

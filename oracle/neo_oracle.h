@@ -6,6 +6,10 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#ifdef __cplusplus
+extern "C" {
+#endif
+
 size_t oracle_bit_ceil(size_t x);
 size_t oracle_next_order(size_t n);
 void oracle_bitrev_table(size_t order, uint32_t* table);
@@ -31,5 +35,9 @@ void oracle_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, 
 
 NEO_ORACLE_DECLARE(float, f32)
 NEO_ORACLE_DECLARE(double, f64)
+
+#ifdef __cplusplus
+}
+#endif
 
 #endif

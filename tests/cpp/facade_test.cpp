@@ -1,0 +1,219 @@
+// facade_test.cpp -- the reference's own plan / convolver tests, restated against the C++ facade (include/neo_b200.hpp).
+// Views are cuda::std::mdspan (same interface as the Kokkos::mdspan neo uses). Needs a GPU; run by tests/test_cpp_facade.py.
+//
+// Mirrors: fft/fft_test.cpp:53-130 (size/order, throw past max_size, round trips in place / out of place / strided view),
+//          fft/rfft_test.cpp:39-62,170-186 (round trip, FFT([1,2,3,4]) known answer),
+//          convolution/uniform_partitioned_convolver_test.cpp:35-75 (identity filter), plus oracle parity.
+#include "../../include/neo_b200.hpp"
+#include "../../oracle/neo_oracle.h"
+
+#include <cuda/std/array>
+#include <cuda/std/mdspan>
+
+#include <cmath>
+#include <complex>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+namespace stdex = cuda::std;
+
+template<typename T>
+using vec = stdex::mdspan<T, stdex::dextents<std::size_t, 1>>;
+template<typename T>
+using strided_vec = stdex::mdspan<T, stdex::dextents<std::size_t, 1>, stdex::layout_stride>;
+template<typename T>
+using mat = stdex::mdspan<T, stdex::dextents<std::size_t, 2>>;
+
+enum struct direction : int
+{
+    forward  = -1,
+    backward = 1,
+};
+
+static int failures = 0;
+#define REQUIRE(cond)                                                                                                  \
+    do {                                                                                                               \
+        if (!(cond)) {                                                                                                 \
+            std::printf("FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond);                                              \
+            ++failures;                                                                                                \
+        }                                                                                                              \
+    } while (0)
+
+template<typename A, typename B>
+static auto rel_l2(A const& got, B const& want) -> double
+{
+    double num = 0, den = 0;
+    for (std::size_t i = 0; i < want.size(); ++i) {
+        num += std::norm(std::complex<double>(got[i]) - std::complex<double>(want[i]));
+        den += std::norm(std::complex<double>(want[i]));
+    }
+    return std::sqrt(num / (den > 0 ? den : 1));
+}
+
+template<typename Float>
+static auto noise(std::size_t n, unsigned seed) -> std::vector<Float>
+{
+    auto v = std::vector<Float>(n);
+    if constexpr (std::is_same_v<Float, float>) { oracle_noise_f32(n, seed, v.data()); }
+    else { oracle_noise_f64(n, seed, v.data()); }
+    return v;
+}
+
+template<typename Float>
+static auto test_fft_plan() -> void
+{
+    using Complex = std::complex<Float>;
+    using Plan    = neo::b200::fft_plan<Complex>;
+    auto const tol = std::is_same_v<Float, float> ? 1e-5 : 1e-12;
+
+    // fft_test.cpp:62-67
+    bool threw = false;
+    try {
+        auto p = Plan{neo::b200::from_order, neo_b200_next_order(Plan::max_size() + 1)};
+    } catch (std::runtime_error const&) {
+        threw = true;
+    }
+    REQUIRE(threw);
+
+    for (std::size_t order = 2; order <= 14; ++order) {
+        auto plan = Plan{neo::b200::from_order, order};
+        REQUIRE(plan.order() == order);
+        REQUIRE(plan.size() == (std::size_t(1) << order));
+        auto const n = plan.size();
+
+        auto raw  = noise<Float>(2 * n, 1);
+        auto orig = std::vector<Complex>(n);
+        for (std::size_t i = 0; i < n; ++i) { orig[i] = {raw[2 * i], raw[2 * i + 1]}; }
+
+        // oracle parity, in place
+        auto want = raw;
+        if constexpr (std::is_same_v<Float, float>) { oracle_fft_c2c_f32(order, want.data(), -1); }
+        else { oracle_fft_c2c_f64(order, want.data(), -1); }
+        auto x = orig;
+        plan(vec<Complex>{x.data(), n}, direction::forward);
+        auto wantc = std::vector<Complex>(n);
+        for (std::size_t i = 0; i < n; ++i) { wantc[i] = {want[2 * i], want[2 * i + 1]}; }
+        REQUIRE(rel_l2(x, wantc) <= tol);
+
+        // round trip in place (fft_test.cpp:79-91)
+        plan(vec<Complex>{x.data(), n}, direction::backward);
+        for (auto& v : x) { v /= Float(n); }
+        REQUIRE(rel_l2(x, orig) <= tol);
+
+        // out of place (fft_test.cpp:93-110)
+        auto y = std::vector<Complex>(n);
+        plan(vec<Complex const>{orig.data(), n}, vec<Complex>{y.data(), n}, direction::forward);
+        REQUIRE(rel_l2(y, wantc) <= tol);
+
+        // stride-2 view (fft_test.cpp:114-128)
+        auto wide = std::vector<Complex>(2 * n, Complex{});
+        for (std::size_t i = 0; i < n; ++i) { wide[2 * i + 1] = orig[i]; }
+        auto const map = stdex::layout_stride::mapping<stdex::dextents<std::size_t, 1>>{stdex::dextents<std::size_t, 1>{n}, cuda::std::array<std::size_t, 1>{2}};
+        plan(strided_vec<Complex>{wide.data() + 1, map}, direction::forward);
+        auto col = std::vector<Complex>(n);
+        bool untouched = true;
+        for (std::size_t i = 0; i < n; ++i) {
+            col[i]    = wide[2 * i + 1];
+            untouched = untouched && wide[2 * i] == Complex{};
+        }
+        REQUIRE(rel_l2(col, wantc) <= tol);
+        REQUIRE(untouched);
+    }
+}
+
+template<typename Float>
+static auto test_rfft_plan() -> void
+{
+    using Complex  = std::complex<Float>;
+    auto const tol = std::is_same_v<Float, float> ? 1e-5 : 1e-12;
+    for (std::size_t order = 2; order <= 14; ++order) {
+        auto plan    = neo::b200::rfft_plan<Float>{neo::b200::from_order, order};
+        auto const n = plan.size();
+        REQUIRE(plan.order() == order);
+        auto sig  = noise<Float>(n, 2);
+        auto spec = std::vector<Complex>(n);  // N-long buffer like overlap_save.hpp:57
+        plan(vec<Float const>{sig.data(), n}, vec<Complex>{spec.data(), n});
+        auto want = std::vector<Float>(2 * n);
+        if constexpr (std::is_same_v<Float, float>) { oracle_rfft_f32(order, sig.data(), want.data()); }
+        else { oracle_rfft_f64(order, sig.data(), want.data()); }
+        auto wantc = std::vector<Complex>(n / 2 + 1), gotc = std::vector<Complex>(n / 2 + 1);
+        for (std::size_t i = 0; i <= n / 2; ++i) {
+            wantc[i] = {want[2 * i], want[2 * i + 1]};
+            gotc[i]  = spec[i];
+        }
+        REQUIRE(rel_l2(gotc, wantc) <= tol);
+        auto back = std::vector<Float>(n);
+        plan(vec<Complex const>{spec.data(), n}, vec<Float>{back.data(), n});  // unnormalised
+        for (auto& v : back) { v /= Float(n); }
+        REQUIRE(rel_l2(back, sig) <= tol);
+    }
+    // rfft_test.cpp:170-186: FFT([1,2,3,4]) = [10, -2+2i, -2, -2-2i]
+    auto plan = neo::b200::fft_plan<Complex>{neo::b200::from_order, 2};
+    auto x    = std::vector<Complex>{{1, 0}, {2, 0}, {3, 0}, {4, 0}};
+    plan(vec<Complex>{x.data(), 4}, direction::forward);
+    auto const kat = std::vector<Complex>{{10, 0}, {-2, 2}, {-2, 0}, {-2, -2}};
+    REQUIRE(rel_l2(x, kat) <= 1e-6);
+}
+
+template<typename Float, template<typename> class Convolver, int OracleKind>
+static auto test_convolver() -> void
+{
+    using Complex  = std::complex<Float>;
+    auto const tol = std::is_same_v<Float, float> ? 1e-5 : 1e-12;
+    // identity filter: uniform_partitioned_convolver_test.cpp:35-75
+    for (std::size_t block : {128U, 256U, 512U, 1024U}) {
+        auto const bins = block + 1;
+        auto h          = std::vector<Complex>(3 * bins, Complex{});
+        for (std::size_t k = 0; k < bins; ++k) { h[k] = {1, 0}; }
+        auto conv = Convolver<Complex>{};
+        conv.filter(mat<Complex const>{h.data(), 3, bins});
+        auto sig = noise<Float>(block * 20, 7);
+        auto out = sig;
+        for (std::size_t b = 0; b < 20; ++b) { conv(vec<Float>{out.data() + b * block, block}); }
+        REQUIRE(rel_l2(out, sig) <= 1e-5);
+    }
+    // oracle parity with a real impulse response, filter swapped once (plugin does: DenseConvolution.cpp:78-108)
+    std::size_t const block = 128, taps = 1000, nblocks = 16;
+    auto conv = Convolver<Complex>{};
+    for (unsigned seed : {11U, 31U}) {
+        auto ir    = noise<Float>(taps, seed);
+        auto parts = neo_b200_num_partitions(taps, block);
+        auto h     = std::vector<Complex>(parts * (block + 1));
+        neo::b200::uniform_partition(ir.data(), 1, taps, block, h.data());
+        conv.filter(mat<Complex const>{h.data(), parts, block + 1});
+        auto sig = noise<Float>(block * nblocks, 13);
+        auto got = sig, want = sig;
+        for (std::size_t b = 0; b < nblocks; ++b) { conv(vec<Float>{got.data() + b * block, block}); }
+        if constexpr (std::is_same_v<Float, float>) {
+            auto* o = oracle_conv_create_f32(OracleKind);
+            oracle_conv_filter_f32(o, reinterpret_cast<float const*>(h.data()), parts, block + 1);
+            for (std::size_t b = 0; b < nblocks; ++b) { oracle_conv_process_f32(o, want.data() + b * block, block); }
+            oracle_conv_destroy_f32(o);
+        } else {
+            auto* o = oracle_conv_create_f64(OracleKind);
+            oracle_conv_filter_f64(o, reinterpret_cast<double const*>(h.data()), parts, block + 1);
+            for (std::size_t b = 0; b < nblocks; ++b) { oracle_conv_process_f64(o, want.data() + b * block, block); }
+            oracle_conv_destroy_f64(o);
+        }
+        REQUIRE(rel_l2(got, want) <= tol);
+    }
+}
+
+int main()
+{
+    if (neo_b200_device_count() < 1) {
+        std::printf("facade_test: no CUDA device (no CPU fallback exists)\n");
+        return 2;
+    }
+    test_fft_plan<float>();
+    test_fft_plan<double>();
+    test_rfft_plan<float>();
+    test_rfft_plan<double>();
+    test_convolver<float, neo::b200::upols_convolver, 0>();
+    test_convolver<float, neo::b200::upola_convolver, 1>();
+    test_convolver<double, neo::b200::upols_convolver, 0>();
+    test_convolver<double, neo::b200::upola_convolver, 1>();
+    std::printf(failures == 0 ? "facade_test: all passed\n" : "facade_test: %d FAILED\n", failures);
+    return failures == 0 ? 0 : 1;
+}

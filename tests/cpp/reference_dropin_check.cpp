@@ -1,0 +1,57 @@
+// reference_dropin_check.cpp -- COMPILE-ONLY proof that the facade satisfies the reference's duck types: neo's own free functions
+// (fft/fft.hpp:56-90, fft/rfft.hpp:28-39) and its mdspan vocabulary are instantiated with the neo::b200 classes.
+// Built only where /root/reference exists (tests/cpp/Makefile), against the unmodified headers + oracle/shim.
+#include <neo/complex.hpp>
+#include <neo/container/mdspan.hpp>
+#include <neo/fft.hpp>
+
+#include "../../include/neo_b200.hpp"
+
+template<typename Complex>
+auto instantiate_c2c() -> void
+{
+    auto plan = neo::b200::fft_plan<Complex>{neo::fft::from_order, 4};
+    auto buf  = stdex::mdarray<Complex, stdex::dextents<std::size_t, 1>>{plan.size()};
+    auto out  = stdex::mdarray<Complex, stdex::dextents<std::size_t, 1>>{plan.size()};
+    neo::fft::fft(plan, buf.to_mdspan());                   // in place
+    neo::fft::ifft(plan, buf.to_mdspan());
+    neo::fft::fft(plan, buf.to_mdspan(), out.to_mdspan());  // picks the 3-argument overload through `requires`
+    neo::fft::ifft(plan, buf.to_mdspan(), out.to_mdspan());
+    static_assert(neo::b200::fft_plan<Complex>::max_order() == neo::fft::fft_plan<Complex>::max_order());
+}
+
+template<typename Float>
+auto instantiate_r2c() -> void
+{
+    using Complex = std::complex<Float>;
+    auto plan     = neo::b200::rfft_plan<Float, Complex>{neo::fft::from_order, 4};
+    auto real     = stdex::mdarray<Float, stdex::dextents<std::size_t, 1>>{plan.size()};
+    auto cplx     = stdex::mdarray<Complex, stdex::dextents<std::size_t, 1>>{plan.size()};
+    neo::fft::rfft(plan, real.to_mdspan(), cplx.to_mdspan());
+    neo::fft::irfft(plan, cplx.to_mdspan(), real.to_mdspan());
+}
+
+template<typename Complex>
+auto instantiate_convolver() -> void
+{
+    using Float = typename Complex::value_type;
+    auto conv   = neo::b200::upols_convolver<Complex>{};
+    auto h      = stdex::mdarray<Complex, stdex::dextents<std::size_t, 2>>{3, 129};
+    auto block  = stdex::mdarray<Float, stdex::dextents<std::size_t, 1>>{128};
+    conv.filter(h.to_mdspan());  // uniform_partitioned_convolver.hpp:24
+    conv(block.to_mdspan());     // uniform_partitioned_convolver.hpp:25
+    auto ola = neo::b200::upola_convolver<Complex>{};
+    ola.filter(h.to_mdspan());
+    ola(block.to_mdspan());
+}
+
+auto instantiate_all() -> void
+{
+    instantiate_c2c<std::complex<float>>();
+    instantiate_c2c<std::complex<double>>();
+    instantiate_c2c<neo::scalar_complex<float>>();
+    instantiate_r2c<float>();
+    instantiate_r2c<double>();
+    instantiate_convolver<std::complex<float>>();
+    instantiate_convolver<std::complex<double>>();
+}
