@@ -238,26 +238,30 @@ struct conv_engine
         return clear_state(stream);
     }
 
-    // window + r2c + FDL insert + MAC for `blocks` blocks; in is a device pointer [inputs][in_stride]
-    int forward(T const* in, size_t in_stride, size_t blocks, cudaStream_t stream)
+    // window + r2c + FDL insert for input channels [chan0, chan0 + nchan); `in` points at channel chan0's row
+    int forward_r2c(T const* in, size_t in_stride, size_t blocks, size_t chan0, size_t nchan, cudaStream_t stream)
     {
         int status = NEO_B200_ERR_UNSUPPORTED;
         NEO_TRY(mark_begin(0, stream));
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
                 conv_r2c_io<T, LOGM> io{in, in_stride, prev.template as<T>(), fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
-                                        cfg.kind == NEO_B200_UPOLA ? 1 : 0, logw, nt};
-                status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), cfg.inputs * blocks, stream);
+                                        cfg.kind == NEO_B200_UPOLA ? 1 : 0, logw, nt, chan0};
+                status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
             }
         });
         if (status != NEO_B200_OK) { return status == NEO_B200_ERR_UNSUPPORTED ? fail(status, "block size %d not supported", m) : status; }
         if (cfg.kind == NEO_B200_UPOLS) {
             // the last block becomes the left half of the next call's first window (overlap_save.hpp:94-95)
-            NEO_CUDA_TRY(cudaMemcpy2DAsync(prev.ptr, m * sizeof(T), in + (blocks - 1) * m, in_stride * sizeof(T), m * sizeof(T), cfg.inputs,
-                                           cudaMemcpyDeviceToDevice, stream));
+            NEO_CUDA_TRY(cudaMemcpy2DAsync(prev.template as<T>() + chan0 * m, m * sizeof(T), in + (blocks - 1) * m, in_stride * sizeof(T),
+                                           m * sizeof(T), nchan, cudaMemcpyDeviceToDevice, stream));
         }
-        NEO_TRY(mark_end(0, stream));
+        return mark_end(0, stream);
+    }
 
+    // spectral MAC of outputs [out0, out0 + nout) for the `blocks` blocks just inserted
+    int forward_mac(size_t blocks, size_t out0, size_t nout, cudaStream_t stream)
+    {
         mac_geom g{};
         g.m         = m;
         g.logw      = logw;
@@ -269,6 +273,7 @@ struct conv_engine
         g.diagonal  = cfg.topology == NEO_B200_DIAGONAL ? 1 : 0;
         g.blocks    = int(blocks);
         g.splits    = splits;
+        g.out0      = int(out0);
         g.acc_plane = cfg.outputs * blocks * size_t(m);
 
         size_t tau = 0;
@@ -279,34 +284,43 @@ struct conv_engine
             g.wp              = int((write_pos + tau) % size_t(ring));
             bool const tma    = sizeof(T) == 4 && m >= 128;  // float rows of whole 1 KB tiles: TMA-staged kernel
             int const tb      = left >= 32 && tma ? 32 : left >= 16 && sizeof(T) == 4 ? 16 : left >= 8 ? 8 : left >= 4 ? 4 : left >= 2 ? 2 : 1;
-            NEO_TRY(launch_mac(tb, g, stream));
+            NEO_TRY(launch_mac(tb, g, nout, stream));
             ++mac_launches;
             tau += size_t(tb);
         }
-        NEO_TRY(mark_end(1, stream));
-        write_pos = (write_pos + blocks) % size_t(ring);
+        return mark_end(1, stream);
+    }
+
+    // the ring position moves once per call, after every channel group has been inserted
+    void advance(size_t blocks) { write_pos = (write_pos + blocks) % size_t(ring); }
+
+    int forward(T const* in, size_t in_stride, size_t blocks, cudaStream_t stream)
+    {
+        NEO_TRY(forward_r2c(in, in_stride, blocks, 0, cfg.inputs, stream));
+        NEO_TRY(forward_mac(blocks, 0, cfg.outputs, stream));
+        advance(blocks);
         return NEO_B200_OK;
     }
 
-    int launch_mac(int tb, mac_geom const& g, cudaStream_t stream)
+    int launch_mac(int tb, mac_geom const& g, size_t nout, cudaStream_t stream)
     {
         auto const* x = fdl.template as<cx<T>>();
         auto const* h = filter.template as<cx<T>>();
         auto* a       = acc.template as<cx<T>>();
         if (tb == 1) {
-            dim3 const grid(unsigned((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads), unsigned(cfg.outputs), unsigned(splits));
+            dim3 const grid(unsigned((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads), unsigned(nout), unsigned(splits));
             fdl_mac_stream_kernel<T><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
             return check_launch("fdl_mac_stream_kernel");
         }
         if constexpr (sizeof(T) == 4) {
             if (m >= 128 && tb >= 8) {
-                dim3 const tgrid(unsigned(nt), unsigned(cfg.outputs), unsigned(splits));
+                dim3 const tgrid{static_cast<unsigned>(nt), static_cast<unsigned>(nout), static_cast<unsigned>(splits)};
                 if (tb == 32) { return launch_tma<32, 8, 3>(tgrid, x, h, a, g, stream); }
                 if (tb == 16) { return launch_tma<16, 8, 3>(tgrid, x, h, a, g, stream); }
                 return launch_tma<8, 8, 3>(tgrid, x, h, a, g, stream);
             }
         }
-        dim3 const grid(unsigned((m + k_mac_threads - 1) / k_mac_threads), unsigned(cfg.outputs), unsigned(splits));
+        dim3 const grid(unsigned((m + k_mac_threads - 1) / k_mac_threads), unsigned(nout), unsigned(splits));
         switch (tb) {
             case 2: fdl_mac_toeplitz_kernel<T, 2><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g); break;
             case 4: fdl_mac_toeplitz_kernel<T, 4><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g); break;
@@ -406,6 +420,37 @@ struct neo_b200_conv
     conv_engine<float> f32;
     conv_engine<double> f64;
     bool sharded;
+
+    // copy streams + events of the pipelined HOST path (created on first use)
+    cudaStream_t s_in{nullptr}, s_out{nullptr};
+    cudaEvent_t ev_start{nullptr};
+    std::vector<cudaEvent_t> ev_in, ev_done;
+
+    int ensure_pipeline(size_t groups)
+    {
+        if (s_in == nullptr) {
+            NEO_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+            NEO_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+            NEO_CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        }
+        while (ev_in.size() < groups) {
+            cudaEvent_t a, b;
+            NEO_CUDA_TRY(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+            NEO_CUDA_TRY(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+            ev_in.push_back(a);
+            ev_done.push_back(b);
+        }
+        return NEO_B200_OK;
+    }
+
+    ~neo_b200_conv()
+    {
+        for (auto ev : ev_in) { cudaEventDestroy(ev); }
+        for (auto ev : ev_done) { cudaEventDestroy(ev); }
+        if (ev_start != nullptr) { cudaEventDestroy(ev_start); }
+        if (s_in != nullptr) { cudaStreamDestroy(s_in); }
+        if (s_out != nullptr) { cudaStreamDestroy(s_out); }
+    }
 };
 
 #define NEO_CONV_ENGINE(conv, CALL) ((conv)->cfg.dtype == NEO_B200_F32 ? (conv)->f32.CALL : (conv)->f64.CALL)
@@ -478,23 +523,54 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
 {
     cudaStream_t const s = conv->stream.stream;
     size_t const stride  = blocks * e.m;
-    T const* din         = static_cast<T const*>(in);
-    T* dout              = static_cast<T*>(out);
-    if (memspace == NEO_B200_HOST) {
-        NEO_TRY(e.stage_in.reserve(conv->cfg.inputs * stride * sizeof(T)));
-        NEO_TRY(e.stage_out.reserve(conv->cfg.outputs * stride * sizeof(T)));
-        NEO_CUDA_TRY(cudaMemcpyAsync(e.stage_in.ptr, in, conv->cfg.inputs * stride * sizeof(T), cudaMemcpyHostToDevice, s));
-        din  = e.stage_in.template as<T>();
-        dout = e.stage_out.template as<T>();
+    size_t const plane   = conv->cfg.outputs * blocks * size_t(e.m);
+    if (memspace == NEO_B200_DEVICE) {
+        NEO_TRY(e.forward(static_cast<T const*>(in), stride, blocks, s));
+        NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), plane, e.splits, static_cast<T*>(out), stride, 0, conv->cfg.outputs, blocks, s));
+        if (conv->cfg.kind == NEO_B200_UPOLA) { e.tail_flip ^= 1; }
+        return NEO_B200_OK;
     }
-    NEO_TRY(e.forward(din, stride, blocks, s));
-    NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), conv->cfg.outputs * blocks * size_t(e.m), e.splits, dout, stride, 0, conv->cfg.outputs,
-                      blocks, s));
+
+    // HOST buffers. Channels of a diagonal bank are independent, so the call is cut into channel groups and pipelined over
+    // three streams: H2D of group g+1 and D2H of group g-1 overlap the kernels of group g (both PCIe directions busy).
+    size_t const chans = conv->cfg.outputs;
+    NEO_TRY(e.stage_in.reserve(conv->cfg.inputs * stride * sizeof(T)));
+    NEO_TRY(e.stage_out.reserve(chans * stride * sizeof(T)));
+    T* const din  = e.stage_in.template as<T>();
+    T* const dout = e.stage_out.template as<T>();
+    size_t groups = 1;
+    // worth it only when the copies are long enough to matter next to the kernels (several blocks per call)
+    if (conv->cfg.topology == NEO_B200_DIAGONAL && blocks >= 4) { groups = chans >= 512 ? 4 : chans >= 128 ? 2 : 1; }
+    if (groups == 1) {
+        NEO_CUDA_TRY(cudaMemcpyAsync(din, in, conv->cfg.inputs * stride * sizeof(T), cudaMemcpyHostToDevice, s));
+        NEO_TRY(e.forward(din, stride, blocks, s));
+        NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), plane, e.splits, dout, stride, 0, chans, blocks, s));
+        NEO_CUDA_TRY(cudaMemcpyAsync(out, dout, chans * stride * sizeof(T), cudaMemcpyDeviceToHost, s));
+    } else {
+        NEO_TRY(conv->ensure_pipeline(groups));
+        NEO_CUDA_TRY(cudaEventRecord(conv->ev_start, s));
+        NEO_CUDA_TRY(cudaStreamWaitEvent(conv->s_in, conv->ev_start, 0));   // previous work on the handle's stream is done first
+        NEO_CUDA_TRY(cudaStreamWaitEvent(conv->s_out, conv->ev_start, 0));
+        for (size_t g = 0; g < groups; ++g) {
+            size_t const c0 = g * chans / groups, c1 = (g + 1) * chans / groups, n = c1 - c0;
+            NEO_CUDA_TRY(cudaMemcpyAsync(din + c0 * stride, static_cast<T const*>(in) + c0 * stride, n * stride * sizeof(T),
+                                         cudaMemcpyHostToDevice, conv->s_in));
+            NEO_CUDA_TRY(cudaEventRecord(conv->ev_in[g], conv->s_in));
+            NEO_CUDA_TRY(cudaStreamWaitEvent(s, conv->ev_in[g], 0));
+            NEO_TRY(e.forward_r2c(din + c0 * stride, stride, blocks, c0, n, s));
+            NEO_TRY(e.forward_mac(blocks, c0, n, s));
+            NEO_TRY(e.inverse(e.acc.template as<cx<T>>() + c0 * blocks * size_t(e.m), plane, e.splits, dout + c0 * stride, stride, c0, n,
+                              blocks, s));
+            NEO_CUDA_TRY(cudaEventRecord(conv->ev_done[g], s));
+            NEO_CUDA_TRY(cudaStreamWaitEvent(conv->s_out, conv->ev_done[g], 0));
+            NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<T*>(out) + c0 * stride, dout + c0 * stride, n * stride * sizeof(T),
+                                         cudaMemcpyDeviceToHost, conv->s_out));
+        }
+        e.advance(blocks);
+        NEO_CUDA_TRY(cudaStreamSynchronize(conv->s_out));
+    }
     if (conv->cfg.kind == NEO_B200_UPOLA) { e.tail_flip ^= 1; }
-    if (memspace == NEO_B200_HOST) {
-        NEO_CUDA_TRY(cudaMemcpyAsync(out, dout, conv->cfg.outputs * stride * sizeof(T), cudaMemcpyDeviceToHost, s));
-        NEO_CUDA_TRY(cudaStreamSynchronize(s));
-    }
+    NEO_CUDA_TRY(cudaStreamSynchronize(s));
     return NEO_B200_OK;
 }
 

@@ -54,6 +54,7 @@ struct mac_geom
     int blocks;        // T of the whole call (row stride of acc)
     int tau0;          // first block of this launch inside the call
     int splits;        // S
+    int out0;          // first output channel of this launch (blockIdx.y is relative to it)
     size_t acc_plane;  // elements per partial plane
 };
 
@@ -125,7 +126,7 @@ __global__ void __launch_bounds__(k_mac_threads)
     using MV          = mac_vec<T>;
     using V           = typename MV::type;
     int const col     = blockIdx.x * k_mac_threads + threadIdx.x;  // in units of V
-    int const out     = blockIdx.y;
+    int const out     = blockIdx.y + g.out0;
     int const split   = blockIdx.z;
     int const row_vec = g.m / MV::VEC;
     if (col >= row_vec) { return; }
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(k_mac_threads)
 {
     using C         = cx<T>;
     int const k     = blockIdx.x * k_mac_threads + threadIdx.x;
-    int const out   = blockIdx.y;
+    int const out   = blockIdx.y + g.out0;
     int const split = blockIdx.z;
     if (k >= g.m) { return; }
     bool const edge = (k == 0);
@@ -335,7 +336,7 @@ __global__ void __launch_bounds__(128)
     int const tid   = threadIdx.x;
     int const lane  = tid & 31;
     int const tile  = blockIdx.x;
-    int const out   = blockIdx.y;
+    int const out   = blockIdx.y + g.out0;
     int const split = blockIdx.z;
     bool const edge = (tile == 0 && tid == 0);  // packed bin 0: (Re X0, Re XB) are two real products
 
@@ -496,6 +497,7 @@ struct conv_r2c_io
     int ring, wp, blocks;
     int overlap_add;   // 0: window = [previous block | block]   1: window = [block | zeros]  (overlap_add.hpp:88-90)
     int logw, nt;      // tile-major FDL layout
+    size_t chan0;      // `in` row 0 is input channel chan0 (channel groups of a pipelined host call)
 
     struct row_state
     {
@@ -506,9 +508,10 @@ struct conv_r2c_io
     __device__ __forceinline__ row_state open(size_t b) const
     {
         constexpr size_t B = size_t(1) << LOGM;
-        size_t const ch    = b / blocks;
-        int const tau      = int(b - ch * blocks);
-        T const* cur       = in + ch * in_stride + size_t(tau) * B;
+        size_t const rel   = b / blocks;
+        size_t const ch    = chan0 + rel;
+        int const tau      = int(b - rel * blocks);
+        T const* cur       = in + rel * in_stride + size_t(tau) * B;
         int slot           = wp + tau;
         slot -= slot >= ring ? ring : 0;
         C* dst = fdl + tiled_offset(ch, nt, logw, size_t(ring), size_t(slot), 0);
