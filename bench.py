@@ -241,6 +241,9 @@ def run_ours(args):
     T = args.blocks
     peak, peak_src = measured_peaks()
     stream = torch.cuda.current_stream()
+    if args.fft_only:  # development aid: just the BASELINE config 2 sweep
+        print(json.dumps({"fft_sweep": fft_sweep(pkg, torch, peak)}), flush=True)
+        return
 
     # ---- state: random impulse responses (unit energy like normalize_impulse), partitioned on the device ----
     lo, hi = rank * PARTS // world, (rank + 1) * PARTS // world
@@ -453,6 +456,7 @@ def main():
     ap.add_argument("--blocks", type=int, default=16, help="blocks per call T (1 = the reference's streaming call)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-fft-sweep", action="store_true")
+    ap.add_argument("--fft-only", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))

@@ -240,7 +240,8 @@ __host__ __device__ constexpr int padded(int i)
 }
 
 // stage list: an optional first stage of radix 2^(logm % loge) (no twiddles, Ns = 1), then logm/loge stages of
-// radix 2^loge. The twiddle LUT holds, for every stage with Ns > 1, W_{Ns*r}^{q*k} at [(q-1)*Ns + k].
+// radix 2^loge. The twiddle LUT holds, for every stage with Ns > 1, W_{Ns*r}^{q*k} for the powers of two q = 2^j only,
+// at [j*Ns + k]; the other q are one to three complex products of those (loads, not FMAs, are the scarce resource).
 __host__ __device__ constexpr int fft_first_logr(int logm, int loge) { return loge == 0 ? 0 : logm % loge; }
 
 __host__ __device__ constexpr int fft_twiddle_offset(int logm, int loge, int logns_target)
@@ -252,7 +253,7 @@ __host__ __device__ constexpr int fft_twiddle_offset(int logm, int loge, int log
     if (r0 > 0) { logns = r0; }
     else { logns = loge; }  // first full stage has Ns = 1: no table
     while (logns < logns_target) {
-        off += ((1 << loge) - 1) << logns;
+        off += loge << logns;
         logns += loge;
     }
     return off;
@@ -272,6 +273,15 @@ struct cta_fft
     static constexpr int TILE = padded<T>(M) + 1;
     using C                   = cx<T>;
 
+    // w[q] = W^(q*k): loaded when q is a power of two (row log2(q) of the stage table), else w[hi] * w[q - hi]
+    template<int N>
+    static __device__ __forceinline__ void stage_twiddle(int q, C (&w)[N], C const* __restrict__ row0, int ns)
+    {
+        int const hi = 1 << (31 - __clz(q));
+        if (q == hi) { w[q] = __ldg(row0 + (31 - __clz(q)) * ns); }
+        else { w[q] = cmul(w[hi], w[q - hi]); }
+    }
+
     template<int LOGNS, int LOGR>
     static __device__ __forceinline__ void stage(C (&v)[E], C* sm, C const* __restrict__ tw, int t)
     {
@@ -289,10 +299,11 @@ struct cta_fft
 #pragma unroll
             for (int q = 0; q < R; ++q) { u[q] = v[m + q * BF]; }
             if constexpr (NS > 1) {
+                C w[R];
 #pragma unroll
                 for (int q = 1; q < R; ++q) {
-                    C const w = __ldg(tw + off + (q - 1) * NS + k);
-                    u[q]      = (DIR < 0) ? cmul(u[q], w) : cmulc(u[q], w);
+                    stage_twiddle(q, w, tw + off + k, NS);
+                    u[q] = (DIR < 0) ? cmul(u[q], w[q]) : cmulc(u[q], w[q]);
                 }
             }
             dft<R, DIR>::run(u);

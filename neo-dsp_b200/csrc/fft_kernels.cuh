@@ -44,13 +44,13 @@ std::vector<cx<T>> make_stage_twiddles(int logm)
     while (logns < logm) {
         long const ns    = 1L << logns;
         double const den = static_cast<double>(ns) * r;
-        for (int q = 1; q < r; ++q) {
+        for (int j = 0; j < loge; ++j) {
             for (long k = 0; k < ns; ++k) {
-                double const a             = -2.0 * 3.14159265358979323846264338327950288 * double(q) * double(k) / den;
-                lut[off + (q - 1) * ns + k] = mk<T>(T(std::cos(a)), T(std::sin(a)));
+                double const a      = -2.0 * 3.14159265358979323846264338327950288 * double(1 << j) * double(k) / den;
+                lut[off + j * ns + k] = mk<T>(T(std::cos(a)), T(std::sin(a)));
             }
         }
-        off += static_cast<size_t>(r - 1) * ns;
+        off += static_cast<size_t>(loge) * ns;
         logns += loge;
     }
     return lut;
