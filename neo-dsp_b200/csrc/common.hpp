@@ -47,9 +47,9 @@ inline void count_launch(std::uint64_t n = 1) { launch_counter().fetch_add(n, st
         }                                                                                                              \
     } while (0)
 
-#define NEO_TRY(expr)                                                                                                  \
+#define NEO_TRY(...)                                                                                                   \
     do {                                                                                                               \
-        int const neo_st_ = (expr);                                                                                    \
+        int const neo_st_ = (__VA_ARGS__);                                                                                    \
         if (neo_st_ != NEO_B200_OK) { return neo_st_; }                                                                \
     } while (0)
 

@@ -3,6 +3,7 @@
 // neo::fft::rfft_plan (src/neo/fft/fallback/fallback_rfft_plan.hpp:15-61).
 #include "fft_kernels.cuh"
 #include "fft_large.cuh"
+#include "fft_split.cuh"
 
 #include <cmath>
 #include <memory>
@@ -35,21 +36,63 @@ template<typename T>
 struct c2c_engine
 {
     int order;
-    fft_tables<T> tables;        // single-CTA path
-    large_fft<T> large;          // four-step path above max_cta_logm
+    fft_tables<T> tables;        // single-CTA path (order-point plan) or split path (max_cta-point plan)
+    device_buffer w_big;         // split path: exp(-2 pi i n / 2^order), n < 2^max_cta
+    device_buffer scratch;       // split path, in-place calls
+    large_fft<T> large;          // four-step path above the split range
     bool use_large{false};
+    int split{0};                // 2 or 4 CTAs per transform (fft_split.cuh)
 
     int init(int order_, cudaStream_t stream)
     {
-        order     = order_;
-        use_large = order > max_cta_logm<T>();
+        order          = order_;
+        constexpr int c = max_cta_logm<T>();
+        split          = order == c + 1 ? 2 : order == c + 2 ? 4 : 0;
+        use_large      = order > c + 2;
         if (use_large) { return large.init(order, stream); }
+        if (split != 0) {
+            NEO_TRY(tables.build(c, false, stream));
+            size_t const m2 = size_t(1) << c;
+            std::vector<cx<T>> w(m2);
+            for (size_t n = 0; n < m2; ++n) {
+                double const a = -2.0 * 3.14159265358979323846264338327950288 * double(n) / std::ldexp(1.0, order);
+                w[n]           = mk<T>(T(std::cos(a)), T(std::sin(a)));
+            }
+            NEO_TRY(w_big.reserve(m2 * sizeof(cx<T>)));
+            NEO_CUDA_TRY(cudaMemcpyAsync(w_big.ptr, w.data(), m2 * sizeof(cx<T>), cudaMemcpyHostToDevice, stream));
+            NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+            return NEO_B200_OK;
+        }
         return tables.build(order, false, stream);
+    }
+
+    int exec_split(cx<T> const* in, cx<T>* out, size_t batch, int direction, cudaStream_t stream)
+    {
+        constexpr int c = max_cta_logm<T>();
+        auto const* wb  = w_big.template as<cx<T>>();
+        if (in != out) {
+            return split == 2 ? launch_c2c_split<T, c, 2>(in, out, tables.tw(), wb, batch, direction, stream)
+                              : launch_c2c_split<T, c, 4>(in, out, tables.tw(), wb, batch, direction, stream);
+        }
+        // in place: the CTAs of one transform read all of it and write interleaved bins -> go through a scratch chunk
+        size_t const bytes = (size_t(1) << order) * sizeof(cx<T>);
+        size_t const chunk = std::max<size_t>(1, std::min(batch, (size_t(64) << 20) / bytes));
+        NEO_TRY(scratch.reserve(chunk * bytes));
+        for (size_t first = 0; first < batch; first += chunk) {
+            size_t const n  = std::min(chunk, batch - first);
+            cx<T>* const s  = scratch.template as<cx<T>>();
+            cx<T>* const io = out + (first << order);
+            NEO_TRY(split == 2 ? launch_c2c_split<T, c, 2>(io, s, tables.tw(), wb, n, direction, stream)
+                               : launch_c2c_split<T, c, 4>(io, s, tables.tw(), wb, n, direction, stream));
+            NEO_CUDA_TRY(cudaMemcpyAsync(io, s, n * bytes, cudaMemcpyDeviceToDevice, stream));
+        }
+        return NEO_B200_OK;
     }
 
     int exec(cx<T> const* in, cx<T>* out, size_t batch, int direction, cudaStream_t stream)
     {
         if (use_large) { return large.exec(in, out, batch, direction, stream); }
+        if (split != 0) { return exec_split(in, out, batch, direction, stream); }
         int status = NEO_B200_ERR_UNSUPPORTED;
         NEO_DISPATCH_LOGM(T, order, {
             if constexpr (LOGM <= max_cta_logm<T>()) {
@@ -66,23 +109,93 @@ template<typename T>
 struct rfft_engine
 {
     int order;                   // real size N = 2^order, complex half size M = N/2
-    fft_tables<T> tables;
+    fft_tables<T> tables;        // single-CTA path: M-point plan; split path: M/2-point plan
+    device_buffer w_n;           // split path: exp(-2 pi i k / N), k < M/2
     large_rfft<T> large;
     bool use_large{false};
+    bool use_split{false};       // two CTAs per transform (fft_split.cuh)
+    bool use_two_pass{false};    // four-CTA split c2c into an L2-resident scratch + Hermitian split pass
+    c2c_engine<T> half;          // two-pass path: the half-size complex transform
+    twiddle2<T> w2m;             // two-pass path: exp(-2 pi i k / N)
+    device_buffer zbuf;
+
+    // half-size transforms of 2^(max_cta) and 2^(max_cta+1) points run as two CTAs of half that size each
+    static constexpr int k_split_lo = max_cta_logm<T>();
+    static constexpr int k_split_hi = max_cta_logm<T>() + 1;
 
     int init(int order_, cudaStream_t stream)
     {
-        order     = order_;
-        use_large = order - 1 > max_cta_logm<T>();
+        order = order_;
         if (order == 0) { return NEO_B200_OK; }
+        int const logm = order - 1;
+        use_split      = logm >= k_split_lo && logm <= k_split_hi;
+        use_two_pass   = logm == k_split_hi + 1;
+        use_large      = logm > k_split_hi + 1;
         if (use_large) { return large.init(order, stream); }
-        return tables.build(order - 1, true, stream);
+        if (use_two_pass) {
+            NEO_TRY(half.init(logm, stream));
+            return w2m.build(order, stream);
+        }
+        if (use_split) {
+            NEO_TRY(tables.build(logm - 1, true, stream));
+            auto const wn = make_split_twiddles<T>(logm);  // exp(-i pi k / M) = exp(-2 pi i k / N); first M/2 entries used
+            size_t const bytes = (wn.size() / 2) * sizeof(cx<T>);
+            NEO_TRY(w_n.reserve(bytes));
+            NEO_CUDA_TRY(cudaMemcpyAsync(w_n.ptr, wn.data(), bytes, cudaMemcpyHostToDevice, stream));
+            NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+            return NEO_B200_OK;
+        }
+        return tables.build(logm, true, stream);
+    }
+
+    // chunks keep the intermediate spectrum L2-resident between the two passes
+    size_t two_pass_chunk(size_t batch)
+    {
+        size_t const bytes = (size_t(1) << (order - 1)) * sizeof(cx<T>);
+        return std::max<size_t>(1, std::min(batch, (size_t(48) << 20) / bytes));
+    }
+
+    int forward_two_pass(T const* in, cx<T>* out, size_t batch, cudaStream_t stream)
+    {
+        size_t const m     = size_t(1) << (order - 1);
+        size_t const chunk = two_pass_chunk(batch);
+        NEO_TRY(zbuf.reserve(chunk * m * sizeof(cx<T>)));
+        cx<T>* const z = zbuf.template as<cx<T>>();
+        for (size_t first = 0; first < batch; first += chunk) {
+            size_t const cnt = std::min(chunk, batch - first);
+            NEO_TRY(half.exec(reinterpret_cast<cx<T> const*>(in) + first * m, z, cnt, -1, stream));
+            dim3 const grid(static_cast<unsigned>((m + 255) / 256), static_cast<unsigned>(cnt));
+            split_pass_kernel<T, -1><<<grid, 256, 0, stream>>>(z, m, out + first * (m + 1), m + 1, w2m.view(), m);
+            NEO_TRY(check_launch("split_pass_kernel"));
+        }
+        return NEO_B200_OK;
+    }
+
+    int backward_two_pass(cx<T> const* in, size_t row_len, T* out, size_t batch, cudaStream_t stream)
+    {
+        size_t const m     = size_t(1) << (order - 1);
+        size_t const chunk = two_pass_chunk(batch);
+        NEO_TRY(zbuf.reserve(chunk * m * sizeof(cx<T>)));
+        cx<T>* const z = zbuf.template as<cx<T>>();
+        for (size_t first = 0; first < batch; first += chunk) {
+            size_t const cnt = std::min(chunk, batch - first);
+            dim3 const grid(static_cast<unsigned>((m + 255) / 256), static_cast<unsigned>(cnt));
+            split_pass_kernel<T, +1><<<grid, 256, 0, stream>>>(in + first * row_len, row_len, z, m, w2m.view(), m);
+            NEO_TRY(check_launch("split_pass_kernel"));
+            NEO_TRY(half.exec(z, reinterpret_cast<cx<T>*>(out) + first * m, cnt, +1, stream));
+        }
+        return NEO_B200_OK;
     }
 
     int forward(T const* in, cx<T>* out, size_t batch, cudaStream_t stream)
     {
         if (order == 0) { return large_rfft<T>::size_one_forward(in, out, batch, stream); }
         if (use_large) { return large.forward(in, out, batch, stream); }
+        if (use_two_pass) { return forward_two_pass(in, out, batch, stream); }
+        if (use_split) {
+            if (order - 1 == k_split_lo) { return launch_r2c_split2<T, k_split_lo - 1>(in, out, tables.tw(), tables.rtw(), batch, stream); }
+            return launch_r2c_split2<T, k_split_hi - 1>(in, out, tables.tw(), tables.rtw(), batch, stream);
+        }
         int status = NEO_B200_ERR_UNSUPPORTED;
         NEO_DISPATCH_LOGM(T, order - 1, {
             if constexpr (LOGM <= max_cta_logm<T>()) {
@@ -97,6 +210,14 @@ struct rfft_engine
     {
         if (order == 0) { return large_rfft<T>::size_one_backward(in, row_len, out, batch, stream); }
         if (use_large) { return large.backward(in, row_len, out, batch, stream); }
+        if (use_two_pass) { return backward_two_pass(in, row_len, out, batch, stream); }
+        if (use_split) {
+            auto const* wn = w_n.template as<cx<T>>();
+            if (order - 1 == k_split_lo) {
+                return launch_c2r_split2<T, k_split_lo - 1>(in, row_len, out, tables.tw(), tables.rtw(), wn, batch, stream);
+            }
+            return launch_c2r_split2<T, k_split_hi - 1>(in, row_len, out, tables.tw(), tables.rtw(), wn, batch, stream);
+        }
         int status = NEO_B200_ERR_UNSUPPORTED;
         NEO_DISPATCH_LOGM(T, order - 1, {
             if constexpr (LOGM <= max_cta_logm<T>()) {
