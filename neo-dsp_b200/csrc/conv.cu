@@ -147,7 +147,7 @@ struct conv_engine
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         size_t const ctas_xy = size_t((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads) * c.outputs;
         size_t const work    = size_t(sources) * parts;
-        size_t want          = (size_t(sms) * 4 + ctas_xy - 1) / ctas_xy;
+        size_t want          = (size_t(sms) * (sources > 1 ? 16 : 4) + ctas_xy - 1) / ctas_xy;
         want                 = std::min(want, std::max<size_t>(1, work / 8));
         splits               = int(std::max<size_t>(1, std::min<size_t>(want, 64)));
         NEO_TRY(acc.reserve(size_t(splits) * c.outputs * c.max_blocks * m * csz));
@@ -308,8 +308,15 @@ struct conv_engine
         auto const* h = filter.template as<cx<T>>();
         auto* a       = acc.template as<cx<T>>();
         if (tb == 1) {
-            dim3 const grid(unsigned((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads), unsigned(nout), unsigned(splits));
-            fdl_mac_stream_kernel<T><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
+            unsigned const gx = unsigned((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads);
+            if (cfg.topology == NEO_B200_MATRIX && nout % 4 == 0) {
+                // four outputs per thread share every FDL row they load
+                dim3 const grid(gx, unsigned(nout / 4), unsigned(splits));
+                fdl_mac_stream_kernel<T, 4><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
+            } else {
+                dim3 const grid(gx, unsigned(nout), unsigned(splits));
+                fdl_mac_stream_kernel<T, 1><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
+            }
             return check_launch("fdl_mac_stream_kernel");
         }
         if constexpr (sizeof(T) == 4) {

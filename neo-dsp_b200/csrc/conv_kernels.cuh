@@ -119,23 +119,27 @@ __device__ __forceinline__ V ld_stream(V const* p)
 constexpr int k_mac_threads = 128;
 constexpr int k_mac_unroll  = 8;
 
-template<typename T>
+// OT outputs per thread: in the matrix topology the same FDL row feeds every output, so it is loaded once per OT filter rows.
+template<typename T, int OT>
 __global__ void __launch_bounds__(k_mac_threads)
     fdl_mac_stream_kernel(cx<T> const* __restrict__ fdl, cx<T> const* __restrict__ filter, cx<T>* __restrict__ acc, mac_geom g)
 {
-    using MV          = mac_vec<T>;
-    using V           = typename MV::type;
-    int const col     = blockIdx.x * k_mac_threads + threadIdx.x;  // in units of V
-    int const out     = blockIdx.y + g.out0;
-    int const split   = blockIdx.z;
-    int const row_vec = g.m / MV::VEC;
+    using MV           = mac_vec<T>;
+    using V            = typename MV::type;
+    constexpr int UNR  = OT == 1 ? k_mac_unroll : 4;
+    int const col      = blockIdx.x * k_mac_threads + threadIdx.x;  // in units of V
+    int const out0     = blockIdx.y * OT + g.out0;
+    int const split    = blockIdx.z;
+    int const row_vec  = g.m / MV::VEC;
     if (col >= row_vec) { return; }
 
-    int const total = g.sources * g.parts;  // virtual partitions of this output
+    int const total = g.sources * g.parts;  // virtual partitions of one output
     int const v0    = int((long long)total * split / g.splits);
     int const v1    = int((long long)total * (split + 1) / g.splits);
 
-    V a = MV::zero();
+    V a[OT];
+#pragma unroll
+    for (int o = 0; o < OT; ++o) { a[o] = MV::zero(); }
     bool const edge = (col == 0);  // this thread owns the packed bin 0
 
     // tile-major addressing in units of V (VEC elements)
@@ -145,11 +149,12 @@ __global__ void __launch_bounds__(k_mac_threads)
     int const within   = (k0 & ((1 << g.logw) - 1)) / MV::VEC;
     V const* const fbase = reinterpret_cast<V const*>(filter) + within;
     V const* const xbase = reinterpret_cast<V const*>(fdl) + within;
+    size_t const ostride = size_t(g.sources) * g.nt * g.parts * tile_vec;  // V elements between consecutive outputs' filters
 
-    for (int v = v0; v < v1; v += k_mac_unroll) {
-        V x[k_mac_unroll], h[k_mac_unroll];
+    for (int v = v0; v < v1; v += UNR) {
+        V x[UNR], h[UNR][OT];
 #pragma unroll
-        for (int u = 0; u < k_mac_unroll; ++u) {
+        for (int u = 0; u < UNR; ++u) {
             int const vp = v + u;
             if (vp < v1) {
                 int const src = vp / g.parts;
@@ -157,22 +162,31 @@ __global__ void __launch_bounds__(k_mac_threads)
                 int slot      = g.wp - g.age0 - p;
                 slot          = slot % g.ring;
                 slot += slot < 0 ? g.ring : 0;
-                int const ch = g.diagonal ? out : src;
-                size_t const filt = size_t(out) * g.sources + src;
-                h[u]              = ld_stream(fbase + ((filt * g.nt + tile) * g.parts + p) * tile_vec);
-                x[u]              = ld_stream(xbase + ((size_t(ch) * g.nt + tile) * g.ring + slot) * tile_vec);
+                int const ch         = g.diagonal ? out0 : src;
+                V const* const hrow = fbase + (((size_t(out0) * g.sources + src) * g.nt + tile) * g.parts + p) * tile_vec;
+#pragma unroll
+                for (int o = 0; o < OT; ++o) { h[u][o] = ld_stream(hrow + o * ostride); }
+                x[u] = OT == 1 ? ld_stream(xbase + ((size_t(ch) * g.nt + tile) * g.ring + slot) * tile_vec)
+                               : xbase[((size_t(ch) * g.nt + tile) * g.ring + slot) * tile_vec];
             } else {
-                h[u] = MV::zero();
+#pragma unroll
+                for (int o = 0; o < OT; ++o) { h[u][o] = MV::zero(); }
                 x[u] = MV::zero();
             }
         }
 #pragma unroll
-        for (int u = 0; u < k_mac_unroll; ++u) {
-            if (edge) { MV::cfma_edge(a, x[u], h[u]); }
-            else { MV::cfma(a, x[u], h[u]); }
+        for (int u = 0; u < UNR; ++u) {
+#pragma unroll
+            for (int o = 0; o < OT; ++o) {
+                if (edge) { MV::cfma_edge(a[o], x[u], h[u][o]); }
+                else { MV::cfma(a[o], x[u], h[u][o]); }
+            }
         }
     }
-    reinterpret_cast<V*>(acc)[size_t(split) * (g.acc_plane / MV::VEC) + (size_t(out) * g.blocks + g.tau0) * row_vec + col] = a;
+#pragma unroll
+    for (int o = 0; o < OT; ++o) {
+        reinterpret_cast<V*>(acc)[size_t(split) * (g.acc_plane / MV::VEC) + (size_t(out0 + o) * g.blocks + g.tau0) * row_vec + col] = a[o];
+    }
 }
 
 // ---- T = TB > 1: Toeplitz form. acc[tau] += H[p] * X(tau - age0 - p); each H[p] is reused TB times from registers and

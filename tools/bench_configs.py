@@ -1,0 +1,116 @@
+#!/usr/bin/env python
+"""Measures the BASELINE.json configs that are not bench.py's headline line (C1, C3, C4) on one GPU and prints one JSON object.
+
+C1  neo::fft c2c complex<float> N=1024 batch=1 forward+inverse (+1/N scale): reference CPU (oracle/_ref) vs the CUDA plan through
+    the C ABI with host buffers (latency-bound by construction: one tiny transform per call) and batched on the device.
+C3  UPOLS stereo, B=512, 2^17-tap IR (P=256): microseconds per block (T=1 streaming) and x real-time at 48 kHz.
+C4  64-in x 64-out convolution matrix, B=256, 2^16-tap IRs (P=256): ms per block-step, T=1 (HBM stream of the 2.16 GB filter
+    set) and T=16.
+"""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import __graft_entry__ as entry
+from oracle import pyoracle
+
+pkg = entry.load_package()
+pkg.set_device(0)
+orc = pyoracle.oracle()
+ref = pyoracle.ref()
+stream = torch.cuda.current_stream()
+out = {}
+
+
+def gpu_time(fn, reps=50, warm=5):
+    for _ in range(warm):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps  # ms
+
+
+# ---- C1 -----------------------------------------------------------------------------------------------------------------
+x = orc.noise(1024, 1, np.complex64)
+chk = ref if ref is not None else orc
+t0 = time.perf_counter()
+reps = 2000
+for _ in range(reps):
+    y = chk.fft(chk.fft(x, -1), +1) / 1024
+cpu_us = (time.perf_counter() - t0) / reps * 1e6  # includes ctypes overhead of two calls
+plan = pkg.FFTPlan(10, np.complex64)
+buf = x.copy()
+t0 = time.perf_counter()
+for _ in range(200):
+    plan(buf, pkg.FORWARD)
+    plan(buf, pkg.BACKWARD)
+host_us = (time.perf_counter() - t0) / 200 * 1e6
+plan.set_stream(stream)
+batch = 1 << 18
+dx = torch.randn((batch, 1024), dtype=torch.complex64, device="cuda")
+ms = gpu_time(lambda: (plan(dx, pkg.FORWARD), plan(dx, pkg.BACKWARD)))
+out["C1"] = {
+    "reference_cpu_us_per_roundtrip_incl_plan_build": cpu_us,
+    "b200_host_call_us_per_roundtrip_batch1": host_us,
+    "b200_device_batched_ns_per_roundtrip": ms * 1e6 / batch,
+    "b200_device_batched_gbs": 2 * 2 * batch * 1024 * 8 / ms / 1e6,
+    "note": "batch=1 through host buffers is PCIe/launch latency; the batched figure is the one comparable with the HBM roofline",
+}
+
+# ---- C3 -----------------------------------------------------------------------------------------------------------------
+B, L, C = 512, 1 << 17, 2
+ir = torch.rand((C, L), device="cuda") * 2 - 1
+ir *= 1.0 / ir.square().sum(dim=1).max().sqrt()
+res = {}
+for T in (1, 16):
+    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=T)
+    conv.set_stream(stream)
+    conv.impulse(ir, B)
+    xin = torch.rand((C, T * B), device="cuda") * 2 - 1
+    yout = torch.empty_like(xin)
+    ms = gpu_time(lambda: conv(xin, out=yout), reps=200, warm=20)
+    res[f"T{T}"] = {"us_per_block": ms * 1e3 / T, "realtime_x_48k": (B * T / 48000.0) / (ms * 1e-3),
+                    "channel_msamples_s": C * B * T / ms / 1e3}
+    conv.close()
+res["bytes_per_channel_block_T1"] = 8 * B + 8 * (B + 1) + 16 * (B + 1) * (L // B)
+res["note"] = "2 channels x 2.1 MB of state: L2-resident, bound by launch latency of three small kernels, not by HBM"
+out["C3"] = res
+
+# ---- C4 -----------------------------------------------------------------------------------------------------------------
+B, L, O, I = 256, 1 << 16, 64, 64
+ir = torch.rand((O, I, L), device="cuda") * 2 - 1
+ir *= 1.0 / ir.square().sum(dim=2).max().sqrt()
+res = {}
+P, K = L // B, B + 1
+for T in (1, 16):
+    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.MATRIX, max_blocks=T)
+    conv.set_stream(stream)
+    conv.impulse(ir, B)
+    xin = torch.rand((I, T * B), device="cuda") * 2 - 1
+    yout = torch.empty((O, T * B), device="cuda")
+    conv.profile(True)
+    ms = gpu_time(lambda: conv(xin, out=yout), reps=30, warm=5)
+    r2c_ms, mac_ms, c2r_ms, launches = conv.profile_read()
+    filt_bytes = 8 * K * P * O * I
+    res[f"T{T}"] = {
+        "ms_per_block_step": ms / T,
+        "realtime_x_48k": (B * T / 48000.0) / (ms * 1e-3),
+        "mac_ms_per_call": mac_ms / 35,
+        "mac_filter_stream_gbs": filt_bytes / (mac_ms / 35) / 1e6,
+        "mac_fp32_tflops": 8.0 * K * P * O * I * T / (mac_ms / 35) / 1e9,
+    }
+    conv.close()
+res["filter_bytes"] = 8 * K * P * O * I
+res["note"] = "T=1: the 2.16 GB filter set streams once per block-step (HBM bound); FDL (34 MB) is L2-resident"
+out["C4"] = res
+print(json.dumps(out, indent=1))
