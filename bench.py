@@ -376,7 +376,7 @@ def run_ours(args):
         with open(tpath) as f:
             traffic = json.load(f).get(f"fdl_mac_T{T}_G{world}")
     roofline = {
-        "kernel": "fdl_mac_stream_kernel<float>" if T == 1 else f"fdl_mac_tma_kernel<{T if T in (8, 16, 32) else 'mixed'},8,3>",
+        "kernel": "fdl_mac_stream_kernel<float>" if T == 1 else ("fdl_mac_tma_kernel<16,16,2>" if T == 16 else "fdl_mac_tma_kernel<32,8,3>" if T == 32 else f"fdl_mac (T={T})"),
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
@@ -393,6 +393,49 @@ def run_ours(args):
 
     cpu_baseline = None
     sweep = None
+    modes = None
+    if world == 1 and not args.no_modes:
+        # the other call shapes, measured the same way (fewer steps), so every number on the line states its T
+        del conv
+        torch.cuda.empty_cache()
+        modes = {f"T{T}": {"value": value, "unit": UNIT, "mac_algorithmic_gbs": achieved, "mac_fp32_tflops": roofline["fp32_tflops"]}}
+        for t_other in (1, 32):
+            if t_other == T:
+                continue
+            c2 = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=t_other)
+            c2.set_stream(stream)
+            gen2 = torch.Generator(device="cuda").manual_seed(11)
+            ir2 = torch.rand((CHANNELS, TAPS), device="cuda", dtype=torch.float32, generator=gen2) * 2 - 1
+            ir2 *= 1.0 / ir2.square().sum(dim=1).max().sqrt()
+            c2.impulse(ir2, BLOCK)
+            del ir2
+            x2 = torch.rand((CHANNELS, t_other * BLOCK), device="cuda", dtype=torch.float32) * 2 - 1
+            y2 = torch.empty_like(x2)
+            for _ in range(3):
+                c2(x2, out=y2)
+            c2.profile(True)
+            c2.profile_read()
+            n2 = 30 if t_other == 1 else 10
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(n2):
+                c2(x2, out=y2)
+            e1.record()
+            torch.cuda.synchronize()
+            _, mac2, _, nl2 = c2.profile_read()
+            ms2 = e0.elapsed_time(e1)
+            alg2 = CHANNELS * 8 * bins * (PARTS + (PARTS + t_other - 1) + t_other)
+            modes[f"T{t_other}"] = {
+                "value": CHANNELS * BLOCK * t_other * n2 / (ms2 * 1e-3) / 1e6,
+                "unit": UNIT,
+                "mac_algorithmic_gbs": alg2 / (mac2 / max(1, nl2) * 1e-3) / 1e9,
+                "mac_fp32_tflops": CHANNELS * 8.0 * bins * PARTS * t_other / (mac2 / max(1, nl2) * 1e-3) / 1e12,
+                "steps": n2,
+            }
+            c2.close()
+            del c2, x2, y2
+            torch.cuda.empty_cache()
     if world == 1:
         cores = host_cores()
         sample = max(cores, min(2 * cores, 128))
@@ -440,6 +483,8 @@ def run_ours(args):
     }
     if cpu_baseline is not None:
         line["cpu_baseline"] = cpu_baseline
+    if modes is not None:
+        line["modes"] = modes
     if sweep is not None:
         line["fft_sweep"] = sweep
     print(json.dumps(line), flush=True)
@@ -457,6 +502,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-fft-sweep", action="store_true")
     ap.add_argument("--fft-only", action="store_true")
+    ap.add_argument("--no-modes", action="store_true", help="skip the extra T=1 / T=32 measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))

@@ -426,14 +426,31 @@ __global__ void __launch_bounds__(128)
         tma::mbar_wait(&full[st], parity);
         float2 const* const h = stage_mem + size_t(st) * cfg::STAGE_EL + tid;
         float2 const* const x = h + CH * W;
+        float2 hreg[CH];
 #pragma unroll
-        for (int i = 0; i < CH; ++i) { win[i] = x[i * W]; }
+        for (int i = 0; i < CH; ++i) {
+            win[i]  = x[i * W];
+            hreg[i] = h[i * W];
+        }
+
+        // the stage now lives in registers: release it BEFORE the FMAs so the refill flies during this chunk's compute.
+        // No CTA barrier: the last of the four warps to get here re-arms the mbarrier and issues the bulk copies.
+        __syncwarp();
+        if (lane == 0) {
+            __threadfence_block();
+            int const before = atomicAdd(&done[st], 1);
+            if (before == cfg::WARPS - 1) {
+                done[st] = 0;
+                if (c + STAGES < c1) { issue(c + STAGES); }
+            }
+        }
+        __syncwarp();
 
         if (!edge) {
 #pragma unroll
             for (int pp = 0; pp < CH; ++pp) {
                 if (!RAGGED || p0 + pp < g.parts) {
-                    float2 const hv = h[pp * W];
+                    float2 const hv = hreg[pp];
 #pragma unroll
                     for (int tau = 0; tau < TB; ++tau) {
                         float2 const xv = win[tau - pp + CH - 1];
@@ -448,7 +465,7 @@ __global__ void __launch_bounds__(128)
 #pragma unroll
             for (int pp = 0; pp < CH; ++pp) {
                 if (!RAGGED || p0 + pp < g.parts) {
-                    float2 const hv = h[pp * W];
+                    float2 const hv = hreg[pp];
 #pragma unroll
                     for (int tau = 0; tau < TB; ++tau) {
                         float2 const xv = win[tau - pp + CH - 1];
@@ -458,18 +475,6 @@ __global__ void __launch_bounds__(128)
                 }
             }
         }
-
-        // release the stage without a CTA barrier: the last of the four warps to finish refills it
-        __syncwarp();
-        if (lane == 0) {
-            __threadfence_block();
-            int const before = atomicAdd(&done[st], 1);
-            if (before == cfg::WARPS - 1) {
-                done[st] = 0;
-                if (c + STAGES < c1) { issue(c + STAGES); }
-            }
-        }
-        __syncwarp();
 
         p0 += CH;
         if (p0 >= g.parts) {
