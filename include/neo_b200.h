@@ -190,6 +190,11 @@ NEO_B200_API int neo_b200_conv_process(neo_b200_conv* conv, void const* in, void
  * [outputs][blocks][B] complex in an internal packed layout (device pointer below; sum across shards elementwise);
  * inverse = c2r + overlap handling of (already summed) spectra for outputs [first, first+count). */
 NEO_B200_API int neo_b200_conv_forward(neo_b200_conv* conv, void const* in, size_t blocks, int memspace);
+/* the same for the channel range [first, first+count) only (diagonal topology, DEVICE memory, `in` is still the whole
+ * [inputs][blocks*B] array): lets a caller overlap the reduction of one channel group with the MAC of the next.
+ * Every channel must be covered exactly once per call; pass final != 0 with the last range (the ring position then advances). */
+NEO_B200_API int neo_b200_conv_forward_range(
+    neo_b200_conv* conv, void const* in, size_t blocks, size_t first, size_t count, int final);
 NEO_B200_API int neo_b200_conv_spectra(neo_b200_conv* conv, void** device_ptr, size_t* bytes_per_output_block);
 NEO_B200_API int neo_b200_conv_inverse(
     neo_b200_conv* conv, void const* spectra_device, void* out, size_t first, size_t count, size_t blocks, int memspace);

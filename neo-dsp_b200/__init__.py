@@ -83,6 +83,7 @@ SIGNATURES = {
     "neo_b200_conv_reset": (_i, [_vp]),
     "neo_b200_conv_process": (_i, [_vp, _vp, _vp, _sz, _i]),
     "neo_b200_conv_forward": (_i, [_vp, _vp, _sz, _i]),
+    "neo_b200_conv_forward_range": (_i, [_vp, _vp, _sz, _sz, _sz, _i]),
     "neo_b200_conv_spectra": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "neo_b200_conv_inverse": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _i]),
     "neo_b200_conv_set_stream": (_i, [_vp, _vp]),
@@ -413,6 +414,11 @@ class Convolver:
     def forward(self, x) -> None:
         block = int(self.cfg.block)
         _check(library().neo_b200_conv_forward(self._h, _ptr(x), x.shape[1] // block, _space(x)))
+
+    def forward_range(self, x, first: int, count: int, final: bool) -> None:
+        """forward() for channels [first, first+count) only; x is the whole [inputs][T*B] device array."""
+        block = int(self.cfg.block)
+        _check(library().neo_b200_conv_forward_range(self._h, _ptr(x), x.shape[1] // block, first, count, int(final)))
 
     def spectra_ptr(self) -> tuple[int, int]:
         p, n = _vp(), _sz(0)

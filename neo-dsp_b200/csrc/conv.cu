@@ -629,6 +629,30 @@ int neo_b200_conv_forward(neo_b200_conv* conv, void const* in, size_t blocks, in
     return conv_forward_impl<double>(conv, conv->f64, in, blocks, memspace);
 }
 
+extern "C++" template<typename T>
+int conv_forward_range_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, size_t blocks, size_t first, size_t count, int final)
+{
+    cudaStream_t const s = conv->stream.stream;
+    size_t const stride  = blocks * e.m;
+    NEO_TRY(e.forward_r2c(static_cast<T const*>(in) + first * stride, stride, blocks, first, count, s));
+    NEO_TRY(e.forward_mac(blocks, first, count, s));
+    if (final != 0) {
+        NEO_TRY(e.reduce_planes(blocks, s));  // small banks split the partition loop over CTAs: fold the partial planes once
+        e.advance(blocks);
+    }
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_forward_range(neo_b200_conv* conv, void const* in, size_t blocks, size_t first, size_t count, int final)
+{
+    NEO_TRY(conv_check_call(conv, blocks));
+    if (in == nullptr) { return fail(NEO_B200_ERR_INVALID, "null buffer"); }
+    if (conv->cfg.topology != NEO_B200_DIAGONAL) { return fail(NEO_B200_ERR_INVALID, "forward_range needs the diagonal topology"); }
+    if (count == 0 || first + count > conv->cfg.outputs) { return fail(NEO_B200_ERR_INVALID, "bad channel range"); }
+    if (conv->cfg.dtype == NEO_B200_F32) { return conv_forward_range_impl<float>(conv, conv->f32, in, blocks, first, count, final); }
+    return conv_forward_range_impl<double>(conv, conv->f64, in, blocks, first, count, final);
+}
+
 int neo_b200_conv_spectra(neo_b200_conv* conv, void** device_ptr, size_t* bytes_per_output_block)
 {
     if (conv == nullptr || device_ptr == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }

@@ -69,6 +69,30 @@ def main():
             got[:, pos * B : (pos + T) * B] = y.cpu().numpy()
         err = np.linalg.norm(got - want[c0:c1]) / np.linalg.norm(want[c0:c1])
         assert err < 1e-5, err
+
+        # the grouped form bench.py uses: channel groups, async reduce-scatter of one group while the next group's MAC runs;
+        # rank r then owns the r-th slice of every group
+        conv.reset()
+        groups, gch = 2, C // 2
+        gsh = gch // world
+        mine = [g * gch + rank * gsh + i for g in range(groups) for i in range(gsh)]
+        got2 = np.zeros((len(mine), B * NB), dtype=np.float32)
+        shards = [torch.empty((gsh, T, 2 * B), device="cuda", dtype=torch.float32) for _ in range(groups)]
+        for pos in range(0, NB, T):
+            x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + T) * B])).cuda()
+            y = torch.empty((groups, gsh, T * B), device="cuda", dtype=torch.float32)
+            spectra = conv.spectra_tensor(T)
+            works = []
+            for g in range(groups):
+                conv.forward_range(x, g * gch, gch, g == groups - 1)
+                works.append(dist.reduce_scatter_tensor(shards[g], spectra[g * gch : (g + 1) * gch], async_op=True))
+            for g in range(groups):
+                works[g].wait()
+                conv.inverse(shards[g], y[g], g * gch + rank * gsh, gsh, T)
+            torch.cuda.synchronize()
+            got2[:, pos * B : (pos + T) * B] = y.view(-1, T * B).cpu().numpy()
+        err2 = np.linalg.norm(got2 - want[mine]) / np.linalg.norm(want[mine])
+        assert err2 < 1e-5, err2
     dist.barrier()
     if rank == 0:
         print(f"dist_worker ok backend={args.backend} world={world} err={err:.2e}")
