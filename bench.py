@@ -219,6 +219,52 @@ def fft_sweep(pkg, torch, peak):
     return out
 
 
+def run_channel_sharded(args, torch, dist, pkg, emit, rank, world, local):
+    """Alternative multi-GPU layout: channels [r*C/G, (r+1)*C/G) with their whole filters on rank r, no
+    data-path collective at all. Not BASELINE config 5's prescribed sharding; reported for comparison (--shard channels)."""
+    T = args.blocks
+    ch = CHANNELS // world
+    stream = torch.cuda.current_stream()
+    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=T)
+    conv.set_stream(stream)
+    gen = torch.Generator(device="cuda").manual_seed(11 + rank)
+    ir = torch.rand((ch, TAPS), device="cuda", dtype=torch.float32, generator=gen) * 2 - 1
+    ir *= 1.0 / ir.square().sum(dim=1).max().sqrt()
+    conv.impulse(ir, BLOCK)
+    del ir
+    xs = [torch.rand((ch, T * BLOCK), device="cuda", dtype=torch.float32) * 2 - 1 for _ in range(4)]
+    ys = torch.empty((ch, T * BLOCK), device="cuda", dtype=torch.float32)
+    for i in range(max(3, args.warmup)):
+        conv(xs[i % 4], out=ys)
+    dist.barrier()
+    torch.cuda.synchronize()
+    launches0 = pkg.kernel_launches()
+    start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        start.record()
+        for i in range(args.steps):
+            conv(xs[i % 4], out=ys)
+        stop.record()
+        dist.barrier()
+        torch.cuda.synchronize()
+    t = torch.tensor([start.elapsed_time(stop)], device="cuda", dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    if rank == 0:
+        value = CHANNELS * BLOCK * T * args.steps / (ms_total * 1e-3) / 1e6
+        emit({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "C5: 1024 channels x 2^20-tap IR each, UPOLS B=1024 (P=1024, K=1025), white-noise input",
+                       "blocks_per_call": T, "sharding": f"channels sharded {world}-way, no collective (alternative layout)",
+                       "realtime_x_wall_1024ch_48k": value * 1e6 / CHANNELS / 48000.0},
+            "clocks": clocks.summary(), "gpu_launches": pkg.kernel_launches() - launches0,
+        })
+    dist.barrier()
+    dist.destroy_process_group()
+
+
 def run_ours(args):
     # stdout carries exactly ONE JSON line: native libraries (NCCL's version banner) write to fd 1 too, so fd 1 is pointed at
     # stderr for the duration of the run and the line goes to the saved descriptor
@@ -258,6 +304,10 @@ def run_ours(args):
         return
 
     # ---- state: random impulse responses (unit energy like normalize_impulse), partitioned on the device ----
+    by_channel = args.shard == "channels" and world > 1
+    if by_channel:
+        run_channel_sharded(args, torch, dist, pkg, emit, rank, world, local)
+        return
     lo, hi = rank * PARTS // world, (rank + 1) * PARTS // world
     conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=T, partition_range=(lo, hi) if world > 1 else None)
     conv.set_stream(stream)
@@ -275,7 +325,9 @@ def run_ours(args):
     shard = CHANNELS // world
     # sharded runs walk the bank in channel groups so that the NCCL reduce-scatter of one group's partial spectra overlaps the
     # MAC of the next; rank r ends up owning the r-th slice of every group
-    groups = 4 if world > 1 else 1
+    # (measured at 8 GPUs: 4 groups LOSE, 20.8k vs 22.8k channel-Msamples/s -- a rank holds only 128 partitions, so quartering the
+    # channels makes every MAC launch too short; the default is therefore one group, --groups overrides)
+    groups = max(1, args.groups) if world > 1 else 1
     gch = CHANNELS // groups          # channels per group
     gsh = gch // world                # of which this rank keeps gsh after the reduce-scatter
     spectra_shard = [torch.empty((gsh, T, 2 * BLOCK), device="cuda", dtype=torch.float32) for _ in range(groups)] if world > 1 else None
@@ -528,6 +580,9 @@ def main():
     ap.add_argument("--no-fft-sweep", action="store_true")
     ap.add_argument("--fft-only", action="store_true")
     ap.add_argument("--no-modes", action="store_true", help="skip the extra T=1 / T=32 measurements")
+    ap.add_argument("--shard", default="partitions", choices=["partitions", "channels"],
+                    help="multi-GPU layout: BASELINE config 5's partition sharding + NCCL reduce (default) or plain channel sharding")
+    ap.add_argument("--groups", type=int, default=1, help="channel groups per sharded step (overlap of reduce-scatter and MAC)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args, int(os.environ.get("RANK", "0")))
