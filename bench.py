@@ -343,10 +343,38 @@ def run_ours(args):
             works[gi].wait()
             conv.inverse(spectra_shard[gi], ys_shard[gi], gi * gch + rank * gsh, gsh, T)
 
+    # software pipeline across steps (throughput mode): the reduce-scatter of step i runs on NCCL's stream while step i+1's
+    # r2c + MAC run; step i's c2r follows one step later. The partial spectra are copied out of the handle first (134 MB D2D)
+    # so the next forward may overwrite them. drain() finishes the last step inside the timed region.
+    pipelined = world > 1 and groups == 1 and not args.no_pipeline
+    pending = []
+    if pipelined:
+        stage = [torch.empty((CHANNELS, T, 2 * BLOCK), device="cuda", dtype=torch.float32) for _ in range(2)]
+        shard2 = [torch.empty((shard, T, 2 * BLOCK), device="cuda", dtype=torch.float32) for _ in range(2)]
+
+    def finish(slot, work):
+        work.wait()
+        conv.inverse(shard2[slot], ys_shard.view(shard, T * BLOCK), rank * shard, shard, T)
+
+    def pipelined_step(i, x):
+        slot = i % 2
+        conv.forward(x)
+        stage[slot].copy_(conv.spectra_tensor(T))
+        work = dist.reduce_scatter_tensor(shard2[slot], stage[slot], async_op=True)
+        if pending:
+            finish(*pending.pop())
+        pending.append((slot, work))
+
+    def drain():
+        while pending:
+            finish(*pending.pop())
+
     def step(i):
         x = xs[i % nbuf]
         if world == 1:
             conv(x, out=ys)
+        elif pipelined:
+            pipelined_step(i, x)
         else:
             sharded_step(x)
 
@@ -357,6 +385,7 @@ def run_ours(args):
 
     for i in range(max(3, args.warmup)):
         step(i)
+    drain()
     barrier()
     launches0 = pkg.kernel_launches()
     conv.profile(True)
@@ -367,6 +396,7 @@ def run_ours(args):
         start.record()
         for i in range(args.steps):
             step(i)
+        drain()
         stop.record()
         barrier()
     ms_total = start.elapsed_time(stop)
@@ -408,7 +438,7 @@ def run_ours(args):
         hy = torch.empty((shard, T * BLOCK), dtype=torch.float32).pin_memory()
         dx = torch.empty((CHANNELS, T * BLOCK), device="cuda", dtype=torch.float32)
 
-        def e2e_step():
+        def e2e_step():  # one call at a time, fully synchronous: no cross-step pipelining here
             dx.copy_(hx, non_blocking=True)
             sharded_step(dx)
             hy.copy_(ys_shard.view(shard, T * BLOCK), non_blocking=True)
@@ -548,7 +578,8 @@ def run_ours(args):
             "blocks_per_call": T,
             "mode": "streaming (reference call shape)" if T == 1 else f"time-batched, {T} blocks per call",
             "sharding": "none" if world == 1 else f"partitions sharded {world}-way + NCCL reduce-scatter of partial spectra, "
-                        f"{groups} channel groups so the reduction of one overlaps the MAC of the next",
+                        + ("the reduce-scatter of step i overlaps the r2c+MAC of step i+1 (c2r one step later, drained inside the timed region)"
+                           if pipelined else f"{groups} channel group(s) per step"),
             "l2": "working set per step (filter+FDL, 17 GB at 1 GPU) exceeds the 126 MB L2; 4 rotating input buffers",
             "realtime_x_aggregate_48k": value * 1e6 / 48000.0,
             "realtime_x_wall_1024ch_48k": value * 1e6 / CHANNELS / 48000.0,
@@ -582,6 +613,7 @@ def main():
     ap.add_argument("--no-modes", action="store_true", help="skip the extra T=1 / T=32 measurements")
     ap.add_argument("--shard", default="partitions", choices=["partitions", "channels"],
                     help="multi-GPU layout: BASELINE config 5's partition sharding + NCCL reduce (default) or plain channel sharding")
+    ap.add_argument("--no-pipeline", action="store_true", help="sharded runs: do not overlap step i's reduce-scatter with step i+1")
     ap.add_argument("--groups", type=int, default=1, help="channel groups per sharded step (overlap of reduce-scatter and MAC)")
     args = ap.parse_args()
     if args.impl == "reference":
