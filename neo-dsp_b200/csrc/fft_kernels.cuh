@@ -28,6 +28,9 @@ struct fft_cfg
     static constexpr int THREADS = TN * G;
     static constexpr int TILE    = F::TILE;
     static constexpr size_t SMEM = size_t(G) * TILE * sizeof(cx<T>);
+    // measured: forcing <= 64 registers (1024 resident threads per SM) spills in c2r and loses 5-13 points of roofline,
+    // so the compiler's own allocation (60-73 registers) stands
+    static constexpr int MIN_CTAS = 1;
 };
 
 // ---- twiddle tables (host, computed in double, rounded once) --------------------------------------------------------
@@ -71,7 +74,7 @@ std::vector<cx<T>> make_split_twiddles(int logm)
 
 // ---- c2c -------------------------------------------------------------------------------------------------------------
 template<typename T, int LOGM, int DIR>
-__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::MIN_CTAS)
     c2c_kernel(cx<T> const* __restrict__ in, cx<T>* __restrict__ out, cx<T> const* __restrict__ tw, size_t batch)
 {
     using cfg = fft_cfg<T, LOGM>;
@@ -101,7 +104,7 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
 
 // ---- r2c: IO policy provides load(b, j) -> z[j] and the spectrum stores ------------------------------------------------
 template<typename T, int LOGM, class IO>
-__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::MIN_CTAS)
     r2c_kernel(IO io, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ rtw, size_t batch)
 {
     using cfg = fft_cfg<T, LOGM>;
@@ -143,7 +146,7 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
 
 // ---- c2r: IO policy provides the spectrum loads and store(b, j, z[j]) -----------------------------------------------------
 template<typename T, int LOGM, class IO>
-__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::MIN_CTAS)
     c2r_kernel(IO io, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ rtw, size_t batch)
 {
     using cfg = fft_cfg<T, LOGM>;
@@ -157,36 +160,30 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS)
     size_t const b  = size_t(blockIdx.x) * cfg::G + g;
     bool const live = b < batch;
 
+    // Hermitian pre-pass straight from global memory: X[k] and its partner X[M-k] are both loaded by this thread (the partner
+    // line is the one a sibling thread loads as its own X[k], so the second touch is an L1 hit); no shared-memory round trip
+    // and all 2E loads are in flight at once
     C v[cfg::E];
     typename IO::row_state row = io.open(live ? b : 0);
+    C own[cfg::E], mate[cfg::E];
 #pragma unroll
     for (int e = 0; e < cfg::E; ++e) {
         int const k = t + e * cfg::TN;
         if (!live) {
-            v[e] = mk<T>(0, 0);
+            own[e] = mate[e] = mk<T>(0, 0);
         } else if (k == 0) {
-            v[e] = io.load_edges(row);  // (Re X[0], Re X[M])
+            own[e]  = io.load_edges(row);  // (Re X[0], Re X[M])
+            mate[e] = own[e];
         } else {
-            v[e] = io.load(row, k);
+            own[e]  = io.load(row, k);
+            mate[e] = io.load(row, cfg::M - k);
         }
     }
-    if constexpr (LOGM > 0) {
 #pragma unroll
-        for (int e = 0; e < cfg::E; ++e) { sm[padded<T>(t + e * cfg::TN)] = v[e]; }
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < cfg::E; ++e) {
-            int const k = t + e * cfg::TN;
-            if (k == 0) {
-                v[e] = mk<T>(v[e].x + v[e].y, v[e].x - v[e].y);
-            } else {
-                C const xp = sm[padded<T>(cfg::M - k)];
-                v[e]       = c2r_pre(v[e], xp, __ldg(rtw + k));
-            }
-        }
-        __syncthreads();
-    } else {
-        v[0] = mk<T>(v[0].x + v[0].y, v[0].x - v[0].y);
+    for (int e = 0; e < cfg::E; ++e) {
+        int const k = t + e * cfg::TN;
+        if (k == 0) { v[e] = mk<T>(own[e].x + own[e].y, own[e].x - own[e].y); }
+        else { v[e] = c2r_pre(own[e], mate[e], __ldg(rtw + k)); }
     }
 
     F::run(v, sm, tw, t);
