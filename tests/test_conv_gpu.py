@@ -161,6 +161,53 @@ def test_matrix_topology_equals_sum_of_reference_convolvers(gpu, orc):
         conv.close()
 
 
+def test_wide_bank_host_pipeline_and_device_path_agree_with_oracle(gpu, orc):
+    # >= 128 channels and >= 4 blocks per call: host-buffer calls are cut into channel groups and pipelined over copy streams
+    import torch
+
+    C, B, P, NB = 160, 64, 5, 16
+    ir, sig = make_case(orc, C, B * P - 3, B, NB)
+    H = orc.uniform_partition(ir, B)
+    want = orc.convolve_blocks(0, H, sig)
+    for pattern in ([4], [8, 4, 1, 3]):
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, max_blocks=8)
+        conv.filter(H)
+        assert rel_l2(run_bank(conv, sig, B, pattern), want) <= 1e-5, pattern
+        conv.close()
+    conv = gpu.Convolver(gpu.UPOLA, np.float32, gpu.DIAGONAL, max_blocks=8)
+    conv.filter(H)
+    assert rel_l2(run_bank(conv, sig, B, [8]), orc.convolve_blocks(1, H, sig)) <= 1e-5
+    conv.close()
+    # same bank with device-resident buffers on a caller-provided stream
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, max_blocks=8)
+    conv.set_stream(torch.cuda.current_stream())
+    conv.filter(torch.from_numpy(H).cuda())
+    dx = torch.from_numpy(sig).cuda()
+    dy = torch.empty_like(dx)
+    for pos in range(0, NB, 8):
+        chunk = dx[:, pos * B : (pos + 8) * B].contiguous()
+        out = torch.empty_like(chunk)
+        conv(chunk, out=out)
+        dy[:, pos * B : (pos + 8) * B] = out
+    torch.cuda.synchronize()
+    assert rel_l2(dy.cpu().numpy(), want) <= 1e-5
+
+
+def test_matrix_topology_four_outputs_per_thread_path(gpu, orc):
+    # outputs % 4 == 0 selects the output-tiled streaming MAC (T = 1) for the matrix topology
+    O, I, B, L, NB = 8, 3, 128, 128 * 6, 9
+    ir = np.stack([np.stack([orc.noise(L, 300 + 10 * o + i, np.float32) for i in range(I)]) for o in range(O)])
+    ir /= np.sqrt((ir**2).sum(axis=2).max())
+    sig = np.stack([orc.noise(B * NB, 13 + i, np.float32) for i in range(I)])
+    want = np.stack([orc.convolve_blocks(0, orc.uniform_partition(ir[o], B), sig).astype(np.float64).sum(axis=0) for o in range(O)])
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.MATRIX, max_blocks=2)
+    conv.impulse(ir, B)
+    got = np.zeros((O, B * NB), dtype=np.float32)
+    for b in range(NB):
+        got[:, b * B : (b + 1) * B] = conv(np.ascontiguousarray(sig[:, b * B : (b + 1) * B]))
+    assert rel_l2(got, want) <= 1e-5
+
+
 def test_partition_sharded_handles_sum_to_the_whole(gpu, orc):
     # one long IR split over "devices": partial spectra add up; inverse runs on the sum (last row)
     import torch
