@@ -308,3 +308,37 @@ def test_python_convolve_front_end(gpu, orc):
         with pytest.raises(RuntimeError):
             gpu.convolve(sig, sig, mode=mode)
     assert gpu.convolve(np.zeros(0, dtype=np.float32), sig).size == 0  # empty-input edge case (direct_convolve_test.cpp)
+
+
+def test_baseline_config4_full_size_matrix_routing(gpu, orc):
+    # BASELINE config 4 at full size: 64 in x 64 out, B=256, 2^16-tap IRs (2.2 GB of filter spectra). Property: an impulse-response
+    # matrix of unit impulses h[o][i] = delta(n - d(o,i)) * g(o,i) makes every output a gain-weighted sum of delayed inputs.
+    import torch
+
+    O = I = 64
+    B, L, NB = 256, 1 << 16, 8
+    rng = np.random.default_rng(5)
+    delays = rng.integers(0, B * NB // 2, size=(O, I))
+    gains = rng.uniform(-1, 1, size=(O, I)).astype(np.float32)
+    ir = torch.zeros((O, I, L), device="cuda")
+    oo, ii = np.meshgrid(np.arange(O), np.arange(I), indexing="ij")
+    ir[torch.from_numpy(oo.ravel()).cuda(), torch.from_numpy(ii.ravel()).cuda(), torch.from_numpy(delays.ravel()).cuda()] = torch.from_numpy(gains.ravel()).cuda()
+    sig = np.stack([orc.noise(B * NB, 400 + i, np.float32) for i in range(I)])
+    want = np.zeros((O, B * NB), dtype=np.float64)
+    for o in range(O):
+        for i in range(I):
+            d = int(delays[o, i])
+            want[o, d:] += gains[o, i] * sig[i, : B * NB - d]
+    for T in (1, 4):
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.MATRIX, max_blocks=T)
+        conv.set_stream(torch.cuda.current_stream())
+        conv.impulse(ir, B)
+        got = np.zeros((O, B * NB), dtype=np.float32)
+        for pos in range(0, NB, T):
+            x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + T) * B])).cuda()
+            y = torch.empty((O, T * B), device="cuda")
+            conv(x, out=y)
+            torch.cuda.synchronize()
+            got[:, pos * B : (pos + T) * B] = y.cpu().numpy()
+        assert rel_l2(got, want) <= 1e-5, T
+        conv.close()

@@ -200,3 +200,31 @@ def test_python_front_end(gpu):
             assert y.shape == (n,) and np.allclose(y, x, atol=1e-6)
     with pytest.raises(RuntimeError):
         gpu.fft(np.zeros(12, dtype=np.complex64))  # non power of two (main.cpp:137-139)
+
+
+@pytest.mark.parametrize("order", [10, 13, 16])
+def test_baseline_config2_full_batch_properties(gpu, order):
+    # BASELINE config 2 at its full size (batch = 2^29/N, 2 GiB in): size-independent properties on the device --
+    # unnormalised round trip gains N, Parseval with the Hermitian weights, DC bin = row sum
+    import torch
+
+    n = 1 << order
+    batch = (1 << 29) // n
+    gen = torch.Generator(device="cuda").manual_seed(2)
+    x = torch.rand((batch, n), device="cuda", generator=gen) * 2 - 1
+    plan = gpu.RFFTPlan(order, "float32")
+    plan.set_stream(torch.cuda.current_stream())
+    spec = plan.rfft(x)
+    back = plan.irfft(spec)
+    torch.cuda.synchronize()
+    err = (back / n - x).double().norm() / x.double().norm()
+    assert float(err) <= 1e-5
+    power = spec.abs().double().square()
+    weights = torch.full((n // 2 + 1,), 2.0, device="cuda", dtype=torch.float64)
+    weights[0] = weights[-1] = 1.0
+    lhs = (power * weights).sum(dim=1) / n
+    rhs = x.double().square().sum(dim=1)
+    assert float(((lhs - rhs).abs() / rhs).max()) < 1e-5
+    assert float((spec[:, 0].real.double() - x.double().sum(dim=1)).abs().max()) < 1e-2
+    assert float(spec[:, 0].imag.abs().max()) == 0.0 and float(spec[:, -1].imag.abs().max()) == 0.0
+    plan.close()
