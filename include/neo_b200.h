@@ -86,6 +86,11 @@ NEO_B200_API size_t neo_b200_fft_max_order(void);                           /* c
  * otherwise out-of-place (the optional 3-argument overload looked up by fft/fft.hpp:65,84). */
 NEO_B200_API int neo_b200_fft_exec(neo_b200_fft_plan* plan, void const* in, void* out, size_t batch, int direction, int memspace);
 
+/* the same on split-complex data (neo::split_complex, complex/split_complex.hpp:10): separate [batch][size] real and imaginary
+ * planes; replaces neo::fft::split_fft_plan<Float> (fft/fallback/fallback_split_fft_plan.hpp:16-137). in == out planes allowed. */
+NEO_B200_API int neo_b200_fft_exec_split(neo_b200_fft_plan* plan, void const* re_in, void const* im_in, void* re_out, void* im_out,
+                                         size_t batch, int direction, int memspace);
+
 /* one transform over a strided rank-1 view (strides in complex elements; layout_stride mdspan, fft_test.cpp:114-128);
  * HOST memory only: staged through a contiguous buffer like backend/ipp.hpp:150-158 */
 NEO_B200_API int neo_b200_fft_exec_strided(

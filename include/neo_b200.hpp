@@ -130,6 +130,64 @@ private:
     std::vector<Complex> _staging;
 };
 
+/// Drop-in for neo::fft::split_fft_plan<Float> (fft/fallback/fallback_split_fft_plan.hpp:16-137): operates on any aggregate with
+/// `.real` / `.imag` rank-1 views (neo::split_complex, complex/split_complex.hpp:10).
+template<typename Float>
+struct split_fft_plan
+{
+    using value_type = Float;
+    using size_type  = std::size_t;
+
+    template<typename Tag>
+    split_fft_plan(Tag /*from_order*/, size_type order)
+    {
+        detail::check(neo_b200_fft_plan_create(&_plan, order, detail::dtype_of<Float>));
+    }
+    split_fft_plan(split_fft_plan const&)                    = delete;
+    auto operator=(split_fft_plan const&) -> split_fft_plan& = delete;
+    split_fft_plan(split_fft_plan&& other) noexcept : _plan{std::exchange(other._plan, nullptr)} {}
+    ~split_fft_plan() { neo_b200_fft_plan_destroy(_plan); }
+
+    [[nodiscard]] auto order() const noexcept -> size_type { return neo_b200_fft_plan_order(_plan); }
+    [[nodiscard]] auto size() const noexcept -> size_type { return neo_b200_fft_plan_size(_plan); }
+
+    template<typename Split, typename Direction>
+    auto operator()(Split x, Direction dir) -> void
+    {
+        (*this)(x, x, dir);
+    }
+
+    template<typename SplitIn, typename SplitOut, typename Direction>
+    auto operator()(SplitIn in, SplitOut out, Direction dir) -> void
+    {
+        auto const n = size();
+        auto gather  = [n](auto view, std::vector<Float>& tmp) -> Float const* {
+            if (detail::is_contiguous(view)) { return view.data_handle(); }
+            tmp.resize(n);
+            for (size_type i = 0; i < n; ++i) { tmp[i] = view[i]; }
+            return tmp.data();
+        };
+        Float const* re = gather(in.real, _re_in);
+        Float const* im = gather(in.imag, _im_in);
+        bool const direct = detail::is_contiguous(out.real) && detail::is_contiguous(out.imag);
+        _re_out.resize(direct ? 0 : n);
+        _im_out.resize(direct ? 0 : n);
+        Float* ro = direct ? out.real.data_handle() : _re_out.data();
+        Float* io = direct ? out.imag.data_handle() : _im_out.data();
+        detail::check(neo_b200_fft_exec_split(_plan, re, im, ro, io, 1, detail::direction_value(dir), NEO_B200_HOST));
+        if (!direct) {
+            for (size_type i = 0; i < n; ++i) {
+                out.real[i] = _re_out[i];
+                out.imag[i] = _im_out[i];
+            }
+        }
+    }
+
+private:
+    neo_b200_fft_plan* _plan{nullptr};
+    std::vector<Float> _re_in, _im_in, _re_out, _im_out;
+};
+
 /// Drop-in for neo::fft::rfft_plan<Float, Complex> (fft/fallback/fallback_rfft_plan.hpp:15-61): two call operators told apart
 /// by element type, real -> complex (N/2+1 bins written) and complex -> real (unnormalised).
 template<typename Float, typename Complex = std::complex<Float>>

@@ -59,6 +59,7 @@ SIGNATURES = {
     "neo_b200_fft_plan_size": (_sz, [_vp]),
     "neo_b200_fft_max_order": (_sz, []),
     "neo_b200_fft_exec": (_i, [_vp, _vp, _vp, _sz, _i, _i]),
+    "neo_b200_fft_exec_split": (_i, [_vp, _vp, _vp, _vp, _vp, _sz, _i, _i]),
     "neo_b200_fft_exec_strided": (_i, [_vp, _vp, C.c_ssize_t, _vp, C.c_ssize_t, _i]),
     "neo_b200_fft_plan_set_stream": (_i, [_vp, _vp]),
     "neo_b200_fft_plan_synchronize": (_i, [_vp]),
@@ -209,6 +210,15 @@ class FFTPlan:
         batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
         _check(library().neo_b200_fft_exec(self._h, _ptr(x), _ptr(out), batch, direction, _space(x)))
         return out
+
+    def split(self, re, im, direction: int = FORWARD):
+        """neo::fft::split_fft_plan (fft/fallback/fallback_split_fft_plan.hpp:27-51): in-place transform of separate real and
+        imaginary planes re[..., size], im[..., size]."""
+        if _dtype_name(re) != self.real or _dtype_name(im) != self.real or re.shape != im.shape or re.shape[-1] != self.size():
+            raise ValueError(f"expected two {self.real}[..., {self.size()}] planes")
+        batch = int(np.prod(re.shape[:-1], dtype=np.int64)) if re.ndim > 1 else 1
+        _check(library().neo_b200_fft_exec_split(self._h, _ptr(re), _ptr(im), _ptr(re), _ptr(im), batch, direction, _space(re)))
+        return re, im
 
     def strided(self, x: np.ndarray, direction: int = FORWARD) -> None:
         """In-place transform of a strided rank-1 numpy view (layout_stride mdspan, fft_test.cpp:114-128)."""

@@ -72,10 +72,37 @@ std::vector<cx<T>> make_split_twiddles(int logm)
     return lut;
 }
 
-// ---- c2c -------------------------------------------------------------------------------------------------------------
-template<typename T, int LOGM, int DIR>
+// ---- c2c: IO policy provides load(b, j) / store(b, j, v) for interleaved or split-complex (SoA) data -----------------------
+template<typename T>
+struct c2c_interleaved_io
+{
+    cx<T> const* in;
+    cx<T>* out;
+    size_t m;
+    __device__ __forceinline__ cx<T> load(size_t b, int j) const { return in[b * m + j]; }
+    __device__ __forceinline__ void store(size_t b, int j, cx<T> v) const { out[b * m + j] = v; }
+};
+
+// neo::split_complex (complex/split_complex.hpp:10): separate real / imag planes, [batch][m] each
+template<typename T>
+struct c2c_split_io
+{
+    T const* re_in;
+    T const* im_in;
+    T* re_out;
+    T* im_out;
+    size_t m;
+    __device__ __forceinline__ cx<T> load(size_t b, int j) const { return mk<T>(re_in[b * m + j], im_in[b * m + j]); }
+    __device__ __forceinline__ void store(size_t b, int j, cx<T> v) const
+    {
+        re_out[b * m + j] = v.x;
+        im_out[b * m + j] = v.y;
+    }
+};
+
+template<typename T, int LOGM, int DIR, class IO>
 __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::MIN_CTAS)
-    c2c_kernel(cx<T> const* __restrict__ in, cx<T>* __restrict__ out, cx<T> const* __restrict__ tw, size_t batch)
+    c2c_kernel(IO io, cx<T> const* __restrict__ tw, size_t batch)
 {
     using cfg = fft_cfg<T, LOGM>;
     using F   = cta_fft<T, LOGM, DIR>;
@@ -89,16 +116,14 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::M
     bool const live = b < batch;
 
     C v[cfg::E];
-    C const* src = in + b * cfg::M;
 #pragma unroll
-    for (int e = 0; e < cfg::E; ++e) { v[e] = live ? src[t + e * cfg::TN] : mk<T>(0, 0); }
+    for (int e = 0; e < cfg::E; ++e) { v[e] = live ? io.load(b, t + e * cfg::TN) : mk<T>(0, 0); }
 
     F::run(v, sm + g * cfg::TILE, tw, t);
 
     if (live) {
-        C* dst = out + b * cfg::M;
 #pragma unroll
-        for (int e = 0; e < cfg::E; ++e) { dst[t + e * cfg::TN] = v[e]; }
+        for (int e = 0; e < cfg::E; ++e) { io.store(b, t + e * cfg::TN, v[e]); }
     }
 }
 
@@ -277,16 +302,41 @@ int launch_c2r(IO const& io, cx<T> const* tw, cx<T> const* rtw, size_t batch, cu
     return check_launch("c2r_kernel");
 }
 
-template<typename T, int LOGM, int DIR>
-int launch_c2c(cx<T> const* in, cx<T>* out, cx<T> const* tw, size_t batch, cudaStream_t stream)
+template<typename T, int LOGM, int DIR, class IO>
+int launch_c2c_io(IO const& io, cx<T> const* tw, size_t batch, cudaStream_t stream)
 {
     using cfg = fft_cfg<T, LOGM>;
     if (batch == 0) { return NEO_B200_OK; }
-    auto kernel = c2c_kernel<T, LOGM, DIR>;
+    auto kernel = c2c_kernel<T, LOGM, DIR, IO>;
     NEO_TRY(enable_smem(kernel, cfg::SMEM));
     size_t const grid = (batch + cfg::G - 1) / cfg::G;
-    kernel<<<static_cast<unsigned>(grid), cfg::THREADS, cfg::SMEM, stream>>>(in, out, tw, batch);
+    kernel<<<static_cast<unsigned>(grid), cfg::THREADS, cfg::SMEM, stream>>>(io, tw, batch);
     return check_launch("c2c_kernel");
+}
+
+template<typename T, int LOGM, int DIR>
+int launch_c2c(cx<T> const* in, cx<T>* out, cx<T> const* tw, size_t batch, cudaStream_t stream)
+{
+    return launch_c2c_io<T, LOGM, DIR>(c2c_interleaved_io<T>{in, out, size_t(1) << LOGM}, tw, batch, stream);
+}
+
+// split <-> interleaved conversion for transforms that do not fit one CTA
+template<typename T>
+__global__ void __launch_bounds__(256) split_to_interleaved_kernel(T const* __restrict__ re, T const* __restrict__ im, cx<T>* __restrict__ out, size_t n)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) { out[i] = mk<T>(re[i], im[i]); }
+}
+
+template<typename T>
+__global__ void __launch_bounds__(256) interleaved_to_split_kernel(cx<T> const* __restrict__ in, T* __restrict__ re, T* __restrict__ im, size_t n)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i < n) {
+        cx<T> const v = in[i];
+        re[i] = v.x;
+        im[i] = v.y;
+    }
 }
 
 // device-resident twiddle tables of one transform size

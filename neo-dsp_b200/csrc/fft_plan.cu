@@ -103,6 +103,40 @@ struct c2c_engine
         if (status == NEO_B200_ERR_UNSUPPORTED) { return fail(status, "c2c order %d not supported", order); }
         return status;
     }
+
+    // split-complex (SoA) data, [batch][size] planes; single-CTA sizes run fused, longer ones through an interleaved scratch
+    int exec_planes(T const* re_in, T const* im_in, T* re_out, T* im_out, size_t batch, int direction, cudaStream_t stream)
+    {
+        size_t const n = size_t(1) << order;
+        if (!use_large && split == 0) {
+            int status = NEO_B200_ERR_UNSUPPORTED;
+            c2c_split_io<T> const io{re_in, im_in, re_out, im_out, n};
+            NEO_DISPATCH_LOGM(T, order, {
+                if constexpr (LOGM <= max_cta_logm<T>()) {
+                    status = direction < 0 ? launch_c2c_io<T, LOGM, -1>(io, tables.tw(), batch, stream)
+                                           : launch_c2c_io<T, LOGM, +1>(io, tables.tw(), batch, stream);
+                }
+            });
+            return status;
+        }
+        size_t const chunk = std::max<size_t>(1, std::min(batch, (size_t(256) << 20) / (n * sizeof(cx<T>))));
+        NEO_TRY(planes.reserve(2 * chunk * n * sizeof(cx<T>)));
+        cx<T>* const a = planes.template as<cx<T>>();
+        cx<T>* const b = a + chunk * n;
+        for (size_t first = 0; first < batch; first += chunk) {
+            size_t const cnt   = std::min(chunk, batch - first);
+            size_t const elems = cnt * n;
+            unsigned const grid = static_cast<unsigned>((elems + 255) / 256);
+            split_to_interleaved_kernel<T><<<grid, 256, 0, stream>>>(re_in + first * n, im_in + first * n, a, elems);
+            NEO_TRY(check_launch("split_to_interleaved_kernel"));
+            NEO_TRY(exec(a, b, cnt, direction, stream));
+            interleaved_to_split_kernel<T><<<grid, 256, 0, stream>>>(b, re_out + first * n, im_out + first * n, elems);
+            NEO_TRY(check_launch("interleaved_to_split_kernel"));
+        }
+        return NEO_B200_OK;
+    }
+
+    device_buffer planes;
 };
 
 template<typename T>
@@ -367,6 +401,45 @@ int neo_b200_fft_exec(neo_b200_fft_plan* plan, void const* in, void* out, size_t
         NEO_CUDA_TRY(cudaMemcpyAsync(plan->staging_in.ptr, static_cast<char const*>(in) + first * row, n * row, cudaMemcpyHostToDevice, s));
         NEO_TRY(fft_exec_device(plan, plan->staging_in.ptr, plan->staging_in.ptr, n, direction));
         NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + first * row, plan->staging_in.ptr, n * row, cudaMemcpyDeviceToHost, s));
+    }
+    NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    return NEO_B200_OK;
+}
+
+int neo_b200_fft_exec_split(neo_b200_fft_plan* plan, void const* re_in, void const* im_in, void* re_out, void* im_out, size_t batch,
+                            int direction, int memspace)
+{
+    if (plan == nullptr || re_in == nullptr || im_in == nullptr || re_out == nullptr || im_out == nullptr) {
+        return fail(NEO_B200_ERR_INVALID, "null argument");
+    }
+    if (direction != NEO_B200_FORWARD && direction != NEO_B200_BACKWARD) {
+        return fail(NEO_B200_ERR_INVALID, "direction must be -1 (forward) or +1 (backward)");
+    }
+    if (batch == 0) { return NEO_B200_OK; }
+    NEO_CUDA_TRY(cudaSetDevice(plan->device));
+    cudaStream_t const s = plan->stream.stream;
+    auto run = [&](void const* ri, void const* ii, void* ro, void* io, size_t n) {
+        if (plan->dtype == NEO_B200_F32) {
+            return plan->f32.exec_planes(static_cast<float const*>(ri), static_cast<float const*>(ii), static_cast<float*>(ro),
+                                         static_cast<float*>(io), n, direction, s);
+        }
+        return plan->f64.exec_planes(static_cast<double const*>(ri), static_cast<double const*>(ii), static_cast<double*>(ro),
+                                     static_cast<double*>(io), n, direction, s);
+    };
+    if (memspace == NEO_B200_DEVICE) { return run(re_in, im_in, re_out, im_out, batch); }
+
+    size_t const row   = (size_t(1) << plan->order) * elem_size(plan->dtype);
+    size_t const chunk = std::max<size_t>(1, std::min(batch, (size_t(128) << 20) / row));
+    NEO_TRY(plan->staging_in.reserve(2 * chunk * row));
+    char* const dre = static_cast<char*>(plan->staging_in.ptr);
+    char* const dim = dre + chunk * row;
+    for (size_t first = 0; first < batch; first += chunk) {
+        size_t const n = std::min(chunk, batch - first);
+        NEO_CUDA_TRY(cudaMemcpyAsync(dre, static_cast<char const*>(re_in) + first * row, n * row, cudaMemcpyHostToDevice, s));
+        NEO_CUDA_TRY(cudaMemcpyAsync(dim, static_cast<char const*>(im_in) + first * row, n * row, cudaMemcpyHostToDevice, s));
+        NEO_TRY(run(dre, dim, dre, dim, n));
+        NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(re_out) + first * row, dre, n * row, cudaMemcpyDeviceToHost, s));
+        NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(im_out) + first * row, dim, n * row, cudaMemcpyDeviceToHost, s));
     }
     NEO_CUDA_TRY(cudaStreamSynchronize(s));
     return NEO_B200_OK;

@@ -64,6 +64,14 @@ for real, cplx, tag in ((np.float32, np.complex64, "f32"), (np.float64, np.compl
     g[f"c2r_junk/{tag}/half"] = r.irfft(junk[: n // 2 + 1], n)
     g[f"c2r_junk/{tag}/full"] = r.irfft(junk, n)
 
+# split-complex plan (fft/fallback/fallback_split_fft_plan.hpp) on the same noise: planes [re, im]
+for real, cplx, tag in ((np.float32, np.complex64, "f32"), (np.float64, np.complex128, "f64")):
+    for order in (1, 4, 8, 11):
+        x = r.noise(1 << order, 1, cplx)
+        for d, name in ((-1, "fwd"), (1, "bwd")):
+            re, im = r.split_fft(x.real.copy(), x.imag.copy(), d)
+            g[f"split/{tag}/{order}/{name}"] = np.stack([re, im])
+
 # known-answer inputs of the reference's own tests, run through the reference
 g["kat/c2c_1234"] = r.fft(np.array([1, 2, 3, 4], dtype=np.complex64), -1)  # fft/rfft_test.cpp:170-186
 delta = np.zeros(16, dtype=np.complex64)

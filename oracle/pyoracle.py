@@ -229,6 +229,13 @@ class _Ref(_Checker):
     def fft_max_order(self) -> int:
         return int(self._fn("fft_max_order", _sz, [])())
 
+    def split_fft(self, re: np.ndarray, im: np.ndarray, direction: int = -1):
+        """split_fft_plan in place on copies of the two planes (1-D)."""
+        re, im = np.ascontiguousarray(re).copy(), np.ascontiguousarray(im).copy()
+        order = int(re.size).bit_length() - 1
+        self._fn("split_fft_" + _SUF[re.dtype], None, [_sz, _vp, _vp, _i])(order, _ptr(re), _ptr(im), direction)
+        return re, im
+
     def overlap_identity(self, add: bool, block: int, filter_size: int, signal: np.ndarray) -> np.ndarray:
         sig = np.ascontiguousarray(signal, dtype=np.float32).copy()
         self._fn("overlap_identity_f32", None, [_i, _sz, _sz, _vp, _sz])(

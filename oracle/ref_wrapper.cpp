@@ -114,6 +114,21 @@ void ref_rfft_f64(std::size_t order, double const* in, double* out) { r2c<double
 void ref_irfft_f32(std::size_t order, float const* in, std::size_t n, float* out) { c2r<float>(order, in, n, out); }
 void ref_irfft_f64(std::size_t order, double const* in, std::size_t n, double* out) { c2r<double>(order, in, n, out); }
 
+// split-complex plan (fft/fallback/fallback_split_fft_plan.hpp:16-137), in place on separate real / imaginary planes
+void ref_split_fft_f32(std::size_t order, float* re, float* im, int direction)
+{
+    auto plan = neo::fft::split_fft_plan<float>{neo::fft::from_order, order};
+    auto x    = neo::split_complex{vec_view<float>{re, plan.size()}, vec_view<float>{im, plan.size()}};
+    plan(x, direction < 0 ? neo::fft::direction::forward : neo::fft::direction::backward);
+}
+
+void ref_split_fft_f64(std::size_t order, double* re, double* im, int direction)
+{
+    auto plan = neo::fft::split_fft_plan<double>{neo::fft::from_order, order};
+    auto x    = neo::split_complex{vec_view<double>{re, plan.size()}, vec_view<double>{im, plan.size()}};
+    plan(x, direction < 0 ? neo::fft::direction::forward : neo::fft::direction::backward);
+}
+
 std::size_t ref_fft_max_order() { return neo::fft::fft_plan<std::complex<float>>::max_order(); }
 std::size_t ref_next_order(std::size_t n) { return neo::fft::next_order(n); }
 

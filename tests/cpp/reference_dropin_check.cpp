@@ -31,6 +31,18 @@ auto instantiate_r2c() -> void
     neo::fft::irfft(plan, cplx.to_mdspan(), real.to_mdspan());
 }
 
+template<typename Float>
+auto instantiate_split() -> void
+{
+    auto plan = neo::b200::split_fft_plan<Float>{neo::fft::from_order, 4};
+    auto re   = stdex::mdarray<Float, stdex::dextents<std::size_t, 1>>{plan.size()};
+    auto im   = stdex::mdarray<Float, stdex::dextents<std::size_t, 1>>{plan.size()};
+    auto x    = neo::split_complex{re.to_mdspan(), im.to_mdspan()};
+    neo::fft::fft(plan, x);        // fft/split_fft.hpp:38-43
+    neo::fft::ifft(plan, x);
+    neo::fft::fft(plan, x, x);     // out-of-place overload, fft/split_fft.hpp:46-51
+}
+
 template<typename Complex>
 auto instantiate_convolver() -> void
 {
@@ -50,6 +62,8 @@ auto instantiate_all() -> void
     instantiate_c2c<std::complex<float>>();
     instantiate_c2c<std::complex<double>>();
     instantiate_c2c<neo::scalar_complex<float>>();
+    instantiate_split<float>();
+    instantiate_split<double>();
     instantiate_r2c<float>();
     instantiate_r2c<double>();
     instantiate_convolver<std::complex<float>>();

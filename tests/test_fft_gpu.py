@@ -228,3 +228,33 @@ def test_baseline_config2_full_batch_properties(gpu, order):
     assert float((spec[:, 0].real.double() - x.double().sum(dim=1)).abs().max()) < 1e-2
     assert float(spec[:, 0].imag.abs().max()) == 0.0 and float(spec[:, -1].imag.abs().max()) == 0.0
     plan.close()
+
+
+def test_split_complex_plan(gpu, orc, golden):
+    # neo::fft::split_fft_plan (fft/split_fft_test.cpp:23-73: round trips in place / copy) + parity with the reference's planes
+    import torch
+
+    for tag, real, cplx in (("f32", np.float32, np.complex64), ("f64", np.float64, np.complex128)):
+        tol = TOL[np.dtype(real).name]
+        for order in (1, 4, 8, 11):
+            x = orc.noise(1 << order, 1, cplx)
+            plan = gpu.FFTPlan(order, cplx)
+            for d, name in ((gpu.FORWARD, "fwd"), (gpu.BACKWARD, "bwd")):
+                re, im = plan.split(np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag), d)
+                want = golden[f"split/{tag}/{order}/{name}"]
+                assert rel_l2(re + 1j * im, want[0] + 1j * want[1]) <= tol, (tag, order, name)
+            re, im = plan.split(np.ascontiguousarray(x.real), np.ascontiguousarray(x.imag), gpu.FORWARD)
+            re, im = plan.split(re, im, gpu.BACKWARD)
+            assert rel_l2((re + 1j * im) / x.size, x) <= tol
+            plan.close()
+    # batched planes on the device, and a size beyond one CTA (interleaved scratch path)
+    for order, batch in ((10, 64), (15, 3)):
+        x = np.stack([orc.noise(1 << order, 5 + b, np.complex64) for b in range(batch)])
+        plan = gpu.FFTPlan(order, np.complex64)
+        plan.set_stream(torch.cuda.current_stream())
+        re, im = torch.from_numpy(np.ascontiguousarray(x.real)).cuda(), torch.from_numpy(np.ascontiguousarray(x.imag)).cuda()
+        plan.split(re, im, gpu.FORWARD)
+        torch.cuda.synchronize()
+        got = re.cpu().numpy() + 1j * im.cpu().numpy()
+        assert rel_l2(got, orc.fft(x, -1)) <= 1e-5, order
+        plan.close()

@@ -124,6 +124,17 @@ def test_transforms_match_reference_golden(orc, golden, tag, real, cplx, tol):
     assert np.array_equal(golden[f"c2r_junk/{tag}/half"], golden[f"c2r_junk/{tag}/full"])
 
 
+def test_split_complex_plan_is_the_same_transform(orc, golden):
+    # fallback_split_fft_plan (SoA planes, backward by swapping the planes) computes what fft_plan computes: the oracle's c2c
+    # stands for both; golden planes come from the reference's split plan itself
+    for tag, cplx, tol in (("f32", np.complex64, 3e-7), ("f64", np.complex128, 1e-15)):
+        for order in (1, 4, 8, 11):
+            x = orc.noise(1 << order, 1, cplx)
+            for d, name in ((-1, "fwd"), (1, "bwd")):
+                planes = golden[f"split/{tag}/{order}/{name}"]
+                assert rel_l2(orc.fft(x, d), planes[0] + 1j * planes[1]) <= tol, (tag, order, name)
+
+
 def test_transforms_against_numpy(orc):
     for order in (1, 3, 6, 9, 12):
         n = 1 << order
