@@ -65,7 +65,8 @@ struct conv_engine
     int tail_flip{0};
 
     fft_tables<T> tables;
-    device_buffer filter, fdl, prev, tail[2], acc, ola_y, stage_in, stage_out, stage_filter;
+    device_buffer filter, fdl, prev[2], tail[2], acc, ola_y, stage_in, stage_out, stage_filter;
+    int prev_flip{0};  // prev[prev_flip] holds the last block of the previous call
 
     // optional per-phase timing with CUDA events on the handle's stream (bench.py's roofline numbers)
     struct span
@@ -115,7 +116,7 @@ struct conv_engine
 
     size_t device_bytes() const
     {
-        return filter.bytes + fdl.bytes + prev.bytes + tail[0].bytes + tail[1].bytes + acc.bytes + ola_y.bytes + stage_in.bytes
+        return filter.bytes + fdl.bytes + prev[0].bytes + prev[1].bytes + tail[0].bytes + tail[1].bytes + acc.bytes + ola_y.bytes + stage_in.bytes
              + stage_out.bytes + stage_filter.bytes;
     }
 
@@ -135,7 +136,8 @@ struct conv_engine
         size_t const csz = sizeof(cx<T>);
         NEO_TRY(filter.reserve(filters * parts * m * csz));
         NEO_TRY(fdl.reserve(c.inputs * size_t(ring) * m * csz));
-        NEO_TRY(prev.reserve(c.inputs * m * sizeof(T)));
+        NEO_TRY(prev[0].reserve(c.inputs * m * sizeof(T)));
+        NEO_TRY(prev[1].reserve(c.inputs * m * sizeof(T)));
         if (c.kind == NEO_B200_UPOLA) {
             NEO_TRY(tail[0].reserve(c.outputs * m * sizeof(T)));
             NEO_TRY(tail[1].reserve(c.outputs * m * sizeof(T)));
@@ -158,7 +160,9 @@ struct conv_engine
     int clear_state(cudaStream_t stream)
     {
         NEO_CUDA_TRY(cudaMemsetAsync(fdl.ptr, 0, fdl.bytes, stream));
-        NEO_CUDA_TRY(cudaMemsetAsync(prev.ptr, 0, prev.bytes, stream));
+        NEO_CUDA_TRY(cudaMemsetAsync(prev[0].ptr, 0, prev[0].bytes, stream));
+        NEO_CUDA_TRY(cudaMemsetAsync(prev[1].ptr, 0, prev[1].bytes, stream));
+        prev_flip = 0;
         if (tail[0].ptr != nullptr) {
             NEO_CUDA_TRY(cudaMemsetAsync(tail[0].ptr, 0, tail[0].bytes, stream));
             NEO_CUDA_TRY(cudaMemsetAsync(tail[1].ptr, 0, tail[1].bytes, stream));
@@ -246,17 +250,13 @@ struct conv_engine
         NEO_TRY(mark_begin(0, stream));
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
-                conv_r2c_io<T, LOGM> io{in, in_stride, prev.template as<T>(), fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
+                conv_r2c_io<T, LOGM> io{in, in_stride, prev[prev_flip].template as<T>(), prev[prev_flip ^ 1].template as<T>(),
+                                        fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
                                         cfg.kind == NEO_B200_UPOLA ? 1 : 0, logw, nt, chan0};
                 status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
             }
         });
         if (status != NEO_B200_OK) { return status == NEO_B200_ERR_UNSUPPORTED ? fail(status, "block size %d not supported", m) : status; }
-        if (cfg.kind == NEO_B200_UPOLS) {
-            // the last block becomes the left half of the next call's first window (overlap_save.hpp:94-95)
-            NEO_CUDA_TRY(cudaMemcpy2DAsync(prev.template as<T>() + chan0 * m, m * sizeof(T), in + (blocks - 1) * m, in_stride * sizeof(T),
-                                           m * sizeof(T), nchan, cudaMemcpyDeviceToDevice, stream));
-        }
         return mark_end(0, stream);
     }
 
@@ -293,7 +293,11 @@ struct conv_engine
     }
 
     // the ring position moves once per call, after every channel group has been inserted
-    void advance(size_t blocks) { write_pos = (write_pos + blocks) % size_t(ring); }
+    void advance(size_t blocks)
+    {
+        write_pos = (write_pos + blocks) % size_t(ring);
+        prev_flip ^= 1;  // the r2c kernels saved this call's last block into the other half-window buffer
+    }
 
     int forward(T const* in, size_t in_stride, size_t blocks, cudaStream_t stream)
     {
@@ -551,6 +555,10 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
     size_t groups = 1;
     // worth it only when the copies are long enough to matter next to the kernels (several blocks per call)
     if (conv->cfg.topology == NEO_B200_DIAGONAL && blocks >= 4) { groups = chans >= 512 ? 4 : chans >= 128 ? 2 : 1; }
+    if (char const* env = std::getenv("NEO_B200_HOST_GROUPS")) {  // tuning knob
+        size_t const want = size_t(std::max(1, std::atoi(env)));
+        if (conv->cfg.topology == NEO_B200_DIAGONAL && want <= chans) { groups = want; }
+    }
     if (groups == 1) {
         NEO_CUDA_TRY(cudaMemcpyAsync(din, in, conv->cfg.inputs * stride * sizeof(T), cudaMemcpyHostToDevice, s));
         NEO_TRY(e.forward(din, stride, blocks, s));

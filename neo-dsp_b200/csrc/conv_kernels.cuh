@@ -512,6 +512,7 @@ struct conv_r2c_io
     T const* in;       // [inputs][in_stride] reals, block tau at offset tau*B
     size_t in_stride;  // reals between channels
     T const* prev;     // [inputs][B] last block of the previous call (overlap-save)
+    T* prev_next;      // [inputs][B] receives the last block of THIS call (ping-pong partner of `prev`)
     C* fdl;
     int ring, wp, blocks;
     int overlap_add;   // 0: window = [previous block | block]   1: window = [block | zeros]  (overlap_add.hpp:88-90)
@@ -523,6 +524,7 @@ struct conv_r2c_io
         C const* lo;
         C const* hi;
         C* dst;        // element (tile 0, slot, 0); tiles are ring << logw apart
+        C* keep;       // non-null for the last block of the call: where its samples are saved as the next half-window
     };
     __device__ __forceinline__ row_state open(size_t b) const
     {
@@ -534,9 +536,16 @@ struct conv_r2c_io
         int slot           = wp + tau;
         slot -= slot >= ring ? ring : 0;
         C* dst = fdl + tiled_offset(ch, nt, logw, size_t(ring), size_t(slot), 0);
-        if (overlap_add) { return {reinterpret_cast<C const*>(cur), nullptr, dst}; }
+        if (overlap_add) { return {reinterpret_cast<C const*>(cur), nullptr, dst, nullptr}; }
         T const* before = tau == 0 ? prev + ch * B : cur - B;
-        return {reinterpret_cast<C const*>(before), reinterpret_cast<C const*>(cur), dst};
+        // slide_window_left + append (overlap_save.hpp:94-95): the newest block is next call's left half
+        C* const save = tau == blocks - 1 ? reinterpret_cast<C*>(prev_next + ch * B) : nullptr;
+        return {reinterpret_cast<C const*>(before), reinterpret_cast<C const*>(cur), dst, save};
+    }
+    __device__ __forceinline__ void keep(row_state const& r, int j, C z) const
+    {
+        constexpr int H = (1 << LOGM) / 2;
+        if (r.keep != nullptr && j >= H) { r.keep[j - H] = z; }
     }
     __device__ __forceinline__ C load(row_state const& r, int j) const
     {
@@ -648,6 +657,7 @@ struct partition_r2c_io
         long const i = 2L * j;
         return mk<T>(i < r.count ? r.src[i] : T(0), i + 1 < r.count ? r.src[i + 1] : T(0));
     }
+    __device__ __forceinline__ void keep(row_state const&, int, C) const {}
     __device__ __forceinline__ void store(row_state const& r, int k, C x) const
     {
         if (packed) { r.dst[((size_t(k >> logw) * parts) << logw) + (k & ((1 << logw) - 1))] = x; }

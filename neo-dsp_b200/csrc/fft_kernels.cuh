@@ -147,6 +147,10 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::M
     typename IO::row_state row = io.open(live ? b : 0);
 #pragma unroll
     for (int e = 0; e < cfg::E; ++e) { v[e] = live ? io.load(row, t + e * cfg::TN) : mk<T>(0, 0); }
+    if (live) {
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) { io.keep(row, t + e * cfg::TN, v[e]); }  // e.g. the convolver's next half-window
+    }
 
     F::run(v, sm, tw, t);
 
@@ -236,6 +240,7 @@ struct r2c_plain_io
         return {reinterpret_cast<C const*>(in) + b * (size_t(1) << LOGM), out + b * ((size_t(1) << LOGM) + 1)};
     }
     __device__ __forceinline__ C load(row_state const& r, int j) const { return r.src[j]; }
+    __device__ __forceinline__ void keep(row_state const&, int, C) const {}
     __device__ __forceinline__ void store(row_state const& r, int k, C x) const { r.dst[k] = x; }
     __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const
     {
