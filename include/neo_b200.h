@@ -140,6 +140,10 @@ NEO_B200_API size_t neo_b200_next_order(size_t size);
 NEO_B200_API int neo_b200_uniform_partition(
     void const* ir, size_t channels, size_t taps, size_t block, void* out, int dtype, int memspace);
 
+/* neo::convolution::normalize_impulse (convolution/normalize_impulse.hpp:13-33, algorithm/normalize_energy.hpp:17-44) in place on
+ * ir [channels][taps]: every sample is scaled by the smallest per-channel 1/sqrt(sum x^2) (1 for an all-zero channel). */
+NEO_B200_API int neo_b200_normalize_impulse(void* ir, size_t channels, size_t taps, int dtype, int memspace);
+
 /* ---- partitioned convolver: replaces neo::convolution::upols_convolver / upola_convolver
  *      (convolution/uniform_partitioned_convolver.hpp:14-65, dense_convolver.hpp:20-41), one handle = a bank of
  *      channels ------------------------------------------------------------------------------------------------------ */

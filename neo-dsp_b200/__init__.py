@@ -76,6 +76,7 @@ SIGNATURES = {
     "neo_b200_fdl_index_sequence": (_i, [_sz, _sz, _vp, _vp]),
     "neo_b200_num_partitions": (_sz, [_sz, _sz]),
     "neo_b200_next_order": (_sz, [_sz]),
+    "neo_b200_normalize_impulse": (_i, [_vp, _sz, _sz, _i, _i]),
     "neo_b200_uniform_partition": (_i, [_vp, _sz, _sz, _sz, _vp, _i, _i]),
     "neo_b200_conv_create": (_i, [C.POINTER(_vp), C.POINTER(ConvConfig)]),
     "neo_b200_conv_destroy": (None, [_vp]),
@@ -333,6 +334,14 @@ def uniform_partition(ir, block: int):
     out = _empty_like_kind(ir, (ch, parts, block + 1), "complex64" if real == "float32" else "complex128")
     _check(library().neo_b200_uniform_partition(_ptr(ir), ch, taps, block, _ptr(out), _DTYPE_CODE[real], _space(ir)))
     return out
+
+
+def normalize_impulse(ir):
+    """neo::convolution::normalize_impulse (convolution/normalize_impulse.hpp:13-33), in place on ir[C][L]; returns ir."""
+    if ir.ndim != 2:
+        raise ValueError("impulse response must be [channels][taps]")
+    _check(library().neo_b200_normalize_impulse(_ptr(ir), int(ir.shape[0]), int(ir.shape[1]), _DTYPE_CODE[_dtype_name(ir)], _space(ir)))
+    return ir
 
 
 class Convolver:

@@ -798,6 +798,41 @@ int neo_b200_uniform_partition(void const* ir, size_t channels, size_t taps, siz
     return fail(NEO_B200_ERR_INVALID, "bad dtype %d", dtype);
 }
 
+extern "C++" template<typename T>
+int normalize_impulse_impl(void* ir, size_t channels, size_t taps, int memspace)
+{
+    stream_ref stream;
+    NEO_TRY(stream.create());
+    cudaStream_t const s = stream.stream;
+    device_buffer data, energy;
+    size_t const bytes = channels * taps * sizeof(T);
+    T* dev             = static_cast<T*>(ir);
+    if (memspace == NEO_B200_HOST) {
+        NEO_TRY(data.reserve(bytes));
+        dev = data.template as<T>();
+        NEO_CUDA_TRY(cudaMemcpyAsync(dev, ir, bytes, cudaMemcpyHostToDevice, s));
+    }
+    NEO_TRY(energy.reserve(channels * sizeof(double)));
+    channel_energy_kernel<T><<<unsigned(channels), 256, 0, s>>>(dev, taps, energy.as<double>());
+    NEO_TRY(check_launch("channel_energy_kernel"));
+    scale_by_min_factor_kernel<T><<<1184, 256, 0, s>>>(dev, channels * taps, energy.as<double>(), unsigned(channels));
+    NEO_TRY(check_launch("scale_by_min_factor_kernel"));
+    if (memspace == NEO_B200_HOST) { NEO_CUDA_TRY(cudaMemcpyAsync(ir, dev, bytes, cudaMemcpyDeviceToHost, s)); }
+    NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    return NEO_B200_OK;
+}
+
+int neo_b200_normalize_impulse(void* ir, size_t channels, size_t taps, int dtype, int memspace)
+{
+    if (ir == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (channels == 0 || taps == 0) { return NEO_B200_OK; }  // normalize_impulse.hpp:20-22
+    if (channels > 0x7fffffffULL) { return fail(NEO_B200_ERR_INVALID, "too many channels"); }
+    NEO_TRY(require_device());
+    if (dtype == NEO_B200_F32) { return normalize_impulse_impl<float>(ir, channels, taps, memspace); }
+    if (dtype == NEO_B200_F64) { return normalize_impulse_impl<double>(ir, channels, taps, memspace); }
+    return fail(NEO_B200_ERR_INVALID, "bad dtype %d", dtype);
+}
+
 // ---- index tables -----------------------------------------------------------------------------------------------------------------
 static int table_to_host(device_buffer& buf, uint32_t* out, size_t count)
 {

@@ -691,6 +691,39 @@ __global__ void __launch_bounds__(256)
     packed[tiled_offset(f, nt, logw, size_t(parts), row - f * parts, k)] = v;
 }
 
+// normalize_impulse step 1: energy[c] = sum_i ir[c][i]^2, one CTA per channel, double accumulation
+template<typename T>
+__global__ void __launch_bounds__(256) channel_energy_kernel(T const* __restrict__ ir, size_t taps, double* __restrict__ energy)
+{
+    __shared__ double partial[256];
+    T const* row = ir + size_t(blockIdx.x) * taps;
+    double acc   = 0.0;
+    for (size_t i = threadIdx.x; i < taps; i += blockDim.x) {
+        double const v = double(row[i]);
+        acc += v * v;
+    }
+    partial[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = 128; s > 0; s >>= 1) {
+        if (int(threadIdx.x) < s) { partial[threadIdx.x] += partial[threadIdx.x + s]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { energy[blockIdx.x] = partial[0]; }
+}
+
+// step 2: factor = min_c (energy == 0 ? 1 : 1/sqrt(energy)) (normalize_impulse.hpp:24-31), applied to every sample
+template<typename T>
+__global__ void __launch_bounds__(256) scale_by_min_factor_kernel(T* __restrict__ ir, size_t total, double const* __restrict__ energy, unsigned channels)
+{
+    double factor = 0.0;
+    for (unsigned c = 0; c < channels; ++c) {
+        double const f = energy[c] == 0.0 ? 1.0 : rsqrt(energy[c]);
+        factor         = (c == 0 || f < factor) ? f : factor;
+    }
+    T const scale = T(factor);
+    for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) { ir[i] = ir[i] * scale; }
+}
+
 __global__ void fdl_index_kernel(unsigned parts, unsigned calls, unsigned* write_pos, unsigned* pairs);
 __global__ void bitrev_table_kernel(unsigned order, unsigned* out);
 

@@ -342,3 +342,14 @@ def test_baseline_config4_full_size_matrix_routing(gpu, orc):
             got[:, pos * B : (pos + T) * B] = y.cpu().numpy()
         assert rel_l2(got, want) <= 1e-5, T
         conv.close()
+
+
+def test_normalize_impulse_matches_oracle(gpu, orc):
+    # convolution/normalize_impulse_test.cpp: unit energy for the loudest channel, common factor for all
+    ir = np.stack([orc.noise(4097, 21 + c, np.float32) * (c + 1) for c in range(3)])
+    got = gpu.normalize_impulse(ir.copy())
+    want = orc.normalize_impulse(ir)
+    assert rel_l2(got, want) <= 2e-6  # the oracle accumulates the energy in float32 like the reference, the kernel in double
+    assert abs(float((got[2].astype(np.float64) ** 2).sum()) - 1.0) < 1e-5
+    zeros = np.zeros((2, 64), dtype=np.float32)
+    assert np.array_equal(gpu.normalize_impulse(zeros.copy()), zeros)  # energy exactly 0 -> factor 1
