@@ -65,7 +65,7 @@ struct conv_engine
     int tail_flip{0};
 
     fft_tables<T> tables;
-    device_buffer filter, fdl, prev[2], tail[2], acc, ola_y, stage_in, stage_out, stage_filter;
+    device_buffer filter, fdl, prev[2], tail[2], acc, ola_y, stage_in, stage_out, stage_filter, tickets;
     int prev_flip{0};  // prev[prev_flip] holds the last block of the previous call
 
     // optional per-phase timing with CUDA events on the handle's stream (bench.py's roofline numbers)
@@ -154,6 +154,9 @@ struct conv_engine
         want                 = std::min(want, std::max<size_t>(1, work / 8));
         splits               = int(std::max<size_t>(1, std::min<size_t>(want, 64)));
         NEO_TRY(acc.reserve(size_t(splits) * c.outputs * c.max_blocks * m * csz));
+        // one ticket per MAC grid cell (x: at most B/128 column blocks, y: outputs); the last split CTA to finish resets it
+        NEO_TRY(tickets.reserve(c.outputs * size_t(std::max(1, m / 128 + 1)) * sizeof(unsigned)));
+        NEO_CUDA_TRY(cudaMemsetAsync(tickets.ptr, 0, tickets.bytes, stream));
         return clear_state(stream);
     }
 
@@ -276,6 +279,7 @@ struct conv_engine
         g.splits    = splits;
         g.out0      = int(out0);
         g.acc_plane = cfg.outputs * blocks * size_t(m);
+        g.tickets   = tickets.template as<unsigned>();
 
         size_t tau = 0;
         NEO_TRY(mark_begin(1, stream));
@@ -385,14 +389,6 @@ struct conv_engine
         }
         NEO_TRY(mark_end(2, stream));
         return NEO_B200_OK;
-    }
-
-    int reduce_planes(size_t blocks, cudaStream_t stream)
-    {
-        if (splits <= 1) { return NEO_B200_OK; }
-        size_t const plane = cfg.outputs * blocks * size_t(m);
-        sum_planes_kernel<T><<<unsigned((plane + 255) / 256), 256, 0, stream>>>(acc.template as<cx<T>>(), plane, splits);
-        return check_launch("sum_planes_kernel");
     }
 };
 
@@ -540,7 +536,7 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
     size_t const plane   = conv->cfg.outputs * blocks * size_t(e.m);
     if (memspace == NEO_B200_DEVICE) {
         NEO_TRY(e.forward(static_cast<T const*>(in), stride, blocks, s));
-        NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), plane, e.splits, static_cast<T*>(out), stride, 0, conv->cfg.outputs, blocks, s));
+        NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), plane, 1, static_cast<T*>(out), stride, 0, conv->cfg.outputs, blocks, s));
         if (conv->cfg.kind == NEO_B200_UPOLA) { e.tail_flip ^= 1; }
         return NEO_B200_OK;
     }
@@ -562,7 +558,7 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
     if (groups == 1) {
         NEO_CUDA_TRY(cudaMemcpyAsync(din, in, conv->cfg.inputs * stride * sizeof(T), cudaMemcpyHostToDevice, s));
         NEO_TRY(e.forward(din, stride, blocks, s));
-        NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), plane, e.splits, dout, stride, 0, chans, blocks, s));
+        NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), plane, 1, dout, stride, 0, chans, blocks, s));
         NEO_CUDA_TRY(cudaMemcpyAsync(out, dout, chans * stride * sizeof(T), cudaMemcpyDeviceToHost, s));
     } else {
         NEO_TRY(conv->ensure_pipeline(groups));
@@ -577,7 +573,7 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
             NEO_CUDA_TRY(cudaStreamWaitEvent(s, conv->ev_in[g], 0));
             NEO_TRY(e.forward_r2c(din + c0 * stride, stride, blocks, c0, n, s));
             NEO_TRY(e.forward_mac(blocks, c0, n, s));
-            NEO_TRY(e.inverse(e.acc.template as<cx<T>>() + c0 * blocks * size_t(e.m), plane, e.splits, dout + c0 * stride, stride, c0, n,
+            NEO_TRY(e.inverse(e.acc.template as<cx<T>>() + c0 * blocks * size_t(e.m), plane, 1, dout + c0 * stride, stride, c0, n,
                               blocks, s));
             NEO_CUDA_TRY(cudaEventRecord(conv->ev_done[g], s));
             NEO_CUDA_TRY(cudaStreamWaitEvent(conv->s_out, conv->ev_done[g], 0));
@@ -625,8 +621,7 @@ int conv_forward_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, si
         NEO_CUDA_TRY(cudaMemcpyAsync(e.stage_in.ptr, in, conv->cfg.inputs * stride * sizeof(T), cudaMemcpyHostToDevice, s));
         din = e.stage_in.template as<T>();
     }
-    NEO_TRY(e.forward(din, stride, blocks, s));
-    return e.reduce_planes(blocks, s);
+    return e.forward(din, stride, blocks, s);
 }
 
 int neo_b200_conv_forward(neo_b200_conv* conv, void const* in, size_t blocks, int memspace)
@@ -644,10 +639,7 @@ int conv_forward_range_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* 
     size_t const stride  = blocks * e.m;
     NEO_TRY(e.forward_r2c(static_cast<T const*>(in) + first * stride, stride, blocks, first, count, s));
     NEO_TRY(e.forward_mac(blocks, first, count, s));
-    if (final != 0) {
-        NEO_TRY(e.reduce_planes(blocks, s));  // small banks split the partition loop over CTAs: fold the partial planes once
-        e.advance(blocks);
-    }
+    if (final != 0) { e.advance(blocks); }
     return NEO_B200_OK;
 }
 

@@ -56,7 +56,43 @@ struct mac_geom
     int splits;        // S
     int out0;          // first output channel of this launch (blockIdx.y is relative to it)
     size_t acc_plane;  // elements per partial plane
+    unsigned* tickets; // one counter per (blockIdx.x, output row of the grid): which split CTA finishes last
 };
+
+// Small banks split the partition loop over gridDim.z CTAs, each leaving a partial plane. The LAST of them to finish (ticket
+// counter) folds the planes into plane 0 in plane order -- deterministic, no float atomics, and the c2r kernel reads one plane.
+// Every thread of the CTA must call it; `mine` says whether this thread owns elements; they sit at acc[first + r*stride].
+template<typename V>
+__device__ __forceinline__ void fold_split_planes(V* acc, size_t plane, int splits, bool mine, size_t first, int rows, size_t stride,
+                                                   unsigned* ticket)
+{
+    if (splits <= 1) { return; }
+    __shared__ bool is_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned const t = atomicAdd(ticket, 1U);
+        is_last          = (t == unsigned(splits) - 1U);
+        if (is_last) { *ticket = 0U; }  // ready for the next launch
+    }
+    __syncthreads();
+    if (!is_last || !mine) { return; }
+    __threadfence();
+    for (int r = 0; r < rows; ++r) {
+        V* const p0 = acc + first + size_t(r) * stride;
+        V s         = __ldcg(p0);
+        for (int p = 1; p < splits; ++p) {
+            V const v = __ldcg(p0 + size_t(p) * plane);
+            s.x += v.x;
+            s.y += v.y;
+            if constexpr (sizeof(V) == 16 && sizeof(s.x) == 4) {
+                s.z += v.z;
+                s.w += v.w;
+            }
+        }
+        *p0 = s;
+    }
+}
 
 // ---- T = 1: pure stream. Every filter and FDL element is used exactly once -> HBM roofline. -------------------------------
 // thread = VEC adjacent bins (16 bytes), 8 rows in flight per thread.
@@ -131,11 +167,11 @@ __global__ void __launch_bounds__(k_mac_threads)
     int const out0     = blockIdx.y * OT + g.out0;
     int const split    = blockIdx.z;
     int const row_vec  = g.m / MV::VEC;
-    if (col >= row_vec) { return; }
+    bool const mine    = col < row_vec;
 
     int const total = g.sources * g.parts;  // virtual partitions of one output
     int const v0    = int((long long)total * split / g.splits);
-    int const v1    = int((long long)total * (split + 1) / g.splits);
+    int const v1    = mine ? int((long long)total * (split + 1) / g.splits) : v0;
 
     V a[OT];
 #pragma unroll
@@ -183,10 +219,15 @@ __global__ void __launch_bounds__(k_mac_threads)
             }
         }
     }
+    size_t const first = (size_t(out0) * g.blocks + g.tau0) * row_vec + col;
+    if (mine) {
 #pragma unroll
-    for (int o = 0; o < OT; ++o) {
-        reinterpret_cast<V*>(acc)[size_t(split) * (g.acc_plane / MV::VEC) + (size_t(out0 + o) * g.blocks + g.tau0) * row_vec + col] = a[o];
+        for (int o = 0; o < OT; ++o) {
+            reinterpret_cast<V*>(acc)[size_t(split) * (g.acc_plane / MV::VEC) + first + size_t(o) * g.blocks * row_vec] = a[o];
+        }
     }
+    fold_split_planes(reinterpret_cast<V*>(acc), g.acc_plane / MV::VEC, g.splits, mine, first, OT, size_t(g.blocks) * row_vec,
+                      g.tickets + (size_t(blockIdx.y) * gridDim.x + blockIdx.x));
 }
 
 // ---- T = TB > 1: Toeplitz form. acc[tau] += H[p] * X(tau - age0 - p); each H[p] is reused TB times from registers and
@@ -199,13 +240,13 @@ __global__ void __launch_bounds__(k_mac_threads)
     int const k     = blockIdx.x * k_mac_threads + threadIdx.x;
     int const out   = blockIdx.y + g.out0;
     int const split = blockIdx.z;
-    if (k >= g.m) { return; }
+    bool const mine = k < g.m;
     bool const edge = (k == 0);
 
     int const chunks_per_src = (g.parts + TB - 1) / TB;
     int const total          = g.sources * chunks_per_src;
     int const c0             = int((long long)total * split / g.splits);
-    int const c1             = int((long long)total * (split + 1) / g.splits);
+    int const c1             = mine ? int((long long)total * (split + 1) / g.splits) : c0;
 
     C a[TB];
 #pragma unroll
@@ -269,9 +310,13 @@ __global__ void __launch_bounds__(k_mac_threads)
             }
         }
     }
-    C* dst = acc + size_t(split) * g.acc_plane + (size_t(out) * g.blocks + g.tau0) * g.m + k;
+    size_t const first = (size_t(out) * g.blocks + g.tau0) * g.m + k;
+    if (mine) {
+        C* dst = acc + size_t(split) * g.acc_plane + first;
 #pragma unroll
-    for (int tau = 0; tau < TB; ++tau) { dst[size_t(tau) * g.m] = a[tau]; }
+        for (int tau = 0; tau < TB; ++tau) { dst[size_t(tau) * g.m] = a[tau]; }
+    }
+    fold_split_planes(acc, g.acc_plane, g.splits, mine, first, TB, size_t(g.m), g.tickets + (size_t(blockIdx.y) * gridDim.x + blockIdx.x));
 }
 
 // ---- the same Toeplitz MAC for float32 rows of at least one full tile, fed by TMA -------------------------------------------------
@@ -488,20 +533,11 @@ __global__ void __launch_bounds__(128)
         }
     }
 
-    float2* dst = acc + size_t(split) * g.acc_plane + (size_t(out) * g.blocks + g.tau0) * g.m + tile * W + tid;
+    size_t const first = (size_t(out) * g.blocks + g.tau0) * g.m + tile * W + tid;
+    float2* dst        = acc + size_t(split) * g.acc_plane + first;
 #pragma unroll
     for (int tau = 0; tau < TB; ++tau) { dst[size_t(tau) * g.m] = a[tau]; }
-}
-
-// sum the S partial planes into plane 0 (only needed before handing spectra to a collective)
-template<typename T>
-__global__ void __launch_bounds__(256) sum_planes_kernel(cx<T>* acc, size_t plane, int splits)
-{
-    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
-    if (i >= plane) { return; }
-    cx<T> s = acc[i];
-    for (int p = 1; p < splits; ++p) { s = cadd(s, acc[size_t(p) * plane + i]); }
-    acc[i] = s;
+    fold_split_planes(acc, g.acc_plane, g.splits, true, first, TB, size_t(g.m), g.tickets + (size_t(blockIdx.y) * gridDim.x + blockIdx.x));
 }
 
 // ---- forward side: window assembly + r2c + FDL insert ---------------------------------------------------------------------------

@@ -6,6 +6,7 @@
 #include "fft_split.cuh"
 
 #include <cmath>
+#include <cstdlib>
 #include <memory>
 
 namespace neo_b200 {
@@ -186,7 +187,8 @@ struct rfft_engine
     size_t two_pass_chunk(size_t batch)
     {
         size_t const bytes = (size_t(1) << (order - 1)) * sizeof(cx<T>);
-        return std::max<size_t>(1, std::min(batch, (size_t(48) << 20) / bytes));
+        static size_t const mb = std::getenv("NEO_B200_FFT_CHUNK_MB") ? size_t(std::atoi(std::getenv("NEO_B200_FFT_CHUNK_MB"))) : 48;
+        return std::max<size_t>(1, std::min(batch, (mb << 20) / bytes));
     }
 
     int forward_two_pass(T const* in, cx<T>* out, size_t batch, cudaStream_t stream)
