@@ -261,10 +261,19 @@ __host__ __device__ constexpr int fft_twiddle_offset(int logm, int loge, int log
 
 __host__ __device__ constexpr int fft_twiddle_count(int logm, int loge) { return fft_twiddle_offset(logm, loge, logm); }
 
-template<typename T, int LOGM, int DIR>
+// LOGE_FORCED >= 0 overrides the points-per-thread choice (the cluster kernels want 16 points per thread for short columns)
+// WARP_PRIVATE: the transform's TN threads are exactly one warp and its tile is touched by no other warp, so the exchanges only
+// need __syncwarp() (the cluster kernel's 512-point rows: no CTA-wide stall per stage).
+template<typename T, int LOGM, int DIR, int LOGE_FORCED = -1, bool WARP_PRIVATE = false>
 struct cta_fft
 {
-    static constexpr int LOGE  = pick_loge<T>(LOGM);
+    static __device__ __forceinline__ void sync()
+    {
+        if constexpr (WARP_PRIVATE) { __syncwarp(); }
+        else { __syncthreads(); }
+    }
+
+    static constexpr int LOGE  = LOGE_FORCED >= 0 ? LOGE_FORCED : pick_loge<T>(LOGM);
     static constexpr int M     = 1 << LOGM;
     static constexpr int E     = 1 << LOGE;
     static constexpr int TN    = M / E;
@@ -278,7 +287,7 @@ struct cta_fft
     static __device__ __forceinline__ void stage_twiddle(int q, C (&w)[N], C const* __restrict__ row0, int ns)
     {
         int const hi = 1 << (31 - __clz(q));
-        if (q == hi) { w[q] = __ldg(row0 + (31 - __clz(q)) * ns); }
+        if (q == hi) { w[q] = row0[(31 - __clz(q)) * ns]; }  // plain load: the table may live in global (read-only path) or shared memory
         else { w[q] = cmul(w[hi], w[q - hi]); }
     }
 
@@ -317,10 +326,10 @@ struct cta_fft
             }
         }
         if constexpr (!last) {
-            __syncthreads();
+            sync();
 #pragma unroll
             for (int e = 0; e < E; ++e) { v[e] = sm[padded<T>(t + e * TN)]; }
-            __syncthreads();
+            sync();
         }
     }
 

@@ -35,9 +35,9 @@ struct fft_cfg
 
 // ---- twiddle tables (host, computed in double, rounded once) --------------------------------------------------------
 template<typename T>
-std::vector<cx<T>> make_stage_twiddles(int logm)
+std::vector<cx<T>> make_stage_twiddles(int logm, int loge_forced = -1)
 {
-    int const loge = pick_loge<T>(logm);
+    int const loge = loge_forced >= 0 ? loge_forced : pick_loge<T>(logm);
     std::vector<cx<T>> lut(static_cast<size_t>(fft_twiddle_count(logm, loge)) + 1);
     if (loge == 0) { return lut; }
     int const r0 = fft_first_logr(logm, loge);

@@ -4,6 +4,7 @@
 #include "fft_kernels.cuh"
 #include "fft_large.cuh"
 #include "fft_split.cuh"
+#include "fft_cluster.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -145,10 +146,13 @@ struct rfft_engine
 {
     int order;                   // real size N = 2^order, complex half size M = N/2
     fft_tables<T> tables;        // single-CTA path: M-point plan; split path: M/2-point plan
+    fft_tables<T> tables_full;   // M = 2^max_cta: c2r runs faster as ONE CTA (measured 0.60 vs 0.34-0.47 of HBM peak), r2c as two
     device_buffer w_n;           // split path: exp(-2 pi i k / N), k < M/2
     large_rfft<T> large;
     bool use_large{false};
     bool use_split{false};       // two CTAs per transform (fft_split.cuh)
+    bool use_cluster{false};     // float32, N = 2^14..2^16: persistent thread-block-cluster four-step (fft_cluster.cuh)
+    rfft_cluster_plan cluster;
     bool use_two_pass{false};    // four-CTA split c2c into an L2-resident scratch + Hermitian split pass
     c2c_engine<T> half;          // two-pass path: the half-size complex transform
     twiddle2<T> w2m;             // two-pass path: exp(-2 pi i k / N)
@@ -163,6 +167,15 @@ struct rfft_engine
         order = order_;
         if (order == 0) { return NEO_B200_OK; }
         int const logm = order - 1;
+        if constexpr (sizeof(T) == 4) {
+            // measured: the cluster kernel wins only at N = 2^16 (0.25 of HBM peak against 0.13 for the two-pass path); at
+            // 2^14 / 2^15 the two-CTA split transforms are faster (0.5-0.6 / 0.4-0.5 against 0.33 / 0.27)
+            bool const all = std::getenv("NEO_B200_CLUSTER_ALL") != nullptr;
+            if ((order == 16 || (all && order >= 14 && order < 16)) && std::getenv("NEO_B200_NO_CLUSTER") == nullptr) {
+                use_cluster = true;
+                return cluster.init(order, stream);
+            }
+        }
         use_split      = logm >= k_split_lo && logm <= k_split_hi;
         use_two_pass   = logm == k_split_hi + 1;
         use_large      = logm > k_split_hi + 1;
@@ -172,6 +185,7 @@ struct rfft_engine
             return w2m.build(order, stream);
         }
         if (use_split) {
+            if (logm == k_split_lo) { NEO_TRY(tables_full.build(logm, true, stream)); }
             NEO_TRY(tables.build(logm - 1, true, stream));
             auto const wn = make_split_twiddles<T>(logm);  // exp(-i pi k / M) = exp(-2 pi i k / N); first M/2 entries used
             size_t const bytes = (wn.size() / 2) * sizeof(cx<T>);
@@ -226,6 +240,9 @@ struct rfft_engine
     int forward(T const* in, cx<T>* out, size_t batch, cudaStream_t stream)
     {
         if (order == 0) { return large_rfft<T>::size_one_forward(in, out, batch, stream); }
+        if constexpr (sizeof(T) == 4) {
+            if (use_cluster) { return cluster.forward(in, out, batch, stream); }
+        }
         if (use_large) { return large.forward(in, out, batch, stream); }
         if (use_two_pass) { return forward_two_pass(in, out, batch, stream); }
         if (use_split) {
@@ -245,12 +262,16 @@ struct rfft_engine
     int backward(cx<T> const* in, size_t row_len, T* out, size_t batch, cudaStream_t stream)
     {
         if (order == 0) { return large_rfft<T>::size_one_backward(in, row_len, out, batch, stream); }
+        if constexpr (sizeof(T) == 4) {
+            if (use_cluster) { return cluster.backward(in, row_len, out, batch, stream); }
+        }
         if (use_large) { return large.backward(in, row_len, out, batch, stream); }
         if (use_two_pass) { return backward_two_pass(in, row_len, out, batch, stream); }
         if (use_split) {
             auto const* wn = w_n.template as<cx<T>>();
             if (order - 1 == k_split_lo) {
-                return launch_c2r_split2<T, k_split_lo - 1>(in, row_len, out, tables.tw(), tables.rtw(), wn, batch, stream);
+                return launch_c2r<T, k_split_lo>(c2r_plain_io<T, k_split_lo>{in, out, row_len}, tables_full.tw(), tables_full.rtw(), batch,
+                                                 stream);
             }
             return launch_c2r_split2<T, k_split_hi - 1>(in, row_len, out, tables.tw(), tables.rtw(), wn, batch, stream);
         }
