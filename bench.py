@@ -2,12 +2,15 @@
 """bench.py -- the reference's headline workload on B200 (BASELINE.json):
 "UPOLS channel-Msamples/s (B=1024, 2^20 taps); batched FFT GB/s vs HBM peak".
 
-    python bench.py --gpus N --steps K --warmup W [--blocks T] [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--frame T | --frame 0 --blocks T] [--impl reference]
 
 A step is one call of the convolver bank: T consecutive blocks of 1024 samples for each of the 1024 channels, each
 channel convolved with its own 2^20-tap impulse response (P = 1024 partitions) -- BASELINE config 5. T = 1 is the
 reference's streaming call (one block per call); T > 1 hands the bank T blocks at once (the CLI / offline case,
-extra/cli/src/convolver.cpp:42-55), which lets the MAC kernel reuse every filter partition T times.
+extra/cli/src/convolver.cpp:42-55). Two forms of T > 1: the direct form (--frame 0 --blocks T) reuses every filter
+partition T times in the MAC kernel (FP32-bound from T = 16); frame mode (--frame T, the default, T = 256) evaluates the
+sum over partitions by a second overlap-save level along block time (neo-dsp_b200/csrc/conv_frame.cuh), HBM-bound again.
+Same results within the float32 tolerance either way (tests/test_conv_frame_gpu.py); every number states its mode.
 
   value        whole-job channel-Msamples/s, inputs resident in HBM, CUDA events on the launching stream, max over ranks
   e2e          the same through the C-ABI call with HOST (pinned) buffers: H2D and D2H inside the timed region
@@ -219,13 +222,19 @@ def fft_sweep(pkg, torch, peak):
     return out
 
 
+def mode_name(frame: int, T: int) -> str:
+    if frame > 0:
+        return f"frame mode: {T} blocks per call, sum over partitions by overlap-save along block time (frame transforms of length {2 * T})"
+    return "streaming (reference call shape)" if T == 1 else f"time-batched direct form, {T} blocks per call"
+
+
 def run_channel_sharded(args, torch, dist, pkg, emit, rank, world, local):
     """Alternative multi-GPU layout: channels [r*C/G, (r+1)*C/G) with their whole filters on rank r, no
     data-path collective at all. Not BASELINE config 5's prescribed sharding; reported for comparison (--shard channels)."""
-    T = args.blocks
+    T = args.frame if args.frame > 0 else args.blocks
     ch = CHANNELS // world
     stream = torch.cuda.current_stream()
-    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=T)
+    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=T, frame_blocks=args.frame)
     conv.set_stream(stream)
     gen = torch.Generator(device="cuda").manual_seed(11 + rank)
     ir = torch.rand((ch, TAPS), device="cuda", dtype=torch.float32, generator=gen) * 2 - 1
@@ -257,7 +266,8 @@ def run_channel_sharded(args, torch, dist, pkg, emit, rank, world, local):
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "C5: 1024 channels x 2^20-tap IR each, UPOLS B=1024 (P=1024, K=1025), white-noise input",
-                       "blocks_per_call": T, "sharding": f"channels sharded {world}-way, no collective (alternative layout)",
+                       "blocks_per_call": T, "mode": mode_name(args.frame, T),
+                       "sharding": f"channels sharded {world}-way, no collective (alternative layout)",
                        "realtime_x_wall_1024ch_48k": value * 1e6 / CHANNELS / 48000.0},
             "clocks": clocks.summary(), "gpu_launches": pkg.kernel_launches() - launches0,
         })
@@ -296,7 +306,10 @@ def run_ours(args):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    T = args.blocks
+    frame = args.frame
+    if frame > 0 and world > 1 and args.shard == "partitions":
+        frame = min(frame, PARTS // world)  # a shard starts on a frame boundary of the partition axis
+    T = frame if frame > 0 else args.blocks
     peak, peak_src = measured_peaks()
     stream = torch.cuda.current_stream()
     if args.fft_only:  # development aid: just the BASELINE config 2 sweep
@@ -314,7 +327,8 @@ def run_ours(args):
         run_channel_sharded(args, torch, dist, pkg, emit, rank, world, local)
         return
     lo, hi = rank * PARTS // world, (rank + 1) * PARTS // world
-    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=T, partition_range=(lo, hi) if world > 1 else None)
+    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=T, partition_range=(lo, hi) if world > 1 else None,
+                         frame_blocks=frame)
     conv.set_stream(stream)
     gen = torch.Generator(device="cuda").manual_seed(11)
     ir = torch.rand((CHANNELS, TAPS), device="cuda", dtype=torch.float32, generator=gen) * 2 - 1
@@ -324,7 +338,7 @@ def run_ours(args):
     torch.cuda.empty_cache()
 
     gen = torch.Generator(device="cuda").manual_seed(13)  # same white noise on every rank
-    nbuf = 4
+    nbuf = 4 if T <= 256 else 2
     xs = [torch.rand((CHANNELS, T * BLOCK), device="cuda", dtype=torch.float32, generator=gen) * 2 - 1 for _ in range(nbuf)]
     ys = torch.empty((CHANNELS, T * BLOCK), device="cuda", dtype=torch.float32)
     shard = CHANNELS // world
@@ -476,18 +490,31 @@ def run_ours(args):
     # ---- roofline of the dominant kernel (spectral MAC), from the event-timed launches inside the timed region ----
     parts_local = hi - lo
     bins = BLOCK + 1
-    # 16*K*P bytes per channel-block at T=1 (FDL row + filter row per partition); with T blocks per launch the
-    # filter is read once and P+T-1 FDL rows serve all T blocks; plus the T accumulator rows written
-    alg_bytes_launch = (CHANNELS // groups) * 8 * bins * (parts_local + (parts_local + T - 1) + T)  # one launch = one channel group
+    if frame > 0:
+        # fused frame kernel, per channel: filter rows Q*L*K + ring slots of older frames (Q-1 if this handle holds partition 0,
+        # else Q) * L*K read, the two frames' level-1 spectra 2T*B read, the new ring slot L*K and the T result rows T*B written
+        q_local = (parts_local + T - 1) // T
+        ring_rows = q_local - 1 if lo == 0 else q_local
+        alg_bytes_launch = (CHANNELS // groups) * 8 * (bins * 2 * T * (q_local + ring_rows + 1) + BLOCK * 2 * T + BLOCK * T)
+        kernel_name = f"frame_fused_kernel<float, LOGL={(2 * T).bit_length() - 1}> (frame transform + ring insert + MAC + inverse frame transform)"
+        fp32 = None
+    else:
+        # 16*K*P bytes per channel-block at T=1 (FDL row + filter row per partition); with T blocks per launch the
+        # filter is read once and P+T-1 FDL rows serve all T blocks; plus the T accumulator rows written
+        alg_bytes_launch = (CHANNELS // groups) * 8 * bins * (parts_local + (parts_local + T - 1) + T)  # one launch = one channel group
+        kernel_name = "fdl_mac_stream_kernel<float>" if T == 1 else ("fdl_mac_tma_kernel<16,16,2>" if T == 16 else "fdl_mac_tma_kernel<32,8,3>" if T == 32 else f"fdl_mac (T={T})")
+        fp32 = None
     mac_ms_avg = ms_mac / max(1, mac_launches)
     achieved = alg_bytes_launch / (mac_ms_avg * 1e-3) / 1e9 if mac_ms_avg > 0 else 0.0
+    if frame == 0 and mac_ms_avg > 0:
+        fp32 = (CHANNELS // groups) * 8.0 * bins * parts_local * T / (mac_ms_avg * 1e-3) / 1e12
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(f"fdl_mac_T{T}_G{world}")
+            traffic = json.load(f).get(f"frame_fused_T{T}_G{world}" if frame > 0 else f"fdl_mac_T{T}_G{world}")
     roofline = {
-        "kernel": "fdl_mac_stream_kernel<float>" if T == 1 else ("fdl_mac_tma_kernel<16,16,2>" if T == 16 else "fdl_mac_tma_kernel<32,8,3>" if T == 32 else f"fdl_mac (T={T})"),
+        "kernel": kernel_name,
         "bound": "hbm",
         "achieved": achieved,
         "peak": peak,
@@ -498,7 +525,7 @@ def run_ours(args):
         "algorithmic_bytes_per_launch": alg_bytes_launch,
         "launch_ms": mac_ms_avg,
         "share_of_step": ms_mac / ms_total if ms_total > 0 else None,
-        "fp32_tflops": (CHANNELS // groups) * 8.0 * bins * parts_local * T / (mac_ms_avg * 1e-3) / 1e12 if mac_ms_avg > 0 else 0.0,
+        "fp32_tflops": fp32,
         "phases_ms_per_step": {"r2c_fdl_insert": ms_r2c / args.steps, "mac": ms_mac / args.steps, "c2r_discard": ms_c2r / args.steps},
     }
 
@@ -508,11 +535,13 @@ def run_ours(args):
         # the other call shapes, measured the same way (fewer steps), so every number on the line states its T
         del conv
         torch.cuda.empty_cache()
-        modes = {f"T{T}": {"value": value, "unit": UNIT, "mac_algorithmic_gbs": achieved, "mac_fp32_tflops": roofline["fp32_tflops"]}}
-        for t_other in (1, 32):
-            if t_other == T:
+        tag = f"frame{T}" if frame > 0 else f"T{T}"
+        modes = {tag: {"value": value, "unit": UNIT, "mac_algorithmic_gbs": achieved, "mac_fp32_tflops": fp32}}
+        others = [(0, 1), (0, 16), (64, 64), (512, 512)]  # (frame, blocks per call)
+        for f_other, t_other in others:
+            if (f_other, t_other) == (frame, T):
                 continue
-            c2 = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=t_other)
+            c2 = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=t_other, frame_blocks=f_other)
             c2.set_stream(stream)
             gen2 = torch.Generator(device="cuda").manual_seed(11)
             ir2 = torch.rand((CHANNELS, TAPS), device="cuda", dtype=torch.float32, generator=gen2) * 2 - 1
@@ -535,12 +564,18 @@ def run_ours(args):
             torch.cuda.synchronize()
             _, mac2, _, nl2 = c2.profile_read()
             ms2 = e0.elapsed_time(e1)
-            alg2 = CHANNELS * 8 * bins * (PARTS + (PARTS + t_other - 1) + t_other)
-            modes[f"T{t_other}"] = {
+            if f_other > 0:
+                q2 = (PARTS + t_other - 1) // t_other
+                alg2 = CHANNELS * 8 * (bins * 2 * t_other * (2 * q2) + BLOCK * 2 * t_other + BLOCK * t_other)
+                flops2 = None
+            else:
+                alg2 = CHANNELS * 8 * bins * (PARTS + (PARTS + t_other - 1) + t_other)
+                flops2 = CHANNELS * 8.0 * bins * PARTS * t_other / (mac2 / max(1, nl2) * 1e-3) / 1e12
+            modes[f"frame{t_other}" if f_other > 0 else f"T{t_other}"] = {
                 "value": CHANNELS * BLOCK * t_other * n2 / (ms2 * 1e-3) / 1e6,
                 "unit": UNIT,
                 "mac_algorithmic_gbs": alg2 / (mac2 / max(1, nl2) * 1e-3) / 1e9,
-                "mac_fp32_tflops": CHANNELS * 8.0 * bins * PARTS * t_other / (mac2 / max(1, nl2) * 1e-3) / 1e12,
+                "mac_fp32_tflops": flops2,
                 "steps": n2,
             }
             c2.close()
@@ -576,7 +611,7 @@ def run_ours(args):
         "config": {
             "workload": "C5: 1024 channels x 2^20-tap IR each, UPOLS B=1024 (P=1024, K=1025), white-noise input",
             "blocks_per_call": T,
-            "mode": "streaming (reference call shape)" if T == 1 else f"time-batched, {T} blocks per call",
+            "mode": mode_name(frame, T),
             "sharding": "none" if world == 1 else f"partitions sharded {world}-way + NCCL reduce-scatter of partial spectra, "
                         + ("the reduce-scatter of step i overlaps the r2c+MAC of step i+1 (c2r one step later, drained inside the timed region)"
                            if pipelined else f"{groups} channel group(s) per step"),
@@ -606,7 +641,9 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--blocks", type=int, default=16, help="blocks per call T (1 = the reference's streaming call)")
+    ap.add_argument("--blocks", type=int, default=16, help="direct form (--frame 0): blocks per call T (1 = the reference's streaming call)")
+    ap.add_argument("--frame", type=int, default=256,
+                    help="frame mode: blocks per call T (power of two, 2..512), second overlap-save level along block time; 0 = direct form")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-fft-sweep", action="store_true")
     ap.add_argument("--fft-only", action="store_true")

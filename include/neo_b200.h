@@ -175,6 +175,11 @@ typedef struct neo_b200_conv_config
      * [partition_begin, partition_end) of every filter and yields PARTIAL spectra. 0,0 = all partitions. */
     size_t partition_begin;
     size_t partition_end;
+    /* 0: direct form. T = 2..512 (power of two): "frame mode" -- every process/forward call carries exactly T blocks and the
+     * per-bin sum over partitions is itself evaluated by partitioned overlap-save along block time (frame transforms of length
+     * 2T, ceil(P/T) streamed rows): HBM-bound instead of FP32-bound for long filters. Same results up to rounding; max_blocks is
+     * forced to T; a sharded handle needs partition_begin % T == 0. */
+    size_t frame_blocks;
 } neo_b200_conv_config;
 
 NEO_B200_API int neo_b200_conv_create(neo_b200_conv** conv, neo_b200_conv_config const* config);
@@ -210,8 +215,9 @@ NEO_B200_API int neo_b200_conv_inverse(
 
 NEO_B200_API int neo_b200_conv_set_stream(neo_b200_conv* conv, void* cuda_stream);
 NEO_B200_API int neo_b200_conv_synchronize(neo_b200_conv* conv);
-/* per-phase device time, measured with CUDA events on the handle's stream while enabled: phase_ms[3] = window+r2c+FDL
- * insert, spectral MAC, c2r+overlap (summed since the last read; the read synchronises the stream);
+/* per-phase device time, measured with CUDA events on the handle's stream while enabled: phase_ms[5] = window+r2c+FDL
+ * insert, spectral MAC, c2r+overlap, frame transform forward, frame transform inverse (the last two are 0 outside frame
+ * mode; summed since the last read; the read synchronises the stream);
  * mac_launches = MAC kernel launches in that span. Measurement aid for benchmarks, no effect on results. */
 NEO_B200_API int neo_b200_conv_profile_enable(neo_b200_conv* conv, int enable);
 NEO_B200_API int neo_b200_conv_profile_read(neo_b200_conv* conv, double* phase_ms, uint64_t* mac_launches);

@@ -313,7 +313,7 @@ struct convolver_bank
     ~convolver_bank() { neo_b200_conv_destroy(_conv); }
 
     auto filter(complex_type const* h, size_type outputs, size_type inputs, size_type partitions, size_type bins, int topology,
-                size_type max_blocks = 1, int memspace = NEO_B200_HOST) -> void
+                size_type max_blocks = 1, int memspace = NEO_B200_HOST, size_type frame_blocks = 0) -> void
     {
         neo_b200_conv_destroy(std::exchange(_conv, nullptr));
         _cfg            = neo_b200_conv_config{};
@@ -324,7 +324,8 @@ struct convolver_bank
         _cfg.inputs     = inputs;
         _cfg.block      = bins - 1;
         _cfg.partitions = partitions;
-        _cfg.max_blocks = max_blocks;
+        _cfg.max_blocks = frame_blocks != 0 ? frame_blocks : max_blocks;
+        _cfg.frame_blocks = frame_blocks;  // T > 0: calls of exactly T blocks, second overlap-save level along block time
         detail::check(neo_b200_conv_create(&_conv, &_cfg));
         detail::check(neo_b200_conv_set_filter(_conv, h, memspace));
     }

@@ -43,6 +43,7 @@ class ConvConfig(C.Structure):
         ("max_blocks", _sz),
         ("partition_begin", _sz),
         ("partition_end", _sz),
+        ("frame_blocks", _sz),
     ]
 
 
@@ -352,8 +353,11 @@ class Convolver:
     """
 
     def __init__(self, kind: int = UPOLS, dtype="float32", topology: int = DIAGONAL, max_blocks: int = 1,
-                 partition_range: tuple[int, int] | None = None):
-        self.kind, self.topology, self.max_blocks = kind, topology, max_blocks
+                 partition_range: tuple[int, int] | None = None, frame_blocks: int = 0):
+        # frame_blocks = T > 0: every call carries exactly T blocks and the sum over partitions is evaluated by a second
+        # overlap-save level along block time (neo_b200.h: neo_b200_conv_config::frame_blocks)
+        self.kind, self.topology, self.max_blocks = kind, topology, (frame_blocks or max_blocks)
+        self.frame_blocks = frame_blocks
         self.real = _REAL_OF[str(np.dtype(dtype))]
         self.partition_range = partition_range
         self._h = _vp()
@@ -365,7 +369,7 @@ class Convolver:
         self._spectra_view = None
         lo, hi = self.partition_range or (0, 0)
         self.cfg = ConvConfig(self.kind, _DTYPE_CODE[self.real], self.topology, outputs, inputs, block, partitions,
-                              self.max_blocks, lo, hi)
+                              self.max_blocks, lo, hi, self.frame_blocks)
         _check(library().neo_b200_conv_create(C.byref(self._h), C.byref(self.cfg)))
         if self._stream is not None:
             _check(library().neo_b200_conv_set_stream(self._h, self._stream))
@@ -408,11 +412,14 @@ class Convolver:
     def profile(self, enable: bool) -> None:
         _check(library().neo_b200_conv_profile_enable(self._h, int(enable)))
 
-    def profile_read(self):
-        """(ms_r2c, ms_mac, ms_c2r, mac_launches) since the last read; synchronises the stream."""
-        ms = (C.c_double * 3)()
+    def profile_read(self, frame_phases: bool = False):
+        """(ms_r2c, ms_mac, ms_c2r, mac_launches) since the last read; synchronises the stream. With frame_phases the tuple is
+        (ms_r2c, ms_mac, ms_c2r, ms_frame_forward, ms_frame_inverse, mac_launches)."""
+        ms = (C.c_double * 5)()
         n = C.c_uint64(0)
         _check(library().neo_b200_conv_profile_read(self._h, ms, C.byref(n)))
+        if frame_phases:
+            return float(ms[0]), float(ms[1]), float(ms[2]), float(ms[3]), float(ms[4]), int(n.value)
         return float(ms[0]), float(ms[1]), float(ms[2]), int(n.value)
 
     def device_bytes(self) -> int:

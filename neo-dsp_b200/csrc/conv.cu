@@ -2,7 +2,7 @@
 // Drop-in for neo::convolution::upols_convolver / upola_convolver
 // (src/neo/convolution/uniform_partitioned_convolver.hpp:14-65, dense_convolver.hpp:20-25) and
 // neo::convolution::uniform_partition (uniform_partition.hpp:13-26).
-#include "conv_kernels.cuh"
+#include "conv_frame.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -68,13 +68,24 @@ struct conv_engine
     device_buffer filter, fdl, prev[2], tail[2], acc, ola_y, stage_in, stage_out, stage_filter, tickets;
     int prev_flip{0};  // prev[prev_flip] holds the last block of the previous call
 
+    // second partition level along block time (conv_frame.cuh). frame == 0: direct form. In frame mode `fdl` is the two-frame
+    // level-1 spectra buffer x1 (ring = 2T rows) and `filter` only lives while a filter is being prepared.
+    int frame{0}, logl{0}, tiles2{0}, ring2{0}, parts2{0}, splits2{1};
+    size_t write_pos2{0};
+    int x1_half{0};  // half of x1 the current call writes
+    fft_tables<T> frame_tables;
+    device_buffer frame_tw8;  // stage twiddles of the 8-points-per-thread variant of the long frame transforms
+    device_buffer fdl2, filter2, acc2, tickets2, nyq_acc;
+    bool fused{false};  // bank with an unsplit partition loop: one kernel per frame step (frame_fused_kernel)
+
     // optional per-phase timing with CUDA events on the handle's stream (bench.py's roofline numbers)
     struct span
     {
         cudaEvent_t begin, end;
     };
     bool profiling{false};
-    std::vector<span> spans[3];  // 0 r2c + FDL insert, 1 MAC, 2 c2r
+    static constexpr int k_phases = 5;
+    std::vector<span> spans[k_phases];  // 0 r2c + FDL insert, 1 MAC, 2 c2r, 3 frame transform forward, 4 frame transform inverse
     std::uint64_t mac_launches{0};
 
     int mark_begin(int phase, cudaStream_t stream)
@@ -98,7 +109,7 @@ struct conv_engine
     int read_profile(double* ms, std::uint64_t* launches, cudaStream_t stream)
     {
         NEO_CUDA_TRY(cudaStreamSynchronize(stream));
-        for (int p = 0; p < 3; ++p) {
+        for (int p = 0; p < k_phases; ++p) {
             ms[p] = 0.0;
             for (auto& s : spans[p]) {
                 float t = 0.f;
@@ -117,7 +128,7 @@ struct conv_engine
     size_t device_bytes() const
     {
         return filter.bytes + fdl.bytes + prev[0].bytes + prev[1].bytes + tail[0].bytes + tail[1].bytes + acc.bytes + ola_y.bytes + stage_in.bytes
-             + stage_out.bytes + stage_filter.bytes;
+             + stage_out.bytes + stage_filter.bytes + fdl2.bytes + filter2.bytes + acc2.bytes + nyq_acc.bytes;
     }
 
     int init(neo_b200_conv_config const& c, cudaStream_t stream)
@@ -126,7 +137,8 @@ struct conv_engine
         m       = int(c.block);
         logb    = int(log2_exact(c.block));
         parts   = int(c.partition_end - c.partition_begin);
-        ring    = int(c.partition_end + c.max_blocks - 1);
+        frame   = int(c.frame_blocks);
+        ring    = frame > 0 ? 2 * frame : int(c.partition_end + c.max_blocks - 1);
         sources = c.topology == NEO_B200_MATRIX ? int(c.inputs) : 1;
         filters = c.outputs * size_t(sources);
         logw    = std::min(logb, int(log2_exact(size_t(tile_width<T>()))));
@@ -134,7 +146,7 @@ struct conv_engine
         NEO_TRY(tables.build(logb, true, stream));
 
         size_t const csz = sizeof(cx<T>);
-        NEO_TRY(filter.reserve(filters * parts * m * csz));
+        if (frame == 0) { NEO_TRY(filter.reserve(filters * parts * m * csz)); }
         NEO_TRY(fdl.reserve(c.inputs * size_t(ring) * m * csz));
         NEO_TRY(prev[0].reserve(c.inputs * m * sizeof(T)));
         NEO_TRY(prev[1].reserve(c.inputs * m * sizeof(T)));
@@ -143,21 +155,51 @@ struct conv_engine
             NEO_TRY(tail[1].reserve(c.outputs * m * sizeof(T)));
             NEO_TRY(ola_y.reserve(c.outputs * c.max_blocks * 2 * m * sizeof(T)));
         }
-        // split the partition loop when (bins x outputs) alone cannot fill the GPU: ~4 CTAs per SM wanted
         int sms = 148;
         int dev = 0;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        size_t const ctas_xy = size_t((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads) * c.outputs;
-        size_t const work    = size_t(sources) * parts;
-        size_t want          = (size_t(sms) * (sources > 1 ? 16 : 4) + ctas_xy - 1) / ctas_xy;
-        want                 = std::min(want, std::max<size_t>(1, work / 8));
-        splits               = int(std::max<size_t>(1, std::min<size_t>(want, 64)));
+        splits = frame > 0 ? 1 : pick_splits(sms, size_t(m), size_t(parts));
         NEO_TRY(acc.reserve(size_t(splits) * c.outputs * c.max_blocks * m * csz));
         // one ticket per MAC grid cell (x: at most B/128 column blocks, y: outputs); the last split CTA to finish resets it
         NEO_TRY(tickets.reserve(c.outputs * size_t(std::max(1, m / 128 + 1)) * sizeof(unsigned)));
         NEO_CUDA_TRY(cudaMemsetAsync(tickets.ptr, 0, tickets.bytes, stream));
+
+        if (frame > 0) {
+            int const len = 2 * frame;
+            int const w   = 1 << logw;
+            logl          = int(log2_exact(size_t(len)));
+            tiles2        = nt * len + (len + w - 1) / w;
+            ring2         = int((c.partition_end + size_t(frame) - 1) / size_t(frame));
+            parts2        = (parts + frame - 1) / frame;
+            size_t const m2 = size_t(tiles2) << logw;
+            splits2       = pick_splits(sms, m2, size_t(parts2));
+            NEO_TRY(frame_tables.build(logl, false, stream));
+            if (frame_variant_is_e8(logl, sizeof(T) == 4)) {
+                auto const tw = make_stage_twiddles<T>(logl, 3);
+                NEO_TRY(frame_tw8.reserve(tw.size() * csz));
+                NEO_CUDA_TRY(cudaMemcpyAsync(frame_tw8.ptr, tw.data(), tw.size() * csz, cudaMemcpyHostToDevice, stream));
+                NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+            }
+            NEO_TRY(filter2.reserve(filters * parts2 * m2 * csz));
+            NEO_TRY(fdl2.reserve(c.inputs * size_t(ring2) * m2 * csz));
+            fused = sources == 1 && splits2 == 1 && std::getenv("NEO_B200_FRAME_UNFUSED") == nullptr;
+            if (fused) { NEO_TRY(nyq_acc.reserve(c.outputs * size_t(len) * csz)); }
+            else { NEO_TRY(acc2.reserve(size_t(splits2) * c.outputs * m2 * csz)); }
+            NEO_TRY(tickets2.reserve(c.outputs * (m2 / 128 + 1) * sizeof(unsigned)));
+            NEO_CUDA_TRY(cudaMemsetAsync(tickets2.ptr, 0, tickets2.bytes, stream));
+        }
         return clear_state(stream);
+    }
+
+    // split the partition loop when (bins x outputs) alone cannot fill the GPU: ~4 CTAs per SM wanted
+    int pick_splits(int sms, size_t bins, size_t rows) const
+    {
+        size_t const ctas_xy = ((bins / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads) * cfg.outputs;
+        size_t const work    = size_t(sources) * rows;
+        size_t want          = (size_t(sms) * (sources > 1 ? 16 : 4) + ctas_xy - 1) / ctas_xy;
+        want                 = std::min(want, std::max<size_t>(1, work / 8));
+        return int(std::max<size_t>(1, std::min<size_t>(want, 64)));
     }
 
     int clear_state(cudaStream_t stream)
@@ -170,9 +212,41 @@ struct conv_engine
             NEO_CUDA_TRY(cudaMemsetAsync(tail[0].ptr, 0, tail[0].bytes, stream));
             NEO_CUDA_TRY(cudaMemsetAsync(tail[1].ptr, 0, tail[1].bytes, stream));
         }
-        write_pos = 0;
-        tail_flip = 0;
+        if (fdl2.ptr != nullptr) { NEO_CUDA_TRY(cudaMemsetAsync(fdl2.ptr, 0, fdl2.bytes, stream)); }
+        write_pos  = 0;
+        write_pos2 = 0;
+        x1_half    = 0;
+        tail_flip  = 0;
         return NEO_B200_OK;
+    }
+
+    // frame mode: the level-1 filter exists only between begin_filter and finish_filter
+    int begin_filter()
+    {
+        if (frame > 0) { NEO_TRY(filter.reserve(filters * parts * m * sizeof(cx<T>))); }
+        return NEO_B200_OK;
+    }
+
+    int finish_filter(cudaStream_t stream)
+    {
+        if (frame > 0) {
+            frame_geom const fg{logb, logw, nt, frame, tiles2};
+            int status = NEO_B200_ERR_UNSUPPORTED;
+            NEO_CUDA_TRY(cudaMemsetAsync(filter2.ptr, 0, filter2.bytes, stream));  // unused Nyquist-tile columns stay zero
+            NEO_DISPATCH_LOGL(logl, {
+                frame_filter_io<T, false> io{filter.template as<cx<T>>(), filter2.template as<cx<T>>(), fg, parts, parts2};
+                status = launch_frame_fft<T, LOGL, -1>(io, frame_tables.tw(), (filters * size_t(parts2)) << logb, stream);
+                if (status == NEO_B200_OK) {
+                    frame_filter_io<T, true> nq{filter.template as<cx<T>>(), filter2.template as<cx<T>>(), fg, parts, parts2};
+                    status = launch_frame_fft<T, LOGL, -1>(nq, frame_tables.tw(), filters * size_t(parts2), stream);
+                }
+            });
+            if (status != NEO_B200_OK) { return status == NEO_B200_ERR_UNSUPPORTED ? fail(status, "frame of %d blocks not supported", frame) : status; }
+            NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+            filter.release();
+        }
+        has_filter = true;
+        return clear_state(stream);
     }
 
     // H in the reference layout [filters][P][B+1]; device pointer
@@ -193,6 +267,7 @@ struct conv_engine
         size_t const p_total = cfg.partitions;
         size_t const k       = size_t(m) + 1;
         size_t const csz     = sizeof(cx<T>);
+        NEO_TRY(begin_filter());
         if (memspace == NEO_B200_DEVICE) {
             NEO_TRY(pack_filter(static_cast<cx<T> const*>(h), 0, filters, p_total, int(cfg.partition_begin), stream));
         } else {
@@ -209,8 +284,7 @@ struct conv_engine
                 NEO_CUDA_TRY(cudaStreamSynchronize(stream));  // staging buffer is reused
             }
         }
-        has_filter = true;
-        return clear_state(stream);
+        return finish_filter(stream);
     }
 
     int partition_into(T const* ir_dev, size_t taps, size_t first_filter, size_t count, cudaStream_t stream)
@@ -228,6 +302,7 @@ struct conv_engine
 
     int set_impulse(void const* ir, size_t taps, int memspace, cudaStream_t stream)
     {
+        NEO_TRY(begin_filter());
         if (memspace == NEO_B200_DEVICE) {
             NEO_TRY(partition_into(static_cast<T const*>(ir), taps, 0, filters, stream));
         } else {
@@ -242,8 +317,7 @@ struct conv_engine
                 NEO_CUDA_TRY(cudaStreamSynchronize(stream));
             }
         }
-        has_filter = true;
-        return clear_state(stream);
+        return finish_filter(stream);
     }
 
     // window + r2c + FDL insert for input channels [chan0, chan0 + nchan); `in` points at channel chan0's row
@@ -254,18 +328,108 @@ struct conv_engine
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
                 conv_r2c_io<T, LOGM> io{in, in_stride, prev[prev_flip].template as<T>(), prev[prev_flip ^ 1].template as<T>(),
-                                        fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
+                                        fdl.template as<cx<T>>(), ring, frame > 0 ? x1_half * frame : int(write_pos), int(blocks),
                                         cfg.kind == NEO_B200_UPOLA ? 1 : 0, logw, nt, chan0};
                 status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
             }
         });
         if (status != NEO_B200_OK) { return status == NEO_B200_ERR_UNSUPPORTED ? fail(status, "block size %d not supported", m) : status; }
-        return mark_end(0, stream);
+        NEO_TRY(mark_end(0, stream));
+        return frame > 0 && !fused ? frame_forward(chan0, nchan, stream) : NEO_B200_OK;
+    }
+
+    // frame mode, bank: frame transform + ring insert + MAC + inverse frame transform in one kernel (Nyquist sequences first)
+    int frame_fused_step(size_t out0, size_t nout, cudaStream_t stream)
+    {
+        frame_geom const fg{logb, logw, nt, frame, tiles2};
+        int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_TRY(mark_begin(1, stream));
+        NEO_DISPATCH_LOGL(logl, {
+            frame_fused_io<T, true> nq{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), filter2.template as<cx<T>>(),
+                                       acc.template as<cx<T>>(), nyq_acc.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2),
+                                       parts2, int(cfg.partition_begin / size_t(frame)), T(1) / T(2 * frame), out0};
+            status = launch_frame_fused<T, LOGL, true>(nq, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout, stream);
+            if (status == NEO_B200_OK) {
+                frame_fused_io<T, false> io{nq.x1, nq.fdl2, nq.filt2, nq.y1, nq.nyq_acc, fg, nq.new_half, nq.ring2, nq.slot,
+                                            nq.parts2, nq.age0, nq.scale, out0};
+                status = launch_frame_fused<T, LOGL, false>(io, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout << logb, stream);
+            }
+        });
+        if (status != NEO_B200_OK) { return status; }
+        ++mac_launches;
+        return mark_end(1, stream);
+    }
+
+    // frame mode: transform the spectra of (previous frame, this frame) along block time into ring slot write_pos2
+    int frame_forward(size_t chan0, size_t nchan, cudaStream_t stream)
+    {
+        frame_geom const fg{logb, logw, nt, frame, tiles2};
+        int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_TRY(mark_begin(3, stream));
+        NEO_DISPATCH_LOGL(logl, {
+            frame_fwd_io<T, false> io{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2), chan0};
+            status = launch_frame_fft<T, LOGL, -1>(io, frame_tables.tw(), nchan << logb, stream);
+            if (status == NEO_B200_OK) {
+                frame_fwd_io<T, true> nq{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2), chan0};
+                status = launch_frame_fft<T, LOGL, -1>(nq, frame_tables.tw(), nchan, stream);
+            }
+        });
+        if (status != NEO_B200_OK) { return status; }
+        return mark_end(3, stream);
+    }
+
+    // frame mode: Q streamed rows of L*B (+ Nyquist) bins, then back to the level-1 spectra of this frame's T blocks
+    int frame_mac(size_t out0, size_t nout, cudaStream_t stream)
+    {
+        if (fused) { return frame_fused_step(out0, nout, stream); }
+        size_t const m2 = size_t(tiles2) << logw;
+        mac_geom g{};
+        g.m           = int(m2);
+        g.logw        = logw;
+        g.nt          = tiles2;
+        g.ring        = ring2;
+        g.parts       = parts2;
+        g.age0        = int(cfg.partition_begin / size_t(frame));
+        g.sources     = sources;
+        g.diagonal    = cfg.topology == NEO_B200_DIAGONAL ? 1 : 0;
+        g.wp          = int(write_pos2);
+        g.blocks      = 1;
+        g.tau0        = 0;
+        g.splits      = splits2;
+        g.out0        = int(out0);
+        g.packed_edge = 0;
+        g.acc_plane   = cfg.outputs * m2;
+        g.tickets     = tickets2.template as<unsigned>();
+        NEO_TRY(mark_begin(1, stream));
+        if (sources == 1 && splits2 == 1) {
+            // bank: short row loops, several columns per thread (about 32 (filter, spectrum) pairs each)
+            int const ncols   = std::max(1, std::min(16, 32 / parts2));
+            size_t const cols = (m2 / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads;
+            dim3 const grid(unsigned((cols + size_t(ncols) - 1) / size_t(ncols)), unsigned(nout));
+            frame_mac_kernel<T><<<grid, k_mac_threads, 0, stream>>>(fdl2.template as<cx<T>>(), filter2.template as<cx<T>>(),
+                                                                     acc2.template as<cx<T>>(), g, ncols);
+            NEO_TRY(check_launch("frame_mac_kernel"));
+        } else {
+            NEO_TRY(launch_stream(fdl2.template as<cx<T>>(), filter2.template as<cx<T>>(), acc2.template as<cx<T>>(), g, nout, stream));
+        }
+        ++mac_launches;
+        NEO_TRY(mark_end(1, stream));
+
+        frame_geom const fg{logb, logw, nt, frame, tiles2};
+        int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_TRY(mark_begin(4, stream));
+        NEO_DISPATCH_LOGL(logl, {
+            frame_inv_io<T> io{acc2.template as<cx<T>>(), acc.template as<cx<T>>(), fg, T(1) / T(2 * frame), out0};
+            status = launch_frame_fft<T, LOGL, 1>(io, frame_tables.tw(), nout << logb, stream);
+        });
+        if (status != NEO_B200_OK) { return status; }
+        return mark_end(4, stream);
     }
 
     // spectral MAC of outputs [out0, out0 + nout) for the `blocks` blocks just inserted
     int forward_mac(size_t blocks, size_t out0, size_t nout, cudaStream_t stream)
     {
+        if (frame > 0) { return frame_mac(out0, nout, stream); }
         mac_geom g{};
         g.m         = m;
         g.logw      = logw;
@@ -278,6 +442,7 @@ struct conv_engine
         g.blocks    = int(blocks);
         g.splits    = splits;
         g.out0      = int(out0);
+        g.packed_edge = 1;
         g.acc_plane = cfg.outputs * blocks * size_t(m);
         g.tickets   = tickets.template as<unsigned>();
 
@@ -299,7 +464,12 @@ struct conv_engine
     // the ring position moves once per call, after every channel group has been inserted
     void advance(size_t blocks)
     {
-        write_pos = (write_pos + blocks) % size_t(ring);
+        if (frame > 0) {
+            write_pos2 = (write_pos2 + 1) % size_t(ring2);
+            x1_half ^= 1;
+        } else {
+            write_pos = (write_pos + blocks) % size_t(ring);
+        }
         prev_flip ^= 1;  // the r2c kernels saved this call's last block into the other half-window buffer
     }
 
@@ -316,18 +486,7 @@ struct conv_engine
         auto const* x = fdl.template as<cx<T>>();
         auto const* h = filter.template as<cx<T>>();
         auto* a       = acc.template as<cx<T>>();
-        if (tb == 1) {
-            unsigned const gx = unsigned((m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads);
-            if (cfg.topology == NEO_B200_MATRIX && nout % 4 == 0) {
-                // four outputs per thread share every FDL row they load
-                dim3 const grid(gx, unsigned(nout / 4), unsigned(splits));
-                fdl_mac_stream_kernel<T, 4><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
-            } else {
-                dim3 const grid(gx, unsigned(nout), unsigned(splits));
-                fdl_mac_stream_kernel<T, 1><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
-            }
-            return check_launch("fdl_mac_stream_kernel");
-        }
+        if (tb == 1) { return launch_stream(x, h, a, g, nout, stream); }
         if constexpr (sizeof(T) == 4) {
             if (m >= 128 && tb >= 8) {
                 dim3 const tgrid{static_cast<unsigned>(nt), static_cast<unsigned>(nout), static_cast<unsigned>(splits)};
@@ -348,6 +507,20 @@ struct conv_engine
                 break;
         }
         return check_launch("fdl_mac_toeplitz_kernel");
+    }
+
+    int launch_stream(cx<T> const* x, cx<T> const* h, cx<T>* a, mac_geom const& g, size_t nout, cudaStream_t stream)
+    {
+        unsigned const gx = unsigned((g.m / mac_vec<T>::VEC + k_mac_threads - 1) / k_mac_threads);
+        if (cfg.topology == NEO_B200_MATRIX && nout % 4 == 0) {
+            // four outputs per thread share every FDL row they load
+            dim3 const grid(gx, unsigned(nout / 4), unsigned(g.splits));
+            fdl_mac_stream_kernel<T, 4><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
+        } else {
+            dim3 const grid(gx, unsigned(nout), unsigned(g.splits));
+            fdl_mac_stream_kernel<T, 1><<<grid, k_mac_threads, 0, stream>>>(x, h, a, g);
+        }
+        return check_launch("fdl_mac_stream_kernel");
     }
 
     template<int TB, int CH, int STAGES>
@@ -408,10 +581,23 @@ int validate(neo_b200_conv_config& c)
     // they agree only for power-of-two B, which is also what every reference test uses
     if (!is_pow2(c.block) || c.block < 2) { return fail(NEO_B200_ERR_INVALID, "block size must be a power of two >= 2, got %zu", c.block); }
     if (c.partitions == 0) { return fail(NEO_B200_ERR_INVALID, "partitions must be > 0"); }
+    if (c.frame_blocks != 0) {
+        if (!is_pow2(c.frame_blocks) || c.frame_blocks < 2 || c.frame_blocks > k_max_frame_blocks) {
+            return fail(NEO_B200_ERR_INVALID, "frame_blocks must be a power of two in [2, %zu], got %zu", k_max_frame_blocks, c.frame_blocks);
+        }
+        if (c.max_blocks != 0 && c.max_blocks != c.frame_blocks) {
+            return fail(NEO_B200_ERR_INVALID, "frame mode processes exactly frame_blocks=%zu blocks per call (max_blocks=%zu)", c.frame_blocks,
+                        c.max_blocks);
+        }
+        c.max_blocks = c.frame_blocks;
+    }
     if (c.max_blocks == 0) { c.max_blocks = 1; }
     if (c.partition_begin == 0 && c.partition_end == 0) { c.partition_end = c.partitions; }
     if (c.partition_begin >= c.partition_end || c.partition_end > c.partitions) {
         return fail(NEO_B200_ERR_INVALID, "bad partition range [%zu, %zu) of %zu", c.partition_begin, c.partition_end, c.partitions);
+    }
+    if (c.frame_blocks != 0 && c.partition_begin % c.frame_blocks != 0) {
+        return fail(NEO_B200_ERR_INVALID, "frame mode: partition_begin=%zu must be a multiple of frame_blocks=%zu", c.partition_begin, c.frame_blocks);
     }
     if (c.partition_end + c.max_blocks > (size_t(1) << 30) || c.outputs > 65535) { return fail(NEO_B200_ERR_INVALID, "configuration too large"); }
     return NEO_B200_OK;
@@ -550,7 +736,13 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
     T* const dout = e.stage_out.template as<T>();
     size_t groups = 1;
     // worth it only when the copies are long enough to matter next to the kernels (several blocks per call)
-    if (conv->cfg.topology == NEO_B200_DIAGONAL && blocks >= 4) { groups = chans >= 512 ? 4 : chans >= 128 ? 2 : 1; }
+    if (conv->cfg.topology == NEO_B200_DIAGONAL && blocks >= 4) {
+        groups = chans >= 512 ? 4 : chans >= 128 ? 2 : 1;
+        // long calls (frame mode): about 64 MB per group, so the un-overlapped first H2D and last D2H stay a small share
+        size_t const by_bytes = chans * stride * sizeof(T) / (size_t(64) << 20);
+        groups                = std::max(groups, std::min<size_t>({by_bytes, size_t(16), chans / 32}));
+        groups                = std::max<size_t>(groups, 1);
+    }
     if (char const* env = std::getenv("NEO_B200_HOST_GROUPS")) {  // tuning knob
         size_t const want = size_t(std::max(1, std::atoi(env)));
         if (conv->cfg.topology == NEO_B200_DIAGONAL && want <= chans) { groups = want; }
@@ -595,6 +787,9 @@ static int conv_check_call(neo_b200_conv* conv, size_t blocks)
     if (!ready) { return fail(NEO_B200_ERR_INVALID, "no filter set"); }
     if (blocks == 0 || blocks > conv->cfg.max_blocks) {
         return fail(NEO_B200_ERR_INVALID, "blocks=%zu outside [1, max_blocks=%zu]", blocks, conv->cfg.max_blocks);
+    }
+    if (conv->cfg.frame_blocks != 0 && blocks != conv->cfg.frame_blocks) {
+        return fail(NEO_B200_ERR_INVALID, "frame mode: every call processes exactly frame_blocks=%zu blocks, got %zu", conv->cfg.frame_blocks, blocks);
     }
     NEO_CUDA_TRY(cudaSetDevice(conv->device));
     return NEO_B200_OK;

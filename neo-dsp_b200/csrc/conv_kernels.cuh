@@ -55,6 +55,7 @@ struct mac_geom
     int tau0;          // first block of this launch inside the call
     int splits;        // S
     int out0;          // first output channel of this launch (blockIdx.y is relative to it)
+    int packed_edge;   // 1: element 0 of a row is the packed pair (Re X[0], Re X[B]); 0: an ordinary complex bin (frame level)
     size_t acc_plane;  // elements per partial plane
     unsigned* tickets; // one counter per (blockIdx.x, output row of the grid): which split CTA finishes last
 };
@@ -176,7 +177,7 @@ __global__ void __launch_bounds__(k_mac_threads)
     V a[OT];
 #pragma unroll
     for (int o = 0; o < OT; ++o) { a[o] = MV::zero(); }
-    bool const edge = (col == 0);  // this thread owns the packed bin 0
+    bool const edge = (col == 0) && g.packed_edge != 0;  // this thread owns the packed bin 0
 
     // tile-major addressing in units of V (VEC elements)
     int const k0       = col * MV::VEC;

@@ -1,0 +1,172 @@
+"""GPU: frame mode (neo_b200_conv_config::frame_blocks = T) -- the sum over partitions evaluated by a second overlap-save level
+along block time -- must reproduce the reference's block-by-block upols/upola convolvers (the oracle) to the same tolerance as
+the direct form: different operation order, same mathematics."""
+import numpy as np
+import pytest
+
+from conftest import TOL, rel_l2
+from test_conv_gpu import make_case, run_bank
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name,kind", [("upols", 0), ("upola", 1)])
+@pytest.mark.parametrize("tag,real", [("f32", np.float32), ("f64", np.float64)])
+def test_golden_vectors_from_the_reference(gpu, golden, name, kind, tag, real):
+    B, L, NB = (int(v) for v in golden["conv/block"])
+    H, sig, want = golden[f"conv/{tag}/H"], golden[f"conv/{tag}/signal"], golden[f"conv/{tag}/{name}"]
+    for T in (2, 4):
+        if NB % T:
+            continue
+        conv = gpu.Convolver(kind, real, gpu.DIAGONAL, frame_blocks=T)
+        conv.filter(H)
+        got = run_bank(conv, sig, B, [T])
+        assert rel_l2(got, want) <= TOL[np.dtype(real).name], T
+        conv.close()
+
+
+@pytest.mark.parametrize("block,taps,channels,T,frames", [
+    (2, 7, 3, 2, 5),                  # P = 4, L = 4: smallest of everything
+    (16, 100, 3, 4, 6),               # P = 7 -> Q = 2, last second-level partition ragged
+    (128, 128 * 9 - 3, 3, 4, 5),      # P = 9 -> Q = 3
+    (128, 1000, 3, 8, 4),             # P = 8 = T: one second-level partition
+    (512, 512 * 17, 2, 16, 3),        # P = 17 -> Q = 2
+    (1024, 1024 * 33 - 5, 2, 32, 3),  # BASELINE config 5's block size
+    (64, 64 * 5, 2, 64, 3),           # T > P: L = 128 frame transform, Nyquist tile wider than one tile of bins
+    (256, 256 * 3, 1, 512, 2),        # largest frame: L = 1024
+    (4096, 4096 * 3, 1, 2, 3),
+])
+def test_frame_mode_matches_oracle(gpu, orc, block, taps, channels, T, frames):
+    ir, sig = make_case(orc, channels, taps, block, T * frames)
+    H = orc.uniform_partition(ir, block)
+    want = orc.convolve_blocks(0, H, sig)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+    conv.filter(H)
+    got = run_bank(conv, sig, block, [T])
+    assert rel_l2(got, want) <= 1e-5, rel_l2(got, want)
+    # every frame on its own is right too (a wrong ring pairing would still pass a whole-signal norm if late frames dominate)
+    for f in range(frames):
+        sl = slice(f * T * block, (f + 1) * T * block)
+        assert rel_l2(got[:, sl], want[:, sl]) <= 2e-5, f
+    # same state machine from time-domain impulse responses, and after reset()
+    conv.impulse(ir, block)
+    assert rel_l2(run_bank(conv, sig, block, [T]), want) <= 1e-5
+    conv.reset()
+    assert rel_l2(run_bank(conv, sig, block, [T]), want) <= 1e-5
+    conv.close()
+
+
+@pytest.mark.parametrize("block,taps,T", [(16, 100, 4), (256, 256 * 9 - 3, 8)])
+def test_frame_mode_upola_and_f64(gpu, orc, block, taps, T):
+    for real in (np.float32, np.float64):
+        ir, sig = make_case(orc, 2, taps, block, T * 4, real)
+        H = orc.uniform_partition(ir, block)
+        for kind in (gpu.UPOLS, gpu.UPOLA):
+            conv = gpu.Convolver(kind, real, gpu.DIAGONAL, frame_blocks=T)
+            conv.filter(H)
+            got = run_bank(conv, sig, block, [T])
+            assert rel_l2(got, orc.convolve_blocks(kind, H, sig)) <= TOL[np.dtype(real).name], (kind, real)
+            conv.close()
+
+
+@pytest.mark.parametrize("outputs", [2, 4])  # 4: the four-outputs-per-thread streaming kernel
+def test_frame_mode_matrix_topology(gpu, orc, outputs):
+    O, I, B, L, T, frames = outputs, 3, 64, 64 * 9, 4, 4
+    NB = T * frames
+    ir = np.stack([np.stack([orc.noise(L, 100 + 10 * o + i, np.float32) for i in range(I)]) for o in range(O)])
+    ir /= np.sqrt((ir**2).sum(axis=2).max())
+    sig = np.stack([orc.noise(B * NB, 13 + i, np.float32) for i in range(I)])
+    want = np.zeros((O, B * NB), dtype=np.float64)
+    for o in range(O):
+        want[o] = orc.convolve_blocks(0, orc.uniform_partition(ir[o], B), sig).astype(np.float64).sum(axis=0)
+    Hm = np.stack([orc.uniform_partition(ir[o], B) for o in range(O)])
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.MATRIX, frame_blocks=T)
+    conv.filter(Hm)
+    got = np.zeros((O, B * NB), dtype=np.float32)
+    for f in range(frames):
+        got[:, f * T * B : (f + 1) * T * B] = conv(np.ascontiguousarray(sig[:, f * T * B : (f + 1) * T * B]))
+    assert rel_l2(got, want) <= 1e-5
+    conv.close()
+
+
+def test_frame_mode_partition_sharded_handles_sum_to_the_whole(gpu, orc):
+    import torch
+
+    C, B, P, T, frames = 4, 128, 12, 2, 9
+    ir, sig = make_case(orc, C, B * P - 17, B, T * frames)
+    H = orc.uniform_partition(ir, B)
+    want = orc.convolve_blocks(0, H, sig)
+    convs = []
+    for lo, hi in [(0, 4), (4, 6), (6, 12)]:
+        c = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, partition_range=(lo, hi), frame_blocks=T)
+        c.filter(H)
+        convs.append(c)
+    got = np.zeros_like(sig)
+    for pos in range(0, T * frames, T):
+        x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + T) * B])).cuda()
+        total = None
+        for c in convs:
+            c.forward(x)
+            c.synchronize()
+            part = c.spectra_tensor(T).clone()
+            total = part if total is None else total + part
+        y = torch.empty_like(x)
+        convs[1].inverse(total.contiguous(), y, 0, C, T)
+        convs[1].synchronize()
+        got[:, pos * B : (pos + T) * B] = y.cpu().numpy()
+    assert rel_l2(got, want) <= 1e-5
+    with pytest.raises(RuntimeError):  # a shard must start on a frame boundary of the partition axis
+        c = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, partition_range=(3, 12), frame_blocks=T)
+        c.filter(H)
+
+
+def test_frame_mode_wide_bank_host_pipeline_and_device_path(gpu, orc):
+    import torch
+
+    C, B, P, T, frames = 160, 64, 5, 4, 4
+    ir, sig = make_case(orc, C, B * P - 3, B, T * frames)
+    H = orc.uniform_partition(ir, B)
+    want = orc.convolve_blocks(0, H, sig)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+    conv.filter(H)
+    assert rel_l2(run_bank(conv, sig, B, [T]), want) <= 1e-5  # host buffers: channel groups over three streams
+    conv.close()
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+    conv.set_stream(torch.cuda.current_stream())
+    conv.filter(torch.from_numpy(H).cuda())
+    dx = torch.from_numpy(sig).cuda()
+    dy = torch.empty_like(dx)
+    for pos in range(0, T * frames, T):
+        chunk = dx[:, pos * B : (pos + T) * B].contiguous()
+        out = torch.empty_like(chunk)
+        conv(chunk, out=out)
+        dy[:, pos * B : (pos + T) * B] = out
+    torch.cuda.synchronize()
+    assert rel_l2(dy.cpu().numpy(), want) <= 1e-5
+    conv.close()
+
+
+def test_frame_mode_small_bank_splits_rows_across_ctas(gpu, orc):
+    # one channel, many second-level partitions: the streamed rows are split over CTAs and folded by the last one
+    B, P, T, frames = 32, 96, 2, 6
+    ir, sig = make_case(orc, 1, B * P, B, T * frames)
+    H = orc.uniform_partition(ir, B)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+    conv.filter(H)
+    assert rel_l2(run_bank(conv, sig, B, [T]), orc.convolve_blocks(0, H, sig)) <= 1e-5
+    conv.close()
+
+
+def test_frame_mode_error_contract(gpu, orc):
+    H = np.zeros((2, 3, 65), dtype=np.complex64)
+    for bad in (3, 1, 1024):
+        with pytest.raises(RuntimeError):
+            gpu.Convolver(gpu.UPOLS, np.float32, frame_blocks=bad).filter(H)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, frame_blocks=4)
+    conv.filter(H)
+    with pytest.raises(RuntimeError):
+        conv(np.zeros((2, 64 * 2), dtype=np.float32))  # not a whole frame
+    with pytest.raises(RuntimeError):
+        conv(np.zeros((2, 64 * 8), dtype=np.float32))
+    conv(np.zeros((2, 64 * 4), dtype=np.float32))
+    conv.close()
