@@ -69,7 +69,7 @@ struct conv_engine
     int prev_flip{0};  // prev[prev_flip] holds the last block of the previous call
 
     // second partition level along block time (conv_frame.cuh). frame == 0: direct form. In frame mode `fdl` is the two-frame
-    // level-1 spectra buffer x1 (ring = 2T rows) and `filter` only lives while a filter is being prepared.
+    // level-1 spectra buffer x1 (2T plain rows of B per channel, not tiled) and `filter` only lives while a filter is prepared.
     int frame{0}, logl{0}, tiles2{0}, ring2{0}, parts2{0}, splits2{1};
     size_t write_pos2{0};
     int x1_half{0};  // half of x1 the current call writes
@@ -329,7 +329,7 @@ struct conv_engine
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
                 conv_r2c_io<T, LOGM> io{in, in_stride, prev[prev_flip].template as<T>(), prev[prev_flip ^ 1].template as<T>(),
                                         fdl.template as<cx<T>>(), ring, frame > 0 ? x1_half * frame : int(write_pos), int(blocks),
-                                        cfg.kind == NEO_B200_UPOLA ? 1 : 0, logw, nt, chan0};
+                                        cfg.kind == NEO_B200_UPOLA ? 1 : 0, frame > 0 ? logb : logw, frame > 0 ? 1 : nt, chan0};
                 status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
             }
         });

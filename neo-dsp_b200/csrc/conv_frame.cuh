@@ -19,7 +19,7 @@
 // imaginary part before the inverse frame transform (both results are real, so IFFT(A0 + i*AB) = Y0 + i*YB, the packed form).
 //
 // HBM layout (W = tile width, nt = B/W, tiles2 = nt*L + ceil(L/W)):
-//   x1     [inputs][nt][2T][W]            level-1 spectra of the previous and the current frame (two halves, ping-pong)
+//   x1     [inputs][2T][B]                level-1 spectra of the previous and the current frame (two halves, ping-pong), row-major
 //   fdl2   [inputs][tiles2][R2][W]        ring of frame spectra, R2 = ceil(partition_end / T); tile2 = tile*L + f, then Nyquist
 //   filt2  [filters][tiles2][Q][W]        Q local second-level partitions
 //   acc2   [S][outputs][tiles2][W]        MAC result (S partial planes, folded into plane 0)
@@ -127,7 +127,7 @@ struct frame_fwd_io
         int const k         = NYQ ? 0 : int(unit & ((size_t(1) << g.logb) - 1));
         int const tile      = k >> g.logw;
         int const w         = k & ((1 << g.logw) - 1);
-        C const* const src  = x1 + (((chan * g.nt + tile) * size_t(L)) << g.logw) + w;
+        C const* const src  = x1 + ((chan * size_t(L)) << g.logb) + k;
         size_t const tile2  = NYQ ? size_t(g.nt) * L : size_t(tile) * L;
         C* const dst        = fdl2 + (((chan * g.tiles2 + tile2) * ring2 + slot) << g.logw) + (NYQ ? 0 : w);
         return {src, dst, k == 0};
@@ -136,7 +136,7 @@ struct frame_fwd_io
     {
         int const half = n < g.frame ? (new_half ^ 1) : new_half;
         int const row  = half * g.frame + (n & (g.frame - 1));
-        C v            = s.src[size_t(row) << g.logw];
+        C v            = s.src[size_t(row) << g.logb];
         if constexpr (NYQ) { return mk<T>(v.y, T(0)); }
         if (s.edge) { v.y = T(0); }
         return v;
@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
     int const tile      = k >> logw;
     int const w         = k & wmask;
     size_t const tile2  = NYQ ? size_t(g.nt) * L : size_t(tile) * L;
-    C const* const src  = io.x1 + (((chan * g.nt + tile) * size_t(L)) << logw) + w;
+    C const* const src  = io.x1 + ((chan * size_t(L)) << g.logb) + k;
     C* const ring       = io.fdl2 + (((chan * g.tiles2 + tile2) * io.ring2) << logw) + (NYQ ? 0 : w);
     C const* const filt = io.filt2 + (((chan * g.tiles2 + tile2) * io.parts2) << logw) + (NYQ ? 0 : w);
     // element (frame bin f, row r) of a [..][rows][W] run of tiles
@@ -386,7 +386,28 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
         int const st = c % 3;
         return st == 2 ? smem_raw : smem_raw + cfg::SMEM + st * ac::STAGE;
     };
-    int const nchunks                  = io.parts2 * ac::NH;
+    int const nchunks = io.parts2 * ac::NH;
+    // Warp-private staging: a warp copies exactly the rows its own threads will read (its TW = 32/G values of t, all CH points u of
+    // the chunk), so the MAC loop needs __syncwarp() only. Lane -> (row, 16-byte piece) is fixed; a chunk moves every pointer by a
+    // constant, so the per-copy address work is one multiply-add.
+    constexpr int TW    = 32 / cfg::G;                  // values of t per warp
+    constexpr int RP    = ac::ROW_PIECES;               // 16-byte pieces per row of G bins
+    constexpr int KSTEP = 16 / int(sizeof(C));          // u advances by KSTEP per copy of a lane
+    static_assert(!ASYNC || (cfg::G <= 32 && (32 / RP) == KSTEP * TW), "warp-private staging geometry");
+    int const lane      = int(threadIdx.x) & 31;
+    int const lrow      = lane / RP;
+    int const u0        = lrow / (TW > 0 ? TW : 1);
+    int const t_mine    = (int(threadIdx.x) >> 5) * TW + lrow % (TW > 0 ? TW : 1);  // the t whose row this lane copies
+    int const f0        = t_mine + u0 * TN;              // frame bin of the lane's first copy of a chunk with eh = 0
+    size_t const eo     = size_t(lane % RP) * KSTEP;     // element offset inside the group of bins
+    C const* const h0   = filt - gi + eo + at(f0, 0, io.parts2);
+    C const* const x0   = ring - gi + eo + at(f0, 0, io.ring2);
+    size_t const h_step = at(KSTEP * TN, 0, io.parts2);  // elements between a lane's consecutive copies
+    size_t const x_step = at(KSTEP * TN, 0, io.ring2);
+    size_t const h_half = at(ac::CH * TN, 0, io.parts2); // elements between the halves eh of a partition
+    size_t const x_half = at(ac::CH * TN, 0, io.ring2);
+    unsigned const dst0 = unsigned((u0 * TN + t_mine) * cfg::G * int(sizeof(C)) + (lane % RP) * 16);  // byte offset inside an operand
+    constexpr unsigned dst_step = unsigned(KSTEP * TN * cfg::G * int(sizeof(C)));
     auto const issue = [&](int c) {
         if constexpr (ASYNC) {
             if (c < nchunks) {
@@ -394,19 +415,14 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
                 int const eh = c - q * ac::NH;
                 int sl       = slot0 - q;
                 sl += sl < 0 ? io.ring2 : 0;
-                unsigned char* const dst_h = stage_ptr(c);
-                unsigned char* const dst_x = dst_h + ac::OPERAND;
+                unsigned char* const dst_h = stage_ptr(c) + dst0;
+                C const* const hp          = h0 + size_t(eh) * h_half + (size_t(q) << logw);
+                C const* const xp          = x0 + size_t(eh) * x_half + (size_t(sl) << logw);
                 bool const want_x          = !(q == 0 && newest_in_regs);
 #pragma unroll
                 for (int i = 0; i < ac::PER_THREAD; ++i) {
-                    int const piece = int(threadIdx.x) + i * cfg::THREADS;
-                    int const row   = piece / ac::ROW_PIECES;          // u * TN + t'
-                    int const sub   = piece - row * ac::ROW_PIECES;
-                    int const u     = row / TN;
-                    int const f     = (row - u * TN) + (eh * ac::CH + u) * TN;
-                    size_t const eo = size_t(sub) * (16 / sizeof(C));  // element offset inside the group of bins
-                    frame_cp_async16(dst_h + size_t(piece) * 16, filt - gi + at(f, q, io.parts2) + eo);
-                    if (want_x) { frame_cp_async16(dst_x + size_t(piece) * 16, ring - gi + at(f, sl, io.ring2) + eo); }
+                    frame_cp_async16(dst_h + i * dst_step, hp + i * h_step);
+                    if (want_x) { frame_cp_async16(dst_h + ac::OPERAND + i * dst_step, xp + i * x_step); }
                 }
             }
             frame_cp_async_commit();
@@ -418,10 +434,10 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
     C v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
-        int const n    = t + e * TN;
-        int const half = n < g.frame ? (io.new_half ^ 1) : io.new_half;
-        int const row  = half * g.frame + (n & (g.frame - 1));
-        C x            = src[size_t(row) << logw];
+        // n = t + e * TN; the first E/2 points are the previous frame (n < T), the rest the current one
+        int const half = e < E / 2 ? (io.new_half ^ 1) : io.new_half;
+        int const row  = half * g.frame + t + (e % (E / 2)) * TN;
+        C x            = src[size_t(row) << g.logb];
         if constexpr (NYQ) { x = mk<T>(x.y, T(0)); }
         else if (k == 0) { x.y = T(0); }
         v[e] = x;
@@ -444,7 +460,7 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
             for (int eh = 0; eh < ac::NH; ++eh) {
                 int const c = q * ac::NH + eh;
                 frame_cp_async_wait<2>();  // chunks are committed in order, one group each: chunk c has landed
-                __syncthreads();
+                __syncwarp();              // ... for every lane of this warp, which copied all the rows the warp reads
                 C const* const sh = reinterpret_cast<C const*>(stage_ptr(c));
                 C const* const sx = reinterpret_cast<C const*>(stage_ptr(c) + ac::OPERAND);
 #pragma unroll
@@ -457,11 +473,12 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
                     a[e].y      = ::fma(x.x, h.y, a[e].y);
                     a[e].y      = ::fma(x.y, h.x, a[e].y);
                 }
-                __syncthreads();  // every thread is done with this stage
+                __syncwarp();  // every lane is done with this warp's rows of the stage
                 issue(c + 3);
             }
         }
         frame_cp_async_wait<0>();
+        __syncthreads();  // stage 2 is the exchange tile the inverse transform is about to write
 #pragma unroll
         for (int e = 0; e < E; ++e) { v[e] = a[e]; }
     } else {

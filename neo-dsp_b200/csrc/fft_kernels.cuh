@@ -28,9 +28,10 @@ struct fft_cfg
     static constexpr int THREADS = TN * G;
     static constexpr int TILE    = F::TILE;
     static constexpr size_t SMEM = size_t(G) * TILE * sizeof(cx<T>);
-    // measured: forcing <= 64 registers (1024 resident threads per SM) spills in c2r and loses 5-13 points of roofline,
-    // so the compiler's own allocation (60-73 registers) stands
-    static constexpr int MIN_CTAS = 1;
+    // measured: forcing <= 64 registers (1024 resident threads per SM) spills in c2r and loses 5-13 points of roofline.
+    // 128 registers (512 resident threads) is the cap: the plain kernels stay below it on their own (ncu: 108 at 2^10 points),
+    // the convolver IO policies would otherwise grow to 139 and lose two of the eight resident CTAs.
+    static constexpr int MIN_CTAS = THREADS <= 512 ? 512 / THREADS : 1;
 };
 
 // ---- twiddle tables (host, computed in double, rounded once) --------------------------------------------------------

@@ -93,6 +93,31 @@ def main():
             got2[:, pos * B : (pos + T) * B] = y.view(-1, T * B).cpu().numpy()
         err2 = np.linalg.norm(got2 - want[mine]) / np.linalg.norm(want[mine])
         assert err2 < 1e-5, err2
+        conv.close()
+
+        # frame mode (calls of exactly TF blocks, second overlap-save level along block time): a shard starts on a frame boundary
+        # of the partition axis; the partial LEVEL-1 spectra are reduced exactly as above
+        P2, TF = 8, 2
+        ir2 = orc.normalize_impulse(np.stack([orc.noise(B * P2 - 9, 21 + c, np.float32) for c in range(C)]))
+        H2 = orc.uniform_partition(ir2, B)
+        want3 = orc.convolve_blocks(0, H2, sig)
+        (lo2, hi2), _ = shard_ranges(P2, C, world, rank)
+        assert lo2 % TF == 0
+        conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, partition_range=(lo2, hi2), frame_blocks=TF)
+        conv.set_stream(torch.cuda.current_stream())
+        conv.filter(H2)
+        got3 = np.zeros((c1 - c0, B * NB), dtype=np.float32)
+        shard = torch.empty((c1 - c0, TF, 2 * B), device="cuda", dtype=torch.float32)
+        for pos in range(0, NB, TF):
+            x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + TF) * B])).cuda()
+            y = torch.empty((c1 - c0, TF * B), device="cuda", dtype=torch.float32)
+            conv.forward(x)
+            dist.reduce_scatter_tensor(shard, conv.spectra_tensor(TF))
+            conv.inverse(shard, y, c0, c1 - c0, TF)
+            torch.cuda.synchronize()
+            got3[:, pos * B : (pos + TF) * B] = y.cpu().numpy()
+        err3 = np.linalg.norm(got3 - want3[c0:c1]) / np.linalg.norm(want3[c0:c1])
+        assert err3 < 1e-5, err3
     dist.barrier()
     if rank == 0:
         print(f"dist_worker ok backend={args.backend} world={world} err={err:.2e}")

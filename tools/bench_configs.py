@@ -82,6 +82,16 @@ for T in (1, 16):
     res[f"T{T}"] = {"us_per_block": ms * 1e3 / T, "realtime_x_48k": (B * T / 48000.0) / (ms * 1e-3),
                     "channel_msamples_s": C * B * T / ms / 1e3}
     conv.close()
+for T in (64,):  # frame mode: second overlap-save level along block time
+    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, frame_blocks=T)
+    conv.set_stream(stream)
+    conv.impulse(ir, B)
+    xin = torch.rand((C, T * B), device="cuda") * 2 - 1
+    yout = torch.empty_like(xin)
+    ms = gpu_time(lambda: conv(xin, out=yout), reps=100, warm=10)
+    res[f"frame{T}"] = {"us_per_block": ms * 1e3 / T, "realtime_x_48k": (B * T / 48000.0) / (ms * 1e-3),
+                        "channel_msamples_s": C * B * T / ms / 1e3}
+    conv.close()
 res["bytes_per_channel_block_T1"] = 8 * B + 8 * (B + 1) + 16 * (B + 1) * (L // B)
 res["note"] = "2 channels x 2.1 MB of state: L2-resident, bound by launch latency of three small kernels, not by HBM"
 out["C3"] = res
@@ -108,6 +118,25 @@ for T in (1, 16):
         "mac_ms_per_call": mac_ms / 35,
         "mac_filter_stream_gbs": filt_bytes / (mac_ms / 35) / 1e6,
         "mac_fp32_tflops": 8.0 * K * P * O * I * T / (mac_ms / 35) / 1e9,
+    }
+    conv.close()
+for T in (32, 64):  # frame mode: the contraction becomes Q = P/T streamed rows of 2T*B bins per (output, input) pair
+    conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.MATRIX, frame_blocks=T)
+    conv.set_stream(stream)
+    conv.impulse(ir, B)
+    xin = torch.rand((I, T * B), device="cuda") * 2 - 1
+    yout = torch.empty((O, T * B), device="cuda")
+    conv.profile(True)
+    ms = gpu_time(lambda: conv(xin, out=yout), reps=30, warm=5)
+    r2c_ms, mac_ms, c2r_ms, ff_ms, fi_ms, launches = conv.profile_read(frame_phases=True)
+    filt2_bytes = 8 * K * 2 * T * ((P + T - 1) // T) * O * I
+    res[f"frame{T}"] = {
+        "ms_per_block_step": ms / T,
+        "realtime_x_48k": (B * T / 48000.0) / (ms * 1e-3),
+        "mac_ms_per_call": mac_ms / 35,
+        "mac_filter_stream_gbs": filt2_bytes / (mac_ms / 35) / 1e6,
+        "frame_transform_ms_per_call": (ff_ms + fi_ms) / 35,
+        "device_gb": conv.device_bytes() / 1e9,
     }
     conv.close()
 res["filter_bytes"] = 8 * K * P * O * I
