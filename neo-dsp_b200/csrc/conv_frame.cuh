@@ -428,19 +428,21 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
             frame_cp_async_commit();
         }
     };
-    issue(0);
-    issue(1);
-
+    // the frame's own spectra first (they head the dependency chain), then the first two MAC chunks behind them in the queue
     C v[E];
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         // n = t + e * TN; the first E/2 points are the previous frame (n < T), the rest the current one
         int const half = e < E / 2 ? (io.new_half ^ 1) : io.new_half;
         int const row  = half * g.frame + t + (e % (E / 2)) * TN;
-        C x            = src[size_t(row) << g.logb];
-        if constexpr (NYQ) { x = mk<T>(x.y, T(0)); }
-        else if (k == 0) { x.y = T(0); }
-        v[e] = x;
+        v[e]           = src[size_t(row) << g.logb];
+    }
+    issue(0);
+    issue(1);
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+        if constexpr (NYQ) { v[e] = mk<T>(v[e].y, T(0)); }
+        else if (k == 0) { v[e].y = T(0); }
     }
     cta_fft<T, LOGL, -1, LOGE_F>::run(v, sm, tw, t);
     issue(2);  // the exchange tile is free until the inverse transform
