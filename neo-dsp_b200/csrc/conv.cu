@@ -327,10 +327,17 @@ struct conv_engine
         NEO_TRY(mark_begin(0, stream));
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
-                conv_r2c_io<T, LOGM> io{in, in_stride, prev[prev_flip].template as<T>(), prev[prev_flip ^ 1].template as<T>(),
-                                        fdl.template as<cx<T>>(), ring, frame > 0 ? x1_half * frame : int(write_pos), int(blocks),
-                                        cfg.kind == NEO_B200_UPOLA ? 1 : 0, frame > 0 ? logb : logw, frame > 0 ? 1 : nt, chan0};
-                status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
+                if (frame > 0) {  // plain rows [2T][B] per channel, this call's half starts at row x1_half * T
+                    conv_r2c_io<T, LOGM, true> io{in, in_stride, prev[prev_flip].template as<T>(), prev[prev_flip ^ 1].template as<T>(),
+                                                  fdl.template as<cx<T>>(), ring, x1_half * frame, int(blocks),
+                                                  cfg.kind == NEO_B200_UPOLA ? 1 : 0, logb, 1, chan0};
+                    status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
+                } else {
+                    conv_r2c_io<T, LOGM> io{in, in_stride, prev[prev_flip].template as<T>(), prev[prev_flip ^ 1].template as<T>(),
+                                            fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
+                                            cfg.kind == NEO_B200_UPOLA ? 1 : 0, logw, nt, chan0};
+                    status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
+                }
             }
         });
         if (status != NEO_B200_OK) { return status == NEO_B200_ERR_UNSUPPORTED ? fail(status, "block size %d not supported", m) : status; }
@@ -540,8 +547,8 @@ struct conv_engine
     }
 
     // c2r + scale + overlap handling of spectra [count][blocks][B] (S partial planes `plane` apart) into out [count][out_stride]
-    int inverse(cx<T> const* spectra, size_t plane, int nsplits, T* out, size_t out_stride, size_t first, size_t count, size_t blocks,
-                cudaStream_t stream)
+    int inverse(cx<T> const* spectra, size_t /*plane*/, int /*nsplits*/, T* out, size_t out_stride, size_t first, size_t count,
+                size_t blocks, cudaStream_t stream)
     {
         bool const ola = cfg.kind == NEO_B200_UPOLA;
         T* const dst   = ola ? ola_y.template as<T>() : out;
@@ -549,7 +556,7 @@ struct conv_engine
         NEO_TRY(mark_begin(2, stream));
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
-                conv_c2r_io<T, LOGM> io{spectra, plane, nsplits, int(blocks), dst, out_stride, T(1) / T(2 * m), ola ? 1 : 0};
+                conv_c2r_io<T, LOGM> io{spectra, int(blocks), dst, out_stride, T(1) / T(2 * m), ola ? 1 : 0};
                 status = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
             }
         });

@@ -542,7 +542,8 @@ __global__ void __launch_bounds__(128)
 }
 
 // ---- forward side: window assembly + r2c + FDL insert ---------------------------------------------------------------------------
-template<typename T, int LOGM>
+// ROWS: the destination rows are plain [slot][B] rows (frame mode's two-frame buffer) instead of 1 KB tiles
+template<typename T, int LOGM, bool ROWS = false>
 struct conv_r2c_io
 {
     using C = cx<T>;
@@ -592,7 +593,8 @@ struct conv_r2c_io
     }
     __device__ __forceinline__ void store(row_state const& r, int k, C x) const
     {
-        r.dst[((size_t(k >> logw) * ring) << logw) + (k & ((1 << logw) - 1))] = x;
+        if constexpr (ROWS) { r.dst[k] = x; }
+        else { r.dst[((size_t(k >> logw) * ring) << logw) + (k & ((1 << logw) - 1))] = x; }
     }
     __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const { r.dst[0] = mk<T>(dc, nyq); }
 };
@@ -602,9 +604,8 @@ template<typename T, int LOGM>
 struct conv_c2r_io
 {
     using C = cx<T>;
-    C const* acc;       // [splits][count][blocks][B], row 0 = first output channel handled
-    size_t acc_plane;
-    int splits, blocks;
+    C const* acc;       // [count][blocks][B], row 0 = first output channel handled (partial planes are folded by the MAC kernel)
+    int blocks;
     T* out;             // overlap-save: [count][out_stride] reals;  overlap-add: scratch [count][blocks][2B]
     size_t out_stride;
     T scale;            // 1 / (2B)  (overlap_save.hpp:108)
@@ -626,9 +627,7 @@ struct conv_c2r_io
     }
     __device__ __forceinline__ C load(row_state const& r, int k) const
     {
-        C s = r.src[k];
-        for (int p = 1; p < splits; ++p) { s = cadd(s, r.src[size_t(p) * acc_plane + k]); }
-        return s;
+        return r.src[k];  // plain loads: the kernel batches all of a thread's points before the first use
     }
     __device__ __forceinline__ C load_edges(row_state const& r) const { return load(r, 0); }
     __device__ __forceinline__ void store(row_state const& r, int j, C z) const
