@@ -14,6 +14,7 @@
 
 #include <complex>
 #include <cstddef>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <type_traits>
@@ -400,5 +401,73 @@ template<typename Complex>
 using upols_convolver = uniform_partitioned_convolver<Complex, NEO_B200_UPOLS>;
 template<typename Complex>
 using upola_convolver = uniform_partitioned_convolver<Complex, NEO_B200_UPOLA>;
+
+/// Drop-in for neo::convolution::overlap_add_convolver / upola_convolver_v2 (convolution/overlap_add_convolver.hpp:21-136,
+/// dense_convolver.hpp:28) for the call shape its test and benchmark use (uniform_partitioned_convolver_test.cpp:40,
+/// benchmark/convolution.cpp:58): `operator()(inout)` takes any WHOLE number of blocks (>= 1) and runs the block loop of
+/// overlap_add_convolver.hpp:85 on the device, up to 32 blocks per launch. A call that ends inside a block -- where the
+/// reference re-transforms the partially filled window -- is rejected with std::invalid_argument.
+template<typename Complex>
+struct overlap_add_convolver
+{
+    using value_type = Complex;
+    using real_type  = detail::real_of<Complex>;
+    using size_type  = std::size_t;
+
+    overlap_add_convolver() = default;
+
+    template<typename Mat>
+    auto filter(Mat h) -> void
+    {
+        static_assert(std::is_same_v<detail::element_of<Mat>, Complex>);
+        auto const parts = static_cast<size_type>(h.extent(0));
+        auto const bins  = static_cast<size_type>(h.extent(1));
+        _copy.resize(parts * bins);
+        for (size_type p = 0; p < parts; ++p) {
+            for (size_type k = 0; k < bins; ++k) {
+                auto const v        = h(p, k);
+                _copy[p * bins + k] = {v.real(), v.imag()};
+            }
+        }
+        _block = bins - 1;
+        _bank.filter(_copy.data(), 1, 1, parts, bins, NEO_B200_DIAGONAL, max_blocks_per_launch);
+    }
+
+    template<typename Vec>
+    auto operator()(Vec inout) -> void
+    {
+        static_assert(std::is_same_v<detail::element_of<Vec>, real_type>);
+        auto const n = static_cast<size_type>(inout.extent(0));
+        if (_block == 0 || n < _block || n % _block != 0) {
+            throw std::invalid_argument{"neo::b200::overlap_add_convolver: call length must be a whole number of blocks"};
+        }
+        _tmp.resize(n);
+        for (size_type i = 0; i < n; ++i) { _tmp[i] = inout[i]; }
+        for (size_type done = 0; done < n / _block;) {
+            auto const blocks = std::min(max_blocks_per_launch, n / _block - done);
+            _bank.process(_tmp.data() + done * _block, _tmp.data() + done * _block, blocks);
+            done += blocks;
+        }
+        for (size_type i = 0; i < n; ++i) { inout[i] = _tmp[i]; }
+    }
+
+private:
+    static constexpr size_type max_blocks_per_launch = 32;
+    convolver_bank<real_type, NEO_B200_UPOLA> _bank;
+    std::vector<std::complex<real_type>> _copy;
+    std::vector<real_type> _tmp;
+    size_type _block{0};
+};
+
+template<typename Complex>
+using upola_convolver_v2 = overlap_add_convolver<Complex>;
+
+/// neo::convolution::split_upols_convolver / split_upola_convolver (dense_convolver.hpp:32-41) differ from the dense aliases only
+/// in how the reference lays its FDL and filter out in host memory (split re/im planes for its SIMD loops); interface and results
+/// are the same (golden vectors: tests/test_conv_gpu.py), and the device layout is this library's own either way.
+template<typename Complex>
+using split_upols_convolver = upols_convolver<Complex>;
+template<typename Complex>
+using split_upola_convolver = upola_convolver<Complex>;
 
 }  // namespace neo::b200

@@ -28,11 +28,34 @@ struct fft_cfg
     static constexpr int THREADS = TN * G;
     static constexpr int TILE    = F::TILE;
     static constexpr size_t SMEM = size_t(G) * TILE * sizeof(cx<T>);
-    // measured: forcing <= 64 registers (1024 resident threads per SM) spills in c2r and loses 5-13 points of roofline.
-    // 128 registers (512 resident threads) is the cap: the plain kernels stay below it on their own (ncu: 108 at 2^10 points),
-    // the convolver IO policies would otherwise grow to 139 and lose two of the eight resident CTAs.
-    static constexpr int MIN_CTAS = THREADS <= 512 ? 512 / THREADS : 1;
 };
+
+// Registers per thread the single-CTA kernels are held to (-> resident CTAs per SM). These kernels are issue/latency bound at
+// 4 warps per scheduler, so occupancy buys more than registers do. Measured on B200, float, fraction of HBM peak at the
+// compiler's own 108-120 registers vs capped (no spills at 72 and up; 64 spills and loses 5-13 points):
+//   r2c  N=1024 .84 -> .91   2048 .84 -> .92   4096 .79 -> .91 (72) / .88 (85)   8192 .68 -> .75
+//   c2r  N=1024 .80 -> .85   2048 .86 -> .82 (kept at 128)   4096 .77 -> .77   8192 .62 -> .69
+enum fft_kind : int
+{
+    k_c2c = 0,
+    k_r2c = 1,
+    k_c2r = 2,
+};
+
+template<typename T>
+constexpr int fft_regcap(int kind, int logm)
+{
+    if (sizeof(T) != 4) { return 128; }
+    if (kind == k_c2r) { return logm == 10 ? 128 : 85; }
+    return logm == 11 ? 72 : 85;
+}
+
+template<typename T, int LOGM, int KIND>
+constexpr int fft_min_ctas()
+{
+    int const n = (65536 / fft_regcap<T>(KIND, LOGM)) / fft_cfg<T, LOGM>::THREADS;
+    return n > 0 ? n : 1;
+}
 
 // ---- twiddle tables (host, computed in double, rounded once) --------------------------------------------------------
 template<typename T>
@@ -102,7 +125,7 @@ struct c2c_split_io
 };
 
 template<typename T, int LOGM, int DIR, class IO>
-__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::MIN_CTAS)
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOGM, k_c2c>())
     c2c_kernel(IO io, cx<T> const* __restrict__ tw, size_t batch)
 {
     using cfg = fft_cfg<T, LOGM>;
@@ -130,7 +153,7 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::M
 
 // ---- r2c: IO policy provides load(b, j) -> z[j] and the spectrum stores ------------------------------------------------
 template<typename T, int LOGM, class IO>
-__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::MIN_CTAS)
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOGM, k_r2c>())
     r2c_kernel(IO io, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ rtw, size_t batch)
 {
     using cfg = fft_cfg<T, LOGM>;
@@ -175,8 +198,11 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::M
 }
 
 // ---- c2r: IO policy provides the spectrum loads and store(b, j, z[j]) -----------------------------------------------------
+#ifndef NEO_B200_C2R_SMEM_MATE_MIN
+#define NEO_B200_C2R_SMEM_MATE_MIN 11  // 2^11 complex points and up fetch the Hermitian partner through shared memory (measured: N=4096 c2r .76 -> .82)
+#endif
 template<typename T, int LOGM, class IO>
-__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::MIN_CTAS)
+__global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOGM, k_c2r>())
     c2r_kernel(IO io, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ rtw, size_t batch)
 {
     using cfg = fft_cfg<T, LOGM>;
@@ -190,30 +216,51 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_cfg<T, LOGM>::M
     size_t const b  = size_t(blockIdx.x) * cfg::G + g;
     bool const live = b < batch;
 
-    // Hermitian pre-pass straight from global memory: X[k] and its partner X[M-k] are both loaded by this thread (the partner
-    // line is the one a sibling thread loads as its own X[k], so the second touch is an L1 hit); no shared-memory round trip
-    // and all 2E loads are in flight at once
     C v[cfg::E];
     typename IO::row_state row = io.open(live ? b : 0);
-    C own[cfg::E], mate[cfg::E];
+    if constexpr (LOGM >= NEO_B200_C2R_SMEM_MATE_MIN) {
+        // long rows: the Hermitian partner X[M-k] comes through the exchange tile (one global load per point; a 64 KB row does
+        // not survive in L1 next to the tile, so a second global touch would be an L2 round trip)
+        C own[cfg::E];
 #pragma unroll
-    for (int e = 0; e < cfg::E; ++e) {
-        int const k = t + e * cfg::TN;
-        if (!live) {
-            own[e] = mate[e] = mk<T>(0, 0);
-        } else if (k == 0) {
-            own[e]  = io.load_edges(row);  // (Re X[0], Re X[M])
-            mate[e] = own[e];
-        } else {
-            own[e]  = io.load(row, k);
-            mate[e] = io.load(row, cfg::M - k);
+        for (int e = 0; e < cfg::E; ++e) {
+            int const k = t + e * cfg::TN;
+            own[e]      = !live ? mk<T>(0, 0) : k == 0 ? io.load_edges(row) : io.load(row, k);
         }
-    }
 #pragma unroll
-    for (int e = 0; e < cfg::E; ++e) {
-        int const k = t + e * cfg::TN;
-        if (k == 0) { v[e] = mk<T>(own[e].x + own[e].y, own[e].x - own[e].y); }
-        else { v[e] = c2r_pre(own[e], mate[e], __ldg(rtw + k)); }
+        for (int e = 0; e < cfg::E; ++e) { sm[padded<T>(t + e * cfg::TN)] = own[e]; }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) {
+            int const k = t + e * cfg::TN;
+            if (k == 0) { v[e] = mk<T>(own[e].x + own[e].y, own[e].x - own[e].y); }
+            else { v[e] = c2r_pre(own[e], sm[padded<T>(cfg::M - k)], __ldg(rtw + k)); }
+        }
+        __syncthreads();
+    } else {
+        // Hermitian pre-pass straight from global memory: X[k] and its partner X[M-k] are both loaded by this thread (the
+        // partner line is the one a sibling thread loads as its own X[k], so the second touch is an L1 hit); no shared-memory
+        // round trip and all 2E loads are in flight at once
+        C own[cfg::E], mate[cfg::E];
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) {
+            int const k = t + e * cfg::TN;
+            if (!live) {
+                own[e] = mate[e] = mk<T>(0, 0);
+            } else if (k == 0) {
+                own[e]  = io.load_edges(row);  // (Re X[0], Re X[M])
+                mate[e] = own[e];
+            } else {
+                own[e]  = io.load(row, k);
+                mate[e] = io.load(row, cfg::M - k);
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < cfg::E; ++e) {
+            int const k = t + e * cfg::TN;
+            if (k == 0) { v[e] = mk<T>(own[e].x + own[e].y, own[e].x - own[e].y); }
+            else { v[e] = c2r_pre(own[e], mate[e], __ldg(rtw + k)); }
+        }
     }
 
     F::run(v, sm, tw, t);

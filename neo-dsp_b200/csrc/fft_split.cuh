@@ -26,7 +26,7 @@ struct split_cfg
 // in: [batch][4*M2] reals, out: [batch][2*M2 + 1] complex. tw: stage twiddles of the M2-point FFT; w_m[k] = exp(-2 pi i k / M)
 // (= the M2-plan's split table); w_n1 = exp(-2 pi i / 2M) (one step of the real transform's twiddle)
 template<typename T, int LOGM2>
-__global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_cfg<T, LOGM2>::MIN_CTAS)
+__global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_min_ctas<T, LOGM2, k_r2c>())
     r2c_split2_kernel(T const* __restrict__ in, cx<T>* __restrict__ out, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ w_m,
                       cx<T> w_n1)
 {
@@ -74,7 +74,7 @@ __global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_cfg<T, LOGM2
 // in: [batch][row_len] complex (first 2*M2+1 used), out: [batch][4*M2] reals, unnormalised.
 // w_n[k] = exp(-2 pi i k / 2M) for k < M2 (first half of the split table one size up)
 template<typename T, int LOGM2>
-__global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_cfg<T, LOGM2>::MIN_CTAS)
+__global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_min_ctas<T, LOGM2, k_c2r>())
     c2r_split2_kernel(cx<T> const* __restrict__ in, size_t row_len, T* __restrict__ out, cx<T> const* __restrict__ tw,
                       cx<T> const* __restrict__ w_m, cx<T> const* __restrict__ w_n)
 {
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_cfg<T, LOGM2
 // while loading (every CTA reads the whole input, M1-1 of those reads come from L2) and its M2-point FFT gives X[r + M1*k2].
 // w_big[n] = exp(-2 pi i n / M), n < M2.
 template<typename T, int LOGM2, int M1, int DIR>
-__global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_cfg<T, LOGM2>::MIN_CTAS)
+__global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_min_ctas<T, LOGM2, k_c2c>())
     c2c_split_kernel(cx<T> const* __restrict__ in, cx<T>* __restrict__ out, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ w_big)
 {
     using cfg = split_cfg<T, LOGM2>;

@@ -14,6 +14,7 @@
 #include <complex>
 #include <cstdio>
 #include <cstdlib>
+#include <stdexcept>
 #include <vector>
 
 namespace stdex = cuda::std;
@@ -200,6 +201,38 @@ static auto test_convolver() -> void
     }
 }
 
+// upola_convolver_v2 (overlap_add_convolver.hpp:21-136): calls of several whole blocks, uneven split, against the oracle's upola
+static auto test_overlap_add_convolver() -> void
+{
+    using Complex = std::complex<float>;
+    std::size_t const block = 64, taps = 700, nblocks = 40;
+    auto ir    = noise<float>(taps, 5);
+    auto parts = neo_b200_num_partitions(taps, block);
+    auto h     = std::vector<Complex>(parts * (block + 1));
+    neo::b200::uniform_partition(ir.data(), 1, taps, block, h.data());
+    auto conv = neo::b200::upola_convolver_v2<Complex>{};
+    conv.filter(mat<Complex const>{h.data(), parts, block + 1});
+    auto sig = noise<float>(block * nblocks, 17);
+    auto got = sig, want = sig;
+    std::size_t pos = 0;
+    for (std::size_t blocks : {1U, 3U, 35U, 1U}) {  // 35 > the 32 blocks one launch takes
+        conv(vec<float>{got.data() + pos * block, blocks * block});
+        pos += blocks;
+    }
+    auto* o = oracle_conv_create_f32(1);
+    oracle_conv_filter_f32(o, reinterpret_cast<float const*>(h.data()), parts, block + 1);
+    for (std::size_t b = 0; b < nblocks; ++b) { oracle_conv_process_f32(o, want.data() + b * block, block); }
+    oracle_conv_destroy_f32(o);
+    REQUIRE(rel_l2(got, want) <= 1e-5);
+    bool threw = false;
+    try {
+        conv(vec<float>{got.data(), block + 7});
+    } catch (std::invalid_argument const&) {
+        threw = true;
+    }
+    REQUIRE(threw);
+}
+
 int main()
 {
     if (neo_b200_device_count() < 1) {
@@ -214,6 +247,9 @@ int main()
     test_convolver<float, neo::b200::upola_convolver, 1>();
     test_convolver<double, neo::b200::upols_convolver, 0>();
     test_convolver<double, neo::b200::upola_convolver, 1>();
+    test_convolver<float, neo::b200::split_upols_convolver, 0>();
+    test_convolver<float, neo::b200::split_upola_convolver, 1>();
+    test_overlap_add_convolver();
     std::printf(failures == 0 ? "facade_test: all passed\n" : "facade_test: %d FAILED\n", failures);
     return failures == 0 ? 0 : 1;
 }

@@ -55,6 +55,15 @@ auto instantiate_convolver() -> void
     auto ola = neo::b200::upola_convolver<Complex>{};
     ola.filter(h.to_mdspan());
     ola(block.to_mdspan());
+    auto ola2 = neo::b200::upola_convolver_v2<Complex>{};  // overlap_add_convolver.hpp:32-33
+    ola2.filter(h.to_mdspan());
+    ola2(block.to_mdspan());
+    auto split = neo::b200::split_upols_convolver<Complex>{};  // dense_convolver.hpp:32-41
+    split.filter(h.to_mdspan());
+    split(block.to_mdspan());
+    auto split_ola = neo::b200::split_upola_convolver<Complex>{};
+    split_ola.filter(h.to_mdspan());
+    split_ola(block.to_mdspan());
 }
 
 auto instantiate_all() -> void
