@@ -366,22 +366,21 @@ def run_ours(args):
     ys_shard = torch.empty((groups, gsh, T * BLOCK), device="cuda", dtype=torch.float32) if world > 1 else None
 
     def sharded_step(x):
-        spectra = conv.spectra_tensor(T)
         works = []
         for gi in range(groups):
             conv.forward_range(x, gi * gch, gch, gi == groups - 1)
+            spectra = conv.spectra_tensor(T)  # the buffer of this call (the handle alternates between two)
             works.append(dist.reduce_scatter_tensor(spectra_shard[gi], spectra[gi * gch : (gi + 1) * gch], async_op=True))
         for gi in range(groups):
             works[gi].wait()
             conv.inverse(spectra_shard[gi], ys_shard[gi], gi * gch + rank * gsh, gsh, T)
 
     # software pipeline across steps (throughput mode): the reduce-scatter of step i runs on NCCL's stream while step i+1's
-    # r2c + MAC run; step i's c2r follows one step later. The partial spectra are copied out of the handle first (134 MB D2D)
-    # so the next forward may overwrite them. drain() finishes the last step inside the timed region.
+    # r2c + MAC run; step i's c2r follows one step later (the handle double-buffers its partial spectra for exactly this).
+    # drain() finishes the last step inside the timed region.
     pipelined = world > 1 and groups == 1 and not args.no_pipeline
     pending = []
     if pipelined:
-        stage = [torch.empty((CHANNELS, T, 2 * BLOCK), device="cuda", dtype=torch.float32) for _ in range(2)]
         shard2 = [torch.empty((shard, T, 2 * BLOCK), device="cuda", dtype=torch.float32) for _ in range(2)]
 
     def finish(slot, work):
@@ -391,8 +390,8 @@ def run_ours(args):
     def pipelined_step(i, x):
         slot = i % 2
         conv.forward(x)
-        stage[slot].copy_(conv.spectra_tensor(T))
-        work = dist.reduce_scatter_tensor(shard2[slot], stage[slot], async_op=True)
+        # a sharded handle alternates between two partial-spectra buffers: NCCL reads this one while the next forward fills the other
+        work = dist.reduce_scatter_tensor(shard2[slot], conv.spectra_tensor(T), async_op=True)
         if pending:
             finish(*pending.pop())
         pending.append((slot, work))
@@ -501,7 +500,7 @@ def run_ours(args):
         conv.close()
         del xs, ys
         if pipelined:
-            del stage, shard2
+            del shard2
         torch.cuda.empty_cache()
         alt = measure_channel_sharded(args, torch, dist, pkg, rank, world, local, max(5, min(args.steps, 30)))
         alt["partition_sharded_device_bytes_per_rank"] = conv_bytes

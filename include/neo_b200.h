@@ -209,6 +209,9 @@ NEO_B200_API int neo_b200_conv_forward(neo_b200_conv* conv, void const* in, size
  * Every channel must be covered exactly once per call; pass final != 0 with the last range (the ring position then advances). */
 NEO_B200_API int neo_b200_conv_forward_range(
     neo_b200_conv* conv, void const* in, size_t blocks, size_t first, size_t count, int final);
+/* device pointer of the partial spectra of the most recent forward / forward_range call (the call in progress, if its final
+ * range is still to come). A partition-sharded handle alternates between two buffers: the pointer stays valid (not overwritten)
+ * until the second-next call, so the reduction of call i may overlap call i+1; ask again AFTER the (first) forward of every call. */
 NEO_B200_API int neo_b200_conv_spectra(neo_b200_conv* conv, void** device_ptr, size_t* bytes_per_output_block);
 NEO_B200_API int neo_b200_conv_inverse(
     neo_b200_conv* conv, void const* spectra_device, void* out, size_t first, size_t count, size_t blocks, int memspace);

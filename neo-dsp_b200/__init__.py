@@ -455,10 +455,12 @@ class Convolver:
         """torch view [outputs][blocks][2B] (float32 pairs) of the partial spectra produced by forward()."""
         import torch
 
-        cached = getattr(self, "_spectra_view", None)
-        if cached is not None and cached[0] == blocks:
-            return cached[1]
-        ptr, _ = self.spectra_ptr()
+        ptr, _ = self.spectra_ptr()  # a partition-sharded handle alternates between two buffers: ask after every forward
+        views = getattr(self, "_spectra_view", None)
+        if not isinstance(views, dict):
+            views = self._spectra_view = {}
+        if (ptr, blocks) in views:
+            return views[(ptr, blocks)]
         n = int(self.cfg.outputs) * blocks * int(self.cfg.block) * 2
         dt = np.float32 if self.real == "float32" else np.float64
 
@@ -466,7 +468,7 @@ class Convolver:
             __cuda_array_interface__ = {"shape": (n,), "typestr": np.dtype(dt).str, "data": (ptr, False), "version": 3}
 
         view = torch.as_tensor(_Raw(), device=f"cuda:{torch.cuda.current_device()}").view(int(self.cfg.outputs), blocks, -1)
-        self._spectra_view = (blocks, view)
+        views[(ptr, blocks)] = view
         return view
 
     def inverse(self, spectra, out, first: int, count: int, blocks: int) -> None:

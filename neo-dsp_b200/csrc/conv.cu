@@ -65,7 +65,13 @@ struct conv_engine
     int tail_flip{0};
 
     fft_tables<T> tables;
-    device_buffer filter, fdl, prev[2], tail[2], acc, ola_y, stage_in, stage_out, stage_filter, tickets;
+    device_buffer filter, fdl, prev[2], tail[2], acc, acc_alt, ola_y, stage_in, stage_out, stage_filter, tickets;
+    // partition-sharded handles alternate between two partial-spectra buffers, so the reduction of call i (NCCL reads the buffer
+    // neo_b200_conv_spectra returned) may still be running while call i+1 writes the other one
+    int acc_cur{0}, acc_last{0};
+    bool in_call{false};  // a forward_range call has started and its final range has not been seen yet
+    cx<T>* acc_w() const { return (acc_cur != 0 ? acc_alt : acc).template as<cx<T>>(); }
+    void* acc_r() const { return in_call ? static_cast<void*>(acc_w()) : (acc_last != 0 ? acc_alt : acc).ptr; }
     int prev_flip{0};  // prev[prev_flip] holds the last block of the previous call
 
     // second partition level along block time (conv_frame.cuh). frame == 0: direct form. In frame mode `fdl` is the two-frame
@@ -127,7 +133,7 @@ struct conv_engine
 
     size_t device_bytes() const
     {
-        return filter.bytes + fdl.bytes + prev[0].bytes + prev[1].bytes + tail[0].bytes + tail[1].bytes + acc.bytes + ola_y.bytes + stage_in.bytes
+        return filter.bytes + fdl.bytes + prev[0].bytes + prev[1].bytes + tail[0].bytes + tail[1].bytes + acc.bytes + acc_alt.bytes + ola_y.bytes + stage_in.bytes
              + stage_out.bytes + stage_filter.bytes + fdl2.bytes + filter2.bytes + acc2.bytes + nyq_acc.bytes;
     }
 
@@ -161,6 +167,7 @@ struct conv_engine
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         splits = frame > 0 ? 1 : pick_splits(sms, size_t(m), size_t(parts));
         NEO_TRY(acc.reserve(size_t(splits) * c.outputs * c.max_blocks * m * csz));
+        if (!(c.partition_begin == 0 && c.partition_end == c.partitions)) { NEO_TRY(acc_alt.reserve(acc.bytes)); }
         // one ticket per MAC grid cell (x: at most B/128 column blocks, y: outputs); the last split CTA to finish resets it
         NEO_TRY(tickets.reserve(c.outputs * size_t(std::max(1, m / 128 + 1)) * sizeof(unsigned)));
         NEO_CUDA_TRY(cudaMemsetAsync(tickets.ptr, 0, tickets.bytes, stream));
@@ -353,7 +360,7 @@ struct conv_engine
         NEO_TRY(mark_begin(1, stream));
         NEO_DISPATCH_LOGL(logl, {
             frame_fused_io<T, true> nq{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), filter2.template as<cx<T>>(),
-                                       acc.template as<cx<T>>(), nyq_acc.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2),
+                                       acc_w(), nyq_acc.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2),
                                        parts2, int(cfg.partition_begin / size_t(frame)), T(1) / T(2 * frame), out0};
             status = launch_frame_fused<T, LOGL, true>(nq, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout, stream);
             if (status == NEO_B200_OK) {
@@ -426,7 +433,7 @@ struct conv_engine
         int status = NEO_B200_ERR_UNSUPPORTED;
         NEO_TRY(mark_begin(4, stream));
         NEO_DISPATCH_LOGL(logl, {
-            frame_inv_io<T> io{acc2.template as<cx<T>>(), acc.template as<cx<T>>(), fg, T(1) / T(2 * frame), out0};
+            frame_inv_io<T> io{acc2.template as<cx<T>>(), acc_w(), fg, T(1) / T(2 * frame), out0};
             status = launch_frame_fft<T, LOGL, 1>(io, frame_tables.tw(), nout << logb, stream);
         });
         if (status != NEO_B200_OK) { return status; }
@@ -478,6 +485,11 @@ struct conv_engine
             write_pos = (write_pos + blocks) % size_t(ring);
         }
         prev_flip ^= 1;  // the r2c kernels saved this call's last block into the other half-window buffer
+        in_call = false;
+        if (acc_alt.ptr != nullptr) {
+            acc_last = acc_cur;
+            acc_cur ^= 1;
+        }
     }
 
     int forward(T const* in, size_t in_stride, size_t blocks, cudaStream_t stream)
@@ -492,7 +504,7 @@ struct conv_engine
     {
         auto const* x = fdl.template as<cx<T>>();
         auto const* h = filter.template as<cx<T>>();
-        auto* a       = acc.template as<cx<T>>();
+        auto* a       = acc_w();
         if (tb == 1) { return launch_stream(x, h, a, g, nout, stream); }
         if constexpr (sizeof(T) == 4) {
             if (m >= 128 && tb >= 8) {
@@ -841,6 +853,7 @@ int conv_forward_range_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* 
     size_t const stride  = blocks * e.m;
     NEO_TRY(e.forward_r2c(static_cast<T const*>(in) + first * stride, stride, blocks, first, count, s));
     NEO_TRY(e.forward_mac(blocks, first, count, s));
+    e.in_call = true;
     if (final != 0) { e.advance(blocks); }
     return NEO_B200_OK;
 }
@@ -858,7 +871,7 @@ int neo_b200_conv_forward_range(neo_b200_conv* conv, void const* in, size_t bloc
 int neo_b200_conv_spectra(neo_b200_conv* conv, void** device_ptr, size_t* bytes_per_output_block)
 {
     if (conv == nullptr || device_ptr == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
-    *device_ptr = conv->cfg.dtype == NEO_B200_F32 ? conv->f32.acc.ptr : conv->f64.acc.ptr;
+    *device_ptr = conv->cfg.dtype == NEO_B200_F32 ? conv->f32.acc_r() : conv->f64.acc_r();
     if (bytes_per_output_block != nullptr) { *bytes_per_output_block = conv->cfg.block * 2 * elem_size(conv->cfg.dtype); }
     return NEO_B200_OK;
 }

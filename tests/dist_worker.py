@@ -81,10 +81,10 @@ def main():
         for pos in range(0, NB, T):
             x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + T) * B])).cuda()
             y = torch.empty((groups, gsh, T * B), device="cuda", dtype=torch.float32)
-            spectra = conv.spectra_tensor(T)
             works = []
             for g in range(groups):
                 conv.forward_range(x, g * gch, gch, g == groups - 1)
+                spectra = conv.spectra_tensor(T)  # after the forward: a sharded handle alternates between two buffers
                 works.append(dist.reduce_scatter_tensor(shards[g], spectra[g * gch : (g + 1) * gch], async_op=True))
             for g in range(groups):
                 works[g].wait()
