@@ -46,6 +46,9 @@ template<typename T>
 constexpr int fft_regcap(int kind, int logm)
 {
     if (sizeof(T) != 4) { return 128; }
+#ifdef NEO_B200_C2R_CAP
+    if (kind == k_c2r) { return NEO_B200_C2R_CAP; }
+#endif
     if (kind == k_c2r) { return logm == 10 ? 128 : 85; }
     return logm == 11 ? 72 : 85;
 }

@@ -157,6 +157,19 @@ def test_frame_mode_small_bank_splits_rows_across_ctas(gpu, orc):
     conv.close()
 
 
+def test_frame_mode_three_kernel_form_for_banks(gpu, orc, monkeypatch):
+    # banks normally take the fused kernel; NEO_B200_FRAME_UNFUSED (read when the handle is created) selects the three-kernel form
+    # (frame transform, frame_mac_kernel over several columns per thread, inverse transform) -- same results
+    monkeypatch.setenv("NEO_B200_FRAME_UNFUSED", "1")
+    for block, taps, T, frames in ((128, 128 * 9 - 3, 4, 5), (1024, 1024 * 33 - 5, 32, 3), (64, 64 * 5, 64, 3)):
+        ir, sig = make_case(orc, 3, taps, block, T * frames)
+        H = orc.uniform_partition(ir, block)
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+        conv.filter(H)
+        assert rel_l2(run_bank(conv, sig, block, [T]), orc.convolve_blocks(0, H, sig)) <= 1e-5, (block, T)
+        conv.close()
+
+
 def test_frame_mode_error_contract(gpu, orc):
     H = np.zeros((2, 3, 65), dtype=np.complex64)
     for bad in (3, 1, 1024):
