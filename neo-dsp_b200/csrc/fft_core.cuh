@@ -261,16 +261,73 @@ __host__ __device__ constexpr int fft_twiddle_offset(int logm, int loge, int log
 
 __host__ __device__ constexpr int fft_twiddle_count(int logm, int loge) { return fft_twiddle_offset(logm, loge, logm); }
 
+// ---- the exchange tile behind cta_fft: overloads on the handle type ------------------------------------------------------------
+// Plain pointer: one CTA's padded shared-memory tile.
+template<typename C>
+__device__ __forceinline__ void tile_store(C* sm, int idx, C v)
+{
+    sm[padded<decltype(v.x)>(idx)] = v;
+}
+template<typename C>
+__device__ __forceinline__ C tile_load(C* sm, int idx)
+{
+    return sm[padded<decltype(sm->x)>(idx)];
+}
+template<typename C>
+__device__ __forceinline__ void tile_sync(C*)
+{
+    __syncthreads();
+}
+
+// Two CTAs of a thread-block cluster share one transform: element idx lives in CTA (idx >> LOGC) & 1 (LOGC = log2 threads per
+// CTA), so the Stockham read pattern t + e*TN (TN = 2 * threads per CTA) is always local and only stores cross the cluster
+// (st.shared::cluster). Loads of arbitrary elements (the Hermitian partner) may be remote.
+template<typename T, int LOGC>
+struct dsmem_tile2
+{
+    cx<T>* local;     // this CTA's half, padded
+    unsigned peer;    // shared::cluster address of the other CTA's half
+    unsigned rank;    // %cluster_ctarank
+    static __device__ __forceinline__ int offset(int idx) { return padded<T>(((idx >> (LOGC + 1)) << LOGC) | (idx & ((1 << LOGC) - 1))); }
+};
+template<typename T, int LOGC>
+__device__ __forceinline__ void tile_store(dsmem_tile2<T, LOGC> sm, int idx, cx<T> v)
+{
+    static_assert(sizeof(T) == 4, "float only");
+    int const off = dsmem_tile2<T, LOGC>::offset(idx);
+    if (unsigned((idx >> LOGC) & 1) == sm.rank) {
+        sm.local[off] = v;
+    } else {
+        asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" ::"r"(sm.peer + unsigned(off) * 8U), "f"(v.x), "f"(v.y) : "memory");
+    }
+}
+template<typename T, int LOGC>
+__device__ __forceinline__ cx<T> tile_load(dsmem_tile2<T, LOGC> sm, int idx)
+{
+    int const off = dsmem_tile2<T, LOGC>::offset(idx);
+    if (unsigned((idx >> LOGC) & 1) == sm.rank) { return sm.local[off]; }
+    cx<T> v;
+    asm volatile("ld.shared::cluster.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "r"(sm.peer + unsigned(off) * 8U) : "memory");
+    return v;
+}
+template<typename T, int LOGC>
+__device__ __forceinline__ void tile_sync(dsmem_tile2<T, LOGC>)
+{
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;\n" ::: "memory");
+}
+
 // LOGE_FORCED >= 0 overrides the points-per-thread choice (the cluster kernels want 16 points per thread for short columns)
 // WARP_PRIVATE: the transform's TN threads are exactly one warp and its tile is touched by no other warp, so the exchanges only
 // need __syncwarp() (the cluster kernel's 512-point rows: no CTA-wide stall per stage).
 template<typename T, int LOGM, int DIR, int LOGE_FORCED = -1, bool WARP_PRIVATE = false>
 struct cta_fft
 {
-    static __device__ __forceinline__ void sync()
+    template<typename SM>
+    static __device__ __forceinline__ void sync(SM sm)
     {
         if constexpr (WARP_PRIVATE) { __syncwarp(); }
-        else { __syncthreads(); }
+        else { tile_sync(sm); }
     }
 
     static constexpr int LOGE  = LOGE_FORCED >= 0 ? LOGE_FORCED : pick_loge<T>(LOGM);
@@ -291,8 +348,8 @@ struct cta_fft
         else { w[q] = cmul(w[hi], w[q - hi]); }
     }
 
-    template<int LOGNS, int LOGR>
-    static __device__ __forceinline__ void stage(C (&v)[E], C* sm, C const* __restrict__ tw, int t)
+    template<int LOGNS, int LOGR, typename SM>
+    static __device__ __forceinline__ void stage(C (&v)[E], SM sm, C const* __restrict__ tw, int t)
     {
         constexpr int NS = 1 << LOGNS;
         constexpr int R  = 1 << LOGR;
@@ -322,19 +379,19 @@ struct cta_fft
             } else {
                 int const base = ((j >> LOGNS) << (LOGNS + LOGR)) + k;
 #pragma unroll
-                for (int q = 0; q < R; ++q) { sm[padded<T>(base + (q << LOGNS))] = u[q]; }
+                for (int q = 0; q < R; ++q) { tile_store(sm, base + (q << LOGNS), u[q]); }
             }
         }
         if constexpr (!last) {
-            sync();
+            sync(sm);
 #pragma unroll
-            for (int e = 0; e < E; ++e) { v[e] = sm[padded<T>(t + e * TN)]; }
-            sync();
+            for (int e = 0; e < E; ++e) { v[e] = tile_load(sm, t + e * TN); }
+            sync(sm);
         }
     }
 
-    template<int LOGNS>
-    static __device__ __forceinline__ void full_stages(C (&v)[E], C* sm, C const* __restrict__ tw, int t)
+    template<int LOGNS, typename SM>
+    static __device__ __forceinline__ void full_stages(C (&v)[E], SM sm, C const* __restrict__ tw, int t)
     {
         if constexpr (LOGNS < LOGM) {
             stage<LOGNS, LOGE>(v, sm, tw, t);
@@ -343,7 +400,8 @@ struct cta_fft
     }
 
     // all threads of the CTA must call (barriers inside)
-    static __device__ __forceinline__ void run(C (&v)[E], C* sm, C const* __restrict__ tw, int t)
+    template<typename SM>
+    static __device__ __forceinline__ void run(C (&v)[E], SM sm, C const* __restrict__ tw, int t)
     {
         if constexpr (LOGM > 0) {
             if constexpr (LOGR0 > 0) { stage<0, LOGR0>(v, sm, tw, t); }

@@ -5,6 +5,7 @@
 #include "fft_large.cuh"
 #include "fft_split.cuh"
 #include "fft_cluster.cuh"
+#include "fft_pair.cuh"
 
 #include <cmath>
 #include <cstdlib>
@@ -153,6 +154,7 @@ struct rfft_engine
     bool use_split{false};       // two CTAs per transform (fft_split.cuh)
     bool use_cluster{false};     // float32, N = 2^14..2^16: persistent thread-block-cluster four-step (fft_cluster.cuh)
     rfft_cluster_plan cluster;
+    bool use_pair{false};        // float32, N = 2^16: one transform per CTA pair, exchange tile in distributed shared memory (fft_pair.cuh)
     bool use_big_cta{false};     // float32, M = 2^14: one 1024-thread CTA per transform (139 KB exchange tile)
     bool use_two_pass{false};    // four-CTA split c2c into an L2-resident scratch + Hermitian split pass
     c2c_engine<T> half;          // two-pass path: the half-size complex transform
@@ -171,6 +173,13 @@ struct rfft_engine
         if constexpr (sizeof(T) == 4) {
             // measured: the cluster kernel wins only at N = 2^16 (0.25 of HBM peak against 0.13 for the two-pass path); at
             // 2^14 / 2^15 the two-CTA split transforms are faster (0.5-0.6 / 0.4-0.5 against 0.33 / 0.27)
+            // measured (N = 2^16): the CTA-pair form (exchange tile in distributed shared memory, one HBM pass, no scratch) reaches
+            // only 0.19 / 0.18 of HBM peak against 0.26 / 0.29 for the L2-scratch cluster four-step -- half of every exchange
+            // crosses the SM-to-SM network (~20 B/clk per SM) and each of its 8 exchanges ends in a cluster barrier. Kept as a knob.
+            if (order == 16 && std::getenv("NEO_B200_PAIR") != nullptr) {
+                use_pair = true;
+                return tables.build(logm, true, stream);
+            }
             bool const all = std::getenv("NEO_B200_CLUSTER_ALL") != nullptr;
             if ((order == 16 || (all && order >= 14 && order < 16)) && std::getenv("NEO_B200_NO_CLUSTER") == nullptr) {
                 use_cluster = true;
@@ -248,6 +257,7 @@ struct rfft_engine
     {
         if (order == 0) { return large_rfft<T>::size_one_forward(in, out, batch, stream); }
         if constexpr (sizeof(T) == 4) {
+            if (use_pair) { return launch_r2c_pair<15>(in, out, tables.tw(), tables.rtw(), batch, stream); }
             if (use_cluster) { return cluster.forward(in, out, batch, stream); }
         }
         if constexpr (sizeof(T) == 4) {
@@ -279,6 +289,7 @@ struct rfft_engine
     {
         if (order == 0) { return large_rfft<T>::size_one_backward(in, row_len, out, batch, stream); }
         if constexpr (sizeof(T) == 4) {
+            if (use_pair) { return launch_c2r_pair<15>(in, row_len, out, tables.tw(), tables.rtw(), batch, stream); }
             if (use_cluster) { return cluster.backward(in, row_len, out, batch, stream); }
         }
         if constexpr (sizeof(T) == 4) {

@@ -163,6 +163,19 @@ def test_long_transforms_four_step(gpu, orc, order):
     rp.close()
 
 
+def test_cta_pair_form_of_the_65536_point_rfft(gpu, orc, monkeypatch):
+    # NEO_B200_PAIR selects the distributed-shared-memory form (fft_pair.cuh) when the plan is created; default is the cluster
+    # four-step, which measured faster -- both must agree with the oracle
+    monkeypatch.setenv("NEO_B200_PAIR", "1")
+    n = 1 << 16
+    x = np.stack([orc.noise(n, 40 + b, np.float32) for b in range(3)])
+    rp = gpu.RFFTPlan(16, np.float32)
+    S = rp.rfft(x)
+    assert rel_l2(S, orc.rfft(x)) <= 1e-5
+    assert rel_l2(rp.irfft(S) / n, x) <= 1e-5
+    rp.close()
+
+
 def test_long_transform_f64(gpu, orc):
     order = 15
     x = orc.noise(1 << order, 7, np.complex128)
