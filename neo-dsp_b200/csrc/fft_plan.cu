@@ -154,6 +154,7 @@ struct rfft_engine
     bool use_split{false};       // two CTAs per transform (fft_split.cuh)
     bool use_cluster{false};     // float32, N = 2^14..2^16: persistent thread-block-cluster four-step (fft_cluster.cuh)
     rfft_cluster_plan cluster;
+    bool use_split15{false};     // float32, N = 2^16 as two 1024-thread CTAs of 2^14 points each (knob)
     bool use_pair{false};        // float32, N = 2^16: one transform per CTA pair, exchange tile in distributed shared memory (fft_pair.cuh)
     bool use_big_cta{false};     // float32, M = 2^14: one 1024-thread CTA per transform (139 KB exchange tile)
     bool use_two_pass{false};    // four-CTA split c2c into an L2-resident scratch + Hermitian split pass
@@ -171,19 +172,32 @@ struct rfft_engine
         if (order == 0) { return NEO_B200_OK; }
         int const logm = order - 1;
         if constexpr (sizeof(T) == 4) {
-            // measured: the cluster kernel wins only at N = 2^16 (0.25 of HBM peak against 0.13 for the two-pass path); at
-            // 2^14 / 2^15 the two-CTA split transforms are faster (0.5-0.6 / 0.4-0.5 against 0.33 / 0.27)
-            // measured (N = 2^16): the CTA-pair form (exchange tile in distributed shared memory, one HBM pass, no scratch) reaches
-            // only 0.19 / 0.18 of HBM peak against 0.26 / 0.29 for the L2-scratch cluster four-step -- half of every exchange
-            // crosses the SM-to-SM network (~20 B/clk per SM) and each of its 8 exchanges ends in a cluster barrier. Kept as a knob.
+            // N = 2^16, measured fractions of HBM peak (r2c / c2r), all parity-tested:
+            //   two 1024-thread CTAs of 2^14 points each (fft_split.cuh, no communication)       0.39 / 0.36   <- shipped
+            //   persistent cluster four-step through an L2 scratch (fft_cluster.cuh)              0.26 / 0.29   NEO_B200_CLUSTER16
+            //   CTA pair, exchange tile in distributed shared memory (fft_pair.cuh)               0.19 / 0.18   NEO_B200_PAIR
+            //   four-CTA split c2c + Hermitian pass (two HBM-side passes)                          0.12 / 0.15   NEO_B200_NO_SPLIT15
+            // The DSMEM form loses because half of every exchange crosses the SM-to-SM network (~20 B/clk per SM) and each of its
+            // 8 exchanges ends in a cluster barrier; the cluster four-step because its phases serialise.
+            bool const all = std::getenv("NEO_B200_CLUSTER_ALL") != nullptr;
             if (order == 16 && std::getenv("NEO_B200_PAIR") != nullptr) {
                 use_pair = true;
                 return tables.build(logm, true, stream);
             }
-            bool const all = std::getenv("NEO_B200_CLUSTER_ALL") != nullptr;
-            if ((order == 16 || (all && order >= 14 && order < 16)) && std::getenv("NEO_B200_NO_CLUSTER") == nullptr) {
+            if (((order == 16 && std::getenv("NEO_B200_CLUSTER16") != nullptr) || (all && order >= 14 && order <= 16))
+                && std::getenv("NEO_B200_NO_CLUSTER") == nullptr) {
                 use_cluster = true;
                 return cluster.init(order, stream);
+            }
+            if (order == 16 && std::getenv("NEO_B200_NO_SPLIT15") == nullptr) {
+                use_split15 = true;
+                NEO_TRY(tables.build(logm - 1, true, stream));
+                auto const wn      = make_split_twiddles<T>(logm);
+                size_t const bytes = (wn.size() / 2) * sizeof(cx<T>);
+                NEO_TRY(w_n.reserve(bytes));
+                NEO_CUDA_TRY(cudaMemcpyAsync(w_n.ptr, wn.data(), bytes, cudaMemcpyHostToDevice, stream));
+                NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+                return NEO_B200_OK;
             }
         }
         // measured (N = 2^15): one 1024-thread CTA per transform 0.48 / 0.41 of HBM peak (r2c / c2r) against 0.37 / 0.36 for two
@@ -257,6 +271,7 @@ struct rfft_engine
     {
         if (order == 0) { return large_rfft<T>::size_one_forward(in, out, batch, stream); }
         if constexpr (sizeof(T) == 4) {
+            if (use_split15) { return launch_r2c_split2<T, 14>(in, out, tables.tw(), tables.rtw(), batch, stream); }
             if (use_pair) { return launch_r2c_pair<15>(in, out, tables.tw(), tables.rtw(), batch, stream); }
             if (use_cluster) { return cluster.forward(in, out, batch, stream); }
         }
@@ -289,6 +304,9 @@ struct rfft_engine
     {
         if (order == 0) { return large_rfft<T>::size_one_backward(in, row_len, out, batch, stream); }
         if constexpr (sizeof(T) == 4) {
+            if (use_split15) {
+                return launch_c2r_split2<T, 14>(in, row_len, out, tables.tw(), tables.rtw(), w_n.template as<cx<T>>(), batch, stream);
+            }
             if (use_pair) { return launch_c2r_pair<15>(in, row_len, out, tables.tw(), tables.rtw(), batch, stream); }
             if (use_cluster) { return cluster.backward(in, row_len, out, batch, stream); }
         }

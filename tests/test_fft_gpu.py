@@ -163,10 +163,12 @@ def test_long_transforms_four_step(gpu, orc, order):
     rp.close()
 
 
-def test_cta_pair_form_of_the_65536_point_rfft(gpu, orc, monkeypatch):
-    # NEO_B200_PAIR selects the distributed-shared-memory form (fft_pair.cuh) when the plan is created; default is the cluster
-    # four-step, which measured faster -- both must agree with the oracle
-    monkeypatch.setenv("NEO_B200_PAIR", "1")
+@pytest.mark.parametrize("knob", ["NEO_B200_PAIR", "NEO_B200_CLUSTER16", "NEO_B200_NO_SPLIT15", None])
+def test_every_form_of_the_65536_point_rfft(gpu, orc, monkeypatch, knob):
+    # four implementations of N = 2^16 exist (fft_plan.cu, rfft_engine::init lists what each measured); the shipped one is two
+    # 2^14-point CTAs, the others are selected by environment knobs when the plan is created -- all must agree with the oracle
+    if knob is not None:
+        monkeypatch.setenv(knob, "1")
     n = 1 << 16
     x = np.stack([orc.noise(n, 40 + b, np.float32) for b in range(3)])
     rp = gpu.RFFTPlan(16, np.float32)
