@@ -20,6 +20,17 @@ def test_header_and_binding_agree(pkg):
     assert sorted(pkg.SIGNATURES) == names
 
 
+def test_config_struct_layout_matches_the_header(pkg):
+    # neo_b200_conv_config is passed by pointer: the ctypes mirror must list the same fields, in order, with the same widths
+    text = open(os.path.join(ROOT, "include", "neo_b200.h")).read()
+    body = re.search(r"typedef struct neo_b200_conv_config\s*\{(.*?)\}\s*neo_b200_conv_config;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(int|size_t)\s+(\w+)\s*;", body)
+    want = [(name, ctypes.c_int if ctype == "int" else ctypes.c_size_t) for ctype, name in fields]
+    assert [(n, t) for n, t in pkg.ConvConfig._fields_] == want
+    assert "frame_blocks" in [n for n, _ in want]
+
+
 def test_library_exports_every_declared_symbol(pkg):
     lib = ctypes.CDLL(pkg.LIBRARY_PATH)
     for name in declared_symbols():

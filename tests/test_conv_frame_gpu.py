@@ -157,6 +157,28 @@ def test_frame_mode_small_bank_splits_rows_across_ctas(gpu, orc):
     conv.close()
 
 
+def test_frame_mode_full_size_north_star_shape(gpu, orc):
+    # BASELINE config 5 geometry (B = 1024, 2^20 taps -> P = 1024) at bench.py's default frame length T = 256 (L = 512, Q = 4,
+    # the cp.async-staged fused kernel). The oracle would need minutes here, so the check is the size-independent property:
+    # an impulse response that is a unit impulse at tap d delays the input by d samples -- delays reach across partitions,
+    # second-level partitions and frames (three frames = 768 blocks are streamed).
+    B, L, T, frames, C = 1024, 1 << 20, 256, 3, 16
+    n = B * T * frames
+    delays = [0, 1, B - 1, B, B * T - 1, B * T, B * T + 5, 2 * B * T - 7, L - 1] + [(c * 1000003 + 11) % (n // 2) for c in range(C - 9)]
+    ird = np.zeros((C, L), dtype=np.float32)
+    for c, d in enumerate(delays):
+        ird[c, d] = 1
+    rng = np.random.default_rng(5)
+    sigd = rng.uniform(-1, 1, size=(C, n)).astype(np.float32)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+    conv.impulse(ird, B)
+    out = run_bank(conv, sigd, B, [T])
+    for c, d in enumerate(delays):
+        expect = np.concatenate([np.zeros(d, dtype=np.float32), sigd[c, : n - d]])
+        assert np.allclose(out[c], expect, atol=5e-5), (c, d, float(np.abs(out[c] - expect).max()))
+    conv.close()
+
+
 def test_frame_mode_three_kernel_form_for_banks(gpu, orc, monkeypatch):
     # banks normally take the fused kernel; NEO_B200_FRAME_UNFUSED (read when the handle is created) selects the three-kernel form
     # (frame transform, frame_mac_kernel over several columns per thread, inverse transform) -- same results
