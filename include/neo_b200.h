@@ -99,6 +99,19 @@ NEO_B200_API int neo_b200_fft_exec_strided(
 NEO_B200_API int neo_b200_fft_plan_set_stream(neo_b200_fft_plan* plan, void* cuda_stream);
 NEO_B200_API int neo_b200_fft_plan_synchronize(neo_b200_fft_plan* plan);
 
+/* ---- dft plan: replaces neo::fft::dft_plan<Complex> == fallback_dft_plan (fft/dft.hpp:28-30,
+ *      fft/fallback/fallback_dft_plan.hpp:24-96): complex transform of ANY size > 0 through Bluestein's chirp-z on a
+ *      power-of-two transform of next_order(2*size+1); unnormalised in both directions like the reference. -------- */
+typedef struct neo_b200_dft_plan neo_b200_dft_plan;
+
+/* `dft_plan{size}` (fallback_dft_plan.hpp:29); dtype = precision of the complex elements (F32 -> complex<float>) */
+NEO_B200_API int neo_b200_dft_plan_create(neo_b200_dft_plan** plan, size_t size, int dtype);
+NEO_B200_API void neo_b200_dft_plan_destroy(neo_b200_dft_plan* plan);
+NEO_B200_API size_t neo_b200_dft_plan_size(neo_b200_dft_plan const* plan);
+/* `plan(x, dir)` (fallback_dft_plan.hpp:48-82) for `batch` contiguous rows of `size` interleaved complex; in == out allowed */
+NEO_B200_API int neo_b200_dft_exec(neo_b200_dft_plan* plan, void const* in, void* out, size_t batch, int direction, int memspace);
+NEO_B200_API int neo_b200_dft_plan_set_stream(neo_b200_dft_plan* plan, void* cuda_stream);
+
 /* ---- rfft plan: replaces neo::fft::rfft_plan<Float, Complex> == fallback_rfft_plan
  *      (fft/fallback/fallback_rfft_plan.hpp:15-61) ---------------------------------------------------------------- */
 typedef struct neo_b200_rfft_plan neo_b200_rfft_plan;

@@ -131,6 +131,56 @@ private:
     std::vector<Complex> _staging;
 };
 
+/// Drop-in for neo::fft::dft_plan<Complex> == fallback_dft_plan (fft/dft.hpp:28-30, fft/fallback/fallback_dft_plan.hpp:24-96):
+/// complex transform of ANY size (Bluestein), `explicit Plan(size)`, in-place `plan(x, dir)`, unnormalised both ways.
+template<typename Complex>
+struct dft_plan
+{
+    using value_type = Complex;
+    using size_type  = std::size_t;
+    using real_type  = detail::real_of<Complex>;
+
+    explicit dft_plan(size_type size) { detail::check(neo_b200_dft_plan_create(&_plan, size, detail::dtype_of<real_type>)); }
+
+    dft_plan(dft_plan const&)                    = delete;
+    auto operator=(dft_plan const&) -> dft_plan& = delete;
+    dft_plan(dft_plan&& other) noexcept : _plan{std::exchange(other._plan, nullptr)} {}
+    auto operator=(dft_plan&& other) noexcept -> dft_plan&
+    {
+        std::swap(_plan, other._plan);
+        return *this;
+    }
+    ~dft_plan() { neo_b200_dft_plan_destroy(_plan); }
+
+    [[nodiscard]] auto size() const noexcept -> size_type { return neo_b200_dft_plan_size(_plan); }
+
+    template<typename Vec, typename Direction>
+    auto operator()(Vec x, Direction dir) -> void
+    {
+        static_assert(std::is_same_v<detail::element_of<Vec>, Complex>);
+        auto const d = detail::direction_value(dir);
+        if (detail::is_contiguous(x)) {
+            detail::check(neo_b200_dft_exec(_plan, x.data_handle(), x.data_handle(), 1, d, NEO_B200_HOST));
+        } else {  // strided view: staged like backend/ipp.hpp:150-158
+            auto const n = static_cast<size_type>(x.extent(0));
+            _staging.resize(n);
+            for (size_type i = 0; i < n; ++i) { _staging[i] = x[i]; }
+            detail::check(neo_b200_dft_exec(_plan, _staging.data(), _staging.data(), 1, d, NEO_B200_HOST));
+            for (size_type i = 0; i < n; ++i) { x[i] = _staging[i]; }
+        }
+    }
+
+    /// batched extension: `batch` contiguous transforms [batch][size()], host or device memory
+    auto batched(Complex const* in, Complex* out, size_type batch, int direction, int memspace = NEO_B200_HOST) -> void
+    {
+        detail::check(neo_b200_dft_exec(_plan, in, out, batch, direction, memspace));
+    }
+
+private:
+    neo_b200_dft_plan* _plan{nullptr};
+    std::vector<Complex> _staging;
+};
+
 /// Drop-in for neo::fft::split_fft_plan<Float> (fft/fallback/fallback_split_fft_plan.hpp:16-137): operates on any aggregate with
 /// `.real` / `.imag` rank-1 views (neo::split_complex, complex/split_complex.hpp:10).
 template<typename Float>

@@ -64,6 +64,11 @@ SIGNATURES = {
     "neo_b200_fft_exec_strided": (_i, [_vp, _vp, C.c_ssize_t, _vp, C.c_ssize_t, _i]),
     "neo_b200_fft_plan_set_stream": (_i, [_vp, _vp]),
     "neo_b200_fft_plan_synchronize": (_i, [_vp]),
+    "neo_b200_dft_plan_create": (_i, [C.POINTER(_vp), _sz, _i]),
+    "neo_b200_dft_plan_destroy": (None, [_vp]),
+    "neo_b200_dft_plan_size": (_sz, [_vp]),
+    "neo_b200_dft_exec": (_i, [_vp, _vp, _vp, _sz, _i, _i]),
+    "neo_b200_dft_plan_set_stream": (_i, [_vp, _vp]),
     "neo_b200_rfft_plan_create": (_i, [C.POINTER(_vp), _sz, _i]),
     "neo_b200_rfft_plan_destroy": (None, [_vp]),
     "neo_b200_rfft_plan_order": (_sz, [_vp]),
@@ -232,6 +237,43 @@ class FFTPlan:
     def close(self) -> None:
         if self._h:
             library().neo_b200_fft_plan_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DFTPlan:
+    """neo::fft::dft_plan<Complex>{size} == fallback_dft_plan (fft/fallback/fallback_dft_plan.hpp:24-96): complex transform of ANY
+    size through Bluestein's chirp-z, batched over leading axes, unnormalised both ways."""
+
+    def __init__(self, size: int, dtype="complex64"):
+        self.real = _REAL_OF[str(np.dtype(dtype))]
+        self.complex = "complex64" if self.real == "float32" else "complex128"
+        self._h = _vp()
+        _check(library().neo_b200_dft_plan_create(C.byref(self._h), size, _DTYPE_CODE[self.real]))
+
+    def size(self) -> int:
+        return int(library().neo_b200_dft_plan_size(self._h))
+
+    def set_stream(self, stream) -> None:
+        _check(library().neo_b200_dft_plan_set_stream(self._h, _stream_ptr(stream)))
+
+    def __call__(self, x, direction: int = FORWARD, out=None):
+        """plan(x, dir): in place when `out` is None (like the reference), else out-of-place. x[..., size]."""
+        if _dtype_name(x) != self.complex or x.shape[-1] != self.size():
+            raise ValueError(f"expected {self.complex}[..., {self.size()}]")
+        out = x if out is None else out
+        batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
+        _check(library().neo_b200_dft_exec(self._h, _ptr(x), _ptr(out), batch, direction, _space(x)))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            library().neo_b200_dft_plan_destroy(self._h)
             self._h = _vp()
 
     def __del__(self):

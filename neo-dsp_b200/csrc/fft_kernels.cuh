@@ -127,6 +127,69 @@ struct c2c_split_io
     }
 };
 
+// ---- Bluestein (dft_plan == fallback_dft_plan, fft/fallback/fallback_dft_plan.hpp:49-82) around a power-of-two c2c of m points:
+// forward leg: a[j] = x[j] * w[j] zero padded (:57-58), transform, multiply by the transformed chirp filter B (:70-72);
+// backward leg: transform back, scale by 1/m (:74-75), multiply by w and keep n points (:78).
+template<typename T>
+struct bluestein_fwd_io
+{
+    cx<T> const* x;      // [batch][n]
+    cx<T>* a;            // [batch][m]
+    cx<T> const* w;      // [n] chirp of this direction
+    cx<T> const* bhat;   // [m] forward transform of the chirp filter
+    size_t n, m;
+    __device__ __forceinline__ cx<T> load(size_t b, int j) const
+    {
+        return size_t(j) < n ? cmul(x[b * n + j], w[j]) : mk<T>(T(0), T(0));
+    }
+    __device__ __forceinline__ void store(size_t b, int k, cx<T> v) const { a[b * m + k] = cmul(v, bhat[k]); }
+};
+
+template<typename T>
+struct bluestein_bwd_io
+{
+    cx<T> const* a;      // [batch][m]
+    cx<T>* out;          // [batch][n]
+    cx<T> const* w;
+    size_t n, m;
+    T scale;             // 1 / m
+    __device__ __forceinline__ cx<T> load(size_t b, int k) const { return a[b * m + k]; }
+    __device__ __forceinline__ void store(size_t b, int j, cx<T> v) const
+    {
+        if (size_t(j) < n) { out[b * n + j] = cmul(mk<T>(v.x * scale, v.y * scale), w[j]); }
+    }
+};
+
+// the same two steps as plain kernels, for padded sizes beyond the single-CTA transform
+template<typename T>
+__global__ void __launch_bounds__(256) bluestein_pre_kernel(cx<T> const* __restrict__ x, cx<T>* __restrict__ a, cx<T> const* __restrict__ w,
+                                                            size_t n, size_t m, size_t total)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) { return; }
+    size_t const b = i / m, j = i - b * m;
+    a[i]           = j < n ? cmul(x[b * n + j], w[j]) : mk<T>(T(0), T(0));
+}
+
+template<typename T>
+__global__ void __launch_bounds__(256) bluestein_mul_kernel(cx<T>* __restrict__ a, cx<T> const* __restrict__ bhat, size_t m, size_t total)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) { return; }
+    a[i] = cmul(a[i], bhat[i % m]);
+}
+
+template<typename T>
+__global__ void __launch_bounds__(256) bluestein_post_kernel(cx<T> const* __restrict__ a, cx<T>* __restrict__ out, cx<T> const* __restrict__ w,
+                                                             size_t n, size_t m, T scale, size_t total)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) { return; }
+    size_t const b = i / n, j = i - b * n;
+    cx<T> const v  = a[b * m + j];
+    out[i]         = cmul(mk<T>(v.x * scale, v.y * scale), w[j]);
+}
+
 template<typename T, int LOGM, int DIR, class IO>
 __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOGM, k_c2c>())
     c2c_kernel(IO io, cx<T> const* __restrict__ tw, size_t batch)

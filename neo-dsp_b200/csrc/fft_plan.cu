@@ -142,6 +142,91 @@ struct c2c_engine
     device_buffer planes;
 };
 
+// dft_plan: any size n through Bluestein's chirp-z (fft/fallback/fallback_dft_plan.hpp:24-96), m = 2^next_order(2n+1)
+template<typename T>
+struct dft_engine
+{
+    size_t n{0}, m{0};
+    int order{0};
+    c2c_engine<T> fft;
+    device_buffer chirp[2];  // w of the forward / backward direction, [n]
+    device_buffer bhat[2];   // forward transform of b (b[0] = w[0], b[i] = b[m-i] = conj(w[i])), [m], per direction
+    device_buffer work;      // [batch][m], grow-only
+
+    int init(size_t size, cudaStream_t stream)
+    {
+        n     = size;
+        order = 0;
+        while ((size_t(1) << order) < 2 * n + 1) { ++order; }  // fallback_dft_plan.hpp:88-91
+        if (size_t(order) > k_max_order) { return fail(NEO_B200_ERR_UNSUPPORTED, "dft size %zu needs a transform of order %d", size, order); }
+        m = size_t(1) << order;
+        NEO_TRY(fft.init(order, stream));
+        std::vector<cx<T>> w(n), b(m);
+        for (int d = 0; d < 2; ++d) {
+            double const coef = (d == 0 ? -1.0 : 1.0) * 3.14159265358979323846264338327950288 / double(n);
+            for (size_t i = 0; i < n; ++i) {
+                // (i*i) % (2n) without overflow for any size that fits the plan
+                unsigned __int128 const sq = static_cast<unsigned __int128>(i) * i;
+                double const a             = double(static_cast<size_t>(sq % (2 * n))) * coef;
+                w[i]                       = mk<T>(T(std::cos(a)), T(std::sin(a)));
+            }
+            std::fill(b.begin(), b.end(), mk<T>(T(0), T(0)));
+            b[0] = w[0];  // as the reference does (:59); w[0] = 1 either way
+            for (size_t i = 1; i < n; ++i) { b[i] = b[m - i] = mk<T>(w[i].x, -w[i].y); }
+            NEO_TRY(chirp[d].reserve(n * sizeof(cx<T>)));
+            NEO_TRY(bhat[d].reserve(m * sizeof(cx<T>)));
+            NEO_CUDA_TRY(cudaMemcpyAsync(chirp[d].ptr, w.data(), n * sizeof(cx<T>), cudaMemcpyHostToDevice, stream));
+            NEO_CUDA_TRY(cudaMemcpyAsync(bhat[d].ptr, b.data(), m * sizeof(cx<T>), cudaMemcpyHostToDevice, stream));
+            NEO_TRY(fft.exec(bhat[d].template as<cx<T>>(), bhat[d].template as<cx<T>>(), 1, -1, stream));
+            NEO_CUDA_TRY(cudaStreamSynchronize(stream));  // host vectors are reused
+        }
+        return NEO_B200_OK;
+    }
+
+    int exec(cx<T> const* in, cx<T>* out, size_t batch, int direction, cudaStream_t stream)
+    {
+        if (batch == 0) { return NEO_B200_OK; }
+        int const d      = direction < 0 ? 0 : 1;
+        auto const* w    = chirp[d].template as<cx<T>>();
+        auto const* bh   = bhat[d].template as<cx<T>>();
+        T const scale    = T(1) / T(m);
+        // the padded transforms are walked in chunks of about 256 MB of work space
+        size_t const chunk = std::max<size_t>(1, std::min(batch, (size_t(256) << 20) / (m * sizeof(cx<T>))));
+        NEO_TRY(work.reserve(chunk * m * sizeof(cx<T>)));
+        cx<T>* const a = work.template as<cx<T>>();
+        for (size_t first = 0; first < batch; first += chunk) {
+            size_t const cnt = std::min(chunk, batch - first);
+            cx<T> const* x   = in + first * n;
+            cx<T>* y         = out + first * n;
+            if (order <= max_cta_logm<T>()) {
+                // two launches: chirp multiply and zero padding ride on the forward transform's loads, the filter product on its
+                // stores; scaling, the second chirp multiply and the cut to n points on the backward transform's stores
+                int status = NEO_B200_ERR_UNSUPPORTED;
+                bluestein_fwd_io<T> const fio{x, a, w, bh, n, m};
+                bluestein_bwd_io<T> const bio{a, y, w, n, m, scale};
+                NEO_DISPATCH_LOGM(T, order, {
+                    if constexpr (LOGM <= max_cta_logm<T>()) {
+                        status = launch_c2c_io<T, LOGM, -1>(fio, fft.tables.tw(), cnt, stream);
+                        if (status == NEO_B200_OK) { status = launch_c2c_io<T, LOGM, +1>(bio, fft.tables.tw(), cnt, stream); }
+                    }
+                });
+                if (status != NEO_B200_OK) { return status; }
+            } else {
+                size_t const padded = cnt * m, kept = cnt * n;
+                bluestein_pre_kernel<T><<<unsigned((padded + 255) / 256), 256, 0, stream>>>(x, a, w, n, m, padded);
+                NEO_TRY(check_launch("bluestein_pre_kernel"));
+                NEO_TRY(fft.exec(a, a, cnt, -1, stream));
+                bluestein_mul_kernel<T><<<unsigned((padded + 255) / 256), 256, 0, stream>>>(a, bh, m, padded);
+                NEO_TRY(check_launch("bluestein_mul_kernel"));
+                NEO_TRY(fft.exec(a, a, cnt, +1, stream));
+                bluestein_post_kernel<T><<<unsigned((kept + 255) / 256), 256, 0, stream>>>(a, y, w, n, m, scale, kept);
+                NEO_TRY(check_launch("bluestein_post_kernel"));
+            }
+        }
+        return NEO_B200_OK;
+    }
+};
+
 template<typename T>
 struct rfft_engine
 {
@@ -363,6 +448,17 @@ struct neo_b200_rfft_plan
     device_buffer staging_in, staging_out;
 };
 
+struct neo_b200_dft_plan
+{
+    size_t size;
+    int dtype;
+    int device;
+    stream_ref stream;
+    dft_engine<float> f32;
+    dft_engine<double> f64;
+    device_buffer staging_in, staging_out;
+};
+
 extern "C" {
 
 const char* neo_b200_last_error(void) { return last_error_slot().c_str(); }
@@ -473,6 +569,70 @@ int neo_b200_fft_exec(neo_b200_fft_plan* plan, void const* in, void* out, size_t
         size_t const n = std::min(chunk, batch - first);
         NEO_CUDA_TRY(cudaMemcpyAsync(plan->staging_in.ptr, static_cast<char const*>(in) + first * row, n * row, cudaMemcpyHostToDevice, s));
         NEO_TRY(fft_exec_device(plan, plan->staging_in.ptr, plan->staging_in.ptr, n, direction));
+        NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + first * row, plan->staging_in.ptr, n * row, cudaMemcpyDeviceToHost, s));
+    }
+    NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    return NEO_B200_OK;
+}
+
+// ---- dft_plan: any size (Bluestein) ------------------------------------------------------------------------------------------------
+int neo_b200_dft_plan_create(neo_b200_dft_plan** plan, size_t size, int dtype)
+{
+    if (plan == nullptr) { return fail(NEO_B200_ERR_INVALID, "plan is null"); }
+    *plan = nullptr;
+    if (dtype != NEO_B200_F32 && dtype != NEO_B200_F64) { return fail(NEO_B200_ERR_INVALID, "bad dtype %d", dtype); }
+    if (size == 0) { return fail(NEO_B200_ERR_INVALID, "dft size must be > 0"); }
+    if (size > (size_t(1) << (k_max_order - 1))) { return fail(NEO_B200_ERR_UNSUPPORTED, "neo_b200: unsupported dft size '%zu'", size); }
+    NEO_TRY(require_device());
+    auto p = std::unique_ptr<neo_b200_dft_plan>(new (std::nothrow) neo_b200_dft_plan{});
+    if (!p) { return fail(NEO_B200_ERR_ALLOC, "out of host memory"); }
+    p->size  = size;
+    p->dtype = dtype;
+    NEO_CUDA_TRY(cudaGetDevice(&p->device));
+    NEO_TRY(p->stream.create());
+    if (dtype == NEO_B200_F32) { NEO_TRY(p->f32.init(size, p->stream.stream)); }
+    else { NEO_TRY(p->f64.init(size, p->stream.stream)); }
+    *plan = p.release();
+    return NEO_B200_OK;
+}
+
+void neo_b200_dft_plan_destroy(neo_b200_dft_plan* plan)
+{
+    if (plan == nullptr) { return; }
+    cudaStreamSynchronize(plan->stream.stream);
+    delete plan;
+}
+
+size_t neo_b200_dft_plan_size(neo_b200_dft_plan const* plan) { return plan != nullptr ? plan->size : 0; }
+
+int neo_b200_dft_plan_set_stream(neo_b200_dft_plan* plan, void* cuda_stream)
+{
+    if (plan == nullptr) { return fail(NEO_B200_ERR_INVALID, "plan is null"); }
+    plan->stream.adopt(cuda_stream);
+    return NEO_B200_OK;
+}
+
+int neo_b200_dft_exec(neo_b200_dft_plan* plan, void const* in, void* out, size_t batch, int direction, int memspace)
+{
+    if (plan == nullptr || in == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (direction != NEO_B200_FORWARD && direction != NEO_B200_BACKWARD) {
+        return fail(NEO_B200_ERR_INVALID, "direction must be -1 (forward) or +1 (backward)");
+    }
+    if (batch == 0) { return NEO_B200_OK; }
+    NEO_CUDA_TRY(cudaSetDevice(plan->device));
+    cudaStream_t const s = plan->stream.stream;
+    auto run = [&](void const* i, void* o, size_t n) {
+        if (plan->dtype == NEO_B200_F32) { return plan->f32.exec(static_cast<float2 const*>(i), static_cast<float2*>(o), n, direction, s); }
+        return plan->f64.exec(static_cast<double2 const*>(i), static_cast<double2*>(o), n, direction, s);
+    };
+    if (memspace == NEO_B200_DEVICE) { return run(in, out, batch); }
+    size_t const row   = plan->size * 2 * elem_size(plan->dtype);
+    size_t const chunk = std::max<size_t>(1, std::min(batch, (size_t(128) << 20) / row));
+    NEO_TRY(plan->staging_in.reserve(chunk * row));
+    for (size_t first = 0; first < batch; first += chunk) {
+        size_t const n = std::min(chunk, batch - first);
+        NEO_CUDA_TRY(cudaMemcpyAsync(plan->staging_in.ptr, static_cast<char const*>(in) + first * row, n * row, cudaMemcpyHostToDevice, s));
+        NEO_TRY(run(plan->staging_in.ptr, plan->staging_in.ptr, n));
         NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + first * row, plan->staging_in.ptr, n * row, cudaMemcpyDeviceToHost, s));
     }
     NEO_CUDA_TRY(cudaStreamSynchronize(s));

@@ -72,6 +72,14 @@ for real, cplx, tag in ((np.float32, np.complex64, "f32"), (np.float64, np.compl
             re, im = r.split_fft(x.real.copy(), x.imag.copy(), d)
             g[f"split/{tag}/{order}/{name}"] = np.stack([re, im])
 
+# dft_plan (Bluestein, fft/fallback/fallback_dft_plan.hpp): sizes that are NOT powers of two, and one that is
+for cplx, tag in ((np.complex64, "c64"), (np.complex128, "c128")):
+    for n in (2, 3, 5, 12, 21, 100, 127, 128):
+        x = r.noise(n, 70 + n, cplx)
+        g[f"dft/{tag}/{n}/x"] = x
+        g[f"dft/{tag}/{n}/fwd"] = r.dft(x, -1)
+        g[f"dft/{tag}/{n}/bwd"] = r.dft(x, +1)
+
 # known-answer inputs of the reference's own tests, run through the reference
 g["kat/c2c_1234"] = r.fft(np.array([1, 2, 3, 4], dtype=np.complex64), -1)  # fft/rfft_test.cpp:170-186
 delta = np.zeros(16, dtype=np.complex64)

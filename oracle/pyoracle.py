@@ -104,6 +104,18 @@ class _Checker:
                 raise RuntimeError(f"unsupported order {order}")
         return out.reshape(x.shape)
 
+    def dft(self, x: np.ndarray, direction: int = -1) -> np.ndarray:
+        """dft_plan (Bluestein, fft/fallback/fallback_dft_plan.hpp:24-96) of the last axis, ANY size, unnormalised; new array."""
+        x = np.ascontiguousarray(x)
+        real = np.dtype(_REAL[x.dtype])
+        n = x.shape[-1]
+        out = x.reshape(-1, n).copy()
+        fn = self._fn("dft_c2c_" + _SUF[real], _i, [_sz, _vp, _i])
+        for row in out:
+            if fn(n, _ptr(row), direction) != 0:
+                raise RuntimeError(f"unsupported size {n}")
+        return out.reshape(x.shape)
+
     def fft_status(self, order: int) -> int:
         """0 if a c2c plan of this order can be built (runs a transform only for small orders)."""
         if order > 27:

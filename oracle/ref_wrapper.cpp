@@ -66,6 +66,18 @@ auto c2r(std::size_t order, Float const* in, std::size_t in_len, Float* out) -> 
     neo::fft::irfft(plan, x, y);
 }
 
+// dft_plan == fallback_dft_plan (fft/dft.hpp:28-30): Bluestein, any size
+template<typename Float>
+auto bluestein(std::size_t size, Float* inout, int direction) -> int
+{
+    using Complex = std::complex<Float>;
+    if (size == 0) { return 1; }
+    auto plan = neo::fft::dft_plan<Complex>{size};
+    auto x    = vec_view<Complex>{reinterpret_cast<Complex*>(inout), size};
+    plan(x, direction < 0 ? neo::fft::direction::forward : neo::fft::direction::backward);
+    return 0;
+}
+
 template<typename Float>
 struct convolver_box
 {
@@ -109,6 +121,8 @@ extern "C" {
 // ---- plans ---------------------------------------------------------------------------
 int ref_fft_c2c_f32(std::size_t order, float* inout, int direction) { return c2c<float>(order, inout, direction); }
 int ref_fft_c2c_f64(std::size_t order, double* inout, int direction) { return c2c<double>(order, inout, direction); }
+int ref_dft_c2c_f32(std::size_t size, float* inout, int direction) { return bluestein<float>(size, inout, direction); }
+int ref_dft_c2c_f64(std::size_t size, double* inout, int direction) { return bluestein<double>(size, inout, direction); }
 void ref_rfft_f32(std::size_t order, float const* in, float* out) { r2c<float>(order, in, out); }
 void ref_rfft_f64(std::size_t order, double const* in, double* out) { r2c<double>(order, in, out); }
 void ref_irfft_f32(std::size_t order, float const* in, std::size_t n, float* out) { c2r<float>(order, in, n, out); }

@@ -201,6 +201,34 @@ static auto test_convolver() -> void
     }
 }
 
+// dft_plan (fft/dft_test.cpp:17-67): Plan{size}, identity and round trip, any size
+template<typename Float>
+static auto test_dft_plan() -> void
+{
+    using Complex  = std::complex<Float>;
+    auto const tol = std::is_same_v<Float, float> ? 1e-5 : 1e-12;
+    for (std::size_t size : {2U, 3U, 21U, 100U, 127U}) {
+        auto plan = neo::b200::dft_plan<Complex>{size};
+        REQUIRE(plan.size() == size);
+        auto x = std::vector<Complex>(size, Complex{});
+        x[0]   = Complex{1, 0};
+        plan(vec<Complex>{x.data(), size}, direction::forward);
+        auto const ones = std::vector<Complex>(size, Complex{1, 0});
+        REQUIRE(rel_l2(x, ones) <= tol);
+        plan(vec<Complex>{x.data(), size}, direction::backward);
+        REQUIRE(std::abs(x[0].real() - Float(size)) <= Float(size) * Float(tol) * 10);
+        auto re  = noise<Float>(size, 3);
+        auto im  = noise<Float>(size, 4);
+        auto sig = std::vector<Complex>(size);
+        for (std::size_t i = 0; i < size; ++i) { sig[i] = {re[i], im[i]}; }
+        auto y = sig;
+        plan(vec<Complex>{y.data(), size}, direction::forward);
+        plan(vec<Complex>{y.data(), size}, direction::backward);
+        for (auto& v : y) { v /= Float(size); }
+        REQUIRE(rel_l2(y, sig) <= 10 * tol);
+    }
+}
+
 // upola_convolver_v2 (overlap_add_convolver.hpp:21-136): calls of several whole blocks, uneven split, against the oracle's upola
 static auto test_overlap_add_convolver() -> void
 {
@@ -243,6 +271,8 @@ int main()
     test_fft_plan<double>();
     test_rfft_plan<float>();
     test_rfft_plan<double>();
+    test_dft_plan<float>();
+    test_dft_plan<double>();
     test_convolver<float, neo::b200::upols_convolver, 0>();
     test_convolver<float, neo::b200::upola_convolver, 1>();
     test_convolver<double, neo::b200::upols_convolver, 0>();

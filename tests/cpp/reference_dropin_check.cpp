@@ -44,6 +44,16 @@ auto instantiate_split() -> void
 }
 
 template<typename Complex>
+auto instantiate_dft() -> void
+{
+    auto plan = neo::b200::dft_plan<Complex>{21};  // fft/dft_test.cpp:24-29: Plan{size}
+    auto buf  = stdex::mdarray<Complex, stdex::dextents<std::size_t, 1>>{21};
+    neo::fft::dft(plan, buf.to_mdspan());   // fft/dft.hpp: dft(plan, x)
+    neo::fft::idft(plan, buf.to_mdspan());
+    (void)plan.size();
+}
+
+template<typename Complex>
 auto instantiate_convolver() -> void
 {
     using Float = typename Complex::value_type;
@@ -75,6 +85,8 @@ auto instantiate_all() -> void
     instantiate_split<double>();
     instantiate_r2c<float>();
     instantiate_r2c<double>();
+    instantiate_dft<std::complex<float>>();
+    instantiate_dft<std::complex<double>>();
     instantiate_convolver<std::complex<float>>();
     instantiate_convolver<std::complex<double>>();
 }

@@ -164,7 +164,7 @@ def test_frame_mode_full_size_north_star_shape(gpu, orc):
     # second-level partitions and frames (three frames = 768 blocks are streamed).
     B, L, T, frames, C = 1024, 1 << 20, 256, 3, 16
     n = B * T * frames
-    delays = [0, 1, B - 1, B, B * T - 1, B * T, B * T + 5, 2 * B * T - 7, L - 1] + [(c * 1000003 + 11) % (n // 2) for c in range(C - 9)]
+    delays = [0, 1, B - 1, B, B * T - 1, B * T, B * T + 5, 2 * B * T - 7, n - 1] + [(c * 1000003 + 11) % (n // 2) for c in range(C - 9)]
     ird = np.zeros((C, L), dtype=np.float32)
     for c, d in enumerate(delays):
         ird[c, d] = 1

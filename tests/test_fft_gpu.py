@@ -178,6 +178,59 @@ def test_every_form_of_the_65536_point_rfft(gpu, orc, monkeypatch, knob):
     rp.close()
 
 
+@pytest.mark.parametrize("real,cplx", CASES)
+def test_dft_plan_any_size_matches_oracle(gpu, orc, golden, real, cplx):
+    # dft_plan == fallback_dft_plan (Bluestein, fft/fallback/fallback_dft_plan.hpp:24-96): the reference tests sizes 2..128/512
+    # (fft/dft_test.cpp:24-26); here a spread of primes, composites and powers of two, batched, both directions
+    tol = TOL[np.dtype(real).name]
+    tag = "c64" if cplx == np.complex64 else "c128"
+    for n in (2, 3, 5, 12, 21, 100, 127, 128):
+        plan = gpu.DFTPlan(n, cplx)
+        x = golden[f"dft/{tag}/{n}/x"]
+        assert rel_l2(plan(x.copy(), gpu.FORWARD), golden[f"dft/{tag}/{n}/fwd"]) <= tol, n
+        assert rel_l2(plan(x.copy(), gpu.BACKWARD), golden[f"dft/{tag}/{n}/bwd"]) <= tol, n
+        plan.close()
+    for n in (1, 7, 96, 255, 257, 1000, 4095, 4096, 4097, 10007):  # 4095 is the last padded size in the fused single-CTA form (float)
+        batch = 3 if n < 5000 else 2
+        x = np.stack([orc.noise(n, 5 + b, cplx) for b in range(batch)])
+        plan = gpu.DFTPlan(n, cplx)
+        assert plan.size() == n
+        for direction in (gpu.FORWARD, gpu.BACKWARD):
+            assert rel_l2(plan(x.copy(), direction), orc.dft(x, direction)) <= tol, (n, direction)
+        out = np.zeros_like(x)
+        plan(x, gpu.FORWARD, out=out)
+        assert rel_l2(out, orc.dft(x, -1)) <= tol
+        back = plan(out.copy(), gpu.BACKWARD)  # fft/dft_test.cpp:49-66: round trip gains a factor of size
+        assert rel_l2(back / n, x) <= 10 * tol
+        plan.close()
+    # fft/dft_test.cpp:31-46: a unit impulse transforms to all ones
+    for n in (2, 21, 127):
+        x = np.zeros(n, dtype=cplx)
+        x[0] = 1
+        plan = gpu.DFTPlan(n, cplx)
+        assert np.allclose(plan(x, gpu.FORWARD), np.ones(n), atol=1e-5 if real == np.float32 else 1e-12)
+        plan.close()
+    with pytest.raises(RuntimeError):
+        gpu.DFTPlan(0, cplx)
+
+
+def test_dft_plan_device_buffers(gpu, orc):
+    import torch
+
+    n, batch = 1500, 64
+    x = np.stack([orc.noise(n, 9 + b, np.complex64) for b in range(4)])
+    xs = np.tile(x, (batch // 4, 1))
+    plan = gpu.DFTPlan(n, np.complex64)
+    plan.set_stream(torch.cuda.current_stream())
+    dx = torch.from_numpy(xs).cuda()
+    dy = torch.empty_like(dx)
+    plan(dx, gpu.FORWARD, out=dy)
+    torch.cuda.synchronize()
+    want = orc.dft(x, -1)
+    assert rel_l2(dy.cpu().numpy()[:4], want) <= 1e-5 and rel_l2(dy.cpu().numpy()[-4:], want) <= 1e-5
+    plan.close()
+
+
 def test_long_transform_f64(gpu, orc):
     order = 15
     x = orc.noise(1 << order, 7, np.complex128)

@@ -84,6 +84,27 @@ def test_kat_delta_all_ones(orc, golden):
     assert np.array_equal(orc.fft(np.eye(1, 16, 0, dtype=np.complex64)[0], -1), golden["kat/c2c_delta16"])
 
 
+def test_dft_plan_bluestein_golden_and_identity(orc, golden):
+    # dft_plan == fallback_dft_plan (fft/dft.hpp:28-30, fallback_dft_plan.hpp:24-96): any size
+    for tag, cplx, tol in (("c64", np.complex64, 0.0), ("c128", np.complex128, 2e-15)):
+        for n in (2, 3, 5, 12, 21, 100, 127, 128):
+            x = golden[f"dft/{tag}/{n}/x"]
+            for d, name in ((-1, "fwd"), (1, "bwd")):
+                want = golden[f"dft/{tag}/{n}/{name}"]
+                got = orc.dft(x, d)
+                assert np.linalg.norm(got - want) <= tol * np.linalg.norm(want), (tag, n, name)
+                k = np.arange(n)
+                exact = np.exp(d * 2j * np.pi * np.outer(k, k) / n) @ x.astype(np.complex128)  # the naive dft() of fft/dft.hpp:34-55
+                assert np.linalg.norm(want - exact) <= (1e-5 if cplx == np.complex64 else 1e-12) * np.linalg.norm(exact)
+    # fft/dft_test.cpp:31-46 ("identity"): a unit impulse transforms to all ones, and back to size at index 0
+    for n in (2, 3, 7, 100, 127):
+        x = np.zeros(n, dtype=np.complex128)
+        x[0] = 1
+        X = orc.dft(x, -1)
+        assert np.allclose(X.real, 1.0) and np.allclose(X.imag, 0.0, atol=1e-12)
+        assert np.isclose(orc.dft(X, +1)[0].real, n)
+
+
 def test_kat_dct2_through_fft(orc):
     # fft/dct_test.cpp:23-39 pins fft_plan at N=8 through the DCT-II of [1..8] against scipy's values.
     # DCT-II via one N-point c2c (Makhoul): v = even samples then reversed odd samples, X = 2 Re(W4N^k FFT(v))
