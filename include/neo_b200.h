@@ -112,6 +112,19 @@ NEO_B200_API size_t neo_b200_dft_plan_size(neo_b200_dft_plan const* plan);
 NEO_B200_API int neo_b200_dft_exec(neo_b200_dft_plan* plan, void const* in, void* out, size_t batch, int direction, int memspace);
 NEO_B200_API int neo_b200_dft_plan_set_stream(neo_b200_dft_plan* plan, void* cuda_stream);
 
+/* ---- dct2 plan: replaces neo::fft::fallback_dct2_plan<Float> (fft/dct.hpp:24-68): unnormalised type-2 DCT of 2^order reals
+ *      (scipy.fft.dct(x, type=2), dct_test.cpp:24-39) through one complex transform of the same size. Order 0 is undefined in
+ *      the reference (its order-0 c2c plan reads past the buffer) and yields 2*x[0] here. ------------------------------------- */
+typedef struct neo_b200_dct2_plan neo_b200_dct2_plan;
+
+NEO_B200_API int neo_b200_dct2_plan_create(neo_b200_dct2_plan** plan, size_t order, int dtype);
+NEO_B200_API void neo_b200_dct2_plan_destroy(neo_b200_dct2_plan* plan);
+NEO_B200_API size_t neo_b200_dct2_plan_order(neo_b200_dct2_plan const* plan);
+NEO_B200_API size_t neo_b200_dct2_plan_size(neo_b200_dct2_plan const* plan);
+/* `plan(x)` (dct.hpp:36-63) for `batch` contiguous rows of 2^order reals; in == out allowed (the reference is in place) */
+NEO_B200_API int neo_b200_dct2_exec(neo_b200_dct2_plan* plan, void const* in, void* out, size_t batch, int memspace);
+NEO_B200_API int neo_b200_dct2_plan_set_stream(neo_b200_dct2_plan* plan, void* cuda_stream);
+
 /* ---- rfft plan: replaces neo::fft::rfft_plan<Float, Complex> == fallback_rfft_plan
  *      (fft/fallback/fallback_rfft_plan.hpp:15-61) ---------------------------------------------------------------- */
 typedef struct neo_b200_rfft_plan neo_b200_rfft_plan;

@@ -181,6 +181,58 @@ private:
     std::vector<Complex> _staging;
 };
 
+/// Drop-in for neo::fft::fallback_dct2_plan<Float> (fft/dct.hpp:24-68): `Plan{from_order, order}`, in-place `plan(x)`.
+template<typename Float>
+struct dct2_plan
+{
+    using value_type = Float;
+    using size_type  = std::size_t;
+
+    template<typename Tag>
+    dct2_plan(Tag /*from_order*/, size_type order)
+    {
+        detail::check(neo_b200_dct2_plan_create(&_plan, order, detail::dtype_of<Float>));
+    }
+
+    dct2_plan(dct2_plan const&)                    = delete;
+    auto operator=(dct2_plan const&) -> dct2_plan& = delete;
+    dct2_plan(dct2_plan&& other) noexcept : _plan{std::exchange(other._plan, nullptr)} {}
+    auto operator=(dct2_plan&& other) noexcept -> dct2_plan&
+    {
+        std::swap(_plan, other._plan);
+        return *this;
+    }
+    ~dct2_plan() { neo_b200_dct2_plan_destroy(_plan); }
+
+    [[nodiscard]] auto order() const noexcept -> size_type { return neo_b200_dct2_plan_order(_plan); }
+    [[nodiscard]] auto size() const noexcept -> size_type { return neo_b200_dct2_plan_size(_plan); }
+
+    template<typename Vec>
+    auto operator()(Vec x) -> void
+    {
+        static_assert(std::is_same_v<detail::element_of<Vec>, Float>);
+        if (detail::is_contiguous(x)) {
+            detail::check(neo_b200_dct2_exec(_plan, x.data_handle(), x.data_handle(), 1, NEO_B200_HOST));
+        } else {
+            auto const n = static_cast<size_type>(x.extent(0));
+            _staging.resize(n);
+            for (size_type i = 0; i < n; ++i) { _staging[i] = x[i]; }
+            detail::check(neo_b200_dct2_exec(_plan, _staging.data(), _staging.data(), 1, NEO_B200_HOST));
+            for (size_type i = 0; i < n; ++i) { x[i] = _staging[i]; }
+        }
+    }
+
+    /// batched extension: `batch` contiguous rows [batch][size()], host or device memory
+    auto batched(Float const* in, Float* out, size_type batch, int memspace = NEO_B200_HOST) -> void
+    {
+        detail::check(neo_b200_dct2_exec(_plan, in, out, batch, memspace));
+    }
+
+private:
+    neo_b200_dct2_plan* _plan{nullptr};
+    std::vector<Float> _staging;
+};
+
 /// Drop-in for neo::fft::split_fft_plan<Float> (fft/fallback/fallback_split_fft_plan.hpp:16-137): operates on any aggregate with
 /// `.real` / `.imag` rank-1 views (neo::split_complex, complex/split_complex.hpp:10).
 template<typename Float>

@@ -64,6 +64,12 @@ SIGNATURES = {
     "neo_b200_fft_exec_strided": (_i, [_vp, _vp, C.c_ssize_t, _vp, C.c_ssize_t, _i]),
     "neo_b200_fft_plan_set_stream": (_i, [_vp, _vp]),
     "neo_b200_fft_plan_synchronize": (_i, [_vp]),
+    "neo_b200_dct2_plan_create": (_i, [C.POINTER(_vp), _sz, _i]),
+    "neo_b200_dct2_plan_destroy": (None, [_vp]),
+    "neo_b200_dct2_plan_order": (_sz, [_vp]),
+    "neo_b200_dct2_plan_size": (_sz, [_vp]),
+    "neo_b200_dct2_exec": (_i, [_vp, _vp, _vp, _sz, _i]),
+    "neo_b200_dct2_plan_set_stream": (_i, [_vp, _vp]),
     "neo_b200_dft_plan_create": (_i, [C.POINTER(_vp), _sz, _i]),
     "neo_b200_dft_plan_destroy": (None, [_vp]),
     "neo_b200_dft_plan_size": (_sz, [_vp]),
@@ -237,6 +243,44 @@ class FFTPlan:
     def close(self) -> None:
         if self._h:
             library().neo_b200_fft_plan_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DCT2Plan:
+    """neo::fft::fallback_dct2_plan<Float>{from_order, order} (fft/dct.hpp:24-68): unnormalised type-2 DCT, batched over leading axes."""
+
+    def __init__(self, order: int, dtype="float32"):
+        self.real = _REAL_OF[str(np.dtype(dtype))]
+        self._h = _vp()
+        _check(library().neo_b200_dct2_plan_create(C.byref(self._h), order, _DTYPE_CODE[self.real]))
+
+    def order(self) -> int:
+        return int(library().neo_b200_dct2_plan_order(self._h))
+
+    def size(self) -> int:
+        return int(library().neo_b200_dct2_plan_size(self._h))
+
+    def set_stream(self, stream) -> None:
+        _check(library().neo_b200_dct2_plan_set_stream(self._h, _stream_ptr(stream)))
+
+    def __call__(self, x, out=None):
+        """plan(x): in place when `out` is None (like the reference). x[..., size] reals."""
+        if _dtype_name(x) != self.real or x.shape[-1] != self.size():
+            raise ValueError(f"expected {self.real}[..., {self.size()}]")
+        out = x if out is None else out
+        batch = int(np.prod(x.shape[:-1], dtype=np.int64)) if x.ndim > 1 else 1
+        _check(library().neo_b200_dct2_exec(self._h, _ptr(x), _ptr(out), batch, _space(x)))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            library().neo_b200_dct2_plan_destroy(self._h)
             self._h = _vp()
 
     def __del__(self):

@@ -160,6 +160,44 @@ struct bluestein_bwd_io
     }
 };
 
+// ---- type-2 DCT through one complex transform of the same size (fallback_dct2_plan, fft/dct.hpp:40-63, Makhoul):
+// loads permute the real row (even samples ascending, odd samples descending from the top), stores keep Re(v * 2 exp(-i pi k / 2n)).
+template<typename T>
+struct dct2_io
+{
+    T const* in;         // [batch][n] reals
+    T* out;              // [batch][n] reals
+    cx<T> const* scale;  // [n]: 2 exp(-i pi k / (2n))
+    size_t n;
+    __device__ __forceinline__ cx<T> load(size_t b, int j) const
+    {
+        size_t const i   = size_t(j);
+        size_t const src = 2 * i < n ? 2 * i : 2 * (n - 1 - i) + 1;
+        return mk<T>(in[b * n + src], T(0));
+    }
+    __device__ __forceinline__ void store(size_t b, int k, cx<T> v) const { out[b * n + k] = v.x * scale[k].x - v.y * scale[k].y; }
+};
+
+template<typename T>
+__global__ void __launch_bounds__(256) dct2_pre_kernel(T const* __restrict__ x, cx<T>* __restrict__ a, size_t n, size_t total)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) { return; }
+    size_t const b = i / n, j = i - b * n;
+    size_t const src = 2 * j < n ? 2 * j : 2 * (n - 1 - j) + 1;
+    a[i] = mk<T>(x[b * n + src], T(0));
+}
+
+template<typename T>
+__global__ void __launch_bounds__(256) dct2_post_kernel(cx<T> const* __restrict__ a, T* __restrict__ out, cx<T> const* __restrict__ scale,
+                                                        size_t n, size_t total)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= total) { return; }
+    cx<T> const s = scale[i % n];
+    out[i]        = a[i].x * s.x - a[i].y * s.y;
+}
+
 // the same two steps as plain kernels, for padded sizes beyond the single-CTA transform
 template<typename T>
 __global__ void __launch_bounds__(256) bluestein_pre_kernel(cx<T> const* __restrict__ x, cx<T>* __restrict__ a, cx<T> const* __restrict__ w,

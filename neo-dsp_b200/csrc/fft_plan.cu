@@ -227,6 +227,61 @@ struct dft_engine
     }
 };
 
+// fallback_dct2_plan (fft/dct.hpp:24-68): unnormalised type-2 DCT of 2^order reals
+template<typename T>
+struct dct2_engine
+{
+    int order{0};
+    size_t n{1};
+    c2c_engine<T> fft;
+    device_buffer scale;  // 2 exp(-i pi k / (2n)), k < n
+    device_buffer work;   // beyond the single-CTA range: [batch][n] complex, grow-only; in-place calls of the fused form: [batch][n] reals
+
+    int init(int order_, cudaStream_t stream)
+    {
+        order = order_;
+        n     = size_t(1) << order;
+        NEO_TRY(fft.init(order, stream));
+        std::vector<cx<T>> s(n);
+        for (size_t k = 0; k < n; ++k) {
+            double const a = -3.14159265358979323846264338327950288 * double(k) / (2.0 * double(n));
+            s[k]           = mk<T>(T(2.0 * std::cos(a)), T(2.0 * std::sin(a)));
+        }
+        NEO_TRY(scale.reserve(n * sizeof(cx<T>)));
+        NEO_CUDA_TRY(cudaMemcpyAsync(scale.ptr, s.data(), n * sizeof(cx<T>), cudaMemcpyHostToDevice, stream));
+        NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+        return NEO_B200_OK;
+    }
+
+    int exec(T const* in, T* out, size_t batch, cudaStream_t stream)
+    {
+        if (batch == 0) { return NEO_B200_OK; }
+        auto const* sc = scale.template as<cx<T>>();
+        if (order <= max_cta_logm<T>()) {
+            // one launch. In place is fine: a row is read completely, by the threads that later write it, before the transform's
+            // first barrier (a one-thread transform has no barrier and no second reader)
+            int status = NEO_B200_ERR_UNSUPPORTED;
+            dct2_io<T> const io{in, out, sc, n};
+            NEO_DISPATCH_LOGM(T, order, {
+                if constexpr (LOGM <= max_cta_logm<T>()) { status = launch_c2c_io<T, LOGM, -1>(io, fft.tables.tw(), batch, stream); }
+            });
+            return status;
+        }
+        size_t const chunk = std::max<size_t>(1, std::min(batch, (size_t(256) << 20) / (n * sizeof(cx<T>))));
+        NEO_TRY(work.reserve(chunk * n * sizeof(cx<T>)));
+        cx<T>* const a = work.template as<cx<T>>();
+        for (size_t first = 0; first < batch; first += chunk) {
+            size_t const cnt = std::min(chunk, batch - first), total = cnt * n;
+            dct2_pre_kernel<T><<<unsigned((total + 255) / 256), 256, 0, stream>>>(in + first * n, a, n, total);
+            NEO_TRY(check_launch("dct2_pre_kernel"));
+            NEO_TRY(fft.exec(a, a, cnt, -1, stream));
+            dct2_post_kernel<T><<<unsigned((total + 255) / 256), 256, 0, stream>>>(a, out + first * n, sc, n, total);
+            NEO_TRY(check_launch("dct2_post_kernel"));
+        }
+        return NEO_B200_OK;
+    }
+};
+
 template<typename T>
 struct rfft_engine
 {
@@ -448,6 +503,17 @@ struct neo_b200_rfft_plan
     device_buffer staging_in, staging_out;
 };
 
+struct neo_b200_dct2_plan
+{
+    size_t order;
+    int dtype;
+    int device;
+    stream_ref stream;
+    dct2_engine<float> f32;
+    dct2_engine<double> f64;
+    device_buffer staging;
+};
+
 struct neo_b200_dft_plan
 {
     size_t size;
@@ -570,6 +636,67 @@ int neo_b200_fft_exec(neo_b200_fft_plan* plan, void const* in, void* out, size_t
         NEO_CUDA_TRY(cudaMemcpyAsync(plan->staging_in.ptr, static_cast<char const*>(in) + first * row, n * row, cudaMemcpyHostToDevice, s));
         NEO_TRY(fft_exec_device(plan, plan->staging_in.ptr, plan->staging_in.ptr, n, direction));
         NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + first * row, plan->staging_in.ptr, n * row, cudaMemcpyDeviceToHost, s));
+    }
+    NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    return NEO_B200_OK;
+}
+
+// ---- dct2 plan (fft/dct.hpp:24-68) ---------------------------------------------------------------------------------------------------
+int neo_b200_dct2_plan_create(neo_b200_dct2_plan** plan, size_t order, int dtype)
+{
+    if (plan == nullptr) { return fail(NEO_B200_ERR_INVALID, "plan is null"); }
+    *plan = nullptr;
+    if (dtype != NEO_B200_F32 && dtype != NEO_B200_F64) { return fail(NEO_B200_ERR_INVALID, "bad dtype %d", dtype); }
+    if (order > k_max_order) { return fail(NEO_B200_ERR_UNSUPPORTED, "neo_b200: unsupported order '%zu'", order); }
+    NEO_TRY(require_device());
+    auto p = std::unique_ptr<neo_b200_dct2_plan>(new (std::nothrow) neo_b200_dct2_plan{});
+    if (!p) { return fail(NEO_B200_ERR_ALLOC, "out of host memory"); }
+    p->order = order;
+    p->dtype = dtype;
+    NEO_CUDA_TRY(cudaGetDevice(&p->device));
+    NEO_TRY(p->stream.create());
+    if (dtype == NEO_B200_F32) { NEO_TRY(p->f32.init(int(order), p->stream.stream)); }
+    else { NEO_TRY(p->f64.init(int(order), p->stream.stream)); }
+    *plan = p.release();
+    return NEO_B200_OK;
+}
+
+void neo_b200_dct2_plan_destroy(neo_b200_dct2_plan* plan)
+{
+    if (plan == nullptr) { return; }
+    cudaStreamSynchronize(plan->stream.stream);
+    delete plan;
+}
+
+size_t neo_b200_dct2_plan_order(neo_b200_dct2_plan const* plan) { return plan != nullptr ? plan->order : 0; }
+size_t neo_b200_dct2_plan_size(neo_b200_dct2_plan const* plan) { return plan != nullptr ? size_t(1) << plan->order : 0; }
+
+int neo_b200_dct2_plan_set_stream(neo_b200_dct2_plan* plan, void* cuda_stream)
+{
+    if (plan == nullptr) { return fail(NEO_B200_ERR_INVALID, "plan is null"); }
+    plan->stream.adopt(cuda_stream);
+    return NEO_B200_OK;
+}
+
+int neo_b200_dct2_exec(neo_b200_dct2_plan* plan, void const* in, void* out, size_t batch, int memspace)
+{
+    if (plan == nullptr || in == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (batch == 0) { return NEO_B200_OK; }
+    NEO_CUDA_TRY(cudaSetDevice(plan->device));
+    cudaStream_t const s = plan->stream.stream;
+    auto run = [&](void const* i, void* o, size_t n) {
+        if (plan->dtype == NEO_B200_F32) { return plan->f32.exec(static_cast<float const*>(i), static_cast<float*>(o), n, s); }
+        return plan->f64.exec(static_cast<double const*>(i), static_cast<double*>(o), n, s);
+    };
+    if (memspace == NEO_B200_DEVICE) { return run(in, out, batch); }
+    size_t const row   = (size_t(1) << plan->order) * elem_size(plan->dtype);
+    size_t const chunk = std::max<size_t>(1, std::min(batch, (size_t(128) << 20) / row));
+    NEO_TRY(plan->staging.reserve(chunk * row));
+    for (size_t first = 0; first < batch; first += chunk) {
+        size_t const n = std::min(chunk, batch - first);
+        NEO_CUDA_TRY(cudaMemcpyAsync(plan->staging.ptr, static_cast<char const*>(in) + first * row, n * row, cudaMemcpyHostToDevice, s));
+        NEO_TRY(run(plan->staging.ptr, plan->staging.ptr, n));
+        NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + first * row, plan->staging.ptr, n * row, cudaMemcpyDeviceToHost, s));
     }
     NEO_CUDA_TRY(cudaStreamSynchronize(s));
     return NEO_B200_OK;

@@ -80,6 +80,14 @@ for cplx, tag in ((np.complex64, "c64"), (np.complex128, "c128")):
         g[f"dft/{tag}/{n}/fwd"] = r.dft(x, -1)
         g[f"dft/{tag}/{n}/bwd"] = r.dft(x, +1)
 
+# fallback_dct2_plan (fft/dct.hpp:24-68)
+for real, tag in ((np.float32, "f32"), (np.float64, "f64")):
+    for order in (1, 3, 6, 10):  # order 0 is undefined in the reference (order-0 c2c reads past its buffer)
+        x = r.noise(1 << order, 90 + order, real)
+        g[f"dct2/{tag}/{order}/x"] = x
+        g[f"dct2/{tag}/{order}/out"] = r.dct2(x)
+g["kat/dct2_1to8"] = r.dct2(np.arange(1, 9, dtype=np.float64))  # fft/dct_test.cpp:24-39
+
 # known-answer inputs of the reference's own tests, run through the reference
 g["kat/c2c_1234"] = r.fft(np.array([1, 2, 3, 4], dtype=np.complex64), -1)  # fft/rfft_test.cpp:170-186
 delta = np.zeros(16, dtype=np.complex64)

@@ -160,10 +160,12 @@ static double oracle_canonical_f64(oracle_mt19937* g)
 #define R_COS cosf
 #define R_SIN sinf
 #define R_SQRT sqrtf
+#define R_FMA fmaf
 #include "neo_oracle_impl.inc"
 #undef REAL
 #undef SUF
 #undef R_COS
+#undef R_FMA
 #undef R_SIN
 #undef R_SQRT
 
@@ -172,9 +174,11 @@ static double oracle_canonical_f64(oracle_mt19937* g)
 #define R_COS cos
 #define R_SIN sin
 #define R_SQRT sqrt
+#define R_FMA fma
 #include "neo_oracle_impl.inc"
 #undef REAL
 #undef SUF
 #undef R_COS
+#undef R_FMA
 #undef R_SIN
 #undef R_SQRT

@@ -22,6 +22,7 @@ void oracle_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, 
     void oracle_twiddle_lut_##S(size_t size, int direction, REAL* out);                                                \
     int oracle_fft_c2c_##S(size_t order, REAL* inout, int direction);                                                  \
     int oracle_dft_c2c_##S(size_t size, REAL* inout, int direction);                                                   \
+    int oracle_dct2_##S(size_t order, REAL* inout);                                                                    \
     void oracle_rfft_##S(size_t order, REAL const* in, REAL* out);                                                     \
     void oracle_irfft_##S(size_t order, REAL const* in, size_t in_len, REAL* out);                                     \
     void oracle_multiply_add_##S(REAL const* x, REAL const* y, REAL const* z, REAL* out, size_t n);                    \

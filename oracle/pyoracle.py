@@ -116,6 +116,20 @@ class _Checker:
                 raise RuntimeError(f"unsupported size {n}")
         return out.reshape(x.shape)
 
+    def dct2(self, x: np.ndarray) -> np.ndarray:
+        """fallback_dct2_plan (fft/dct.hpp:24-68): unnormalised type-2 DCT of the last axis (power-of-two length); new array."""
+        x = np.ascontiguousarray(x)
+        real = np.dtype(x.dtype)
+        n = x.shape[-1]
+        order = int(n).bit_length() - 1
+        assert 1 << order == n
+        out = x.reshape(-1, n).copy()
+        fn = self._fn("dct2_" + _SUF[real], _i, [_sz, _vp])
+        for row in out:
+            if fn(order, _ptr(row)) != 0:
+                raise RuntimeError(f"unsupported order {order}")
+        return out.reshape(x.shape)
+
     def fft_status(self, order: int) -> int:
         """0 if a c2c plan of this order can be built (runs a transform only for small orders)."""
         if order > 27:

@@ -13,6 +13,7 @@
 #include <neo/algorithm.hpp>
 #include <neo/convolution.hpp>
 #include <neo/fft.hpp>
+#include <neo/fft/dct.hpp>
 #include <neo/testing/testing.hpp>
 
 #include <atomic>
@@ -64,6 +65,16 @@ auto c2r(std::size_t order, Float const* in, std::size_t in_len, Float* out) -> 
     auto x        = vec_view<Complex const>{reinterpret_cast<Complex const*>(in), in_len};
     auto y        = vec_view<Float>{out, plan.size()};
     neo::fft::irfft(plan, x, y);
+}
+
+// fallback_dct2_plan (fft/dct.hpp:24-68)
+template<typename Float>
+auto dct2(std::size_t order, Float* inout) -> int
+{
+    if (order > 27) { return 1; }
+    auto plan = neo::fft::fallback_dct2_plan<Float>{neo::fft::from_order, order};
+    plan(vec_view<Float>{inout, plan.size()});
+    return 0;
 }
 
 // dft_plan == fallback_dft_plan (fft/dft.hpp:28-30): Bluestein, any size
@@ -121,6 +132,8 @@ extern "C" {
 // ---- plans ---------------------------------------------------------------------------
 int ref_fft_c2c_f32(std::size_t order, float* inout, int direction) { return c2c<float>(order, inout, direction); }
 int ref_fft_c2c_f64(std::size_t order, double* inout, int direction) { return c2c<double>(order, inout, direction); }
+int ref_dct2_f32(std::size_t order, float* inout) { return dct2<float>(order, inout); }
+int ref_dct2_f64(std::size_t order, double* inout) { return dct2<double>(order, inout); }
 int ref_dft_c2c_f32(std::size_t size, float* inout, int direction) { return bluestein<float>(size, inout, direction); }
 int ref_dft_c2c_f64(std::size_t size, double* inout, int direction) { return bluestein<double>(size, inout, direction); }
 void ref_rfft_f32(std::size_t order, float const* in, float* out) { r2c<float>(order, in, out); }

@@ -43,6 +43,16 @@ auto instantiate_split() -> void
     neo::fft::fft(plan, x, x);     // out-of-place overload, fft/split_fft.hpp:46-51
 }
 
+template<typename Float>
+auto instantiate_dct2() -> void
+{
+    auto plan = neo::b200::dct2_plan<Float>{neo::fft::from_order, 3};  // fft/dct_test.cpp:17-22
+    auto buf  = stdex::mdarray<Float, stdex::dextents<std::size_t, 1>>{8};
+    plan(buf.to_mdspan());
+    (void)plan.order();
+    (void)plan.size();
+}
+
 template<typename Complex>
 auto instantiate_dft() -> void
 {
@@ -85,6 +95,8 @@ auto instantiate_all() -> void
     instantiate_split<double>();
     instantiate_r2c<float>();
     instantiate_r2c<double>();
+    instantiate_dct2<float>();
+    instantiate_dct2<double>();
     instantiate_dft<std::complex<float>>();
     instantiate_dft<std::complex<double>>();
     instantiate_convolver<std::complex<float>>();

@@ -214,6 +214,32 @@ def test_dft_plan_any_size_matches_oracle(gpu, orc, golden, real, cplx):
         gpu.DFTPlan(0, cplx)
 
 
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+def test_dct2_plan_matches_oracle_and_scipy_known_answer(gpu, orc, golden, real):
+    # fallback_dct2_plan (fft/dct.hpp:24-68); dct_test.cpp:24-39: scipy.fft.dct([1..8], type=2)
+    tol = TOL[np.dtype(real).name]
+    tag = "f32" if real == np.float32 else "f64"
+    plan = gpu.DCT2Plan(3, real)
+    assert plan.order() == 3 and plan.size() == 8
+    got = plan(np.arange(1, 9, dtype=real))
+    assert np.allclose(got, [72.0, -25.76929209, 0.0, -2.6938192, 0.0, -0.80361161, 0.0, -0.20280929], atol=2e-5 if real == np.float32 else 1e-7)
+    plan.close()
+    for order in (1, 3, 6, 10):
+        plan = gpu.DCT2Plan(order, real)
+        assert rel_l2(plan(golden[f"dct2/{tag}/{order}/x"].copy()), golden[f"dct2/{tag}/{order}/out"]) <= tol, order
+        plan.close()
+    for order in (0, 2, 5, 9, 12, 13, 14, 16):  # 14 and 16 leave the single-CTA range (float): pre / transform / post kernels
+        n = 1 << order
+        x = np.stack([orc.noise(n, 60 + b, real) for b in range(3 if order < 14 else 2)])
+        plan = gpu.DCT2Plan(order, real)
+        want = orc.dct2(x)
+        assert rel_l2(plan(x.copy()), want) <= tol, order
+        out = np.zeros_like(x)
+        plan(x, out=out)
+        assert rel_l2(out, want) <= tol
+        plan.close()
+
+
 def test_dft_plan_device_buffers(gpu, orc):
     import torch
 

@@ -105,6 +105,19 @@ def test_dft_plan_bluestein_golden_and_identity(orc, golden):
         assert np.isclose(orc.dft(X, +1)[0].real, n)
 
 
+def test_dct2_plan_golden_and_scipy_known_answer(orc, golden):
+    # fallback_dct2_plan (fft/dct.hpp:24-68); known answer fft/dct_test.cpp:24-39 = scipy.fft.dct([1..8], type=2)
+    want = [72.0, -25.76929209, 0.0, -2.6938192, 0.0, -0.80361161, 0.0, -0.20280929]
+    assert np.allclose(orc.dct2(np.arange(1, 9, dtype=np.float64)), want, atol=1e-7)
+    assert np.allclose(golden["kat/dct2_1to8"], want, atol=1e-7)
+    for tag, real, tol in (("f32", np.float32, 0.0), ("f64", np.float64, 1e-15)):
+        for order in (1, 3, 6, 10):
+            x, out = golden[f"dct2/{tag}/{order}/x"], golden[f"dct2/{tag}/{order}/out"]
+            got = orc.dct2(x)
+            assert np.linalg.norm(got - out) <= tol * max(np.linalg.norm(out), 1e-30), (tag, order)
+    assert float(orc.dct2(np.array([3.0], dtype=np.float32))[0]) == 6.0  # order 0: undefined in the reference, DCT-II of one sample here
+
+
 def test_kat_dct2_through_fft(orc):
     # fft/dct_test.cpp:23-39 pins fft_plan at N=8 through the DCT-II of [1..8] against scipy's values.
     # DCT-II via one N-point c2c (Makhoul): v = even samples then reversed odd samples, X = 2 Re(W4N^k FFT(v))
