@@ -168,6 +168,15 @@ NEO_B200_API int neo_b200_uniform_partition(
 
 /* neo::convolution::normalize_impulse (convolution/normalize_impulse.hpp:13-33, algorithm/normalize_energy.hpp:17-44) in place on
  * ir [channels][taps]: every sample is scaled by the smallest per-channel 1/sqrt(sum x^2) (1 for an all-zero channel). */
+/* `stft_plan{options}(x)` (fft/stft.hpp:39-109): x [channels][len] reals -> out [channels][frames][n/2+1] complex, n = bit_ceil(
+ * transform_size), frames = neo_b200_num_stft_frames(len, frame_size, overlap_size); frame f starts at f*(frame_size-overlap_size),
+ * is clipped at the end of the signal, zero padded to n and multiplied by `window` ([n] reals in the same memory space; NULL =
+ * rectangular; the reference default is hann_window, math/windowing.hpp:27-41). uniform_partition is the frame = B, transform = 2B,
+ * overlap = 0, rectangular case. */
+NEO_B200_API size_t neo_b200_num_stft_frames(size_t signal, size_t frame_size, size_t overlap_size);
+NEO_B200_API int neo_b200_stft(void const* x, size_t channels, size_t len, size_t frame_size, size_t transform_size,
+                               size_t overlap_size, void const* window, void* out, int dtype, int memspace);
+
 NEO_B200_API int neo_b200_normalize_impulse(void* ir, size_t channels, size_t taps, int dtype, int memspace);
 
 /* ---- partitioned convolver: replaces neo::convolution::upols_convolver / upola_convolver

@@ -12,6 +12,7 @@
 
 #include "neo_b200.h"
 
+#include <cmath>
 #include <complex>
 #include <cstddef>
 #include <algorithm>
@@ -61,6 +62,17 @@ struct from_order_tag
     explicit from_order_tag() = default;
 };
 inline constexpr auto from_order = from_order_tag{};
+
+namespace detail {
+/// hann_window (math/windowing.hpp:27-41), evaluated in double and rounded by the caller
+struct hann
+{
+    auto operator()(std::size_t index, std::size_t size) const noexcept -> double
+    {
+        return 0.5 * (1.0 - std::cos(2.0 * 3.14159265358979323846 * static_cast<double>(index) / static_cast<double>(size - 1)));
+    }
+};
+}  // namespace detail
 
 /// Drop-in for neo::fft::fft_plan<Complex> (fft/reference/c2c_dit2_plan.hpp:22-104): in-place `plan(x, dir)`, unnormalised,
 /// plus the optional out-of-place overload that fft/fft.hpp:63-71 looks for. Complex = std::complex<T> or
@@ -179,6 +191,46 @@ struct dft_plan
 private:
     neo_b200_dft_plan* _plan{nullptr};
     std::vector<Complex> _staging;
+};
+
+/// neo::fft::stft_plan<Float> (fft/stft.hpp:39-109) on the device. The reference returns an owning rank-3 mdarray; this facade stays
+/// container-agnostic: `frames(len)`, `bins()`, then `operator()(x, channels, len, out)` fills out [channels][frames][bins].
+/// INTEGRATION.md shows the three-line wrapper that gives neo::fft::stft_plan::operator() back its signature.
+template<typename Float>
+struct stft_plan
+{
+    using size_type    = std::size_t;
+    using complex_type = std::complex<Float>;
+
+    /// stft_plan(transform_size) (stft.hpp:43-49): frame = transform, half overlap, hann window
+    explicit stft_plan(size_type transform_size) : stft_plan(transform_size, transform_size, transform_size / 2) {}
+
+    /// window(index, size) as in stft_options::window; default hann_window (math/windowing.hpp:27-41)
+    template<typename Window = detail::hann>
+    stft_plan(size_type frame_size, size_type transform_size, size_type overlap_size, Window window = {})
+        : _frame{frame_size}, _transform{transform_size}, _overlap{overlap_size}
+    {
+        auto n = size_type(1);
+        while (n < transform_size) { n *= 2; }
+        _window.resize(n);
+        for (size_type i = 0; i < n; ++i) { _window[i] = static_cast<Float>(window(i, n)); }  // fill_window, windowing.hpp:61-67
+    }
+
+    [[nodiscard]] auto bins() const noexcept -> size_type { return _window.size() / 2 + 1; }
+    [[nodiscard]] auto frames(size_type signal_size) const noexcept -> size_type
+    {
+        return neo_b200_num_stft_frames(signal_size, _frame, _overlap);
+    }
+
+    auto operator()(Float const* x, size_type channels, size_type len, complex_type* out, int memspace = NEO_B200_HOST) -> void
+    {
+        if (memspace != NEO_B200_HOST) { throw std::invalid_argument{"stft_plan: the window lives in host memory; use neo_b200_stft directly"}; }
+        detail::check(neo_b200_stft(x, channels, len, _frame, _transform, _overlap, _window.data(), out, detail::dtype_of<Float>, memspace));
+    }
+
+private:
+    size_type _frame, _transform, _overlap;
+    std::vector<Float> _window;
 };
 
 /// Drop-in for neo::fft::fallback_dct2_plan<Float> (fft/dct.hpp:24-68): `Plan{from_order, order}`, in-place `plan(x)`.

@@ -64,6 +64,8 @@ SIGNATURES = {
     "neo_b200_fft_exec_strided": (_i, [_vp, _vp, C.c_ssize_t, _vp, C.c_ssize_t, _i]),
     "neo_b200_fft_plan_set_stream": (_i, [_vp, _vp]),
     "neo_b200_fft_plan_synchronize": (_i, [_vp]),
+    "neo_b200_num_stft_frames": (_sz, [_sz, _sz, _sz]),
+    "neo_b200_stft": (_i, [_vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _i, _i]),
     "neo_b200_dct2_plan_create": (_i, [C.POINTER(_vp), _sz, _i]),
     "neo_b200_dct2_plan_destroy": (None, [_vp]),
     "neo_b200_dct2_plan_order": (_sz, [_vp]),
@@ -420,6 +422,49 @@ def uniform_partition(ir, block: int):
     parts = num_partitions(taps, block)
     out = _empty_like_kind(ir, (ch, parts, block + 1), "complex64" if real == "float32" else "complex128")
     _check(library().neo_b200_uniform_partition(_ptr(ir), ch, taps, block, _ptr(out), _DTYPE_CODE[real], _space(ir)))
+    return out
+
+
+def window(kind: str, size: int, dtype="float32") -> np.ndarray:
+    """math/windowing.hpp:14-67: "rectangular", "hann" (the stft default) or "hamming" of `size` points, evaluated in `dtype`."""
+    real = np.dtype(dtype).type
+    if kind == "rectangular":
+        return np.ones(size, dtype=real)
+    i = np.arange(size, dtype=real)
+    c = np.cos((real(np.pi) * real(2)) * i / real(size - 1)).astype(real)
+    if kind == "hann":
+        return (real(0.5) * (real(1) - c)).astype(real)
+    if kind == "hamming":
+        return (real(0.54) - real(0.46) * c).astype(real)
+    raise ValueError(f"unknown window '{kind}'")
+
+
+def num_stft_frames(signal: int, frame_size: int, overlap_size: int) -> int:
+    return int(library().neo_b200_num_stft_frames(signal, frame_size, overlap_size))
+
+
+def stft(x, frame_size: int, transform_size: int | None = None, overlap_size: int | None = None, window_kind="hann"):
+    """neo::fft::stft(x, options) (fft/stft.hpp:39-125): x[C][L] reals -> [C][frames][bins] complex. Defaults follow
+    stft_plan(transform_size) (:43-49): frame = transform, overlap = transform / 2, hann window. `window_kind` may also be an array
+    of bit_ceil(transform_size) values."""
+    if x.ndim != 2:
+        raise ValueError("signal must be [channels][samples]")
+    real = _dtype_name(x)
+    transform_size = frame_size if transform_size is None else transform_size
+    overlap_size = transform_size // 2 if overlap_size is None else overlap_size
+    n = 1 << max(0, int(transform_size - 1).bit_length())
+    ch, length = int(x.shape[0]), int(x.shape[1])
+    frames = num_stft_frames(length, frame_size, overlap_size)
+    out = _empty_like_kind(x, (ch, frames, n // 2 + 1), "complex64" if real == "float32" else "complex128")
+    win = window(window_kind, n, real) if isinstance(window_kind, str) else window_kind
+    wptr = None
+    if not (isinstance(window_kind, str) and window_kind == "rectangular"):
+        if _space(x) == DEVICE and isinstance(win, np.ndarray):
+            import torch
+
+            win = torch.from_numpy(np.ascontiguousarray(win)).to(x.device)
+        wptr = _ptr(win)
+    _check(library().neo_b200_stft(_ptr(x), ch, length, frame_size, transform_size, overlap_size, wptr, _ptr(out), _DTYPE_CODE[real], _space(x)))
     return out
 
 

@@ -1005,6 +1005,83 @@ int neo_b200_uniform_partition(void const* ir, size_t channels, size_t taps, siz
     return fail(NEO_B200_ERR_INVALID, "bad dtype %d", dtype);
 }
 
+size_t neo_b200_num_stft_frames(size_t signal, size_t frame, size_t overlap)
+{
+    // num_sftf_frames (fft/stft.hpp:21-25): idiv(signal - frame + overlap, frame - overlap) + 1, idiv rounds up (math/idiv.hpp:11-14)
+    if (frame == 0 || overlap >= frame || signal < frame) { return 0; }
+    size_t const hop = frame - overlap;
+    return (signal - frame + overlap + hop - 1) / hop + 1;
+}
+
+extern "C++" template<typename T>
+int stft_impl(void const* x, size_t channels, size_t len, size_t frame, size_t transform, size_t overlap, void const* window, void* out,
+              int memspace)
+{
+    size_t const order = neo_b200_next_order(transform);  // rfft_plan{from_order, next_order(transform_size)}, stft.hpp:104
+    if (order < 1) { return fail(NEO_B200_ERR_INVALID, "transform size must be at least 2"); }
+    int const logm = int(order) - 1;
+    if (logm > max_cta_logm<T>()) { return fail(NEO_B200_ERR_UNSUPPORTED, "transform size %zu exceeds the single-CTA transform range", transform); }
+    size_t const n      = size_t(1) << order;
+    size_t const bins   = n / 2 + 1;
+    size_t const frames = neo_b200_num_stft_frames(len, frame, overlap);
+    if (frame > n) { return fail(NEO_B200_ERR_INVALID, "frame size %zu larger than the transform size %zu", frame, n); }
+    stream_ref stream;
+    NEO_TRY(stream.create());
+    cudaStream_t const s = stream.stream;
+    fft_tables<T> tables;
+    NEO_TRY(tables.build(logm, true, s));
+    device_buffer d_win, d_in, d_out;
+    T const* win = static_cast<T const*>(window);
+    if (window != nullptr && memspace == NEO_B200_HOST) {
+        NEO_TRY(d_win.reserve(n * sizeof(T)));
+        NEO_CUDA_TRY(cudaMemcpyAsync(d_win.ptr, window, n * sizeof(T), cudaMemcpyHostToDevice, s));
+        win = d_win.template as<T>();
+    }
+    size_t const out_row = frames * bins * sizeof(cx<T>);
+    size_t chunk         = channels;
+    if (memspace == NEO_B200_HOST) {
+        chunk = std::max<size_t>(1, std::min(channels, (size_t(256) << 20) / std::max<size_t>(out_row, 1)));
+        NEO_TRY(d_in.reserve(chunk * len * sizeof(T)));
+        NEO_TRY(d_out.reserve(chunk * out_row));
+    }
+    for (size_t c = 0; c < channels; c += chunk) {
+        size_t const cnt = std::min(chunk, channels - c);
+        T const* in_dev  = static_cast<T const*>(x) + c * len;
+        cx<T>* out_dev   = static_cast<cx<T>*>(out) + c * frames * bins;
+        if (memspace == NEO_B200_HOST) {
+            NEO_CUDA_TRY(cudaMemcpyAsync(d_in.ptr, in_dev, cnt * len * sizeof(T), cudaMemcpyHostToDevice, s));
+            in_dev  = d_in.template as<T>();
+            out_dev = d_out.template as<cx<T>>();
+        }
+        int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_DISPATCH_LOGM(T, logm, {
+            if constexpr (LOGM <= max_cta_logm<T>()) {
+                stft_r2c_io<T, LOGM> io{in_dev, len, frame, frame - overlap, frames, win, out_dev};
+                status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), cnt * frames, s);
+            }
+        });
+        if (status != NEO_B200_OK) { return status; }
+        if (memspace == NEO_B200_HOST) {
+            NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + c * out_row, d_out.ptr, cnt * out_row, cudaMemcpyDeviceToHost, s));
+        }
+        NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return NEO_B200_OK;
+}
+
+int neo_b200_stft(void const* x, size_t channels, size_t len, size_t frame_size, size_t transform_size, size_t overlap_size,
+                  void const* window, void* out, int dtype, int memspace)
+{
+    if (x == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (frame_size == 0 || overlap_size >= frame_size) { return fail(NEO_B200_ERR_INVALID, "need 0 <= overlap < frame size"); }
+    if (len < frame_size) { return fail(NEO_B200_ERR_INVALID, "signal shorter than one frame"); }  // stft.hpp:24 underflows
+    if (channels == 0) { return NEO_B200_OK; }
+    NEO_TRY(require_device());
+    if (dtype == NEO_B200_F32) { return stft_impl<float>(x, channels, len, frame_size, transform_size, overlap_size, window, out, memspace); }
+    if (dtype == NEO_B200_F64) { return stft_impl<double>(x, channels, len, frame_size, transform_size, overlap_size, window, out, memspace); }
+    return fail(NEO_B200_ERR_INVALID, "bad dtype %d", dtype);
+}
+
 extern "C++" template<typename T>
 int normalize_impulse_impl(void* ir, size_t channels, size_t taps, int memspace)
 {

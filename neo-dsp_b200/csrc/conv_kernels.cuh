@@ -710,6 +710,54 @@ struct partition_r2c_io
     }
 };
 
+// stft_plan (fft/stft.hpp:70-99): frame f of channel c = x[c][f*hop .. f*hop + frame) (clipped at the end of the signal), zero padded to
+// the transform size 2M, times the window (null = rectangular); out [C][frames][M+1]
+template<typename T, int LOGM>
+struct stft_r2c_io
+{
+    using C = cx<T>;
+    T const* x;          // [channels][len]
+    size_t len;
+    size_t frame, hop;   // hop = frame - overlap
+    size_t frames;
+    T const* window;     // [2M] or null
+    C* out;
+
+    struct row_state
+    {
+        T const* src;
+        long count;
+        C* dst;
+    };
+    __device__ __forceinline__ row_state open(size_t b) const
+    {
+        constexpr size_t M = size_t(1) << LOGM;
+        size_t const c     = b / frames;
+        size_t const f     = b - c * frames;
+        size_t const first = f * hop;
+        size_t const left  = len - first;
+        return {x + c * len + first, long(left < frame ? left : frame), out + b * (M + 1)};
+    }
+    __device__ __forceinline__ C load(row_state const& r, int j) const
+    {
+        long const i = 2L * j;
+        T a = i < r.count ? r.src[i] : T(0);
+        T b = i + 1 < r.count ? r.src[i + 1] : T(0);
+        if (window != nullptr) {
+            a *= window[i];
+            b *= window[i + 1];
+        }
+        return mk<T>(a, b);
+    }
+    __device__ __forceinline__ void keep(row_state const&, int, C) const {}
+    __device__ __forceinline__ void store(row_state const& r, int k, C v) const { r.dst[k] = v; }
+    __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const
+    {
+        r.dst[0]         = mk<T>(dc, T(0));
+        r.dst[1 << LOGM] = mk<T>(nyq, T(0));
+    }
+};
+
 // reference layout H[f][P][B+1] -> convolver layout [f][parts][B] for partitions [part0, part0+parts)
 template<typename T>
 __global__ void __launch_bounds__(256)

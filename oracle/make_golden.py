@@ -80,6 +80,13 @@ for cplx, tag in ((np.complex64, "c64"), (np.complex128, "c128")):
         g[f"dft/{tag}/{n}/fwd"] = r.dft(x, -1)
         g[f"dft/{tag}/{n}/bwd"] = r.dft(x, +1)
 
+# stft_plan (fft/stft.hpp:39-109): (frame, transform, overlap, window kind 0 rect / 1 hann / 2 hamming), 2 channels x 1000 samples
+for real, tag in ((np.float32, "f32"), (np.float64, "f64")):
+    x = np.stack([r.noise(1000, 5 + c, real) for c in range(2)])
+    g[f"stft/{tag}/x"] = x
+    for frame, transform, overlap, win in ((256, 256, 128, 1), (128, 256, 0, 0), (100, 128, 30, 2), (64, 64, 48, 1), (256, 300, 17, 1)):
+        g[f"stft/{tag}/{frame}_{transform}_{overlap}_{win}"] = r.stft(x, frame, transform, overlap, win)
+
 # fallback_dct2_plan (fft/dct.hpp:24-68)
 for real, tag in ((np.float32, "f32"), (np.float64, "f64")):
     for order in (1, 3, 6, 10):  # order 0 is undefined in the reference (order-0 c2c reads past its buffer)

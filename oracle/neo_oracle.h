@@ -27,6 +27,8 @@ void oracle_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, 
     void oracle_irfft_##S(size_t order, REAL const* in, size_t in_len, REAL* out);                                     \
     void oracle_multiply_add_##S(REAL const* x, REAL const* y, REAL const* z, REAL* out, size_t n);                    \
     size_t oracle_uniform_partition_##S(REAL const* ir, size_t channels, size_t len, size_t block, REAL* out);         \
+    size_t oracle_stft_##S(REAL const* x, size_t channels, size_t len, size_t frame, size_t transform, size_t overlap, \
+                           int window, REAL* out);                                                                     \
     void oracle_normalize_impulse_##S(REAL* ir, size_t channels, size_t len);                                          \
     struct oracle_conv_##S* oracle_conv_create_##S(int kind);                                                          \
     void oracle_conv_destroy_##S(struct oracle_conv_##S* c);                                                           \

@@ -130,6 +130,19 @@ class _Checker:
                 raise RuntimeError(f"unsupported order {order}")
         return out.reshape(x.shape)
 
+    def stft(self, x: np.ndarray, frame: int, transform: int, overlap: int, window: int = 1) -> np.ndarray:
+        """stft_plan (fft/stft.hpp:39-109) of x[C][L]: window 0 rectangular / 1 hann / 2 hamming; returns [C][frames][bins]."""
+        x = np.ascontiguousarray(x)
+        real = np.dtype(x.dtype)
+        ch, length = x.shape
+        n = 1 << max(0, int(transform - 1).bit_length())
+        frames = self.num_stft_frames(length, frame, overlap)
+        out = np.zeros((ch, frames, n // 2 + 1), dtype=_CPLX[real])
+        fn = self._fn("stft_" + _SUF[real], _sz, [_vp, _sz, _sz, _sz, _sz, _sz, _i, _vp])
+        got = fn(_ptr(x), ch, length, frame, transform, overlap, window, _ptr(out))
+        assert got == frames
+        return out
+
     def fft_status(self, order: int) -> int:
         """0 if a c2c plan of this order can be built (runs a transform only for small orders)."""
         if order > 27:

@@ -67,6 +67,21 @@ auto c2r(std::size_t order, Float const* in, std::size_t in_len, Float* out) -> 
     neo::fft::irfft(plan, x, y);
 }
 
+// stft_plan (fft/stft.hpp:39-109): window 0 rectangular, 1 hann, 2 hamming (math/windowing.hpp); out [C][frames][bins], returns frames
+template<typename Float>
+auto stft_impl(Float const* x, std::size_t channels, std::size_t len, std::size_t frame, std::size_t transform, std::size_t overlap,
+               int window, Float* out) -> std::size_t
+{
+    auto options = neo::fft::stft_options<Float>{.frame_size = frame, .transform_size = transform, .overlap_size = overlap};
+    if (window == 0) { options.window = neo::rectangular_window<Float>{}; }
+    else if (window == 1) { options.window = neo::hann_window<Float>{}; }
+    else { options.window = neo::hamming_window<Float>{}; }
+    auto plan   = neo::fft::stft_plan<Float>{options};
+    auto result = plan(mat_view<Float const>{x, channels, len});
+    if (out != nullptr) { std::memcpy(out, result.data(), result.size() * sizeof(std::complex<Float>)); }
+    return result.extent(1);
+}
+
 // fallback_dct2_plan (fft/dct.hpp:24-68)
 template<typename Float>
 auto dct2(std::size_t order, Float* inout) -> int
@@ -274,6 +289,16 @@ void ref_multiply_add_c64(float const* x, float const* y, float const* z, float*
 
 // ---- filter preparation -------------------------------------------------------------------
 // uniform_partition (convolution/uniform_partition.hpp:13-26): out is [C][P][B+1] complex, returns P
+std::size_t ref_stft_f32(float const* x, std::size_t channels, std::size_t len, std::size_t frame, std::size_t transform,
+                         std::size_t overlap, int window, float* out)
+{
+    return stft_impl<float>(x, channels, len, frame, transform, overlap, window, out);
+}
+std::size_t ref_stft_f64(double const* x, std::size_t channels, std::size_t len, std::size_t frame, std::size_t transform,
+                         std::size_t overlap, int window, double* out)
+{
+    return stft_impl<double>(x, channels, len, frame, transform, overlap, window, out);
+}
 std::size_t ref_uniform_partition_f32(float const* ir, std::size_t channels, std::size_t len, std::size_t block, float* out)
 {
     auto parts = neo::convolution::uniform_partition(mat_view<float const>{ir, channels, len}, block);

@@ -229,6 +229,30 @@ static auto test_dft_plan() -> void
     }
 }
 
+// stft_plan (fft/stft.hpp:39-109, stft_test.cpp:15-40): frame/bin counts and one frame against the rfft plan
+static auto test_stft_plan() -> void
+{
+    using Complex = std::complex<float>;
+    std::size_t const len = 1024, channels = 2;
+    auto sig  = noise<float>(len * channels, 21);
+    auto plan = neo::b200::stft_plan<float>{256};  // frame 256, half overlap, hann
+    REQUIRE(plan.bins() == 129);
+    REQUIRE(plan.frames(len) == 8);  // num_sftf_frames: idiv(1024 - 256 + 128, 128) + 1 (fft/stft.hpp:21-25)
+    auto out = std::vector<Complex>(channels * plan.frames(len) * plan.bins());
+    plan(sig.data(), channels, len, out.data());
+    // frame 3 of channel 1 by hand: window, then the r2c plan
+    auto frame = std::vector<float>(256);
+    for (std::size_t i = 0; i < 256; ++i) {
+        auto const w = 0.5 * (1.0 - std::cos(2.0 * 3.14159265358979323846 * double(i) / 255.0));
+        frame[i]     = float(double(sig[len + 3 * 128 + i]) * w);
+    }
+    auto want = std::vector<Complex>(129);
+    auto rp   = neo::b200::rfft_plan<float, Complex>{neo::b200::from_order, 8};
+    rp(vec<float const>{frame.data(), 256}, vec<Complex>{want.data(), 129});
+    auto got = std::vector<Complex>(out.begin() + (8 + 3) * 129, out.begin() + (8 + 4) * 129);
+    REQUIRE(rel_l2(got, want) <= 1e-5);
+}
+
 // upola_convolver_v2 (overlap_add_convolver.hpp:21-136): calls of several whole blocks, uneven split, against the oracle's upola
 static auto test_overlap_add_convolver() -> void
 {
@@ -271,6 +295,7 @@ int main()
     test_fft_plan<double>();
     test_rfft_plan<float>();
     test_rfft_plan<double>();
+    test_stft_plan();
     test_dft_plan<float>();
     test_dft_plan<double>();
     test_convolver<float, neo::b200::upols_convolver, 0>();

@@ -240,6 +240,36 @@ def test_dct2_plan_matches_oracle_and_scipy_known_answer(gpu, orc, golden, real)
         plan.close()
 
 
+@pytest.mark.parametrize("tag,real", [("f32", np.float32), ("f64", np.float64)])
+def test_stft_matches_reference_golden_and_oracle(gpu, orc, golden, tag, real):
+    # stft_plan (fft/stft.hpp:39-109): overlap, zero padding, hann / hamming / rectangular windows, ragged last frame
+    import torch
+
+    tol = TOL[np.dtype(real).name]
+    kinds = {0: "rectangular", 1: "hann", 2: "hamming"}
+    x = golden[f"stft/{tag}/x"]
+    for frame, transform, overlap, win in ((256, 256, 128, 1), (128, 256, 0, 0), (100, 128, 30, 2), (64, 64, 48, 1), (256, 300, 17, 1)):
+        want = golden[f"stft/{tag}/{frame}_{transform}_{overlap}_{win}"]
+        got = gpu.stft(x, frame, transform, overlap, kinds[win])
+        assert got.shape == want.shape
+        assert rel_l2(got, want) <= tol, (frame, transform, overlap, win)
+        assert gpu.num_stft_frames(x.shape[1], frame, overlap) == want.shape[1]
+    # defaults of stft_plan(transform_size): frame = transform, half overlap, hann (stft.hpp:43-49; stft_test.cpp:33)
+    assert rel_l2(gpu.stft(x, 256), golden[f"stft/{tag}/256_256_128_1"]) <= tol
+    # larger, device-resident, many channels: oracle side by side
+    xs = np.stack([orc.noise(20000, 30 + c, real) for c in range(5)])
+    want = orc.stft(xs, 2048, 4096, 1536, 1)
+    got = gpu.stft(torch.from_numpy(xs).cuda(), 2048, 4096, 1536, "hann")
+    assert rel_l2(got.cpu().numpy(), want) <= tol
+    # uniform_partition is the rectangular, no-overlap, transform = 2 * frame case
+    head = np.ascontiguousarray(xs[:, :16384])
+    assert rel_l2(gpu.stft(head, 1024, 2048, 0, "rectangular"), orc.uniform_partition(head, 1024)) <= tol
+    with pytest.raises(RuntimeError):
+        gpu.stft(x, 64, 64, 64)  # overlap must be smaller than the frame
+    with pytest.raises(RuntimeError):
+        gpu.stft(np.ascontiguousarray(x[:, :32]), 64)  # signal shorter than one frame
+
+
 def test_dft_plan_device_buffers(gpu, orc):
     import torch
 

@@ -118,6 +118,28 @@ def test_dct2_plan_golden_and_scipy_known_answer(orc, golden):
     assert float(orc.dct2(np.array([3.0], dtype=np.float32))[0]) == 6.0  # order 0: undefined in the reference, DCT-II of one sample here
 
 
+STFT_CASES = ((256, 256, 128, 1), (128, 256, 0, 0), (100, 128, 30, 2), (64, 64, 48, 1), (256, 300, 17, 1))
+
+
+def test_stft_plan_golden(orc, golden):
+    # stft_plan (fft/stft.hpp:39-109): frames with overlap, zero padding to the transform size, hann / hamming / rectangular window
+    for tag, tol in (("f32", 0.0), ("f64", 1e-15)):
+        x = golden[f"stft/{tag}/x"]
+        for frame, transform, overlap, win in STFT_CASES:
+            want = golden[f"stft/{tag}/{frame}_{transform}_{overlap}_{win}"]
+            got = orc.stft(x, frame, transform, overlap, win)
+            assert got.shape == want.shape == (2, orc.num_stft_frames(1000, frame, overlap), (1 << (transform - 1).bit_length()) // 2 + 1)
+            assert np.linalg.norm(got - want) <= tol * np.linalg.norm(want), (tag, frame, transform, overlap, win)
+    # uniform_partition is the frame = B, transform = 2B, no overlap, rectangular special case (uniform_partition.hpp:13-26)
+    x = golden["stft/f32/x"][:, :896]
+    assert np.array_equal(orc.uniform_partition(x, 128), orc.stft(x, 128, 256, 0, 0))
+    # against numpy for one case
+    xx = golden["stft/f64/x"]
+    w = 0.5 * (1 - np.cos(2 * np.pi * np.arange(256) / 255))
+    want = np.stack([[np.fft.rfft(xx[c, f * 128 : f * 128 + 256] * w[: len(xx[c, f * 128 : f * 128 + 256])], 256) for f in range(7)] for c in range(2)])
+    assert np.allclose(golden["stft/f64/256_256_128_1"][:, :7], want, atol=1e-10)
+
+
 def test_kat_dct2_through_fft(orc):
     # fft/dct_test.cpp:23-39 pins fft_plan at N=8 through the DCT-II of [1..8] against scipy's values.
     # DCT-II via one N-point c2c (Makhoul): v = even samples then reversed odd samples, X = 2 Re(W4N^k FFT(v))
