@@ -510,19 +510,25 @@ struct uniform_partitioned_convolver
 
     uniform_partitioned_convolver() = default;
 
-    template<typename Mat, typename... Ignored>
-    auto filter(Mat h, Ignored... /*args*/) -> void
+    /// `filter(H)` for the dense aliases; `filter(H, sparsity)` for the sparse ones (sparse_filter.hpp:25-28): `sparsity(row, col,
+    /// value)` decides which bins the reference would store in its CSR matrix (csr_matrix.hpp:64-98); rejected bins are zeroed here,
+    /// which is the same sum (multiply_add over stored elements only, algorithm/multiply_add.hpp:306-324).
+    template<typename Mat, typename... Args>
+    auto filter(Mat h, Args... args) -> void
     {
         static_assert(std::is_same_v<detail::element_of<Mat>, Complex>);
         auto const parts = static_cast<std::size_t>(h.extent(0));
         auto const bins  = static_cast<std::size_t>(h.extent(1));
         auto const* ptr  = reinterpret_cast<std::complex<real_type> const*>(h.data_handle());
-        if (h.stride(1) != 1 || static_cast<std::size_t>(h.stride(0)) != bins) {
+        constexpr bool has_predicate = sizeof...(Args) == 1 && (std::is_invocable_r_v<bool, Args, std::size_t, std::size_t, Complex> && ...);
+        if (has_predicate || h.stride(1) != 1 || static_cast<std::size_t>(h.stride(0)) != bins) {
             _copy.resize(parts * bins);
             for (std::size_t p = 0; p < parts; ++p) {
                 for (std::size_t k = 0; k < bins; ++k) {
-                    auto const v        = h(p, k);
-                    _copy[p * bins + k] = {v.real(), v.imag()};
+                    auto const v = h(p, k);
+                    bool keep    = true;
+                    if constexpr (has_predicate) { keep = (static_cast<bool>(args(p, k, v)) && ...); }
+                    _copy[p * bins + k] = keep ? std::complex<real_type>{v.real(), v.imag()} : std::complex<real_type>{};
                 }
             }
             ptr = _copy.data();
@@ -619,6 +625,14 @@ using upola_convolver_v2 = overlap_add_convolver<Complex>;
 /// neo::convolution::split_upols_convolver / split_upola_convolver (dense_convolver.hpp:32-41) differ from the dense aliases only
 /// in how the reference lays its FDL and filter out in host memory (split re/im planes for its SIMD loops); interface and results
 /// are the same (golden vectors: tests/test_conv_gpu.py), and the device layout is this library's own either way.
+/// neo::convolution::sparse_upols_convolver / sparse_upola_convolver (sparse_convolver.hpp:14-22): `filter(H, sparsity)`. The device
+/// filter stays dense (zeros where the predicate rejects): same results; a CSR device layout that would also skip the bytes is
+/// SURVEY 8f rank 4 and not built.
+template<typename Complex>
+using sparse_upols_convolver = upols_convolver<Complex>;
+template<typename Complex>
+using sparse_upola_convolver = upola_convolver<Complex>;
+
 template<typename Complex>
 using split_upols_convolver = upols_convolver<Complex>;
 template<typename Complex>

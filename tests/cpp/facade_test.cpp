@@ -229,6 +229,41 @@ static auto test_dft_plan() -> void
     }
 }
 
+// sparse_upols_convolver (sparse_convolver.hpp:14-17): filter(H, sparsity) == the dense convolver on H with the rejected bins zeroed
+static auto test_sparse_convolver() -> void
+{
+    using Complex = std::complex<float>;
+    std::size_t const block = 128, taps = 1000, nblocks = 12;
+    auto ir    = noise<float>(taps, 41);
+    auto parts = neo_b200_num_partitions(taps, block);
+    auto h     = std::vector<Complex>(parts * (block + 1));
+    neo::b200::uniform_partition(ir.data(), 1, taps, block, h.data());
+    auto const keep = [](std::size_t row, std::size_t col, Complex v) { return std::abs(v) > 0.5F && (row + col) % 3 != 0; };
+    auto masked     = h;
+    for (std::size_t p = 0; p < parts; ++p) {
+        for (std::size_t k = 0; k <= block; ++k) {
+            if (!keep(p, k, h[p * (block + 1) + k])) { masked[p * (block + 1) + k] = Complex{}; }
+        }
+    }
+    auto conv = neo::b200::sparse_upols_convolver<Complex>{};
+    conv.filter(mat<Complex const>{h.data(), parts, block + 1}, keep);
+    auto sig = noise<float>(block * nblocks, 43);
+    auto got = sig, want = sig;
+    for (std::size_t b = 0; b < nblocks; ++b) { conv(vec<float>{got.data() + b * block, block}); }
+    auto* o = oracle_conv_create_f32(0);
+    oracle_conv_filter_f32(o, reinterpret_cast<float const*>(masked.data()), parts, block + 1);
+    for (std::size_t b = 0; b < nblocks; ++b) { oracle_conv_process_f32(o, want.data() + b * block, block); }
+    oracle_conv_destroy_f32(o);
+    REQUIRE(rel_l2(got, want) <= 1e-5);
+    // identity filter with an all-pass predicate (uniform_partitioned_convolver_test.cpp:57-61)
+    auto id = std::vector<Complex>(3 * (block + 1), Complex{});
+    for (std::size_t k = 0; k <= block; ++k) { id[k] = {1, 0}; }
+    conv.filter(mat<Complex const>{id.data(), 3, block + 1}, [](auto, auto, auto) { return true; });
+    auto out = sig;
+    for (std::size_t b = 0; b < nblocks; ++b) { conv(vec<float>{out.data() + b * block, block}); }
+    REQUIRE(rel_l2(out, sig) <= 1e-5);
+}
+
 // stft_plan (fft/stft.hpp:39-109, stft_test.cpp:15-40): frame/bin counts and one frame against the rfft plan
 static auto test_stft_plan() -> void
 {
@@ -305,6 +340,7 @@ int main()
     test_convolver<float, neo::b200::split_upols_convolver, 0>();
     test_convolver<float, neo::b200::split_upola_convolver, 1>();
     test_overlap_add_convolver();
+    test_sparse_convolver();
     std::printf(failures == 0 ? "facade_test: all passed\n" : "facade_test: %d FAILED\n", failures);
     return failures == 0 ? 0 : 1;
 }

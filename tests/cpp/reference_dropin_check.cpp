@@ -78,6 +78,12 @@ auto instantiate_convolver() -> void
     auto ola2 = neo::b200::upola_convolver_v2<Complex>{};  // overlap_add_convolver.hpp:32-33
     ola2.filter(h.to_mdspan());
     ola2(block.to_mdspan());
+    auto sparse = neo::b200::sparse_upols_convolver<Complex>{};  // sparse_convolver.hpp:14-22, test :57-61
+    sparse.filter(h.to_mdspan(), [](auto, auto, auto) { return true; });
+    sparse(block.to_mdspan());
+    auto sparse_ola = neo::b200::sparse_upola_convolver<Complex>{};
+    sparse_ola.filter(h.to_mdspan(), [](auto, auto, auto) { return true; });
+    sparse_ola(block.to_mdspan());
     auto split = neo::b200::split_upols_convolver<Complex>{};  // dense_convolver.hpp:32-41
     split.filter(h.to_mdspan());
     split(block.to_mdspan());
