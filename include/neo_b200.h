@@ -112,6 +112,19 @@ NEO_B200_API size_t neo_b200_dft_plan_size(neo_b200_dft_plan const* plan);
 NEO_B200_API int neo_b200_dft_exec(neo_b200_dft_plan* plan, void const* in, void* out, size_t batch, int direction, int memspace);
 NEO_B200_API int neo_b200_dft_plan_set_stream(neo_b200_dft_plan* plan, void* cuda_stream);
 
+/* ---- fft_convolver: replaces neo::convolution::fft_convolver<Float> (convolution/fft_convolver.hpp:18-93), mode::full: one-shot
+ *      linear convolution of signal[signal_size] with patch[patch_size] through zero padded real transforms of
+ *      bit_ceil(signal_size + patch_size - 1) points; `batch` independent (signal, patch) pairs per call. ---------------------- */
+typedef struct neo_b200_fft_convolver neo_b200_fft_convolver;
+
+NEO_B200_API int neo_b200_fft_convolver_create(neo_b200_fft_convolver** conv, size_t signal_size, size_t patch_size, int dtype);
+NEO_B200_API void neo_b200_fft_convolver_destroy(neo_b200_fft_convolver* conv);
+NEO_B200_API size_t neo_b200_fft_convolver_output_size(neo_b200_fft_convolver const* conv);
+/* `convolver(signal, patch, output)` (fft_convolver.hpp:39-54): signal [batch][signal_size], patch [batch][patch_size] ->
+ * out [batch][signal_size + patch_size - 1] reals */
+NEO_B200_API int neo_b200_fft_convolver_exec(
+    neo_b200_fft_convolver* conv, void const* signal, void const* patch, void* out, size_t batch, int memspace);
+
 /* ---- dct2 plan: replaces neo::fft::fallback_dct2_plan<Float> (fft/dct.hpp:24-68): unnormalised type-2 DCT of 2^order reals
  *      (scipy.fft.dct(x, type=2), dct_test.cpp:24-39) through one complex transform of the same size. Order 0 is undefined in
  *      the reference (its order-0 c2c plan reads past the buffer) and yields 2*x[0] here. ------------------------------------- */

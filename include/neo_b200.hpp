@@ -498,6 +498,49 @@ private:
     neo_b200_conv_config _cfg{};
 };
 
+/// Drop-in for neo::convolution::fft_convolver<Float> (convolution/fft_convolver.hpp:18-93): `fft_convolver{signal_size, patch_size}`,
+/// `convolver(signal, patch, output)` with output_size() = signal_size + patch_size - 1 (mode::full).
+template<typename Float>
+struct fft_convolver
+{
+    using size_type = std::size_t;
+
+    fft_convolver(size_type signal_size, size_type patch_size) : _signal{signal_size}, _patch{patch_size}
+    {
+        detail::check(neo_b200_fft_convolver_create(&_conv, signal_size, patch_size, detail::dtype_of<Float>));
+    }
+    fft_convolver(fft_convolver const&)                    = delete;
+    auto operator=(fft_convolver const&) -> fft_convolver& = delete;
+    ~fft_convolver() { neo_b200_fft_convolver_destroy(_conv); }
+
+    [[nodiscard]] auto signal_size() const noexcept -> size_type { return _signal; }
+    [[nodiscard]] auto patch_size() const noexcept -> size_type { return _patch; }
+    [[nodiscard]] auto output_size() const noexcept -> size_type { return neo_b200_fft_convolver_output_size(_conv); }
+
+    template<typename Signal, typename Patch, typename Output>
+    auto operator()(Signal signal, Patch patch, Output output) -> void
+    {
+        _a.resize(_signal);
+        _b.resize(_patch);
+        _c.resize(output_size());
+        for (size_type i = 0; i < _signal; ++i) { _a[i] = static_cast<Float>(signal[i]); }
+        for (size_type i = 0; i < _patch; ++i) { _b[i] = static_cast<Float>(patch[i]); }
+        detail::check(neo_b200_fft_convolver_exec(_conv, _a.data(), _b.data(), _c.data(), 1, NEO_B200_HOST));
+        for (size_type i = 0; i < _c.size(); ++i) { output[i] = _c[i]; }
+    }
+
+    /// batched extension: [batch][signal_size] x [batch][patch_size] -> [batch][output_size()], host or device memory
+    auto batched(Float const* signal, Float const* patch, Float* out, size_type batch, int memspace = NEO_B200_HOST) -> void
+    {
+        detail::check(neo_b200_fft_convolver_exec(_conv, signal, patch, out, batch, memspace));
+    }
+
+private:
+    neo_b200_fft_convolver* _conv{nullptr};
+    size_type _signal, _patch;
+    std::vector<Float> _a, _b, _c;
+};
+
 /// Drop-in for neo::convolution::upols_convolver<Complex> / upola_convolver<Complex>
 /// (convolution/uniform_partitioned_convolver.hpp:14-65): default constructible, `filter(H[P][K])` deep-copies the
 /// partitions and resets all state, `operator()(block[B])` processes one block in place. One instance = one channel, as in

@@ -64,6 +64,10 @@ SIGNATURES = {
     "neo_b200_fft_exec_strided": (_i, [_vp, _vp, C.c_ssize_t, _vp, C.c_ssize_t, _i]),
     "neo_b200_fft_plan_set_stream": (_i, [_vp, _vp]),
     "neo_b200_fft_plan_synchronize": (_i, [_vp]),
+    "neo_b200_fft_convolver_create": (_i, [C.POINTER(_vp), _sz, _sz, _i]),
+    "neo_b200_fft_convolver_destroy": (None, [_vp]),
+    "neo_b200_fft_convolver_output_size": (_sz, [_vp]),
+    "neo_b200_fft_convolver_exec": (_i, [_vp, _vp, _vp, _vp, _sz, _i]),
     "neo_b200_num_stft_frames": (_sz, [_sz, _sz, _sz]),
     "neo_b200_stft": (_i, [_vp, _sz, _sz, _sz, _sz, _sz, _vp, _vp, _i, _i]),
     "neo_b200_dct2_plan_create": (_i, [C.POINTER(_vp), _sz, _i]),
@@ -675,6 +679,34 @@ def irfft(x, n: int):
     return out
 
 
+def fft_convolve(signal, patch):
+    """neo::convolution::fft_convolve (convolution/fft_convolver.hpp:84-93), mode::full, batched over leading axes:
+    signal[..., n] * patch[..., m] -> [..., n + m - 1]."""
+    real = _dtype_name(signal)
+    if _dtype_name(patch) != real or signal.shape[:-1] != patch.shape[:-1]:
+        raise ValueError("signal and patch must share dtype and batch shape")
+    n, m = int(signal.shape[-1]), int(patch.shape[-1])
+    batch = int(np.prod(signal.shape[:-1], dtype=np.int64)) if signal.ndim > 1 else 1
+    if n == 0 or m == 0:
+        return _empty_like_kind(signal, tuple(signal.shape[:-1]) + (0,), real)  # fft_convolver.hpp:88-90
+    h = _vp()
+    _check(library().neo_b200_fft_convolver_create(C.byref(h), n, m, _DTYPE_CODE[real]))
+    try:
+        out = _empty_like_kind(signal, tuple(signal.shape[:-1]) + (n + m - 1,), real)
+        if _space(signal) == DEVICE:
+            import torch
+
+            torch.cuda.synchronize()  # the handle runs on its own stream: the inputs must be complete
+        _check(library().neo_b200_fft_convolver_exec(h, _ptr(signal), _ptr(patch), _ptr(out), batch, _space(signal)))
+        if _space(signal) == DEVICE:
+            import torch
+
+            torch.cuda.synchronize()  # the handle (and its stream) is destroyed below
+    finally:
+        library().neo_b200_fft_convolver_destroy(h)
+    return out
+
+
 def convolve(in1, in2, mode: str = "full", method: str = "upols", block: int | None = None):
     """neo.convolve (extra/python/src/main.cpp:171-198): full linear convolution of two 1-D signals. The reference binds
     method="direct"/"fft"; the partitioned methods of convolution/method.hpp:8-17 ("upols", "upola") are what runs here."""
@@ -688,6 +720,8 @@ def convolve(in1, in2, mode: str = "full", method: str = "upols", block: int | N
         raise RuntimeError("unsupported ndim")  # main.cpp:126
     if sig.size == 0 or ir.size == 0:
         return np.zeros(0, dtype=np.float32)
+    if method == "fft":  # main.cpp:190-192: fft_convolve
+        return fft_convolve(sig, ir)
     if block is None:
         block = max(2, min(4096, 1 << max(1, (ir.size - 1).bit_length())))
     total = sig.size + ir.size - 1

@@ -503,6 +503,67 @@ struct neo_b200_rfft_plan
     device_buffer staging_in, staging_out;
 };
 
+// fft_convolver (convolution/fft_convolver.hpp:18-93): rows of [batch][len] reals -> [2*batch][n] zero padded (signal rows, then patch rows)
+template<typename T>
+__global__ void __launch_bounds__(256) fftconv_pad_kernel(T const* __restrict__ signal, size_t sig_len, T const* __restrict__ patch,
+                                                          size_t patch_len, T* __restrict__ padded, size_t n, size_t batch)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= 2 * batch * n) { return; }
+    size_t const row = i / n, j = i - row * n;
+    padded[i] = row < batch ? (j < sig_len ? signal[row * sig_len + j] : T(0)) : (j < patch_len ? patch[(row - batch) * patch_len + j] : T(0));
+}
+
+template<typename T>
+__global__ void __launch_bounds__(256) fftconv_mul_kernel(cx<T>* __restrict__ spec, size_t half)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= half) { return; }
+    spec[i] = cmul(spec[i], spec[half + i]);  // multiply(signal_spectrum, patch_spectrum, signal_spectrum), fft_convolver.hpp:52
+}
+
+template<typename T>
+__global__ void __launch_bounds__(256) fftconv_cut_kernel(T const* __restrict__ full, size_t n, T* __restrict__ out, size_t out_len,
+                                                          T scale, size_t batch)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= batch * out_len) { return; }
+    size_t const row = i / out_len, j = i - row * out_len;
+    out[i]           = full[row * n + j] * scale;  // scale(1/N) + copy of the first output_size() samples, :69-71
+}
+
+struct neo_b200_fft_convolver
+{
+    size_t signal_size, patch_size, order;
+    int dtype;
+    int device;
+    stream_ref stream;
+    rfft_engine<float> f32;
+    rfft_engine<double> f64;
+    device_buffer padded, spectra, full, staging_a, staging_b, staging_out;
+
+    template<typename T>
+    int run(rfft_engine<T>& eng, T const* signal, T const* patch, T* out, size_t batch)
+    {
+        cudaStream_t const s = stream.stream;
+        size_t const n = size_t(1) << order, bins = n / 2 + 1, out_len = signal_size + patch_size - 1;
+        NEO_TRY(padded.reserve(2 * batch * n * sizeof(T)));
+        NEO_TRY(spectra.reserve(2 * batch * bins * sizeof(cx<T>)));
+        NEO_TRY(full.reserve(batch * n * sizeof(T)));
+        size_t const total = 2 * batch * n;
+        fftconv_pad_kernel<T><<<unsigned((total + 255) / 256), 256, 0, s>>>(signal, signal_size, patch, patch_size, padded.template as<T>(), n, batch);
+        NEO_TRY(check_launch("fftconv_pad_kernel"));
+        NEO_TRY(eng.forward(padded.template as<T>(), spectra.template as<cx<T>>(), 2 * batch, s));
+        size_t const half = batch * bins;
+        fftconv_mul_kernel<T><<<unsigned((half + 255) / 256), 256, 0, s>>>(spectra.template as<cx<T>>(), half);
+        NEO_TRY(check_launch("fftconv_mul_kernel"));
+        NEO_TRY(eng.backward(spectra.template as<cx<T>>(), bins, full.template as<T>(), batch, s));
+        size_t const kept = batch * out_len;
+        fftconv_cut_kernel<T><<<unsigned((kept + 255) / 256), 256, 0, s>>>(full.template as<T>(), n, out, out_len, T(1) / T(n), batch);
+        return check_launch("fftconv_cut_kernel");
+    }
+};
+
 struct neo_b200_dct2_plan
 {
     size_t order;
@@ -638,6 +699,74 @@ int neo_b200_fft_exec(neo_b200_fft_plan* plan, void const* in, void* out, size_t
         NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<char*>(out) + first * row, plan->staging_in.ptr, n * row, cudaMemcpyDeviceToHost, s));
     }
     NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    return NEO_B200_OK;
+}
+
+// ---- fft_convolver (convolution/fft_convolver.hpp:18-93) ------------------------------------------------------------------------------
+int neo_b200_fft_convolver_create(neo_b200_fft_convolver** conv, size_t signal_size, size_t patch_size, int dtype)
+{
+    if (conv == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    *conv = nullptr;
+    if (dtype != NEO_B200_F32 && dtype != NEO_B200_F64) { return fail(NEO_B200_ERR_INVALID, "bad dtype %d", dtype); }
+    if (signal_size == 0 || patch_size == 0) { return fail(NEO_B200_ERR_INVALID, "signal and patch sizes must be > 0"); }
+    size_t const order = neo_b200_next_order(signal_size + patch_size - 1);  // fft_convolver.hpp:76
+    if (order > k_max_order) { return fail(NEO_B200_ERR_UNSUPPORTED, "neo_b200: unsupported order '%zu'", order); }
+    NEO_TRY(require_device());
+    auto p = std::unique_ptr<neo_b200_fft_convolver>(new (std::nothrow) neo_b200_fft_convolver{});
+    if (!p) { return fail(NEO_B200_ERR_ALLOC, "out of host memory"); }
+    p->signal_size = signal_size;
+    p->patch_size  = patch_size;
+    p->order       = order;
+    p->dtype       = dtype;
+    NEO_CUDA_TRY(cudaGetDevice(&p->device));
+    NEO_TRY(p->stream.create());
+    if (dtype == NEO_B200_F32) { NEO_TRY(p->f32.init(int(order), p->stream.stream)); }
+    else { NEO_TRY(p->f64.init(int(order), p->stream.stream)); }
+    *conv = p.release();
+    return NEO_B200_OK;
+}
+
+void neo_b200_fft_convolver_destroy(neo_b200_fft_convolver* conv)
+{
+    if (conv == nullptr) { return; }
+    cudaStreamSynchronize(conv->stream.stream);
+    delete conv;
+}
+
+size_t neo_b200_fft_convolver_output_size(neo_b200_fft_convolver const* conv)
+{
+    return conv != nullptr ? conv->signal_size + conv->patch_size - 1 : 0;  // output_size<mode::full>, convolution/mode.hpp:24-29
+}
+
+int neo_b200_fft_convolver_exec(neo_b200_fft_convolver* conv, void const* signal, void const* patch, void* out, size_t batch, int memspace)
+{
+    if (conv == nullptr || signal == nullptr || patch == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (batch == 0) { return NEO_B200_OK; }
+    NEO_CUDA_TRY(cudaSetDevice(conv->device));
+    cudaStream_t const s = conv->stream.stream;
+    size_t const es = elem_size(conv->dtype), out_len = conv->signal_size + conv->patch_size - 1;
+    void const* ds = signal;
+    void const* dp = patch;
+    void* dout     = out;
+    if (memspace == NEO_B200_HOST) {
+        NEO_TRY(conv->staging_a.reserve(batch * conv->signal_size * es));
+        NEO_TRY(conv->staging_b.reserve(batch * conv->patch_size * es));
+        NEO_TRY(conv->staging_out.reserve(batch * out_len * es));
+        NEO_CUDA_TRY(cudaMemcpyAsync(conv->staging_a.ptr, signal, batch * conv->signal_size * es, cudaMemcpyHostToDevice, s));
+        NEO_CUDA_TRY(cudaMemcpyAsync(conv->staging_b.ptr, patch, batch * conv->patch_size * es, cudaMemcpyHostToDevice, s));
+        ds   = conv->staging_a.ptr;
+        dp   = conv->staging_b.ptr;
+        dout = conv->staging_out.ptr;
+    }
+    if (conv->dtype == NEO_B200_F32) {
+        NEO_TRY(conv->run(conv->f32, static_cast<float const*>(ds), static_cast<float const*>(dp), static_cast<float*>(dout), batch));
+    } else {
+        NEO_TRY(conv->run(conv->f64, static_cast<double const*>(ds), static_cast<double const*>(dp), static_cast<double*>(dout), batch));
+    }
+    if (memspace == NEO_B200_HOST) {
+        NEO_CUDA_TRY(cudaMemcpyAsync(out, dout, batch * out_len * es, cudaMemcpyDeviceToHost, s));
+        NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    }
     return NEO_B200_OK;
 }
 

@@ -87,6 +87,14 @@ for real, tag in ((np.float32, "f32"), (np.float64, "f64")):
     for frame, transform, overlap, win in ((256, 256, 128, 1), (128, 256, 0, 0), (100, 128, 30, 2), (64, 64, 48, 1), (256, 300, 17, 1)):
         g[f"stft/{tag}/{frame}_{transform}_{overlap}_{win}"] = r.stft(x, frame, transform, overlap, win)
 
+# fft_convolve (convolution/fft_convolver.hpp:18-93), mode::full
+for real, tag in ((np.float32, "f32"), (np.float64, "f64")):
+    for n, m in ((2, 2), (7, 3), (100, 31), (513, 512)):
+        x, h = r.noise(n, 5, real), r.noise(m, 6, real)
+        g[f"fft_convolve/{tag}/{n}_{m}/signal"] = x
+        g[f"fft_convolve/{tag}/{n}_{m}/patch"] = h
+        g[f"fft_convolve/{tag}/{n}_{m}/out"] = r.fft_convolve(x, h)
+
 # fallback_dct2_plan (fft/dct.hpp:24-68)
 for real, tag in ((np.float32, "f32"), (np.float64, "f64")):
     for order in (1, 3, 6, 10):  # order 0 is undefined in the reference (order-0 c2c reads past its buffer)

@@ -35,6 +35,7 @@ void oracle_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, 
     void oracle_conv_filter_##S(struct oracle_conv_##S* c, REAL const* h, size_t parts, size_t bins);                  \
     void oracle_conv_process_##S(struct oracle_conv_##S* c, REAL* inout, size_t num_samples);                          \
     void oracle_direct_convolve_##S(REAL const* sig, size_t sig_len, REAL const* ir, size_t ir_len, REAL* out, size_t out_len); \
+    void oracle_fft_convolve_##S(REAL const* sig, size_t sig_len, REAL const* patch, size_t patch_len, REAL* out);      \
     void oracle_noise_##S(size_t n, uint32_t seed, REAL* out);
 
 NEO_ORACLE_DECLARE(float, f32)

@@ -143,6 +143,14 @@ class _Checker:
         assert got == frames
         return out
 
+    def fft_convolve(self, signal: np.ndarray, patch: np.ndarray) -> np.ndarray:
+        """fft_convolve (convolution/fft_convolver.hpp:18-93), mode::full: signal[n] * patch[m] -> [n + m - 1]."""
+        signal = np.ascontiguousarray(signal)
+        patch = np.ascontiguousarray(patch, dtype=signal.dtype)
+        out = np.zeros(signal.size + patch.size - 1, dtype=signal.dtype)
+        self._fn("fft_convolve_" + _SUF[signal.dtype], None, [_vp, _sz, _vp, _sz, _vp])(_ptr(signal), signal.size, _ptr(patch), patch.size, _ptr(out))
+        return out
+
     def fft_status(self, order: int) -> int:
         """0 if a c2c plan of this order can be built (runs a transform only for small orders)."""
         if order > 27:

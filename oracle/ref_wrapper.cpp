@@ -289,6 +289,17 @@ void ref_multiply_add_c64(float const* x, float const* y, float const* z, float*
 
 // ---- filter preparation -------------------------------------------------------------------
 // uniform_partition (convolution/uniform_partition.hpp:13-26): out is [C][P][B+1] complex, returns P
+// fft_convolve (convolution/fft_convolver.hpp:84-93), mode::full: out is [n + m - 1]
+void ref_fft_convolve_f32(float const* signal, std::size_t n, float const* patch, std::size_t m, float* out)
+{
+    auto result = neo::convolution::fft_convolve(vec_view<float const>{signal, n}, vec_view<float const>{patch, m});
+    std::memcpy(out, result.data(), result.size() * sizeof(float));
+}
+void ref_fft_convolve_f64(double const* signal, std::size_t n, double const* patch, std::size_t m, double* out)
+{
+    auto result = neo::convolution::fft_convolve(vec_view<double const>{signal, n}, vec_view<double const>{patch, m});
+    std::memcpy(out, result.data(), result.size() * sizeof(double));
+}
 std::size_t ref_stft_f32(float const* x, std::size_t channels, std::size_t len, std::size_t frame, std::size_t transform,
                          std::size_t overlap, int window, float* out)
 {

@@ -44,6 +44,16 @@ auto instantiate_split() -> void
 }
 
 template<typename Float>
+auto instantiate_fft_convolver() -> void
+{
+    auto conv   = neo::b200::fft_convolver<Float>{100, 31};  // convolution/fft_convolver.hpp:21
+    auto signal = stdex::mdarray<Float, stdex::dextents<std::size_t, 1>>{100};
+    auto patch  = stdex::mdarray<Float, stdex::dextents<std::size_t, 1>>{31};
+    auto output = stdex::mdarray<Float, stdex::dextents<std::size_t, 1>>{conv.output_size()};
+    conv(signal.to_mdspan(), patch.to_mdspan(), output.to_mdspan());  // :39
+}
+
+template<typename Float>
 auto instantiate_dct2() -> void
 {
     auto plan = neo::b200::dct2_plan<Float>{neo::fft::from_order, 3};  // fft/dct_test.cpp:17-22
@@ -101,6 +111,8 @@ auto instantiate_all() -> void
     instantiate_split<double>();
     instantiate_r2c<float>();
     instantiate_r2c<double>();
+    instantiate_fft_convolver<float>();
+    instantiate_fft_convolver<double>();
     instantiate_dct2<float>();
     instantiate_dct2<double>();
     instantiate_dft<std::complex<float>>();

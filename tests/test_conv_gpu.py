@@ -344,6 +344,29 @@ def test_baseline_config4_full_size_matrix_routing(gpu, orc):
         conv.close()
 
 
+@pytest.mark.parametrize("tag,real", [("f32", np.float32), ("f64", np.float64)])
+def test_fft_convolve_matches_reference_golden_and_oracle(gpu, orc, golden, tag, real):
+    # fft_convolver (convolution/fft_convolver.hpp:18-93), mode::full
+    import torch
+
+    tol = TOL[np.dtype(real).name]
+    for n, m in ((2, 2), (7, 3), (100, 31), (513, 512)):
+        x, h = golden[f"fft_convolve/{tag}/{n}_{m}/signal"], golden[f"fft_convolve/{tag}/{n}_{m}/patch"]
+        got = gpu.fft_convolve(x, h)
+        assert got.shape == (n + m - 1,)
+        assert rel_l2(got, golden[f"fft_convolve/{tag}/{n}_{m}/out"]) <= 10 * tol, (n, m)
+    # batched, device resident, a transform beyond the single-CTA range (2^17 points)
+    n, m, batch = 70000, 40000, 3
+    xs = np.stack([orc.noise(n, 50 + b, real) for b in range(batch)])
+    hs = np.stack([orc.noise(m, 60 + b, real) for b in range(batch)])
+    got = gpu.fft_convolve(torch.from_numpy(xs).cuda(), torch.from_numpy(hs).cuda()).cpu().numpy()
+    for b in range(batch):
+        assert rel_l2(got[b], orc.fft_convolve(xs[b], hs[b])) <= 10 * tol, b
+    assert rel_l2(gpu.fft_convolve(np.ones(1, dtype=real), np.full(1, 3, dtype=real)), np.full(1, 3.0)) <= tol  # N = 1
+    if real == np.float32:
+        assert rel_l2(gpu.convolve(xs[0, :500], hs[0, :60], method="fft"), orc.direct_convolve(xs[0, :500], hs[0, :60], 559)) <= 1e-5
+
+
 def test_normalize_impulse_matches_oracle(gpu, orc):
     # convolution/normalize_impulse_test.cpp: unit energy for the loudest channel, common factor for all
     ir = np.stack([orc.noise(4097, 21 + c, np.float32) * (c + 1) for c in range(3)])

@@ -140,6 +140,19 @@ def test_stft_plan_golden(orc, golden):
     assert np.allclose(golden["stft/f64/256_256_128_1"][:, :7], want, atol=1e-10)
 
 
+def test_fft_convolve_golden_and_direct(orc, golden):
+    # fft_convolver (convolution/fft_convolver.hpp:18-93) against the compiled reference and against direct_convolve
+    for tag, tol in (("f32", 0.0), ("f64", 1e-15)):
+        for n, m in ((2, 2), (7, 3), (100, 31), (513, 512)):
+            x, h = golden[f"fft_convolve/{tag}/{n}_{m}/signal"], golden[f"fft_convolve/{tag}/{n}_{m}/patch"]
+            want = golden[f"fft_convolve/{tag}/{n}_{m}/out"]
+            got = orc.fft_convolve(x, h)
+            assert got.shape == (n + m - 1,)
+            assert np.linalg.norm(got - want) <= tol * np.linalg.norm(want), (tag, n, m)
+            direct = orc.direct_convolve(x, h, n + m - 1)
+            assert np.linalg.norm(want - direct) <= (1e-5 if tag == "f32" else 1e-12) * np.linalg.norm(direct)
+
+
 def test_kat_dct2_through_fft(orc):
     # fft/dct_test.cpp:23-39 pins fft_plan at N=8 through the DCT-II of [1..8] against scipy's values.
     # DCT-II via one N-point c2c (Makhoul): v = even samples then reversed odd samples, X = 2 Re(W4N^k FFT(v))
