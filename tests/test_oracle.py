@@ -153,6 +153,44 @@ def test_fft_convolve_golden_and_direct(orc, golden):
             assert np.linalg.norm(want - direct) <= (1e-5 if tag == "f32" else 1e-12) * np.linalg.norm(direct)
 
 
+def test_randomised_shapes_against_numpy(orc):
+    # property checks over randomised sizes (hypothesis): the restated plans agree with numpy's definitions
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(1, 300), seed=st.integers(0, 1000), direction=st.sampled_from([-1, 1]))
+    def dft_any_size(n, seed, direction):
+        x = orc.noise(n, seed, np.complex128)
+        k = np.arange(n)
+        exact = np.exp(direction * 2j * np.pi * np.outer(k, k) / n) @ x
+        assert np.linalg.norm(orc.dft(x, direction) - exact) <= 1e-11 * max(np.linalg.norm(exact), 1e-30)
+
+    @settings(max_examples=25, deadline=None)
+    @given(frame=st.integers(2, 64), pad=st.integers(0, 40), overlap_frac=st.floats(0, 0.9), extra=st.integers(0, 200), win=st.sampled_from([0, 1, 2]))
+    def stft_frames(frame, pad, overlap_frac, extra, win):
+        transform, overlap, length = frame + pad, int(overlap_frac * (frame - 1)), frame + extra
+        n = 1 << max(0, (transform - 1).bit_length())
+        x = orc.noise(length, 3, np.float64)[None]
+        S = orc.stft(x, frame, transform, overlap, win)[0]
+        i = np.arange(n)
+        w = np.ones(n) if win == 0 else 0.5 * (1 - np.cos(2 * np.pi * i / (n - 1))) if win == 1 else 0.54 - 0.46 * np.cos(2 * np.pi * i / (n - 1))
+        for f in range(S.shape[0]):
+            seg = x[0, f * (frame - overlap) : f * (frame - overlap) + frame]
+            buf = np.zeros(n)
+            buf[: len(seg)] = seg
+            assert np.allclose(S[f], np.fft.rfft(buf * w), atol=1e-10)
+
+    @settings(max_examples=25, deadline=None)
+    @given(n=st.integers(1, 200), m=st.integers(1, 200))
+    def fft_convolve_full(n, m):
+        x, h = orc.noise(n, 1, np.float64), orc.noise(m, 2, np.float64)
+        assert np.allclose(orc.fft_convolve(x, h), np.convolve(x, h), atol=1e-11)
+
+    dft_any_size()
+    stft_frames()
+    fft_convolve_full()
+
+
 def test_kat_dct2_through_fft(orc):
     # fft/dct_test.cpp:23-39 pins fft_plan at N=8 through the DCT-II of [1..8] against scipy's values.
     # DCT-II via one N-point c2c (Makhoul): v = even samples then reversed odd samples, X = 2 Re(W4N^k FFT(v))
