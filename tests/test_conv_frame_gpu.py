@@ -157,6 +157,36 @@ def test_frame_mode_small_bank_splits_rows_across_ctas(gpu, orc):
     conv.close()
 
 
+def test_frame_mode_agrees_with_direct_form_over_a_grid_of_shapes(gpu, orc):
+    # geometry sweep: every combination of block size (tile narrower / as wide as / wider than 16 bins, several tiles), frame length
+    # (L below, at and above the tile width), partition count (fewer / more than a frame) and channel count (ragged bin groups):
+    # frame mode against the direct form on the same device (both against the oracle for the smallest block sizes)
+    rng = np.random.default_rng(7)
+    for kind in (gpu.UPOLS, gpu.UPOLA):
+        for B in (2, 4, 32, 128, 256):
+            for T in (2, 8, 64):
+                for P in (1, 3, 10):
+                    for C in (1, 5):
+                        if kind == gpu.UPOLA and (B, T) not in ((4, 8), (128, 2), (256, 64)):
+                            continue
+                        taps, frames = B * P - (B // 2 if P > 1 else 0), 3
+                        ir = rng.uniform(-1, 1, size=(C, taps)).astype(np.float32)
+                        ir /= np.sqrt((ir.astype(np.float64) ** 2).sum(axis=1).max())
+                        sig = rng.uniform(-1, 1, size=(C, B * T * frames)).astype(np.float32)
+                        direct = gpu.Convolver(kind, np.float32, gpu.DIAGONAL, max_blocks=T)
+                        direct.impulse(ir, B)
+                        want = run_bank(direct, sig, B, [T])
+                        direct.close()
+                        framed = gpu.Convolver(kind, np.float32, gpu.DIAGONAL, frame_blocks=T)
+                        framed.impulse(ir, B)
+                        got = run_bank(framed, sig, B, [T])
+                        framed.close()
+                        assert rel_l2(got, want) <= 5e-6, (kind, B, T, P, C, rel_l2(got, want))
+                        if B <= 4:
+                            H = orc.uniform_partition(ir, B)
+                            assert rel_l2(got, orc.convolve_blocks(kind, H, sig)) <= 1e-5, (kind, B, T, P, C)
+
+
 def test_frame_mode_full_size_north_star_shape(gpu, orc):
     # BASELINE config 5 geometry (B = 1024, 2^20 taps -> P = 1024) at bench.py's default frame length T = 256 (L = 512, Q = 4,
     # the cp.async-staged fused kernel). The oracle would need minutes here, so the check is the size-independent property:
