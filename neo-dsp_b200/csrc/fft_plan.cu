@@ -287,7 +287,7 @@ struct rfft_engine
 {
     int order;                   // real size N = 2^order, complex half size M = N/2
     fft_tables<T> tables;        // single-CTA path: M-point plan; split path: M/2-point plan
-    fft_tables<T> tables_full;   // M = 2^max_cta: c2r runs faster as ONE CTA (measured 0.60 vs 0.34-0.47 of HBM peak), r2c as two
+    fft_tables<T> tables_full;   // M = 2^max_cta as ONE CTA: only behind the NEO_B200_R2C_ONE_CTA / NEO_B200_C2R_ONE_CTA knobs
     device_buffer w_n;           // split path: exp(-2 pi i k / N), k < M/2
     large_rfft<T> large;
     bool use_large{false};
@@ -460,6 +460,9 @@ struct rfft_engine
         if (use_split) {
             auto const* wn = w_n.template as<cx<T>>();
             if (order - 1 == k_split_lo) {
+                // measured with the register caps in place: two CTAs 0.48-0.49 of HBM peak, one 8192-point CTA 0.44-0.45
+                static bool const one_cta = std::getenv("NEO_B200_C2R_ONE_CTA") != nullptr;  // tuning knob
+                if (!one_cta) { return launch_c2r_split2<T, k_split_lo - 1>(in, row_len, out, tables.tw(), tables.rtw(), wn, batch, stream); }
                 return launch_c2r<T, k_split_lo>(c2r_plain_io<T, k_split_lo>{in, out, row_len}, tables_full.tw(), tables_full.rtw(), batch,
                                                  stream);
             }
