@@ -298,8 +298,9 @@ constexpr size_t k_max_frame_blocks = 512;
 // forward frame transform -> ring insert -> MAC over the Q second-level partitions -> inverse frame transform, all in ONE kernel with
 // the L values of a bin held in registers between the steps (a thread owns frame bins f = t + e*TN of its bin k before AND after
 // cta_fft::run, so the MAC needs no exchange). Against the three-kernel form this never writes or re-reads the MAC result and never
-// re-reads the frame spectrum it has just produced: per frame 3 S + (filter + old ring slots) bytes instead of 9 S + (filter + ring),
-// S = level-1 spectra of one frame. Diagonal topology, unsplit partition loop (sources == 1, splits == 1).
+// re-reads the frame spectrum it has just produced: with S = the level-1 spectra of one frame (T rows of B bins per channel), a frame
+// step moves 5 S (two frames read, the new ring slot written, T result rows written) + filter + older ring slots, instead of 11 S +
+// filter + the whole ring. Diagonal topology, unsplit partition loop (sources == 1, splits == 1).
 template<typename T, bool NYQ>
 struct frame_fused_io
 {
