@@ -83,6 +83,7 @@ struct conv_engine
     device_buffer frame_tw8;  // stage twiddles of the 8-points-per-thread variant of the long frame transforms
     device_buffer fdl2, filter2, acc2, tickets2, nyq_acc;
     bool fused{false};  // bank with an unsplit partition loop: one kernel per frame step (frame_fused_kernel)
+    frame_knobs knobs;  // environment knobs as they stood when the handle was created
 
     // optional per-phase timing with CUDA events on the handle's stream (bench.py's roofline numbers)
     struct span
@@ -182,7 +183,8 @@ struct conv_engine
             size_t const m2 = size_t(tiles2) << logw;
             splits2       = pick_splits(sms, m2, size_t(parts2));
             NEO_TRY(frame_tables.build(logl, false, stream));
-            if (frame_variant_is_e8(logl, sizeof(T) == 4)) {
+            knobs = frame_knobs::from_env();
+            if (knobs.eight_points(logl, sizeof(T) == 4)) {
                 auto const tw = make_stage_twiddles<T>(logl, 3);
                 NEO_TRY(frame_tw8.reserve(tw.size() * csz));
                 NEO_CUDA_TRY(cudaMemcpyAsync(frame_tw8.ptr, tw.data(), tw.size() * csz, cudaMemcpyHostToDevice, stream));
@@ -362,11 +364,11 @@ struct conv_engine
             frame_fused_io<T, true> nq{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), filter2.template as<cx<T>>(),
                                        acc_w(), nyq_acc.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2),
                                        parts2, int(cfg.partition_begin / size_t(frame)), T(1) / T(2 * frame), out0};
-            status = launch_frame_fused<T, LOGL, true>(nq, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout, stream);
+            status = launch_frame_fused<T, LOGL, true>(nq, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout, stream, knobs);
             if (status == NEO_B200_OK) {
                 frame_fused_io<T, false> io{nq.x1, nq.fdl2, nq.filt2, nq.y1, nq.nyq_acc, fg, nq.new_half, nq.ring2, nq.slot,
                                             nq.parts2, nq.age0, nq.scale, out0};
-                status = launch_frame_fused<T, LOGL, false>(io, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout << logb, stream);
+                status = launch_frame_fused<T, LOGL, false>(io, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout << logb, stream, knobs);
             }
         });
         if (status != NEO_B200_OK) { return status; }
@@ -382,7 +384,7 @@ struct conv_engine
         NEO_TRY(mark_begin(3, stream));
         NEO_DISPATCH_LOGL(logl, {
             frame_fwd_io<T, false> io{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2), chan0};
-            status = launch_frame_fft<T, LOGL, -1>(io, frame_tables.tw(), nchan << logb, stream);
+            status = launch_frame_fft<T, LOGL, -1>(io, frame_tables.tw(), nchan << logb, stream, knobs);
             if (status == NEO_B200_OK) {
                 frame_fwd_io<T, true> nq{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2), chan0};
                 status = launch_frame_fft<T, LOGL, -1>(nq, frame_tables.tw(), nchan, stream);
@@ -434,7 +436,7 @@ struct conv_engine
         NEO_TRY(mark_begin(4, stream));
         NEO_DISPATCH_LOGL(logl, {
             frame_inv_io<T> io{acc2.template as<cx<T>>(), acc_w(), fg, T(1) / T(2 * frame), out0};
-            status = launch_frame_fft<T, LOGL, 1>(io, frame_tables.tw(), nout << logb, stream);
+            status = launch_frame_fft<T, LOGL, 1>(io, frame_tables.tw(), nout << logb, stream, knobs);
         });
         if (status != NEO_B200_OK) { return status; }
         return mark_end(4, stream);

@@ -259,20 +259,26 @@ int launch_frame_fft_g(IO const& io, cx<T> const* tw, size_t units, cudaStream_t
     return check_launch("frame_fft_kernel");
 }
 
-inline int frame_variant()
+// tuning knobs, read once per handle (conv_engine::init) and passed down, so a handle never changes form after its tables are built
+struct frame_knobs
 {
-    static int const v = [] {
-        char const* env = std::getenv("NEO_B200_FRAME_VARIANT");  // tuning knob
-        return env != nullptr ? std::atoi(env) : -1;
-    }();
-    return v;
-}
+    int variant{-1};   // NEO_B200_FRAME_VARIANT: fused-kernel geometry at L >= 256 (float)
+    bool async{true};  // NEO_B200_FRAME_NO_ASYNC clears it: MAC operands straight into registers
+    static frame_knobs from_env()
+    {
+        frame_knobs k;
+        if (char const* v = std::getenv("NEO_B200_FRAME_VARIANT")) { k.variant = std::atoi(v); }
+        k.async = std::getenv("NEO_B200_FRAME_NO_ASYNC") == nullptr;
+        return k;
+    }
+    bool eight_points(int logl, bool is_f32) const { return is_f32 && logl >= 8 && (variant == 2 || variant == 3 || variant == 4); }
+};
 
 template<typename T, int LOGL, int DIR, typename IO>
-int launch_frame_fft(IO const& io, cx<T> const* tw, size_t units, cudaStream_t stream)
+int launch_frame_fft(IO const& io, cx<T> const* tw, size_t units, cudaStream_t stream, frame_knobs const& knobs = {})
 {
     if constexpr (LOGL >= 8) {
-        if (frame_variant() == 1) { return launch_frame_fft_g<T, LOGL, DIR, IO, frame_default_logg<T, LOGL>() - 1>(io, tw, units, stream); }
+        if (knobs.variant == 1) { return launch_frame_fft_g<T, LOGL, DIR, IO, frame_default_logg<T, LOGL>() - 1>(io, tw, units, stream); }
     }
     return launch_frame_fft_g<T, LOGL, DIR, IO, -1>(io, tw, units, stream);
 }
@@ -544,14 +550,8 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
     }
 }
 
-inline bool frame_async_enabled()
-{
-    static bool const v = std::getenv("NEO_B200_FRAME_NO_ASYNC") == nullptr;  // tuning knob
-    return v;
-}
-
 template<typename T, int LOGL, int LOGG, int LOGE_F, int REGCAP, bool NYQ>
-int launch_frame_fused_g(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, size_t units, cudaStream_t stream)
+int launch_frame_fused_g(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, size_t units, cudaStream_t stream, bool async)
 {
     using cfg = frame_cfg<T, LOGL, LOGG, LOGE_F>;
     if constexpr (cfg::THREADS > 1024) { return fail(NEO_B200_ERR_UNSUPPORTED, "frame kernel variant needs %d threads", cfg::THREADS); }
@@ -559,7 +559,7 @@ int launch_frame_fused_g(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, size
         if (units == 0) { return NEO_B200_OK; }
         if constexpr (!NYQ && LOGL >= 6) {
             using ac = frame_async_cfg<T, LOGL, LOGG, LOGE_F>;
-            if (frame_async_enabled() && (1 << io.g.logw) >= cfg::G && units % cfg::G == 0 && ac::SMEM <= 227 * 1024) {
+            if (async && (1 << io.g.logw) >= cfg::G && units % cfg::G == 0 && ac::SMEM <= 227 * 1024) {
                 auto kernel = frame_fused_kernel<T, LOGL, LOGG, LOGE_F, REGCAP, NYQ, true>;
                 NEO_TRY(enable_smem(kernel, ac::SMEM));
                 kernel<<<unsigned(units / cfg::G), cfg::THREADS, ac::SMEM, stream>>>(io, tw, units);
@@ -575,30 +575,26 @@ int launch_frame_fused_g(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, size
     }
 }
 
-// which twiddle table a launch wants: 0 = the transform's default points per thread, 1 = 8 points per thread
-inline bool frame_variant_is_e8(int logl, bool is_f32)
-{
-    int const v = frame_variant();
-    return is_f32 && logl >= 8 && (v == 2 || v == 3 || v == 4);
-}
-
+// tw: stage twiddles of the transform's default points per thread; tw8: of the 8-points-per-thread variants (only when knobs ask)
 template<typename T, int LOGL, bool NYQ>
-int launch_frame_fused(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, cx<T> const* tw8, size_t units, cudaStream_t stream)
+int launch_frame_fused(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, cx<T> const* tw8, size_t units, cudaStream_t stream,
+                       frame_knobs const& knobs)
 {
     constexpr int g0 = frame_default_logg<T, LOGL>();
+    bool const a     = knobs.async;
     if constexpr (sizeof(T) == 4 && LOGL >= 8) {
         constexpr int g16 = LOGL >= 10 ? 3 : 4;  // 16 points per thread: 2^(LOGL-4) threads per bin, <= 512 threads per CTA
-        switch (frame_variant()) {
-            case 1: return launch_frame_fused_g<T, LOGL, g16 - 1, -1, 128, NYQ>(io, tw, units, stream);
-            case 2: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 3 : LOGL >= 9 ? 4 : 4, 3, 64, NYQ>(io, tw8, units, stream);
-            case 3: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 2 : 3, 3, 64, NYQ>(io, tw8, units, stream);
-            case 4: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 2 : 3, 3, 96, NYQ>(io, tw8, units, stream);
-            default: return launch_frame_fused_g<T, LOGL, g16, -1, 128, NYQ>(io, tw, units, stream);
+        switch (knobs.variant) {
+            case 1: return launch_frame_fused_g<T, LOGL, g16 - 1, -1, 128, NYQ>(io, tw, units, stream, a);
+            case 2: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 3 : 4, 3, 64, NYQ>(io, tw8, units, stream, a);
+            case 3: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 2 : 3, 3, 64, NYQ>(io, tw8, units, stream, a);
+            case 4: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 2 : 3, 3, 96, NYQ>(io, tw8, units, stream, a);
+            default: return launch_frame_fused_g<T, LOGL, g16, -1, 128, NYQ>(io, tw, units, stream, a);
         }
     } else if constexpr (frame_cfg<T, LOGL, g0>::THREADS > 512) {
-        return launch_frame_fused_g<T, LOGL, g0 - 1, -1, 128, NYQ>(io, tw, units, stream);
+        return launch_frame_fused_g<T, LOGL, g0 - 1, -1, 128, NYQ>(io, tw, units, stream, a);
     } else {
-        return launch_frame_fused_g<T, LOGL, g0, -1, 128, NYQ>(io, tw, units, stream);
+        return launch_frame_fused_g<T, LOGL, g0, -1, 128, NYQ>(io, tw, units, stream, a);
     }
 }
 

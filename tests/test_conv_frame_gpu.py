@@ -209,6 +209,23 @@ def test_frame_mode_full_size_north_star_shape(gpu, orc):
     conv.close()
 
 
+@pytest.mark.parametrize("knob,value", [(None, None), ("NEO_B200_FRAME_NO_ASYNC", "1"), ("NEO_B200_FRAME_VARIANT", "1"),
+                                        ("NEO_B200_FRAME_VARIANT", "2"), ("NEO_B200_FRAME_VARIANT", "3"), ("NEO_B200_FRAME_VARIANT", "4")])
+def test_fused_frame_kernel_geometries_at_long_frames(gpu, orc, monkeypatch, knob, value):
+    # L = 256 and L = 512 frame transforms: the shipped geometry (16 points per thread, cp.async-staged MAC) and the alternatives the
+    # knobs select when the handle is created (tuning knobs) must all reproduce the reference
+    if knob is not None:
+        monkeypatch.setenv(knob, value)
+    for B, P, T, frames in ((128, 20, 128, 2), (128, 5, 256, 2)):
+        ir, sig = make_case(orc, 2, B * P - 9, B, T * frames)
+        H = orc.uniform_partition(ir, B)
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+        conv.filter(H)
+        got = run_bank(conv, sig, B, [T])
+        assert rel_l2(got, orc.convolve_blocks(0, H, sig)) <= 1e-5, (knob, value, T)
+        conv.close()
+
+
 def test_frame_mode_three_kernel_form_for_banks(gpu, orc, monkeypatch):
     # banks normally take the fused kernel; NEO_B200_FRAME_UNFUSED (read when the handle is created) selects the three-kernel form
     # (frame transform, frame_mac_kernel over several columns per thread, inverse transform) -- same results

@@ -142,4 +142,40 @@ for T in (32, 64):  # frame mode: the contraction becomes Q = P/T streamed rows 
 res["filter_bytes"] = 8 * K * P * O * I
 res["note"] = "T=1: the 2.16 GB filter set streams once per block-step (HBM bound); FDL (34 MB) is L2-resident"
 out["C4"] = res
+# ---- float64: the same kernels instantiated for double (8 points per thread, 64-element tiles) ------------------------------------
+res = {}
+peak = None
+try:
+    peak = json.load(open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")))["hbm_gbs"]
+except Exception:
+    pass
+for order in (10, 12, 14):
+    n = 1 << order
+    batch = (1 << 27) // n
+    xr = torch.rand((batch, n), device="cuda", dtype=torch.float64) * 2 - 1
+    rp = pkg.RFFTPlan(order, "float64")
+    rp.set_stream(stream)
+    spec = torch.empty((batch, n // 2 + 1), dtype=torch.complex128, device="cuda")
+    back = torch.empty_like(xr)
+    ms_f = gpu_time(lambda: rp.rfft(xr, out=spec), reps=10, warm=3)
+    ms_b = gpu_time(lambda: rp.irfft(spec, out=back), reps=10, warm=3)
+    bytes_ = batch * (8 * n + 16 * (n // 2 + 1))
+    res[f"rfft_n{n}"] = {"r2c_gbs": bytes_ / ms_f / 1e6, "c2r_gbs": bytes_ / ms_b / 1e6,
+                         "r2c_frac": bytes_ / ms_f / 1e6 / peak if peak else None, "c2r_frac": bytes_ / ms_b / 1e6 / peak if peak else None}
+    rp.close()
+    del xr, spec, back
+B, L, C = 1024, 1 << 18, 256
+ir = torch.rand((C, L), device="cuda", dtype=torch.float64) * 2 - 1
+ir *= 1.0 / ir.square().sum(dim=1).max().sqrt()
+for frame, T in ((0, 1), (0, 8), (64, 64)):
+    conv = pkg.Convolver(pkg.UPOLS, "float64", pkg.DIAGONAL, max_blocks=T, frame_blocks=frame)
+    conv.set_stream(stream)
+    conv.impulse(ir, B)
+    xin = torch.rand((C, T * B), device="cuda", dtype=torch.float64) * 2 - 1
+    yout = torch.empty_like(xin)
+    ms = gpu_time(lambda: conv(xin, out=yout), reps=20, warm=3)
+    res[("frame" if frame else "T") + str(T)] = {"channel_msamples_s": C * B * T / ms / 1e3, "ms_per_call": ms}
+    conv.close()
+res["bank"] = "256 channels x 2^18-tap IRs, B = 1024 (P = 256), float64"
+out["F64"] = res
 print(json.dumps(out, indent=1))
