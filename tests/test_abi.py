@@ -53,6 +53,37 @@ def test_order_past_max_is_unsupported_like_the_reference(pkg):
         pkg.RFFTPlan(28)
 
 
+def test_convolver_configuration_is_validated_before_any_device_work(pkg):
+    # neo_b200_conv_create checks its configuration first, so the error contract is testable without a GPU
+    def create(**kw):
+        cfg = dict(kind=0, dtype=0, topology=0, outputs=2, inputs=2, block=64, partitions=8, max_blocks=0, partition_begin=0,
+                   partition_end=0, frame_blocks=0)
+        cfg.update(kw)
+        h = ctypes.c_void_p()
+        c = pkg.ConvConfig(*[cfg[name] for name, _ in pkg.ConvConfig._fields_])
+        status = pkg.library().neo_b200_conv_create(ctypes.byref(h), ctypes.byref(c))
+        message = pkg.library().neo_b200_last_error().decode()
+        if status == 0:
+            pkg.library().neo_b200_conv_destroy(h)
+        return status, message
+
+    for kw, needle in (
+        (dict(block=96), "power of two"),
+        (dict(partitions=0), "partitions"),
+        (dict(frame_blocks=3), "frame_blocks"),
+        (dict(frame_blocks=1024), "frame_blocks"),
+        (dict(frame_blocks=4, max_blocks=8), "frame_blocks"),
+        (dict(frame_blocks=4, partition_begin=2, partition_end=8), "multiple of frame_blocks"),
+        (dict(partition_begin=5, partition_end=3), "partition range"),
+        (dict(topology=0, inputs=3), "diagonal"),
+        (dict(kind=7), "kind"),
+    ):
+        status, message = create(**kw)
+        assert status != 0 and needle in message, (kw, message)
+    status, message = create(frame_blocks=4)  # a valid configuration gets as far as the device check
+    assert status == 0 or "no CPU fallback" in message
+
+
 def test_no_cpu_fallback(pkg):
     if pkg.device_count() > 0:
         pytest.skip("a CUDA device is present")
