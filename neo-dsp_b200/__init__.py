@@ -655,6 +655,15 @@ def _c2c(x, n, norm, direction):
     return x if scale == 1.0 else (x * x.real.dtype.type(scale)).astype(x.dtype)
 
 
+def rfftfreq(size: int, inv_sample_rate: float, dtype="float32") -> np.ndarray:
+    """neo::rfftfreq (fft/rfftfreq.hpp:12-29): out[i] = i * (1 / inv_sample_rate) * (1 / size) for i < size, evaluated in `dtype`
+    in the reference's order (host-side index helper, no transform involved)."""
+    real = np.dtype(dtype).type
+    fs = real(1) / real(inv_sample_rate)
+    inv_size = real(1) / real(size)
+    return (np.arange(size).astype(real) * fs * inv_size).astype(real)
+
+
 def fft(x, n=None, norm="backward"):
     return _c2c(x, n, norm, FORWARD)
 

@@ -45,6 +45,15 @@ def test_integer_helpers_need_no_device(pkg):
     assert pkg.library().neo_b200_version().startswith(b"neo_b200")
 
 
+def test_rfftfreq_helper(pkg):
+    import numpy as np
+
+    # fft/rfftfreq.hpp:12-29: index * fs / size over `size` entries
+    got = pkg.rfftfreq(8, 1.0 / 48000.0)
+    assert got.dtype == np.float32 and np.allclose(got, np.arange(8) * 48000.0 / 8)
+    assert np.allclose(pkg.rfftfreq(5, 0.5, "float64"), np.arange(5) * 2.0 / 5)
+
+
 def test_order_past_max_is_unsupported_like_the_reference(pkg):
     # fft_test.cpp:62-67 expects a throw for next_order(max_size()+1)
     with pytest.raises(RuntimeError, match="unsupported order"):
