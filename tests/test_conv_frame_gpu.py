@@ -208,6 +208,16 @@ def test_frame_mode_full_size_north_star_shape(gpu, orc):
         assert np.allclose(out[c], expect, atol=5e-5), (c, d, float(np.abs(out[c] - expect).max()))
     conv.close()
 
+    # and full oracle parity at the same geometry on a 2-channel slice with random impulse responses (2 frames = 512 blocks: the
+    # reference's block-by-block convolver needs a few seconds for that on the CPU)
+    ir, sig = make_case(orc, 2, L, B, 2 * T)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+    conv.impulse(ir, B)
+    got = run_bank(conv, sig, B, [T])
+    conv.close()
+    want = orc.convolve_blocks(0, orc.uniform_partition(ir, B), sig)
+    assert rel_l2(got, want) <= 1e-5, rel_l2(got, want)
+
 
 @pytest.mark.parametrize("knob,value", [(None, None), ("NEO_B200_FRAME_NO_ASYNC", "1"), ("NEO_B200_FRAME_VARIANT", "1"),
                                         ("NEO_B200_FRAME_VARIANT", "2"), ("NEO_B200_FRAME_VARIANT", "3"), ("NEO_B200_FRAME_VARIANT", "4")])
