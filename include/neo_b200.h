@@ -228,6 +228,11 @@ typedef struct neo_b200_conv_config
      * 2T, ceil(P/T) streamed rows): HBM-bound instead of FP32-bound for long filters. Same results up to rounding; max_blocks is
      * forced to T; a sharded handle needs partition_begin % T == 0. */
     size_t frame_blocks;
+    /* partition-sharded handles only. 0: the handle receives the live input and reaches back partition_begin blocks into its own
+     * delay line of spectra. != 0: the CALLER delays the time-domain input of this handle by partition_begin blocks (zeros first);
+     * the handle then pairs its first partition with the newest spectrum and keeps a ring of only its own partitions -- what a
+     * multi-device bank does (neo_b200_bank_*), exact because the delay line is linear (fdl_index.hpp:24-36). */
+    size_t input_delayed;
 } neo_b200_conv_config;
 
 NEO_B200_API int neo_b200_conv_create(neo_b200_conv** conv, neo_b200_conv_config const* config);
@@ -254,7 +259,9 @@ NEO_B200_API int neo_b200_conv_process(neo_b200_conv* conv, void const* in, void
 NEO_B200_API int neo_b200_conv_forward(neo_b200_conv* conv, void const* in, size_t blocks, int memspace);
 /* the same for the channel range [first, first+count) only (diagonal topology, DEVICE memory, `in` is still the whole
  * [inputs][blocks*B] array): lets a caller overlap the reduction of one channel group with the MAC of the next.
- * Every channel must be covered exactly once per call; pass final != 0 with the last range (the ring position then advances). */
+ * The ranges of one call tile the bank in ascending order (the first starts at channel 0, each next one where the previous ended),
+ * all with the same `blocks`; pass final != 0 with the range that ends at the last channel (the ring position then advances).
+ * Anything else is rejected, and neo_b200_conv_process / _forward are rejected while such a call is in progress. */
 NEO_B200_API int neo_b200_conv_forward_range(
     neo_b200_conv* conv, void const* in, size_t blocks, size_t first, size_t count, int final);
 /* device pointer of the partial spectra of the most recent forward / forward_range call (the call in progress, if its final
@@ -274,6 +281,84 @@ NEO_B200_API int neo_b200_conv_profile_enable(neo_b200_conv* conv, int enable);
 NEO_B200_API int neo_b200_conv_profile_read(neo_b200_conv* conv, double* phase_ms, uint64_t* mac_launches);
 /* bytes of device memory held by the handle (filter + FDL + scratch) */
 NEO_B200_API size_t neo_b200_conv_device_bytes(neo_b200_conv const* conv);
+
+/* ---- multi-GPU bank: one convolver bank spread over the GPUs of one box -----------------------------------------------------------
+ * What a caller of the reference does with N host threads -- one private convolver per channel
+ * (convolution/uniform_partitioned_convolver.hpp:28-34; extra/cli/src/convolver.cpp:37-40 builds one per channel) -- and, for one very
+ * long impulse response, what the linearity of the delay line allows (convolution/fdl_index.hpp:24-36: partition p pairs with the
+ * spectrum of p blocks ago): N = channel_groups x partition_shards ranks, rank = group * partition_shards + shard.
+ *   - rank (g, s) holds partitions [lo_s, hi_s) of the filters of channel group g (matrix topology: OUTPUT channel group g) and yields
+ *     partial spectra; the partition_shards partial spectra of a group are summed over NVLink and every rank finishes (c2r + overlap)
+ *     1/N of the bank's output rows;
+ *   - every rank moves only 1/N of the input rows and 1/N of the output rows across ITS host link; ranks that need the same input
+ *     rows exchange them over NVLink;
+ *   - results are those of the single-device handle up to float rounding of the split sum (same tolerance as the reference parity).
+ * Two ways to build it:
+ *   neo_b200_bank_create       every rank lives in the calling process (a C++ host with N GPUs); the devices exchange data through
+ *                              peer-mapped memory and the reduction is fused into the c2r kernel. The same device may be named
+ *                              more than once.
+ *   neo_b200_bank_create_rank  one rank per process (torchrun / MPI); data exchange through NCCL (ncclAllGather of input rows,
+ *                              ncclReduceScatter of partial spectra), loaded at run time from libnccl.so.2 (or $NEO_B200_NCCL_LIB).
+ *                              Rank 0 calls neo_b200_bank_unique_id and hands the 128 bytes to every rank out of band.
+ * Row pointers: `in_rows[l]` / `out_rows[l]` belong to LOCAL rank l (0 .. neo_b200_bank_local_ranks-1) and point at the rows that rank
+ * moves: [in_count][blocks*B] / [out_count][blocks*B] reals, rows in_first.. / out_first.. of the bank (neo_b200_bank_local_rank).
+ * With every rank local and one [channels][blocks*B] array, in_rows[l] = array + in_first_l * blocks * B. HOST memory should be pinned
+ * for the copies to overlap; DEVICE pointers must live on the rank's own device. */
+typedef struct neo_b200_bank neo_b200_bank;
+
+typedef struct neo_b200_bank_layout
+{
+    size_t channel_groups;    /* Gc */
+    size_t partition_shards;  /* Gp, at most 8; in frame mode shards start on frame boundaries of the partition axis */
+} neo_b200_bank_layout;
+
+typedef struct neo_b200_bank_rank_info
+{
+    int rank;                 /* global rank = channel_group * partition_shards + partition_shard */
+    int device;               /* CUDA device (-1 from neo_b200_bank_layout_info) */
+    size_t channel_group, partition_shard;
+    size_t group_first, group_count;          /* channels (matrix: outputs) whose filters the rank holds */
+    size_t in_first, in_count;                /* input rows the rank brings in */
+    size_t out_first, out_count;              /* output rows the rank finishes and returns */
+    size_t partition_begin, partition_end;    /* partitions of every filter of the group held by the rank */
+    size_t delay_blocks;                      /* frame mode: the rank transforms its input this many blocks late instead of keeping a
+                                                 deeper ring of spectra (neo_b200_conv_config::input_delayed) */
+} neo_b200_bank_rank_info;
+
+#define NEO_B200_BANK_ID_BYTES 128
+NEO_B200_API int neo_b200_bank_unique_id(void* id /* NEO_B200_BANK_ID_BYTES */);
+/* config: the WHOLE bank (outputs, inputs, partitions of the whole filter; partition_begin/end = 0). outputs and inputs must be
+ * multiples of the number of ranks. */
+NEO_B200_API int neo_b200_bank_create(neo_b200_bank** bank, neo_b200_conv_config const* config, neo_b200_bank_layout const* layout,
+                                      int const* devices, size_t n_devices);
+NEO_B200_API int neo_b200_bank_create_rank(neo_b200_bank** bank, neo_b200_conv_config const* config, neo_b200_bank_layout const* layout,
+                                           int device, int rank, int world, void const* unique_id);
+NEO_B200_API void neo_b200_bank_destroy(neo_b200_bank* bank);
+NEO_B200_API int neo_b200_bank_local_ranks(neo_b200_bank const* bank, size_t* count);
+NEO_B200_API int neo_b200_bank_local_rank(neo_b200_bank const* bank, size_t local_index, neo_b200_bank_rank_info* info);
+/* the same facts for any rank of a layout, without building anything (lets a launcher prepare each rank's rows and filters) */
+NEO_B200_API int neo_b200_bank_layout_info(neo_b200_conv_config const* config, neo_b200_bank_layout const* layout, size_t rank,
+                                           neo_b200_bank_rank_info* info);
+
+/* `convolver.filter(...)` for every convolver of the bank (uniform_partitioned_convolver.hpp:38-45). per local rank: the impulse
+ * responses / partitions of ITS channel group, all P partitions of them (the rank picks its own range): DIAGONAL [group_count][taps]
+ * or [group_count][P][B+1], MATRIX [group_count][inputs][taps] or [group_count][inputs][P][B+1]; HOST, or DEVICE on the rank's device. */
+NEO_B200_API int neo_b200_bank_set_impulse(neo_b200_bank* bank, void const* const* ir_per_rank, size_t taps, int memspace);
+NEO_B200_API int neo_b200_bank_set_filter(neo_b200_bank* bank, void const* const* h_per_rank, int memspace);
+NEO_B200_API int neo_b200_bank_reset(neo_b200_bank* bank);
+
+/* `convolver(block)` for every channel of the bank, `blocks` blocks per call (uniform_partitioned_convolver.hpp:48-65).
+ * submit only enqueues; wait returns when the OLDEST outstanding submit has delivered its output rows. Up to two submits may be
+ * outstanding (a third waits inside submit), so the input copy of step i+1 and the output copy of step i-1 overlap the kernels of
+ * step i. In rank-per-process banks every rank must make the same sequence of calls. process = submit + wait until idle. */
+NEO_B200_API int neo_b200_bank_submit(neo_b200_bank* bank, void const* const* in_rows, void* const* out_rows, size_t blocks, int memspace);
+NEO_B200_API int neo_b200_bank_wait(neo_b200_bank* bank);
+NEO_B200_API int neo_b200_bank_process(neo_b200_bank* bank, void const* const* in_rows, void* const* out_rows, size_t blocks, int memspace);
+
+/* per-phase device time of one local rank (see neo_b200_conv_profile_read) and its device memory */
+NEO_B200_API int neo_b200_bank_profile_enable(neo_b200_bank* bank, int enable);
+NEO_B200_API int neo_b200_bank_profile_read(neo_b200_bank* bank, size_t local_index, double* phase_ms, uint64_t* mac_launches);
+NEO_B200_API size_t neo_b200_bank_device_bytes(neo_b200_bank const* bank, size_t local_index);
 
 #ifdef __cplusplus
 }

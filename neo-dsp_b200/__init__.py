@@ -44,8 +44,34 @@ class ConvConfig(C.Structure):
         ("partition_begin", _sz),
         ("partition_end", _sz),
         ("frame_blocks", _sz),
+        ("input_delayed", _sz),
     ]
 
+
+class BankLayout(C.Structure):
+    _fields_ = [("channel_groups", _sz), ("partition_shards", _sz)]
+
+
+class BankRankInfo(C.Structure):
+    _fields_ = [
+        ("rank", _i),
+        ("device", _i),
+        ("channel_group", _sz),
+        ("partition_shard", _sz),
+        ("group_first", _sz),
+        ("group_count", _sz),
+        ("in_first", _sz),
+        ("in_count", _sz),
+        ("out_first", _sz),
+        ("out_count", _sz),
+        ("partition_begin", _sz),
+        ("partition_end", _sz),
+        ("delay_blocks", _sz),
+    ]
+
+
+BANK_ID_BYTES = 128
+_pp = C.POINTER(_vp)
 
 # name -> (restype, argtypes): exactly the entry points include/neo_b200.h declares
 SIGNATURES = {
@@ -111,6 +137,22 @@ SIGNATURES = {
     "neo_b200_conv_profile_enable": (_i, [_vp, _i]),
     "neo_b200_conv_profile_read": (_i, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "neo_b200_conv_device_bytes": (_sz, [_vp]),
+    "neo_b200_bank_unique_id": (_i, [_vp]),
+    "neo_b200_bank_create": (_i, [C.POINTER(_vp), C.POINTER(ConvConfig), C.POINTER(BankLayout), C.POINTER(_i), _sz]),
+    "neo_b200_bank_create_rank": (_i, [C.POINTER(_vp), C.POINTER(ConvConfig), C.POINTER(BankLayout), _i, _i, _i, _vp]),
+    "neo_b200_bank_destroy": (None, [_vp]),
+    "neo_b200_bank_local_ranks": (_i, [_vp, C.POINTER(_sz)]),
+    "neo_b200_bank_local_rank": (_i, [_vp, _sz, C.POINTER(BankRankInfo)]),
+    "neo_b200_bank_layout_info": (_i, [C.POINTER(ConvConfig), C.POINTER(BankLayout), _sz, C.POINTER(BankRankInfo)]),
+    "neo_b200_bank_set_impulse": (_i, [_vp, _pp, _sz, _i]),
+    "neo_b200_bank_set_filter": (_i, [_vp, _pp, _i]),
+    "neo_b200_bank_reset": (_i, [_vp]),
+    "neo_b200_bank_submit": (_i, [_vp, _pp, _pp, _sz, _i]),
+    "neo_b200_bank_wait": (_i, [_vp]),
+    "neo_b200_bank_process": (_i, [_vp, _pp, _pp, _sz, _i]),
+    "neo_b200_bank_profile_enable": (_i, [_vp, _i]),
+    "neo_b200_bank_profile_read": (_i, [_vp, _sz, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "neo_b200_bank_device_bytes": (_sz, [_vp, _sz]),
 }
 
 _lib = None
@@ -613,6 +655,150 @@ class Convolver:
     def close(self) -> None:
         if self._h:
             library().neo_b200_conv_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def bank_unique_id() -> bytes:
+    """The 128-byte id rank 0 creates and hands to every rank of a rank-per-process Bank (out of band: torch.distributed, MPI ...)."""
+    buf = C.create_string_buffer(BANK_ID_BYTES)
+    _check(library().neo_b200_bank_unique_id(buf))
+    return bytes(buf.raw)
+
+
+def _info_dict(info: BankRankInfo) -> dict:
+    return {name: int(getattr(info, name)) for name, _ in BankRankInfo._fields_}
+
+
+class Bank:
+    """One convolver bank spread over the GPUs of one box (neo_b200_bank_*, include/neo_b200.h): `layout = (channel_groups,
+    partition_shards)`, rank = group * partition_shards + shard.
+
+    All ranks in this process:  Bank(..., layout=(Gc, Gp), devices=[0, 1, ...])   (peer-memory transport)
+    One rank per process:       Bank(..., layout=(Gc, Gp), rank=r, world=N, unique_id=id, device=local)   (NCCL transport)
+
+    `ranks` lists what each LOCAL rank holds and moves (BankRankInfo as dicts). Buffers: one array for the whole process
+    ([rows of all local ranks][T*B], local ranks ascending) or a list with one array per local rank."""
+
+    def __init__(self, kind: int, dtype, topology: int, outputs: int, inputs: int, block: int, partitions: int, max_blocks: int = 1,
+                 frame_blocks: int = 0, layout=(1, 1), devices=None, rank=None, world=None, unique_id=None, device=None):
+        self.real = _REAL_OF[str(np.dtype(dtype))]
+        self.topology = topology
+        inputs = outputs if topology == DIAGONAL else inputs
+        self.cfg = ConvConfig(kind, _DTYPE_CODE[self.real], topology, outputs, inputs, block, partitions, frame_blocks or max_blocks, 0, 0,
+                              frame_blocks, 0)
+        self.layout = BankLayout(int(layout[0]), int(layout[1]))
+        self._h = _vp()
+        lib = library()
+        if devices is not None:
+            dev = (_i * len(devices))(*[int(d) for d in devices])
+            _check(lib.neo_b200_bank_create(C.byref(self._h), C.byref(self.cfg), C.byref(self.layout), dev, len(devices)))
+        else:
+            uid = C.create_string_buffer(unique_id, BANK_ID_BYTES) if unique_id is not None else None
+            _check(lib.neo_b200_bank_create_rank(C.byref(self._h), C.byref(self.cfg), C.byref(self.layout), int(device or 0), int(rank),
+                                                 int(world), uid))
+        n = _sz(0)
+        _check(lib.neo_b200_bank_local_ranks(self._h, C.byref(n)))
+        self.ranks = []
+        for l in range(int(n.value)):
+            info = BankRankInfo()
+            _check(lib.neo_b200_bank_local_rank(self._h, l, C.byref(info)))
+            self.ranks.append(_info_dict(info))
+
+    @staticmethod
+    def layout_info(kind, dtype, topology, outputs, inputs, block, partitions, max_blocks, frame_blocks, layout, rank: int) -> dict:
+        real = _REAL_OF[str(np.dtype(dtype))]
+        inputs = outputs if topology == DIAGONAL else inputs
+        cfg = ConvConfig(kind, _DTYPE_CODE[real], topology, outputs, inputs, block, partitions, frame_blocks or max_blocks, 0, 0, frame_blocks, 0)
+        lay = BankLayout(int(layout[0]), int(layout[1]))
+        info = BankRankInfo()
+        _check(library().neo_b200_bank_layout_info(C.byref(cfg), C.byref(lay), rank, C.byref(info)))
+        return _info_dict(info)
+
+    def _per_rank(self, arrays, key_first: str, key_count: str, what: str):
+        """one pointer per local rank from a list of arrays, or from one array holding the rows of all local ranks in rank order"""
+        if isinstance(arrays, (list, tuple)):
+            if len(arrays) != len(self.ranks):
+                raise ValueError(f"{what}: expected {len(self.ranks)} arrays, one per local rank")
+            for a, r in zip(arrays, self.ranks):
+                if a.shape[0] != r[key_count]:
+                    raise ValueError(f"{what}: rank {r['rank']} moves {r[key_count]} rows, got {a.shape[0]}")
+            return (_vp * len(arrays))(*[_ptr(a) for a in arrays]), _space(arrays[0]), arrays
+        total = sum(r[key_count] for r in self.ranks)
+        if arrays.shape[0] != total:
+            raise ValueError(f"{what}: expected {total} rows (those of the local ranks), got {arrays.shape[0]}")
+        if _is_device(arrays) and len(self.ranks) > 1:
+            raise ValueError(f"{what}: device buffers of a multi-rank process must be given per rank (each on its own device)")
+        base, row_bytes = _ptr(arrays), int(np.prod(arrays.shape[1:])) * (4 if self.real == "float32" else 8) * (2 if "complex" in _dtype_name(arrays) else 1)
+        first0 = self.ranks[0][key_first]
+        ptrs = [base + (r[key_first] - first0) * row_bytes for r in self.ranks]
+        return (_vp * len(ptrs))(*ptrs), _space(arrays), arrays
+
+    def impulse(self, ir) -> None:
+        """ir: per local rank the impulse responses of ITS channel group ([group_count][taps] / [group_count][inputs][taps]), or one
+        array with the groups of all local ranks' ... one entry PER RANK (ranks of the same group repeat the group's rows)."""
+        arrs = ir if isinstance(ir, (list, tuple)) else [ir]
+        if len(arrs) != len(self.ranks):
+            raise ValueError(f"expected {len(self.ranks)} impulse-response arrays, one per local rank")
+        taps = int(arrs[0].shape[-1])
+        ptrs = (_vp * len(arrs))(*[_ptr(a) for a in arrs])
+        _check(library().neo_b200_bank_set_impulse(self._h, ptrs, taps, _space(arrs[0])))
+
+    def impulse_global(self, ir) -> None:
+        """ir: the impulse responses of the WHOLE bank on the host ([channels][taps] / [outputs][inputs][taps]); every local rank takes
+        its group's rows."""
+        self.impulse([np.ascontiguousarray(ir[r["group_first"] : r["group_first"] + r["group_count"]]) for r in self.ranks])
+
+    def filter_global(self, H) -> None:
+        arrs = [np.ascontiguousarray(H[r["group_first"] : r["group_first"] + r["group_count"]]) for r in self.ranks]
+        ptrs = (_vp * len(arrs))(*[_ptr(a) for a in arrs])
+        _check(library().neo_b200_bank_set_filter(self._h, ptrs, HOST))
+
+    def reset(self) -> None:
+        _check(library().neo_b200_bank_reset(self._h))
+
+    def submit(self, x, out) -> None:
+        first = x[0] if isinstance(x, (list, tuple)) else x
+        blocks = int(first.shape[1]) // int(self.cfg.block)
+        xin, space, keep_x = self._per_rank(x, "in_first", "in_count", "input")
+        yout, space_o, keep_y = self._per_rank(out, "out_first", "out_count", "output")
+        if space != space_o:
+            raise ValueError("input and output must live in the same memory space")
+        self._keep = (keep_x, keep_y, getattr(self, "_keep", None) and self._keep[:2])  # buffers of the steps in flight stay alive
+        _check(library().neo_b200_bank_submit(self._h, xin, yout, blocks, space))
+
+    def wait(self) -> None:
+        _check(library().neo_b200_bank_wait(self._h))
+
+    def __call__(self, x, out):
+        first = x[0] if isinstance(x, (list, tuple)) else x
+        blocks = int(first.shape[1]) // int(self.cfg.block)
+        xin, space, _ = self._per_rank(x, "in_first", "in_count", "input")
+        yout, _, _ = self._per_rank(out, "out_first", "out_count", "output")
+        _check(library().neo_b200_bank_process(self._h, xin, yout, blocks, space))
+        return out
+
+    def profile(self, enable: bool) -> None:
+        _check(library().neo_b200_bank_profile_enable(self._h, int(enable)))
+
+    def profile_read(self, local_index: int = 0):
+        """(ms_r2c, ms_mac, ms_c2r, ms_frame_forward, ms_frame_inverse, mac_launches) of one local rank since the last read"""
+        ms = (C.c_double * 5)()
+        n = C.c_uint64(0)
+        _check(library().neo_b200_bank_profile_read(self._h, local_index, ms, C.byref(n)))
+        return float(ms[0]), float(ms[1]), float(ms[2]), float(ms[3]), float(ms[4]), int(n.value)
+
+    def device_bytes(self, local_index: int = 0) -> int:
+        return int(library().neo_b200_bank_device_bytes(self._h, local_index))
+
+    def close(self) -> None:
+        if self._h:
+            library().neo_b200_bank_destroy(self._h)
             self._h = _vp()
 
     def __del__(self):

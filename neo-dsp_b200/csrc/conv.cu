@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <memory>
+#include <type_traits>
 #include <vector>
 
 namespace neo_b200 {
@@ -55,6 +56,8 @@ struct conv_engine
     int logb{0};
     int m{0};           // B
     int parts{0};       // local partitions
+    size_t age0{0};     // age (in blocks) of the first local partition as THIS handle sees its input: partition_begin, or 0 when the
+                        // caller feeds the input already delayed by partition_begin blocks (config.input_delayed)
     int ring{0};
     int sources{1};
     int splits{1};
@@ -62,14 +65,14 @@ struct conv_engine
     size_t filters{0};  // outputs * sources
     size_t write_pos{0};
     bool has_filter{false};
-    int tail_flip{0};
 
     fft_tables<T> tables;
-    device_buffer filter, fdl, prev[2], tail[2], acc, acc_alt, ola_y, stage_in, stage_out, stage_filter, tickets;
+    device_buffer filter, fdl, prev[2], tail, acc, acc_alt, ola_y, stage_in, stage_out, stage_filter, tickets;
     // partition-sharded handles alternate between two partial-spectra buffers, so the reduction of call i (NCCL reads the buffer
     // neo_b200_conv_spectra returned) may still be running while call i+1 writes the other one
     int acc_cur{0}, acc_last{0};
     bool in_call{false};  // a forward_range call has started and its final range has not been seen yet
+    size_t range_next{0}, range_blocks{0};  // ... the channel its next range must start at, and its block count
     cx<T>* acc_w() const { return (acc_cur != 0 ? acc_alt : acc).template as<cx<T>>(); }
     void* acc_r() const { return in_call ? static_cast<void*>(acc_w()) : (acc_last != 0 ? acc_alt : acc).ptr; }
     int prev_flip{0};  // prev[prev_flip] holds the last block of the previous call
@@ -95,13 +98,44 @@ struct conv_engine
     std::vector<span> spans[k_phases];  // 0 r2c + FDL insert, 1 MAC, 2 c2r, 3 frame transform forward, 4 frame transform inverse
     std::uint64_t mac_launches{0};
 
+    // event pairs are recycled through `pool`: nothing is created inside a steady-state timed loop, nothing leaks when the caller
+    // never reads, and whatever is left is destroyed with the engine
+    std::vector<span> pool;
+    double folded_ms[k_phases] = {0, 0, 0, 0, 0};
+    static constexpr size_t k_max_open_spans = 4096;
+
+    ~conv_engine()
+    {
+        for (auto& list : spans) {
+            for (auto& s : list) { pool.push_back(s); }
+        }
+        for (auto& s : pool) {
+            cudaEventDestroy(s.begin);
+            cudaEventDestroy(s.end);
+        }
+    }
+
     int mark_begin(int phase, cudaStream_t stream)
     {
         if (!profiling) { return NEO_B200_OK; }
+        if (spans[phase].size() >= k_max_open_spans) { NEO_TRY(fold_spans(stream)); }  // a caller that never reads: bounded memory
         span s{};
-        NEO_CUDA_TRY(cudaEventCreate(&s.begin));
-        NEO_CUDA_TRY(cudaEventCreate(&s.end));
-        NEO_CUDA_TRY(cudaEventRecord(s.begin, stream));
+        if (!pool.empty()) {
+            s = pool.back();
+            pool.pop_back();
+        } else {
+            NEO_CUDA_TRY(cudaEventCreate(&s.begin));
+            cudaError_t const err = cudaEventCreate(&s.end);
+            if (err != cudaSuccess) {
+                cudaEventDestroy(s.begin);
+                return fail(NEO_B200_ERR_CUDA, "cudaEventCreate: %s", cudaGetErrorString(err));
+            }
+        }
+        cudaError_t const err = cudaEventRecord(s.begin, stream);
+        if (err != cudaSuccess) {
+            pool.push_back(s);
+            return fail(NEO_B200_ERR_CUDA, "cudaEventRecord: %s", cudaGetErrorString(err));
+        }
         spans[phase].push_back(s);
         return NEO_B200_OK;
     }
@@ -113,19 +147,28 @@ struct conv_engine
         return NEO_B200_OK;
     }
 
-    int read_profile(double* ms, std::uint64_t* launches, cudaStream_t stream)
+    // accumulate every finished span into folded_ms and recycle its events
+    int fold_spans(cudaStream_t stream)
     {
         NEO_CUDA_TRY(cudaStreamSynchronize(stream));
         for (int p = 0; p < k_phases; ++p) {
-            ms[p] = 0.0;
             for (auto& s : spans[p]) {
                 float t = 0.f;
-                NEO_CUDA_TRY(cudaEventElapsedTime(&t, s.begin, s.end));
-                ms[p] += double(t);
-                cudaEventDestroy(s.begin);
-                cudaEventDestroy(s.end);
+                if (cudaEventElapsedTime(&t, s.begin, s.end) == cudaSuccess) { folded_ms[p] += double(t); }
+                pool.push_back(s);
             }
             spans[p].clear();
+        }
+        (void)cudaGetLastError();
+        return NEO_B200_OK;
+    }
+
+    int read_profile(double* ms, std::uint64_t* launches, cudaStream_t stream)
+    {
+        NEO_TRY(fold_spans(stream));
+        for (int p = 0; p < k_phases; ++p) {
+            ms[p]        = folded_ms[p];
+            folded_ms[p] = 0.0;
         }
         *launches    = mac_launches;
         mac_launches = 0;
@@ -134,7 +177,7 @@ struct conv_engine
 
     size_t device_bytes() const
     {
-        return filter.bytes + fdl.bytes + prev[0].bytes + prev[1].bytes + tail[0].bytes + tail[1].bytes + acc.bytes + acc_alt.bytes + ola_y.bytes + stage_in.bytes
+        return filter.bytes + fdl.bytes + prev[0].bytes + prev[1].bytes + tail.bytes + acc.bytes + acc_alt.bytes + ola_y.bytes + stage_in.bytes
              + stage_out.bytes + stage_filter.bytes + fdl2.bytes + filter2.bytes + acc2.bytes + nyq_acc.bytes;
     }
 
@@ -145,7 +188,8 @@ struct conv_engine
         logb    = int(log2_exact(c.block));
         parts   = int(c.partition_end - c.partition_begin);
         frame   = int(c.frame_blocks);
-        ring    = frame > 0 ? 2 * frame : int(c.partition_end + c.max_blocks - 1);
+        age0    = c.input_delayed != 0 ? 0 : c.partition_begin;
+        ring    = frame > 0 ? 2 * frame : int(age0 + size_t(parts) + c.max_blocks - 1);
         sources = c.topology == NEO_B200_MATRIX ? int(c.inputs) : 1;
         filters = c.outputs * size_t(sources);
         logw    = std::min(logb, int(log2_exact(size_t(tile_width<T>()))));
@@ -158,8 +202,7 @@ struct conv_engine
         NEO_TRY(prev[0].reserve(c.inputs * m * sizeof(T)));
         NEO_TRY(prev[1].reserve(c.inputs * m * sizeof(T)));
         if (c.kind == NEO_B200_UPOLA) {
-            NEO_TRY(tail[0].reserve(c.outputs * m * sizeof(T)));
-            NEO_TRY(tail[1].reserve(c.outputs * m * sizeof(T)));
+            NEO_TRY(tail.reserve(c.outputs * m * sizeof(T)));
             NEO_TRY(ola_y.reserve(c.outputs * c.max_blocks * 2 * m * sizeof(T)));
         }
         int sms = 148;
@@ -178,7 +221,7 @@ struct conv_engine
             int const w   = 1 << logw;
             logl          = int(log2_exact(size_t(len)));
             tiles2        = nt * len + (len + w - 1) / w;
-            ring2         = int((c.partition_end + size_t(frame) - 1) / size_t(frame));
+            ring2         = int((age0 + size_t(parts) + size_t(frame) - 1) / size_t(frame));
             parts2        = (parts + frame - 1) / frame;
             size_t const m2 = size_t(tiles2) << logw;
             splits2       = pick_splits(sms, m2, size_t(parts2));
@@ -217,15 +260,14 @@ struct conv_engine
         NEO_CUDA_TRY(cudaMemsetAsync(prev[0].ptr, 0, prev[0].bytes, stream));
         NEO_CUDA_TRY(cudaMemsetAsync(prev[1].ptr, 0, prev[1].bytes, stream));
         prev_flip = 0;
-        if (tail[0].ptr != nullptr) {
-            NEO_CUDA_TRY(cudaMemsetAsync(tail[0].ptr, 0, tail[0].bytes, stream));
-            NEO_CUDA_TRY(cudaMemsetAsync(tail[1].ptr, 0, tail[1].bytes, stream));
-        }
+        if (tail.ptr != nullptr) { NEO_CUDA_TRY(cudaMemsetAsync(tail.ptr, 0, tail.bytes, stream)); }
         if (fdl2.ptr != nullptr) { NEO_CUDA_TRY(cudaMemsetAsync(fdl2.ptr, 0, fdl2.bytes, stream)); }
         write_pos  = 0;
         write_pos2 = 0;
         x1_half    = 0;
-        tail_flip  = 0;
+        in_call    = false;  // a reset in the middle of a grouped call abandons it
+        range_next = range_blocks = 0;
+        acc_cur = acc_last = 0;
         return NEO_B200_OK;
     }
 
@@ -363,7 +405,7 @@ struct conv_engine
         NEO_DISPATCH_LOGL(logl, {
             frame_fused_io<T, true> nq{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), filter2.template as<cx<T>>(),
                                        acc_w(), nyq_acc.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2),
-                                       parts2, int(cfg.partition_begin / size_t(frame)), T(1) / T(2 * frame), out0};
+                                       parts2, int(age0 / size_t(frame)), T(1) / T(2 * frame), out0};
             status = launch_frame_fused<T, LOGL, true>(nq, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout, stream, knobs);
             if (status == NEO_B200_OK) {
                 frame_fused_io<T, false> io{nq.x1, nq.fdl2, nq.filt2, nq.y1, nq.nyq_acc, fg, nq.new_half, nq.ring2, nq.slot,
@@ -405,7 +447,7 @@ struct conv_engine
         g.nt          = tiles2;
         g.ring        = ring2;
         g.parts       = parts2;
-        g.age0        = int(cfg.partition_begin / size_t(frame));
+        g.age0        = int(age0 / size_t(frame));
         g.sources     = sources;
         g.diagonal    = cfg.topology == NEO_B200_DIAGONAL ? 1 : 0;
         g.wp          = int(write_pos2);
@@ -452,7 +494,7 @@ struct conv_engine
         g.nt        = nt;
         g.ring      = ring;
         g.parts     = parts;
-        g.age0      = int(cfg.partition_begin);
+        g.age0      = int(age0);
         g.sources   = sources;
         g.diagonal  = cfg.topology == NEO_B200_DIAGONAL ? 1 : 0;
         g.blocks    = int(blocks);
@@ -564,21 +606,44 @@ struct conv_engine
     int inverse(cx<T> const* spectra, size_t /*plane*/, int /*nsplits*/, T* out, size_t out_stride, size_t first, size_t count,
                 size_t blocks, cudaStream_t stream)
     {
+        cx<T> const* one[1] = {spectra};
+        return inverse_sum(one, 1, out, out_stride, first, count, blocks, stream);
+    }
+
+    // the same for the sum of `nsrc` partial spectra buffers (partition shards of a multi-device bank; peer-mapped pointers are
+    // read over NVLink inside the c2r kernel: reduction and inverse transform are one pass)
+    int inverse_sum(cx<T> const* const* srcs, int nsrc, T* out, size_t out_stride, size_t first, size_t count, size_t blocks,
+                    cudaStream_t stream)
+    {
         bool const ola = cfg.kind == NEO_B200_UPOLA;
         T* const dst   = ola ? ola_y.template as<T>() : out;
         int status     = NEO_B200_ERR_UNSUPPORTED;
+        if (nsrc < 1 || nsrc > k_bank_max_shards) { return fail(NEO_B200_ERR_INVALID, "bad number of partial spectra %d", nsrc); }
         NEO_TRY(mark_begin(2, stream));
         NEO_DISPATCH_LOGM(T, logb, {
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
-                conv_c2r_io<T, LOGM> io{spectra, int(blocks), dst, out_stride, T(1) / T(2 * m), ola ? 1 : 0};
-                status = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
+                if (nsrc == 1) {
+                    conv_c2r_io<T, LOGM> io{srcs[0], int(blocks), dst, out_stride, T(1) / T(2 * m), ola ? 1 : 0};
+                    status = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
+                } else {
+                    conv_c2r_sum_io<T, LOGM> io{};
+                    for (int j = 0; j < nsrc; ++j) { io.src[j] = srcs[j]; }
+                    io.nsrc        = nsrc;
+                    io.blocks      = int(blocks);
+                    io.out         = dst;
+                    io.out_stride  = out_stride;
+                    io.scale       = T(1) / T(2 * m);
+                    io.overlap_add = ola ? 1 : 0;
+                    status         = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
+                }
             }
         });
         if (status != NEO_B200_OK) { return status; }
         if (ola) {
-            dim3 const grid(unsigned((m + 255) / 256), unsigned(blocks), unsigned(count));
-            ola_combine_kernel<T><<<grid, 256, 0, stream>>>(ola_y.template as<T>(), tail[tail_flip].template as<T>(),
-                                                            tail[tail_flip ^ 1].template as<T>(), out, out_stride, m, int(blocks), first);
+            // the tail belongs to a channel and is updated in place: any number of inverse calls over disjoint channel ranges
+            // may finish one step (overlap_add.hpp:103-106)
+            dim3 const grid(unsigned((m + 255) / 256), unsigned(count));
+            ola_combine_kernel<T><<<grid, 256, 0, stream>>>(ola_y.template as<T>(), tail.template as<T>(), out, out_stride, m, int(blocks), first);
             NEO_TRY(check_launch("ola_combine_kernel"));
         }
         NEO_TRY(mark_end(2, stream));
@@ -670,6 +735,8 @@ struct neo_b200_conv
     }
 };
 
+#include "conv_bank.cuh"
+
 #define NEO_CONV_ENGINE(conv, CALL) ((conv)->cfg.dtype == NEO_B200_F32 ? (conv)->f32.CALL : (conv)->f64.CALL)
 
 extern "C" {
@@ -744,7 +811,6 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
     if (memspace == NEO_B200_DEVICE) {
         NEO_TRY(e.forward(static_cast<T const*>(in), stride, blocks, s));
         NEO_TRY(e.inverse(e.acc.template as<cx<T>>(), plane, 1, static_cast<T*>(out), stride, 0, conv->cfg.outputs, blocks, s));
-        if (conv->cfg.kind == NEO_B200_UPOLA) { e.tail_flip ^= 1; }
         return NEO_B200_OK;
     }
 
@@ -796,16 +862,19 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
         e.advance(blocks);
         NEO_CUDA_TRY(cudaStreamSynchronize(conv->s_out));
     }
-    if (conv->cfg.kind == NEO_B200_UPOLA) { e.tail_flip ^= 1; }
     NEO_CUDA_TRY(cudaStreamSynchronize(s));
     return NEO_B200_OK;
 }
 
-static int conv_check_call(neo_b200_conv* conv, size_t blocks)
+static int conv_check_call(neo_b200_conv* conv, size_t blocks, bool whole_bank = true)
 {
     if (conv == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
     bool const ready = conv->cfg.dtype == NEO_B200_F32 ? conv->f32.has_filter : conv->f64.has_filter;
     if (!ready) { return fail(NEO_B200_ERR_INVALID, "no filter set"); }
+    bool const in_call = conv->cfg.dtype == NEO_B200_F32 ? conv->f32.in_call : conv->f64.in_call;
+    if (whole_bank && in_call) {
+        return fail(NEO_B200_ERR_INVALID, "a forward_range call is in progress: pass final != 0 with its last channel range (or reset) first");
+    }
     if (blocks == 0 || blocks > conv->cfg.max_blocks) {
         return fail(NEO_B200_ERR_INVALID, "blocks=%zu outside [1, max_blocks=%zu]", blocks, conv->cfg.max_blocks);
     }
@@ -853,16 +922,37 @@ int conv_forward_range_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* 
 {
     cudaStream_t const s = conv->stream.stream;
     size_t const stride  = blocks * e.m;
+    // the ranges of one call tile the bank in ascending order, every channel exactly once, the same block count throughout
+    if (!e.in_call) {
+        e.range_next   = 0;
+        e.range_blocks = blocks;
+    }
+    if (first != e.range_next) {
+        return fail(NEO_B200_ERR_INVALID, "forward_range: channel range must start at %zu (ranges tile the bank in ascending order), got %zu",
+                    e.range_next, first);
+    }
+    if (blocks != e.range_blocks) {
+        return fail(NEO_B200_ERR_INVALID, "forward_range: blocks=%zu differs from the %zu of the call in progress", blocks, e.range_blocks);
+    }
+    if ((final != 0) != (first + count == conv->cfg.outputs)) {
+        return fail(NEO_B200_ERR_INVALID, "forward_range: final must be set exactly with the range that ends at channel %zu", conv->cfg.outputs);
+    }
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, in) != cudaSuccess || (attr.type != cudaMemoryTypeDevice && attr.type != cudaMemoryTypeManaged)) {
+        (void)cudaGetLastError();
+        return fail(NEO_B200_ERR_INVALID, "forward_range needs DEVICE memory");
+    }
     NEO_TRY(e.forward_r2c(static_cast<T const*>(in) + first * stride, stride, blocks, first, count, s));
     NEO_TRY(e.forward_mac(blocks, first, count, s));
-    e.in_call = true;
+    e.in_call    = true;
+    e.range_next = first + count;
     if (final != 0) { e.advance(blocks); }
     return NEO_B200_OK;
 }
 
 int neo_b200_conv_forward_range(neo_b200_conv* conv, void const* in, size_t blocks, size_t first, size_t count, int final)
 {
-    NEO_TRY(conv_check_call(conv, blocks));
+    NEO_TRY(conv_check_call(conv, blocks, false));
     if (in == nullptr) { return fail(NEO_B200_ERR_INVALID, "null buffer"); }
     if (conv->cfg.topology != NEO_B200_DIAGONAL) { return fail(NEO_B200_ERR_INVALID, "forward_range needs the diagonal topology"); }
     if (count == 0 || first + count > conv->cfg.outputs) { return fail(NEO_B200_ERR_INVALID, "bad channel range"); }
@@ -890,7 +980,6 @@ int conv_inverse_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* spectr
         dout = e.stage_out.template as<T>();
     }
     NEO_TRY(e.inverse(static_cast<cx<T> const*>(spectra), 0, 1, dout, stride, first, count, blocks, s));
-    if (conv->cfg.kind == NEO_B200_UPOLA) { e.tail_flip ^= 1; }
     if (memspace == NEO_B200_HOST) {
         NEO_CUDA_TRY(cudaMemcpyAsync(out, dout, count * stride * sizeof(T), cudaMemcpyDeviceToHost, s));
         NEO_CUDA_TRY(cudaStreamSynchronize(s));
@@ -900,7 +989,7 @@ int conv_inverse_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* spectr
 
 int neo_b200_conv_inverse(neo_b200_conv* conv, void const* spectra_device, void* out, size_t first, size_t count, size_t blocks, int memspace)
 {
-    NEO_TRY(conv_check_call(conv, blocks));
+    NEO_TRY(conv_check_call(conv, blocks, false));
     if (spectra_device == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null buffer"); }
     if (first + count > conv->cfg.outputs) { return fail(NEO_B200_ERR_INVALID, "output range [%zu, %zu) outside the bank", first, first + count); }
     if (count == 0) { return NEO_B200_OK; }

@@ -643,20 +643,84 @@ struct conv_c2r_io
     }
 };
 
-// overlap-add epilogue (overlap_add.hpp:103-106): out = y[0..B) + tail, tail' = y[B..2B) of the last block
+// ---- inverse side of a partition-sharded bank whose shards sit in peer-mapped memory: the cross-device reduction of the partial
+// spectra is fused into the loads of the c2r kernel. src[j] is the partial-spectra buffer of partition shard j (this device's own
+// buffer or a peer's, read over NVLink through the mapped pointer), all with the same [count][blocks][B] layout; they are summed in
+// shard order, so every device would produce the same bits for the same channel.
+constexpr int k_bank_max_shards = 8;
+
+template<typename T, int LOGM>
+struct conv_c2r_sum_io
+{
+    using C = cx<T>;
+    C const* src[k_bank_max_shards];
+    int nsrc;
+    int blocks;
+    T* out;
+    size_t out_stride;
+    T scale;
+    int overlap_add;
+
+    struct row_state
+    {
+        size_t off;
+        C* dst;
+    };
+    __device__ __forceinline__ row_state open(size_t b) const
+    {
+        constexpr size_t B = size_t(1) << LOGM;
+        size_t const ch    = b / blocks;
+        size_t const tau   = b - ch * blocks;
+        T* dst             = overlap_add ? out + (ch * blocks + tau) * 2 * B : out + ch * out_stride + tau * B;
+        return {(ch * blocks + tau) * B, reinterpret_cast<C*>(dst)};
+    }
+    __device__ __forceinline__ C load(row_state const& r, int k) const
+    {
+        C v = src[0][r.off + k];
+        for (int j = 1; j < nsrc; ++j) {
+            C const p = src[j][r.off + k];
+            v.x += p.x;
+            v.y += p.y;
+        }
+        return v;
+    }
+    __device__ __forceinline__ C load_edges(row_state const& r) const { return load(r, 0); }
+    __device__ __forceinline__ void store(row_state const& r, int j, C z) const
+    {
+        constexpr int H = (1 << LOGM) / 2;
+        z.x *= scale;
+        z.y *= scale;
+        if (overlap_add) {
+            r.dst[j] = z;
+        } else if (j >= H) {
+            r.dst[j - H] = z;
+        }
+    }
+};
+
+// overlap-add epilogue (overlap_add.hpp:103-106): out = y[0..B) + tail, tail' = y[B..2B) of the last block.
+// One thread walks all blocks of one sample position of one channel, so the tail is read and rewritten IN PLACE by the same
+// thread: the tail state belongs to a channel, and a step may be finished by several calls over disjoint channel ranges
+// (neo_b200_conv_inverse) without any per-call ping-pong.
 template<typename T>
 __global__ void __launch_bounds__(256)
-    ola_combine_kernel(T const* __restrict__ y, T const* __restrict__ tail_in, T* __restrict__ tail_out, T* __restrict__ out,
-                       size_t out_stride, int block, int blocks, size_t first)
+    ola_combine_kernel(T const* __restrict__ y, T* __restrict__ tail, T* __restrict__ out, size_t out_stride, int block, int blocks, size_t first)
 {
-    size_t const ch  = blockIdx.z;
-    int const tau    = blockIdx.y;
-    int const i      = blockIdx.x * blockDim.x + threadIdx.x;
+    size_t const ch = blockIdx.y;
+    int const i     = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= block) { return; }
-    T const* yrow  = y + (ch * blocks + tau) * 2 * size_t(block);
-    T const before = tau == 0 ? tail_in[(first + ch) * block + i] : yrow[i - block];  // y[tau-1][B + i]
-    out[ch * out_stride + size_t(tau) * block + i] = yrow[i] + before;
-    if (tau == blocks - 1) { tail_out[(first + ch) * block + i] = yrow[block + i]; }
+    T const* yrow = y + ch * size_t(blocks) * 2 * size_t(block) + i;
+    T* const dst  = out + ch * out_stride + i;
+    T* const keep = tail + (first + ch) * size_t(block) + i;
+    T before      = *keep;
+#pragma unroll 4
+    for (int tau = 0; tau < blocks; ++tau) {
+        T const lo = yrow[size_t(tau) * 2 * block];
+        T const hi = yrow[size_t(tau) * 2 * block + block];
+        dst[size_t(tau) * block] = lo + before;
+        before                   = hi;
+    }
+    *keep = before;
 }
 
 // ---- filter preparation ----------------------------------------------------------------------------------------------------------

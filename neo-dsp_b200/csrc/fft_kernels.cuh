@@ -282,9 +282,12 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOG
 
     F::run(v, sm, tw, t);
 
+    // Hermitian exchange: both sides are unit stride (k ascending on the store, M - k descending on the load), so the tile is used
+    // UNPADDED here -- with the stage padding a half-warp's 16 partners straddle a pad boundary and collide two-way (ncu: 16 % of the
+    // kernel's shared-memory wavefronts were bank conflicts)
     if constexpr (LOGM > 0) {
 #pragma unroll
-        for (int e = 0; e < cfg::E; ++e) { sm[padded<T>(t + e * cfg::TN)] = v[e]; }
+        for (int e = 0; e < cfg::E; ++e) { sm[t + e * cfg::TN] = v[e]; }
         __syncthreads();
     }
     if (live) {
@@ -294,7 +297,7 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOG
             if (k == 0) {
                 io.store_edges(row, v[e].x + v[e].y, v[e].x - v[e].y);
             } else {
-                C const zp = sm[padded<T>(cfg::M - k)];
+                C const zp = sm[cfg::M - k];
                 io.store(row, k, r2c_post(v[e], zp, __ldg(rtw + k)));
             }
         }
@@ -332,13 +335,13 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOG
             own[e]      = !live ? mk<T>(0, 0) : k == 0 ? io.load_edges(row) : io.load(row, k);
         }
 #pragma unroll
-        for (int e = 0; e < cfg::E; ++e) { sm[padded<T>(t + e * cfg::TN)] = own[e]; }
+        for (int e = 0; e < cfg::E; ++e) { sm[t + e * cfg::TN] = own[e]; }  // unpadded: unit stride both ways (see r2c_kernel)
         __syncthreads();
 #pragma unroll
         for (int e = 0; e < cfg::E; ++e) {
             int const k = t + e * cfg::TN;
             if (k == 0) { v[e] = mk<T>(own[e].x + own[e].y, own[e].x - own[e].y); }
-            else { v[e] = c2r_pre(own[e], sm[padded<T>(cfg::M - k)], __ldg(rtw + k)); }
+            else { v[e] = c2r_pre(own[e], sm[cfg::M - k], __ldg(rtw + k)); }
         }
         __syncthreads();
     } else {

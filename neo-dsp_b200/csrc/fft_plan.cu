@@ -4,6 +4,7 @@
 #include "fft_kernels.cuh"
 #include "fft_large.cuh"
 #include "fft_split.cuh"
+#include "fft_stream.cuh"
 #include "fft_cluster.cuh"
 #include "fft_pair.cuh"
 
@@ -367,6 +368,14 @@ struct rfft_engine
         return tables.build(logm, true, stream);
     }
 
+    // the TMA-staged persistent kernels want 16-byte aligned arrays (any cudaMalloc / torch allocation is); NEO_B200_NO_STREAM
+    // switches them off (A/B measurements)
+    static bool stream_ok(void const* a, void const* b)
+    {
+        static bool const off = std::getenv("NEO_B200_NO_STREAM") != nullptr;
+        return !off && (reinterpret_cast<std::uintptr_t>(a) & 15U) == 0 && (reinterpret_cast<std::uintptr_t>(b) & 15U) == 0;
+    }
+
     // chunks keep the intermediate spectrum L2-resident between the two passes
     size_t two_pass_chunk(size_t batch)
     {
@@ -420,6 +429,13 @@ struct rfft_engine
         }
         if (use_large) { return large.forward(in, out, batch, stream); }
         if (use_two_pass) { return forward_two_pass(in, out, batch, stream); }
+        if constexpr (sizeof(T) == 4) {
+            // N = 2^13, 2^14: persistent CTAs fed by TMA bulk copies (fft_stream.cuh); needs 16-byte aligned arrays
+            if (stream_ok(in, out)) {
+                if (order == 13) { return launch_r2c_stream<12>(in, out, tables.tw(), tables.rtw(), batch, stream); }
+                if (order == 14) { return launch_r2c_stream<13>(in, out, tables_full.tw(), tables_full.rtw(), batch, stream); }
+            }
+        }
         if (use_split) {
             if (order - 1 == k_split_lo) {
                 static bool const one_cta = std::getenv("NEO_B200_R2C_ONE_CTA") != nullptr;  // tuning knob
@@ -457,6 +473,12 @@ struct rfft_engine
         }
         if (use_large) { return large.backward(in, row_len, out, batch, stream); }
         if (use_two_pass) { return backward_two_pass(in, row_len, out, batch, stream); }
+        if constexpr (sizeof(T) == 4) {
+            if (stream_ok(in, out)) {
+                if (order == 13) { return launch_c2r_stream<12>(in, row_len, out, tables.tw(), tables.rtw(), batch, stream); }
+                if (order == 14) { return launch_c2r_stream<13>(in, row_len, out, tables_full.tw(), tables_full.rtw(), batch, stream); }
+            }
+        }
         if (use_split) {
             auto const* wn = w_n.template as<cx<T>>();
             if (order - 1 == k_split_lo) {

@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_min_ctas<T, 
     F::run(v, sm, tw, t);
 
 #pragma unroll
-    for (int e = 0; e < cfg::E; ++e) { sm[padded<T>(t + e * cfg::TN)] = v[e]; }
+    for (int e = 0; e < cfg::E; ++e) { sm[t + e * cfg::TN] = v[e]; }  // unpadded: unit stride both ways
     __syncthreads();
     C* const row = out + b * (2 * size_t(M2) + 1);
 #pragma unroll
@@ -63,7 +63,7 @@ __global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_min_ctas<T, 
             row[0]      = mk<T>(v[e].x + v[e].y, T(0));
             row[2 * M2] = mk<T>(v[e].x - v[e].y, T(0));
         } else {
-            C const zp = sm[padded<T>((M2 - r - k2) & (M2 - 1))];
+            C const zp = sm[(M2 - r - k2) & (M2 - 1)];
             C w        = __ldg(w_m + k2);  // W_2M^(2 k2)
             if (r != 0) { w = cmul(w, w_n1); }
             row[k] = r2c_post(v[e], zp, w);

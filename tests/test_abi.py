@@ -66,7 +66,7 @@ def test_convolver_configuration_is_validated_before_any_device_work(pkg):
     # neo_b200_conv_create checks its configuration first, so the error contract is testable without a GPU
     def create(**kw):
         cfg = dict(kind=0, dtype=0, topology=0, outputs=2, inputs=2, block=64, partitions=8, max_blocks=0, partition_begin=0,
-                   partition_end=0, frame_blocks=0)
+                   partition_end=0, frame_blocks=0, input_delayed=0)
         cfg.update(kw)
         h = ctypes.c_void_p()
         c = pkg.ConvConfig(*[cfg[name] for name, _ in pkg.ConvConfig._fields_])
@@ -91,6 +91,29 @@ def test_convolver_configuration_is_validated_before_any_device_work(pkg):
         assert status != 0 and needle in message, (kw, message)
     status, message = create(frame_blocks=4)  # a valid configuration gets as far as the device check
     assert status == 0 or "no CPU fallback" in message
+
+
+def test_bank_layout_arithmetic_needs_no_device(pkg):
+    # neo_b200_bank_layout_info: rank = group * shards + shard; rows and partitions per rank; frame-aligned shards with their delay
+    info = lambda layout, rank, frame=256: pkg.Bank.layout_info(pkg.UPOLS, "float32", pkg.DIAGONAL, 1024, 1024, 1024, 1024, frame or 16, frame, layout, rank)
+    r = info((4, 2), 5)
+    assert (r["channel_group"], r["partition_shard"]) == (2, 1)
+    assert (r["group_first"], r["group_count"]) == (512, 256)
+    assert (r["in_first"], r["in_count"], r["out_first"], r["out_count"]) == (640, 128, 640, 128)
+    assert (r["partition_begin"], r["partition_end"], r["delay_blocks"]) == (512, 1024, 512)
+    r = info((1, 8), 3, frame=0)  # direct form: no delayed input, the handle reaches back through its own ring
+    assert (r["partition_begin"], r["partition_end"], r["delay_blocks"]) == (384, 512, 0)
+    covered = []
+    for rank in range(8):
+        r = info((2, 4), rank)
+        covered.append((r["channel_group"], r["partition_begin"], r["partition_end"]))
+        assert r["partition_begin"] % 256 == 0
+    assert covered == [(g, s * 256, (s + 1) * 256) for g in range(2) for s in range(4)]
+    for bad in ((3, 2), (1, 16)):
+        with pytest.raises(RuntimeError):
+            pkg.Bank.layout_info(pkg.UPOLS, "float32", pkg.DIAGONAL, 1024, 1024, 1024, 1024, 256, 256, bad, 0)
+    with pytest.raises(RuntimeError, match="shards"):  # 1024 partitions = 4 frames of 256: cannot be cut into 8 shards
+        info((1, 8), 0)
 
 
 def test_no_cpu_fallback(pkg):

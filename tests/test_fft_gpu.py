@@ -44,6 +44,26 @@ def test_rfft_irfft_match_oracle_every_order(gpu, orc, real, cplx):
         plan.close()
 
 
+@pytest.mark.parametrize("order,batch", [(13, 701), (14, 333)])
+def test_tma_staged_persistent_rfft_many_rows(gpu, orc, order, batch):
+    # N = 2^13 / 2^14 run as persistent CTAs fed by bulk copies (fft_stream.cuh): more rows than CTA slots (296 / 148), odd and even
+    # rows (spectrum rows of N/2+1 bins alternate between 16-byte aligned and not), and N-long spectrum rows on the way back
+    n = 1 << order
+    x = np.stack([orc.noise(n, 2 + (b % 5), np.float32) * np.float32(1 + b % 3) for b in range(batch)])
+    base = orc.rfft(x[:15])
+    plan = gpu.RFFTPlan(order, np.float32)
+    spec = plan.rfft(x)
+    for b in range(batch):  # rows repeat with period 15 (5 seeds x 3 gains): every row is checked against the oracle
+        assert rel_l2(spec[b], base[b % 15]) <= 1e-5, (order, b)
+    back = plan.irfft(spec)
+    assert rel_l2(back[:15], orc.irfft(base, n)) <= 1e-5
+    assert rel_l2(back, x * np.float32(n)) <= 1e-5
+    wide = np.zeros((batch, n), dtype=np.complex64)  # callers may hand N-long rows (overlap_save.hpp:57,107)
+    wide[:, : n // 2 + 1] = spec
+    assert np.array_equal(plan.irfft(wide), back)
+    plan.close()
+
+
 def test_golden_vectors_from_the_reference(gpu, golden):
     for tag, real, cplx in (("f32", np.float32, np.complex64), ("f64", np.float64, np.complex128)):
         tol = TOL[np.dtype(real).name]
