@@ -355,6 +355,11 @@ NEO_B200_API int neo_b200_bank_submit(neo_b200_bank* bank, void const* const* in
 NEO_B200_API int neo_b200_bank_wait(neo_b200_bank* bank);
 NEO_B200_API int neo_b200_bank_process(neo_b200_bank* bank, void const* const* in_rows, void* const* out_rows, size_t blocks, int memspace);
 
+/* device time of a run of steps, CUDA events on the bank's own streams: start waits for outstanding work and records at the head of
+ * every local rank's input stream; stop records behind the last submitted step on every output stream, waits, and yields the
+ * longest span over the local ranks in milliseconds. */
+NEO_B200_API int neo_b200_bank_timer_start(neo_b200_bank* bank);
+NEO_B200_API int neo_b200_bank_timer_stop(neo_b200_bank* bank, double* ms);
 /* per-phase device time of one local rank (see neo_b200_conv_profile_read) and its device memory */
 NEO_B200_API int neo_b200_bank_profile_enable(neo_b200_bank* bank, int enable);
 NEO_B200_API int neo_b200_bank_profile_read(neo_b200_bank* bank, size_t local_index, double* phase_ms, uint64_t* mac_launches);

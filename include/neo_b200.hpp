@@ -584,6 +584,12 @@ struct uniform_partitioned_convolver
     {
         static_assert(std::is_same_v<detail::element_of<Vec>, real_type>);
         auto const n = static_cast<std::size_t>(block.extent(0));
+        // the reference asserts the extent (uniform_partitioned_convolver.hpp:50); here a wrong extent would make the device copy
+        // run past the caller's buffer, so it is an error in release builds too
+        if (_bank.handle() == nullptr) { throw std::invalid_argument{"neo::b200::uniform_partitioned_convolver: filter() has not been called"}; }
+        if (n != _bank.block_size()) {
+            throw std::invalid_argument{"neo::b200::uniform_partitioned_convolver: block extent differs from the filter's block size"};
+        }
         if (detail::is_contiguous(block)) {
             _bank.process(block.data_handle(), block.data_handle(), 1);
         } else {

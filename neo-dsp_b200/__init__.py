@@ -150,6 +150,8 @@ SIGNATURES = {
     "neo_b200_bank_submit": (_i, [_vp, _pp, _pp, _sz, _i]),
     "neo_b200_bank_wait": (_i, [_vp]),
     "neo_b200_bank_process": (_i, [_vp, _pp, _pp, _sz, _i]),
+    "neo_b200_bank_timer_start": (_i, [_vp]),
+    "neo_b200_bank_timer_stop": (_i, [_vp, C.POINTER(C.c_double)]),
     "neo_b200_bank_profile_enable": (_i, [_vp, _i]),
     "neo_b200_bank_profile_read": (_i, [_vp, _sz, C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "neo_b200_bank_device_bytes": (_sz, [_vp, _sz]),
@@ -740,8 +742,9 @@ class Bank:
         return (_vp * len(ptrs))(*ptrs), _space(arrays), arrays
 
     def impulse(self, ir) -> None:
-        """ir: per local rank the impulse responses of ITS channel group ([group_count][taps] / [group_count][inputs][taps]), or one
-        array with the groups of all local ranks' ... one entry PER RANK (ranks of the same group repeat the group's rows)."""
+        """ir: one array PER LOCAL RANK with the impulse responses of that rank's channel group ([group_count][taps], matrix topology
+        [group_count][inputs][taps]); the partition shards of one group each get the group's rows. HOST arrays, or DEVICE arrays on the
+        rank's own device."""
         arrs = ir if isinstance(ir, (list, tuple)) else [ir]
         if len(arrs) != len(self.ranks):
             raise ValueError(f"expected {len(self.ranks)} impulse-response arrays, one per local rank")
@@ -782,6 +785,15 @@ class Bank:
         yout, _, _ = self._per_rank(out, "out_first", "out_count", "output")
         _check(library().neo_b200_bank_process(self._h, xin, yout, blocks, space))
         return out
+
+    def timer_start(self) -> None:
+        _check(library().neo_b200_bank_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        """milliseconds of device time since timer_start (CUDA events on the bank's streams, longest local rank); waits for all steps"""
+        ms = C.c_double(0.0)
+        _check(library().neo_b200_bank_timer_stop(self._h, C.byref(ms)))
+        return float(ms.value)
 
     def profile(self, enable: bool) -> None:
         _check(library().neo_b200_bank_profile_enable(self._h, int(enable)))

@@ -111,6 +111,7 @@ struct bank_rank
     device_buffer red[2];          // nccl transport: reduce-scatter result [out_count][T][B] complex
     device_buffer yout[2];         // HOST calls: finished rows on the device before they go back
     cudaEvent_t ev_in[2]{}, ev_fwd[2]{}, ev_red[2]{}, ev_c2r[2]{}, ev_out[2]{};
+    cudaEvent_t t_begin{nullptr}, t_end{nullptr};  // neo_b200_bank_timer_*
     void* partial[2]{};            // partial spectra buffer the forward of (step & 1) wrote
     size_t gather_first{0}, gather_count{0};  // input rows the rank's forward reads (global index, count)
     nccl_api::comm_t comm_world{nullptr}, comm_in{nullptr}, comm_out{nullptr};
@@ -123,6 +124,8 @@ struct bank_rank
                 NEO_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
             }
         }
+        NEO_CUDA_TRY(cudaEventCreate(&t_begin));
+        NEO_CUDA_TRY(cudaEventCreate(&t_end));
         return NEO_B200_OK;
     }
 
@@ -145,6 +148,9 @@ struct bank_rank
             for (cudaEvent_t e : {ev_in[b], ev_fwd[b], ev_red[b], ev_c2r[b], ev_out[b]}) {
                 if (e != nullptr) { cudaEventDestroy(e); }
             }
+        }
+        for (cudaEvent_t e : {t_begin, t_end}) {
+            if (e != nullptr) { cudaEventDestroy(e); }
         }
         for (cudaStream_t s : {s_in, s_cmp, s_red, s_out}) {
             if (s != nullptr) { cudaStreamDestroy(s); }
@@ -651,6 +657,43 @@ int neo_b200_bank_process(neo_b200_bank* bank, void const* const* in_rows, void*
 {
     NEO_TRY(neo_b200_bank_submit(bank, in_rows, out_rows, blocks, memspace));
     while (!bank->pending.empty()) { NEO_TRY(neo_b200_bank_wait(bank)); }
+    return NEO_B200_OK;
+}
+
+int neo_b200_bank_timer_start(neo_b200_bank* bank)
+{
+    if (bank == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    while (!bank->pending.empty()) { NEO_TRY(bank_wait_oldest(bank)); }
+    int before = 0;
+    cudaGetDevice(&before);
+    for (auto& r : bank->ranks) {
+        NEO_CUDA_TRY(cudaSetDevice(r.info.device));
+        for (cudaStream_t s : {r.s_in, r.s_cmp, r.s_red, r.s_out}) { NEO_CUDA_TRY(cudaStreamSynchronize(s)); }
+        NEO_CUDA_TRY(cudaEventRecord(r.t_begin, r.s_in));  // every step starts on the input stream
+    }
+    cudaSetDevice(before);
+    return NEO_B200_OK;
+}
+
+int neo_b200_bank_timer_stop(neo_b200_bank* bank, double* ms)
+{
+    if (bank == nullptr || ms == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    int before = 0;
+    cudaGetDevice(&before);
+    for (auto& r : bank->ranks) {  // every step ends on the output stream: the event follows the last submitted step there
+        NEO_CUDA_TRY(cudaSetDevice(r.info.device));
+        NEO_CUDA_TRY(cudaEventRecord(r.t_end, r.s_out));
+    }
+    while (!bank->pending.empty()) { NEO_TRY(bank_wait_oldest(bank)); }
+    *ms = 0.0;
+    for (auto& r : bank->ranks) {
+        NEO_CUDA_TRY(cudaSetDevice(r.info.device));
+        NEO_CUDA_TRY(cudaEventSynchronize(r.t_end));
+        float t = 0.f;
+        NEO_CUDA_TRY(cudaEventElapsedTime(&t, r.t_begin, r.t_end));
+        *ms = std::max(*ms, double(t));
+    }
+    cudaSetDevice(before);
     return NEO_B200_OK;
 }
 

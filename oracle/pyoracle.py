@@ -18,6 +18,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 ORACLE_SO = os.path.join(_HERE, "liboracle.so")
 REF_SO = os.path.join(_HERE, "_ref", "libneo_ref.so")
+REF_V4_SO = os.path.join(_HERE, "_ref", "libneo_ref_v4.so")  # the same translation unit built -march=x86-64-v4 (AVX-512 hosts)
 
 _vp, _sz, _i, _u32 = C.c_void_p, C.c_size_t, C.c_int, C.c_uint32
 
@@ -33,7 +34,7 @@ def build(force: bool = False) -> None:
             os.path.join(_HERE, "ref_wrapper.cpp")
         )
         if force or stale:
-            subprocess.run(["make", "-C", _HERE, "-B", "_ref/libneo_ref.so"], check=True, capture_output=True)
+            subprocess.run(["make", "-C", _HERE, "-B", "_ref/libneo_ref.so", "_ref/libneo_ref_v4.so"], check=True, capture_output=True)
 
 
 def _ptr(a: np.ndarray):
@@ -302,6 +303,11 @@ class _Ref(_Checker):
         fn = self._fn("rfft_bench_f32", C.c_double, [_sz, _vp, _sz, _sz])
         return float(fn(order, _ptr(data), data.shape[0], threads))
 
+    def c2c_bench(self, order: int, data: np.ndarray, reps: int) -> float:
+        """`reps` forward + inverse + 1/N round trips of one complex64 plan in place on one thread; returns seconds."""
+        fn = self._fn("c2c_bench_f32", C.c_double, [_sz, _vp, _sz])
+        return float(fn(order, _ptr(data), reps))
+
 
 @functools.lru_cache(maxsize=None)
 def oracle() -> _Oracle:
@@ -310,8 +316,27 @@ def oracle() -> _Oracle:
     return _Oracle(ORACLE_SO, "oracle_")
 
 
+def _host_has_avx512() -> bool:
+    try:
+        with open("/proc/cpuinfo") as f:
+            flags = next((line for line in f if line.startswith("flags")), "")
+    except OSError:
+        return False
+    return all(f" {name}" in flags for name in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"))
+
+
 @functools.lru_cache(maxsize=None)
 def ref() -> _Ref | None:
     if not os.path.exists(REF_SO):
         return None
     return _Ref(REF_SO, "ref_")
+
+
+@functools.lru_cache(maxsize=None)
+def ref_timing() -> tuple[_Ref, str] | None:
+    """The reference build bench.py TIMES: the widest instruction set this host runs (the library cannot be rebuilt -march=native on
+    the GPU box, so two builds travel). Returns (library, compiler flags it was built with)."""
+    if os.path.exists(REF_V4_SO) and _host_has_avx512():
+        return _Ref(REF_V4_SO, "ref_"), "g++ -O3 -march=x86-64-v4"
+    r = ref()
+    return (r, "g++ -O3 -march=x86-64-v3") if r is not None else None

@@ -366,6 +366,18 @@ void ref_conv_process_f64(void* h, double* block, std::size_t n)
 // shares one filter so the sample fits host RAM), spread over `threads` std::threads.
 // Every channel processes `nblocks` blocks of B = bins-1 samples in place in signal[c][nblocks*B].
 // Returns seconds spent in the block loop only (filter setup excluded, as convolution.cpp:26-40 excludes it).
+// Worker threads are created first and released together by a start gate, so thread creation is outside the timed region.
+namespace {
+struct start_gate
+{
+    std::atomic<bool> go{false};
+    void wait() const
+    {
+        while (!go.load(std::memory_order_acquire)) { std::this_thread::yield(); }
+    }
+};
+}  // namespace
+
 double ref_conv_bench_f32(
     int kind,
     float const* filters,
@@ -381,15 +393,21 @@ double ref_conv_bench_f32(
     auto const block = bins - 1;
     auto boxes       = std::vector<std::unique_ptr<convolver_box<float>>>(channels);
 
+    // returns the seconds between the release of the workers and the last one finishing
     auto for_channels = [&](auto fn) {
         auto next = std::atomic<std::size_t>{0};
+        auto gate = start_gate{};
         auto pool = std::vector<std::thread>{};
         for (std::size_t t = 0; t < threads; ++t) {
             pool.emplace_back([&] {
+                gate.wait();
                 for (auto c = next.fetch_add(1); c < channels; c = next.fetch_add(1)) { fn(c); }
             });
         }
+        auto const start = std::chrono::steady_clock::now();
+        gate.go.store(true, std::memory_order_release);
         for (auto& t : pool) { t.join(); }
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     };
 
     for_channels([&](std::size_t c) {
@@ -397,26 +415,27 @@ double ref_conv_bench_f32(
         boxes[c]->filter(filters + c * filter_stride * 2, parts, bins);
     });
 
-    auto const start = std::chrono::steady_clock::now();
-    for_channels([&](std::size_t c) {
+    return for_channels([&](std::size_t c) {
         for (std::size_t b = 0; b < nblocks; ++b) { boxes[c]->process(signal + (c * nblocks + b) * block, block); }
     });
-    auto const stop = std::chrono::steady_clock::now();
-    return std::chrono::duration<double>(stop - start).count();
 }
 
-// batched rfft+irfft round trips, batch split over threads, one plan per thread
+// batched rfft+irfft round trips, batch split over threads, one plan per thread (the pair the reference's
+// own driver times, extra/benchmark/src/rfft.cpp:22-31). Plans and scratch are built before the start gate opens.
 double ref_rfft_bench_f32(std::size_t order, float* data, std::size_t batch, std::size_t threads)
 {
-    using C       = std::complex<float>;
-    auto const n  = std::size_t(1) << order;
-    auto next     = std::atomic<std::size_t>{0};
-    auto pool     = std::vector<std::thread>{};
-    auto const t0 = std::chrono::steady_clock::now();
+    using C      = std::complex<float>;
+    auto const n = std::size_t(1) << order;
+    auto next    = std::atomic<std::size_t>{0};
+    auto ready   = std::atomic<std::size_t>{0};
+    auto gate    = start_gate{};
+    auto pool    = std::vector<std::thread>{};
     for (std::size_t t = 0; t < threads; ++t) {
         pool.emplace_back([&] {
             auto plan = neo::fft::rfft_plan<float, C>{neo::fft::from_order, order};
             auto spec = std::vector<C>(n);
+            ready.fetch_add(1);
+            gate.wait();
             for (auto b = next.fetch_add(1); b < batch; b = next.fetch_add(1)) {
                 auto x = vec_view<float>{data + b * n, n};
                 neo::fft::rfft(plan, x, vec_view<C>{spec.data(), n});
@@ -424,9 +443,28 @@ double ref_rfft_bench_f32(std::size_t order, float* data, std::size_t batch, std
             }
         });
     }
+    while (ready.load() < threads) { std::this_thread::yield(); }
+    auto const t0 = std::chrono::steady_clock::now();
+    gate.go.store(true, std::memory_order_release);
     for (auto& t : pool) { t.join(); }
-    auto const t1 = std::chrono::steady_clock::now();
-    return std::chrono::duration<double>(t1 - t0).count();
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+}
+
+// BASELINE config 1 (extra/benchmark/src/fft.cpp:12-38): one complex<float> plan of 2^order points, forward then inverse then 1/N
+// scale in place, `reps` round trips on one thread. Returns seconds.
+double ref_c2c_bench_f32(std::size_t order, float* inout, std::size_t reps)
+{
+    using C      = std::complex<float>;
+    auto const n = std::size_t(1) << order;
+    auto plan    = neo::fft::fft_plan<C>{neo::fft::from_order, order};
+    auto x       = vec_view<C>{reinterpret_cast<C*>(inout), n};
+    auto const t0 = std::chrono::steady_clock::now();
+    for (std::size_t r = 0; r < reps; ++r) {
+        neo::fft::fft(plan, x);
+        neo::fft::ifft(plan, x);
+        neo::scale(1.0F / static_cast<float>(n), x);
+    }
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
 }
 
 }  // extern "C"

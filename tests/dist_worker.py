@@ -1,9 +1,10 @@
 """Worker for the multi-process tests (launched with torch.distributed.run).
 
-    --backend gloo : CPU, world_size 2. Exercises the host-side sharding logic of the partition-sharded path (partition ranges,
-                     channel shards, reduce-scatter layout) with the ORACLE standing in for the per-rank CUDA kernels --
-                     test infrastructure only; it proves the decomposition bench.py uses is exact, not the kernels.
-    --backend nccl : one GPU per rank, the real path: conv_forward -> NCCL reduce-scatter of partial spectra -> conv_inverse.
+    --backend gloo : CPU, world_size 2. The library's layout arithmetic (neo_b200_bank_layout_info: which rows, channel group and
+                     partition range each rank holds, and how late a shard sees its input) with the ORACLE standing in for the
+                     per-rank CUDA kernels -- test infrastructure only; it proves the decomposition the bank uses is exact.
+    --backend nccl : one GPU per rank, the real path: the library bank in rank-per-process mode (neo_b200_bank_create_rank):
+                     ncclAllGather of input rows, forward, ncclReduceScatter of partial spectra, inverse; pipelined submits.
 """
 import argparse
 import os
@@ -19,9 +20,114 @@ import __graft_entry__ as entry  # noqa: E402
 from oracle import pyoracle  # noqa: E402
 
 
-def shard_ranges(parts: int, channels: int, world: int, rank: int):
-    """the decomposition bench.py uses: partitions [lo, hi) of every filter, channels [c0, c1) for the inverse"""
-    return (rank * parts // world, (rank + 1) * parts // world), (rank * channels // world, (rank + 1) * channels // world)
+def rel(got, want):
+    return float(np.linalg.norm(got.astype(np.float64) - want) / np.linalg.norm(want))
+
+
+def gloo_layouts(pkg, orc, rank, world):
+    C, B, P, NB = 4, 64, 8, 16
+    ir = orc.normalize_impulse(np.stack([orc.noise(B * P - 9, 11 + c, np.float32) for c in range(C)]))
+    sig = np.stack([orc.noise(B * NB, 13 + c, np.float32) for c in range(C)])
+    H = orc.uniform_partition(ir, B)
+    want = orc.convolve_blocks(0, H, sig)
+    worst = 0.0
+    for layout in ((1, 2), (2, 1)):
+        for frame in (0, 4):
+            info = pkg.Bank.layout_info(pkg.UPOLS, "float32", pkg.DIAGONAL, C, C, B, P, frame or 2, frame, layout, rank)
+            lo, hi = info["partition_begin"], info["partition_end"]
+            g0, gn = info["group_first"], info["group_count"]
+            if frame:
+                assert lo % frame == 0 and info["delay_blocks"] == lo
+            # the rank's partial result for its channel group: its partitions only, on an input delayed by `lo` blocks (linearity of
+            # the delay line, fdl_index.hpp:24-36) -- what the delayed-input shard computes, in the time domain
+            Hl = np.ascontiguousarray(H[g0 : g0 + gn, lo:hi])
+            delayed = np.concatenate([np.zeros((gn, lo * B), np.float32), sig[g0 : g0 + gn]], axis=1)[:, : B * NB]
+            part = np.zeros((C, B * NB), dtype=np.float64)
+            part[g0 : g0 + gn] = orc.convolve_blocks(0, Hl, delayed).astype(np.float64)
+            total = torch.from_numpy(part)
+            dist.all_reduce(total)  # gloo has no reduce_scatter: all_reduce then slice is the same reduction
+            o0, on = info["out_first"], info["out_count"]
+            err = rel(total[o0 : o0 + on].numpy(), want[o0 : o0 + on])
+            assert err < 1e-6, (layout, frame, err)
+            worst = max(worst, err)
+            covered = torch.zeros(C)
+            covered[o0 : o0 + on] = 1
+            dist.all_reduce(covered)
+            assert torch.all(covered == 1), "every output row belongs to exactly one rank"
+    return worst
+
+
+def nccl_bank(pkg, orc, rank, world, local):
+    worst = 0.0
+    uid_box = [pkg.bank_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid_box, src=0)
+    # diagonal bank: both layouts of two ranks, direct form and frame mode, overlap-save and overlap-add, two steps in flight
+    C, B, P, T, steps = 8, 64, 16, 4, 6
+    ir = orc.normalize_impulse(np.stack([orc.noise(B * P - 9, 11 + c, np.float32) for c in range(C)]))
+    sig = np.stack([orc.noise(B * T * steps, 13 + c, np.float32) for c in range(C)])
+    H = orc.uniform_partition(ir, B)
+    for kind in (pkg.UPOLS, pkg.UPOLA):
+        want = orc.convolve_blocks(kind, H, sig)
+        for layout in ((1, 2), (2, 1)):
+            for frame in (0, T):
+                uid = [pkg.bank_unique_id() if rank == 0 else None]
+                dist.broadcast_object_list(uid, src=0)
+                bank = pkg.Bank(kind, "float32", pkg.DIAGONAL, C, C, B, P, max_blocks=T, frame_blocks=frame, layout=layout, rank=rank,
+                                world=world, unique_id=uid[0], device=local)
+                info = bank.ranks[0]
+                bank.impulse([np.ascontiguousarray(ir[info["group_first"] : info["group_first"] + info["group_count"]])])
+                i0, n_in, o0, n_out = info["in_first"], info["in_count"], info["out_first"], info["out_count"]
+                ins = [np.ascontiguousarray(sig[i0 : i0 + n_in, s * T * B : (s + 1) * T * B]) for s in range(steps)]
+                outs = [np.zeros((n_out, T * B), np.float32) for _ in range(steps)]
+                for s in range(steps):
+                    bank.submit([ins[s]], [outs[s]])
+                    if s >= 1:
+                        bank.wait()
+                bank.wait()
+                got = np.concatenate(outs, axis=1)
+                err = rel(got, want[o0 : o0 + n_out])
+                assert err < 1e-5, (kind, layout, frame, err)
+                worst = max(worst, err)
+                # device buffers after a reset
+                bank.reset()
+                got2 = []
+                for s in range(steps):
+                    x = torch.from_numpy(ins[s]).cuda()
+                    y = torch.empty((n_out, T * B), device="cuda", dtype=torch.float32)
+                    torch.cuda.synchronize()
+                    bank([x], [y])
+                    got2.append(y.cpu().numpy())
+                assert rel(np.concatenate(got2, axis=1), want[o0 : o0 + n_out]) < 1e-5, (kind, layout, frame)
+                bank.close()
+    # matrix topology sharded by output channel (BASELINE config 4's sharding) and by partitions
+    O, I, L = 4, 2, B * 6
+    irm = np.stack([np.stack([orc.noise(L, 100 + 10 * o + i, np.float32) for i in range(I)]) for o in range(O)])
+    irm /= np.sqrt((irm**2).sum(axis=2).max())
+    sigm = np.stack([orc.noise(B * T * steps, 13 + i, np.float32) for i in range(I)])
+    wantm = np.zeros((O, B * T * steps))
+    for o in range(O):
+        wantm[o] = orc.convolve_blocks(0, orc.uniform_partition(irm[o], B), sigm).astype(np.float64).sum(axis=0)
+    for layout in ((2, 1), (1, 2)):
+        for frame in (0, 2):
+            Tm = 2
+            uid = [pkg.bank_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(uid, src=0)
+            bank = pkg.Bank(pkg.UPOLS, "float32", pkg.MATRIX, O, I, B, L // B, max_blocks=Tm, frame_blocks=frame, layout=layout, rank=rank,
+                            world=world, unique_id=uid[0], device=local)
+            info = bank.ranks[0]
+            bank.impulse([np.ascontiguousarray(irm[info["group_first"] : info["group_first"] + info["group_count"]])])
+            i0, n_in, o0, n_out = info["in_first"], info["in_count"], info["out_first"], info["out_count"]
+            got = []
+            for s in range(T * steps // Tm):
+                x = np.ascontiguousarray(sigm[i0 : i0 + n_in, s * Tm * B : (s + 1) * Tm * B])
+                y = np.zeros((n_out, Tm * B), np.float32)
+                bank([x], [y])
+                got.append(y)
+            err = rel(np.concatenate(got, axis=1), wantm[o0 : o0 + n_out])
+            assert err < 1e-5, ("matrix", layout, frame, err)
+            worst = max(worst, err)
+            bank.close()
+    return worst
 
 
 def main():
@@ -30,94 +136,16 @@ def main():
     args = ap.parse_args()
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     orc = pyoracle.oracle()
-    C, B, P, NB, T = 4, 64, 6, 12, 3
-    ir = orc.normalize_impulse(np.stack([orc.noise(B * P - 9, 11 + c, np.float32) for c in range(C)]))
-    sig = np.stack([orc.noise(B * NB, 13 + c, np.float32) for c in range(C)])
-    H = orc.uniform_partition(ir, B)
-    want = orc.convolve_blocks(0, H, sig)
-    (lo, hi), (c0, c1) = shard_ranges(P, C, world, rank)
-
+    pkg = entry.load_package()
     if args.backend == "gloo":
         dist.init_process_group("gloo")
-        # rank-local partial result: this rank's partitions only, on an input delayed by `lo` blocks (linearity of the FDL)
-        Hl = np.ascontiguousarray(H[:, lo:hi])
-        delayed = np.concatenate([np.zeros((C, lo * B), np.float32), sig], axis=1)[:, : B * NB]
-        part = torch.from_numpy(orc.convolve_blocks(0, Hl, delayed).astype(np.float64))
-        # gloo has no reduce_scatter: all_reduce then slice is the same reduction
-        dist.all_reduce(part)
-        out = part[c0:c1]
-        err = np.linalg.norm(out.numpy() - want[c0:c1]) / np.linalg.norm(want[c0:c1])
-        assert err < 1e-6, err
+        err = gloo_layouts(pkg, orc, rank, world)
     else:
         local = int(os.environ.get("LOCAL_RANK", rank))
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-        pkg = entry.load_package()
         pkg.set_device(local)
-        conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, max_blocks=T, partition_range=(lo, hi))
-        conv.set_stream(torch.cuda.current_stream())
-        conv.filter(H)
-        got = np.zeros((c1 - c0, B * NB), dtype=np.float32)
-        shard = torch.empty((c1 - c0, T, 2 * B), device="cuda", dtype=torch.float32)
-        for pos in range(0, NB, T):
-            x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + T) * B])).cuda()
-            y = torch.empty((c1 - c0, T * B), device="cuda", dtype=torch.float32)
-            conv.forward(x)
-            dist.reduce_scatter_tensor(shard, conv.spectra_tensor(T))
-            conv.inverse(shard, y, c0, c1 - c0, T)
-            torch.cuda.synchronize()
-            got[:, pos * B : (pos + T) * B] = y.cpu().numpy()
-        err = np.linalg.norm(got - want[c0:c1]) / np.linalg.norm(want[c0:c1])
-        assert err < 1e-5, err
-
-        # the grouped form bench.py uses: channel groups, async reduce-scatter of one group while the next group's MAC runs;
-        # rank r then owns the r-th slice of every group
-        conv.reset()
-        groups, gch = 2, C // 2
-        gsh = gch // world
-        mine = [g * gch + rank * gsh + i for g in range(groups) for i in range(gsh)]
-        got2 = np.zeros((len(mine), B * NB), dtype=np.float32)
-        shards = [torch.empty((gsh, T, 2 * B), device="cuda", dtype=torch.float32) for _ in range(groups)]
-        for pos in range(0, NB, T):
-            x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + T) * B])).cuda()
-            y = torch.empty((groups, gsh, T * B), device="cuda", dtype=torch.float32)
-            works = []
-            for g in range(groups):
-                conv.forward_range(x, g * gch, gch, g == groups - 1)
-                spectra = conv.spectra_tensor(T)  # after the forward: a sharded handle alternates between two buffers
-                works.append(dist.reduce_scatter_tensor(shards[g], spectra[g * gch : (g + 1) * gch], async_op=True))
-            for g in range(groups):
-                works[g].wait()
-                conv.inverse(shards[g], y[g], g * gch + rank * gsh, gsh, T)
-            torch.cuda.synchronize()
-            got2[:, pos * B : (pos + T) * B] = y.view(-1, T * B).cpu().numpy()
-        err2 = np.linalg.norm(got2 - want[mine]) / np.linalg.norm(want[mine])
-        assert err2 < 1e-5, err2
-        conv.close()
-
-        # frame mode (calls of exactly TF blocks, second overlap-save level along block time): a shard starts on a frame boundary
-        # of the partition axis; the partial LEVEL-1 spectra are reduced exactly as above
-        P2, TF = 8, 2
-        ir2 = orc.normalize_impulse(np.stack([orc.noise(B * P2 - 9, 21 + c, np.float32) for c in range(C)]))
-        H2 = orc.uniform_partition(ir2, B)
-        want3 = orc.convolve_blocks(0, H2, sig)
-        (lo2, hi2), _ = shard_ranges(P2, C, world, rank)
-        assert lo2 % TF == 0
-        conv = pkg.Convolver(pkg.UPOLS, "float32", pkg.DIAGONAL, partition_range=(lo2, hi2), frame_blocks=TF)
-        conv.set_stream(torch.cuda.current_stream())
-        conv.filter(H2)
-        got3 = np.zeros((c1 - c0, B * NB), dtype=np.float32)
-        shard = torch.empty((c1 - c0, TF, 2 * B), device="cuda", dtype=torch.float32)
-        for pos in range(0, NB, TF):
-            x = torch.from_numpy(np.ascontiguousarray(sig[:, pos * B : (pos + TF) * B])).cuda()
-            y = torch.empty((c1 - c0, TF * B), device="cuda", dtype=torch.float32)
-            conv.forward(x)
-            dist.reduce_scatter_tensor(shard, conv.spectra_tensor(TF))
-            conv.inverse(shard, y, c0, c1 - c0, TF)
-            torch.cuda.synchronize()
-            got3[:, pos * B : (pos + TF) * B] = y.cpu().numpy()
-        err3 = np.linalg.norm(got3 - want3[c0:c1]) / np.linalg.norm(want3[c0:c1])
-        assert err3 < 1e-5, err3
+        err = nccl_bank(pkg, orc, rank, world, local)
     dist.barrier()
     if rank == 0:
         print(f"dist_worker ok backend={args.backend} world={world} err={err:.2e}")
