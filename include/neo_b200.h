@@ -11,9 +11,13 @@
  *   - `dtype` names the REAL element type (NEO_B200_F32 / NEO_B200_F64);
  *   - transforms are UNNORMALISED in both directions, like every reference plan (c2c_dit2_plan.hpp:84-95,
  *     fallback_rfft_plan.hpp:39-55); forward is exp(-2 pi i nk/N) (fft/direction.hpp:8-12);
- *   - `memspace` says where in/out live: HOST buffers are staged through pinned memory and the call returns when the
- *     result is in `out`; DEVICE buffers are used in place, the work is enqueued on the handle's stream and the
- *     call returns immediately (use *_synchronize or the stream);
+ *   - `memspace` says where in/out live. HOST: any host memory; the call returns when the result is in `out`. Transform plans and
+ *     short convolver calls copy straight from / to the caller's pointer (pinned memory gets DMA speed, pageable memory the
+ *     driver's own staging). Convolver calls of >= 4 blocks on a diagonal bank are cut into channel groups and pipelined over
+ *     three streams (H2D of group g+1 and D2H of group g-1 overlap the kernels of group g); page-locked caller memory is used as it
+ *     is, pageable memory is staged through two pinned chunks per direction by the calling thread and a few helper threads.
+ *     DEVICE: buffers are used in place, the work is enqueued on the handle's stream and the call returns immediately (use
+ *     *_synchronize or the stream);
  *   - every function returns a neo_b200_status (0 = ok); neo_b200_last_error() gives the message of the last
  *     failure on the calling thread. The C++ facade turns failures of create/set_filter into std::runtime_error,
  *     which is what the reference throws from plan construction (c2c_dit2_plan.hpp:98-104, backend/ipp.hpp:30-51);
@@ -270,6 +274,18 @@ NEO_B200_API int neo_b200_conv_forward_range(
 NEO_B200_API int neo_b200_conv_spectra(neo_b200_conv* conv, void** device_ptr, size_t* bytes_per_output_block);
 NEO_B200_API int neo_b200_conv_inverse(
     neo_b200_conv* conv, void const* spectra_device, void* out, size_t first, size_t count, size_t blocks, int memspace);
+
+/* the chunk step of neo::convolution::overlap_add_convolver == upola_convolver_v2 (convolution/overlap_add_convolver.hpp:85-132), which
+ * accepts calls of any length >= one block and therefore calls that END INSIDE a block: `window` [channels][2B] reals is transformed AS
+ * IT STANDS (:92; after a partial chunk it holds the previous inverse transform's output with new samples written over part of it), its
+ * spectrum replaces the newest delay-line row (:94), all partitions are accumulated (:96-111), and the inverse transform scaled by 1/2B
+ * comes back in `y` [channels][2B] (:114-115). commit != 0: the chunk completed a block and the delay line advances (:122-131). The
+ * caller keeps window, overlap and input position, as the reference object does (include/neo_b200.hpp: overlap_add_convolver).
+ * Unsharded overlap-add diagonal banks in the direct form. */
+NEO_B200_API int neo_b200_conv_process_window(neo_b200_conv* conv, void const* window, void* y, int commit, int memspace);
+/* the overlap-add tail [outputs][B] a handle carries between neo_b200_conv_process calls (overlap_add.hpp:106): lets a caller move
+ * from whole-block calls to the chunk step above without losing state */
+NEO_B200_API int neo_b200_conv_tail(neo_b200_conv* conv, void* tail, int memspace);
 
 NEO_B200_API int neo_b200_conv_set_stream(neo_b200_conv* conv, void* cuda_stream);
 NEO_B200_API int neo_b200_conv_synchronize(neo_b200_conv* conv);

@@ -612,10 +612,14 @@ template<typename Complex>
 using upola_convolver = uniform_partitioned_convolver<Complex, NEO_B200_UPOLA>;
 
 /// Drop-in for neo::convolution::overlap_add_convolver / upola_convolver_v2 (convolution/overlap_add_convolver.hpp:21-136,
-/// dense_convolver.hpp:28) for the call shape its test and benchmark use (uniform_partitioned_convolver_test.cpp:40,
-/// benchmark/convolution.cpp:58): `operator()(inout)` takes any WHOLE number of blocks (>= 1) and runs the block loop of
-/// overlap_add_convolver.hpp:85 on the device, up to 32 blocks per launch. A call that ends inside a block -- where the
-/// reference re-transforms the partially filled window -- is rejected with std::invalid_argument.
+/// dense_convolver.hpp:28): `operator()(inout)` takes ANY number of samples >= one block (:74 asserts that).
+///   - Calls of whole blocks on a clean window -- what its test and benchmark use (uniform_partitioned_convolver_test.cpp:40,
+///     benchmark/convolution.cpp:58) -- run the block loop of :85 on the device, up to 32 blocks per launch.
+///   - A call that ends inside a block follows the reference chunk by chunk (:85-132), including its peculiarity: the window is
+///     transformed as it stands, and after a partial chunk it holds the previous inverse transform's OUTPUT (:114-115 write the result
+///     back into the window), so the next chunk of the same block transforms output samples next to the new input. Window, overlap
+///     and input position live here, as in the reference object; each chunk is one neo_b200_conv_process_window call. Once a call
+///     has ended inside a block the object stays on this chunk path.
 template<typename Complex>
 struct overlap_add_convolver
 {
@@ -640,6 +644,11 @@ struct overlap_add_convolver
         }
         _block = bins - 1;
         _bank.filter(_copy.data(), 1, 1, parts, bins, NEO_B200_DIAGONAL, max_blocks_per_launch);
+        _window.assign(2 * _block, real_type{});   // overlap_add_convolver.hpp:61-63: zero-initialised
+        _overlap.assign(_block, real_type{});
+        _y.assign(2 * _block, real_type{});
+        _input_pos  = 0;
+        _chunk_path = false;
     }
 
     template<typename Vec>
@@ -647,25 +656,55 @@ struct overlap_add_convolver
     {
         static_assert(std::is_same_v<detail::element_of<Vec>, real_type>);
         auto const n = static_cast<size_type>(inout.extent(0));
-        if (_block == 0 || n < _block || n % _block != 0) {
-            throw std::invalid_argument{"neo::b200::overlap_add_convolver: call length must be a whole number of blocks"};
-        }
+        if (_block == 0) { throw std::invalid_argument{"neo::b200::overlap_add_convolver: filter() has not been called"}; }
+        if (n < _block) { throw std::invalid_argument{"neo::b200::overlap_add_convolver: call shorter than one block"}; }  // :74
         _tmp.resize(n);
         for (size_type i = 0; i < n; ++i) { _tmp[i] = inout[i]; }
-        for (size_type done = 0; done < n / _block;) {
-            auto const blocks = std::min(max_blocks_per_launch, n / _block - done);
-            _bank.process(_tmp.data() + done * _block, _tmp.data() + done * _block, blocks);
-            done += blocks;
+        if (!_chunk_path && n % _block == 0) {
+            for (size_type done = 0; done < n / _block;) {
+                auto const blocks = std::min(max_blocks_per_launch, n / _block - done);
+                _bank.process(_tmp.data() + done * _block, _tmp.data() + done * _block, blocks);
+                done += blocks;
+            }
+        } else {
+            if (!_chunk_path) {  // the overlap so far lives in the handle (overlap_add.hpp:106); from here on it lives in this object
+                detail::check(neo_b200_conv_tail(_bank.handle(), _overlap.data(), NEO_B200_HOST));
+                _chunk_path = true;
+            }
+            chunks(_tmp.data(), n);
         }
         for (size_type i = 0; i < n; ++i) { inout[i] = _tmp[i]; }
     }
 
 private:
+    // overlap_add_convolver.hpp:85-132, one device call per chunk
+    auto chunks(real_type* inout, size_type num_samples) -> void
+    {
+        size_type done = 0;
+        while (done < num_samples) {
+            auto const todo = std::min(num_samples - done, _block - _input_pos);
+            std::copy_n(inout + done, todo, _window.begin() + static_cast<std::ptrdiff_t>(_input_pos));                        // :91
+            bool const completes = _input_pos + todo == _block;
+            detail::check(neo_b200_conv_process_window(_bank.handle(), _window.data(), _y.data(), completes ? 1 : 0, NEO_B200_HOST));  // :92-115
+            _window = _y;  // :114-115: the window now holds the scaled inverse transform
+            for (size_type i = 0; i < todo; ++i) { inout[done + i] = _window[_input_pos + i] + _overlap[_input_pos + i]; }    // :117-118
+            _input_pos += todo;
+            if (_input_pos == _block) {                                                                                         // :122-131
+                _input_pos = 0;
+                std::copy_n(_window.begin() + static_cast<std::ptrdiff_t>(_block), _block, _overlap.begin());
+                std::fill(_window.begin(), _window.end(), real_type{});
+            }
+            done += todo;
+        }
+    }
+
     static constexpr size_type max_blocks_per_launch = 32;
     convolver_bank<real_type, NEO_B200_UPOLA> _bank;
     std::vector<std::complex<real_type>> _copy;
-    std::vector<real_type> _tmp;
+    std::vector<real_type> _tmp, _window, _overlap, _y;
     size_type _block{0};
+    size_type _input_pos{0};
+    bool _chunk_path{false};
 };
 
 template<typename Complex>

@@ -132,6 +132,8 @@ SIGNATURES = {
     "neo_b200_conv_forward_range": (_i, [_vp, _vp, _sz, _sz, _sz, _i]),
     "neo_b200_conv_spectra": (_i, [_vp, C.POINTER(_vp), C.POINTER(_sz)]),
     "neo_b200_conv_inverse": (_i, [_vp, _vp, _vp, _sz, _sz, _sz, _i]),
+    "neo_b200_conv_process_window": (_i, [_vp, _vp, _vp, _i, _i]),
+    "neo_b200_conv_tail": (_i, [_vp, _vp, _i]),
     "neo_b200_conv_set_stream": (_i, [_vp, _vp]),
     "neo_b200_conv_synchronize": (_i, [_vp]),
     "neo_b200_conv_profile_enable": (_i, [_vp, _i]),

@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <memory>
+#include <thread>
 #include <type_traits>
 #include <vector>
 
@@ -396,6 +397,43 @@ struct conv_engine
         return frame > 0 && !fused ? frame_forward(chan0, nchan, stream) : NEO_B200_OK;
     }
 
+    // one chunk of neo::convolution::overlap_add_convolver (overlap_add_convolver.hpp:91-115): transform the windows [channels][2B] as
+    // they stand into the newest delay-line row, MAC over all partitions, inverse transform, scale by 1/2B -> y [channels][2B].
+    // commit: the chunk completed a block, the delay line advances (:122-131). Overlap-add, direct form.
+    int window_step(T const* window, T* y, bool commit, cudaStream_t stream)
+    {
+        int status = NEO_B200_ERR_UNSUPPORTED;
+        NEO_DISPATCH_LOGM(T, logb, {
+            if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
+                window_r2c_io<T, LOGM> io{};
+                io.in          = window;
+                io.in_stride   = 2 * size_t(m);
+                io.prev        = nullptr;
+                io.prev_next   = nullptr;
+                io.fdl         = fdl.template as<cx<T>>();
+                io.ring        = ring;
+                io.wp          = int(write_pos);
+                io.blocks      = 1;
+                io.overlap_add = 0;
+                io.logw        = logw;
+                io.nt          = nt;
+                io.chan0       = 0;
+                status         = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), cfg.inputs, stream);
+            }
+        });
+        if (status != NEO_B200_OK) { return status; }
+        NEO_TRY(forward_mac(1, 0, cfg.outputs, stream));
+        NEO_DISPATCH_LOGM(T, logb, {
+            if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
+                conv_c2r_io<T, LOGM> io{acc_w(), 1, y, 2 * size_t(m), T(1) / T(2 * m), 1};
+                status = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), cfg.outputs, stream);
+            }
+        });
+        if (status != NEO_B200_OK) { return status; }
+        if (commit) { advance(1); }
+        return NEO_B200_OK;
+    }
+
     // frame mode, bank: frame transform + ring insert + MAC + inverse frame transform in one kernel (Nyquist sequences first)
     int frame_fused_step(size_t out0, size_t nout, cudaStream_t stream)
     {
@@ -707,6 +745,10 @@ struct neo_b200_conv
     cudaStream_t s_in{nullptr}, s_out{nullptr};
     cudaEvent_t ev_start{nullptr};
     std::vector<cudaEvent_t> ev_in, ev_done;
+    // pageable HOST buffers of long calls are staged through these pinned chunks (two per direction), so the DMA engines run at PCIe
+    // speed and the copies overlap the kernels whatever memory the caller hands over
+    pinned_buffer pin_in[2], pin_out[2];
+    cudaEvent_t ev_h2d[2]{}, ev_d2h[2]{};
 
     int ensure_pipeline(size_t groups)
     {
@@ -714,6 +756,11 @@ struct neo_b200_conv
             NEO_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
             NEO_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
             NEO_CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+        }
+        if (ev_h2d[0] == nullptr) {
+            for (cudaEvent_t* ev : {&ev_h2d[0], &ev_h2d[1], &ev_d2h[0], &ev_d2h[1]}) {
+                NEO_CUDA_TRY(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+            }
         }
         while (ev_in.size() < groups) {
             cudaEvent_t a, b;
@@ -730,6 +777,9 @@ struct neo_b200_conv
         for (auto ev : ev_in) { cudaEventDestroy(ev); }
         for (auto ev : ev_done) { cudaEventDestroy(ev); }
         if (ev_start != nullptr) { cudaEventDestroy(ev_start); }
+        for (cudaEvent_t ev : {ev_h2d[0], ev_h2d[1], ev_d2h[0], ev_d2h[1]}) {
+            if (ev != nullptr) { cudaEventDestroy(ev); }
+        }
         if (s_in != nullptr) { cudaStreamDestroy(s_in); }
         if (s_out != nullptr) { cudaStreamDestroy(s_out); }
     }
@@ -802,6 +852,39 @@ int neo_b200_conv_reset(neo_b200_conv* conv)
     return NEO_CONV_ENGINE(conv, clear_state(conv->stream.stream));
 }
 
+// true when the CUDA runtime knows the pointer as page-locked host memory (cudaMallocHost / cudaHostRegister / torch pin_memory)
+static bool host_is_pinned(void const* p)
+{
+    cudaPointerAttributes attr{};
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) {
+        (void)cudaGetLastError();
+        return false;
+    }
+    return attr.type == cudaMemoryTypeHost;
+}
+
+// host memcpy with a few helper threads: one core moves ~10 GB/s, a PCIe 5 x16 link ~50 GB/s each way
+static void parallel_copy(void* dst, void const* src, size_t bytes)
+{
+    size_t const min_piece = size_t(4) << 20;
+    unsigned const hw      = std::max(1U, std::thread::hardware_concurrency());
+    size_t const pieces    = std::min<size_t>({size_t(8), size_t(hw), bytes / min_piece});
+    if (pieces <= 1) {
+        std::memcpy(dst, src, bytes);
+        return;
+    }
+    std::vector<std::thread> helpers;
+    size_t const piece = ((bytes / pieces) + 4095) / 4096 * 4096;
+    for (size_t i = 1; i < pieces; ++i) {
+        size_t const off = i * piece;
+        if (off >= bytes) { break; }
+        size_t const len = std::min(piece, bytes - off);
+        helpers.emplace_back([=] { std::memcpy(static_cast<char*>(dst) + off, static_cast<char const*>(src) + off, len); });
+    }
+    std::memcpy(dst, src, std::min(piece, bytes));
+    for (auto& t : helpers) { t.join(); }
+}
+
 extern "C++" template<typename T>
 int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, void* out, size_t blocks, int memspace)
 {
@@ -844,10 +927,39 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
         NEO_CUDA_TRY(cudaEventRecord(conv->ev_start, s));
         NEO_CUDA_TRY(cudaStreamWaitEvent(conv->s_in, conv->ev_start, 0));   // previous work on the handle's stream is done first
         NEO_CUDA_TRY(cudaStreamWaitEvent(conv->s_out, conv->ev_start, 0));
+        // Pinned caller memory is handed to the DMA engines as it is. Pageable memory (std::vector, numpy) would make every
+        // cudaMemcpyAsync host-synchronous and slow, so it is staged: the calling thread (plus helpers) copies group g into a pinned
+        // chunk while the device works on group g-1, and copies group g-2 out of its pinned chunk.
+        bool const staged      = !host_is_pinned(in) || !host_is_pinned(out);
+        size_t const max_group = ((chans + groups - 1) / groups) * stride * sizeof(T);
+        if (staged) {
+            for (int i = 0; i < 2; ++i) {
+                NEO_TRY(conv->pin_in[i].reserve(max_group));
+                NEO_TRY(conv->pin_out[i].reserve(max_group));
+            }
+        }
+        auto const range = [&](size_t g, size_t* c0, size_t* n) {
+            *c0 = g * chans / groups;
+            *n  = (g + 1) * chans / groups - *c0;
+        };
+        auto const drain = [&](size_t g) -> int {  // staged: group g has arrived in its pinned chunk, hand it to the caller
+            size_t c0, n;
+            range(g, &c0, &n);
+            NEO_CUDA_TRY(cudaEventSynchronize(conv->ev_d2h[g & 1]));
+            parallel_copy(static_cast<T*>(out) + c0 * stride, conv->pin_out[g & 1].ptr, n * stride * sizeof(T));
+            return NEO_B200_OK;
+        };
         for (size_t g = 0; g < groups; ++g) {
-            size_t const c0 = g * chans / groups, c1 = (g + 1) * chans / groups, n = c1 - c0;
-            NEO_CUDA_TRY(cudaMemcpyAsync(din + c0 * stride, static_cast<T const*>(in) + c0 * stride, n * stride * sizeof(T),
-                                         cudaMemcpyHostToDevice, conv->s_in));
+            size_t c0, n;
+            range(g, &c0, &n);
+            void const* src = static_cast<T const*>(in) + c0 * stride;
+            if (staged) {
+                if (g >= 2) { NEO_CUDA_TRY(cudaEventSynchronize(conv->ev_h2d[g & 1])); }  // the chunk's previous copy has left
+                parallel_copy(conv->pin_in[g & 1].ptr, src, n * stride * sizeof(T));
+                src = conv->pin_in[g & 1].ptr;
+            }
+            NEO_CUDA_TRY(cudaMemcpyAsync(din + c0 * stride, src, n * stride * sizeof(T), cudaMemcpyHostToDevice, conv->s_in));
+            if (staged) { NEO_CUDA_TRY(cudaEventRecord(conv->ev_h2d[g & 1], conv->s_in)); }
             NEO_CUDA_TRY(cudaEventRecord(conv->ev_in[g], conv->s_in));
             NEO_CUDA_TRY(cudaStreamWaitEvent(s, conv->ev_in[g], 0));
             NEO_TRY(e.forward_r2c(din + c0 * stride, stride, blocks, c0, n, s));
@@ -856,10 +968,15 @@ int conv_process_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* in, vo
                               blocks, s));
             NEO_CUDA_TRY(cudaEventRecord(conv->ev_done[g], s));
             NEO_CUDA_TRY(cudaStreamWaitEvent(conv->s_out, conv->ev_done[g], 0));
-            NEO_CUDA_TRY(cudaMemcpyAsync(static_cast<T*>(out) + c0 * stride, dout + c0 * stride, n * stride * sizeof(T),
-                                         cudaMemcpyDeviceToHost, conv->s_out));
+            if (staged && g >= 2) { NEO_TRY(drain(g - 2)); }  // frees pin_out[g & 1] for this group
+            void* const dst = staged ? conv->pin_out[g & 1].ptr : static_cast<void*>(static_cast<T*>(out) + c0 * stride);
+            NEO_CUDA_TRY(cudaMemcpyAsync(dst, dout + c0 * stride, n * stride * sizeof(T), cudaMemcpyDeviceToHost, conv->s_out));
+            if (staged) { NEO_CUDA_TRY(cudaEventRecord(conv->ev_d2h[g & 1], conv->s_out)); }
         }
         e.advance(blocks);
+        if (staged) {
+            for (size_t g = groups >= 2 ? groups - 2 : 0; g < groups; ++g) { NEO_TRY(drain(g)); }
+        }
         NEO_CUDA_TRY(cudaStreamSynchronize(conv->s_out));
     }
     NEO_CUDA_TRY(cudaStreamSynchronize(s));
@@ -995,6 +1112,51 @@ int neo_b200_conv_inverse(neo_b200_conv* conv, void const* spectra_device, void*
     if (count == 0) { return NEO_B200_OK; }
     if (conv->cfg.dtype == NEO_B200_F32) { return conv_inverse_impl<float>(conv, conv->f32, spectra_device, out, first, count, blocks, memspace); }
     return conv_inverse_impl<double>(conv, conv->f64, spectra_device, out, first, count, blocks, memspace);
+}
+
+extern "C++" template<typename T>
+int conv_window_impl(neo_b200_conv* conv, conv_engine<T>& e, void const* window, void* y, int commit, int memspace)
+{
+    cudaStream_t const s = conv->stream.stream;
+    size_t const bytes   = conv->cfg.outputs * 2 * size_t(e.m) * sizeof(T);
+    T const* win         = static_cast<T const*>(window);
+    T* out               = static_cast<T*>(y);
+    if (memspace == NEO_B200_HOST) {
+        NEO_TRY(e.stage_in.reserve(bytes));
+        NEO_TRY(e.stage_out.reserve(bytes));
+        NEO_CUDA_TRY(cudaMemcpyAsync(e.stage_in.ptr, window, bytes, cudaMemcpyHostToDevice, s));
+        win = e.stage_in.template as<T>();
+        out = e.stage_out.template as<T>();
+    }
+    NEO_TRY(e.window_step(win, out, commit != 0, s));
+    if (memspace == NEO_B200_HOST) {
+        NEO_CUDA_TRY(cudaMemcpyAsync(y, out, bytes, cudaMemcpyDeviceToHost, s));
+        NEO_CUDA_TRY(cudaStreamSynchronize(s));
+    }
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_process_window(neo_b200_conv* conv, void const* window, void* y, int commit, int memspace)
+{
+    NEO_TRY(conv_check_call(conv, 1));
+    if (window == nullptr || y == nullptr) { return fail(NEO_B200_ERR_INVALID, "null buffer"); }
+    if (conv->cfg.kind != NEO_B200_UPOLA || conv->cfg.topology != NEO_B200_DIAGONAL || conv->cfg.frame_blocks != 0 || conv->sharded) {
+        return fail(NEO_B200_ERR_INVALID, "process_window needs an unsharded overlap-add diagonal bank in the direct form");
+    }
+    if (conv->cfg.dtype == NEO_B200_F32) { return conv_window_impl<float>(conv, conv->f32, window, y, commit, memspace); }
+    return conv_window_impl<double>(conv, conv->f64, window, y, commit, memspace);
+}
+
+int neo_b200_conv_tail(neo_b200_conv* conv, void* tail, int memspace)
+{
+    if (conv == nullptr || tail == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (conv->cfg.kind != NEO_B200_UPOLA) { return fail(NEO_B200_ERR_INVALID, "only overlap-add handles keep a tail"); }
+    NEO_CUDA_TRY(cudaSetDevice(conv->device));
+    device_buffer const& buf = conv->cfg.dtype == NEO_B200_F32 ? conv->f32.tail : conv->f64.tail;
+    NEO_CUDA_TRY(cudaMemcpyAsync(tail, buf.ptr, buf.bytes, memspace == NEO_B200_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice,
+                                 conv->stream.stream));
+    NEO_CUDA_TRY(cudaStreamSynchronize(conv->stream.stream));
+    return NEO_B200_OK;
 }
 
 int neo_b200_conv_set_stream(neo_b200_conv* conv, void* cuda_stream)

@@ -599,6 +599,23 @@ struct conv_r2c_io
     __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const { r.dst[0] = mk<T>(dc, nyq); }
 };
 
+// neo::convolution::overlap_add_convolver (overlap_add_convolver.hpp:85-132) transforms its real window AS IT STANDS: after a call
+// that ended inside a block the window holds the previous inverse transform's output with the new samples written over part of it.
+// rows: [channels][2B] reals; the spectrum replaces delay-line row `wp` (the reference re-inserts into _current_segment, :94).
+template<typename T, int LOGM>
+struct window_r2c_io : conv_r2c_io<T, LOGM>
+{
+    using base = conv_r2c_io<T, LOGM>;
+    using C    = cx<T>;
+    using typename base::row_state;
+    __device__ __forceinline__ row_state open(size_t b) const
+    {
+        constexpr int H    = (1 << LOGM) / 2;
+        C const* const lo  = reinterpret_cast<C const*>(this->in + b * this->in_stride);
+        return {lo, lo + H, this->fdl + tiled_offset(this->chan0 + b, this->nt, this->logw, size_t(this->ring), size_t(this->wp), 0), nullptr};
+    }
+};
+
 // ---- inverse side: partial-plane gather + c2r + scale + overlap-save discard -------------------------------------------------
 template<typename T, int LOGM>
 struct conv_c2r_io

@@ -49,6 +49,9 @@ constexpr int fft_regcap(int kind, int logm)
 #ifdef NEO_B200_C2R_CAP
     if (kind == k_c2r) { return NEO_B200_C2R_CAP; }
 #endif
+    // 2^13 points = 512 threads: 64 registers (no spills, checked with -Xptxas -v) let TWO CTAs share an SM, so one CTA's global
+    // loads and barriers hide behind the other's butterflies; at 85 the SM held one CTA and its phases ran back to back
+    if (logm == 13) { return 64; }
     if (kind == k_c2r) { return logm == 10 ? 128 : 85; }
     return logm == 11 ? 72 : 85;
 }

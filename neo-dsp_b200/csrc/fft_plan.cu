@@ -372,8 +372,8 @@ struct rfft_engine
     // switches them off (A/B measurements)
     static bool stream_ok(void const* a, void const* b)
     {
-        static bool const off = std::getenv("NEO_B200_NO_STREAM") != nullptr;
-        return !off && (reinterpret_cast<std::uintptr_t>(a) & 15U) == 0 && (reinterpret_cast<std::uintptr_t>(b) & 15U) == 0;
+        static bool const on = std::getenv("NEO_B200_STREAM") != nullptr;
+        return on && (reinterpret_cast<std::uintptr_t>(a) & 15U) == 0 && (reinterpret_cast<std::uintptr_t>(b) & 15U) == 0;
     }
 
     // chunks keep the intermediate spectrum L2-resident between the two passes
@@ -438,7 +438,7 @@ struct rfft_engine
         }
         if (use_split) {
             if (order - 1 == k_split_lo) {
-                static bool const one_cta = std::getenv("NEO_B200_R2C_ONE_CTA") != nullptr;  // tuning knob
+                static bool const one_cta = std::getenv("NEO_B200_R2C_SPLIT14") == nullptr;  // tuning knob: two 4096-point CTAs instead
                 if (one_cta) {
                     return launch_r2c<T, k_split_lo>(r2c_plain_io<T, k_split_lo>{in, out}, tables_full.tw(), tables_full.rtw(), batch, stream);
                 }
@@ -483,7 +483,7 @@ struct rfft_engine
             auto const* wn = w_n.template as<cx<T>>();
             if (order - 1 == k_split_lo) {
                 // measured with the register caps in place: two CTAs 0.48-0.49 of HBM peak, one 8192-point CTA 0.44-0.45
-                static bool const one_cta = std::getenv("NEO_B200_C2R_ONE_CTA") != nullptr;  // tuning knob
+                static bool const one_cta = std::getenv("NEO_B200_C2R_SPLIT14") == nullptr;  // tuning knob: two 4096-point CTAs instead
                 if (!one_cta) { return launch_c2r_split2<T, k_split_lo - 1>(in, row_len, out, tables.tw(), tables.rtw(), wn, batch, stream); }
                 return launch_c2r<T, k_split_lo>(c2r_plain_io<T, k_split_lo>{in, out, row_len}, tables_full.tw(), tables_full.rtw(), batch,
                                                  stream);

@@ -313,11 +313,36 @@ static auto test_overlap_add_convolver() -> void
     REQUIRE(rel_l2(got, want) <= 1e-5);
     bool threw = false;
     try {
-        conv(vec<float>{got.data(), block + 7});
+        conv(vec<float>{got.data(), block - 1});  // overlap_add_convolver.hpp:74 asserts block_size <= extent
     } catch (std::invalid_argument const&) {
         threw = true;
     }
     REQUIRE(threw);
+
+    // calls that END INSIDE a block (overlap_add_convolver.hpp:85-132), against the oracle's restatement of the same object (kind 4):
+    // whole-block calls first (device-side tail), then ragged lengths, then whole blocks again while a block is half filled
+    for (std::size_t blk : {std::size_t(64), std::size_t(256)}) {
+        auto const p2 = neo_b200_num_partitions(taps, blk);
+        auto h2       = std::vector<Complex>(p2 * (blk + 1));
+        neo::b200::uniform_partition(ir.data(), 1, taps, blk, h2.data());
+        auto v2 = neo::b200::upola_convolver_v2<Complex>{};
+        v2.filter(mat<Complex const>{h2.data(), p2, blk + 1});
+        auto* o2 = oracle_conv_create_f32(4);
+        oracle_conv_filter_f32(o2, reinterpret_cast<float const*>(h2.data()), p2, blk + 1);
+        std::size_t const lengths[] = {2 * blk, blk, blk + 7, 3 * blk - 7, blk + blk / 2, 2 * blk, blk + blk / 2, blk + 1, 4 * blk - 1, blk};
+        std::size_t total = 0;
+        for (auto len : lengths) { total += len; }
+        auto sig2 = noise<float>(total, 23);
+        auto g2 = sig2, w2 = sig2;
+        std::size_t at = 0;
+        for (auto len : lengths) {
+            v2(vec<float>{g2.data() + at, len});
+            oracle_conv_process_f32(o2, w2.data() + at, len);
+            at += len;
+        }
+        oracle_conv_destroy_f32(o2);
+        REQUIRE(rel_l2(g2, w2) <= 1e-5);
+    }
 }
 
 int main()
