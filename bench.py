@@ -705,6 +705,7 @@ def measure_layout(args, pkg, torch, dist, rank, world, local, layout, T, frame,
     ys = [torch.empty((n_out, T * BLOCK), device="cuda", dtype=torch.float32) for _ in range(2)]
     max_over_ranks = lambda v: float(_allreduce_max(torch, dist, v))
     warm = max(3, args.warmup)
+    torch.cuda.synchronize()  # the bank's streams do not wait for torch's: the inputs above must be complete
     run_bank_timed(bank, xs, ys, warm, True)
     dist.barrier()
     torch.cuda.synchronize()
@@ -774,7 +775,9 @@ def bank_parity(pkg, torch, dist, bank, info, rank, T, frame):
     ys = []
     for s in range(steps):
         y = torch.empty((info["out_count"], T * BLOCK), device="cuda", dtype=torch.float32)
-        bank([x_all[:, s * T * BLOCK : (s + 1) * T * BLOCK].contiguous()], [y])
+        x = x_all[:, s * T * BLOCK : (s + 1) * T * BLOCK].contiguous()
+        torch.cuda.synchronize()  # the bank runs on its own streams: its device inputs must be complete when it is called
+        bank([x], [y])
         ys.append(y)
     got = torch.cat(ys, dim=1)
     err = torch.zeros(1, device="cuda", dtype=torch.float64)
@@ -815,6 +818,7 @@ def sharded_c4(args, pkg, torch, dist, rank, world, local):
         xs = [torch.rand((info["in_count"], T * B), device="cuda", dtype=torch.float32) * 2 - 1 for _ in range(2)]
         ys = [torch.empty((info["out_count"], T * B), device="cuda", dtype=torch.float32) for _ in range(2)]
         steps = 30 if T == 1 else 10
+        torch.cuda.synchronize()
         run_bank_timed(bank, xs, ys, 3, True)
         dist.barrier()
         ms, _ = run_bank_timed(bank, xs, ys, steps, True)
@@ -827,7 +831,9 @@ def sharded_c4(args, pkg, torch, dist, rank, world, local):
         got = []
         for s in range(nsteps):
             y = torch.empty((info["out_count"], T * B), device="cuda", dtype=torch.float32)
-            bank([x_all[:, s * T * B : (s + 1) * T * B].contiguous()], [y])
+            x = x_all[:, s * T * B : (s + 1) * T * B].contiguous()
+            torch.cuda.synchronize()  # the bank's own streams do not wait for torch's
+            bank([x], [y])
             got.append(y)
         got = torch.cat(got, dim=1)
         err = torch.zeros(1, device="cuda", dtype=torch.float64)

@@ -319,7 +319,13 @@ NEO_B200_API size_t neo_b200_conv_device_bytes(neo_b200_conv const* conv);
  * Row pointers: `in_rows[l]` / `out_rows[l]` belong to LOCAL rank l (0 .. neo_b200_bank_local_ranks-1) and point at the rows that rank
  * moves: [in_count][blocks*B] / [out_count][blocks*B] reals, rows in_first.. / out_first.. of the bank (neo_b200_bank_local_rank).
  * With every rank local and one [channels][blocks*B] array, in_rows[l] = array + in_first_l * blocks * B. HOST memory should be pinned
- * for the copies to overlap; DEVICE pointers must live on the rank's own device. */
+ * for the copies to overlap; DEVICE pointers must live on the rank's own device, and their contents must be complete when submit is
+ * called (the bank works on its own streams and does not wait for the caller's).
+ * When the group's handles run the fused frame kernel (frame mode, wide banks) the partial spectra are PUSHED: each shard's kernel
+ * stores the result rows of a channel directly into the inbox of the rank that finishes it (peer-mapped memory over NVLink; CUDA IPC
+ * mappings between processes, with a one-word ncclAllGather per step as the cross-process gate), and the c2r kernel sums its local
+ * inbox slots. Otherwise they are pulled (devices[] banks: the c2r kernel loads the shards' buffers through peer pointers) or summed
+ * by ncclReduceScatter (rank-per-process banks). */
 typedef struct neo_b200_bank neo_b200_bank;
 
 typedef struct neo_b200_bank_layout

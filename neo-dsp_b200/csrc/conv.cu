@@ -87,6 +87,9 @@ struct conv_engine
     device_buffer frame_tw8;  // stage twiddles of the 8-points-per-thread variant of the long frame transforms
     device_buffer fdl2, filter2, acc2, tickets2, nyq_acc;
     bool fused{false};  // bank with an unsplit partition loop: one kernel per frame step (frame_fused_kernel)
+    // set by a multi-device bank before forward_mac (frame_fused_io::y1_owner): where the result rows of each owner's channels go
+    cx<T>* push_dst[k_bank_max_shards] = {};
+    int push_owners{0}, push_own_count{0};
     frame_knobs knobs;  // environment knobs as they stood when the handle was created
 
     // optional per-phase timing with CUDA events on the handle's stream (bench.py's roofline numbers)
@@ -443,11 +446,12 @@ struct conv_engine
         NEO_DISPATCH_LOGL(logl, {
             frame_fused_io<T, true> nq{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), filter2.template as<cx<T>>(),
                                        acc_w(), nyq_acc.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2),
-                                       parts2, int(age0 / size_t(frame)), T(1) / T(2 * frame), out0};
+                                       parts2, int(age0 / size_t(frame)), T(1) / T(2 * frame), out0, {}, 0, 0};
             status = launch_frame_fused<T, LOGL, true>(nq, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout, stream, knobs);
             if (status == NEO_B200_OK) {
                 frame_fused_io<T, false> io{nq.x1, nq.fdl2, nq.filt2, nq.y1, nq.nyq_acc, fg, nq.new_half, nq.ring2, nq.slot,
-                                            nq.parts2, nq.age0, nq.scale, out0};
+                                            nq.parts2, nq.age0, nq.scale, out0, {}, push_owners, push_own_count};
+                for (int o = 0; o < push_owners; ++o) { io.y1_owner[o] = push_dst[o]; }
                 status = launch_frame_fused<T, LOGL, false>(io, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout << logb, stream, knobs);
             }
         });

@@ -113,6 +113,15 @@ struct bank_rank
     cudaEvent_t ev_in[2]{}, ev_fwd[2]{}, ev_red[2]{}, ev_c2r[2]{}, ev_out[2]{};
     cudaEvent_t t_begin{nullptr}, t_end{nullptr};  // neo_b200_bank_timer_*
     void* partial[2]{};            // partial spectra buffer the forward of (step & 1) wrote
+    // push form (fused frame kernel, partition shards > 1): every shard of the group writes the partial spectra of MY channels into
+    // my inbox while it computes them; slot (parity, shard) holds [out_count][T][B] complex. inbox_of[s] = base of shard s's inbox as
+    // seen from this rank (its own pointer, a peer-mapped pointer, or a CUDA IPC mapping of another process's allocation)
+    bool push{false};
+    device_buffer inbox;
+    size_t inbox_slot{0};          // complex elements per (parity, shard) slot
+    void* inbox_of[k_bank_max_shards] = {};
+    bool inbox_ipc[k_bank_max_shards] = {};
+    device_buffer gate;            // nccl transport: one word per shard, all-gathered as a cross-process stream barrier
     size_t gather_first{0}, gather_count{0};  // input rows the rank's forward reads (global index, count)
     nccl_api::comm_t comm_world{nullptr}, comm_in{nullptr}, comm_out{nullptr};
 
@@ -139,6 +148,9 @@ struct bank_rank
             if (comm_out != nullptr) { api->CommDestroy(comm_out); }
             if (comm_in != nullptr && comm_in != comm_world) { api->CommDestroy(comm_in); }
             if (comm_world != nullptr) { api->CommDestroy(comm_world); }
+        }
+        for (int s = 0; s < k_bank_max_shards; ++s) {
+            if (inbox_ipc[s] && inbox_of[s] != nullptr) { cudaIpcCloseMemHandle(inbox_of[s]); }
         }
         neo_b200_conv_destroy(conv);
         xring.release();
@@ -269,6 +281,58 @@ int bank_build_rank(neo_b200_bank* bank, bank_rank& r)
     NEO_TRY(r.xring.reserve(r.slots * r.slot_elems * esz));
     NEO_CUDA_TRY(cudaMemsetAsync(r.xring.ptr, 0, r.xring.bytes, r.s_in));
     NEO_CUDA_TRY(cudaStreamSynchronize(r.s_in));
+    bool fused = false;
+    (void)bank_with_engine(r.conv, [&](auto& e) {
+        fused = e.fused;
+        return NEO_B200_OK;
+    });
+    size_t const gp_n = bank->layout.partition_shards;
+    r.push            = fused && gp_n > 1 && std::getenv("NEO_B200_BANK_NO_PUSH") == nullptr;
+    if (r.push) {
+        r.inbox_slot = r.info.out_count * c.max_blocks * c.block;
+        NEO_TRY(r.inbox.reserve(2 * gp_n * r.inbox_slot * 2 * esz));
+        r.inbox_of[r.info.partition_shard] = r.inbox.ptr;
+    }
+    return NEO_B200_OK;
+}
+
+// push form: every rank of a group learns where the other shards' inboxes are. All ranks in one process: their pointers, readable
+// and writable through peer access. One rank per process: CUDA IPC handles, exchanged with ncclAllGather on the group communicator.
+int bank_connect_inboxes(neo_b200_bank* bank)
+{
+    size_t const gp_n = bank->layout.partition_shards;
+    for (auto& r : bank->ranks) {
+        if (!r.push) { continue; }
+        NEO_CUDA_TRY(cudaSetDevice(r.info.device));
+        size_t const base = r.info.channel_group * gp_n;
+        if (!bank->nccl) {
+            for (size_t s = 0; s < gp_n; ++s) {
+                bank_rank* const peer = bank->find(base + s);
+                if (!peer->push) { return fail(NEO_B200_ERR_INVALID, "the ranks of a group disagree about the push form"); }
+                r.inbox_of[s] = peer->inbox.ptr;
+            }
+            continue;
+        }
+        cudaIpcMemHandle_t mine{};
+        NEO_CUDA_TRY(cudaIpcGetMemHandle(&mine, r.inbox.ptr));
+        device_buffer staging;
+        NEO_TRY(staging.reserve(gp_n * sizeof(mine)));
+        char* const slots = staging.as<char>();
+        NEO_CUDA_TRY(cudaMemcpyAsync(slots + r.info.partition_shard * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, r.s_red));
+        NEO_NCCL_TRY(bank->api, bank->api->AllGather(slots + r.info.partition_shard * sizeof(mine), slots, sizeof(mine) / 4, nccl_api::k_float32,
+                                                     r.comm_out, r.s_red));
+        std::vector<cudaIpcMemHandle_t> all(gp_n);
+        NEO_CUDA_TRY(cudaMemcpyAsync(all.data(), slots, gp_n * sizeof(mine), cudaMemcpyDeviceToHost, r.s_red));
+        NEO_CUDA_TRY(cudaStreamSynchronize(r.s_red));
+        for (size_t s = 0; s < gp_n; ++s) {
+            if (s == r.info.partition_shard) { continue; }
+            NEO_CUDA_TRY(cudaIpcOpenMemHandle(&r.inbox_of[s], all[s], cudaIpcMemLazyEnablePeerAccess));
+            r.inbox_ipc[s] = true;
+        }
+        NEO_TRY(r.gate.reserve(gp_n * sizeof(float)));
+        NEO_CUDA_TRY(cudaMemsetAsync(r.gate.ptr, 0, r.gate.bytes, r.s_red));
+        NEO_CUDA_TRY(cudaStreamSynchronize(r.s_red));
+    }
     return NEO_B200_OK;
 }
 
@@ -367,7 +431,8 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         bank_domains(bank, r, &gather, &reduce);
         if (bank->nccl) {
             NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_in[b], 0));
-            if (gp_n > 1) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_red[b], 0)); }  // reduce-scatter of two steps ago read this buffer
+            // reduce-scatter of two steps ago read this buffer (push form: the gate of the previous step already orders it)
+            if (gp_n > 1 && !r.push) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_red[b], 0)); }
         } else {
             for (size_t p : gather) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, bank->find(p)->ev_in[b], 0)); }
             // the partial spectra buffer of this parity was last read by the c2r of two steps ago on every rank of the group
@@ -384,12 +449,28 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
             using E = std::remove_reference_t<decltype(e)>;
             if constexpr (std::is_same_v<E, conv_engine<T>>) {
                 NEO_TRY(e.forward_r2c(x, pitch, blocks, 0, r.conv->cfg.inputs, r.s_cmp));
+                e.push_owners = 0;
+                if (r.push) {  // result rows of owner o's channels go into o's inbox, slot (parity, my shard)
+                    e.push_owners    = int(gp_n);
+                    e.push_own_count = int(r.info.out_count);
+                    for (size_t o = 0; o < gp_n; ++o) {
+                        e.push_dst[o] = static_cast<cx<T>*>(r.inbox_of[o]) + (size_t(b) * gp_n + r.info.partition_shard) * r.inbox_slot;
+                    }
+                }
                 NEO_TRY(e.forward_mac(blocks, 0, r.conv->cfg.outputs, r.s_cmp));
                 r.partial[b] = e.acc_w();
                 e.advance(blocks);
             }
             return NEO_B200_OK;
         }));
+        if (r.push && bank->nccl) {
+            // gate of step i: a tiny all-gather on the compute stream. It completes on this rank only after every shard of the group has
+            // reached it, i.e. finished its forward of step i (its stores into my inbox are done) and -- because each rank waits for
+            // its own c2r of step i-1 first -- finished reading the inbox slots that the forwards of step i+1 will overwrite.
+            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_c2r[b ^ 1], 0));
+            float* const words = r.gate.as<float>();
+            NEO_NCCL_TRY(bank->api, bank->api->AllGather(words + r.info.partition_shard, words, 1, nccl_api::k_float32, r.comm_out, r.s_cmp));
+        }
         NEO_CUDA_TRY(cudaEventRecord(r.ev_fwd[b], r.s_cmp));
     }
 
@@ -406,6 +487,15 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         if (gp_n == 1) {
             NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[b], 0));
             srcs[0] = static_cast<cx<T> const*>(r.partial[b]) + own_in_group * blocks * c.block;
+        } else if (r.push) {
+            // the shards have pushed their partial spectra of my channels into my inbox: a LOCAL sum, in shard order
+            if (bank->nccl) {
+                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[b], 0));  // recorded behind the gate
+            } else {
+                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, bank->find(p)->ev_fwd[b], 0)); }
+            }
+            nsrc = int(gp_n);
+            for (size_t s = 0; s < gp_n; ++s) { srcs[s] = r.inbox.template as<cx<T>>() + (size_t(b) * gp_n + s) * r.inbox_slot; }
         } else if (bank->nccl) {
             NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_red, r.ev_fwd[b], 0));
             NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_red, r.ev_c2r[b], 0));  // the c2r of two steps ago read red[b]
@@ -509,6 +599,7 @@ int neo_b200_bank_create(neo_b200_bank** out, neo_b200_conv_config const* config
         }
     }
     for (auto& r : bank->ranks) { NEO_TRY(bank_build_rank(bank.get(), r)); }
+    NEO_TRY(bank_connect_inboxes(bank.get()));
     cudaSetDevice(before);
     *out = bank.release();
     return NEO_B200_OK;
@@ -545,6 +636,7 @@ int neo_b200_bank_create_rank(neo_b200_bank** out, neo_b200_conv_config const* c
         if (need_out) { NEO_NCCL_TRY(bank->api, bank->api->CommSplit(r.comm_world, color, key, &r.comm_out, nullptr)); }
     }
     NEO_TRY(bank_build_rank(bank.get(), r));
+    NEO_TRY(bank_connect_inboxes(bank.get()));
     *out = bank.release();
     return NEO_B200_OK;
 }
@@ -723,7 +815,7 @@ size_t neo_b200_bank_device_bytes(neo_b200_bank const* bank, size_t local_index)
 {
     if (bank == nullptr || local_index >= bank->ranks.size()) { return 0; }
     bank_rank const& r = bank->ranks[local_index];
-    return neo_b200_conv_device_bytes(r.conv) + r.xring.bytes + r.red[0].bytes + r.red[1].bytes + r.yout[0].bytes + r.yout[1].bytes;
+    return neo_b200_conv_device_bytes(r.conv) + r.xring.bytes + r.red[0].bytes + r.red[1].bytes + r.yout[0].bytes + r.yout[1].bytes + r.inbox.bytes;
 }
 
 }  // extern "C"

@@ -322,6 +322,11 @@ struct frame_fused_io
     int parts2, age0;  // local second-level partitions and the age of the first one
     T scale;           // 1 / L
     size_t chan0;
+    // multi-device bank, push form: the T result rows of channel c go to the device that finishes c (owner = c / own_count), straight
+    // into that device's inbox through a peer-mapped pointer (st.global over NVLink) -- the exchange of the partial spectra rides on
+    // the stores of the kernel that produces them. owners <= 1: everything goes to y1.
+    C* y1_owner[k_bank_max_shards];
+    int owners, own_count;
 };
 
 // REGCAP: registers per thread the kernel is held to (resident CTAs = 65536 / REGCAP / threads, at least one)
@@ -540,7 +545,11 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
         }
         cta_fft<T, LOGL, 1, LOGE_F>::run(v, sm, tw, t);
         if (live) {
-            C* const dst = io.y1 + ((chan * g.frame) << g.logb) + k;
+            C* dst = io.y1 + ((chan * g.frame) << g.logb) + k;
+            if (io.owners > 1) {
+                int const o = int(chan) / io.own_count;
+                dst         = io.y1_owner[o] + (((chan - size_t(o) * io.own_count) * g.frame) << g.logb) + k;
+            }
 #pragma unroll
             for (int e = 0; e < E; ++e) {
                 int const n = t + e * TN;

@@ -140,6 +140,33 @@ def test_bank_device_buffers_and_profile(gpu, orc):
     bank.close()
 
 
+@pytest.mark.parametrize("block,T,P,channels,layout", [(256, 8, 32, 64, (1, 2)), (128, 32, 128, 64, (2, 2)), (128, 32, 128, 32, (1, 4))])
+def test_bank_push_form_fused_frame_kernel(gpu, orc, monkeypatch, block, T, P, channels, layout):
+    # banks wide enough for the fused frame kernel: every partition shard writes the partial spectra of a channel straight into the
+    # inbox of the rank that finishes it (peer stores inside frame_fused_kernel), the c2r kernel sums the inbox slots. Same answer
+    # as the pull form (NEO_B200_BANK_NO_PUSH: c2r loads the shards' buffers) and as the oracle.
+    steps = 5
+    ir, sig = make_case(orc, channels, block * P - 3, block, T * steps)
+    want = orc.convolve_blocks(0, orc.uniform_partition(ir, block), sig)
+    n = layout[0] * layout[1]
+    results, sizes = {}, {}
+    for form in ("push", "pull"):
+        if form == "pull":
+            monkeypatch.setenv("NEO_B200_BANK_NO_PUSH", "1")
+        bank = gpu.Bank(gpu.UPOLS, np.float32, gpu.DIAGONAL, channels, channels, block, P, frame_blocks=T, layout=layout, devices=devices_for(gpu, n))
+        bank.impulse_global(ir)
+        results[form] = run_bank_steps(bank, sig, block, T, pipelined=True)
+        sizes[form] = bank.device_bytes(0)
+        assert rel_l2(results[form], want) <= 1e-5, (form, rel_l2(results[form], want))
+        for st in range(steps):
+            sl = slice(st * T * block, (st + 1) * T * block)
+            assert rel_l2(results[form][:, sl], want[:, sl]) <= 2e-5, (form, st)
+        bank.close()
+    monkeypatch.delenv("NEO_B200_BANK_NO_PUSH")
+    assert sizes["push"] > sizes["pull"], "the push form allocates inboxes: it was not taken"
+    assert np.array_equal(results["push"], results["pull"])  # same partial spectra summed in the same shard order
+
+
 def test_bank_error_contract(gpu):
     with pytest.raises(RuntimeError):  # layout does not match the number of devices
         gpu.Bank(gpu.UPOLS, np.float32, gpu.DIAGONAL, 8, 8, 64, 8, layout=(2, 2), devices=[0, 0])
