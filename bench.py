@@ -686,12 +686,13 @@ def make_bank(pkg, torch, dist, rank, world, local, layout, T, frame, topology=N
 
 
 def run_bank_timed(bank, xs, ys, steps, device: bool):
-    """`steps` pipelined steps (two in flight); returns device milliseconds (CUDA events on the bank's streams) and wall seconds"""
+    """`steps` pipelined steps (three in flight: the copy-in of step i+2 and the copy-out of step i-1 overlap the kernels of step i);
+    returns device milliseconds (CUDA events on the bank's streams) and wall seconds"""
     t0 = time.perf_counter()
     bank.timer_start()
     for i in range(steps):
         bank.submit([xs[i % len(xs)]], [ys[i % len(ys)]])
-        if i >= 1:
+        if i >= 2:
             bank.wait()
     ms = bank.timer_stop()
     return ms, time.perf_counter() - t0
@@ -702,7 +703,7 @@ def measure_layout(args, pkg, torch, dist, rank, world, local, layout, T, frame,
     bank, info = make_bank(pkg, torch, dist, rank, world, local, layout, T, frame)
     n_in, n_out = info["in_count"], info["out_count"]
     xs = [torch.rand((n_in, T * BLOCK), device="cuda", dtype=torch.float32) * 2 - 1 for _ in range(4)]
-    ys = [torch.empty((n_out, T * BLOCK), device="cuda", dtype=torch.float32) for _ in range(2)]
+    ys = [torch.empty((n_out, T * BLOCK), device="cuda", dtype=torch.float32) for _ in range(3)]
     max_over_ranks = lambda v: float(_allreduce_max(torch, dist, v))
     warm = max(3, args.warmup)
     torch.cuda.synchronize()  # the bank's streams do not wait for torch's: the inputs above must be complete
@@ -743,10 +744,10 @@ def measure_layout(args, pkg, torch, dist, rank, world, local, layout, T, frame,
     }
 
     if want_e2e:
-        # end to end: every rank moves ITS 1/N of the rows between pinned host memory and the device, two steps in flight
-        hx = [torch.rand((n_in, T * BLOCK), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
-        hy = [torch.empty((n_out, T * BLOCK), dtype=torch.float32).pin_memory().numpy() for _ in range(2)]
-        run_bank_timed(bank, hx, hy, 3, False)
+        # end to end: every rank moves ITS 1/N of the rows between pinned host memory and the device, three steps in flight
+        hx = [torch.rand((n_in, T * BLOCK), dtype=torch.float32).pin_memory().numpy() for _ in range(3)]
+        hy = [torch.empty((n_out, T * BLOCK), dtype=torch.float32).pin_memory().numpy() for _ in range(3)]
+        run_bank_timed(bank, hx, hy, 4, False)
         n_e2e = max(4, min(steps, 20))
         dist.barrier()
         _, wall = run_bank_timed(bank, hx, hy, n_e2e, False)
@@ -815,8 +816,8 @@ def sharded_c4(args, pkg, torch, dist, rank, world, local):
     out = {"workload": "C4: 64-in x 64-out convolution matrix, B=256, 2^16-tap IRs, sharded by output channel", "layout": f"{world} output groups x 1"}
     for frame, T in ((0, 1), (64, 64)):
         bank, info = make_bank(pkg, torch, dist, rank, world, local, (world, 1), T, frame, topology=pkg.MATRIX, outputs=O, inputs=I, block=B, taps=L, seed=4100)
-        xs = [torch.rand((info["in_count"], T * B), device="cuda", dtype=torch.float32) * 2 - 1 for _ in range(2)]
-        ys = [torch.empty((info["out_count"], T * B), device="cuda", dtype=torch.float32) for _ in range(2)]
+        xs = [torch.rand((info["in_count"], T * B), device="cuda", dtype=torch.float32) * 2 - 1 for _ in range(3)]
+        ys = [torch.empty((info["out_count"], T * B), device="cuda", dtype=torch.float32) for _ in range(3)]
         steps = 30 if T == 1 else 10
         torch.cuda.synchronize()
         run_bank_timed(bank, xs, ys, 3, True)
@@ -894,7 +895,7 @@ def run_sharded(args, pkg, torch, dist, emit, rank, world, local, peak, peak_src
             "config": {
                 "workload": WORKLOAD, "blocks_per_call": T, "mode": main["mode"],
                 "sharding": f"library bank (neo_b200_bank_*, NCCL transport): {main['layout']}; partial spectra of a group summed by "
-                            "ncclReduceScatter over NVLink, input rows of a group exchanged by ncclAllGather, two steps in flight",
+                            "ncclReduceScatter over NVLink, input rows of a group exchanged by ncclAllGather, three steps in flight",
                 "layout": {"channel_groups": layout[0], "partition_shards": layout[1]},
                 "l2": "working set per rank and step (filter + delay line, several GB) exceeds the 126 MB L2; 4 rotating input buffers",
                 "realtime_x_aggregate_48k": main["value"] * 1e6 / 48000.0, "realtime_x_wall_1024ch_48k": main["realtime_x_wall_1024ch_48k"],

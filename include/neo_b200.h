@@ -370,9 +370,9 @@ NEO_B200_API int neo_b200_bank_set_filter(neo_b200_bank* bank, void const* const
 NEO_B200_API int neo_b200_bank_reset(neo_b200_bank* bank);
 
 /* `convolver(block)` for every channel of the bank, `blocks` blocks per call (uniform_partitioned_convolver.hpp:48-65).
- * submit only enqueues; wait returns when the OLDEST outstanding submit has delivered its output rows. Up to two submits may be
- * outstanding (a third waits inside submit), so the input copy of step i+1 and the output copy of step i-1 overlap the kernels of
- * step i. In rank-per-process banks every rank must make the same sequence of calls. process = submit + wait until idle. */
+ * submit only enqueues; wait returns when the OLDEST outstanding submit has delivered its output rows. Up to three submits may be
+ * outstanding (a fourth waits inside submit), so the input copy of step i+2 and the output copy of step i-1 overlap the kernels of
+ * step i and both directions of the host link stay busy. In rank-per-process banks every rank must make the same sequence of calls. process = submit + wait until idle. */
 NEO_B200_API int neo_b200_bank_submit(neo_b200_bank* bank, void const* const* in_rows, void* const* out_rows, size_t blocks, int memspace);
 NEO_B200_API int neo_b200_bank_wait(neo_b200_bank* bank);
 NEO_B200_API int neo_b200_bank_process(neo_b200_bank* bank, void const* const* in_rows, void* const* out_rows, size_t blocks, int memspace);

@@ -100,6 +100,10 @@ struct nccl_api
         }                                                                                                                          \
     } while (0)
 
+// steps in flight: the copy-in of step i+2 and the copy-out of step i-1 overlap the kernels of step i (the spectra buffers between
+// forward and inverse stay double-buffered; their reuse is ordered by events, it does not limit the depth of the I/O pipeline)
+constexpr unsigned k_bank_depth = 3;
+
 // ---- one rank of the bank that lives in this process -----------------------------------------------------------------------------------
 struct bank_rank
 {
@@ -109,8 +113,9 @@ struct bank_rank
     device_buffer xring;           // [slots][gather_count][max_blocks * B] time-domain input rows
     size_t slots{0}, slot_elems{0};
     device_buffer red[2];          // nccl transport: reduce-scatter result [out_count][T][B] complex
-    device_buffer yout[2];         // HOST calls: finished rows on the device before they go back
-    cudaEvent_t ev_in[2]{}, ev_fwd[2]{}, ev_red[2]{}, ev_c2r[2]{}, ev_out[2]{};
+    device_buffer yout[3];         // HOST calls: finished rows on the device before they go back (step mod 3)
+    // per-step events, rings of four indexed by step & 3: up to three steps are in flight and a step waits on steps up to three back
+    cudaEvent_t ev_in[4]{}, ev_fwd[4]{}, ev_red[4]{}, ev_c2r[4]{}, ev_out[4]{};
     cudaEvent_t t_begin{nullptr}, t_end{nullptr};  // neo_b200_bank_timer_*
     void* partial[2]{};            // partial spectra buffer the forward of (step & 1) wrote
     // push form (fused frame kernel, partition shards > 1): every shard of the group writes the partial spectra of MY channels into
@@ -128,7 +133,7 @@ struct bank_rank
     int create_streams()
     {
         for (cudaStream_t* s : {&s_in, &s_cmp, &s_red, &s_out}) { NEO_CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking)); }
-        for (int b = 0; b < 2; ++b) {
+        for (int b = 0; b < 4; ++b) {
             for (cudaEvent_t* e : {&ev_in[b], &ev_fwd[b], &ev_red[b], &ev_c2r[b], &ev_out[b]}) {
                 NEO_CUDA_TRY(cudaEventCreateWithFlags(e, cudaEventDisableTiming));
             }
@@ -154,9 +159,9 @@ struct bank_rank
         }
         neo_b200_conv_destroy(conv);
         xring.release();
-        for (int b = 0; b < 2; ++b) {
-            red[b].release();
-            yout[b].release();
+        for (auto& buf : red) { buf.release(); }
+        for (auto& buf : yout) { buf.release(); }
+        for (int b = 0; b < 4; ++b) {
             for (cudaEvent_t e : {ev_in[b], ev_fwd[b], ev_red[b], ev_c2r[b], ev_out[b]}) {
                 if (e != nullptr) { cudaEventDestroy(e); }
             }
@@ -276,7 +281,7 @@ int bank_build_rank(neo_b200_bank* bank, bank_rank& r)
     r.gather_first = c.topology == NEO_B200_MATRIX ? 0 : r.info.group_first;
     r.gather_count = c.topology == NEO_B200_MATRIX ? c.inputs : r.info.group_count;
     size_t const esz = elem_size(c.dtype);
-    r.slots          = (c.frame_blocks > 0 ? r.info.delay_blocks / c.frame_blocks : 0) + 2;
+    r.slots          = (c.frame_blocks > 0 ? r.info.delay_blocks / c.frame_blocks : 0) + k_bank_depth;
     r.slot_elems     = r.gather_count * c.max_blocks * c.block;
     NEO_TRY(r.xring.reserve(r.slots * r.slot_elems * esz));
     NEO_CUDA_TRY(cudaMemsetAsync(r.xring.ptr, 0, r.xring.bytes, r.s_in));
@@ -372,10 +377,10 @@ inline void bank_domains(neo_b200_bank const* bank, bank_rank const& r, std::vec
 int bank_wait_oldest(neo_b200_bank* bank)
 {
     if (bank->pending.empty()) { return NEO_B200_OK; }
-    int const b = int(bank->pending.front() & 1U);
+    int const e = int(bank->pending.front() & 3U);
     for (auto& r : bank->ranks) {
         NEO_CUDA_TRY(cudaSetDevice(r.info.device));
-        NEO_CUDA_TRY(cudaEventSynchronize(r.ev_out[b]));
+        NEO_CUDA_TRY(cudaEventSynchronize(r.ev_out[e]));
     }
     bank->pending.pop_front();
     return NEO_B200_OK;
@@ -387,7 +392,14 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
     neo_b200_conv_config const& c = bank->cfg;
     size_t const pitch            = blocks * c.block;          // reals per row of this call
     std::uint64_t const step      = bank->step;
-    int const b                   = int(step & 1U);
+    int const b                   = int(step & 1U);  // parity of the double-buffered spectra (partial buffers, inbox slots)
+    int const e0                  = int(step & 3U);  // this step's slot in the event rings
+    // event of `back` steps ago in a ring (nullptr before the first step: nothing to wait for)
+    auto const ago = [&](cudaEvent_t const (&ring)[4], unsigned back) -> cudaEvent_t { return step >= back ? ring[(step - back) & 3U] : nullptr; };
+    auto const wait_for = [&](cudaStream_t s, cudaEvent_t ev) -> int {
+        if (ev != nullptr) { NEO_CUDA_TRY(cudaStreamWaitEvent(s, ev, 0)); }
+        return NEO_B200_OK;
+    };
     size_t const gp_n             = bank->layout.partition_shards;
     bool const host               = memspace == NEO_B200_HOST;
     cudaMemcpyKind const kin      = host ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToDevice;
@@ -398,11 +410,11 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         NEO_CUDA_TRY(cudaSetDevice(r.info.device));
         std::vector<size_t> gather;
         bank_domains(bank, r, &gather, nullptr);
-        // the slot about to be overwritten was last read by the forward of two steps ago, on every rank it is pushed to
+        // the slot about to be overwritten was last read by the forward of k_bank_depth steps ago, on every rank it is pushed to
         if (bank->nccl) {
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_in, r.ev_fwd[b], 0));
+            NEO_TRY(wait_for(r.s_in, ago(r.ev_fwd, k_bank_depth)));
         } else {
-            for (size_t p : gather) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_in, bank->find(p)->ev_fwd[b], 0)); }
+            for (size_t p : gather) { NEO_TRY(wait_for(r.s_in, ago(bank->find(p)->ev_fwd, k_bank_depth))); }
         }
         T* const slot      = r.xring.template as<T>() + (step % r.slots) * r.slot_elems;
         size_t const mine  = (r.info.in_first - r.gather_first) * pitch;  // offset of the rank's own rows inside a slot
@@ -421,7 +433,7 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
                 }
             }
         }
-        NEO_CUDA_TRY(cudaEventRecord(r.ev_in[b], r.s_in));
+        NEO_CUDA_TRY(cudaEventRecord(r.ev_in[e0], r.s_in));
     }
 
     // ---- 2. forward: window + r2c + delay line + MAC of the rank's partitions -> partial spectra ----
@@ -430,18 +442,18 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         std::vector<size_t> gather, reduce;
         bank_domains(bank, r, &gather, &reduce);
         if (bank->nccl) {
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_in[b], 0));
+            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_in[e0], 0));
             // reduce-scatter of two steps ago read this buffer (push form: the gate of the previous step already orders it)
-            if (gp_n > 1 && !r.push) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_red[b], 0)); }
+            if (gp_n > 1 && !r.push) { NEO_TRY(wait_for(r.s_cmp, ago(r.ev_red, 2))); }
         } else {
-            for (size_t p : gather) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, bank->find(p)->ev_in[b], 0)); }
-            // the partial spectra buffer of this parity was last read by the c2r of two steps ago on every rank of the group
+            for (size_t p : gather) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, bank->find(p)->ev_in[e0], 0)); }
+            // the partial spectra buffer / inbox slot of this parity was last read by the c2r of two steps ago on every rank of the group
             if (gp_n > 1) {
-                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, bank->find(p)->ev_c2r[b], 0)); }
+                for (size_t p : reduce) { NEO_TRY(wait_for(r.s_cmp, ago(bank->find(p)->ev_c2r, 2))); }
             }
         }
         // an unsharded handle has a single spectra buffer: the c2r of the previous step must have read it
-        if (gp_n == 1) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_c2r[b ^ 1], 0)); }
+        if (gp_n == 1) { NEO_TRY(wait_for(r.s_cmp, ago(r.ev_c2r, 1))); }
         size_t const delay_slots = c.frame_blocks > 0 ? r.info.delay_blocks / c.frame_blocks : 0;
         size_t const read_slot   = (step + r.slots - delay_slots) % r.slots;  // zeros until the delayed step exists
         T const* const x         = r.xring.template as<T>() + read_slot * r.slot_elems;
@@ -467,11 +479,11 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
             // gate of step i: a tiny all-gather on the compute stream. It completes on this rank only after every shard of the group has
             // reached it, i.e. finished its forward of step i (its stores into my inbox are done) and -- because each rank waits for
             // its own c2r of step i-1 first -- finished reading the inbox slots that the forwards of step i+1 will overwrite.
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_c2r[b ^ 1], 0));
+            NEO_TRY(wait_for(r.s_cmp, ago(r.ev_c2r, 1)));
             float* const words = r.gate.as<float>();
             NEO_NCCL_TRY(bank->api, bank->api->AllGather(words + r.info.partition_shard, words, 1, nccl_api::k_float32, r.comm_out, r.s_cmp));
         }
-        NEO_CUDA_TRY(cudaEventRecord(r.ev_fwd[b], r.s_cmp));
+        NEO_CUDA_TRY(cudaEventRecord(r.ev_fwd[e0], r.s_cmp));
     }
 
     // ---- 3. reduction over the partition shards + c2r for the rank's own channels; 4. output rows ----
@@ -485,39 +497,40 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         cx<T> const* srcs[k_bank_max_shards];
         int nsrc = 1;
         if (gp_n == 1) {
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[b], 0));
+            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[e0], 0));
             srcs[0] = static_cast<cx<T> const*>(r.partial[b]) + own_in_group * blocks * c.block;
         } else if (r.push) {
             // the shards have pushed their partial spectra of my channels into my inbox: a LOCAL sum, in shard order
             if (bank->nccl) {
-                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[b], 0));  // recorded behind the gate
+                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[e0], 0));  // recorded behind the gate
             } else {
-                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, bank->find(p)->ev_fwd[b], 0)); }
+                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, bank->find(p)->ev_fwd[e0], 0)); }
             }
             nsrc = int(gp_n);
             for (size_t s = 0; s < gp_n; ++s) { srcs[s] = r.inbox.template as<cx<T>>() + (size_t(b) * gp_n + s) * r.inbox_slot; }
         } else if (bank->nccl) {
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_red, r.ev_fwd[b], 0));
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_red, r.ev_c2r[b], 0));  // the c2r of two steps ago read red[b]
+            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_red, r.ev_fwd[e0], 0));
+            NEO_TRY(wait_for(r.s_red, ago(r.ev_c2r, 2)));  // the c2r of two steps ago read red[b]
             NEO_TRY(r.red[b].reserve(own_elems * sizeof(cx<T>)));
             NEO_NCCL_TRY(bank->api, bank->api->ReduceScatter(r.partial[b], r.red[b].ptr, own_elems * 2,
                                                              sizeof(T) == 4 ? nccl_api::k_float32 : nccl_api::k_float64, nccl_api::k_sum,
                                                              r.comm_out, r.s_red));
-            NEO_CUDA_TRY(cudaEventRecord(r.ev_red[b], r.s_red));
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_red[b], 0));
+            NEO_CUDA_TRY(cudaEventRecord(r.ev_red[e0], r.s_red));
+            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_red[e0], 0));
             srcs[0] = r.red[b].template as<cx<T>>();
         } else {
             nsrc = 0;
             for (size_t p : reduce) {  // shard order: every rank sums in the same order
                 bank_rank* const peer = bank->find(p);
-                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, peer->ev_fwd[b], 0));
+                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, peer->ev_fwd[e0], 0));
                 srcs[nsrc++] = static_cast<cx<T> const*>(peer->partial[b]) + own_in_group * blocks * c.block;
             }
         }
         T* dst = static_cast<T*>(out_rows[l]);
         if (host) {
-            NEO_TRY(r.yout[b].reserve(r.info.out_count * c.max_blocks * c.block * sizeof(T)));
-            dst = r.yout[b].template as<T>();
+            device_buffer& stage = r.yout[step % k_bank_depth];  // its previous copy-out is ahead of this step on the same stream
+            NEO_TRY(stage.reserve(r.info.out_count * c.max_blocks * c.block * sizeof(T)));
+            dst = stage.template as<T>();
         }
         NEO_TRY(bank_with_engine(r.conv, [&](auto& e) -> int {
             using E = std::remove_reference_t<decltype(e)>;
@@ -526,11 +539,11 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
             }
             return NEO_B200_OK;
         }));
-        NEO_CUDA_TRY(cudaEventRecord(r.ev_c2r[b], r.s_out));
+        NEO_CUDA_TRY(cudaEventRecord(r.ev_c2r[e0], r.s_out));
         if (host) {
             NEO_CUDA_TRY(cudaMemcpyAsync(out_rows[l], dst, r.info.out_count * pitch * sizeof(T), cudaMemcpyDeviceToHost, r.s_out));
         }
-        NEO_CUDA_TRY(cudaEventRecord(r.ev_out[b], r.s_out));
+        NEO_CUDA_TRY(cudaEventRecord(r.ev_out[e0], r.s_out));
     }
     bank->pending.push_back(step);
     ++bank->step;
@@ -726,7 +739,7 @@ int neo_b200_bank_reset(neo_b200_bank* bank)
 int neo_b200_bank_submit(neo_b200_bank* bank, void const* const* in_rows, void* const* out_rows, size_t blocks, int memspace)
 {
     NEO_TRY(bank_check_call(bank, in_rows, out_rows, blocks));
-    while (bank->pending.size() >= 2) { NEO_TRY(bank_wait_oldest(bank)); }  // every buffer of a step is double-buffered: two steps in flight
+    while (bank->pending.size() >= size_t(k_bank_depth)) { NEO_TRY(bank_wait_oldest(bank)); }  // input ring and output staging are k_bank_depth deep
     int before = 0;
     cudaGetDevice(&before);
     int const status = bank->cfg.dtype == NEO_B200_F32 ? bank_submit_impl<float>(bank, in_rows, out_rows, blocks, memspace)
@@ -815,7 +828,7 @@ size_t neo_b200_bank_device_bytes(neo_b200_bank const* bank, size_t local_index)
 {
     if (bank == nullptr || local_index >= bank->ranks.size()) { return 0; }
     bank_rank const& r = bank->ranks[local_index];
-    return neo_b200_conv_device_bytes(r.conv) + r.xring.bytes + r.red[0].bytes + r.red[1].bytes + r.yout[0].bytes + r.yout[1].bytes + r.inbox.bytes;
+    return neo_b200_conv_device_bytes(r.conv) + r.xring.bytes + r.red[0].bytes + r.red[1].bytes + r.yout[0].bytes + r.yout[1].bytes + r.yout[2].bytes + r.inbox.bytes;
 }
 
 }  // extern "C"

@@ -4,9 +4,12 @@
 #include "fft_kernels.cuh"
 #include "fft_large.cuh"
 #include "fft_split.cuh"
-#include "fft_stream.cuh"
+// two forms of the 65536-point real transform that were measured and lost: compiled only on request
+#ifdef NEO_B200_EXPERIMENTAL_FFT
 #include "fft_cluster.cuh"
 #include "fft_pair.cuh"
+#include "fft_stream.cuh"  // persistent CTAs fed by TMA bulk copies, N = 2^13 / 2^14 (NEO_B200_STREAM=1): 0.65/0.71 and 0.52/0.54 of HBM peak
+#endif
 
 #include <cmath>
 #include <cstdlib>
@@ -293,8 +296,10 @@ struct rfft_engine
     large_rfft<T> large;
     bool use_large{false};
     bool use_split{false};       // two CTAs per transform (fft_split.cuh)
+#ifdef NEO_B200_EXPERIMENTAL_FFT
     bool use_cluster{false};     // float32, N = 2^14..2^16: persistent thread-block-cluster four-step (fft_cluster.cuh)
     rfft_cluster_plan cluster;
+#endif
     bool use_split15{false};     // float32, N = 2^16 as two 1024-thread CTAs of 2^14 points each (knob)
     bool use_pair{false};        // float32, N = 2^16: one transform per CTA pair, exchange tile in distributed shared memory (fft_pair.cuh)
     bool use_big_cta{false};     // float32, M = 2^14: one 1024-thread CTA per transform (139 KB exchange tile)
@@ -320,6 +325,7 @@ struct rfft_engine
             //   four-CTA split c2c + Hermitian pass (two HBM-side passes)                          0.12 / 0.15   NEO_B200_NO_SPLIT15
             // The DSMEM form loses because half of every exchange crosses the SM-to-SM network (~20 B/clk per SM) and each of its
             // 8 exchanges ends in a cluster barrier; the cluster four-step because its phases serialise.
+#ifdef NEO_B200_EXPERIMENTAL_FFT
             bool const all = std::getenv("NEO_B200_CLUSTER_ALL") != nullptr;
             if (order == 16 && std::getenv("NEO_B200_PAIR") != nullptr) {
                 use_pair = true;
@@ -330,6 +336,7 @@ struct rfft_engine
                 use_cluster = true;
                 return cluster.init(order, stream);
             }
+#endif
             if (order == 16 && std::getenv("NEO_B200_NO_SPLIT15") == nullptr) {
                 use_split15 = true;
                 NEO_TRY(tables.build(logm - 1, true, stream));
@@ -421,14 +428,17 @@ struct rfft_engine
         if (order == 0) { return large_rfft<T>::size_one_forward(in, out, batch, stream); }
         if constexpr (sizeof(T) == 4) {
             if (use_split15) { return launch_r2c_split2<T, 14>(in, out, tables.tw(), tables.rtw(), batch, stream); }
+#ifdef NEO_B200_EXPERIMENTAL_FFT
             if (use_pair) { return launch_r2c_pair<15>(in, out, tables.tw(), tables.rtw(), batch, stream); }
             if (use_cluster) { return cluster.forward(in, out, batch, stream); }
+#endif
         }
         if constexpr (sizeof(T) == 4) {
             if (use_big_cta) { return launch_r2c<T, 14>(r2c_plain_io<T, 14>{in, out}, tables.tw(), tables.rtw(), batch, stream); }
         }
         if (use_large) { return large.forward(in, out, batch, stream); }
         if (use_two_pass) { return forward_two_pass(in, out, batch, stream); }
+#ifdef NEO_B200_EXPERIMENTAL_FFT
         if constexpr (sizeof(T) == 4) {
             // N = 2^13, 2^14: persistent CTAs fed by TMA bulk copies (fft_stream.cuh); needs 16-byte aligned arrays
             if (stream_ok(in, out)) {
@@ -436,6 +446,7 @@ struct rfft_engine
                 if (order == 14) { return launch_r2c_stream<13>(in, out, tables_full.tw(), tables_full.rtw(), batch, stream); }
             }
         }
+#endif
         if (use_split) {
             if (order - 1 == k_split_lo) {
                 static bool const one_cta = std::getenv("NEO_B200_R2C_SPLIT14") == nullptr;  // tuning knob: two 4096-point CTAs instead
@@ -463,8 +474,10 @@ struct rfft_engine
             if (use_split15) {
                 return launch_c2r_split2<T, 14>(in, row_len, out, tables.tw(), tables.rtw(), w_n.template as<cx<T>>(), batch, stream);
             }
+#ifdef NEO_B200_EXPERIMENTAL_FFT
             if (use_pair) { return launch_c2r_pair<15>(in, row_len, out, tables.tw(), tables.rtw(), batch, stream); }
             if (use_cluster) { return cluster.backward(in, row_len, out, batch, stream); }
+#endif
         }
         if constexpr (sizeof(T) == 4) {
             if (use_big_cta) {
@@ -473,12 +486,14 @@ struct rfft_engine
         }
         if (use_large) { return large.backward(in, row_len, out, batch, stream); }
         if (use_two_pass) { return backward_two_pass(in, row_len, out, batch, stream); }
+#ifdef NEO_B200_EXPERIMENTAL_FFT
         if constexpr (sizeof(T) == 4) {
             if (stream_ok(in, out)) {
                 if (order == 13) { return launch_c2r_stream<12>(in, row_len, out, tables.tw(), tables.rtw(), batch, stream); }
                 if (order == 14) { return launch_c2r_stream<13>(in, row_len, out, tables_full.tw(), tables_full.rtw(), batch, stream); }
             }
         }
+#endif
         if (use_split) {
             auto const* wn = w_n.template as<cx<T>>();
             if (order - 1 == k_split_lo) {

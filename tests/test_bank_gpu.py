@@ -17,7 +17,7 @@ def devices_for(gpu, n):
 
 
 def run_bank_steps(bank, sig, block, T, pipelined=False):
-    """feed sig[rows][n] through the bank T blocks per call; pipelined: two submits in flight, separate buffers per step"""
+    """feed sig[rows][n] through the bank T blocks per call; pipelined: three submits in flight, separate buffers per step"""
     n_in = sig.shape[0]
     n_out = sum(r["out_count"] for r in bank.ranks)
     steps = sig.shape[1] // (T * block)
@@ -26,8 +26,9 @@ def run_bank_steps(bank, sig, block, T, pipelined=False):
     if pipelined:
         for s in range(steps):
             bank.submit(ins[s], outs[s])
-            if s >= 1:
+            if s >= 2:
                 bank.wait()
+        bank.wait()
         bank.wait()
     else:
         for s in range(steps):
@@ -54,7 +55,7 @@ def test_bank_layouts_match_oracle(gpu, orc, layout, frame):
     for s in range(steps):  # every step on its own: a wrong slot / ring pairing must not hide behind the whole-signal norm
         sl = slice(s * T * B, (s + 1) * T * B)
         assert rel_l2(got[:, sl], want[:, sl]) <= 2e-5, s
-    # same state machine after reset, now software-pipelined (two steps in flight)
+    # same state machine after reset, now software-pipelined (three steps in flight)
     bank.reset()
     got2 = run_bank_steps(bank, sig, B, T, pipelined=True)
     assert rel_l2(got2, want) <= 1e-5

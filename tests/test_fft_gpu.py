@@ -45,9 +45,10 @@ def test_rfft_irfft_match_oracle_every_order(gpu, orc, real, cplx):
 
 
 @pytest.mark.parametrize("order,batch", [(13, 701), (14, 333)])
-def test_tma_staged_persistent_rfft_many_rows(gpu, orc, order, batch):
-    # N = 2^13 / 2^14 run as persistent CTAs fed by bulk copies (fft_stream.cuh): more rows than CTA slots (296 / 148), odd and even
-    # rows (spectrum rows of N/2+1 bins alternate between 16-byte aligned and not), and N-long spectrum rows on the way back
+def test_long_rfft_many_rows(gpu, orc, order, batch):
+    # N = 2^13 / 2^14 (512-thread CTAs, two per SM): more rows than one wave of CTAs, odd and even rows (spectrum rows of N/2+1 bins
+    # alternate between 16-byte aligned and not), and N-long spectrum rows on the way back. Also the parity test of the TMA-staged
+    # persistent form (fft_stream.cuh) when the library is built with EXTRA=-DNEO_B200_EXPERIMENTAL_FFT and run with NEO_B200_STREAM=1.
     n = 1 << order
     x = np.stack([orc.noise(n, 2 + (b % 5), np.float32) * np.float32(1 + b % 3) for b in range(batch)])
     base = orc.rfft(x[:15])
@@ -183,7 +184,7 @@ def test_long_transforms_four_step(gpu, orc, order):
     rp.close()
 
 
-@pytest.mark.parametrize("knob", ["NEO_B200_PAIR", "NEO_B200_CLUSTER16", "NEO_B200_NO_SPLIT15", None])
+@pytest.mark.parametrize("knob", ["NEO_B200_NO_SPLIT15", None])
 def test_every_form_of_the_65536_point_rfft(gpu, orc, monkeypatch, knob):
     # four implementations of N = 2^16 exist (fft_plan.cu, rfft_engine::init lists what each measured); the shipped one is two
     # 2^14-point CTAs, the others are selected by environment knobs when the plan is created -- all must agree with the oracle

@@ -9,7 +9,8 @@ import torch
 
 import __graft_entry__ as entry
 
-CHANNELS, BLOCK, TAPS = 1024, 1024, 1 << 20
+CHANNELS, BLOCK = 1024, 1024
+TAPS = int(os.environ.get("FRAME_TAPS", 1 << 20))  # 2^19 taps at T = 256 gives Q = 2 frame partitions: one shard of a 2-way partition split
 
 
 def main():
