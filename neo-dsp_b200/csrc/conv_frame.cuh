@@ -264,11 +264,13 @@ struct frame_knobs
 {
     int variant{-1};   // NEO_B200_FRAME_VARIANT: fused-kernel geometry at L >= 256 (float)
     bool async{true};  // NEO_B200_FRAME_NO_ASYNC clears it: MAC operands straight into registers
+    bool pipelined{true};  // NEO_B200_FRAME_NO_PIPELINE clears it: one CTA per unit instead of the persistent software-pipelined form
     static frame_knobs from_env()
     {
         frame_knobs k;
         if (char const* v = std::getenv("NEO_B200_FRAME_VARIANT")) { k.variant = std::atoi(v); }
         k.async = std::getenv("NEO_B200_FRAME_NO_ASYNC") == nullptr;
+        k.pipelined = std::getenv("NEO_B200_FRAME_NO_PIPELINE") == nullptr;
         return k;
     }
     bool eight_points(int logl, bool is_f32) const { return is_f32 && logl >= 8 && (variant == 2 || variant == 3 || variant == 4); }
@@ -559,13 +561,232 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
     }
 }
 
-template<typename T, int LOGL, int LOGG, int LOGE_F, int REGCAP, bool NYQ>
-int launch_frame_fused_g(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, size_t units, cudaStream_t stream, bool async)
+// ---- the same frame step as a PERSISTENT, software-pipelined CTA -------------------------------------------------------------------
+// ncu on frame_fused_kernel with few second-level partitions (Q = 2: one partition shard of a two-way split, or T = 512 on one device):
+// 48 % issue-active, 55 % of DRAM peak -- per unit (G bins of one channel) the two frame transforms need ~10.8k issue cycles and the
+// unit's bytes ~15.3k cycles of HBM time, and with one 512-thread CTA per SM (128 registers x 512 threads, ~200 KB of shared memory)
+// they run one after the other. Here one CTA per SM walks units u = blockIdx.x, blockIdx.x + gridDim.x, ... and keeps HBM busy
+// during the transforms:
+//   - the two frames' level-1 spectra of unit u+1 are fetched with cp.async into a staging buffer while unit u's forward transform
+//     runs (they used to be the first thing a CTA waited for);
+//   - the first two MAC chunks of unit u+1 are fetched while unit u's inverse transform runs.
+// Same arithmetic, same operand order, same results as frame_fused_kernel. MAC chunks are a quarter of a thread's points (CHDIV = 4)
+// so that tile + two stages + the spectra staging buffer fit 227 KB.
+template<typename T, int LOGL, int LOGG, int LOGE_F>
+struct frame_pipe_cfg
+{
+    using cfg                        = frame_cfg<T, LOGL, LOGG, LOGE_F>;
+    static constexpr int CH          = cfg::E >= 4 ? cfg::E / 4 : 1;
+    static constexpr int NH          = cfg::E / CH;
+    static constexpr int OPERAND     = CH * cfg::TN * cfg::G * int(sizeof(cx<T>));
+    static constexpr int STAGE       = 2 * OPERAND;
+    static constexpr int XSTAGE      = cfg::L * cfg::G * int(sizeof(cx<T>));                          // 2T rows of G bins
+    static constexpr size_t SMEM     = cfg::SMEM + 2 * size_t(STAGE) + size_t(XSTAGE);
+    static constexpr int PER_THREAD  = OPERAND / 16 / cfg::THREADS;
+    static constexpr int ROW_PIECES  = cfg::G * int(sizeof(cx<T>)) / 16;
+    static constexpr int X_PER_THREAD = XSTAGE / 16 / cfg::THREADS;
+    static constexpr bool OK = STAGE <= int(cfg::SMEM) && PER_THREAD >= 1 && PER_THREAD * 16 * cfg::THREADS == OPERAND
+                            && X_PER_THREAD * 16 * cfg::THREADS == XSTAGE && SMEM <= 227 * 1024 && cfg::THREADS <= 1024;
+};
+
+template<typename T, int LOGL, int LOGG, int LOGE_F, int REGCAP>
+__global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, frame_min_ctas<T, LOGL, LOGG, LOGE_F, REGCAP>())
+    frame_fused_pipelined_kernel(frame_fused_io<T, false> io, cx<T> const* __restrict__ tw, size_t units)
+{
+    using cfg = frame_cfg<T, LOGL, LOGG, LOGE_F>;
+    using pc  = frame_pipe_cfg<T, LOGL, LOGG, LOGE_F>;
+    using C   = cx<T>;
+    constexpr int E = cfg::E, TN = cfg::TN, L = cfg::L, G = cfg::G;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int const gi = threadIdx.x % G;
+    int const t  = threadIdx.x / G;
+    C* const sm  = reinterpret_cast<C*>(smem_raw) + gi * cfg::F::TILE;
+    unsigned char* const xstage = smem_raw + cfg::SMEM + 2 * pc::STAGE;
+
+    frame_geom const& g = io.g;
+    int const logw      = g.logw;
+    int const wmask     = (1 << logw) - 1;
+    auto const at       = [&](int f, int r, int rows) -> size_t { return (size_t(f) * rows + r) << logw; };
+    int slot0           = (io.slot - io.age0) % io.ring2;  // ring slot paired with local partition 0
+    slot0 += slot0 < 0 ? io.ring2 : 0;
+    bool const newest_in_regs = io.age0 == 0;
+    int const nchunks         = io.parts2 * pc::NH;
+    auto const stage_ptr      = [&](int c) -> unsigned char* {  // stage 2 is the exchange tile
+        int const st = c % 3;
+        return st == 2 ? smem_raw : smem_raw + cfg::SMEM + st * pc::STAGE;
+    };
+
+    // what a unit (G adjacent bins of one channel; the first of them is `unit`) addresses
+    struct where
+    {
+        size_t chan;
+        int k0;          // first bin of the group
+        C const* src;    // x1 row 0, bin k0
+        C* ring;         // ring element (frame bin 0, slot 0), bin k0
+        C const* filt;   // filter element (frame bin 0, partition 0), bin k0
+    };
+    auto const locate = [&](size_t unit) -> where {
+        size_t const chan  = io.chan0 + (unit >> g.logb);
+        int const k0       = int(unit & ((size_t(1) << g.logb) - 1));
+        size_t const tile2 = size_t(k0 >> logw) * L;
+        int const w0       = k0 & wmask;
+        return {chan, k0, io.x1 + ((chan * size_t(L)) << g.logb) + k0, io.fdl2 + (((chan * g.tiles2 + tile2) * io.ring2) << logw) + w0,
+                io.filt2 + (((chan * g.tiles2 + tile2) * io.parts2) << logw) + w0};
+    };
+
+    // warp-private MAC staging, exactly as in frame_fused_kernel (a warp copies the rows its own threads read)
+    constexpr int TW    = 32 / G;
+    constexpr int RP    = pc::ROW_PIECES;
+    constexpr int KSTEP = 16 / int(sizeof(C));
+    static_assert(G <= 32 && (32 / RP) == KSTEP * TW, "warp-private staging geometry");
+    int const lane      = int(threadIdx.x) & 31;
+    int const lrow      = lane / RP;
+    int const u0        = lrow / TW;
+    int const t_mine    = (int(threadIdx.x) >> 5) * TW + lrow % TW;
+    int const f0        = t_mine + u0 * TN;
+    size_t const eo     = size_t(lane % RP) * KSTEP;
+    unsigned const dst0 = unsigned((u0 * TN + t_mine) * G * int(sizeof(C)) + (lane % RP) * 16);
+    constexpr unsigned dst_step = unsigned(KSTEP * TN * G * int(sizeof(C)));
+    auto const issue = [&](where const& u, int c) {
+        if (c < nchunks) {
+            int const q  = c / pc::NH;
+            int const eh = c - q * pc::NH;
+            int sl       = slot0 - q;
+            sl += sl < 0 ? io.ring2 : 0;
+            unsigned char* const dst_h = stage_ptr(c) + dst0;
+            C const* const hp          = u.filt + eo + at(f0 + eh * pc::CH * TN, q, io.parts2);
+            C const* const xp          = u.ring + eo + at(f0 + eh * pc::CH * TN, sl, io.ring2);
+            bool const want_x          = !(q == 0 && newest_in_regs);
+#pragma unroll
+            for (int i = 0; i < pc::PER_THREAD; ++i) {
+                frame_cp_async16(dst_h + i * dst_step, hp + at(i * KSTEP * TN, 0, io.parts2));
+                if (want_x) { frame_cp_async16(dst_h + pc::OPERAND + i * dst_step, xp + at(i * KSTEP * TN, 0, io.ring2)); }
+            }
+        }
+        frame_cp_async_commit();
+    };
+    // the two frames' level-1 spectra of a unit -> staging [frame bin n][G bins]; piece p = (row n, 16 bytes of the row's G bins)
+    auto const fetch_x1 = [&](where const& u) {
+#pragma unroll
+        for (int i = 0; i < pc::X_PER_THREAD; ++i) {
+            int const p    = int(threadIdx.x) + i * cfg::THREADS;
+            int const n    = p / RP;
+            int const half = n < g.frame ? (io.new_half ^ 1) : io.new_half;
+            int const row  = half * g.frame + (n & (g.frame - 1));
+            frame_cp_async16(xstage + size_t(p) * 16, u.src + (size_t(row) << g.logb) + size_t(p % RP) * KSTEP);
+        }
+        frame_cp_async_commit();
+    };
+
+    size_t const stride = size_t(gridDim.x) * G;
+    size_t unit         = size_t(blockIdx.x) * G;
+    if (unit >= units) { return; }
+    where cur = locate(unit);
+    fetch_x1(cur);
+    issue(cur, 0);
+    issue(cur, 1);
+    for (; unit < units; unit += stride) {
+        bool const more  = unit + stride < units;
+        where const next = more ? locate(unit + stride) : cur;
+        int const k      = cur.k0 + gi;
+
+        frame_cp_async_wait<0>();  // this unit's spectra and its first two MAC chunks have landed
+        __syncthreads();
+        C v[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { v[e] = reinterpret_cast<C const*>(xstage)[(t + e * TN) * G + gi]; }
+        __syncthreads();           // the staging buffer is free: the next unit's spectra travel during this unit's forward transform
+        if (more) { fetch_x1(next); }
+        else { frame_cp_async_commit(); }
+        if (k == 0) {
+#pragma unroll
+            for (int e = 0; e < E; ++e) { v[e].y = T(0); }
+        }
+        cta_fft<T, LOGL, -1, LOGE_F>::run(v, sm, tw, t);
+        issue(cur, 2);  // the exchange tile is free until the inverse transform
+        C* const ring = cur.ring + gi;
+#pragma unroll
+        for (int e = 0; e < E; ++e) { ring[at(t + e * TN, io.slot, io.ring2)] = v[e]; }
+
+        C a[E];
+#pragma unroll
+        for (int e = 0; e < E; ++e) { a[e] = mk<T>(T(0), T(0)); }
+        for (int q = 0; q < io.parts2; ++q) {
+            bool const own = q == 0 && newest_in_regs;
+#pragma unroll
+            for (int eh = 0; eh < pc::NH; ++eh) {
+                int const c = q * pc::NH + eh;
+                frame_cp_async_wait<2>();  // groups complete in order: chunk c (and everything older) has landed
+                __syncwarp();
+                C const* const sh = reinterpret_cast<C const*>(stage_ptr(c));
+                C const* const sx = reinterpret_cast<C const*>(stage_ptr(c) + pc::OPERAND);
+#pragma unroll
+                for (int u = 0; u < pc::CH; ++u) {
+                    int const e = eh * pc::CH + u;
+                    C const h   = sh[(u * TN + t) * G + gi];
+                    C const x   = own ? v[e] : sx[(u * TN + t) * G + gi];
+                    a[e].x      = ::fma(x.x, h.x, a[e].x);
+                    a[e].x      = ::fma(-x.y, h.y, a[e].x);
+                    a[e].y      = ::fma(x.x, h.y, a[e].y);
+                    a[e].y      = ::fma(x.y, h.x, a[e].y);
+                }
+                __syncwarp();
+                issue(cur, c + 3);
+            }
+        }
+        frame_cp_async_wait<0>();
+        __syncthreads();  // every warp is done with the stages; stage 2 is the exchange tile the inverse transform writes
+        if (more) {       // the next unit's first two chunks travel during this unit's inverse transform
+            issue(next, 0);
+            issue(next, 1);
+        }
+        if (k == 0) {  // + i * (Nyquist result): the inverse transform then yields the packed pair (Re Y[0], Re Y[B])
+#pragma unroll
+            for (int e = 0; e < E; ++e) {
+                C const n = io.nyq_acc[cur.chan * L + t + e * TN];
+                a[e].x -= n.y;
+                a[e].y += n.x;
+            }
+        }
+        cta_fft<T, LOGL, 1, LOGE_F>::run(a, sm, tw, t);
+        C* dst = io.y1 + ((cur.chan * g.frame) << g.logb) + k;
+        if (io.owners > 1) {
+            int const o = int(cur.chan) / io.own_count;
+            dst         = io.y1_owner[o] + (((cur.chan - size_t(o) * io.own_count) * g.frame) << g.logb) + k;
+        }
+#pragma unroll
+        for (int e = 0; e < E; ++e) {
+            int const n = t + e * TN;
+            if (n >= g.frame) { dst[size_t(n - g.frame) << g.logb] = mk<T>(a[e].x * io.scale, a[e].y * io.scale); }
+        }
+        cur = next;
+    }
+}
+
+// PIPE: the persistent software-pipelined form may be taken (instantiated for the default geometries only)
+template<typename T, int LOGL, int LOGG, int LOGE_F, int REGCAP, bool NYQ, bool PIPE = false>
+int launch_frame_fused_g(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, size_t units, cudaStream_t stream, bool async, bool pipelined = false)
 {
     using cfg = frame_cfg<T, LOGL, LOGG, LOGE_F>;
     if constexpr (cfg::THREADS > 1024) { return fail(NEO_B200_ERR_UNSUPPORTED, "frame kernel variant needs %d threads", cfg::THREADS); }
     else {
         if (units == 0) { return NEO_B200_OK; }
+        if constexpr (PIPE && !NYQ && LOGL >= 7 && sizeof(T) == 4) {
+            using pc = frame_pipe_cfg<T, LOGL, LOGG, LOGE_F>;
+            if constexpr (pc::OK) {
+                if (async && pipelined && (1 << io.g.logw) >= cfg::G && units % cfg::G == 0) {
+                    auto kernel = frame_fused_pipelined_kernel<T, LOGL, LOGG, LOGE_F, REGCAP>;
+                    NEO_TRY(enable_smem(kernel, pc::SMEM));
+                    int dev = 0, sms = 148, per_sm = 1;
+                    cudaGetDevice(&dev);
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+                    NEO_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, cfg::THREADS, pc::SMEM));
+                    size_t const resident = size_t(sms) * size_t(std::max(1, per_sm));  // persistent: one CTA per resident slot
+                    kernel<<<unsigned(std::min(units / cfg::G, resident)), cfg::THREADS, pc::SMEM, stream>>>(io, tw, units);
+                    return check_launch("frame_fused_pipelined_kernel");
+                }
+            }
+        }
         if constexpr (!NYQ && LOGL >= 6) {
             using ac = frame_async_cfg<T, LOGL, LOGG, LOGE_F>;
             if (async && (1 << io.g.logw) >= cfg::G && units % cfg::G == 0 && ac::SMEM <= 227 * 1024) {
@@ -598,12 +819,12 @@ int launch_frame_fused(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, cx<T> 
             case 2: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 3 : 4, 3, 64, NYQ>(io, tw8, units, stream, a);
             case 3: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 2 : 3, 3, 64, NYQ>(io, tw8, units, stream, a);
             case 4: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 2 : 3, 3, 96, NYQ>(io, tw8, units, stream, a);
-            default: return launch_frame_fused_g<T, LOGL, g16, -1, 128, NYQ>(io, tw, units, stream, a);
+            default: return launch_frame_fused_g<T, LOGL, g16, -1, 128, NYQ, true>(io, tw, units, stream, a, knobs.pipelined);
         }
     } else if constexpr (frame_cfg<T, LOGL, g0>::THREADS > 512) {
-        return launch_frame_fused_g<T, LOGL, g0 - 1, -1, 128, NYQ>(io, tw, units, stream, a);
+        return launch_frame_fused_g<T, LOGL, g0 - 1, -1, 128, NYQ, true>(io, tw, units, stream, a, knobs.pipelined);
     } else {
-        return launch_frame_fused_g<T, LOGL, g0, -1, 128, NYQ>(io, tw, units, stream, a);
+        return launch_frame_fused_g<T, LOGL, g0, -1, 128, NYQ, true>(io, tw, units, stream, a, knobs.pipelined);
     }
 }
 

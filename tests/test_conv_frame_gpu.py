@@ -56,6 +56,28 @@ def test_frame_mode_matches_oracle(gpu, orc, block, taps, channels, T, frames):
     conv.close()
 
 
+@pytest.mark.parametrize("block,T,P,channels", [(1024, 64, 130, 8), (512, 128, 256, 6), (256, 512, 700, 8)])
+def test_frame_mode_persistent_pipelined_kernel_many_units(gpu, orc, monkeypatch, block, T, P, channels):
+    # banks with more units (16 adjacent bins of a channel) than resident CTAs: the persistent software-pipelined fused kernel walks
+    # several units per CTA, prefetching the next unit's spectra and first MAC chunks. Same bits as the one-CTA-per-unit form
+    # (NEO_B200_FRAME_NO_PIPELINE), and the oracle's answer.
+    steps = 3
+    ir, sig = make_case(orc, channels, block * P - 11, block, T * steps)
+    H = orc.uniform_partition(ir, block)
+    want = orc.convolve_blocks(0, H, sig)
+    got = {}
+    for form in ("pipelined", "plain"):
+        if form == "plain":
+            monkeypatch.setenv("NEO_B200_FRAME_NO_PIPELINE", "1")
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+        conv.filter(H)
+        got[form] = run_bank(conv, sig, block, [T])
+        conv.close()
+        assert rel_l2(got[form], want) <= 1e-5, (form, rel_l2(got[form], want))
+    monkeypatch.delenv("NEO_B200_FRAME_NO_PIPELINE")
+    assert np.array_equal(got["pipelined"], got["plain"])
+
+
 @pytest.mark.parametrize("block,taps,T", [(16, 100, 4), (256, 256 * 9 - 3, 8)])
 def test_frame_mode_upola_and_f64(gpu, orc, block, taps, T):
     for real in (np.float32, np.float64):
