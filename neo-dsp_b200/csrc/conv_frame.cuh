@@ -774,7 +774,10 @@ int launch_frame_fused_g(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, size
         if constexpr (PIPE && !NYQ && LOGL >= 7 && sizeof(T) == 4) {
             using pc = frame_pipe_cfg<T, LOGL, LOGG, LOGE_F>;
             if constexpr (pc::OK) {
-                if (async && pipelined && (1 << io.g.logw) >= cfg::G && units % cfg::G == 0) {
+                // measured (C5 geometry, ms per fused step, pipelined / one CTA per unit): T=256 Q=4 7.26 / 6.57, T=128 Q=8 6.33 / 5.91,
+                // T=256 Q=2 5.05 / 5.21, T=512 Q=2 11.07 / 12.47 -- the smaller MAC chunks cost more than the prefetch buys while the
+                // MAC stream dominates; with one or two partitions per unit the transforms dominate and the prefetch pays
+                if (async && pipelined && io.parts2 <= 2 && (1 << io.g.logw) >= cfg::G && units % cfg::G == 0) {
                     auto kernel = frame_fused_pipelined_kernel<T, LOGL, LOGG, LOGE_F, REGCAP>;
                     NEO_TRY(enable_smem(kernel, pc::SMEM));
                     int dev = 0, sms = 148, per_sm = 1;
