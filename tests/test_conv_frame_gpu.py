@@ -56,7 +56,7 @@ def test_frame_mode_matches_oracle(gpu, orc, block, taps, channels, T, frames):
     conv.close()
 
 
-@pytest.mark.parametrize("block,T,P,channels", [(1024, 64, 128, 8), (512, 128, 200, 6), (256, 512, 700, 8)])
+@pytest.mark.parametrize("block,T,P,channels", [(1024, 64, 128, 16), (512, 128, 200, 12), (256, 512, 700, 8)])
 def test_frame_mode_persistent_pipelined_kernel_many_units(gpu, orc, monkeypatch, block, T, P, channels):
     # banks with more units (16 adjacent bins of a channel) than resident CTAs: the persistent software-pipelined fused kernel walks
     # several units per CTA, prefetching the next unit's spectra and first MAC chunks (taken with at most two second-level partitions:
