@@ -535,9 +535,10 @@ def run_single(args, pkg, torch, emit, peak, peak_src):
     mac_ms_avg = ms_mac / max(1, mac_launches)
     achieved = alg_bytes_launch / (mac_ms_avg * 1e-3) / 1e9 if mac_ms_avg > 0 else 0.0
     fp32 = CHANNELS * 8.0 * (BLOCK + 1) * PARTS * T / (mac_ms_avg * 1e-3) / 1e12 if frame == 0 and mac_ms_avg > 0 else None
+    traffic, traffic_src = ncu_traffic(f"frame_fused_T{T}_G1" if frame > 0 else f"fdl_mac_T{T}_G1")
     roofline = {
         "kernel": kernel_name, "bound": "hbm", "achieved": achieved, "peak": peak, "peak_source": peak_src, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": ncu_traffic(f"frame_fused_T{T}_G1" if frame > 0 else f"fdl_mac_T{T}_G1"),
+        "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
         "algorithmic_bytes_per_launch": alg_bytes_launch, "launch_ms": mac_ms_avg,
         "share_of_step": ms_mac / ms_total if ms_total > 0 else None, "fp32_tflops": fp32,
         "phases_ms_per_step": {"r2c_fdl_insert": ms_r2c / args.steps, "mac": ms_mac / args.steps, "c2r_discard": ms_c2r / args.steps},
@@ -645,14 +646,16 @@ def run_single(args, pkg, torch, emit, peak, peak_src):
     emit(line)
 
 
-def ncu_traffic(key: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch from an ncu --set full capture of this kernel (profiles/traffic.json
-    records which capture); None when that kernel / layout was never captured."""
+def ncu_traffic(key: str, scale: int = 1):
+    """(bytes, source): dram__bytes_read.sum + dram__bytes_write.sum per launch from an ncu --set full capture of this kernel
+    (profiles/traffic.json names the capture); `scale` multiplies per-channel entries. (None, None) when never captured."""
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
         with open(tpath) as f:
-            return json.load(f).get(key)
-    return None
+            entry = json.load(f).get(key)
+        if isinstance(entry, dict):
+            return entry["bytes"] * scale, "ncu capture, not measured in this run: " + entry["capture"]
+    return None, None
 
 
 # ---- N GPUs: the library's bank --------------------------------------------------------------------------------------------------
@@ -734,11 +737,17 @@ def measure_layout(args, pkg, torch, dist, rank, world, local, layout, T, frame,
         alg = info["group_count"] * direct_bytes_per_channel(T, parts_local)
     mac_ms = ms_mac / max(1, mac_launches)
     peak, peak_src = measured_peaks()
+    q_local = (parts_local + T - 1) // T if frame > 0 else 0
+    traffic, traffic_src = ncu_traffic(f"frame_fused_T{T}_Q{q_local}_per_channel", info["group_count"]) if frame > 0 else (None, None)
+    if traffic is None and frame > 0 and layout[1] == 1 and info["group_count"] > 0:  # unsharded partitions: the one-GPU kernel on fewer channels
+        whole, traffic_src = ncu_traffic(f"frame_fused_T{T}_G1")
+        traffic = whole * info["group_count"] // CHANNELS if whole is not None else None
     res["roofline"] = {
-        "kernel": "frame_fused_kernel<float>" if frame > 0 else "fdl_mac kernel", "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
+        "kernel": ("frame_fused_pipelined_kernel<float>" if q_local <= 2 else "frame_fused_kernel<float>") if frame > 0 else "fdl_mac kernel",
+        "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
         "achieved": alg / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0, "frac": (alg / (mac_ms * 1e-3) / 1e9 / peak) if mac_ms > 0 else 0.0,
         "algorithmic_bytes_per_launch": alg, "launch_ms": mac_ms, "rank": rank,
-        "traffic": ncu_traffic(f"frame_fused_T{T}_shard{layout[1]}" if frame > 0 else f"fdl_mac_T{T}_shard{layout[1]}"),
+        "traffic": traffic, "traffic_source": traffic_src,
         "phases_ms_per_step": {"r2c_fdl_insert": ms_r2c / steps, "mac": ms_mac / steps, "c2r_discard": ms_c2r / steps},
         "share_of_step": (ms_mac / steps) / (ms_total / steps) if ms_total > 0 else None,
     }

@@ -321,11 +321,14 @@ NEO_B200_API size_t neo_b200_conv_device_bytes(neo_b200_conv const* conv);
  * With every rank local and one [channels][blocks*B] array, in_rows[l] = array + in_first_l * blocks * B. HOST memory should be pinned
  * for the copies to overlap; DEVICE pointers must live on the rank's own device, and their contents must be complete when submit is
  * called (the bank works on its own streams and does not wait for the caller's).
- * When the group's handles run the fused frame kernel (frame mode, wide banks) the partial spectra are PUSHED: each shard's kernel
- * stores the result rows of a channel directly into the inbox of the rank that finishes it (peer-mapped memory over NVLink; CUDA IPC
- * mappings between processes, with a one-word ncclAllGather per step as the cross-process gate), and the c2r kernel sums its local
- * inbox slots. Otherwise they are pulled (devices[] banks: the c2r kernel loads the shards' buffers through peer pointers) or summed
- * by ncclReduceScatter (rank-per-process banks). */
+ * How the partial spectra of a group reach the rank that finishes a channel (environment NEO_B200_BANK_EXCHANGE, read at creation):
+ *   dma        (default) every shard's kernels write their partial spectra locally and the copy engines move each owner's rows into
+ *              its inbox over NVLink (peer-mapped memory; CUDA IPC mappings between processes, with a one-word ncclAllGather per
+ *              step as the cross-process gate); the c2r kernel sums its own rows and its inbox slots -- no SM and no store queue of a
+ *              compute kernel is spent on the exchange;
+ *   kernel     the fused frame kernel stores the result rows straight into the owners' inboxes (peer stores from inside the kernel);
+ *   collective ncclReduceScatter of the partial spectra (rank-per-process banks) / peer loads inside the c2r kernel (devices[] banks).
+ * All three give the same bits (shards are summed in shard order). */
 typedef struct neo_b200_bank neo_b200_bank;
 
 typedef struct neo_b200_bank_layout

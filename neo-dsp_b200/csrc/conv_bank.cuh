@@ -121,7 +121,8 @@ struct bank_rank
     // push form (fused frame kernel, partition shards > 1): every shard of the group writes the partial spectra of MY channels into
     // my inbox while it computes them; slot (parity, shard) holds [out_count][T][B] complex. inbox_of[s] = base of shard s's inbox as
     // seen from this rank (its own pointer, a peer-mapped pointer, or a CUDA IPC mapping of another process's allocation)
-    bool push{false};
+    bool push{false};              // the fused frame kernel stores into the owners' inboxes itself (NEO_B200_BANK_EXCHANGE=kernel)
+    bool dma{false};               // default: kernels write locally, the copy engines move each owner's rows into its inbox
     device_buffer inbox;
     size_t inbox_slot{0};          // complex elements per (parity, shard) slot
     void* inbox_of[k_bank_max_shards] = {};
@@ -292,8 +293,18 @@ int bank_build_rank(neo_b200_bank* bank, bank_rank& r)
         return NEO_B200_OK;
     });
     size_t const gp_n = bank->layout.partition_shards;
-    r.push            = fused && gp_n > 1 && std::getenv("NEO_B200_BANK_NO_PUSH") == nullptr;
-    if (r.push) {
+    // how the partial spectra of a group reach the rank that finishes a channel (NEO_B200_BANK_EXCHANGE):
+    //   dma        (default) every shard's kernels write their partial spectra locally; the copy engines then move each owner's rows
+    //              into its inbox over NVLink (no SM and no store queue of the compute kernel involved) and the c2r kernel sums its
+    //              own rows and its inbox slots;
+    //   kernel     the fused frame kernel stores the rows straight into the owners' inboxes (peer stores; wide frame-mode banks);
+    //   collective ncclReduceScatter (rank-per-process) / peer loads inside the c2r kernel (devices[] banks).
+    // measured, BASELINE config 5 on 2 GPUs (1 x 2), ms per fused step / per step: kernel 7.6 / 8.7, collective 5.5 / 8.7, dma see DESIGN.md
+    char const* const how = std::getenv("NEO_B200_BANK_EXCHANGE");
+    std::string const exchange = how != nullptr ? how : "dma";
+    r.push = gp_n > 1 && fused && exchange == "kernel";
+    r.dma  = gp_n > 1 && !r.push && exchange != "collective";
+    if (r.push || r.dma) {
         r.inbox_slot = r.info.out_count * c.max_blocks * c.block;
         NEO_TRY(r.inbox.reserve(2 * gp_n * r.inbox_slot * 2 * esz));
         r.inbox_of[r.info.partition_shard] = r.inbox.ptr;
@@ -307,13 +318,13 @@ int bank_connect_inboxes(neo_b200_bank* bank)
 {
     size_t const gp_n = bank->layout.partition_shards;
     for (auto& r : bank->ranks) {
-        if (!r.push) { continue; }
+        if (!r.push && !r.dma) { continue; }
         NEO_CUDA_TRY(cudaSetDevice(r.info.device));
         size_t const base = r.info.channel_group * gp_n;
         if (!bank->nccl) {
             for (size_t s = 0; s < gp_n; ++s) {
                 bank_rank* const peer = bank->find(base + s);
-                if (!peer->push) { return fail(NEO_B200_ERR_INVALID, "the ranks of a group disagree about the push form"); }
+                if (peer->push != r.push || peer->dma != r.dma) { return fail(NEO_B200_ERR_INVALID, "the ranks of a group disagree about the exchange form"); }
                 r.inbox_of[s] = peer->inbox.ptr;
             }
             continue;
@@ -443,14 +454,16 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         bank_domains(bank, r, &gather, &reduce);
         if (bank->nccl) {
             NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_in[e0], 0));
-            // reduce-scatter of two steps ago read this buffer (push form: the gate of the previous step already orders it)
+            // the reduce-scatter / copy-out of two steps ago read this buffer (kernel push: the gate of the previous step orders it)
             if (gp_n > 1 && !r.push) { NEO_TRY(wait_for(r.s_cmp, ago(r.ev_red, 2))); }
+            if (r.dma) { NEO_TRY(wait_for(r.s_cmp, ago(r.ev_c2r, 2))); }  // ... and the c2r of two steps ago read the rank's own rows of it
         } else {
             for (size_t p : gather) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, bank->find(p)->ev_in[e0], 0)); }
             // the partial spectra buffer / inbox slot of this parity was last read by the c2r of two steps ago on every rank of the group
             if (gp_n > 1) {
                 for (size_t p : reduce) { NEO_TRY(wait_for(r.s_cmp, ago(bank->find(p)->ev_c2r, 2))); }
             }
+            if (r.dma) { NEO_TRY(wait_for(r.s_cmp, ago(r.ev_red, 2))); }  // the copy-out of two steps ago read this buffer
         }
         // an unsharded handle has a single spectra buffer: the c2r of the previous step must have read it
         if (gp_n == 1) { NEO_TRY(wait_for(r.s_cmp, ago(r.ev_c2r, 1))); }
@@ -486,7 +499,32 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         NEO_CUDA_TRY(cudaEventRecord(r.ev_fwd[e0], r.s_cmp));
     }
 
-    // ---- 3. reduction over the partition shards + c2r for the rank's own channels; 4. output rows ----
+    // ---- 3a. copy-engine exchange: each rank hands every other shard of its group the partial spectra of THAT shard's channels ----
+    for (auto& r : bank->ranks) {
+        if (!r.dma) { continue; }
+        NEO_CUDA_TRY(cudaSetDevice(r.info.device));
+        size_t const base      = r.info.channel_group * gp_n;
+        size_t const own_elems = r.info.out_count * blocks * c.block;
+        NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_red, r.ev_fwd[e0], 0));
+        for (size_t o = 0; o < gp_n; ++o) {
+            if (o == r.info.partition_shard) { continue; }
+            // the owner's c2r of two steps ago read this inbox slot (rank-per-process: the gate of the previous step orders it)
+            if (!bank->nccl) { NEO_TRY(wait_for(r.s_red, ago(bank->find(base + o)->ev_c2r, 2))); }
+            cx<T>* const dst       = static_cast<cx<T>*>(r.inbox_of[o]) + (size_t(b) * gp_n + r.info.partition_shard) * r.inbox_slot;
+            cx<T> const* const src = static_cast<cx<T> const*>(r.partial[b]) + o * own_elems;
+            NEO_CUDA_TRY(cudaMemcpyAsync(dst, src, own_elems * sizeof(cx<T>), cudaMemcpyDeviceToDevice, r.s_red));
+        }
+        if (bank->nccl) {
+            // gate of step i: completes here only when every shard of the group has reached it -- its copies of step i have landed
+            // and, because each rank first waits for its own c2r of step i-1, the inbox slots that step i+1 overwrites are free
+            NEO_TRY(wait_for(r.s_red, ago(r.ev_c2r, 1)));
+            float* const words = r.gate.as<float>();
+            NEO_NCCL_TRY(bank->api, bank->api->AllGather(words + r.info.partition_shard, words, 1, nccl_api::k_float32, r.comm_out, r.s_red));
+        }
+        NEO_CUDA_TRY(cudaEventRecord(r.ev_red[e0], r.s_red));
+    }
+
+    // ---- 3b. reduction over the partition shards + c2r for the rank's own channels; 4. output rows ----
     for (size_t l = 0; l < bank->ranks.size(); ++l) {
         bank_rank& r = bank->ranks[l];
         NEO_CUDA_TRY(cudaSetDevice(r.info.device));
@@ -499,6 +537,18 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         if (gp_n == 1) {
             NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[e0], 0));
             srcs[0] = static_cast<cx<T> const*>(r.partial[b]) + own_in_group * blocks * c.block;
+        } else if (r.dma) {
+            // own rows straight from the rank's partial spectra, the other shards' rows from the inbox: a LOCAL sum, in shard order
+            if (bank->nccl) {
+                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_red[e0], 0));  // recorded behind the gate
+            } else {
+                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, bank->find(p)->ev_red[e0], 0)); }
+            }
+            nsrc = int(gp_n);
+            for (size_t s = 0; s < gp_n; ++s) {
+                srcs[s] = s == r.info.partition_shard ? static_cast<cx<T> const*>(r.partial[b]) + own_in_group * blocks * c.block
+                                                      : r.inbox.template as<cx<T>>() + (size_t(b) * gp_n + s) * r.inbox_slot;
+            }
         } else if (r.push) {
             // the shards have pushed their partial spectra of my channels into my inbox: a LOCAL sum, in shard order
             if (bank->nccl) {

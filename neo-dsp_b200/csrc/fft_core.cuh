@@ -430,6 +430,37 @@ __device__ __forceinline__ C r2c_post(C z, C zp, C w)
     return r;
 }
 
+// Both members of a Hermitian pair from one twiddle product. With s = Z[k] + conj(Z[M-k]), d = Z[k] - conj(Z[M-k]) and
+// W^(M-k) = -conj(W^k):   X[k] = (s - i W d) / 2,   X[M-k] = conj(s + i W d) / 2
+template<typename C>
+__device__ __forceinline__ void r2c_post_pair(C z, C zp, C w, C& xk, C& xmk)
+{
+    using T = decltype(z.x);
+    C const zc = cconj(zp);
+    C const s  = cadd(z, zc);
+    C const d  = csub(z, zc);
+    C const wd = cmul(w, d);
+    T const hx = T(0.5) * s.x, hy = T(0.5) * s.y;
+    xk.x  = fma(T(0.5), wd.y, hx);
+    xk.y  = fma(T(-0.5), wd.x, hy);
+    xmk.x = fma(T(-0.5), wd.y, hx);
+    xmk.y = fma(T(-0.5), wd.x, -hy);
+}
+
+// c2r: Z[k] = s + i conj(W) d and Z[M-k] = conj(s - i conj(W) d) with s = X[k] + conj(X[M-k]), d = X[k] - conj(X[M-k])
+template<typename C>
+__device__ __forceinline__ void c2r_pre_pair(C x, C xp, C w, C& zk, C& zmk)
+{
+    C const xc = cconj(xp);
+    C const s  = cadd(x, xc);
+    C const d  = csub(x, xc);
+    C const wd = cmulc(d, w);
+    zk.x  = s.x - wd.y;
+    zk.y  = s.y + wd.x;
+    zmk.x = s.x + wd.y;
+    zmk.y = wd.x - s.y;
+}
+
 template<typename C>
 __device__ __forceinline__ C c2r_pre(C x, C xp, C w)
 {

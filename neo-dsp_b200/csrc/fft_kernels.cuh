@@ -287,30 +287,45 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOG
 
     // Hermitian exchange: both sides are unit stride (k ascending on the store, M - k descending on the load), so the tile is used
     // UNPADDED here -- with the stage padding a half-warp's 16 partners straddle a pad boundary and collide two-way (ncu: 16 % of the
-    // kernel's shared-memory wavefronts were bank conflicts)
-    if constexpr (LOGM > 0) {
+    // kernel's shared-memory wavefronts were bank conflicts).
+    // A thread finishes PAIRS: for each of its bins k < M/2 (the first half of its points) it fetches Z[M-k] and produces X[k] and
+    // X[M-k] from one twiddle product -- half the partner loads, half the twiddle loads and 10 of 24 flops per pair less than doing
+    // every bin on its own.
+    if constexpr (cfg::E >= 2) {
+        constexpr int M = cfg::M, E = cfg::E, TN = cfg::TN;
 #pragma unroll
-        for (int e = 0; e < cfg::E; ++e) { sm[t + e * cfg::TN] = v[e]; }
+        for (int e = 0; e < E; ++e) { sm[t + e * TN] = v[e]; }
         __syncthreads();
-    }
-    if (live) {
+        if (live) {
 #pragma unroll
-        for (int e = 0; e < cfg::E; ++e) {
-            int const k = t + e * cfg::TN;
-            if (k == 0) {
-                io.store_edges(row, v[e].x + v[e].y, v[e].x - v[e].y);
-            } else {
-                C const zp = sm[cfg::M - k];
-                io.store(row, k, r2c_post(v[e], zp, __ldg(rtw + k)));
+            for (int e = 0; e < E / 2; ++e) {
+                int const k = t + e * TN;
+                if (k == 0) {
+                    io.store_edges(row, v[e].x + v[e].y, v[e].x - v[e].y);
+                } else {
+                    C xk, xmk;
+                    r2c_post_pair(v[e], sm[M - k], __ldg(rtw + k), xk, xmk);
+                    io.store(row, k, xk);
+                    io.store(row, M - k, xmk);
+                }
             }
+            if (t == 0) { io.store(row, M / 2, cconj(v[E / 2])); }  // the self-paired bin: W^(M/2) = -i
+        }
+    } else {
+        // one point per thread (M <= 4): every bin on its own
+        if constexpr (LOGM > 0) {
+            sm[t] = v[0];
+            __syncthreads();
+        }
+        if (live) {
+            int const k = t;
+            if (k == 0) { io.store_edges(row, v[0].x + v[0].y, v[0].x - v[0].y); }
+            else { io.store(row, k, r2c_post(v[0], sm[cfg::M - k], __ldg(rtw + k))); }
         }
     }
 }
 
 // ---- c2r: IO policy provides the spectrum loads and store(b, j, z[j]) -----------------------------------------------------
-#ifndef NEO_B200_C2R_SMEM_MATE_MIN
-#define NEO_B200_C2R_SMEM_MATE_MIN 11  // 2^11 complex points and up fetch the Hermitian partner through shared memory (measured: N=4096 c2r .76 -> .82)
-#endif
 template<typename T, int LOGM, class IO>
 __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOGM, k_c2r>())
     c2r_kernel(IO io, cx<T> const* __restrict__ tw, cx<T> const* __restrict__ rtw, size_t batch)
@@ -328,49 +343,46 @@ __global__ void __launch_bounds__(fft_cfg<T, LOGM>::THREADS, fft_min_ctas<T, LOG
 
     C v[cfg::E];
     typename IO::row_state row = io.open(live ? b : 0);
-    if constexpr (LOGM >= NEO_B200_C2R_SMEM_MATE_MIN) {
-        // long rows: the Hermitian partner X[M-k] comes through the exchange tile (one global load per point; a 64 KB row does
-        // not survive in L1 next to the tile, so a second global touch would be an L2 round trip)
-        C own[cfg::E];
+    if constexpr (cfg::E >= 2) {
+        // Hermitian pre-pass by PAIRS: a thread loads X[k] for the first half of its points (k < M/2) and the partners X[M-k], forms
+        // Z[k] and Z[M-k] from one twiddle product (c2r_pre_pair), keeps Z[k] and hands Z[M-k] to its owner through the (unpadded,
+        // unit-stride) tile. E global loads per thread instead of 2E, half the twiddle loads, 12 instead of 20 flops per pair.
+        constexpr int M = cfg::M, E = cfg::E, TN = cfg::TN, HALF = E / 2;
+        C own[HALF], mate[HALF];
 #pragma unroll
-        for (int e = 0; e < cfg::E; ++e) {
-            int const k = t + e * cfg::TN;
-            own[e]      = !live ? mk<T>(0, 0) : k == 0 ? io.load_edges(row) : io.load(row, k);
-        }
-#pragma unroll
-        for (int e = 0; e < cfg::E; ++e) { sm[t + e * cfg::TN] = own[e]; }  // unpadded: unit stride both ways (see r2c_kernel)
-        __syncthreads();
-#pragma unroll
-        for (int e = 0; e < cfg::E; ++e) {
-            int const k = t + e * cfg::TN;
-            if (k == 0) { v[e] = mk<T>(own[e].x + own[e].y, own[e].x - own[e].y); }
-            else { v[e] = c2r_pre(own[e], sm[cfg::M - k], __ldg(rtw + k)); }
-        }
-        __syncthreads();
-    } else {
-        // Hermitian pre-pass straight from global memory: X[k] and its partner X[M-k] are both loaded by this thread (the
-        // partner line is the one a sibling thread loads as its own X[k], so the second touch is an L1 hit); no shared-memory
-        // round trip and all 2E loads are in flight at once
-        C own[cfg::E], mate[cfg::E];
-#pragma unroll
-        for (int e = 0; e < cfg::E; ++e) {
-            int const k = t + e * cfg::TN;
+        for (int e = 0; e < HALF; ++e) {
+            int const k = t + e * TN;
             if (!live) {
                 own[e] = mate[e] = mk<T>(0, 0);
             } else if (k == 0) {
-                own[e]  = io.load_edges(row);  // (Re X[0], Re X[M])
-                mate[e] = own[e];
+                own[e]  = io.load_edges(row);    // (Re X[0], Re X[M])
+                mate[e] = io.load(row, M / 2);   // the self-paired bin
             } else {
                 own[e]  = io.load(row, k);
-                mate[e] = io.load(row, cfg::M - k);
+                mate[e] = io.load(row, M - k);
             }
         }
 #pragma unroll
-        for (int e = 0; e < cfg::E; ++e) {
-            int const k = t + e * cfg::TN;
-            if (k == 0) { v[e] = mk<T>(own[e].x + own[e].y, own[e].x - own[e].y); }
-            else { v[e] = c2r_pre(own[e], mate[e], __ldg(rtw + k)); }
+        for (int e = 0; e < HALF; ++e) {
+            int const k = t + e * TN;
+            if (k == 0) {
+                v[e]    = mk<T>(own[e].x + own[e].y, own[e].x - own[e].y);
+                v[HALF] = mk<T>(T(2) * mate[e].x, T(-2) * mate[e].y);  // Z[M/2] = 2 conj(X[M/2]); index M/2 = HALF * TN is this thread's
+            } else {
+                C zmk;
+                c2r_pre_pair(own[e], mate[e], __ldg(rtw + k), v[e], zmk);
+                sm[M - k] = zmk;
+            }
         }
+        __syncthreads();
+#pragma unroll
+        for (int e = HALF; e < E; ++e) {
+            if (!(e == HALF && t == 0)) { v[e] = sm[t + e * TN]; }
+        }
+        __syncthreads();
+    } else {
+        C const own = live ? io.load_edges(row) : mk<T>(0, 0);
+        v[0]        = mk<T>(own.x + own.y, own.x - own.y);
     }
 
     F::run(v, sm, tw, t);

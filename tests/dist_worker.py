@@ -99,16 +99,16 @@ def nccl_bank(pkg, orc, rank, world, local):
                     got2.append(y.cpu().numpy())
                 assert rel(np.concatenate(got2, axis=1), want[o0 : o0 + n_out]) < 1e-5, (kind, layout, frame)
                 bank.close()
-    # a bank wide enough for the fused frame kernel: push form (peer stores into the owner's inbox through CUDA IPC mappings, a tiny
-    # all-gather as the cross-process gate) against the reduce-scatter form (NEO_B200_BANK_NO_PUSH) and the oracle
+    # a bank wide enough for the fused frame kernel, every exchange form between processes (NEO_B200_BANK_EXCHANGE): "dma" (copy engines
+    # write into the owner's inbox through CUDA IPC mappings, a one-word all-gather as the cross-process gate), "kernel" (the fused frame
+    # kernel stores into those mappings itself) and "collective" (ncclReduceScatter), against the oracle and each other
     C2, B2, P2, T2, steps2 = 64, 128, 128, 32, 5
     ir2 = orc.normalize_impulse(np.stack([orc.noise(B2 * P2 - 3, 11 + c, np.float32) for c in range(C2)]))
     sig2 = np.stack([orc.noise(B2 * T2 * steps2, 13 + c, np.float32) for c in range(C2)])
     want2 = orc.convolve_blocks(0, orc.uniform_partition(ir2, B2), sig2)
     forms = {}
-    for form in ("push", "reduce_scatter"):
-        if form == "reduce_scatter":
-            os.environ["NEO_B200_BANK_NO_PUSH"] = "1"
+    for form in ("dma", "kernel", "collective"):
+        os.environ["NEO_B200_BANK_EXCHANGE"] = form
         uid = [pkg.bank_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         bank = pkg.Bank(pkg.UPOLS, "float32", pkg.DIAGONAL, C2, C2, B2, P2, frame_blocks=T2, layout=(1, 2), rank=rank, world=world,
@@ -120,8 +120,9 @@ def nccl_bank(pkg, orc, rank, world, local):
         outs = [np.zeros((n_out, T2 * B2), np.float32) for _ in range(steps2)]
         for s in range(steps2):
             bank.submit([ins[s]], [outs[s]])
-            if s >= 1:
+            if s >= 2:
                 bank.wait()
+        bank.wait()
         bank.wait()
         forms[form] = np.concatenate(outs, axis=1)
         err = rel(forms[form], want2[o0 : o0 + n_out])
@@ -129,8 +130,9 @@ def nccl_bank(pkg, orc, rank, world, local):
         worst = max(worst, err)
         forms[form + "_bytes"] = bank.device_bytes(0)
         bank.close()
-    os.environ.pop("NEO_B200_BANK_NO_PUSH", None)
-    assert forms["push_bytes"] != forms["reduce_scatter_bytes"], "the push form was not taken"
+    os.environ.pop("NEO_B200_BANK_EXCHANGE", None)
+    assert forms["dma_bytes"] != forms["collective_bytes"] and forms["kernel_bytes"] != forms["collective_bytes"], "form not taken"
+    assert np.array_equal(forms["dma"], forms["kernel"])
     # matrix topology sharded by output channel (BASELINE config 4's sharding) and by partitions
     O, I, L = 4, 2, B * 6
     irm = np.stack([np.stack([orc.noise(L, 100 + 10 * o + i, np.float32) for i in range(I)]) for o in range(O)])

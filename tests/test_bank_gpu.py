@@ -142,18 +142,18 @@ def test_bank_device_buffers_and_profile(gpu, orc):
 
 
 @pytest.mark.parametrize("block,T,P,channels,layout", [(256, 8, 32, 64, (1, 2)), (128, 32, 128, 64, (2, 2)), (128, 32, 128, 32, (1, 4))])
-def test_bank_push_form_fused_frame_kernel(gpu, orc, monkeypatch, block, T, P, channels, layout):
-    # banks wide enough for the fused frame kernel: every partition shard writes the partial spectra of a channel straight into the
-    # inbox of the rank that finishes it (peer stores inside frame_fused_kernel), the c2r kernel sums the inbox slots. Same answer
-    # as the pull form (NEO_B200_BANK_NO_PUSH: c2r loads the shards' buffers) and as the oracle.
+def test_bank_exchange_forms_agree(gpu, orc, monkeypatch, block, T, P, channels, layout):
+    # three ways for the partial spectra of a group to reach the rank that finishes a channel (NEO_B200_BANK_EXCHANGE), on banks wide
+    # enough for the fused frame kernel: "dma" (default: copy engines move each owner's rows into its inbox, the c2r kernel sums its own
+    # rows and the inbox slots), "kernel" (frame_fused_kernel stores the rows into the owners' inboxes itself: peer stores) and
+    # "collective" (the c2r kernel loads the shards' buffers through peer pointers). Same bits, and the oracle's answer.
     steps = 5
     ir, sig = make_case(orc, channels, block * P - 3, block, T * steps)
     want = orc.convolve_blocks(0, orc.uniform_partition(ir, block), sig)
     n = layout[0] * layout[1]
     results, sizes = {}, {}
-    for form in ("push", "pull"):
-        if form == "pull":
-            monkeypatch.setenv("NEO_B200_BANK_NO_PUSH", "1")
+    for form in ("dma", "kernel", "collective"):
+        monkeypatch.setenv("NEO_B200_BANK_EXCHANGE", form)
         bank = gpu.Bank(gpu.UPOLS, np.float32, gpu.DIAGONAL, channels, channels, block, P, frame_blocks=T, layout=layout, devices=devices_for(gpu, n))
         bank.impulse_global(ir)
         results[form] = run_bank_steps(bank, sig, block, T, pipelined=True)
@@ -163,9 +163,30 @@ def test_bank_push_form_fused_frame_kernel(gpu, orc, monkeypatch, block, T, P, c
             sl = slice(st * T * block, (st + 1) * T * block)
             assert rel_l2(results[form][:, sl], want[:, sl]) <= 2e-5, (form, st)
         bank.close()
-    monkeypatch.delenv("NEO_B200_BANK_NO_PUSH")
-    assert sizes["push"] > sizes["pull"], "the push form allocates inboxes: it was not taken"
-    assert np.array_equal(results["push"], results["pull"])  # same partial spectra summed in the same shard order
+    monkeypatch.delenv("NEO_B200_BANK_EXCHANGE")
+    assert sizes["dma"] > sizes["collective"] and sizes["kernel"] > sizes["collective"], "inboxes were not allocated: form not taken"
+    assert np.array_equal(results["dma"], results["collective"]) and np.array_equal(results["kernel"], results["collective"])
+
+
+def test_bank_dma_exchange_direct_form_and_upola(gpu, orc):
+    # the default exchange works on any kernel path: direct form with ragged call lengths, overlap-add, float64
+    C, B, P = 8, 64, 12
+    pattern = [2, 3, 1, 3, 3, 2]
+    for kind, real in ((gpu.UPOLS, np.float32), (gpu.UPOLA, np.float64)):
+        ir, sig = make_case(orc, C, B * P - 7, B, sum(pattern), real)
+        want = orc.convolve_blocks(kind, orc.uniform_partition(ir, B), sig)
+        bank = gpu.Bank(kind, real, gpu.DIAGONAL, C, C, B, P, max_blocks=3, layout=(2, 2), devices=devices_for(gpu, 4))
+        bank.impulse_global(ir)
+        got = np.zeros_like(sig)
+        pos = 0
+        for t in pattern:
+            x = np.ascontiguousarray(sig[:, pos * B : (pos + t) * B])
+            y = np.zeros_like(x)
+            bank(x, y)
+            got[:, pos * B : (pos + t) * B] = y
+            pos += t
+        assert rel_l2(got, want) <= TOL[np.dtype(real).name], (kind, rel_l2(got, want))
+        bank.close()
 
 
 def test_bank_error_contract(gpu):
