@@ -328,7 +328,7 @@ NEO_B200_API size_t neo_b200_conv_device_bytes(neo_b200_conv const* conv);
  *              compute kernel is spent on the exchange;
  *   kernel     the fused frame kernel stores the result rows straight into the owners' inboxes (peer stores from inside the kernel);
  *   collective ncclReduceScatter of the partial spectra (rank-per-process banks) / peer loads inside the c2r kernel (devices[] banks).
- * All three give the same bits (shards are summed in shard order). */
+ * dma, kernel and the peer-load form sum in shard order and give identical bits; ncclReduceScatter sums in NCCL's own order. */
 typedef struct neo_b200_bank neo_b200_bank;
 
 typedef struct neo_b200_bank_layout
