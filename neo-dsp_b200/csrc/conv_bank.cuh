@@ -179,6 +179,16 @@ struct bank_rank
 }  // namespace
 }  // namespace neo_b200
 
+// a submitted step: its inverse side (sum of the group's partial spectra + c2r + copy-out) may still be waiting to be enqueued
+struct neo_b200_bank_step
+{
+    std::uint64_t step{0};
+    size_t blocks{0};
+    int memspace{0};
+    std::vector<void*> out_rows;
+    bool finished{false};
+};
+
 struct neo_b200_bank
 {
     neo_b200_conv_config cfg{};
@@ -188,7 +198,7 @@ struct neo_b200_bank
     neo_b200::nccl_api* api{nullptr};
     std::deque<neo_b200::bank_rank> ranks;   // the ranks of this process, ascending (deque: a rank owns device buffers and never moves)
     std::uint64_t step{0};
-    std::deque<std::uint64_t> pending;       // submitted, not yet waited for
+    std::deque<neo_b200_bank_step> pending;  // submitted, not yet waited for
     bool has_filter{false};
 
     ~neo_b200_bank()
@@ -385,10 +395,14 @@ inline void bank_domains(neo_b200_bank const* bank, bank_rank const& r, std::vec
     }
 }
 
+int bank_finish(neo_b200_bank* bank, neo_b200_bank_step& st);
+int bank_finish_older(neo_b200_bank* bank);
+
 int bank_wait_oldest(neo_b200_bank* bank)
 {
     if (bank->pending.empty()) { return NEO_B200_OK; }
-    int const e = int(bank->pending.front() & 3U);
+    NEO_TRY(bank_finish(bank, bank->pending.front()));  // nobody submitted after it: its inverse side has not been enqueued yet
+    int const e = int(bank->pending.front().step & 3U);
     for (auto& r : bank->ranks) {
         NEO_CUDA_TRY(cudaSetDevice(r.info.device));
         NEO_CUDA_TRY(cudaEventSynchronize(r.ev_out[e]));
@@ -447,6 +461,11 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         NEO_CUDA_TRY(cudaEventRecord(r.ev_in[e0], r.s_in));
     }
 
+    // kernel-push form: the gate behind this step's forward waits for the previous step's c2r, so that c2r goes first
+    bool any_push = false;
+    for (auto& r : bank->ranks) { any_push = any_push || r.push; }
+    if (any_push) { NEO_TRY(bank_finish_older(bank)); }
+
     // ---- 2. forward: window + r2c + delay line + MAC of the rank's partitions -> partial spectra ----
     for (auto& r : bank->ranks) {
         NEO_CUDA_TRY(cudaSetDevice(r.info.device));
@@ -499,6 +518,9 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         NEO_CUDA_TRY(cudaEventRecord(r.ev_fwd[e0], r.s_cmp));
     }
 
+    // the previous step's inverse side goes behind this step's forward on the compute stream (its exchange had the forward to finish)
+    NEO_TRY(bank_finish_older(bank));
+
     // ---- 3a. copy-engine exchange: each rank hands every other shard of its group the partial spectra of THAT shard's channels ----
     for (auto& r : bank->ranks) {
         if (!r.dma) { continue; }
@@ -524,25 +546,61 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         NEO_CUDA_TRY(cudaEventRecord(r.ev_red[e0], r.s_red));
     }
 
-    // ---- 3b. reduction over the partition shards + c2r for the rank's own channels; 4. output rows ----
+    // the reduce-scatter of the collective form is this step's exchange too
+    for (auto& r : bank->ranks) {
+        if (gp_n == 1 || r.dma || r.push || !bank->nccl) { continue; }
+        NEO_CUDA_TRY(cudaSetDevice(r.info.device));
+        size_t const own_elems = r.info.out_count * blocks * c.block;
+        NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_red, r.ev_fwd[e0], 0));
+        NEO_TRY(wait_for(r.s_red, ago(r.ev_c2r, 2)));  // the c2r of two steps ago read red[b]
+        NEO_TRY(r.red[b].reserve(own_elems * sizeof(cx<T>)));
+        NEO_NCCL_TRY(bank->api, bank->api->ReduceScatter(r.partial[b], r.red[b].ptr, own_elems * 2,
+                                                         sizeof(T) == 4 ? nccl_api::k_float32 : nccl_api::k_float64, nccl_api::k_sum, r.comm_out,
+                                                         r.s_red));
+        NEO_CUDA_TRY(cudaEventRecord(r.ev_red[e0], r.s_red));
+    }
+
+    neo_b200_bank_step st;
+    st.step     = step;
+    st.blocks   = blocks;
+    st.memspace = memspace;
+    st.out_rows.assign(out_rows, out_rows + bank->ranks.size());
+    bank->pending.push_back(std::move(st));
+    ++bank->step;
+    // without partition shards nothing is exchanged: the inverse side follows at once. With shards it is enqueued behind the NEXT
+    // step's forward (or by wait), so the exchange of this step has a whole forward to complete and the compute stream never idles.
+    if (gp_n == 1) { NEO_TRY(bank_finish(bank, bank->pending.back())); }
+    return NEO_B200_OK;
+}
+
+// ---- 3b. sum over the partition shards + c2r for the rank's own channels; 4. output rows. On the compute stream: the transforms are
+// issue-bound, running them beside the next forward only slows both (measured), what overlaps them is the copy engines' work ----
+template<typename T>
+int bank_finish_impl(neo_b200_bank* bank, neo_b200_bank_step& st)
+{
+    neo_b200_conv_config const& c = bank->cfg;
+    size_t const blocks = st.blocks;
+    size_t const pitch  = blocks * c.block;
+    int const b         = int(st.step & 1U);
+    int const e0        = int(st.step & 3U);
+    size_t const gp_n   = bank->layout.partition_shards;
+    bool const host     = st.memspace == NEO_B200_HOST;
     for (size_t l = 0; l < bank->ranks.size(); ++l) {
         bank_rank& r = bank->ranks[l];
         NEO_CUDA_TRY(cudaSetDevice(r.info.device));
         std::vector<size_t> reduce;
         bank_domains(bank, r, nullptr, &reduce);
         size_t const own_in_group = r.info.out_first - r.info.group_first;  // first own channel, relative to the group
-        size_t const own_elems    = r.info.out_count * blocks * c.block;    // complex elements of the rank's own spectra
         cx<T> const* srcs[k_bank_max_shards];
         int nsrc = 1;
         if (gp_n == 1) {
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[e0], 0));
-            srcs[0] = static_cast<cx<T> const*>(r.partial[b]) + own_in_group * blocks * c.block;
+            srcs[0] = static_cast<cx<T> const*>(r.partial[b]) + own_in_group * blocks * c.block;  // same stream as the forward
         } else if (r.dma) {
             // own rows straight from the rank's partial spectra, the other shards' rows from the inbox: a LOCAL sum, in shard order
             if (bank->nccl) {
-                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_red[e0], 0));  // recorded behind the gate
+                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_red[e0], 0));  // recorded behind the gate
             } else {
-                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, bank->find(p)->ev_red[e0], 0)); }
+                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, bank->find(p)->ev_red[e0], 0)); }
             }
             nsrc = int(gp_n);
             for (size_t s = 0; s < gp_n; ++s) {
@@ -551,52 +609,60 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
             }
         } else if (r.push) {
             // the shards have pushed their partial spectra of my channels into my inbox: a LOCAL sum, in shard order
-            if (bank->nccl) {
-                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_fwd[e0], 0));  // recorded behind the gate
-            } else {
-                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, bank->find(p)->ev_fwd[e0], 0)); }
+            // (rank-per-process: the gate sits on this stream behind the forward)
+            if (!bank->nccl) {
+                for (size_t p : reduce) { NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, bank->find(p)->ev_fwd[e0], 0)); }
             }
             nsrc = int(gp_n);
             for (size_t s = 0; s < gp_n; ++s) { srcs[s] = r.inbox.template as<cx<T>>() + (size_t(b) * gp_n + s) * r.inbox_slot; }
         } else if (bank->nccl) {
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_red, r.ev_fwd[e0], 0));
-            NEO_TRY(wait_for(r.s_red, ago(r.ev_c2r, 2)));  // the c2r of two steps ago read red[b]
-            NEO_TRY(r.red[b].reserve(own_elems * sizeof(cx<T>)));
-            NEO_NCCL_TRY(bank->api, bank->api->ReduceScatter(r.partial[b], r.red[b].ptr, own_elems * 2,
-                                                             sizeof(T) == 4 ? nccl_api::k_float32 : nccl_api::k_float64, nccl_api::k_sum,
-                                                             r.comm_out, r.s_red));
-            NEO_CUDA_TRY(cudaEventRecord(r.ev_red[e0], r.s_red));
-            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_red[e0], 0));
+            NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_red[e0], 0));
             srcs[0] = r.red[b].template as<cx<T>>();
         } else {
             nsrc = 0;
             for (size_t p : reduce) {  // shard order: every rank sums in the same order
                 bank_rank* const peer = bank->find(p);
-                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, peer->ev_fwd[e0], 0));
+                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, peer->ev_fwd[e0], 0));
                 srcs[nsrc++] = static_cast<cx<T> const*>(peer->partial[b]) + own_in_group * blocks * c.block;
             }
         }
-        T* dst = static_cast<T*>(out_rows[l]);
+        T* dst = static_cast<T*>(st.out_rows[l]);
         if (host) {
-            device_buffer& stage = r.yout[step % k_bank_depth];  // its previous copy-out is ahead of this step on the same stream
+            device_buffer& stage = r.yout[st.step % k_bank_depth];
             NEO_TRY(stage.reserve(r.info.out_count * c.max_blocks * c.block * sizeof(T)));
             dst = stage.template as<T>();
+            if (st.step >= k_bank_depth) {  // its previous copy-out (on the output stream) has left
+                NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_cmp, r.ev_out[(st.step - k_bank_depth) & 3U], 0));
+            }
         }
         NEO_TRY(bank_with_engine(r.conv, [&](auto& e) -> int {
             using E = std::remove_reference_t<decltype(e)>;
             if constexpr (std::is_same_v<E, conv_engine<T>>) {
-                return e.inverse_sum(srcs, nsrc, dst, pitch, own_in_group, r.info.out_count, blocks, r.s_out);
+                return e.inverse_sum(srcs, nsrc, dst, pitch, own_in_group, r.info.out_count, blocks, r.s_cmp);
             }
             return NEO_B200_OK;
         }));
-        NEO_CUDA_TRY(cudaEventRecord(r.ev_c2r[e0], r.s_out));
+        NEO_CUDA_TRY(cudaEventRecord(r.ev_c2r[e0], r.s_cmp));
+        NEO_CUDA_TRY(cudaStreamWaitEvent(r.s_out, r.ev_c2r[e0], 0));
         if (host) {
-            NEO_CUDA_TRY(cudaMemcpyAsync(out_rows[l], dst, r.info.out_count * pitch * sizeof(T), cudaMemcpyDeviceToHost, r.s_out));
+            NEO_CUDA_TRY(cudaMemcpyAsync(st.out_rows[l], dst, r.info.out_count * pitch * sizeof(T), cudaMemcpyDeviceToHost, r.s_out));
         }
         NEO_CUDA_TRY(cudaEventRecord(r.ev_out[e0], r.s_out));
     }
-    bank->pending.push_back(step);
-    ++bank->step;
+    st.finished = true;
+    return NEO_B200_OK;
+}
+
+int bank_finish(neo_b200_bank* bank, neo_b200_bank_step& st)
+{
+    if (st.finished) { return NEO_B200_OK; }
+    return bank->cfg.dtype == NEO_B200_F32 ? bank_finish_impl<float>(bank, st) : bank_finish_impl<double>(bank, st);
+}
+
+// enqueue the inverse side of every step submitted before the current one
+int bank_finish_older(neo_b200_bank* bank)
+{
+    for (auto& st : bank->pending) { NEO_TRY(bank_finish(bank, st)); }
     return NEO_B200_OK;
 }
 
@@ -835,6 +901,7 @@ int neo_b200_bank_timer_stop(neo_b200_bank* bank, double* ms)
     if (bank == nullptr || ms == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
     int before = 0;
     cudaGetDevice(&before);
+    NEO_TRY(bank_finish_older(bank));  // the inverse side of the last step may still be waiting for a next submit
     for (auto& r : bank->ranks) {  // every step ends on the output stream: the event follows the last submitted step there
         NEO_CUDA_TRY(cudaSetDevice(r.info.device));
         NEO_CUDA_TRY(cudaEventRecord(r.t_end, r.s_out));
