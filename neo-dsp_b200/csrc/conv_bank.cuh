@@ -128,6 +128,12 @@ struct bank_rank
     void* inbox_of[k_bank_max_shards] = {};
     bool inbox_ipc[k_bank_max_shards] = {};
     device_buffer gate;            // nccl transport: one word per shard, all-gathered as a cross-process stream barrier
+    // input rows by copy engine between processes: the other ranks' input rings as CUDA IPC mappings (index = position in the rank's
+    // gather domain), the number of slots of each, and the gate words of the input side
+    bool dma_in{false};
+    std::vector<void*> xring_of;
+    std::vector<size_t> xslots_of;
+    device_buffer gate_in;
     size_t gather_first{0}, gather_count{0};  // input rows the rank's forward reads (global index, count)
     nccl_api::comm_t comm_world{nullptr}, comm_in{nullptr}, comm_out{nullptr};
 
@@ -157,6 +163,11 @@ struct bank_rank
         }
         for (int s = 0; s < k_bank_max_shards; ++s) {
             if (inbox_ipc[s] && inbox_of[s] != nullptr) { cudaIpcCloseMemHandle(inbox_of[s]); }
+        }
+        if (dma_in) {
+            for (void* p : xring_of) {
+                if (p != nullptr && p != xring.ptr) { cudaIpcCloseMemHandle(p); }
+            }
         }
         neo_b200_conv_destroy(conv);
         xring.release();
@@ -324,6 +335,52 @@ int bank_build_rank(neo_b200_bank* bank, bank_rank& r)
 
 // push form: every rank of a group learns where the other shards' inboxes are. All ranks in one process: their pointers, readable
 // and writable through peer access. One rank per process: CUDA IPC handles, exchanged with ncclAllGather on the group communicator.
+inline void bank_domains(neo_b200_bank const* bank, bank_rank const& r, std::vector<size_t>* gather, std::vector<size_t>* reduce);
+
+// rank-per-process banks, copy-engine exchange: the ranks of a gather domain map each other's input rings (CUDA IPC), so that a rank's
+// input rows reach the others by cudaMemcpyAsync over NVLink instead of an SM-resident ncclAllGather kernel
+int bank_connect_inputs(neo_b200_bank* bank)
+{
+    if (!bank->nccl) { return NEO_B200_OK; }
+    char const* const how = std::getenv("NEO_B200_BANK_EXCHANGE");
+    if (how != nullptr && std::string(how) == "collective") { return NEO_B200_OK; }
+    for (auto& r : bank->ranks) {
+        std::vector<size_t> gather;
+        bank_domains(bank, r, &gather, nullptr);
+        if (gather.size() <= 1) { continue; }
+        NEO_CUDA_TRY(cudaSetDevice(r.info.device));
+        size_t const n = gather.size();
+        size_t me      = 0;
+        for (size_t i = 0; i < n; ++i) {
+            if (gather[i] == size_t(r.info.rank)) { me = i; }
+        }
+        cudaIpcMemHandle_t mine{};
+        NEO_CUDA_TRY(cudaIpcGetMemHandle(&mine, r.xring.ptr));
+        device_buffer staging;
+        NEO_TRY(staging.reserve(n * sizeof(mine)));
+        char* const slots = staging.as<char>();
+        NEO_CUDA_TRY(cudaMemcpyAsync(slots + me * sizeof(mine), &mine, sizeof(mine), cudaMemcpyHostToDevice, r.s_in));
+        NEO_NCCL_TRY(bank->api, bank->api->AllGather(slots + me * sizeof(mine), slots, sizeof(mine) / 4, nccl_api::k_float32, r.comm_in, r.s_in));
+        std::vector<cudaIpcMemHandle_t> all(n);
+        NEO_CUDA_TRY(cudaMemcpyAsync(all.data(), slots, n * sizeof(mine), cudaMemcpyDeviceToHost, r.s_in));
+        NEO_CUDA_TRY(cudaStreamSynchronize(r.s_in));
+        r.xring_of.assign(n, nullptr);
+        r.xslots_of.assign(n, 0);
+        for (size_t i = 0; i < n; ++i) {
+            neo_b200_bank_rank_info peer{};
+            bank_fill_info(bank->cfg, bank->layout, bank->world, gather[i], -1, &peer);
+            r.xslots_of[i] = (bank->cfg.frame_blocks > 0 ? peer.delay_blocks / bank->cfg.frame_blocks : 0) + k_bank_depth;
+            if (i == me) { r.xring_of[i] = r.xring.ptr; }
+            else { NEO_CUDA_TRY(cudaIpcOpenMemHandle(&r.xring_of[i], all[i], cudaIpcMemLazyEnablePeerAccess)); }
+        }
+        NEO_TRY(r.gate_in.reserve(n * sizeof(float)));
+        NEO_CUDA_TRY(cudaMemsetAsync(r.gate_in.ptr, 0, r.gate_in.bytes, r.s_in));
+        NEO_CUDA_TRY(cudaStreamSynchronize(r.s_in));
+        r.dma_in = true;
+    }
+    return NEO_B200_OK;
+}
+
 int bank_connect_inboxes(neo_b200_bank* bank)
 {
     size_t const gp_n = bank->layout.partition_shards;
@@ -446,7 +503,24 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
         size_t const bytes = r.info.in_count * pitch * sizeof(T);
         NEO_CUDA_TRY(cudaMemcpyAsync(slot + mine, in_rows[l], bytes, kin, r.s_in));
         if (gather.size() > 1) {
-            if (bank->nccl) {
+            if (bank->nccl && r.dma_in) {
+                // copy engines push the rows into the other ranks' rings (all ranks of a gather domain hold the same rows per slot)
+                size_t me = 0;
+                for (size_t i = 0; i < gather.size(); ++i) {
+                    if (gather[i] == size_t(r.info.rank)) { me = i; }
+                }
+                for (size_t i = 0; i < gather.size(); ++i) {
+                    if (i == me) { continue; }
+                    T* const dst = static_cast<T*>(r.xring_of[i]) + (step % r.xslots_of[i]) * r.slot_elems + mine;
+                    NEO_CUDA_TRY(cudaMemcpyAsync(dst, slot + mine, bytes, cudaMemcpyDeviceToDevice, r.s_in));
+                }
+                // gate of the input side: completes here when every rank of the domain has reached it -- its rows of this step have
+                // landed and, because each rank first waits for its own forward of two steps ago, the slots step i+1 overwrites
+                // (last read by the forwards of step i-2) are free
+                NEO_TRY(wait_for(r.s_in, ago(r.ev_fwd, 2)));
+                float* const words = r.gate_in.as<float>();
+                NEO_NCCL_TRY(bank->api, bank->api->AllGather(words + me, words, 1, nccl_api::k_float32, r.comm_in, r.s_in));
+            } else if (bank->nccl) {
                 NEO_NCCL_TRY(bank->api, bank->api->AllGather(slot + mine, slot, r.info.in_count * pitch,
                                                              sizeof(T) == 4 ? nccl_api::k_float32 : nccl_api::k_float64, r.comm_in, r.s_in));
             } else {
@@ -766,6 +840,7 @@ int neo_b200_bank_create_rank(neo_b200_bank** out, neo_b200_conv_config const* c
     }
     NEO_TRY(bank_build_rank(bank.get(), r));
     NEO_TRY(bank_connect_inboxes(bank.get()));
+    NEO_TRY(bank_connect_inputs(bank.get()));
     *out = bank.release();
     return NEO_B200_OK;
 }
