@@ -920,6 +920,18 @@ int neo_b200_bank_reset(neo_b200_bank* bank)
         NEO_TRY(neo_b200_conv_reset(r.conv));
         NEO_TRY(neo_b200_conv_synchronize(r.conv));
         NEO_CUDA_TRY(cudaMemsetAsync(r.xring.ptr, 0, r.xring.bytes, r.s_in));
+        // rank-per-process: nobody may push rows of the next step into this ring before it has been cleared -- every rank of the
+        // gather domain passes this gate only after all of them have cleared theirs
+        if (r.dma_in) {
+            float* const words = r.gate_in.as<float>();
+            size_t me          = 0;
+            std::vector<size_t> gather;
+            bank_domains(bank, r, &gather, nullptr);
+            for (size_t i = 0; i < gather.size(); ++i) {
+                if (gather[i] == size_t(r.info.rank)) { me = i; }
+            }
+            NEO_NCCL_TRY(bank->api, bank->api->AllGather(words + me, words, 1, nccl_api::k_float32, r.comm_in, r.s_in));
+        }
         NEO_CUDA_TRY(cudaStreamSynchronize(r.s_in));
     }
     cudaSetDevice(before);

@@ -693,11 +693,18 @@ struct conv_c2r_sum_io
     }
     __device__ __forceinline__ C load(row_state const& r, int k) const
     {
-        C v = src[0][r.off + k];
-        for (int j = 1; j < nsrc; ++j) {
-            C const p = src[j][r.off + k];
-            v.x += p.x;
-            v.y += p.y;
+        // fully unrolled with a uniform predicate: the source pointers stay in registers / constant bank (a run-time indexed pointer
+        // array would be copied to local memory) and the loads of all sources are in flight together
+        C p[k_bank_max_shards];
+#pragma unroll
+        for (int j = 0; j < k_bank_max_shards; ++j) { p[j] = j < nsrc ? src[j][r.off + k] : mk<T>(T(0), T(0)); }
+        C v = p[0];
+#pragma unroll
+        for (int j = 1; j < k_bank_max_shards; ++j) {
+            if (j < nsrc) {
+                v.x += p[j].x;
+                v.y += p[j].y;
+            }
         }
         return v;
     }

@@ -57,6 +57,11 @@ def gloo_layouts(pkg, orc, rank, world):
     return worst
 
 
+def note(rank, *what):
+    if rank == 0:
+        print("dist_worker:", *what, file=sys.stderr, flush=True)
+
+
 def nccl_bank(pkg, orc, rank, world, local):
     worst = 0.0
     uid_box = [pkg.bank_unique_id() if rank == 0 else None]
@@ -70,6 +75,7 @@ def nccl_bank(pkg, orc, rank, world, local):
         want = orc.convolve_blocks(kind, H, sig)
         for layout in ((1, 2), (2, 1)):
             for frame in (0, T):
+                note(rank, "diagonal", kind, layout, frame)
                 uid = [pkg.bank_unique_id() if rank == 0 else None]
                 dist.broadcast_object_list(uid, src=0)
                 bank = pkg.Bank(kind, "float32", pkg.DIAGONAL, C, C, B, P, max_blocks=T, frame_blocks=frame, layout=layout, rank=rank,
@@ -89,6 +95,7 @@ def nccl_bank(pkg, orc, rank, world, local):
                 assert err < 1e-5, (kind, layout, frame, err)
                 worst = max(worst, err)
                 # device buffers after a reset
+                note(rank, "  reset + device buffers")
                 bank.reset()
                 got2 = []
                 for s in range(steps):
@@ -109,6 +116,7 @@ def nccl_bank(pkg, orc, rank, world, local):
     forms = {}
     for form in ("dma", "kernel", "collective"):
         os.environ["NEO_B200_BANK_EXCHANGE"] = form
+        note(rank, "exchange form", form)
         uid = [pkg.bank_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         bank = pkg.Bank(pkg.UPOLS, "float32", pkg.DIAGONAL, C2, C2, B2, P2, frame_blocks=T2, layout=(1, 2), rank=rank, world=world,
@@ -144,6 +152,7 @@ def nccl_bank(pkg, orc, rank, world, local):
     for layout in ((2, 1), (1, 2)):
         for frame in (0, 2):
             Tm = 2
+            note(rank, "matrix", layout, frame)
             uid = [pkg.bank_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(uid, src=0)
             bank = pkg.Bank(pkg.UPOLS, "float32", pkg.MATRIX, O, I, B, L // B, max_blocks=Tm, frame_blocks=frame, layout=layout, rank=rank,
@@ -187,4 +196,11 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except BaseException:  # a failed rank must not sit in a destructor waiting for a collective its peer will never join
+        import traceback
+
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
