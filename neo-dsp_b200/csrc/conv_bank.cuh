@@ -641,9 +641,11 @@ int bank_submit_impl(neo_b200_bank* bank, void const* const* in_rows, void* cons
     st.out_rows.assign(out_rows, out_rows + bank->ranks.size());
     bank->pending.push_back(std::move(st));
     ++bank->step;
-    // without partition shards nothing is exchanged: the inverse side follows at once. With shards it is enqueued behind the NEXT
-    // step's forward (or by wait), so the exchange of this step has a whole forward to complete and the compute stream never idles.
-    if (gp_n == 1) { NEO_TRY(bank_finish(bank, bank->pending.back())); }
+    // without partition shards nothing is exchanged: the inverse side follows at once. With shards and DEVICE buffers it is enqueued
+    // behind the NEXT step's forward (or by wait), so the exchange of this step has a whole forward to complete and the compute stream
+    // never idles. HOST calls are bound by the host link, not by the kernels: there the copy-out must start as early as possible
+    // (deferring it would put a forward and an input copy between a step's c2r and the submit that its completion unblocks).
+    if (gp_n == 1 || host) { NEO_TRY(bank_finish(bank, bank->pending.back())); }
     return NEO_B200_OK;
 }
 
