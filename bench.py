@@ -872,7 +872,21 @@ def sharded_c4(args, pkg, torch, dist, rank, world, local):
     return out
 
 
+def bind_to_gpu_numa_node(local: int):
+    """pin this rank's threads to the CPUs next to its GPU (NVML's ideal affinity) BEFORE any pinned host memory is allocated, so the
+    staging buffers are first-touched on the GPU's own NUMA node and the ranks do not all pull through one socket"""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(local))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def run_sharded(args, pkg, torch, dist, emit, rank, world, local, peak, peak_src):
+    cpus = bind_to_gpu_numa_node(local)
     frame = args.frame
     layout = parse_layout(args.layout, world)
     if frame > 0:
@@ -908,6 +922,7 @@ def run_sharded(args, pkg, torch, dist, emit, rank, world, local, peak, peak_src
                 "layout": {"channel_groups": layout[0], "partition_shards": layout[1]},
                 "l2": "working set per rank and step (filter + delay line, several GB) exceeds the 126 MB L2; 4 rotating input buffers",
                 "realtime_x_aggregate_48k": main["value"] * 1e6 / 48000.0, "realtime_x_wall_1024ch_48k": main["realtime_x_wall_1024ch_48k"],
+                "host_cpus_rank0": f"{len(cpus)} CPUs next to GPU 0 (NVML affinity)" if cpus else "default affinity",
             },
             "clocks": main["clocks"], "e2e": main.get("e2e"), "gpu_launches": main["gpu_launches"], "roofline": main["roofline"],
             "parity_rel_l2": main["parity_rel_l2"], "parity_tolerance": PARITY_TOL,

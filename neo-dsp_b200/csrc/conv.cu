@@ -668,15 +668,17 @@ struct conv_engine
                     conv_c2r_io<T, LOGM> io{srcs[0], int(blocks), dst, out_stride, T(1) / T(2 * m), ola ? 1 : 0};
                     status = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
                 } else {
-                    conv_c2r_sum_io<T, LOGM> io{};
-                    for (int j = 0; j < nsrc; ++j) { io.src[j] = srcs[j]; }
-                    io.nsrc        = nsrc;
-                    io.blocks      = int(blocks);
-                    io.out         = dst;
-                    io.out_stride  = out_stride;
-                    io.scale       = T(1) / T(2 * m);
-                    io.overlap_add = ola ? 1 : 0;
-                    status         = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
+                    auto const run = [&](auto io) {
+                        for (int j = 0; j < nsrc; ++j) { io.src[j] = srcs[j]; }
+                        io.nsrc        = nsrc;
+                        io.blocks      = int(blocks);
+                        io.out         = dst;
+                        io.out_stride  = out_stride;
+                        io.scale       = T(1) / T(2 * m);
+                        io.overlap_add = ola ? 1 : 0;
+                        return launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
+                    };
+                    status = nsrc == 2 ? run(conv_c2r_sum_io<T, LOGM, 2>{}) : run(conv_c2r_sum_io<T, LOGM, 0>{});
                 }
             }
         });

@@ -666,7 +666,9 @@ struct conv_c2r_io
 // shard order, so every device would produce the same bits for the same channel.
 constexpr int k_bank_max_shards = 8;
 
-template<typename T, int LOGM>
+// NSRC > 0: the number of shards is a compile-time constant (two, the common split: no predicated loads or adds in the instruction
+// stream -- the run-time form issues all k_bank_max_shards of them, 40 % more instructions at two shards); NSRC = 0: `nsrc` at run time
+template<typename T, int LOGM, int NSRC = 0>
 struct conv_c2r_sum_io
 {
     using C = cx<T>;
@@ -693,20 +695,33 @@ struct conv_c2r_sum_io
     }
     __device__ __forceinline__ C load(row_state const& r, int k) const
     {
-        // fully unrolled with a uniform predicate: the source pointers stay in registers / constant bank (a run-time indexed pointer
-        // array would be copied to local memory) and the loads of all sources are in flight together
-        C p[k_bank_max_shards];
+        if constexpr (NSRC > 0) {
+            C p[NSRC];
 #pragma unroll
-        for (int j = 0; j < k_bank_max_shards; ++j) { p[j] = j < nsrc ? src[j][r.off + k] : mk<T>(T(0), T(0)); }
-        C v = p[0];
+            for (int j = 0; j < NSRC; ++j) { p[j] = src[j][r.off + k]; }
+            C v = p[0];
 #pragma unroll
-        for (int j = 1; j < k_bank_max_shards; ++j) {
-            if (j < nsrc) {
+            for (int j = 1; j < NSRC; ++j) {
                 v.x += p[j].x;
                 v.y += p[j].y;
             }
+            return v;
+        } else {
+            // fully unrolled with a uniform predicate: the source pointers stay in registers / constant bank (a run-time indexed
+            // pointer array would be copied to local memory) and the loads of all sources are in flight together
+            C p[k_bank_max_shards];
+#pragma unroll
+            for (int j = 0; j < k_bank_max_shards; ++j) { p[j] = j < nsrc ? src[j][r.off + k] : mk<T>(T(0), T(0)); }
+            C v = p[0];
+#pragma unroll
+            for (int j = 1; j < k_bank_max_shards; ++j) {
+                if (j < nsrc) {
+                    v.x += p[j].x;
+                    v.y += p[j].y;
+                }
+            }
+            return v;
         }
-        return v;
     }
     __device__ __forceinline__ C load_edges(row_state const& r) const { return load(r, 0); }
     __device__ __forceinline__ void store(row_state const& r, int j, C z) const
