@@ -498,6 +498,77 @@ private:
     neo_b200_conv_config _cfg{};
 };
 
+/// The same bank spread over several GPUs of one box (neo_b200_bank_*): what a host that builds one convolver per channel on N
+/// threads (extra/cli/src/convolver.cpp:37-40) does with N devices instead. `layout` = {channel groups, partition shards}; channels
+/// (matrix topology: outputs) and inputs must be multiples of the number of devices. `impulse` takes the impulse responses of the
+/// WHOLE bank ([channels][taps] or [outputs][inputs][taps], host memory) and hands every device its group's rows; `process` takes
+/// whole [inputs][T*B] / [outputs][T*B] host arrays; `submit` + `wait` keep up to three calls in flight (pinned memory recommended).
+template<typename Float, int Kind>
+struct multi_gpu_bank
+{
+    using size_type = std::size_t;
+
+    multi_gpu_bank() = default;
+    multi_gpu_bank(multi_gpu_bank const&)                    = delete;
+    auto operator=(multi_gpu_bank const&) -> multi_gpu_bank& = delete;
+    ~multi_gpu_bank() { neo_b200_bank_destroy(_bank); }
+
+    auto create(std::vector<int> const& devices, neo_b200_bank_layout layout, int topology, size_type outputs, size_type inputs,
+                size_type block, size_type partitions, size_type max_blocks = 1, size_type frame_blocks = 0) -> void
+    {
+        neo_b200_bank_destroy(std::exchange(_bank, nullptr));
+        _cfg              = neo_b200_conv_config{};
+        _cfg.kind         = Kind;
+        _cfg.dtype        = detail::dtype_of<Float>;
+        _cfg.topology     = topology;
+        _cfg.outputs      = outputs;
+        _cfg.inputs       = topology == NEO_B200_DIAGONAL ? outputs : inputs;
+        _cfg.block        = block;
+        _cfg.partitions   = partitions;
+        _cfg.max_blocks   = frame_blocks != 0 ? frame_blocks : max_blocks;
+        _cfg.frame_blocks = frame_blocks;
+        detail::check(neo_b200_bank_create(&_bank, &_cfg, &layout, devices.data(), devices.size()));
+        _ranks.resize(devices.size());
+        for (size_type l = 0; l < _ranks.size(); ++l) { detail::check(neo_b200_bank_local_rank(_bank, l, &_ranks[l])); }
+    }
+
+    /// `convolver.filter(uniform_partition(ir, block))` for every convolver of the bank, partitioned on the devices
+    auto impulse(Float const* ir, size_type taps) -> void
+    {
+        size_type const row = (_cfg.topology == NEO_B200_MATRIX ? _cfg.inputs : 1) * taps;  // reals per output / channel
+        auto ptrs           = std::vector<void const*>(_ranks.size());
+        for (size_type l = 0; l < _ranks.size(); ++l) { ptrs[l] = ir + _ranks[l].group_first * row; }
+        detail::check(neo_b200_bank_set_impulse(_bank, ptrs.data(), taps, NEO_B200_HOST));
+    }
+
+    auto submit(Float const* in, Float* out, size_type blocks) -> void
+    {
+        size_type const pitch = blocks * _cfg.block;
+        auto ins              = std::vector<void const*>(_ranks.size());
+        auto outs             = std::vector<void*>(_ranks.size());
+        for (size_type l = 0; l < _ranks.size(); ++l) {
+            ins[l]  = in + _ranks[l].in_first * pitch;
+            outs[l] = out + _ranks[l].out_first * pitch;
+        }
+        detail::check(neo_b200_bank_submit(_bank, ins.data(), outs.data(), blocks, NEO_B200_HOST));
+    }
+    auto wait() -> void { detail::check(neo_b200_bank_wait(_bank)); }
+    auto process(Float const* in, Float* out, size_type blocks) -> void
+    {
+        submit(in, out, blocks);
+        for (int i = 0; i < 3; ++i) { wait(); }
+    }
+    auto reset() -> void { detail::check(neo_b200_bank_reset(_bank)); }
+
+    [[nodiscard]] auto ranks() const noexcept -> std::vector<neo_b200_bank_rank_info> const& { return _ranks; }
+    [[nodiscard]] auto handle() const noexcept -> neo_b200_bank* { return _bank; }
+
+private:
+    neo_b200_bank* _bank{nullptr};
+    neo_b200_conv_config _cfg{};
+    std::vector<neo_b200_bank_rank_info> _ranks;
+};
+
 /// Drop-in for neo::convolution::fft_convolver<Float> (convolution/fft_convolver.hpp:18-93): `fft_convolver{signal_size, patch_size}`,
 /// `convolver(signal, patch, output)` with output_size() = signal_size + patch_size - 1 (mode::full).
 template<typename Float>

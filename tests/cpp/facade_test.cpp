@@ -345,6 +345,46 @@ static auto test_overlap_add_convolver() -> void
     }
 }
 
+// multi_gpu_bank: the facade over neo_b200_bank_* with every rank on device 0 (or spread over the box's devices), against the oracle
+static auto test_multi_gpu_bank() -> void
+{
+    std::size_t const channels = 8, block = 64, taps = 64 * 12 - 5, T = 4, steps = 5;
+    auto const parts = neo_b200_num_partitions(taps, block);
+    auto ir  = noise<float>(channels * taps, 31);
+    auto sig = noise<float>(channels * T * block * steps, 37);
+    auto want = sig;
+    auto h    = std::vector<std::complex<float>>(channels * parts * (block + 1));
+    neo::b200::uniform_partition(ir.data(), channels, taps, block, h.data());
+    for (std::size_t c = 0; c < channels; ++c) {
+        auto* o = oracle_conv_create_f32(0);
+        oracle_conv_filter_f32(o, reinterpret_cast<float const*>(h.data() + c * parts * (block + 1)), parts, block + 1);
+        // the bank's arrays are [channels][T*block] per call: channel c's samples of call s sit at (s*channels + c)*T*block
+        for (std::size_t s = 0; s < steps; ++s) {
+            for (std::size_t b = 0; b < T; ++b) { oracle_conv_process_f32(o, want.data() + (s * channels + c) * T * block + b * block, block); }
+        }
+        oracle_conv_destroy_f32(o);
+    }
+    int const ndev = neo_b200_device_count();
+    for (auto layout : {neo_b200_bank_layout{2, 2}, neo_b200_bank_layout{1, 4}, neo_b200_bank_layout{4, 1}}) {
+        for (std::size_t frame : {std::size_t(0), T}) {
+            auto devices = std::vector<int>(4);
+            for (int r = 0; r < 4; ++r) { devices[r] = r % ndev; }
+            auto bank = neo::b200::multi_gpu_bank<float, NEO_B200_UPOLS>{};
+            bank.create(devices, layout, NEO_B200_DIAGONAL, channels, channels, block, parts, T, frame);
+            bank.impulse(ir.data(), taps);
+            auto got = std::vector<float>(sig.size());
+            for (std::size_t s = 0; s < steps; ++s) {
+                bank.submit(sig.data() + s * channels * T * block, got.data() + s * channels * T * block, T);
+                if (s >= 2) { bank.wait(); }
+            }
+            bank.wait();
+            bank.wait();
+            bank.wait();
+            REQUIRE(rel_l2(got, want) <= 1e-5);
+        }
+    }
+}
+
 int main()
 {
     if (neo_b200_device_count() < 1) {
@@ -366,6 +406,7 @@ int main()
     test_convolver<float, neo::b200::split_upola_convolver, 1>();
     test_overlap_add_convolver();
     test_sparse_convolver();
+    test_multi_gpu_bank();
     std::printf(failures == 0 ? "facade_test: all passed\n" : "facade_test: %d FAILED\n", failures);
     return failures == 0 ? 0 : 1;
 }

@@ -344,6 +344,71 @@ def test_baseline_config4_full_size_matrix_routing(gpu, orc):
         conv.close()
 
 
+def test_baseline_config4_slice_matches_oracle(gpu, orc):
+    # BASELINE config 4's geometry on a slice the oracle finishes in seconds: 8 outputs x 64 inputs, B=256, 2^16-tap random IRs
+    # (P=256, K=257). Every (o, i) pair is one reference convolver, summed per output (uniform_partitioned_convolver.hpp:48-65,
+    # dense_filter.hpp:31-35): streaming, time-batched direct form and frame mode.
+    O, I, B, L, NB = 8, 64, 256, 1 << 16, 16
+    rng = np.random.default_rng(41)
+    ir = rng.uniform(-1, 1, size=(O, I, L)).astype(np.float32)
+    ir *= np.float32(1.0 / np.sqrt((ir.astype(np.float64) ** 2).sum(axis=2).max()))
+    sig = np.stack([orc.noise(B * NB, 500 + i, np.float32) for i in range(I)])
+    want = np.zeros((O, B * NB), dtype=np.float64)
+    for o in range(O):
+        want[o] = orc.convolve_blocks(0, orc.uniform_partition(ir[o], B), sig).astype(np.float64).sum(axis=0)
+    for frame, T in ((0, 1), (0, 16), (8, 8)):
+        conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.MATRIX, max_blocks=T, frame_blocks=frame)
+        conv.impulse(ir, B)
+        got = np.zeros((O, B * NB), dtype=np.float32)
+        for pos in range(0, NB, T):
+            got[:, pos * B : (pos + T) * B] = conv(np.ascontiguousarray(sig[:, pos * B : (pos + T) * B]))
+        assert rel_l2(got, want) <= 1e-5, (frame, T, rel_l2(got, want))
+        conv.close()
+
+
+def test_upola_grouped_forward_with_several_inverse_ranges(gpu, orc):
+    # the overlap-add tail belongs to a channel, not to a call: a step finished by SEVERAL inverse calls over disjoint channel ranges
+    # (the grouped reduce-scatter shape) must leave every channel's tail right (it used to ping-pong per inverse call)
+    import torch
+
+    C, B, P, T, steps = 6, 64, 5, 3, 6
+    ir, sig = make_case(orc, C, B * P - 4, B, T * steps)
+    H = orc.uniform_partition(ir, B)
+    want = orc.convolve_blocks(gpu.UPOLA, H, sig)
+    conv = gpu.Convolver(gpu.UPOLA, np.float32, gpu.DIAGONAL, max_blocks=T)
+    conv.set_stream(torch.cuda.current_stream())
+    conv.filter(H)
+    got = np.zeros_like(sig)
+    for s in range(steps):
+        x = torch.from_numpy(np.ascontiguousarray(sig[:, s * T * B : (s + 1) * T * B])).cuda()
+        conv.forward_range(x, 0, 2, False)
+        conv.forward_range(x, 2, 4, True)
+        spectra = conv.spectra_tensor(T)
+        y = torch.empty((C, T * B), device="cuda", dtype=torch.float32)
+        for first, count in ((0, 1), (1, 3), (4, 2)):  # three inverse ranges per step, not aligned with the forward groups
+            conv.inverse(spectra[first : first + count].contiguous(), y[first : first + count], first, count, T)
+        torch.cuda.synchronize()
+        got[:, s * T * B : (s + 1) * T * B] = y.cpu().numpy()
+    assert rel_l2(got, want) <= 1e-5, rel_l2(got, want)
+    # the contract of forward_range is enforced: ascending tiling ranges, one block count, final with the last range, no process() inside
+    x = torch.zeros((C, T * B), device="cuda")
+    conv.reset()
+    with pytest.raises(RuntimeError, match="must start at"):
+        conv.forward_range(x, 2, 4, True)
+    conv.forward_range(x, 0, 2, False)
+    with pytest.raises(RuntimeError, match="must start at"):
+        conv.forward_range(x, 0, 2, False)
+    with pytest.raises(RuntimeError, match="final"):
+        conv.forward_range(x, 2, 4, False)
+    with pytest.raises(RuntimeError, match="in progress"):
+        conv(x, out=torch.empty_like(x))
+    with pytest.raises(RuntimeError, match="blocks"):
+        conv.forward_range(torch.zeros((C, B), device="cuda"), 2, 4, True)
+    conv.reset()  # abandons the grouped call
+    conv(x, out=torch.empty_like(x))
+    conv.close()
+
+
 @pytest.mark.parametrize("tag,real", [("f32", np.float32), ("f64", np.float64)])
 def test_fft_convolve_matches_reference_golden_and_oracle(gpu, orc, golden, tag, real):
     # fft_convolver (convolution/fft_convolver.hpp:18-93), mode::full
