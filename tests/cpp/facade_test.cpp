@@ -348,7 +348,7 @@ static auto test_overlap_add_convolver() -> void
 // multi_gpu_bank: the facade over neo_b200_bank_* with every rank on device 0 (or spread over the box's devices), against the oracle
 static auto test_multi_gpu_bank() -> void
 {
-    std::size_t const channels = 8, block = 64, taps = 64 * 12 - 5, T = 4, steps = 5;
+    std::size_t const channels = 8, block = 64, taps = 64 * 16 - 5, T = 4, steps = 5;
     auto const parts = neo_b200_num_partitions(taps, block);
     auto ir  = noise<float>(channels * taps, 31);
     auto sig = noise<float>(channels * T * block * steps, 37);
