@@ -819,7 +819,7 @@ int launch_frame_fused(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, cx<T> 
         constexpr int g16 = LOGL >= 10 ? 3 : 4;  // 16 points per thread: 2^(LOGL-4) threads per bin, <= 512 threads per CTA
         switch (knobs.variant) {
             case 1: return launch_frame_fused_g<T, LOGL, g16 - 1, -1, 128, NYQ>(io, tw, units, stream, a);
-            case 2: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 3 : 4, 3, 64, NYQ, true>(io, tw8, units, stream, a, knobs.pipelined);
+            case 2: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 3 : 4, 3, 64, NYQ>(io, tw8, units, stream, a);
             case 3: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 2 : 3, 3, 64, NYQ>(io, tw8, units, stream, a);
             case 4: return launch_frame_fused_g<T, LOGL, LOGL >= 10 ? 2 : 3, 3, 96, NYQ>(io, tw8, units, stream, a);
             default: return launch_frame_fused_g<T, LOGL, g16, -1, 128, NYQ, true>(io, tw, units, stream, a, knobs.pipelined);
