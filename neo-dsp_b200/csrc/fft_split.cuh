@@ -55,20 +55,26 @@ __global__ void __launch_bounds__(split_cfg<T, LOGM2>::THREADS, fft_min_ctas<T, 
     for (int e = 0; e < cfg::E; ++e) { sm[t + e * cfg::TN] = v[e]; }  // unpadded: unit stride both ways
     __syncthreads();
     C* const row = out + b * (2 * size_t(M2) + 1);
+    // pairs, as in r2c_kernel: bin k = r + 2 k2 (k2 < M2/2: the first half of the thread's points) and its partner M - k = r + 2 p2,
+    // p2 = M2 - r - k2, come from one twiddle product
+    constexpr int M = 2 * M2;
 #pragma unroll
-    for (int e = 0; e < cfg::E; ++e) {
+    for (int e = 0; e < cfg::E / 2; ++e) {
         int const k2 = t + e * cfg::TN;
         int const k  = r + 2 * k2;
         if (k == 0) {
-            row[0]      = mk<T>(v[e].x + v[e].y, T(0));
-            row[2 * M2] = mk<T>(v[e].x - v[e].y, T(0));
+            row[0] = mk<T>(v[e].x + v[e].y, T(0));
+            row[M] = mk<T>(v[e].x - v[e].y, T(0));
         } else {
-            C const zp = sm[(M2 - r - k2) & (M2 - 1)];
-            C w        = __ldg(w_m + k2);  // W_2M^(2 k2)
+            C w = __ldg(w_m + k2);  // W_2M^(2 k2)
             if (r != 0) { w = cmul(w, w_n1); }
-            row[k] = r2c_post(v[e], zp, w);
+            C xk, xmk;
+            r2c_post_pair(v[e], sm[M2 - r - k2], w, xk, xmk);
+            row[k]     = xk;
+            row[M - k] = xmk;
         }
     }
+    if (r == 0 && t == 0) { row[M2] = cconj(v[cfg::E / 2]); }  // the self-paired bin k = M/2 (local index M2/2 of the even bins)
 }
 
 // in: [batch][row_len] complex (first 2*M2+1 used), out: [batch][4*M2] reals, unnormalised.
