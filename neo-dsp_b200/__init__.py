@@ -20,7 +20,8 @@ from typing import Any
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_HERE, "libneo_b200.so")
+# NEO_B200_LIBRARY: another build of the same library (A/B measurements of compile-time choices); never a fallback
+LIBRARY_PATH = os.environ.get("NEO_B200_LIBRARY") or os.path.join(_HERE, "libneo_b200.so")
 
 F32, F64 = 0, 1
 FORWARD, BACKWARD = -1, 1

@@ -52,6 +52,9 @@ constexpr int fft_regcap(int kind, int logm)
     // 2^13 points = 512 threads: 64 registers (no spills, checked with -Xptxas -v) let TWO CTAs share an SM, so one CTA's global
     // loads and barriers hide behind the other's butterflies; at 85 the SM held one CTA and its phases ran back to back
     if (logm == 13) { return 64; }
+    // with the pairwise Hermitian pass the 2^10 .. 2^12-point kernels fit 64 registers without spills too (-Xptxas -v): 16 / 8 / 4
+    // CTAs per SM. Measured against the round-1 caps (72-128) on one box: c2r N=2048 0.93 -> 0.99, N=8192 0.77 -> 0.79, the rest equal
+    if (logm >= 10 && logm <= 12) { return 64; }
     if (kind == k_c2r) { return logm == 10 ? 128 : 85; }
     return logm == 11 ? 72 : 85;
 }
