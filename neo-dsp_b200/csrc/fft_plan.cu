@@ -4,6 +4,7 @@
 #include "fft_kernels.cuh"
 #include "fft_large.cuh"
 #include "fft_split.cuh"
+#include "fft_wide.cuh"
 // two forms of the 65536-point real transform that were measured and lost: compiled only on request
 #ifdef NEO_B200_EXPERIMENTAL_FFT
 #include "fft_cluster.cuh"
@@ -303,6 +304,9 @@ struct rfft_engine
     bool use_split15{false};     // float32, N = 2^16 as two 1024-thread CTAs of 2^14 points each (knob)
     bool use_pair{false};        // float32, N = 2^16: one transform per CTA pair, exchange tile in distributed shared memory (fft_pair.cuh)
     bool use_big_cta{false};     // float32, M = 2^14: one 1024-thread CTA per transform (139 KB exchange tile)
+    bool use_wide{false};        // float32, N = 2^14 / 2^15: 32 points per thread, three stages, Hermitian split in registers (fft_wide.cuh)
+    wide_tables<13, 4, 5> wide13;
+    wide_tables<14, 5, 5> wide14;
     bool use_two_pass{false};    // four-CTA split c2c into an L2-resident scratch + Hermitian split pass
     c2c_engine<T> half;          // two-pass path: the half-size complex transform
     twiddle2<T> w2m;             // two-pass path: exp(-2 pi i k / N)
@@ -317,6 +321,13 @@ struct rfft_engine
         order = order_;
         if (order == 0) { return NEO_B200_OK; }
         int const logm = order - 1;
+        if constexpr (sizeof(T) == 4) {
+            if ((order == 14 || order == 15) && std::getenv("NEO_B200_NO_WIDE") == nullptr) {
+                use_wide = true;
+                NEO_TRY(order == 14 ? wide13.build(stream) : wide14.build(stream));
+                // no return: the 16-points-per-thread path below stays initialised for arrays that are not 16-byte aligned
+            }
+        }
         if constexpr (sizeof(T) == 4) {
             // N = 2^16, measured fractions of HBM peak (r2c / c2r), all parity-tested:
             //   two 1024-thread CTAs of 2^14 points each (fft_split.cuh, no communication)       0.39 / 0.36   <- shipped
@@ -427,6 +438,11 @@ struct rfft_engine
     {
         if (order == 0) { return large_rfft<T>::size_one_forward(in, out, batch, stream); }
         if constexpr (sizeof(T) == 4) {
+            if (use_wide && wide_aligned(in)) {
+                return order == 14 ? launch_r2c_wide(wide13, in, out, batch, stream) : launch_r2c_wide(wide14, in, out, batch, stream);
+            }
+        }
+        if constexpr (sizeof(T) == 4) {
             if (use_split15) { return launch_r2c_split2<T, 14>(in, out, tables.tw(), tables.rtw(), batch, stream); }
 #ifdef NEO_B200_EXPERIMENTAL_FFT
             if (use_pair) { return launch_r2c_pair<15>(in, out, tables.tw(), tables.rtw(), batch, stream); }
@@ -470,6 +486,12 @@ struct rfft_engine
     int backward(cx<T> const* in, size_t row_len, T* out, size_t batch, cudaStream_t stream)
     {
         if (order == 0) { return large_rfft<T>::size_one_backward(in, row_len, out, batch, stream); }
+        if constexpr (sizeof(T) == 4) {
+            if (use_wide && wide_aligned(out)) {
+                return order == 14 ? launch_c2r_wide(wide13, in, row_len, out, batch, stream)
+                                   : launch_c2r_wide(wide14, in, row_len, out, batch, stream);
+            }
+        }
         if constexpr (sizeof(T) == 4) {
             if (use_split15) {
                 return launch_c2r_split2<T, 14>(in, row_len, out, tables.tw(), tables.rtw(), w_n.template as<cx<T>>(), batch, stream);

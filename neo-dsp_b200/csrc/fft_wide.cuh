@@ -1,0 +1,688 @@
+// fft_wide.cuh -- long real transforms (float32, N = 2^14 .. 2^16) with 32 complex points per thread.
+//
+// Same contract as r2c_kernel / c2r_kernel (fallback_rfft_plan.hpp:28-55: half-size complex transform + Hermitian split), different
+// shape. The 16-points-per-thread cta_fft needs 4 shared-memory exchanges for a 2^13-point row (three stages + the Hermitian
+// partner exchange): 64 bytes of shared-memory traffic and ~89 instructions per complex point, which is issue-bound BELOW the HBM
+// roofline. Here a row of M = R1*R2*16 points goes through exactly THREE register stages and TWO exchanges:
+//
+//   forward   n = n' + (M/R1) n1,  n' = a + 16 a2,   k = k1 + R1 k2 + (M/16) k3
+//     S1  butterfly n'      : DFT_R1 over n1, times W_M^(n' k1)               -> tile (k1, a2, a)     [thread: 32/R1 adjacent n']
+//     S2  butterfly (k1, a) : DFT_R2 over a2, times W_(16 R2)^(a k2)          -> tile (k1, k2, a)     [in place: no barrier between
+//                                                                                                      its loads and its stores]
+//     S3  butterfly j = k1 + R1 k2 : DFT_16 over a                            -> Z[j + J k3], J = M/16
+//   A thread owns stage-3 butterflies j and J - j: Z[j + J k3] and its Hermitian partner Z[M - (j + J k3)] = Z[(J - j) + J (15 - k3)]
+//   are then both in ITS registers, so the real-transform split needs no exchange at all (thread 0 owns the two self-paired
+//   butterflies 0 and J/2). The backward transform is the transposed flow (Hermitian pre-pass in registers, S3', S2' in place, S1').
+//
+// Tile: row (k1, x) = 16 complex values = 128 bytes, its eight 16-byte chunks XOR-swizzled by k1 & 7. Every access is conflict-free
+// (tools/wide_fft_model.py replays the index math and the bank pattern): S1 stores / S1' loads are 128-bit and unit stride, S2 moves
+// one row per half-warp, S3 reads its rows with 128-bit loads whose 8 lanes per wavefront hit 8 different chunks.
+// Global side: the real row moves as 128-bit accesses (two adjacent complex points per thread), the spectrum as coalesced 64-bit
+// accesses ascending (k) and descending (M - k).
+#pragma once
+
+#include "fft_kernels.cuh"
+
+#include <type_traits>
+
+namespace neo_b200 {
+
+template<int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f)
+{
+    if constexpr (I < N) {
+        f(std::integral_constant<int, I>{});
+        static_for<I + 1, N>(f);
+    }
+}
+
+// bulk-copy (TMA) plumbing of the prefetching kernels: one mbarrier, one global -> shared bulk copy per row
+namespace wtma {
+__device__ __forceinline__ unsigned saddr(void const* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ void init(void* bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+// the tile was last touched through the generic proxy (LDS / STS); order those accesses before the bulk copy's writes
+__device__ __forceinline__ void fetch(void* dst, void const* src, unsigned bytes, void* bar)
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(saddr(bar)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(saddr(dst)), "l"(src),
+                 "r"(bytes), "r"(saddr(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void wait(void* bar, unsigned parity)
+{
+    asm volatile("{\n"
+                 ".reg .pred p;\n"
+                 "WAIT_%=:\n"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+                 "@!p bra WAIT_%=;\n"
+                 "}\n" ::"r"(saddr(bar)),
+                 "r"(parity)
+                 : "memory");
+}
+}  // namespace wtma
+
+// cos / sin of 2 pi e / 64 as compile-time constants
+__host__ __device__ constexpr double wide_cos64_quarter(int e)
+{
+    constexpr double q[17] = {1.0,
+                              0.9951847266721969,
+                              0.9807852804032304,
+                              0.9569403357322088,
+                              0.9238795325112867,
+                              0.881921264348355,
+                              0.8314696123025452,
+                              0.773010453362737,
+                              0.7071067811865476,
+                              0.6343932841636455,
+                              0.5555702330196023,
+                              0.4713967368259978,
+                              0.38268343236508984,
+                              0.29028467725446233,
+                              0.19509032201612833,
+                              0.09801714032956077,
+                              0.0};
+    return q[e];
+}
+__host__ __device__ constexpr double wide_cos64(int e)
+{
+    e = ((e % 64) + 64) % 64;
+    if (e <= 16) { return wide_cos64_quarter(e); }
+    if (e <= 32) { return -wide_cos64_quarter(32 - e); }
+    if (e <= 48) { return -wide_cos64_quarter(e - 32); }
+    return wide_cos64_quarter(64 - e);
+}
+__host__ __device__ constexpr double wide_sin64(int e) { return wide_cos64(e - 16); }
+
+// multiply by exp(DIR * 2 pi i EXP / 64), EXP known at compile time
+template<int EXP, int DIR>
+__device__ __forceinline__ float2 mul_w64(float2 a)
+{
+    constexpr int e = ((EXP % 64) + 64) % 64;
+    if constexpr (e == 0) {
+        return a;
+    } else if constexpr (e == 16) {
+        return rot90<DIR>(a);
+    } else if constexpr (e == 32) {
+        return make_float2(-a.x, -a.y);
+    } else if constexpr (e == 48) {
+        return rot90<-DIR>(a);
+    } else {
+        constexpr float wr = float(wide_cos64(e));
+        constexpr float wi = float(DIR < 0 ? -wide_sin64(e) : wide_sin64(e));
+        return make_float2(a.x * wr - a.y * wi, a.x * wi + a.y * wr);
+    }
+}
+
+// exp(-2 pi i EXP / 64) as a value
+template<int EXP>
+__device__ __forceinline__ float2 w64_const()
+{
+    return make_float2(float(wide_cos64(EXP)), float(-wide_sin64(EXP)));
+}
+
+// 32-point DFT in registers: 4 x 8 (n = 8 n1 + n2, k = k1 + 4 k2)
+template<int DIR>
+struct dft32
+{
+    static __device__ __forceinline__ void run(float2* u)
+    {
+        float2 a[8][4];
+#pragma unroll
+        for (int n2 = 0; n2 < 8; ++n2) {
+#pragma unroll
+            for (int n1 = 0; n1 < 4; ++n1) { a[n2][n1] = u[8 * n1 + n2]; }
+            dft<4, DIR>::run(a[n2]);
+        }
+        static_for<1, 8>([&](auto n2) {
+            static_for<1, 4>([&](auto k1) {
+                constexpr int N2 = decltype(n2)::value, K1 = decltype(k1)::value;
+                a[N2][K1] = mul_w64<2 * N2 * K1, DIR>(a[N2][K1]);
+            });
+        });
+#pragma unroll
+        for (int k1 = 0; k1 < 4; ++k1) {
+            float2 b[8];
+#pragma unroll
+            for (int n2 = 0; n2 < 8; ++n2) { b[n2] = a[n2][k1]; }
+            dft<8, DIR>::run(b);
+#pragma unroll
+            for (int k2 = 0; k2 < 8; ++k2) { u[k1 + 4 * k2] = b[k2]; }
+        }
+    }
+};
+
+template<int R, int DIR>
+struct wdft
+{
+    static __device__ __forceinline__ void run(float2* u)
+    {
+        if constexpr (R == 32) { dft32<DIR>::run(u); }
+        else { dft<R, DIR>::run(u); }
+    }
+};
+
+template<int LOGM, int LOGR1, int LOGR2>
+struct wide_cfg
+{
+    static_assert(LOGR1 + LOGR2 + 4 == LOGM, "three stages, the last one radix 16");
+    static_assert(LOGR1 >= 3 && LOGR1 <= 5 && LOGR2 >= 3 && LOGR2 <= 5, "radix 8, 16 or 32");
+    static constexpr int M       = 1 << LOGM;
+    static constexpr int R1      = 1 << LOGR1;
+    static constexpr int R2      = 1 << LOGR2;
+    static constexpr int NT      = M / 32;   // threads per transform
+    static constexpr int S1      = M / R1;   // stage-1 butterflies = input stride of n1
+    static constexpr int J       = M / 16;   // stage-3 butterflies
+    static constexpr int BF1     = 32 / R1;  // stage-1 butterflies per thread
+    static constexpr int BF2     = 32 / R2;
+    static constexpr int LOGP    = LOGR1 > 4 ? LOGR1 : 4;  // rows of the power-of-two twiddle table
+    static constexpr int XS      = S1 > J ? S1 : J;        // its row length
+    static constexpr size_t SMEM = size_t(M) * sizeof(float2);
+    static_assert(NT % 32 == 0, "whole warps");
+};
+
+// twiddles w[q] = W^(q x), q < R: the powers of two come from the table (row log2 q, stride xs), the rest are products
+template<int R, class Load>
+__device__ __forceinline__ void wide_twiddles(float2 (&w)[R], Load&& load)
+{
+#pragma unroll
+    for (int q = 1; q < R; ++q) {
+        int const hi = 1 << (31 - __clz(q));
+        if (q == hi) { w[q] = load(31 - __clz(q)); }
+        else { w[q] = cmul(w[hi], w[q - hi]); }
+    }
+}
+
+// Hermitian split of a thread's two stage-3 butterflies (za: butterfly jA, zb: butterfly jB), results straight to the spectrum row.
+// t > 0: jA = t, jB = J - t, Z[t + J k3] pairs with zb[15 - k3], twiddle W_2M^(t + J k3) = W_2M^t * exp(-2 pi i k3 / 32).
+// t = 0: butterflies 0 and J/2 pair within themselves.
+template<int M, class Store>
+__device__ __forceinline__ void wide_r2c_post(float2 const (&za)[16], float2 const (&zb)[16], int t, float2 wt, Store&& store)
+{
+    constexpr int J = M / 16;
+    if (t != 0) {
+        static_for<0, 16>([&](auto k3c) {
+            constexpr int k3 = decltype(k3c)::value;
+            float2 xk, xmk;
+            r2c_post_pair(za[k3], zb[15 - k3], cmul(wt, w64_const<2 * k3>()), xk, xmk);
+            int const k = t + J * k3;
+            store(k, xk);
+            store(M - k, xmk);
+        });
+    } else {
+        store(0, make_float2(za[0].x + za[0].y, 0.0F));
+        store(M, make_float2(za[0].x - za[0].y, 0.0F));
+        store(M / 2, cconj(za[8]));
+        static_for<1, 8>([&](auto k3c) {
+            constexpr int k3 = decltype(k3c)::value;
+            float2 xk, xmk;
+            r2c_post_pair(za[k3], za[16 - k3], w64_const<2 * k3>(), xk, xmk);
+            store(J * k3, xk);
+            store(M - J * k3, xmk);
+        });
+        static_for<0, 8>([&](auto k3c) {
+            constexpr int k3 = decltype(k3c)::value;
+            float2 xk, xmk;
+            r2c_post_pair(zb[k3], zb[15 - k3], w64_const<1 + 2 * k3>(), xk, xmk);
+            store(J / 2 + J * k3, xk);
+            store(M - J / 2 - J * k3, xmk);
+        });
+    }
+}
+
+// the reverse: xa[k3] = X[jA + J k3], xb[k3] = X[jB + J k3] (and Re X[M] for thread 0) -> Z of both butterflies, in place
+template<int M>
+__device__ __forceinline__ void wide_c2r_pre(float2 (&xa)[16], float2 (&xb)[16], int t, float2 wt, float nyq)
+{
+    if (t != 0) {
+        static_for<0, 16>([&](auto k3c) {
+            constexpr int k3 = decltype(k3c)::value;
+            float2 zk, zmk;
+            c2r_pre_pair(xa[k3], xb[15 - k3], cmul(wt, w64_const<2 * k3>()), zk, zmk);
+            xa[k3]      = zk;
+            xb[15 - k3] = zmk;
+        });
+    } else {
+        float const dc = xa[0].x;
+        xa[0]          = make_float2(dc + nyq, dc - nyq);
+        xa[8]          = make_float2(2.0F * xa[8].x, -2.0F * xa[8].y);
+        static_for<1, 8>([&](auto k3c) {
+            constexpr int k3 = decltype(k3c)::value;
+            float2 zk, zmk;
+            c2r_pre_pair(xa[k3], xa[16 - k3], w64_const<2 * k3>(), zk, zmk);
+            xa[k3]      = zk;
+            xa[16 - k3] = zmk;
+        });
+        static_for<0, 8>([&](auto k3c) {
+            constexpr int k3 = decltype(k3c)::value;
+            float2 zk, zmk;
+            c2r_pre_pair(xb[k3], xb[15 - k3], w64_const<1 + 2 * k3>(), zk, zmk);
+            xb[k3]      = zk;
+            xb[15 - k3] = zmk;
+        });
+    }
+}
+
+// ---- the three stages over one CTA's tile. DIR = -1: forward (S1, S2, S3), +1: backward (S3', S2', S1') ----------------------------
+template<int LOGM, int LOGR1, int LOGR2>
+struct wide_fft
+{
+    using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
+    static constexpr int M = cfg::M, R1 = cfg::R1, R2 = cfg::R2, NT = cfg::NT, S1 = cfg::S1, J = cfg::J, BF1 = cfg::BF1, BF2 = cfg::BF2,
+                         XS = cfg::XS;
+
+    // stage 2 / 2': DFT_R2 along x of tile (k1, x, a), in place. tb: forward [R2][16] = W_(16 R2)^(a k2); backward [R1][R2] =
+    // W_(R1 R2)^(a2 k1) (applied conjugated)
+    template<int DIR>
+    static __device__ __forceinline__ void stage2(float2* sm, float2 const* __restrict__ tb, int t)
+    {
+#pragma unroll
+        for (int m = 0; m < BF2; ++m) {
+            int const beta = t + NT * m;
+            int const a = beta & 15, k1 = beta >> 4;
+            float2* const p = sm + k1 * (R2 * 16) + ((((a >> 1) ^ (k1 & 7)) << 1) | (a & 1));
+            float2 u[R2];
+#pragma unroll
+            for (int x = 0; x < R2; ++x) { u[x] = p[x * 16]; }
+            wdft<R2, DIR>::run(u);
+            if constexpr (DIR < 0) {
+#pragma unroll
+                for (int k2 = 1; k2 < R2; ++k2) { u[k2] = cmul(u[k2], __ldg(tb + k2 * 16 + a)); }
+            } else {
+#pragma unroll
+                for (int a2 = 1; a2 < R2; ++a2) { u[a2] = cmulc(u[a2], __ldg(tb + k1 * R2 + a2)); }
+            }
+#pragma unroll
+            for (int x = 0; x < R2; ++x) { p[x * 16] = u[x]; }
+        }
+    }
+
+    // rows of a stage-3 butterfly: 8 chunks of two values
+    static __device__ __forceinline__ int row_chunk0(int j) { return ((j & (R1 - 1)) * R2 + (j >> LOGR1)) * 8; }
+
+    static __device__ __forceinline__ void load_row(float4 const* sm4, int j, float2 (&v)[16])
+    {
+        int const base = row_chunk0(j), key = j & 7;  // k1 & 7 = j & 7 (R1 >= 8)
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float4 const q = sm4[base + (c ^ key)];
+            v[2 * c]       = make_float2(q.x, q.y);
+            v[2 * c + 1]   = make_float2(q.z, q.w);
+        }
+    }
+
+    static __device__ __forceinline__ void store_row(float4* sm4, int j, float2 const (&v)[16])
+    {
+        int const base = row_chunk0(j), key = j & 7;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) { sm4[base + (c ^ key)] = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y); }
+    }
+};
+
+// in: [batch][2M] reals (16-byte aligned), out: [batch][M+1] complex. ta: [LOGP][XS] W_M^(2^p x); tb: [R2][16]; rtw: W_2M^k, k < J/2
+// PF: persistent CTAs; the NEXT row travels into the tile by one bulk copy (TMA) while this row's stage 3, Hermitian split and stores
+// run -- the tile is idle from the stage-3 loads on -- so stage 1 reads its inputs from shared memory and no warp waits on DRAM.
+template<int LOGM, int LOGR1, int LOGR2, int MINCTAS, bool PF>
+__global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
+    r2c_wide_kernel(float const* __restrict__ in, float2* __restrict__ out, float2 const* __restrict__ ta, float2 const* __restrict__ tb,
+                    float2 const* __restrict__ rtw, size_t batch)
+{
+    using W   = wide_fft<LOGM, LOGR1, LOGR2>;
+    using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
+    constexpr int M = cfg::M, R1 = cfg::R1, R2 = cfg::R2, NT = cfg::NT, S1 = cfg::S1, J = cfg::J, BF1 = cfg::BF1, XS = cfg::XS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* const sm  = reinterpret_cast<float2*>(smem_raw);
+    float4* const sm4 = reinterpret_cast<float4*>(smem_raw);
+    int const t       = threadIdx.x;
+    __shared__ __align__(8) unsigned long long bar;
+    unsigned parity = 0;
+    if constexpr (PF) {
+        static_assert(!PF || BF1 == 2 || BF1 == 1, "one pass over the staged row");
+        if (t == 0) {
+            wtma::init(&bar);
+            if (blockIdx.x < batch) { wtma::fetch(sm, in + size_t(blockIdx.x) * (2 * size_t(M)), unsigned(cfg::SMEM), &bar); }
+        }
+        __syncthreads();
+    }
+    float2 const wt = __ldg(rtw + t);
+
+    for (size_t b = blockIdx.x; b < batch; b += gridDim.x) {
+        // ---- stage 1
+        if constexpr (BF1 >= 2) {
+#pragma unroll
+            for (int m = 0; m < BF1 / 2; ++m) {
+                int const n = 2 * t + 2 * NT * m;  // this thread's butterflies n and n + 1
+                float2 ua[R1], ub[R1];
+                if constexpr (PF) {
+                    wtma::wait(&bar, parity);
+                    parity ^= 1U;
+#pragma unroll
+                    for (int n1 = 0; n1 < R1; ++n1) {
+                        float4 const q = sm4[(n >> 1) + n1 * (S1 / 2)];
+                        ua[n1]         = make_float2(q.x, q.y);
+                        ub[n1]         = make_float2(q.z, q.w);
+                    }
+                    __syncthreads();  // every thread has its inputs: the tile may be overwritten
+                } else {
+                    float4 const* const src = reinterpret_cast<float4 const*>(in + b * (2 * size_t(M))) + (n >> 1);
+#pragma unroll
+                    for (int n1 = 0; n1 < R1; ++n1) {
+                        float4 const q = __ldcs(src + n1 * (S1 / 2));
+                        ua[n1]         = make_float2(q.x, q.y);
+                        ub[n1]         = make_float2(q.z, q.w);
+                    }
+                }
+                wdft<R1, -1>::run(ua);
+                wdft<R1, -1>::run(ub);
+                {
+                    float4 const* const ta4 = reinterpret_cast<float4 const*>(ta) + (n >> 1);
+                    float2 wa[R1], wb[R1];
+#pragma unroll
+                    for (int q = 1; q < R1; ++q) {
+                        int const hi = 1 << (31 - __clz(q));
+                        if (q == hi) {
+                            float4 const w4 = __ldg(ta4 + (31 - __clz(q)) * (XS / 2));
+                            wa[q]           = make_float2(w4.x, w4.y);
+                            wb[q]           = make_float2(w4.z, w4.w);
+                        } else {
+                            wa[q] = cmul(wa[hi], wa[q - hi]);
+                            wb[q] = cmul(wb[hi], wb[q - hi]);
+                        }
+                        ua[q] = cmul(ua[q], wa[q]);
+                        ub[q] = cmul(ub[q], wb[q]);
+                    }
+                }
+                int const a2 = n >> 4, ah = (n & 15) >> 1;
+#pragma unroll
+                for (int k1 = 0; k1 < R1; ++k1) {
+                    sm4[(k1 * R2 + a2) * 8 + (ah ^ (k1 & 7))] = make_float4(ua[k1].x, ua[k1].y, ub[k1].x, ub[k1].y);
+                }
+            }
+        } else {
+            int const n = t;
+            float2 u[R1];
+            if constexpr (PF) {
+                wtma::wait(&bar, parity);
+                parity ^= 1U;
+#pragma unroll
+                for (int n1 = 0; n1 < R1; ++n1) { u[n1] = sm[n + n1 * S1]; }
+                __syncthreads();
+            } else {
+                float2 const* const src = reinterpret_cast<float2 const*>(in + b * (2 * size_t(M))) + n;
+#pragma unroll
+                for (int n1 = 0; n1 < R1; ++n1) { u[n1] = __ldcs(src + n1 * S1); }
+            }
+            wdft<R1, -1>::run(u);
+            {
+                float2 w[R1];
+#pragma unroll
+                for (int q = 1; q < R1; ++q) {
+                    int const hi = 1 << (31 - __clz(q));
+                    if (q == hi) { w[q] = __ldg(ta + (31 - __clz(q)) * XS + n); }
+                    else { w[q] = cmul(w[hi], w[q - hi]); }
+                    u[q] = cmul(u[q], w[q]);
+                }
+            }
+            int const a = n & 15, a2 = n >> 4;
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1) { sm[(k1 * R2 + a2) * 16 + ((((a >> 1) ^ (k1 & 7)) << 1) | (a & 1))] = u[k1]; }
+        }
+        __syncthreads();
+        // ---- stage 2, in place
+        W::template stage2<-1>(sm, tb, t);
+        __syncthreads();
+        // ---- stage 3 + Hermitian split in registers
+        {
+            int const ja = t, jb = t == 0 ? J / 2 : J - t;
+            float2 za[16], zb[16];
+            W::load_row(sm4, ja, za);
+            W::load_row(sm4, jb, zb);
+            __syncthreads();  // the tile is free for the next row's stage 1
+            if constexpr (PF) {
+                if (t == 0 && b + gridDim.x < batch) { wtma::fetch(sm, in + (b + gridDim.x) * (2 * size_t(M)), unsigned(cfg::SMEM), &bar); }
+            }
+            dft<16, -1>::run(za);
+            dft<16, -1>::run(zb);
+            float2* const row = out + b * (size_t(M) + 1);
+            wide_r2c_post<M>(za, zb, t, wt, [&](int k, float2 x) { row[k] = x; });
+        }
+    }
+}
+
+// in: [batch][row_len] complex (first M+1 used), out: [batch][2M] reals (16-byte aligned), unnormalised. tb: [R1][R2]
+// PF: as in r2c_wide_kernel. A spectrum row of M+1 bins starts on an 8-byte boundary only, so the bulk copy takes the M bins from
+// the row's first 16-byte boundary on (bins lo .. lo+M-1, lo = 0 or 1) and thread 0 fetches the one bin left out (X[M] or X[0]).
+template<int LOGM, int LOGR1, int LOGR2, int MINCTAS, bool PF>
+__global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
+    c2r_wide_kernel(float2 const* __restrict__ in, size_t row_len, float* __restrict__ out, float2 const* __restrict__ ta,
+                    float2 const* __restrict__ tb, float2 const* __restrict__ rtw, size_t batch)
+{
+    using W   = wide_fft<LOGM, LOGR1, LOGR2>;
+    using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
+    constexpr int M = cfg::M, R1 = cfg::R1, R2 = cfg::R2, NT = cfg::NT, S1 = cfg::S1, J = cfg::J, BF1 = cfg::BF1, XS = cfg::XS;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* const sm  = reinterpret_cast<float2*>(smem_raw);
+    float4* const sm4 = reinterpret_cast<float4*>(smem_raw);
+    int const t       = threadIdx.x;
+    __shared__ __align__(8) unsigned long long bar;
+    unsigned parity = 0;
+    auto const misaligned = [&](size_t row) { return int((reinterpret_cast<std::uintptr_t>(in + row * row_len) >> 3) & 1U); };
+    if constexpr (PF) {
+        if (t == 0) {
+            wtma::init(&bar);
+            if (blockIdx.x < batch) {
+                wtma::fetch(sm, in + size_t(blockIdx.x) * row_len + misaligned(blockIdx.x), unsigned(cfg::SMEM), &bar);
+            }
+        }
+        __syncthreads();
+    }
+    float2 const wt = __ldg(rtw + t);
+
+    for (size_t b = blockIdx.x; b < batch; b += gridDim.x) {
+        // ---- Hermitian pre-pass in registers + stage 3'
+        {
+            float2 const* const x = in + b * row_len;
+            int const ja = t, jb = t == 0 ? J / 2 : J - t;
+            float2 za[16], zb[16];
+            float nyq = 0.0F;
+            if constexpr (PF) {
+                int const lo = misaligned(b);
+                float2 edge  = make_float2(0.0F, 0.0F);
+                if (t == 0) { edge = x[lo ? 0 : M]; }
+                wtma::wait(&bar, parity);
+                parity ^= 1U;
+                float2 const* const s = sm - lo;  // bin k sits at s[k], lo <= k < lo + M
+#pragma unroll
+                for (int k3 = 0; k3 < 16; ++k3) { za[k3] = (k3 == 0 && t == 0) ? sm[0] : s[ja + J * k3]; }
+#pragma unroll
+                for (int k3 = 0; k3 < 16; ++k3) { zb[k3] = s[jb + J * k3]; }
+                if (t == 0) {
+                    nyq = lo ? sm[M - 1].x : edge.x;
+                    if (lo) { za[0] = edge; }
+                }
+                __syncthreads();  // every thread has its inputs: the tile may be overwritten
+            } else {
+#pragma unroll
+                for (int k3 = 0; k3 < 16; ++k3) { za[k3] = __ldcs(x + ja + J * k3); }
+#pragma unroll
+                for (int k3 = 0; k3 < 16; ++k3) { zb[k3] = __ldcs(x + jb + J * k3); }
+                nyq = t == 0 ? x[M].x : 0.0F;
+            }
+            wide_c2r_pre<M>(za, zb, t, wt, nyq);
+            dft<16, +1>::run(za);
+            dft<16, +1>::run(zb);
+            {
+                float2 w[16];
+                wide_twiddles(w, [&](int p) { return __ldg(ta + p * XS + ja); });
+#pragma unroll
+                for (int a = 1; a < 16; ++a) { za[a] = cmulc(za[a], w[a]); }
+                wide_twiddles(w, [&](int p) { return __ldg(ta + p * XS + jb); });
+#pragma unroll
+                for (int a = 1; a < 16; ++a) { zb[a] = cmulc(zb[a], w[a]); }
+            }
+            W::store_row(sm4, ja, za);
+            W::store_row(sm4, jb, zb);
+        }
+        __syncthreads();
+        // ---- stage 2', in place
+        W::template stage2<+1>(sm, tb, t);
+        __syncthreads();
+        // ---- stage 1'
+        if constexpr (BF1 >= 2) {
+#pragma unroll
+            for (int m = 0; m < BF1 / 2; ++m) {
+                int const n  = 2 * t + 2 * NT * m;
+                int const a2 = n >> 4, ah = (n & 15) >> 1;
+                float2 ua[R1], ub[R1];
+#pragma unroll
+                for (int k1 = 0; k1 < R1; ++k1) {
+                    float4 const q = sm4[(k1 * R2 + a2) * 8 + (ah ^ (k1 & 7))];
+                    ua[k1]         = make_float2(q.x, q.y);
+                    ub[k1]         = make_float2(q.z, q.w);
+                }
+                if (m == BF1 / 2 - 1) {
+                    __syncthreads();  // the tile is free for the next row
+                    if constexpr (PF) {
+                        if (t == 0 && b + gridDim.x < batch) {
+                            wtma::fetch(sm, in + (b + gridDim.x) * row_len + misaligned(b + gridDim.x), unsigned(cfg::SMEM), &bar);
+                        }
+                    }
+                }
+                wdft<R1, +1>::run(ua);
+                wdft<R1, +1>::run(ub);
+                float4* const dst = reinterpret_cast<float4*>(out + b * (2 * size_t(M))) + (n >> 1);
+#pragma unroll
+                for (int b2 = 0; b2 < R1; ++b2) { __stcs(dst + b2 * (S1 / 2), make_float4(ua[b2].x, ua[b2].y, ub[b2].x, ub[b2].y)); }
+            }
+        } else {
+            int const n = t, a = n & 15, a2 = n >> 4;
+            float2 u[R1];
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1) { u[k1] = sm[(k1 * R2 + a2) * 16 + ((((a >> 1) ^ (k1 & 7)) << 1) | (a & 1))]; }
+            __syncthreads();
+            if constexpr (PF) {
+                if (t == 0 && b + gridDim.x < batch) {
+                    wtma::fetch(sm, in + (b + gridDim.x) * row_len + misaligned(b + gridDim.x), unsigned(cfg::SMEM), &bar);
+                }
+            }
+            wdft<R1, +1>::run(u);
+            float2* const dst = reinterpret_cast<float2*>(out + b * (2 * size_t(M))) + n;
+#pragma unroll
+            for (int b2 = 0; b2 < R1; ++b2) { __stcs(dst + b2 * S1, u[b2]); }
+        }
+    }
+}
+
+// ---- tables + launchers --------------------------------------------------------------------------------------------------------------
+template<int LOGM, int LOGR1, int LOGR2>
+struct wide_tables
+{
+    using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
+    device_buffer ta, tb_fwd, tb_bwd, rtw;
+
+    int build(cudaStream_t stream)
+    {
+        constexpr double pi = 3.14159265358979323846264338327950288;
+        constexpr int M = cfg::M, R1 = cfg::R1, R2 = cfg::R2, J = cfg::J, XS = cfg::XS, LOGP = cfg::LOGP;
+        std::vector<float2> a(size_t(LOGP) * XS), f(size_t(R2) * 16), g(size_t(R1) * R2), r(J / 2 + 1);
+        for (int p = 0; p < LOGP; ++p) {
+            for (int x = 0; x < XS; ++x) {
+                // exponent reduced mod M in integers before the angle is formed
+                long const e   = (long(x) << p) & (M - 1);
+                double const v = -2.0 * pi * double(e) / double(M);
+                a[size_t(p) * XS + x] = make_float2(float(std::cos(v)), float(std::sin(v)));
+            }
+        }
+        for (int k2 = 0; k2 < R2; ++k2) {
+            for (int x = 0; x < 16; ++x) {
+                double const v   = -2.0 * pi * double(x * k2) / double(16 * R2);
+                f[k2 * 16 + x] = make_float2(float(std::cos(v)), float(std::sin(v)));
+            }
+        }
+        for (int k1 = 0; k1 < R1; ++k1) {
+            for (int a2 = 0; a2 < R2; ++a2) {
+                double const v    = -2.0 * pi * double(k1 * a2) / double(R1 * R2);
+                g[k1 * R2 + a2] = make_float2(float(std::cos(v)), float(std::sin(v)));
+            }
+        }
+        for (int k = 0; k <= J / 2; ++k) {
+            double const v = -pi * double(k) / double(M);
+            r[k]           = make_float2(float(std::cos(v)), float(std::sin(v)));
+        }
+        auto upload = [&](device_buffer& dst, std::vector<float2> const& src) -> int {
+            NEO_TRY(dst.reserve(src.size() * sizeof(float2)));
+            NEO_CUDA_TRY(cudaMemcpyAsync(dst.ptr, src.data(), src.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
+            return NEO_B200_OK;
+        };
+        NEO_TRY(upload(ta, a));
+        NEO_TRY(upload(tb_fwd, f));
+        NEO_TRY(upload(tb_bwd, g));
+        NEO_TRY(upload(rtw, r));
+        NEO_CUDA_TRY(cudaStreamSynchronize(stream));  // host vectors die here
+        return NEO_B200_OK;
+    }
+};
+
+inline bool wide_aligned(void const* p) { return (reinterpret_cast<std::uintptr_t>(p) & 15U) == 0; }
+
+// resident CTAs per SM at 128 registers per thread
+template<int LOGM, int LOGR1, int LOGR2>
+constexpr int wide_min_ctas()
+{
+    int const by_regs = 512 / wide_cfg<LOGM, LOGR1, LOGR2>::NT;
+    int const by_smem = int((227 * 1024) / (wide_cfg<LOGM, LOGR1, LOGR2>::SMEM + 2048));
+    int const n       = by_regs < by_smem ? by_regs : by_smem;
+    return n > 0 ? n : 1;
+}
+
+// NEO_B200_WIDE_NO_PREFETCH: one CTA per row with plain global loads instead of persistent CTAs fed by bulk copies (A/B knob)
+inline bool wide_prefetch()
+{
+    static bool const on = std::getenv("NEO_B200_WIDE_NO_PREFETCH") == nullptr;
+    return on;
+}
+
+inline unsigned wide_grid(size_t batch, int ctas_per_sm, bool persist)
+{
+    if (!persist) { return unsigned(batch); }
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return unsigned(std::min<size_t>(batch, size_t(sms) * ctas_per_sm));
+}
+
+template<int LOGM, int LOGR1, int LOGR2>
+int launch_r2c_wide(wide_tables<LOGM, LOGR1, LOGR2> const& tb, float const* in, float2* out, size_t batch, cudaStream_t stream)
+{
+    using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
+    if (batch == 0) { return NEO_B200_OK; }
+    constexpr int ctas = wide_min_ctas<LOGM, LOGR1, LOGR2>();
+    bool const pf      = wide_prefetch();
+    auto kernel        = pf ? r2c_wide_kernel<LOGM, LOGR1, LOGR2, ctas, true> : r2c_wide_kernel<LOGM, LOGR1, LOGR2, ctas, false>;
+    NEO_TRY(enable_smem(kernel, cfg::SMEM));
+    kernel<<<wide_grid(batch, ctas, pf), cfg::NT, cfg::SMEM, stream>>>(in, out, tb.ta.template as<float2>(), tb.tb_fwd.template as<float2>(),
+                                                                       tb.rtw.template as<float2>(), batch);
+    return check_launch("r2c_wide_kernel");
+}
+
+template<int LOGM, int LOGR1, int LOGR2>
+int launch_c2r_wide(wide_tables<LOGM, LOGR1, LOGR2> const& tb, float2 const* in, size_t row_len, float* out, size_t batch,
+                    cudaStream_t stream)
+{
+    using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
+    if (batch == 0) { return NEO_B200_OK; }
+    constexpr int ctas = wide_min_ctas<LOGM, LOGR1, LOGR2>();
+    // the bulk copy wants the first 16-byte boundary of every row inside it and 8-byte aligned rows
+    bool const pf = wide_prefetch() && (reinterpret_cast<std::uintptr_t>(in) & 7U) == 0;
+    auto kernel   = pf ? c2r_wide_kernel<LOGM, LOGR1, LOGR2, ctas, true> : c2r_wide_kernel<LOGM, LOGR1, LOGR2, ctas, false>;
+    NEO_TRY(enable_smem(kernel, cfg::SMEM));
+    kernel<<<wide_grid(batch, ctas, pf), cfg::NT, cfg::SMEM, stream>>>(in, row_len, out, tb.ta.template as<float2>(),
+                                                                       tb.tb_bwd.template as<float2>(), tb.rtw.template as<float2>(), batch);
+    return check_launch("c2r_wide_kernel");
+}
+
+}  // namespace neo_b200
