@@ -39,9 +39,9 @@ __device__ __forceinline__ void static_for(F&& f)
 // bulk-copy (TMA) plumbing of the prefetching kernels: one mbarrier, one global -> shared bulk copy per row
 namespace wtma {
 __device__ __forceinline__ unsigned saddr(void const* p) { return static_cast<unsigned>(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ void init(void* bar)
+__device__ __forceinline__ void init(void* bar, unsigned arrivals)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(saddr(bar)) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(saddr(bar)), "r"(arrivals) : "memory");
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
 // the tile was last touched through the generic proxy (LDS / STS); order those accesses before the bulk copy's writes
@@ -181,7 +181,8 @@ struct wide_cfg
     static constexpr int BF2     = 32 / R2;
     static constexpr int LOGP    = LOGR1 > 4 ? LOGR1 : 4;  // rows of the power-of-two twiddle table
     static constexpr int XS      = S1 > J ? S1 : J;        // its row length
-    static constexpr size_t SMEM = size_t(M) * sizeof(float2);
+    static constexpr size_t SMEM    = size_t(M) * sizeof(float2);              // the tile
+    static constexpr size_t SMEM_PF = SMEM + size_t(3 * M / 4) * sizeof(float2);  // + the staging buffer of the prefetching kernels
     static_assert(NT % 32 == 0, "whole warps");
 };
 
@@ -324,8 +325,28 @@ struct wide_fft
 };
 
 // in: [batch][2M] reals (16-byte aligned), out: [batch][M+1] complex. ta: [LOGP][XS] W_M^(2^p x); tb: [R2][16]; rtw: W_2M^k, k < J/2
-// PF: persistent CTAs; the NEXT row travels into the tile by one bulk copy (TMA) while this row's stage 3, Hermitian split and stores
-// run -- the tile is idle from the stage-3 loads on -- so stage 1 reads its inputs from shared memory and no warp waits on DRAM.
+// PF: persistent CTAs, and no warp ever waits on DRAM: the NEXT row travels into shared memory by bulk copies (TMA) while this row is
+// transformed. Its first three quarters go into a staging buffer behind the tile as soon as stage 1 has taken this row's inputs
+// (a whole row time ahead: at the SM's fair share of the HBM bandwidth a row needs about that long); the last quarter goes into the
+// tile itself, which is idle from the stage-3 loads on. Both copies signal one mbarrier (two arrivals per phase).
+template<int M>
+struct wide_stage
+{
+    static constexpr int ST = 3 * M / 4;  // complex elements of a row kept in the staging buffer; the rest sits at the tile's start
+    static constexpr unsigned EARLY = unsigned(ST) * 8U, LATE = unsigned(M - ST) * 8U;
+    float2* tile;
+    float2* stage;
+    __device__ __forceinline__ void fetch_early(float2 const* row, void* bar) const { wtma::fetch(stage, row, EARLY, bar); }
+    __device__ __forceinline__ void fetch_late(float2 const* row, void* bar) const { wtma::fetch(tile, row + ST, LATE, bar); }
+    // element e of the staged row; REGION known at compile time wherever the caller's index is
+    template<bool IN_TILE>
+    __device__ __forceinline__ float2 const* at(int e) const
+    {
+        return IN_TILE ? tile + (e - ST) : stage + e;
+    }
+    __device__ __forceinline__ float2 get(int e) const { return e < ST ? stage[e] : tile[e - ST]; }
+};
+
 template<int LOGM, int LOGR1, int LOGR2, int MINCTAS, bool PF>
 __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
     r2c_wide_kernel(float const* __restrict__ in, float2* __restrict__ out, float2 const* __restrict__ ta, float2 const* __restrict__ tb,
@@ -340,17 +361,23 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
     int const t       = threadIdx.x;
     __shared__ __align__(8) unsigned long long bar;
     unsigned parity = 0;
+    wide_stage<M> const st{sm, sm + M};
+    auto const zrow = [&](size_t row) { return reinterpret_cast<float2 const*>(in) + row * size_t(M); };
     if constexpr (PF) {
         static_assert(!PF || BF1 == 2 || BF1 == 1, "one pass over the staged row");
+        static_assert((3 * R1) % 4 == 0, "the staging boundary falls between two stage-1 inputs");
         if (t == 0) {
-            wtma::init(&bar);
-            if (blockIdx.x < batch) { wtma::fetch(sm, in + size_t(blockIdx.x) * (2 * size_t(M)), unsigned(cfg::SMEM), &bar); }
+            wtma::init(&bar, 2);
+            if (blockIdx.x < batch) {
+                st.fetch_early(zrow(blockIdx.x), &bar);
+                st.fetch_late(zrow(blockIdx.x), &bar);
+            }
         }
         __syncthreads();
     }
-    float2 const wt = __ldg(rtw + t);
 
     for (size_t b = blockIdx.x; b < batch; b += gridDim.x) {
+        bool const more = b + gridDim.x < batch;
         // ---- stage 1
         if constexpr (BF1 >= 2) {
 #pragma unroll
@@ -360,13 +387,14 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
                 if constexpr (PF) {
                     wtma::wait(&bar, parity);
                     parity ^= 1U;
-#pragma unroll
-                    for (int n1 = 0; n1 < R1; ++n1) {
-                        float4 const q = sm4[(n >> 1) + n1 * (S1 / 2)];
+                    static_for<0, R1>([&](auto n1c) {
+                        constexpr int n1 = decltype(n1c)::value;
+                        float4 const q = *reinterpret_cast<float4 const*>(st.template at<(n1 * S1 >= wide_stage<M>::ST)>(n + n1 * S1));
                         ua[n1]         = make_float2(q.x, q.y);
                         ub[n1]         = make_float2(q.z, q.w);
-                    }
-                    __syncthreads();  // every thread has its inputs: the tile may be overwritten
+                    });
+                    __syncthreads();  // every thread has its inputs: staging buffer and tile may be overwritten
+                    if (t == 0 && more) { st.fetch_early(zrow(b + gridDim.x), &bar); }
                 } else {
                     float4 const* const src = reinterpret_cast<float4 const*>(in + b * (2 * size_t(M))) + (n >> 1);
 #pragma unroll
@@ -408,9 +436,12 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
             if constexpr (PF) {
                 wtma::wait(&bar, parity);
                 parity ^= 1U;
-#pragma unroll
-                for (int n1 = 0; n1 < R1; ++n1) { u[n1] = sm[n + n1 * S1]; }
+                static_for<0, R1>([&](auto n1c) {
+                    constexpr int n1 = decltype(n1c)::value;
+                    u[n1]            = *st.template at<(n1 * S1 >= wide_stage<M>::ST)>(n + n1 * S1);
+                });
                 __syncthreads();
+                if (t == 0 && more) { st.fetch_early(zrow(b + gridDim.x), &bar); }
             } else {
                 float2 const* const src = reinterpret_cast<float2 const*>(in + b * (2 * size_t(M))) + n;
 #pragma unroll
@@ -438,12 +469,13 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
         // ---- stage 3 + Hermitian split in registers
         {
             int const ja = t, jb = t == 0 ? J / 2 : J - t;
+            float2 const wt = __ldg(rtw + t);
             float2 za[16], zb[16];
             W::load_row(sm4, ja, za);
             W::load_row(sm4, jb, zb);
-            __syncthreads();  // the tile is free for the next row's stage 1
+            __syncthreads();  // the tile is free for the next row
             if constexpr (PF) {
-                if (t == 0 && b + gridDim.x < batch) { wtma::fetch(sm, in + (b + gridDim.x) * (2 * size_t(M)), unsigned(cfg::SMEM), &bar); }
+                if (t == 0 && more) { st.fetch_late(zrow(b + gridDim.x), &bar); }
             }
             dft<16, -1>::run(za);
             dft<16, -1>::run(zb);
@@ -454,7 +486,7 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
 }
 
 // in: [batch][row_len] complex (first M+1 used), out: [batch][2M] reals (16-byte aligned), unnormalised. tb: [R1][R2]
-// PF: as in r2c_wide_kernel. A spectrum row of M+1 bins starts on an 8-byte boundary only, so the bulk copy takes the M bins from
+// PF: as in r2c_wide_kernel. A spectrum row of M+1 bins starts on an 8-byte boundary only, so the bulk copies take the M bins from
 // the row's first 16-byte boundary on (bins lo .. lo+M-1, lo = 0 or 1) and thread 0 fetches the one bin left out (X[M] or X[0]).
 template<int LOGM, int LOGR1, int LOGR2, int MINCTAS, bool PF>
 __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
@@ -470,41 +502,56 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
     int const t       = threadIdx.x;
     __shared__ __align__(8) unsigned long long bar;
     unsigned parity = 0;
-    auto const misaligned = [&](size_t row) { return int((reinterpret_cast<std::uintptr_t>(in + row * row_len) >> 3) & 1U); };
+    wide_stage<M> const st{sm, sm + M};
+    // first bin of row `row` that sits on a 16-byte boundary
+    auto const xrow = [&](size_t row) {
+        float2 const* const x = in + row * row_len;
+        return x + ((reinterpret_cast<std::uintptr_t>(x) >> 3) & 1U);
+    };
     if constexpr (PF) {
         if (t == 0) {
-            wtma::init(&bar);
+            wtma::init(&bar, 2);
             if (blockIdx.x < batch) {
-                wtma::fetch(sm, in + size_t(blockIdx.x) * row_len + misaligned(blockIdx.x), unsigned(cfg::SMEM), &bar);
+                st.fetch_early(xrow(blockIdx.x), &bar);
+                st.fetch_late(xrow(blockIdx.x), &bar);
             }
         }
         __syncthreads();
     }
-    float2 const wt = __ldg(rtw + t);
 
     for (size_t b = blockIdx.x; b < batch; b += gridDim.x) {
+        bool const more = b + gridDim.x < batch;
         // ---- Hermitian pre-pass in registers + stage 3'
         {
             float2 const* const x = in + b * row_len;
             int const ja = t, jb = t == 0 ? J / 2 : J - t;
+            float2 const wt = __ldg(rtw + t);
             float2 za[16], zb[16];
             float nyq = 0.0F;
             if constexpr (PF) {
-                int const lo = misaligned(b);
+                int const lo = int(xrow(b) - x);
                 float2 edge  = make_float2(0.0F, 0.0F);
                 if (t == 0) { edge = x[lo ? 0 : M]; }
                 wtma::wait(&bar, parity);
                 parity ^= 1U;
-                float2 const* const s = sm - lo;  // bin k sits at s[k], lo <= k < lo + M
+                // bin k sits at staged element k - lo. For t > 0 both ja + J k3 - lo and jb + J k3 - lo stay inside [J k3, J (k3 + 1)),
+                // so the region follows from k3 alone (the staging boundary 3M/4 = 12 J)
+                if (t != 0) {
+                    static_for<0, 16>([&](auto k3c) {
+                        constexpr int k3 = decltype(k3c)::value;
+                        za[k3]           = *st.template at<(k3 >= 12)>(ja + J * k3 - lo);
+                        zb[k3]           = *st.template at<(k3 >= 12)>(jb + J * k3 - lo);
+                    });
+                } else {
 #pragma unroll
-                for (int k3 = 0; k3 < 16; ++k3) { za[k3] = (k3 == 0 && t == 0) ? sm[0] : s[ja + J * k3]; }
+                    for (int k3 = 1; k3 < 16; ++k3) { za[k3] = st.get(J * k3 - lo); }
 #pragma unroll
-                for (int k3 = 0; k3 < 16; ++k3) { zb[k3] = s[jb + J * k3]; }
-                if (t == 0) {
-                    nyq = lo ? sm[M - 1].x : edge.x;
-                    if (lo) { za[0] = edge; }
+                    for (int k3 = 0; k3 < 16; ++k3) { zb[k3] = st.get(J / 2 + J * k3 - lo); }
+                    za[0] = lo ? edge : st.get(0);
+                    nyq   = lo ? st.get(M - 1).x : edge.x;
                 }
-                __syncthreads();  // every thread has its inputs: the tile may be overwritten
+                __syncthreads();  // every thread has its inputs: staging buffer and tile may be overwritten
+                if (t == 0 && more) { st.fetch_early(xrow(b + gridDim.x), &bar); }
             } else {
 #pragma unroll
                 for (int k3 = 0; k3 < 16; ++k3) { za[k3] = __ldcs(x + ja + J * k3); }
@@ -547,9 +594,7 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
                 if (m == BF1 / 2 - 1) {
                     __syncthreads();  // the tile is free for the next row
                     if constexpr (PF) {
-                        if (t == 0 && b + gridDim.x < batch) {
-                            wtma::fetch(sm, in + (b + gridDim.x) * row_len + misaligned(b + gridDim.x), unsigned(cfg::SMEM), &bar);
-                        }
+                        if (t == 0 && more) { st.fetch_late(xrow(b + gridDim.x), &bar); }
                     }
                 }
                 wdft<R1, +1>::run(ua);
@@ -565,9 +610,7 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
             for (int k1 = 0; k1 < R1; ++k1) { u[k1] = sm[(k1 * R2 + a2) * 16 + ((((a >> 1) ^ (k1 & 7)) << 1) | (a & 1))]; }
             __syncthreads();
             if constexpr (PF) {
-                if (t == 0 && b + gridDim.x < batch) {
-                    wtma::fetch(sm, in + (b + gridDim.x) * row_len + misaligned(b + gridDim.x), unsigned(cfg::SMEM), &bar);
-                }
+                if (t == 0 && more) { st.fetch_late(xrow(b + gridDim.x), &bar); }
             }
             wdft<R1, +1>::run(u);
             float2* const dst = reinterpret_cast<float2*>(out + b * (2 * size_t(M))) + n;
@@ -634,7 +677,7 @@ template<int LOGM, int LOGR1, int LOGR2>
 constexpr int wide_min_ctas()
 {
     int const by_regs = 512 / wide_cfg<LOGM, LOGR1, LOGR2>::NT;
-    int const by_smem = int((227 * 1024) / (wide_cfg<LOGM, LOGR1, LOGR2>::SMEM + 2048));
+    int const by_smem = int((228 * 1024) / (wide_cfg<LOGM, LOGR1, LOGR2>::SMEM_PF + 1024 + 64));
     int const n       = by_regs < by_smem ? by_regs : by_smem;
     return n > 0 ? n : 1;
 }
@@ -663,8 +706,9 @@ int launch_r2c_wide(wide_tables<LOGM, LOGR1, LOGR2> const& tb, float const* in, 
     constexpr int ctas = wide_min_ctas<LOGM, LOGR1, LOGR2>();
     bool const pf      = wide_prefetch();
     auto kernel        = pf ? r2c_wide_kernel<LOGM, LOGR1, LOGR2, ctas, true> : r2c_wide_kernel<LOGM, LOGR1, LOGR2, ctas, false>;
-    NEO_TRY(enable_smem(kernel, cfg::SMEM));
-    kernel<<<wide_grid(batch, ctas, pf), cfg::NT, cfg::SMEM, stream>>>(in, out, tb.ta.template as<float2>(), tb.tb_fwd.template as<float2>(),
+    size_t const smem = pf ? cfg::SMEM_PF : cfg::SMEM;
+    NEO_TRY(enable_smem(kernel, smem));
+    kernel<<<wide_grid(batch, ctas, pf), cfg::NT, smem, stream>>>(in, out, tb.ta.template as<float2>(), tb.tb_fwd.template as<float2>(),
                                                                        tb.rtw.template as<float2>(), batch);
     return check_launch("r2c_wide_kernel");
 }
@@ -679,8 +723,9 @@ int launch_c2r_wide(wide_tables<LOGM, LOGR1, LOGR2> const& tb, float2 const* in,
     // the bulk copy wants the first 16-byte boundary of every row inside it and 8-byte aligned rows
     bool const pf = wide_prefetch() && (reinterpret_cast<std::uintptr_t>(in) & 7U) == 0;
     auto kernel   = pf ? c2r_wide_kernel<LOGM, LOGR1, LOGR2, ctas, true> : c2r_wide_kernel<LOGM, LOGR1, LOGR2, ctas, false>;
-    NEO_TRY(enable_smem(kernel, cfg::SMEM));
-    kernel<<<wide_grid(batch, ctas, pf), cfg::NT, cfg::SMEM, stream>>>(in, row_len, out, tb.ta.template as<float2>(),
+    size_t const smem = pf ? cfg::SMEM_PF : cfg::SMEM;
+    NEO_TRY(enable_smem(kernel, smem));
+    kernel<<<wide_grid(batch, ctas, pf), cfg::NT, smem, stream>>>(in, row_len, out, tb.ta.template as<float2>(),
                                                                        tb.tb_bwd.template as<float2>(), tb.rtw.template as<float2>(), batch);
     return check_launch("c2r_wide_kernel");
 }
