@@ -305,8 +305,10 @@ struct rfft_engine
     bool use_pair{false};        // float32, N = 2^16: one transform per CTA pair, exchange tile in distributed shared memory (fft_pair.cuh)
     bool use_big_cta{false};     // float32, M = 2^14: one 1024-thread CTA per transform (139 KB exchange tile)
     bool use_wide{false};        // float32, N = 2^14 / 2^15: 32 points per thread, three stages, Hermitian split in registers (fft_wide.cuh)
+    wide_tables<12, 4, 4> wide12;
     wide_tables<13, 4, 5> wide13;
     wide_tables<14, 5, 5> wide14;
+    wide_split_tables<14, 5, 5> wide15s;  // N = 2^16: two CTAs of 2^14 points per transform
     bool use_two_pass{false};    // four-CTA split c2c into an L2-resident scratch + Hermitian split pass
     c2c_engine<T> half;          // two-pass path: the half-size complex transform
     twiddle2<T> w2m;             // two-pass path: exp(-2 pi i k / N)
@@ -322,9 +324,13 @@ struct rfft_engine
         if (order == 0) { return NEO_B200_OK; }
         int const logm = order - 1;
         if constexpr (sizeof(T) == 4) {
-            if ((order == 14 || order == 15) && std::getenv("NEO_B200_NO_WIDE") == nullptr) {
+            bool const w13 = order == 13 && std::getenv("NEO_B200_WIDE13") != nullptr;  // A/B knob: N = 8192 through the wide kernel too
+            if ((order == 14 || order == 15 || order == 16 || w13) && std::getenv("NEO_B200_NO_WIDE") == nullptr) {
                 use_wide = true;
-                NEO_TRY(order == 14 ? wide13.build(stream) : wide14.build(stream));
+                NEO_TRY(order == 13   ? wide12.build(stream)
+                        : order == 14 ? wide13.build(stream)
+                        : order == 15 ? wide14.build(stream)
+                                      : wide15s.build(stream));
                 // no return: the 16-points-per-thread path below stays initialised for arrays that are not 16-byte aligned
             }
         }
@@ -439,7 +445,10 @@ struct rfft_engine
         if (order == 0) { return large_rfft<T>::size_one_forward(in, out, batch, stream); }
         if constexpr (sizeof(T) == 4) {
             if (use_wide && wide_aligned(in)) {
-                return order == 14 ? launch_r2c_wide(wide13, in, out, batch, stream) : launch_r2c_wide(wide14, in, out, batch, stream);
+                if (order == 16) { return launch_r2c_wide_split(wide15s, in, out, batch, stream); }
+                return order == 13   ? launch_r2c_wide(wide12, in, out, batch, stream)
+                       : order == 14 ? launch_r2c_wide(wide13, in, out, batch, stream)
+                                     : launch_r2c_wide(wide14, in, out, batch, stream);
             }
         }
         if constexpr (sizeof(T) == 4) {
@@ -488,8 +497,10 @@ struct rfft_engine
         if (order == 0) { return large_rfft<T>::size_one_backward(in, row_len, out, batch, stream); }
         if constexpr (sizeof(T) == 4) {
             if (use_wide && wide_aligned(out)) {
-                return order == 14 ? launch_c2r_wide(wide13, in, row_len, out, batch, stream)
-                                   : launch_c2r_wide(wide14, in, row_len, out, batch, stream);
+                if (order == 16) { return launch_c2r_wide_split(wide15s, in, row_len, out, batch, stream); }
+                return order == 13   ? launch_c2r_wide(wide12, in, row_len, out, batch, stream)
+                       : order == 14 ? launch_c2r_wide(wide13, in, row_len, out, batch, stream)
+                                     : launch_c2r_wide(wide14, in, row_len, out, batch, stream);
             }
         }
         if constexpr (sizeof(T) == 4) {

@@ -97,6 +97,12 @@ __host__ __device__ constexpr double wide_cos64(int e)
     return wide_cos64_quarter(64 - e);
 }
 __host__ __device__ constexpr double wide_sin64(int e) { return wide_cos64(e - 16); }
+__host__ __device__ constexpr double wide_sqrt(double x)
+{
+    double y = x > 1.0 ? x : 1.0;  // Newton from above
+    for (int i = 0; i < 64; ++i) { y = 0.5 * (y + x / y); }
+    return x <= 0.0 ? 0.0 : y;
+}
 
 // multiply by exp(DIR * 2 pi i EXP / 64), EXP known at compile time
 template<int EXP, int DIR>
@@ -123,6 +129,18 @@ template<int EXP>
 __device__ __forceinline__ float2 w64_const()
 {
     return make_float2(float(wide_cos64(EXP)), float(-wide_sin64(EXP)));
+}
+
+// exp(-2 pi i EXP / 128), EXP odd: half-angle of the table above
+template<int EXP>
+__device__ __forceinline__ float2 w128_const()
+{
+    static_assert(EXP >= 0 && EXP < 64, "first half turn");
+    // cos(x/2), sin(x/2) from cos x, 0 <= x/2 < pi/2 ... pi: EXP < 32 -> first quadrant, else second
+    constexpr double c  = wide_cos64(EXP);  // cos(2 pi EXP / 64) = cos of twice the wanted angle
+    constexpr double ch = EXP < 32 ? wide_sqrt((1.0 + c) * 0.5) : -wide_sqrt((1.0 + c) * 0.5);
+    constexpr double sh = wide_sqrt((1.0 - c) * 0.5);
+    return make_float2(float(ch), float(-sh));
 }
 
 // 32-point DFT in registers: 4 x 8 (n = 8 n1 + n2, k = k1 + 4 k2)
@@ -620,6 +638,286 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
     }
 }
 
+// ---- N = 4 M2 real points as TWO CTAs per transform (the half-size complex transform of M = 2 M2 points is one decimation-in-
+// frequency step too long for one tile): CTA r = 0, 1 forms y_r[n] = (z[n] + (-1)^r z[n + M2]) W_M^(r n) on the fly and its M2-point
+// wide transform yields the bins of parity r. Both CTAs of a row run side by side (adjacent block indices), so the second read of
+// every line is an L2 hit. Each CTA still needs the WHOLE row (2 M2 complex = twice the tile): the first half travels into the tile
+// (late bulk copy), the first three quarters of the second half into the staging buffer (early bulk copy), the rest comes by
+// ordinary loads issued before the wait.
+//   forward:  Z[r + 2 k2] pairs with Z[M - r - 2 k2] = sub-bin M2 - r - k2: r = 0 as in r2c_wide_kernel, r = 1 rows j and J-1-j (no
+//             self-paired rows); twiddle W_2M^(r + 2 k2) = W_2M^r * W_2M2^k2.
+//   backward: the Hermitian pre-pass pairs X[k] with X[M - k] BEFORE the parity split, so both parities use rows j and J - j:
+//             X[k2], X[M-k2], X[M2-k2], X[M2+k2] give Z at those four bins and from them y_r[k2] and y_r[M2-k2].
+template<int LOGM2, int LOGR1, int LOGR2>
+__global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
+    r2c_wide_split_kernel(float const* __restrict__ in, float2* __restrict__ out, float2 const* __restrict__ ta, float2 const* __restrict__ tb,
+                          float2 const* __restrict__ rtw, float2 const* __restrict__ w_m, float2 w_2m1, size_t batch)
+{
+    using W   = wide_fft<LOGM2, LOGR1, LOGR2>;
+    using cfg = wide_cfg<LOGM2, LOGR1, LOGR2>;
+    constexpr int M2 = cfg::M, M = 2 * M2, R1 = cfg::R1, R2 = cfg::R2, S1 = cfg::S1, J = cfg::J, XS = cfg::XS;
+    static_assert(cfg::BF1 == 1 && R1 == 32, "one radix-32 butterfly per thread in stage 1");
+    constexpr int ST = wide_stage<M2>::ST;  // staged part of the second half
+    constexpr int NG = (M2 - ST) / S1;      // inputs per thread that come by ordinary loads
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* const sm  = reinterpret_cast<float2*>(smem_raw);
+    float4* const sm4 = reinterpret_cast<float4*>(smem_raw);
+    float2* const stg = sm + M2;
+    int const t       = threadIdx.x;
+    int const r       = blockIdx.x & 1;
+    __shared__ __align__(8) unsigned long long bar;
+    unsigned parity = 0;
+    size_t const units = 2 * batch;  // (row, parity), parity fastest: gridDim.x is even, so a CTA keeps its parity
+    auto const zrow = [&](size_t unit) { return reinterpret_cast<float2 const*>(in) + (unit >> 1) * size_t(M); };
+    if (t == 0) {
+        wtma::init(&bar, 2);
+        if (blockIdx.x < units) {
+            wtma::fetch(stg, zrow(blockIdx.x) + M2, unsigned(ST) * 8U, &bar);
+            wtma::fetch(sm, zrow(blockIdx.x), unsigned(M2) * 8U, &bar);
+        }
+    }
+    __syncthreads();
+    float2 const w_in = r ? __ldg(w_m + t) : make_float2(1.0F, 0.0F);  // W_M^n', n' = t
+
+    for (size_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        bool const more = unit + gridDim.x < units;
+        // ---- stage 1 on y_r
+        {
+            int const n = t;
+            float2 u[R1], g[NG];
+            float2 const* const z = zrow(unit);
+#pragma unroll
+            for (int i = 0; i < NG; ++i) { g[i] = __ldcs(z + M2 + ST + n + i * S1); }
+            wtma::wait(&bar, parity);
+            parity ^= 1U;
+            static_for<0, R1>([&](auto n1c) {
+                constexpr int n1 = decltype(n1c)::value;
+                float2 const a   = sm[n + n1 * S1];
+                float2 c;
+                if constexpr (n1 * S1 < ST) { c = stg[n + n1 * S1]; }
+                else { c = g[n1 - ST / S1]; }
+                // W_M^(n' + S1 n1) = W_M^n' * exp(-2 pi i n1 / 64)
+                u[n1] = r ? cmul(mul_w64<n1, -1>(csub(a, c)), w_in) : cadd(a, c);
+            });
+            __syncthreads();  // every thread has its inputs: staging buffer and tile may be overwritten
+            if (t == 0 && more) { wtma::fetch(stg, zrow(unit + gridDim.x) + M2, unsigned(ST) * 8U, &bar); }
+            wdft<R1, -1>::run(u);
+            {
+                float2 w[R1];
+#pragma unroll
+                for (int q = 1; q < R1; ++q) {
+                    int const hi = 1 << (31 - __clz(q));
+                    if (q == hi) { w[q] = __ldg(ta + (31 - __clz(q)) * XS + n); }
+                    else { w[q] = cmul(w[hi], w[q - hi]); }
+                    u[q] = cmul(u[q], w[q]);
+                }
+            }
+            int const a = n & 15, a2 = n >> 4;
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1) { sm[(k1 * R2 + a2) * 16 + ((((a >> 1) ^ (k1 & 7)) << 1) | (a & 1))] = u[k1]; }
+        }
+        __syncthreads();
+        W::template stage2<-1>(sm, tb, t);
+        __syncthreads();
+        {
+            int const ja = t, jb = r ? J - 1 - t : (t == 0 ? J / 2 : J - t);
+            float2 wt = __ldg(rtw + t);
+            float2 za[16], zb[16];
+            W::load_row(sm4, ja, za);
+            W::load_row(sm4, jb, zb);
+            __syncthreads();  // the tile is free for the next unit
+            if (t == 0 && more) { wtma::fetch(sm, zrow(unit + gridDim.x), unsigned(M2) * 8U, &bar); }
+            dft<16, -1>::run(za);
+            dft<16, -1>::run(zb);
+            float2* const row = out + (unit >> 1) * (size_t(M) + 1);
+            if (r == 0) {
+                wide_r2c_post<M2>(za, zb, t, wt, [&](int k, float2 x) { row[2 * k] = x; });
+            } else {
+                wt = cmul(wt, w_2m1);
+                static_for<0, 16>([&](auto k3c) {
+                    constexpr int k3 = decltype(k3c)::value;
+                    float2 xk, xmk;
+                    r2c_post_pair(za[k3], zb[15 - k3], cmul(wt, w64_const<2 * k3>()), xk, xmk);
+                    int const k2 = t + J * k3;
+                    row[1 + 2 * k2]     = xk;
+                    row[M - 1 - 2 * k2] = xmk;
+                });
+            }
+        }
+    }
+}
+
+// in: [batch][row_len] complex (first 2 M2 + 1 used), out: [batch][4 M2] reals, unnormalised. w_m[k] = exp(-2 pi i k / M), k < J
+template<int LOGM2, int LOGR1, int LOGR2>
+__global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
+    c2r_wide_split_kernel(float2 const* __restrict__ in, size_t row_len, float* __restrict__ out, float2 const* __restrict__ ta,
+                          float2 const* __restrict__ tb, float2 const* __restrict__ rtw, float2 const* __restrict__ w_m, size_t batch)
+{
+    using W   = wide_fft<LOGM2, LOGR1, LOGR2>;
+    using cfg = wide_cfg<LOGM2, LOGR1, LOGR2>;
+    constexpr int M2 = cfg::M, M = 2 * M2, R1 = cfg::R1, R2 = cfg::R2, S1 = cfg::S1, J = cfg::J, XS = cfg::XS;
+    static_assert(cfg::BF1 == 1 && R1 == 32, "one radix-32 butterfly per thread in stage 1'");
+    constexpr int ST = wide_stage<M2>::ST;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    float2* const sm  = reinterpret_cast<float2*>(smem_raw);
+    float4* const sm4 = reinterpret_cast<float4*>(smem_raw);
+    float2* const stg = sm + M2;
+    int const t       = threadIdx.x;
+    int const r       = blockIdx.x & 1;
+    __shared__ __align__(8) unsigned long long bar;
+    unsigned parity = 0;
+    size_t const units = 2 * batch;
+    // first bin of a unit's row that sits on a 16-byte boundary
+    auto const xrow = [&](size_t unit) {
+        float2 const* const x = in + (unit >> 1) * row_len;
+        return x + ((reinterpret_cast<std::uintptr_t>(x) >> 3) & 1U);
+    };
+    if (t == 0) {
+        wtma::init(&bar, 2);
+        if (blockIdx.x < units) {
+            wtma::fetch(stg, xrow(blockIdx.x) + M2, unsigned(ST) * 8U, &bar);
+            wtma::fetch(sm, xrow(blockIdx.x), unsigned(M2) * 8U, &bar);
+        }
+    }
+    __syncthreads();
+    // the staged window holds bins lo .. lo + M2 + ST - 1 at tile[k - lo] (k - lo < M2) / stg[k - lo - M2]
+    auto const staged = [&](int e) { return e < M2 ? sm[e] : stg[e - M2]; };
+
+    for (size_t unit = blockIdx.x; unit < units; unit += gridDim.x) {
+        bool const more = unit + gridDim.x < units;
+        {
+            float2 const* const x = in + (unit >> 1) * row_len;
+            int const lo = int(xrow(unit) - x);
+            int const ja = t, jb = t == 0 ? J / 2 : J - t;
+            float2 const wt = __ldg(rtw + t);
+            // xa[k3] = X[k2], xb[15-k3] = X[M2-k2], ya[k3] = X[M2+k2], yb[15-k3] = X[M-k2]   (k2 = ja + J k3; row jb = J - ja)
+            float2 xa[16], xb[16], ya[16], yb[16];
+            // ordinary loads first: the bins beyond the staged window (k - lo >= M2 + ST  <=>  k3 >= 12 of the second half)
+            if (t != 0) {
+#pragma unroll
+                for (int k3 = 12; k3 < 16; ++k3) {
+                    ya[k3] = __ldcs(x + M2 + ja + J * k3);
+                    yb[k3] = __ldcs(x + M2 + jb + J * k3);
+                }
+            }
+            wtma::wait(&bar, parity);
+            parity ^= 1U;
+            if (t != 0) {
+                static_for<0, 16>([&](auto k3c) {
+                    constexpr int k3 = decltype(k3c)::value;
+                    xa[k3]           = sm[ja + J * k3 - lo];
+                    xb[k3]           = sm[jb + J * k3 - lo];
+                    if constexpr (k3 < 12) {
+                        ya[k3] = stg[ja + J * k3 - lo];
+                        yb[k3] = stg[jb + J * k3 - lo];
+                    }
+                });
+            } else {
+                // thread 0: rows 0 and J/2 of both halves; bins at the window's edges come by ordinary loads
+                auto const bin = [&](int k) { return (k - lo >= 0 && k - lo < M2 + ST) ? staged(k - lo) : x[k]; };
+#pragma unroll
+                for (int k3 = 0; k3 < 16; ++k3) {
+                    xa[k3] = bin(J * k3);
+                    xb[k3] = bin(J / 2 + J * k3);
+                    ya[k3] = bin(M2 + J * k3);
+                    yb[k3] = bin(M2 + J / 2 + J * k3);
+                }
+            }
+            float const nyq = t == 0 ? x[M].x : 0.0F;
+            // Hermitian pre-pass on the FULL-size spectrum (M bins), twiddle W_2M^k -- before the barrier, so that 32 values per thread
+            // are live across it, not 64
+            float2 za[16], zb[16];
+            if (t != 0) {
+                static_for<0, 16>([&](auto k3c) {
+                    constexpr int k3 = decltype(k3c)::value;
+                    // k = k2 = ja + J k3:  W_2M^k2 = W_2M^ja * exp(-2 pi i k3 / 64)   (J / 2M = 1/64)
+                    float2 const w = cmul(wt, w64_const<k3>());
+                    float2 z_k, z_mk, z_m2mk, z_m2pk;
+                    c2r_pre_pair(xa[k3], yb[15 - k3], w, z_k, z_mk);  // X[k2], X[M - k2]
+                    // k = M2 - k2: W_2M^(M2 - k2) = -i conj(W_2M^k2)
+                    float2 const wp = make_float2(-w.y, -w.x);
+                    c2r_pre_pair(xb[15 - k3], ya[k3], wp, z_m2mk, z_m2pk);  // X[M2 - k2], X[M2 + k2]
+                    if (r == 0) {
+                        za[k3]      = cadd(z_k, z_m2pk);
+                        zb[15 - k3] = cadd(z_m2mk, z_mk);
+                    } else {
+                        za[k3]      = csub(z_k, z_m2pk);
+                        zb[15 - k3] = csub(z_m2mk, z_mk);
+                    }
+                });
+            } else {
+                // row 0: k2 = J k3. k3 = 0: Z[0] from the edges, Z[M2] = 2 conj(X[M2]); the other bins pair first half <-> second half
+                float2 zf[16], zs[16];  // Z[k2] and Z[M2 + k2] along row 0
+                zf[0] = make_float2(xa[0].x + nyq, xa[0].x - nyq);
+                zs[0] = make_float2(2.0F * ya[0].x, -2.0F * ya[0].y);
+                static_for<1, 16>([&](auto k3c) {
+                    constexpr int k3 = decltype(k3c)::value;
+                    // X[k2] and X[M - k2], M - k2 = M2 + J (16 - k3); twiddle W_2M^(J k3) = exp(-2 pi i k3 / 64)
+                    float2 z_k, z_mk;
+                    c2r_pre_pair(xa[k3], ya[16 - k3], w64_const<k3>(), z_k, z_mk);
+                    zf[k3]      = z_k;
+                    zs[16 - k3] = z_mk;
+                });
+                float2 zf2[16], zs2[16];  // along row J/2: k2 = J/2 + J k3, twiddle exp(-2 pi i (1 + 2 k3) / 128)
+                static_for<0, 16>([&](auto k3c) {
+                    constexpr int k3 = decltype(k3c)::value;
+                    // X[k2] = xb[k3], X[M - k2] = X[M2 + J/2 + J (15 - k3)] = yb[15 - k3]
+                    float2 const w = w128_const<1 + 2 * k3>();
+                    float2 z_k, z_mk;
+                    c2r_pre_pair(xb[k3], yb[15 - k3], w, z_k, z_mk);
+                    zf2[k3]      = z_k;   // Z[k2]
+                    zs2[15 - k3] = z_mk;  // Z[M - k2] = Z[M2 + (J/2 + J (15 - k3))]
+                });
+#pragma unroll
+                for (int k3 = 0; k3 < 16; ++k3) {
+                    za[k3] = r == 0 ? cadd(zf[k3], zs[k3]) : csub(zf[k3], zs[k3]);
+                    zb[k3] = r == 0 ? cadd(zf2[k3], zs2[k3]) : csub(zf2[k3], zs2[k3]);
+                }
+            }
+            __syncthreads();  // every thread has consumed its inputs: staging buffer and tile may be overwritten
+            if (t == 0 && more) { wtma::fetch(stg, xrow(unit + gridDim.x) + M2, unsigned(ST) * 8U, &bar); }
+            if (r != 0) {
+                // times conj(W_M^k2), k2 = j + J k3:  W_M^j * exp(-2 pi i k3 / 32)
+                float2 const wa = __ldg(w_m + ja), wb = __ldg(w_m + jb);
+                static_for<0, 16>([&](auto k3c) {
+                    constexpr int k3 = decltype(k3c)::value;
+                    za[k3]           = cmulc(mul_w64<2 * k3, +1>(za[k3]), wa);
+                    zb[k3]           = cmulc(mul_w64<2 * k3, +1>(zb[k3]), wb);
+                });
+            }
+            dft<16, +1>::run(za);
+            dft<16, +1>::run(zb);
+            {
+                float2 w[16];
+                wide_twiddles(w, [&](int p) { return __ldg(ta + p * XS + ja); });
+#pragma unroll
+                for (int a = 1; a < 16; ++a) { za[a] = cmulc(za[a], w[a]); }
+                wide_twiddles(w, [&](int p) { return __ldg(ta + p * XS + jb); });
+#pragma unroll
+                for (int a = 1; a < 16; ++a) { zb[a] = cmulc(zb[a], w[a]); }
+            }
+            W::store_row(sm4, ja, za);
+            W::store_row(sm4, jb, zb);
+        }
+        __syncthreads();
+        W::template stage2<+1>(sm, tb, t);
+        __syncthreads();
+        {
+            int const n = t, a = n & 15, a2 = n >> 4;
+            float2 u[R1];
+#pragma unroll
+            for (int k1 = 0; k1 < R1; ++k1) { u[k1] = sm[(k1 * R2 + a2) * 16 + ((((a >> 1) ^ (k1 & 7)) << 1) | (a & 1))]; }
+            __syncthreads();
+            if (t == 0 && more) { wtma::fetch(sm, xrow(unit + gridDim.x), unsigned(M2) * 8U, &bar); }
+            wdft<R1, +1>::run(u);
+            // y_r's transform is z[r + 2 n]
+            float2* const dst = reinterpret_cast<float2*>(out + (unit >> 1) * (2 * size_t(M))) + r + 2 * n;
+#pragma unroll
+            for (int b2 = 0; b2 < R1; ++b2) { __stcs(dst + 2 * b2 * S1, u[b2]); }
+        }
+    }
+}
+
 // ---- tables + launchers --------------------------------------------------------------------------------------------------------------
 template<int LOGM, int LOGR1, int LOGR2>
 struct wide_tables
@@ -728,6 +1026,75 @@ int launch_c2r_wide(wide_tables<LOGM, LOGR1, LOGR2> const& tb, float2 const* in,
     kernel<<<wide_grid(batch, ctas, pf), cfg::NT, smem, stream>>>(in, row_len, out, tb.ta.template as<float2>(),
                                                                        tb.tb_bwd.template as<float2>(), tb.rtw.template as<float2>(), batch);
     return check_launch("c2r_wide_kernel");
+}
+
+// ---- split pair (N = 2^16): tables of the M2-point transform + the decimation step's twiddles ------------------------------------
+template<int LOGM2, int LOGR1, int LOGR2>
+struct wide_split_tables
+{
+    using cfg = wide_cfg<LOGM2, LOGR1, LOGR2>;
+    wide_tables<LOGM2, LOGR1, LOGR2> sub;
+    device_buffer w_m;       // exp(-2 pi i k / M), k < J   (M = 2 M2)
+    device_buffer rtw_full;  // exp(-i pi k / M), k <= J/2: the real-transform twiddle of the FULL size
+    float2 w_2m1{};          // exp(-i pi / M)
+
+    int build(cudaStream_t stream)
+    {
+        constexpr double pi = 3.14159265358979323846264338327950288;
+        constexpr int M = 2 * cfg::M, J = cfg::J;
+        NEO_TRY(sub.build(stream));
+        std::vector<float2> a(J), b(J / 2 + 1);
+        for (int k = 0; k < J; ++k) {
+            double const v = -2.0 * pi * double(k) / double(M);
+            a[k]           = make_float2(float(std::cos(v)), float(std::sin(v)));
+        }
+        for (int k = 0; k <= J / 2; ++k) {
+            double const v = -pi * double(k) / double(M);
+            b[k]           = make_float2(float(std::cos(v)), float(std::sin(v)));
+        }
+        w_2m1 = make_float2(float(std::cos(-pi / double(M))), float(std::sin(-pi / double(M))));
+        NEO_TRY(w_m.reserve(a.size() * sizeof(float2)));
+        NEO_CUDA_TRY(cudaMemcpyAsync(w_m.ptr, a.data(), a.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
+        NEO_TRY(rtw_full.reserve(b.size() * sizeof(float2)));
+        NEO_CUDA_TRY(cudaMemcpyAsync(rtw_full.ptr, b.data(), b.size() * sizeof(float2), cudaMemcpyHostToDevice, stream));
+        NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+        return NEO_B200_OK;
+    }
+};
+
+inline unsigned wide_split_grid(size_t batch)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return unsigned(std::min<size_t>(2 * batch, size_t(sms) & ~size_t(1)));  // even: a CTA keeps its parity, the pair of a row runs together
+}
+
+template<int LOGM2, int LOGR1, int LOGR2>
+int launch_r2c_wide_split(wide_split_tables<LOGM2, LOGR1, LOGR2> const& tb, float const* in, float2* out, size_t batch, cudaStream_t stream)
+{
+    using cfg = wide_cfg<LOGM2, LOGR1, LOGR2>;
+    if (batch == 0) { return NEO_B200_OK; }
+    auto kernel = r2c_wide_split_kernel<LOGM2, LOGR1, LOGR2>;
+    NEO_TRY(enable_smem(kernel, cfg::SMEM_PF));
+    kernel<<<wide_split_grid(batch), cfg::NT, cfg::SMEM_PF, stream>>>(in, out, tb.sub.ta.template as<float2>(),
+                                                                      tb.sub.tb_fwd.template as<float2>(), tb.sub.rtw.template as<float2>(),
+                                                                      tb.w_m.template as<float2>(), tb.w_2m1, batch);
+    return check_launch("r2c_wide_split_kernel");
+}
+
+template<int LOGM2, int LOGR1, int LOGR2>
+int launch_c2r_wide_split(wide_split_tables<LOGM2, LOGR1, LOGR2> const& tb, float2 const* in, size_t row_len, float* out, size_t batch,
+                          cudaStream_t stream)
+{
+    using cfg = wide_cfg<LOGM2, LOGR1, LOGR2>;
+    if (batch == 0) { return NEO_B200_OK; }
+    auto kernel = c2r_wide_split_kernel<LOGM2, LOGR1, LOGR2>;
+    NEO_TRY(enable_smem(kernel, cfg::SMEM_PF));
+    kernel<<<wide_split_grid(batch), cfg::NT, cfg::SMEM_PF, stream>>>(in, row_len, out, tb.sub.ta.template as<float2>(),
+                                                                      tb.sub.tb_bwd.template as<float2>(),
+                                                                      tb.rtw_full.template as<float2>(), tb.w_m.template as<float2>(), batch);
+    return check_launch("c2r_wide_split_kernel");
 }
 
 }  // namespace neo_b200

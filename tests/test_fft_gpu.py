@@ -44,7 +44,7 @@ def test_rfft_irfft_match_oracle_every_order(gpu, orc, real, cplx):
         plan.close()
 
 
-@pytest.mark.parametrize("order,batch", [(13, 701), (14, 333), (14, 1201), (15, 301), (15, 610)])
+@pytest.mark.parametrize("order,batch", [(13, 701), (14, 333), (14, 1201), (15, 301), (15, 610), (16, 151)])
 def test_long_rfft_many_rows(gpu, orc, order, batch):
     # N = 2^13 / 2^14 (512-thread CTAs, two per SM): more rows than one wave of CTAs, odd and even rows (spectrum rows of N/2+1 bins
     # alternate between 16-byte aligned and not), and N-long spectrum rows on the way back. Also the parity test of the TMA-staged
