@@ -3,6 +3,7 @@
 // (src/neo/convolution/uniform_partitioned_convolver.hpp:14-65, dense_convolver.hpp:20-25) and
 // neo::convolution::uniform_partition (uniform_partition.hpp:13-26).
 #include "conv_frame.cuh"
+#include "fft_wide.cuh"
 
 #include <algorithm>
 #include <cstdlib>
@@ -68,6 +69,13 @@ struct conv_engine
     bool has_filter{false};
 
     fft_tables<T> tables;
+    // float32, B = 1024 (the 2048-point real transforms of BASELINE config 5): one warp per transform, 32 points per thread, Hermitian
+    // split in registers, 128-bit accesses on the real side (fft_wide.cuh). NEO_B200_CONV_NO_WIDE keeps the 16-points-per-thread kernels.
+    // Measured (C5, frame mode T = 256, ms per step): c2r 0.668 -> 0.631 (15 % fewer instructions, 0.78 of HBM by its 12 bytes per sample);
+    // r2c 0.682 -> 0.699 (14 % fewer instructions, but 16 instead of 32 resident warps leave its loads exposed), so the forward side
+    // takes the wide kernel only with NEO_B200_CONV_WIDE_R2C.
+    wide_tables<10, 3, 3> wide10;
+    bool use_wide{false}, use_wide_r2c{false};
     device_buffer filter, fdl, prev[2], tail, acc, acc_alt, ola_y, stage_in, stage_out, stage_filter, tickets;
     // partition-sharded handles alternate between two partial-spectra buffers, so the reduction of call i (NCCL reads the buffer
     // neo_b200_conv_spectra returned) may still be running while call i+1 writes the other one
@@ -199,6 +207,11 @@ struct conv_engine
         logw    = std::min(logb, int(log2_exact(size_t(tile_width<T>()))));
         nt      = m >> logw;
         NEO_TRY(tables.build(logb, true, stream));
+        if constexpr (sizeof(T) == 4) {
+            use_wide = logb == 10 && std::getenv("NEO_B200_CONV_NO_WIDE") == nullptr;
+            if (use_wide) { NEO_TRY(wide10.build(stream)); }
+            use_wide_r2c = use_wide && std::getenv("NEO_B200_CONV_WIDE_R2C") != nullptr;
+        }
 
         size_t const csz = sizeof(cx<T>);
         if (frame == 0) { NEO_TRY(filter.reserve(filters * parts * m * csz)); }
@@ -375,6 +388,36 @@ struct conv_engine
         return finish_filter(stream);
     }
 
+    // the wide kernels move the real rows with 128-bit accesses
+    bool wide_rows_ok(void const* rows, size_t stride) const
+    {
+        return use_wide && (reinterpret_cast<std::uintptr_t>(rows) & 15U) == 0 && stride % 4 == 0;
+    }
+
+    template<int LOGM, class IO>
+    int run_r2c(IO const& io, bool wide, size_t batch, cudaStream_t stream)
+    {
+        if constexpr (sizeof(T) == 4 && LOGM == 10) {
+            if (wide) {
+                return launch_r2c_wide_io<10, 3, 3>(io, wide10.ta.template as<float2>(), wide10.tb_fwd.template as<float2>(),
+                                                    wide10.rtw.template as<float2>(), batch, stream);
+            }
+        }
+        return launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), batch, stream);
+    }
+
+    template<int LOGM, class IO>
+    int run_c2r(IO const& io, bool wide, size_t batch, cudaStream_t stream)
+    {
+        if constexpr (sizeof(T) == 4 && LOGM == 10) {
+            if (wide) {
+                return launch_c2r_wide_io<10, 3, 3>(io, wide10.ta.template as<float2>(), wide10.tb_bwd.template as<float2>(),
+                                                    wide10.rtw.template as<float2>(), batch, stream);
+            }
+        }
+        return launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), batch, stream);
+    }
+
     // window + r2c + FDL insert for input channels [chan0, chan0 + nchan); `in` points at channel chan0's row
     int forward_r2c(T const* in, size_t in_stride, size_t blocks, size_t chan0, size_t nchan, cudaStream_t stream)
     {
@@ -386,12 +429,12 @@ struct conv_engine
                     conv_r2c_io<T, LOGM, true> io{in, in_stride, prev[prev_flip].template as<T>(), prev[prev_flip ^ 1].template as<T>(),
                                                   fdl.template as<cx<T>>(), ring, x1_half * frame, int(blocks),
                                                   cfg.kind == NEO_B200_UPOLA ? 1 : 0, logb, 1, chan0};
-                    status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
+                    status = run_r2c<LOGM>(io, use_wide_r2c && wide_rows_ok(in, in_stride), nchan * blocks, stream);
                 } else {
                     conv_r2c_io<T, LOGM> io{in, in_stride, prev[prev_flip].template as<T>(), prev[prev_flip ^ 1].template as<T>(),
                                             fdl.template as<cx<T>>(), ring, int(write_pos), int(blocks),
                                             cfg.kind == NEO_B200_UPOLA ? 1 : 0, logw, nt, chan0};
-                    status = launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), nchan * blocks, stream);
+                    status = run_r2c<LOGM>(io, use_wide_r2c && wide_rows_ok(in, in_stride), nchan * blocks, stream);
                 }
             }
         });
@@ -666,7 +709,7 @@ struct conv_engine
             if constexpr (LOGM >= 1 && LOGM <= max_cta_logm<T>()) {
                 if (nsrc == 1) {
                     conv_c2r_io<T, LOGM> io{srcs[0], int(blocks), dst, out_stride, T(1) / T(2 * m), ola ? 1 : 0};
-                    status = launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
+                    status = run_c2r<LOGM>(io, wide_rows_ok(dst, ola ? 4 : out_stride), count * blocks, stream);
                 } else {
                     auto const run = [&](auto io) {
                         for (int j = 0; j < nsrc; ++j) { io.src[j] = srcs[j]; }
@@ -676,7 +719,7 @@ struct conv_engine
                         io.out_stride  = out_stride;
                         io.scale       = T(1) / T(2 * m);
                         io.overlap_add = ola ? 1 : 0;
-                        return launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), count * blocks, stream);
+                        return run_c2r<LOGM>(io, wide_rows_ok(dst, ola ? 4 : out_stride), count * blocks, stream);
                     };
                     status = nsrc == 2 ? run(conv_c2r_sum_io<T, LOGM, 2>{}) : run(conv_c2r_sum_io<T, LOGM, 0>{});
                 }

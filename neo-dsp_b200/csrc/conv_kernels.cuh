@@ -597,6 +597,19 @@ struct conv_r2c_io
         else { r.dst[((size_t(k >> logw) * ring) << logw) + (k & ((1 << logw) - 1))] = x; }
     }
     __device__ __forceinline__ void store_edges(row_state const& r, T dc, T nyq) const { r.dst[0] = mk<T>(dc, nyq); }
+    // the wide kernel's 128-bit accesses (float rows on 16-byte boundaries): complex pairs j, j + 1 of the lower (previous block) /
+    // upper (this block) half-window, j even and relative to the half
+    template<bool HI>
+    __device__ __forceinline__ float4 load_pair(row_state const& r, int j) const
+    {
+        static_assert(sizeof(T) == 4, "float rows");
+        if constexpr (HI) { return r.hi != nullptr ? *reinterpret_cast<float4 const*>(r.hi + j) : make_float4(0.0F, 0.0F, 0.0F, 0.0F); }
+        else { return *reinterpret_cast<float4 const*>(r.lo + j); }
+    }
+    __device__ __forceinline__ void keep_pair(row_state const& r, int j, float4 v) const
+    {
+        if (r.keep != nullptr) { *reinterpret_cast<float4*>(r.keep + j) = v; }
+    }
 };
 
 // neo::convolution::overlap_add_convolver (overlap_add_convolver.hpp:85-132) transforms its real window AS IT STANDS: after a call
@@ -657,6 +670,16 @@ struct conv_c2r_io
         } else if (j >= H) {
             r.dst[j - H] = z;  // keep samples [B, 2B) (overlap_save.hpp:111)
         }
+    }
+    // the wide kernel's 128-bit stores: samples z0, z1 = complex pairs j, j + 1 of the lower / upper half of the real row
+    template<bool HI>
+    __device__ __forceinline__ void store_pair(row_state const& r, int j, C z0, C z1) const
+    {
+        static_assert(sizeof(T) == 4, "float rows");
+        constexpr int H = (1 << LOGM) / 2;
+        float4 const v  = make_float4(z0.x * scale, z0.y * scale, z1.x * scale, z1.y * scale);
+        if (overlap_add) { *reinterpret_cast<float4*>(r.dst + j + (HI ? H : 0)) = v; }
+        else if (HI) { *reinterpret_cast<float4*>(r.dst + j) = v; }
     }
 };
 
@@ -734,6 +757,16 @@ struct conv_c2r_sum_io
         } else if (j >= H) {
             r.dst[j - H] = z;
         }
+    }
+    // the wide kernel's 128-bit stores: samples z0, z1 = complex pairs j, j + 1 of the lower / upper half of the real row
+    template<bool HI>
+    __device__ __forceinline__ void store_pair(row_state const& r, int j, C z0, C z1) const
+    {
+        static_assert(sizeof(T) == 4, "float rows");
+        constexpr int H = (1 << LOGM) / 2;
+        float4 const v  = make_float4(z0.x * scale, z0.y * scale, z1.x * scale, z1.y * scale);
+        if (overlap_add) { *reinterpret_cast<float4*>(r.dst + j + (HI ? H : 0)) = v; }
+        else if (HI) { *reinterpret_cast<float4*>(r.dst + j) = v; }
     }
 };
 

@@ -219,8 +219,8 @@ __device__ __forceinline__ void wide_twiddles(float2 (&w)[R], Load&& load)
 // Hermitian split of a thread's two stage-3 butterflies (za: butterfly jA, zb: butterfly jB), results straight to the spectrum row.
 // t > 0: jA = t, jB = J - t, Z[t + J k3] pairs with zb[15 - k3], twiddle W_2M^(t + J k3) = W_2M^t * exp(-2 pi i k3 / 32).
 // t = 0: butterflies 0 and J/2 pair within themselves.
-template<int M, class Store>
-__device__ __forceinline__ void wide_r2c_post(float2 const (&za)[16], float2 const (&zb)[16], int t, float2 wt, Store&& store)
+template<int M, class Store, class Edges>
+__device__ __forceinline__ void wide_r2c_post(float2 const (&za)[16], float2 const (&zb)[16], int t, float2 wt, Store&& store, Edges&& edges)
 {
     constexpr int J = M / 16;
     if (t != 0) {
@@ -233,8 +233,7 @@ __device__ __forceinline__ void wide_r2c_post(float2 const (&za)[16], float2 con
             store(M - k, xmk);
         });
     } else {
-        store(0, make_float2(za[0].x + za[0].y, 0.0F));
-        store(M, make_float2(za[0].x - za[0].y, 0.0F));
+        edges(za[0].x + za[0].y, za[0].x - za[0].y);  // X[0], X[M]: both real
         store(M / 2, cconj(za[8]));
         static_for<1, 8>([&](auto k3c) {
             constexpr int k3 = decltype(k3c)::value;
@@ -373,9 +372,9 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
     using W   = wide_fft<LOGM, LOGR1, LOGR2>;
     using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
     constexpr int M = cfg::M, R1 = cfg::R1, R2 = cfg::R2, NT = cfg::NT, S1 = cfg::S1, J = cfg::J, BF1 = cfg::BF1, XS = cfg::XS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* const sm  = reinterpret_cast<float2*>(smem_raw);
-    float4* const sm4 = reinterpret_cast<float4*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char wide_smem_raw[];
+    float2* const sm  = reinterpret_cast<float2*>(wide_smem_raw);
+    float4* const sm4 = reinterpret_cast<float4*>(wide_smem_raw);
     int const t       = threadIdx.x;
     __shared__ __align__(8) unsigned long long bar;
     unsigned parity = 0;
@@ -498,7 +497,11 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
             dft<16, -1>::run(za);
             dft<16, -1>::run(zb);
             float2* const row = out + b * (size_t(M) + 1);
-            wide_r2c_post<M>(za, zb, t, wt, [&](int k, float2 x) { row[k] = x; });
+            wide_r2c_post<M>(za, zb, t, wt, [&](int k, float2 x) { row[k] = x; },
+                             [&](float dc, float nyq) {
+                                 row[0] = make_float2(dc, 0.0F);
+                                 row[M] = make_float2(nyq, 0.0F);
+                             });
         }
     }
 }
@@ -514,9 +517,9 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
     using W   = wide_fft<LOGM, LOGR1, LOGR2>;
     using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
     constexpr int M = cfg::M, R1 = cfg::R1, R2 = cfg::R2, NT = cfg::NT, S1 = cfg::S1, J = cfg::J, BF1 = cfg::BF1, XS = cfg::XS;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* const sm  = reinterpret_cast<float2*>(smem_raw);
-    float4* const sm4 = reinterpret_cast<float4*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char wide_smem_raw[];
+    float2* const sm  = reinterpret_cast<float2*>(wide_smem_raw);
+    float4* const sm4 = reinterpret_cast<float4*>(wide_smem_raw);
     int const t       = threadIdx.x;
     __shared__ __align__(8) unsigned long long bar;
     unsigned parity = 0;
@@ -659,9 +662,9 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
     static_assert(cfg::BF1 == 1 && R1 == 32, "one radix-32 butterfly per thread in stage 1");
     constexpr int ST = wide_stage<M2>::ST;  // staged part of the second half
     constexpr int NG = (M2 - ST) / S1;      // inputs per thread that come by ordinary loads
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* const sm  = reinterpret_cast<float2*>(smem_raw);
-    float4* const sm4 = reinterpret_cast<float4*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char wide_smem_raw[];
+    float2* const sm  = reinterpret_cast<float2*>(wide_smem_raw);
+    float4* const sm4 = reinterpret_cast<float4*>(wide_smem_raw);
     float2* const stg = sm + M2;
     int const t       = threadIdx.x;
     int const r       = blockIdx.x & 1;
@@ -731,7 +734,11 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
             dft<16, -1>::run(zb);
             float2* const row = out + (unit >> 1) * (size_t(M) + 1);
             if (r == 0) {
-                wide_r2c_post<M2>(za, zb, t, wt, [&](int k, float2 x) { row[2 * k] = x; });
+                wide_r2c_post<M2>(za, zb, t, wt, [&](int k, float2 x) { row[2 * k] = x; },
+                                  [&](float dc, float nyq) {
+                                      row[0] = make_float2(dc, 0.0F);
+                                      row[M] = make_float2(nyq, 0.0F);
+                                  });
             } else {
                 wt = cmul(wt, w_2m1);
                 static_for<0, 16>([&](auto k3c) {
@@ -758,9 +765,9 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
     constexpr int M2 = cfg::M, M = 2 * M2, R1 = cfg::R1, R2 = cfg::R2, S1 = cfg::S1, J = cfg::J, XS = cfg::XS;
     static_assert(cfg::BF1 == 1 && R1 == 32, "one radix-32 butterfly per thread in stage 1'");
     constexpr int ST = wide_stage<M2>::ST;
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    float2* const sm  = reinterpret_cast<float2*>(smem_raw);
-    float4* const sm4 = reinterpret_cast<float4*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char wide_smem_raw[];
+    float2* const sm  = reinterpret_cast<float2*>(wide_smem_raw);
+    float4* const sm4 = reinterpret_cast<float4*>(wide_smem_raw);
     float2* const stg = sm + M2;
     int const t       = threadIdx.x;
     int const r       = blockIdx.x & 1;
@@ -916,6 +923,175 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
             for (int b2 = 0; b2 < R1; ++b2) { __stcs(dst + 2 * b2 * S1, u[b2]); }
         }
     }
+}
+
+// ---- one WARP per transform (M = 1024: the convolver's 2048-point real transforms), load / store sides as policy objects like
+// r2c_kernel / c2r_kernel. The three stages only need __syncwarp(): warps never wait for each other, so their load, butterfly and
+// store phases drift apart and overlap. Policies provide (besides open / store / store_edges / load / load_edges of the narrow
+// kernels) the 128-bit accesses of the real side: load_pair<HI>(row, j), keep_pair(row, j, v), store_pair<HI>(row, j, z0, z1) with j
+// an even index inside the lower (HI = false) or upper half of the real row's complex pairs.
+template<int LOGM, int LOGR1, int LOGR2, int G, class IO>
+__global__ void __launch_bounds__(32 * G, 512 / (32 * G))
+    r2c_wide_io_kernel(IO io, float2 const* __restrict__ ta, float2 const* __restrict__ tb, float2 const* __restrict__ rtw, size_t batch)
+{
+    using W   = wide_fft<LOGM, LOGR1, LOGR2>;
+    using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
+    constexpr int M = cfg::M, R1 = cfg::R1, R2 = cfg::R2, NT = cfg::NT, S1 = cfg::S1, J = cfg::J, BF1 = cfg::BF1, XS = cfg::XS, H = M / 2;
+    static_assert(NT == 32 && BF1 >= 2, "one warp per transform, pairs of stage-1 butterflies");
+    extern __shared__ __align__(128) unsigned char wide_smem_raw[];
+    int const t      = threadIdx.x & 31;
+    size_t const b   = size_t(blockIdx.x) * G + (threadIdx.x >> 5);
+    if (b >= batch) { return; }  // whole warps leave: nothing below synchronises across warps
+    float2* const sm  = reinterpret_cast<float2*>(wide_smem_raw) + (threadIdx.x >> 5) * M;
+    float4* const sm4 = reinterpret_cast<float4*>(sm);
+    typename IO::row_state const row = io.open(b);
+
+    // the whole row first (all of a thread's 128-bit loads in flight together), then the stage-1 passes
+    float4 q[BF1 / 2][R1];
+#pragma unroll
+    for (int m = 0; m < BF1 / 2; ++m) {
+        int const n = 2 * t + 2 * NT * m;
+        static_for<0, R1>([&](auto n1c) {
+            constexpr int n1 = decltype(n1c)::value;
+            if constexpr (n1 < R1 / 2) { q[m][n1] = io.template load_pair<false>(row, n + S1 * n1); }
+            else { q[m][n1] = io.template load_pair<true>(row, n + S1 * n1 - H); }
+        });
+    }
+#pragma unroll
+    for (int m = 0; m < BF1 / 2; ++m) {
+        int const n = 2 * t + 2 * NT * m;
+        float2 ua[R1], ub[R1];
+#pragma unroll
+        for (int n1 = 0; n1 < R1; ++n1) {
+            if (n1 >= R1 / 2) { io.keep_pair(row, n + S1 * n1 - H, q[m][n1]); }
+            ua[n1] = make_float2(q[m][n1].x, q[m][n1].y);
+            ub[n1] = make_float2(q[m][n1].z, q[m][n1].w);
+        }
+        wdft<R1, -1>::run(ua);
+        wdft<R1, -1>::run(ub);
+        {
+            float4 const* const ta4 = reinterpret_cast<float4 const*>(ta) + (n >> 1);
+            float2 wa[R1], wb[R1];
+#pragma unroll
+            for (int q = 1; q < R1; ++q) {
+                int const hi = 1 << (31 - __clz(q));
+                if (q == hi) {
+                    float4 const w4 = __ldg(ta4 + (31 - __clz(q)) * (XS / 2));
+                    wa[q]           = make_float2(w4.x, w4.y);
+                    wb[q]           = make_float2(w4.z, w4.w);
+                } else {
+                    wa[q] = cmul(wa[hi], wa[q - hi]);
+                    wb[q] = cmul(wb[hi], wb[q - hi]);
+                }
+                ua[q] = cmul(ua[q], wa[q]);
+                ub[q] = cmul(ub[q], wb[q]);
+            }
+        }
+        int const a2 = n >> 4, ah = (n & 15) >> 1;
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) { sm4[(k1 * R2 + a2) * 8 + (ah ^ (k1 & 7))] = make_float4(ua[k1].x, ua[k1].y, ub[k1].x, ub[k1].y); }
+    }
+    __syncwarp();
+    W::template stage2<-1>(sm, tb, t);
+    __syncwarp();
+    {
+        int const ja = t, jb = t == 0 ? J / 2 : J - t;
+        float2 const wt = __ldg(rtw + t);
+        float2 za[16], zb[16];
+        W::load_row(sm4, ja, za);
+        W::load_row(sm4, jb, zb);
+        dft<16, -1>::run(za);
+        dft<16, -1>::run(zb);
+        wide_r2c_post<M>(za, zb, t, wt, [&](int k, float2 x) { io.store(row, k, x); },
+                         [&](float dc, float nyq) { io.store_edges(row, dc, nyq); });
+    }
+}
+
+template<int LOGM, int LOGR1, int LOGR2, int G, class IO>
+__global__ void __launch_bounds__(32 * G, 512 / (32 * G))
+    c2r_wide_io_kernel(IO io, float2 const* __restrict__ ta, float2 const* __restrict__ tb, float2 const* __restrict__ rtw, size_t batch)
+{
+    using W   = wide_fft<LOGM, LOGR1, LOGR2>;
+    using cfg = wide_cfg<LOGM, LOGR1, LOGR2>;
+    constexpr int M = cfg::M, R1 = cfg::R1, R2 = cfg::R2, NT = cfg::NT, S1 = cfg::S1, J = cfg::J, BF1 = cfg::BF1, XS = cfg::XS, H = M / 2;
+    static_assert(NT == 32 && BF1 >= 2, "one warp per transform, pairs of stage-1 butterflies");
+    extern __shared__ __align__(128) unsigned char wide_smem_raw[];
+    int const t    = threadIdx.x & 31;
+    size_t const b = size_t(blockIdx.x) * G + (threadIdx.x >> 5);
+    if (b >= batch) { return; }
+    float2* const sm  = reinterpret_cast<float2*>(wide_smem_raw) + (threadIdx.x >> 5) * M;
+    float4* const sm4 = reinterpret_cast<float4*>(sm);
+    typename IO::row_state const row = io.open(b);
+    {
+        int const ja = t, jb = t == 0 ? J / 2 : J - t;
+        float2 const wt = __ldg(rtw + t);
+        float2 za[16], zb[16];
+#pragma unroll
+        for (int k3 = 0; k3 < 16; ++k3) { za[k3] = io.load(row, ja + J * k3); }  // thread 0, k3 = 0: the packed pair (Re X[0], Re X[M])
+#pragma unroll
+        for (int k3 = 0; k3 < 16; ++k3) { zb[k3] = io.load(row, jb + J * k3); }
+        float const nyq = za[0].y;  // only thread 0 uses it
+        wide_c2r_pre<M>(za, zb, t, wt, nyq);
+        dft<16, +1>::run(za);
+        dft<16, +1>::run(zb);
+        {
+            float2 w[16];
+            wide_twiddles(w, [&](int p) { return __ldg(ta + p * XS + ja); });
+#pragma unroll
+            for (int a = 1; a < 16; ++a) { za[a] = cmulc(za[a], w[a]); }
+            wide_twiddles(w, [&](int p) { return __ldg(ta + p * XS + jb); });
+#pragma unroll
+            for (int a = 1; a < 16; ++a) { zb[a] = cmulc(zb[a], w[a]); }
+        }
+        W::store_row(sm4, ja, za);
+        W::store_row(sm4, jb, zb);
+    }
+    __syncwarp();
+    W::template stage2<+1>(sm, tb, t);
+    __syncwarp();
+#pragma unroll
+    for (int m = 0; m < BF1 / 2; ++m) {
+        int const n  = 2 * t + 2 * NT * m;
+        int const a2 = n >> 4, ah = (n & 15) >> 1;
+        float2 ua[R1], ub[R1];
+#pragma unroll
+        for (int k1 = 0; k1 < R1; ++k1) {
+            float4 const q = sm4[(k1 * R2 + a2) * 8 + (ah ^ (k1 & 7))];
+            ua[k1]         = make_float2(q.x, q.y);
+            ub[k1]         = make_float2(q.z, q.w);
+        }
+        wdft<R1, +1>::run(ua);
+        wdft<R1, +1>::run(ub);
+        static_for<0, R1>([&](auto b2c) {
+            constexpr int b2 = decltype(b2c)::value;
+            if constexpr (b2 < R1 / 2) { io.template store_pair<false>(row, n + S1 * b2, ua[b2], ub[b2]); }
+            else { io.template store_pair<true>(row, n + S1 * b2 - H, ua[b2], ub[b2]); }
+        });
+    }
+}
+
+template<int LOGM, int LOGR1, int LOGR2, class IO>
+int launch_r2c_wide_io(IO const& io, float2 const* ta, float2 const* tb, float2 const* rtw, size_t batch, cudaStream_t stream)
+{
+    using cfg       = wide_cfg<LOGM, LOGR1, LOGR2>;
+    constexpr int G = 4;
+    if (batch == 0) { return NEO_B200_OK; }
+    auto kernel = r2c_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO>;
+    NEO_TRY(enable_smem(kernel, G * cfg::SMEM));
+    kernel<<<unsigned((batch + G - 1) / G), 32 * G, G * cfg::SMEM, stream>>>(io, ta, tb, rtw, batch);
+    return check_launch("r2c_wide_io_kernel");
+}
+
+template<int LOGM, int LOGR1, int LOGR2, class IO>
+int launch_c2r_wide_io(IO const& io, float2 const* ta, float2 const* tb, float2 const* rtw, size_t batch, cudaStream_t stream)
+{
+    using cfg       = wide_cfg<LOGM, LOGR1, LOGR2>;
+    constexpr int G = 4;
+    if (batch == 0) { return NEO_B200_OK; }
+    auto kernel = c2r_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO>;
+    NEO_TRY(enable_smem(kernel, G * cfg::SMEM));
+    kernel<<<unsigned((batch + G - 1) / G), 32 * G, G * cfg::SMEM, stream>>>(io, ta, tb, rtw, batch);
+    return check_launch("c2r_wide_io_kernel");
 }
 
 // ---- tables + launchers --------------------------------------------------------------------------------------------------------------
