@@ -200,7 +200,14 @@ struct wide_cfg
     static constexpr int LOGP    = LOGR1 > 4 ? LOGR1 : 4;  // rows of the power-of-two twiddle table
     static constexpr int XS      = S1 > J ? S1 : J;        // its row length
     static constexpr size_t SMEM    = size_t(M) * sizeof(float2);              // the tile
-    static constexpr size_t SMEM_PF = SMEM + size_t(3 * M / 4) * sizeof(float2);  // + the staging buffer of the prefetching kernels
+    // prefetching kernels: tile + staging buffer + the stage-2 twiddle table, 7/4 of the tile in total. The staging buffer holds the
+    // first ST elements of the next row (a whole number of stage-1 input segments / stage-3 rows), the table sits behind it
+    static constexpr int TB_FWD     = R2 * 16;   // W_(16 R2)^(a k2)
+    static constexpr int TB_BWD     = R1 * R2;   // W_(R1 R2)^(a2 k1)
+    static constexpr int ST_FWD     = 3 * M / 4 - TB_FWD;
+    static constexpr int ST_BWD     = 3 * M / 4 - TB_BWD;
+    static constexpr size_t SMEM_PF = SMEM + size_t(3 * M / 4) * sizeof(float2);
+    static_assert(ST_FWD % S1 == 0 && ST_BWD % J == 0, "staging boundary between two stage-1 inputs / two stage-3 rows");
     static_assert(NT % 32 == 0, "whole warps");
 };
 
@@ -295,9 +302,11 @@ struct wide_fft
 
     // stage 2 / 2': DFT_R2 along x of tile (k1, x, a), in place. tb: forward [R2][16] = W_(16 R2)^(a k2); backward [R1][R2] =
     // W_(R1 R2)^(a2 k1) (applied conjugated)
-    template<int DIR>
+    // TB_SHARED: tb points into shared memory (the persistent kernels copy the table once per CTA)
+    template<int DIR, bool TB_SHARED = false>
     static __device__ __forceinline__ void stage2(float2* sm, float2 const* __restrict__ tb, int t)
     {
+        auto const tw = [&](int i) { return TB_SHARED ? tb[i] : __ldg(tb + i); };
 #pragma unroll
         for (int m = 0; m < BF2; ++m) {
             int const beta = t + NT * m;
@@ -309,10 +318,10 @@ struct wide_fft
             wdft<R2, DIR>::run(u);
             if constexpr (DIR < 0) {
 #pragma unroll
-                for (int k2 = 1; k2 < R2; ++k2) { u[k2] = cmul(u[k2], __ldg(tb + k2 * 16 + a)); }
+                for (int k2 = 1; k2 < R2; ++k2) { u[k2] = cmul(u[k2], tw(k2 * 16 + a)); }
             } else {
 #pragma unroll
-                for (int a2 = 1; a2 < R2; ++a2) { u[a2] = cmulc(u[a2], __ldg(tb + k1 * R2 + a2)); }
+                for (int a2 = 1; a2 < R2; ++a2) { u[a2] = cmulc(u[a2], tw(k1 * R2 + a2)); }
             }
 #pragma unroll
             for (int x = 0; x < R2; ++x) { p[x * 16] = u[x]; }
@@ -346,10 +355,9 @@ struct wide_fft
 // transformed. Its first three quarters go into a staging buffer behind the tile as soon as stage 1 has taken this row's inputs
 // (a whole row time ahead: at the SM's fair share of the HBM bandwidth a row needs about that long); the last quarter goes into the
 // tile itself, which is idle from the stage-3 loads on. Both copies signal one mbarrier (two arrivals per phase).
-template<int M>
+template<int M, int ST>  // ST: complex elements of a row kept in the staging buffer; the rest sits at the tile's start
 struct wide_stage
 {
-    static constexpr int ST = 3 * M / 4;  // complex elements of a row kept in the staging buffer; the rest sits at the tile's start
     static constexpr unsigned EARLY = unsigned(ST) * 8U, LATE = unsigned(M - ST) * 8U;
     float2* tile;
     float2* stage;
@@ -378,11 +386,13 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
     int const t       = threadIdx.x;
     __shared__ __align__(8) unsigned long long bar;
     unsigned parity = 0;
-    wide_stage<M> const st{sm, sm + M};
+    using stage_t = wide_stage<M, cfg::ST_FWD>;
+    stage_t const st{sm, sm + M};
+    float2* const tbs = sm + M + cfg::ST_FWD;  // stage-2 twiddles in shared memory (PF)
     auto const zrow = [&](size_t row) { return reinterpret_cast<float2 const*>(in) + row * size_t(M); };
     if constexpr (PF) {
         static_assert(!PF || BF1 == 2 || BF1 == 1, "one pass over the staged row");
-        static_assert((3 * R1) % 4 == 0, "the staging boundary falls between two stage-1 inputs");
+        for (int i = t; i < cfg::TB_FWD; i += NT) { tbs[i] = __ldg(tb + i); }
         if (t == 0) {
             wtma::init(&bar, 2);
             if (blockIdx.x < batch) {
@@ -406,7 +416,7 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
                     parity ^= 1U;
                     static_for<0, R1>([&](auto n1c) {
                         constexpr int n1 = decltype(n1c)::value;
-                        float4 const q = *reinterpret_cast<float4 const*>(st.template at<(n1 * S1 >= wide_stage<M>::ST)>(n + n1 * S1));
+                        float4 const q = *reinterpret_cast<float4 const*>(st.template at<(n1 * S1 >= cfg::ST_FWD)>(n + n1 * S1));
                         ua[n1]         = make_float2(q.x, q.y);
                         ub[n1]         = make_float2(q.z, q.w);
                     });
@@ -455,7 +465,7 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
                 parity ^= 1U;
                 static_for<0, R1>([&](auto n1c) {
                     constexpr int n1 = decltype(n1c)::value;
-                    u[n1]            = *st.template at<(n1 * S1 >= wide_stage<M>::ST)>(n + n1 * S1);
+                    u[n1]            = *st.template at<(n1 * S1 >= cfg::ST_FWD)>(n + n1 * S1);
                 });
                 __syncthreads();
                 if (t == 0 && more) { st.fetch_early(zrow(b + gridDim.x), &bar); }
@@ -481,7 +491,8 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
         }
         __syncthreads();
         // ---- stage 2, in place
-        W::template stage2<-1>(sm, tb, t);
+        if constexpr (PF) { W::template stage2<-1, true>(sm, tbs, t); }
+        else { W::template stage2<-1>(sm, tb, t); }
         __syncthreads();
         // ---- stage 3 + Hermitian split in registers
         {
@@ -523,13 +534,17 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
     int const t       = threadIdx.x;
     __shared__ __align__(8) unsigned long long bar;
     unsigned parity = 0;
-    wide_stage<M> const st{sm, sm + M};
+    using stage_t = wide_stage<M, cfg::ST_BWD>;
+    stage_t const st{sm, sm + M};
+    float2* const tbs = sm + M + cfg::ST_BWD;
+    constexpr int K3T = cfg::ST_BWD / J;  // stage-3 inputs k3 >= K3T sit in the tile, the others in the staging buffer
     // first bin of row `row` that sits on a 16-byte boundary
     auto const xrow = [&](size_t row) {
         float2 const* const x = in + row * row_len;
         return x + ((reinterpret_cast<std::uintptr_t>(x) >> 3) & 1U);
     };
     if constexpr (PF) {
+        for (int i = t; i < cfg::TB_BWD; i += NT) { tbs[i] = __ldg(tb + i); }
         if (t == 0) {
             wtma::init(&bar, 2);
             if (blockIdx.x < batch) {
@@ -556,12 +571,12 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
                 wtma::wait(&bar, parity);
                 parity ^= 1U;
                 // bin k sits at staged element k - lo. For t > 0 both ja + J k3 - lo and jb + J k3 - lo stay inside [J k3, J (k3 + 1)),
-                // so the region follows from k3 alone (the staging boundary 3M/4 = 12 J)
+                // so the region follows from k3 alone (the staging boundary is K3T J)
                 if (t != 0) {
                     static_for<0, 16>([&](auto k3c) {
                         constexpr int k3 = decltype(k3c)::value;
-                        za[k3]           = *st.template at<(k3 >= 12)>(ja + J * k3 - lo);
-                        zb[k3]           = *st.template at<(k3 >= 12)>(jb + J * k3 - lo);
+                        za[k3]           = *st.template at<(k3 >= K3T)>(ja + J * k3 - lo);
+                        zb[k3]           = *st.template at<(k3 >= K3T)>(jb + J * k3 - lo);
                     });
                 } else {
 #pragma unroll
@@ -597,7 +612,8 @@ __global__ void __launch_bounds__(wide_cfg<LOGM, LOGR1, LOGR2>::NT, MINCTAS)
         }
         __syncthreads();
         // ---- stage 2', in place
-        W::template stage2<+1>(sm, tb, t);
+        if constexpr (PF) { W::template stage2<+1, true>(sm, tbs, t); }
+        else { W::template stage2<+1>(sm, tb, t); }
         __syncthreads();
         // ---- stage 1'
         if constexpr (BF1 >= 2) {
@@ -660,18 +676,20 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
     using cfg = wide_cfg<LOGM2, LOGR1, LOGR2>;
     constexpr int M2 = cfg::M, M = 2 * M2, R1 = cfg::R1, R2 = cfg::R2, S1 = cfg::S1, J = cfg::J, XS = cfg::XS;
     static_assert(cfg::BF1 == 1 && R1 == 32, "one radix-32 butterfly per thread in stage 1");
-    constexpr int ST = wide_stage<M2>::ST;  // staged part of the second half
-    constexpr int NG = (M2 - ST) / S1;      // inputs per thread that come by ordinary loads
+    constexpr int ST = cfg::ST_FWD;      // staged part of the second half
+    constexpr int NG = (M2 - ST) / S1;   // inputs per thread that come by ordinary loads
     extern __shared__ __align__(128) unsigned char wide_smem_raw[];
     float2* const sm  = reinterpret_cast<float2*>(wide_smem_raw);
     float4* const sm4 = reinterpret_cast<float4*>(wide_smem_raw);
     float2* const stg = sm + M2;
+    float2* const tbs = stg + ST;  // stage-2 twiddles
     int const t       = threadIdx.x;
     int const r       = blockIdx.x & 1;
     __shared__ __align__(8) unsigned long long bar;
     unsigned parity = 0;
     size_t const units = 2 * batch;  // (row, parity), parity fastest: gridDim.x is even, so a CTA keeps its parity
     auto const zrow = [&](size_t unit) { return reinterpret_cast<float2 const*>(in) + (unit >> 1) * size_t(M); };
+    for (int i = t; i < cfg::TB_FWD; i += cfg::NT) { tbs[i] = __ldg(tb + i); }
     if (t == 0) {
         wtma::init(&bar, 2);
         if (blockIdx.x < units) {
@@ -720,7 +738,7 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
             for (int k1 = 0; k1 < R1; ++k1) { sm[(k1 * R2 + a2) * 16 + ((((a >> 1) ^ (k1 & 7)) << 1) | (a & 1))] = u[k1]; }
         }
         __syncthreads();
-        W::template stage2<-1>(sm, tb, t);
+        W::template stage2<-1, true>(sm, tbs, t);
         __syncthreads();
         {
             int const ja = t, jb = r ? J - 1 - t : (t == 0 ? J / 2 : J - t);
@@ -764,16 +782,19 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
     using cfg = wide_cfg<LOGM2, LOGR1, LOGR2>;
     constexpr int M2 = cfg::M, M = 2 * M2, R1 = cfg::R1, R2 = cfg::R2, S1 = cfg::S1, J = cfg::J, XS = cfg::XS;
     static_assert(cfg::BF1 == 1 && R1 == 32, "one radix-32 butterfly per thread in stage 1'");
-    constexpr int ST = wide_stage<M2>::ST;
+    constexpr int ST  = cfg::ST_BWD;
+    constexpr int K3T = ST / J;  // second-half bins with k3 >= K3T lie beyond the staged window
     extern __shared__ __align__(128) unsigned char wide_smem_raw[];
     float2* const sm  = reinterpret_cast<float2*>(wide_smem_raw);
     float4* const sm4 = reinterpret_cast<float4*>(wide_smem_raw);
     float2* const stg = sm + M2;
+    float2* const tbs = stg + ST;
     int const t       = threadIdx.x;
     int const r       = blockIdx.x & 1;
     __shared__ __align__(8) unsigned long long bar;
     unsigned parity = 0;
     size_t const units = 2 * batch;
+    for (int i = t; i < cfg::TB_BWD; i += cfg::NT) { tbs[i] = __ldg(tb + i); }
     // first bin of a unit's row that sits on a 16-byte boundary
     auto const xrow = [&](size_t unit) {
         float2 const* const x = in + (unit >> 1) * row_len;
@@ -799,10 +820,10 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
             float2 const wt = __ldg(rtw + t);
             // xa[k3] = X[k2], xb[15-k3] = X[M2-k2], ya[k3] = X[M2+k2], yb[15-k3] = X[M-k2]   (k2 = ja + J k3; row jb = J - ja)
             float2 xa[16], xb[16], ya[16], yb[16];
-            // ordinary loads first: the bins beyond the staged window (k - lo >= M2 + ST  <=>  k3 >= 12 of the second half)
+            // ordinary loads first: the bins beyond the staged window (k - lo >= M2 + ST  <=>  k3 >= K3T of the second half)
             if (t != 0) {
 #pragma unroll
-                for (int k3 = 12; k3 < 16; ++k3) {
+                for (int k3 = K3T; k3 < 16; ++k3) {
                     ya[k3] = __ldcs(x + M2 + ja + J * k3);
                     yb[k3] = __ldcs(x + M2 + jb + J * k3);
                 }
@@ -814,7 +835,7 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
                     constexpr int k3 = decltype(k3c)::value;
                     xa[k3]           = sm[ja + J * k3 - lo];
                     xb[k3]           = sm[jb + J * k3 - lo];
-                    if constexpr (k3 < 12) {
+                    if constexpr (k3 < K3T) {
                         ya[k3] = stg[ja + J * k3 - lo];
                         yb[k3] = stg[jb + J * k3 - lo];
                     }
@@ -907,7 +928,7 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
             W::store_row(sm4, jb, zb);
         }
         __syncthreads();
-        W::template stage2<+1>(sm, tb, t);
+        W::template stage2<+1, true>(sm, tbs, t);
         __syncthreads();
         {
             int const n = t, a = n & 15, a2 = n >> 4;
