@@ -93,6 +93,7 @@ struct conv_engine
     int x1_half{0};  // half of x1 the current call writes
     fft_tables<T> frame_tables;
     device_buffer frame_tw8;  // stage twiddles of the 8-points-per-thread variant of the long frame transforms
+    device_buffer frame_tw32; // ... and of the 32-points-per-thread form (float, L = 512 / 1024)
     device_buffer fdl2, filter2, acc2, tickets2, nyq_acc;
     bool fused{false};  // bank with an unsplit partition loop: one kernel per frame step (frame_fused_kernel)
     // set by a multi-device bank before forward_mac (frame_fused_io::y1_owner): where the result rows of each owner's channels go
@@ -244,6 +245,12 @@ struct conv_engine
             splits2       = pick_splits(sms, m2, size_t(parts2));
             NEO_TRY(frame_tables.build(logl, false, stream));
             knobs = frame_knobs::from_env();
+            if (knobs.wide_points(logl, sizeof(T) == 4)) {
+                auto const tw = make_stage_twiddles<T>(logl, 5);
+                NEO_TRY(frame_tw32.reserve(tw.size() * csz));
+                NEO_CUDA_TRY(cudaMemcpyAsync(frame_tw32.ptr, tw.data(), tw.size() * csz, cudaMemcpyHostToDevice, stream));
+                NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+            }
             if (knobs.eight_points(logl, sizeof(T) == 4)) {
                 auto const tw = make_stage_twiddles<T>(logl, 3);
                 NEO_TRY(frame_tw8.reserve(tw.size() * csz));
@@ -490,12 +497,13 @@ struct conv_engine
             frame_fused_io<T, true> nq{fdl.template as<cx<T>>(), fdl2.template as<cx<T>>(), filter2.template as<cx<T>>(),
                                        acc_w(), nyq_acc.template as<cx<T>>(), fg, x1_half, ring2, int(write_pos2),
                                        parts2, int(age0 / size_t(frame)), T(1) / T(2 * frame), out0, {}, 0, 0};
-            status = launch_frame_fused<T, LOGL, true>(nq, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout, stream, knobs);
+            status = launch_frame_fused<T, LOGL, true>(nq, frame_tables.tw(), frame_tw8.template as<cx<T>>(), frame_tw32.template as<cx<T>>(), nout, stream, knobs);
             if (status == NEO_B200_OK) {
                 frame_fused_io<T, false> io{nq.x1, nq.fdl2, nq.filt2, nq.y1, nq.nyq_acc, fg, nq.new_half, nq.ring2, nq.slot,
                                             nq.parts2, nq.age0, nq.scale, out0, {}, push_owners, push_own_count};
                 for (int o = 0; o < push_owners; ++o) { io.y1_owner[o] = push_dst[o]; }
-                status = launch_frame_fused<T, LOGL, false>(io, frame_tables.tw(), frame_tw8.template as<cx<T>>(), nout << logb, stream, knobs);
+                status = launch_frame_fused<T, LOGL, false>(io, frame_tables.tw(), frame_tw8.template as<cx<T>>(), frame_tw32.template as<cx<T>>(), nout << logb,
+                                                           stream, knobs);
             }
         });
         if (status != NEO_B200_OK) { return status; }

@@ -27,6 +27,7 @@
 #pragma once
 
 #include "conv_kernels.cuh"
+#include "fft_wide.cuh"
 
 #include <cstdlib>
 
@@ -274,6 +275,8 @@ struct frame_knobs
         return k;
     }
     bool eight_points(int logl, bool is_f32) const { return is_f32 && logl >= 8 && (variant == 2 || variant == 3 || variant == 4); }
+    // 32 points per thread (float, L = 512 / 1024): two register stages and ONE exchange per frame transform, 256 / 512 threads
+    bool wide_points(int logl, bool is_f32) const { return is_f32 && logl >= 9 && logl <= 10 && (variant == 5 || variant < 0); }
 };
 
 template<typename T, int LOGL, int DIR, typename IO>
@@ -347,10 +350,13 @@ template<typename T, int LOGL, int LOGG, int LOGE_F>
 struct frame_async_cfg
 {
     using cfg                      = frame_cfg<T, LOGL, LOGG, LOGE_F>;
-    static constexpr int CH        = cfg::E >= 2 ? cfg::E / 2 : 1;                                 // points per thread and chunk
+    // points per thread and chunk: half a thread's points; 4 with 32 points per thread, so that tile + two stages stay under half an
+    // SM's shared memory and two CTAs are resident
+    static constexpr int CH        = cfg::E >= 32 ? 4 : cfg::E >= 2 ? cfg::E / 2 : 1;
     static constexpr int NH        = cfg::E / CH;                                                  // chunks per partition
     static constexpr int OPERAND   = CH * cfg::TN * cfg::G * int(sizeof(cx<T>));                   // bytes of one operand of a chunk
     static constexpr int STAGE     = 2 * OPERAND;                                                  // <= the exchange tile
+    static constexpr int NS        = 2 + int(cfg::SMEM) / STAGE;                                   // stages: two private + those the idle tile holds
     static constexpr size_t SMEM   = cfg::SMEM + 2 * size_t(STAGE);
     static constexpr int PER_THREAD = OPERAND / 16 / cfg::THREADS;                                 // 16-byte pieces per thread
     static constexpr int ROW_PIECES = cfg::G * int(sizeof(cx<T>)) / 16;                            // pieces per group of bins
@@ -396,9 +402,9 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
 
     // ---- ASYNC: chunk c = (partition q = c / NH, half eh = c % NH of the thread's points); stage = c % 3 ----
     using ac = frame_async_cfg<T, LOGL, LOGG, LOGE_F>;
-    auto const stage_ptr = [&](int c) -> unsigned char* {  // stage 2 is the exchange tile
-        int const st = c % 3;
-        return st == 2 ? smem_raw : smem_raw + cfg::SMEM + st * ac::STAGE;
+    auto const stage_ptr = [&](int c) -> unsigned char* {  // stages 2 .. NS-1 lie in the exchange tile
+        int const st = c % ac::NS;
+        return st >= 2 ? smem_raw + (st - 2) * ac::STAGE : smem_raw + cfg::SMEM + st * ac::STAGE;
     };
     int const nchunks = io.parts2 * ac::NH;
     // Warp-private staging: a warp copies exactly the rows its own threads will read (its TW = 32/G values of t, all CH points u of
@@ -459,14 +465,48 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
         else if (k == 0) { v[e].y = T(0); }
     }
     cta_fft<T, LOGL, -1, LOGE_F>::run(v, sm, tw, t);
-    issue(2);  // the exchange tile is free until the inverse transform
+    if constexpr (ASYNC) {  // the exchange tile is free until the inverse transform
+#pragma unroll
+        for (int c = 2; c < ac::NS; ++c) { issue(c); }
+    }
     if (live) {
 #pragma unroll
         for (int e = 0; e < E; ++e) { ring[at(t + e * TN, io.slot, io.ring2)] = v[e]; }
     }
 
     // MAC over the local partitions q (row q of the filter pairs with the frame spectrum of age0 + q frames ago)
-    if constexpr (ASYNC) {
+    if constexpr (ASYNC && E >= 32) {
+        // 32 points per thread: the sum is formed IN PLACE (partition 0 overwrites the frame spectrum it has just consumed), so one
+        // array of E values is live, not two, and the kernel keeps to 128 registers. Same products in the same order as below.
+        for (int q = 0; q < io.parts2; ++q) {
+            bool const first = q == 0;
+            bool const own   = first && newest_in_regs;
+#pragma unroll
+            for (int eh = 0; eh < ac::NH; ++eh) {
+                int const c = q * ac::NH + eh;
+                frame_cp_async_wait<ac::NS - 1>();
+                __syncwarp();
+                C const* const sh = reinterpret_cast<C const*>(stage_ptr(c));
+                C const* const sx = reinterpret_cast<C const*>(stage_ptr(c) + ac::OPERAND);
+#pragma unroll
+                for (int u = 0; u < ac::CH; ++u) {
+                    int const e = eh * ac::CH + u;
+                    C const h   = sh[(u * TN + t) * cfg::G + gi];
+                    C const x   = own ? v[e] : sx[(u * TN + t) * cfg::G + gi];
+                    C acc       = first ? mk<T>(T(0), T(0)) : v[e];
+                    acc.x       = ::fma(x.x, h.x, acc.x);
+                    acc.x       = ::fma(-x.y, h.y, acc.x);
+                    acc.y       = ::fma(x.x, h.y, acc.y);
+                    acc.y       = ::fma(x.y, h.x, acc.y);
+                    v[e]        = acc;
+                }
+                __syncwarp();
+                issue(c + ac::NS);
+            }
+        }
+        frame_cp_async_wait<0>();
+        __syncthreads();  // stage 2 is the exchange tile the inverse transform is about to write
+    } else if constexpr (ASYNC) {
         C a[E];
 #pragma unroll
         for (int e = 0; e < E; ++e) { a[e] = mk<T>(T(0), T(0)); }
@@ -475,7 +515,7 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
 #pragma unroll
             for (int eh = 0; eh < ac::NH; ++eh) {
                 int const c = q * ac::NH + eh;
-                frame_cp_async_wait<2>();  // chunks are committed in order, one group each: chunk c has landed
+                frame_cp_async_wait<ac::NS - 1>();  // chunks are committed in order, one group each: chunk c has landed
                 __syncwarp();              // ... for every lane of this warp, which copied all the rows the warp reads
                 C const* const sh = reinterpret_cast<C const*>(stage_ptr(c));
                 C const* const sx = reinterpret_cast<C const*>(stage_ptr(c) + ac::OPERAND);
@@ -490,7 +530,7 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
                     a[e].y      = ::fma(x.y, h.x, a[e].y);
                 }
                 __syncwarp();  // every lane is done with this warp's rows of the stage
-                issue(c + 3);
+                issue(c + ac::NS);
             }
         }
         frame_cp_async_wait<0>();
@@ -808,13 +848,24 @@ int launch_frame_fused_g(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, size
     }
 }
 
-// tw: stage twiddles of the transform's default points per thread; tw8: of the 8-points-per-thread variants (only when knobs ask)
+// tw: stage twiddles of the transform's default points per thread; tw8: of the 8-points-per-thread variants (only when knobs ask);
+// tw32: of the 32-points-per-thread form (float, L = 512 / 1024)
 template<typename T, int LOGL, bool NYQ>
-int launch_frame_fused(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, cx<T> const* tw8, size_t units, cudaStream_t stream,
-                       frame_knobs const& knobs)
+int launch_frame_fused(frame_fused_io<T, NYQ> const& io, cx<T> const* tw, cx<T> const* tw8, cx<T> const* tw32, size_t units,
+                       cudaStream_t stream, frame_knobs const& knobs)
 {
     constexpr int g0 = frame_default_logg<T, LOGL>();
     bool const a     = knobs.async;
+    if constexpr (sizeof(T) == 4 && LOGL >= 9 && LOGL <= 10) {
+        // 32 points per thread: two register stages and ONE exchange per frame transform, the sum over the partitions formed in place,
+        // 16 bins x L/32 threads per CTA -- two resident CTAs at L = 512, so one unit's transforms run under the other's MAC stream.
+        // measured (C5 geometry, ms per fused step, this form / 16 points per thread): T=256 Q=2 4.44 / 5.05, T=512 Q=2 9.09 / 11.1,
+        // T=256 Q=4 7.29 / 6.53 (its MAC chunks are a quarter of the size: the longer the MAC stream, the more that costs)
+        bool const wins = LOGL >= 10 || io.parts2 <= 2;
+        if (knobs.variant == 5 || (knobs.variant < 0 && a && wins && tw32 != nullptr)) {
+            return launch_frame_fused_g<T, LOGL, 4, 5, 128, NYQ>(io, tw32, units, stream, a);
+        }
+    }
     if constexpr (sizeof(T) == 4 && LOGL >= 8) {
         constexpr int g16 = LOGL >= 10 ? 3 : 4;  // 16 points per thread: 2^(LOGL-4) threads per bin, <= 512 threads per CTA
         switch (knobs.variant) {

@@ -174,6 +174,13 @@ struct dft32
     }
 };
 
+// the same butterfly under the name cta_fft looks up (float only): lets cta_fft run with 32 points per thread
+template<int DIR>
+struct dft<32, DIR>
+{
+    static __device__ __forceinline__ void run(float2* u) { dft32<DIR>::run(u); }
+};
+
 template<int R, int DIR>
 struct wdft
 {

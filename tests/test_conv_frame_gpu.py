@@ -243,7 +243,8 @@ def test_frame_mode_full_size_north_star_shape(gpu, orc):
 
 
 @pytest.mark.parametrize("knob,value", [(None, None), ("NEO_B200_FRAME_NO_ASYNC", "1"), ("NEO_B200_FRAME_VARIANT", "1"),
-                                        ("NEO_B200_FRAME_VARIANT", "2"), ("NEO_B200_FRAME_VARIANT", "3"), ("NEO_B200_FRAME_VARIANT", "4")])
+                                        ("NEO_B200_FRAME_VARIANT", "2"), ("NEO_B200_FRAME_VARIANT", "3"), ("NEO_B200_FRAME_VARIANT", "4"),
+                                        ("NEO_B200_FRAME_VARIANT", "5")])
 def test_fused_frame_kernel_geometries_at_long_frames(gpu, orc, monkeypatch, knob, value):
     # L = 256 and L = 512 frame transforms: the shipped geometry (16 points per thread, cp.async-staged MAC) and the alternatives the
     # knobs select when the handle is created (tuning knobs) must all reproduce the reference
@@ -257,6 +258,21 @@ def test_fused_frame_kernel_geometries_at_long_frames(gpu, orc, monkeypatch, kno
         got = run_bank(conv, sig, B, [T])
         assert rel_l2(got, orc.convolve_blocks(0, H, sig)) <= 1e-5, (knob, value, T)
         conv.close()
+
+
+@pytest.mark.parametrize("variant", ["0", "5"])
+@pytest.mark.parametrize("B,P,T,frames,channels", [(128, 600, 256, 3, 2), (128, 1100, 512, 2, 2), (16, 1500, 256, 7, 3)])
+def test_fused_frame_kernel_32_points_per_thread_several_partitions(gpu, orc, monkeypatch, variant, B, P, T, frames, channels):
+    # L = 512 / 1024 frame transforms with 32 points per thread (two register stages, one exchange, the sum over the second-level
+    # partitions formed in place): Q = 3, 3 and 6 second-level partitions, ring wrap, ragged last partition
+    monkeypatch.setenv("NEO_B200_FRAME_VARIANT", variant)
+    ir, sig = make_case(orc, channels, B * P - 5, B, T * frames)
+    H = orc.uniform_partition(ir, B)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, frame_blocks=T)
+    conv.filter(H)
+    got = run_bank(conv, sig, B, [T])
+    conv.close()
+    assert rel_l2(got, orc.convolve_blocks(0, H, sig)) <= 1e-5, (variant, T)
 
 
 def test_frame_mode_three_kernel_form_for_banks(gpu, orc, monkeypatch):
