@@ -467,6 +467,30 @@ def build_conv(pkg, torch, stream, T, frame, channels=CHANNELS, first=0):
     return conv
 
 
+def host_link_probe(torch, hx, hy, iters: int = 3):
+    """GB/s per direction of pinned H2D + D2H copies running at the same time (the bound of every e2e number here)"""
+    dx, dy = torch.empty(hx.shape, dtype=hx.dtype, device="cuda"), torch.empty(hy.shape, dtype=hy.dtype, device="cuda")
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    best = 0.0
+    for _ in range(iters):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        s1.wait_event(e0)
+        s2.wait_event(e0)
+        with torch.cuda.stream(s1):
+            dx.copy_(hx, non_blocking=True)
+        with torch.cuda.stream(s2):
+            hy.copy_(dy, non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s1)
+        torch.cuda.current_stream().wait_stream(s2)
+        e1.record()
+        torch.cuda.synchronize()
+        best = max(best, hx.numel() * hx.element_size() / (e0.elapsed_time(e1) * 1e-3) / 1e9)
+    del dx, dy
+    return best
+
+
 def e2e_host(conv, hx, hy, steps):
     """the C-ABI call a reference-side caller makes: HOST buffers in, HOST buffers out, returns when hy holds the result"""
     T = hx.shape[1] // BLOCK
@@ -522,6 +546,11 @@ def run_single(args, pkg, torch, emit, peak, peak_src):
     io_bytes = CHANNELS * T * BLOCK * 4
     e2e = {"value": e2e_pinned, "unit": UNIT, "h2d_bytes_per_step": io_bytes, "d2h_bytes_per_step": io_bytes, "steps": n_e2e,
            "host_memory": "pinned", "blocks_per_call": T}
+    # what bounds it: the host link with both directions busy (plain pinned copies of the same buffers, no kernels)
+    link = host_link_probe(torch, hx, hy)
+    e2e["host_link"] = {"both_directions_gbs_each": link, "achieved_gbs_each": e2e_pinned * 1e6 * 4 / 1e9,
+                        "what": "cudaMemcpyAsync H2D and D2H of the step's 1 GiB buffers on two streams at once, GB/s per direction; "
+                                "e2e moves the same bytes, so achieved / both_directions is its fraction of the link"}
     del hx, hy, px, py
 
     # ---- roofline of the dominant kernel (spectral MAC), from the event-timed launches inside the timed region ----
