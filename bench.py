@@ -557,7 +557,8 @@ def run_single(args, pkg, torch, emit, peak, peak_src):
     if frame > 0:
         q = (PARTS + T - 1) // T
         alg_bytes_launch = CHANNELS * frame_bytes_per_channel(T, q)
-        kernel_name = f"frame_fused_kernel<float, LOGL={(2 * T).bit_length() - 1}> (frame transform + ring insert + MAC + inverse frame transform)"
+        kernel_name = (f"frame_fused_kernel<float, LOGL={(2 * T).bit_length() - 1}{', 32 points per thread' if T >= 512 or (T == 256 and q <= 2) else ''}>"
+                       " (frame transform + ring insert + MAC + inverse frame transform)")
     else:
         alg_bytes_launch = CHANNELS * direct_bytes_per_channel(T, PARTS)
         kernel_name = "fdl_mac_stream_kernel<float>" if T == 1 else f"fdl_mac_tma_kernel (T={T})"
@@ -772,7 +773,8 @@ def measure_layout(args, pkg, torch, dist, rank, world, local, layout, T, frame,
         whole, traffic_src = ncu_traffic(f"frame_fused_T{T}_G1")
         traffic = whole * info["group_count"] // CHANNELS if whole is not None else None
     res["roofline"] = {
-        "kernel": ("frame_fused_pipelined_kernel<float>" if q_local <= 2 else "frame_fused_kernel<float>") if frame > 0 else "fdl_mac kernel",
+        "kernel": (("frame_fused_kernel<float, 32 points per thread>" if q_local <= 2 or T >= 512 else "frame_fused_kernel<float>") if T >= 256
+                   else "frame_fused_kernel<float>") if frame > 0 else "fdl_mac kernel",
         "bound": "hbm", "unit": "GB/s", "peak": peak, "peak_source": peak_src,
         "achieved": alg / (mac_ms * 1e-3) / 1e9 if mac_ms > 0 else 0.0, "frac": (alg / (mac_ms * 1e-3) / 1e9 / peak) if mac_ms > 0 else 0.0,
         "algorithmic_bytes_per_launch": alg, "launch_ms": mac_ms, "rank": rank,
