@@ -246,6 +246,16 @@ NEO_B200_API void neo_b200_conv_destroy(neo_b200_conv* conv);
  * (window, FDL, write position). H: DIAGONAL [outputs][P][block+1], MATRIX [outputs][inputs][P][block+1] complex,
  * P = config.partitions; a sharded handle reads only its own partition range from it. */
 NEO_B200_API int neo_b200_conv_set_filter(neo_b200_conv* conv, void const* H, int memspace);
+/* `sparse_filter::filter(partitions, sparsity)` (sparse_filter.hpp:25-28, behind sparse_upols_convolver / sparse_upola_convolver,
+ * sparse_convolver.hpp:14-22): the filters of a DIAGONAL bank as the CSR matrices neo::csr_matrix builds from the partitions and
+ * the caller's sparsity predicate (container/csr_matrix.hpp:64-98): rows = partitions, columns = the block+1 bins, stored elements
+ * in row-major order. Filter f owns entries [filter_base[f], filter_base[f+1]) of `values` (complex) and `cols`; row_ptr[f*(P+1)+p]
+ * is relative to filter_base[f]; filter_base has outputs+1 entries. All four arrays in HOST memory (the predicate is host code).
+ * The device keeps only the stored elements (a bitmap form of the same matrix: 32-bin presence words + packed values) and the MAC
+ * touches only them (algorithm/multiply_add.hpp:306-324), skipping the delay-line rows of empty 32-bin segments as well.
+ * Direct form only (frame_blocks = 0), unsharded partitions. Zeroes all state like neo_b200_conv_set_filter. */
+NEO_B200_API int neo_b200_conv_set_filter_csr(neo_b200_conv* conv, void const* values, uint64_t const* cols, uint64_t const* row_ptr,
+                                              uint64_t const* filter_base);
 /* same, starting from time-domain impulse responses [filters][taps] (uniform_partition fused in, on the device) */
 NEO_B200_API int neo_b200_conv_set_impulse(neo_b200_conv* conv, void const* ir, size_t taps, int memspace);
 /* zero window / FDL / write position, keep the filter */

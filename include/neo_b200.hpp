@@ -15,6 +15,7 @@
 #include <cmath>
 #include <complex>
 #include <cstddef>
+#include <cstdint>
 #include <algorithm>
 #include <stdexcept>
 #include <string>
@@ -485,12 +486,31 @@ struct convolver_bank
         detail::check(neo_b200_conv_set_filter(_conv, h, memspace));
     }
 
+    /// diagonal bank with sparse filters: the CSR matrices of neo::csr_matrix (csr_matrix.hpp:64-98), see neo_b200_conv_set_filter_csr
+    auto filter_csr(complex_type const* values, std::uint64_t const* cols, std::uint64_t const* row_ptr, std::uint64_t const* filter_base,
+                    size_type outputs, size_type partitions, size_type bins, size_type max_blocks = 1) -> void
+    {
+        neo_b200_conv_destroy(std::exchange(_conv, nullptr));
+        _cfg            = neo_b200_conv_config{};
+        _cfg.kind       = Kind;
+        _cfg.dtype      = detail::dtype_of<Float>;
+        _cfg.topology   = NEO_B200_DIAGONAL;
+        _cfg.outputs    = outputs;
+        _cfg.inputs     = outputs;
+        _cfg.block      = bins - 1;
+        _cfg.partitions = partitions;
+        _cfg.max_blocks = max_blocks;
+        detail::check(neo_b200_conv_create(&_conv, &_cfg));
+        detail::check(neo_b200_conv_set_filter_csr(_conv, values, cols, row_ptr, filter_base));
+    }
+
     auto process(Float const* in, Float* out, size_type blocks, int memspace = NEO_B200_HOST) -> void
     {
         detail::check(neo_b200_conv_process(_conv, in, out, blocks, memspace));
     }
 
     [[nodiscard]] auto block_size() const noexcept -> size_type { return _cfg.block; }
+    [[nodiscard]] auto device_bytes() const noexcept -> size_type { return neo_b200_conv_device_bytes(_conv); }
     [[nodiscard]] auto handle() const noexcept -> neo_b200_conv* { return _conv; }
 
 private:
@@ -625,8 +645,9 @@ struct uniform_partitioned_convolver
     uniform_partitioned_convolver() = default;
 
     /// `filter(H)` for the dense aliases; `filter(H, sparsity)` for the sparse ones (sparse_filter.hpp:25-28): `sparsity(row, col,
-    /// value)` decides which bins the reference would store in its CSR matrix (csr_matrix.hpp:64-98); rejected bins are zeroed here,
-    /// which is the same sum (multiply_add over stored elements only, algorithm/multiply_add.hpp:306-324).
+    /// value)` decides which bins the reference stores in its CSR matrix. The same three containers are built here, element for
+    /// element as csr_matrix's constructor does (csr_matrix.hpp:64-98), and handed to the device, which keeps only the stored
+    /// elements and multiplies only them (algorithm/multiply_add.hpp:306-324).
     template<typename Mat, typename... Args>
     auto filter(Mat h, Args... args) -> void
     {
@@ -635,20 +656,43 @@ struct uniform_partitioned_convolver
         auto const bins  = static_cast<std::size_t>(h.extent(1));
         auto const* ptr  = reinterpret_cast<std::complex<real_type> const*>(h.data_handle());
         constexpr bool has_predicate = sizeof...(Args) == 1 && (std::is_invocable_r_v<bool, Args, std::size_t, std::size_t, Complex> && ...);
-        if (has_predicate || h.stride(1) != 1 || static_cast<std::size_t>(h.stride(0)) != bins) {
+        if constexpr (has_predicate) {
+            _csr_rows.assign(parts + 1, 0);
+            _csr_cols.clear();
+            _copy.clear();
+            for (std::size_t p = 0; p < parts; ++p) {
+                _csr_rows[p] = _csr_cols.size();
+                for (std::size_t k = 0; k < bins; ++k) {
+                    auto const v = h(p, k);
+                    if ((static_cast<bool>(args(p, k, v)) && ...)) {
+                        _copy.emplace_back(v.real(), v.imag());
+                        _csr_cols.push_back(k);
+                    }
+                }
+            }
+            _csr_rows[parts]          = _csr_cols.size();
+            std::uint64_t const fb[2] = {0, _csr_cols.size()};
+            _bank.filter_csr(_copy.data(), _csr_cols.data(), _csr_rows.data(), fb, 1, parts, bins);
+            return;
+        }
+        if (h.stride(1) != 1 || static_cast<std::size_t>(h.stride(0)) != bins) {
             _copy.resize(parts * bins);
             for (std::size_t p = 0; p < parts; ++p) {
                 for (std::size_t k = 0; k < bins; ++k) {
-                    auto const v = h(p, k);
-                    bool keep    = true;
-                    if constexpr (has_predicate) { keep = (static_cast<bool>(args(p, k, v)) && ...); }
-                    _copy[p * bins + k] = keep ? std::complex<real_type>{v.real(), v.imag()} : std::complex<real_type>{};
+                    auto const v        = h(p, k);
+                    _copy[p * bins + k] = std::complex<real_type>{v.real(), v.imag()};
                 }
             }
             ptr = _copy.data();
         }
         _bank.filter(ptr, 1, 1, parts, bins, NEO_B200_DIAGONAL);
     }
+
+    /// the CSR containers of the last sparse filter() call (row_container, column_container: csr_matrix.hpp:46-48) and what the
+    /// device holds for this convolver
+    [[nodiscard]] auto csr_row_container() const noexcept -> std::vector<std::uint64_t> const& { return _csr_rows; }
+    [[nodiscard]] auto csr_column_container() const noexcept -> std::vector<std::uint64_t> const& { return _csr_cols; }
+    [[nodiscard]] auto device_bytes() const noexcept -> std::size_t { return _bank.device_bytes(); }
 
     template<typename Vec>
     auto operator()(Vec block) -> void
@@ -673,6 +717,7 @@ struct uniform_partitioned_convolver
 
 private:
     convolver_bank<real_type, Kind> _bank;
+    std::vector<std::uint64_t> _csr_rows, _csr_cols;
     std::vector<std::complex<real_type>> _copy;
     std::vector<real_type> _tmp;
 };
@@ -784,9 +829,8 @@ using upola_convolver_v2 = overlap_add_convolver<Complex>;
 /// neo::convolution::split_upols_convolver / split_upola_convolver (dense_convolver.hpp:32-41) differ from the dense aliases only
 /// in how the reference lays its FDL and filter out in host memory (split re/im planes for its SIMD loops); interface and results
 /// are the same (golden vectors: tests/test_conv_gpu.py), and the device layout is this library's own either way.
-/// neo::convolution::sparse_upols_convolver / sparse_upola_convolver (sparse_convolver.hpp:14-22): `filter(H, sparsity)`. The device
-/// filter stays dense (zeros where the predicate rejects): same results; a CSR device layout that would also skip the bytes is
-/// SURVEY 8f rank 4 and not built.
+/// neo::convolution::sparse_upols_convolver / sparse_upola_convolver (sparse_convolver.hpp:14-22): `filter(H, sparsity)` builds the
+/// reference's CSR matrix on the host and the device keeps only its stored elements (neo_b200_conv_set_filter_csr).
 template<typename Complex>
 using sparse_upols_convolver = upols_convolver<Complex>;
 template<typename Complex>

@@ -126,6 +126,7 @@ SIGNATURES = {
     "neo_b200_conv_create": (_i, [C.POINTER(_vp), C.POINTER(ConvConfig)]),
     "neo_b200_conv_destroy": (None, [_vp]),
     "neo_b200_conv_set_filter": (_i, [_vp, _vp, _i]),
+    "neo_b200_conv_set_filter_csr": (_i, [_vp, _vp, _vp, _vp, _vp]),
     "neo_b200_conv_set_impulse": (_i, [_vp, _vp, _sz, _i]),
     "neo_b200_conv_reset": (_i, [_vp]),
     "neo_b200_conv_process": (_i, [_vp, _vp, _vp, _sz, _i]),
@@ -568,6 +569,32 @@ class Convolver:
         partitions, bins = int(H.shape[-2]), int(H.shape[-1])
         self._create(outputs, inputs, bins - 1, partitions)
         _check(library().neo_b200_conv_set_filter(self._h, _ptr(H), _space(H)))
+
+    def filter_sparse(self, H, keep) -> None:
+        """sparse convolvers' filter(partitions, sparsity) (sparse_filter.hpp:25-28): H [C][P][B+1] numpy, `keep` a boolean array of
+        the same shape (the sparsity predicate evaluated per element). The CSR matrices are built here exactly as neo::csr_matrix
+        builds them (row-major stored elements, csr_matrix.hpp:64-98) and handed to neo_b200_conv_set_filter_csr; the device keeps
+        only the stored elements."""
+        import numpy as np
+
+        if self.topology != DIAGONAL or H.ndim != 3:
+            raise ValueError("sparse filters: diagonal topology, H[C][P][B+1]")
+        H = np.ascontiguousarray(H)
+        keep = np.ascontiguousarray(keep, dtype=bool)
+        if keep.shape != H.shape or _dtype_name(H) != ("complex64" if self.real == "float32" else "complex128"):
+            raise ValueError("sparsity mask / dtype mismatch")
+        outputs, partitions, bins = (int(v) for v in H.shape)
+        self._create(outputs, outputs, bins - 1, partitions)
+        counts = keep.sum(axis=2).astype(np.uint64)                       # [C][P] stored elements per row
+        row_ptr = np.zeros((outputs, partitions + 1), dtype=np.uint64)
+        row_ptr[:, 1:] = np.cumsum(counts, axis=1)
+        base = np.zeros(outputs + 1, dtype=np.uint64)
+        base[1:] = np.cumsum(row_ptr[:, -1])
+        cols = np.ascontiguousarray(np.nonzero(keep)[2].astype(np.uint64))  # row-major order = CSR order
+        vals = np.ascontiguousarray(H[keep])
+        self.csr = (row_ptr, cols, vals, base)
+        _check(library().neo_b200_conv_set_filter_csr(self._h, _ptr(vals) if vals.size else None, _ptr(cols) if cols.size else _ptr(base),
+                                                      _ptr(row_ptr), _ptr(base)))
 
     def impulse(self, ir, block: int) -> None:
         """filter(uniform_partition(ir, block)) without materialising H on the host. ir: [C][L] or [O][I][L]."""

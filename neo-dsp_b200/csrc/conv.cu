@@ -77,6 +77,11 @@ struct conv_engine
     wide_tables<10, 3, 3> wide10;
     bool use_wide{false}, use_wide_r2c{false};
     device_buffer filter, fdl, prev[2], tail, acc, acc_alt, ola_y, stage_in, stage_out, stage_filter, tickets;
+    // sparse filters (set_filter_csr): bitmap form of the reference's CSR matrices (conv_kernels.cuh, fdl_mac_sparse_kernel); the
+    // dense filter buffer is released while they are in place
+    bool sparse{false};
+    int nseg{1};
+    device_buffer sp_meta, sp_vals, sp_base;
     // partition-sharded handles alternate between two partial-spectra buffers, so the reduction of call i (NCCL reads the buffer
     // neo_b200_conv_spectra returned) may still be running while call i+1 writes the other one
     int acc_cur{0}, acc_last{0};
@@ -190,7 +195,7 @@ struct conv_engine
 
     size_t device_bytes() const
     {
-        return filter.bytes + fdl.bytes + prev[0].bytes + prev[1].bytes + tail.bytes + acc.bytes + acc_alt.bytes + ola_y.bytes + stage_in.bytes
+        return sp_meta.bytes + sp_vals.bytes + sp_base.bytes + filter.bytes + fdl.bytes + prev[0].bytes + prev[1].bytes + tail.bytes + acc.bytes + acc_alt.bytes + ola_y.bytes + stage_in.bytes
              + stage_out.bytes + stage_filter.bytes + fdl2.bytes + filter2.bytes + acc2.bytes + nyq_acc.bytes;
     }
 
@@ -298,8 +303,79 @@ struct conv_engine
     // frame mode: the level-1 filter exists only between begin_filter and finish_filter
     int begin_filter()
     {
-        if (frame > 0) { NEO_TRY(filter.reserve(filters * parts * m * sizeof(cx<T>))); }
+        if (frame > 0 || filter.ptr == nullptr) { NEO_TRY(filter.reserve(filters * parts * m * sizeof(cx<T>))); }
+        if (sparse) {  // a dense filter replaces the sparse one
+            sparse = false;
+            sp_meta.release();
+            sp_vals.release();
+            sp_base.release();
+        }
         return NEO_B200_OK;
+    }
+
+    // `sparse_filter::filter(partitions, sparsity)` (sparse_filter.hpp:25-28) for every channel of a diagonal bank: the CSR matrices
+    // exactly as neo::csr_matrix builds them (csr_matrix.hpp:64-98; rows = partitions, columns = the B+1 bins). Filter f owns entries
+    // [filter_base[f], filter_base[f+1]) of values / cols; row_ptr[f * (P+1) + p] is relative to filter_base[f]. Host memory.
+    int set_filter_csr(cx<T> const* values, std::uint64_t const* cols, std::uint64_t const* row_ptr, std::uint64_t const* filter_base,
+                       cudaStream_t stream)
+    {
+        if (cfg.topology != NEO_B200_DIAGONAL || frame > 0 || cfg.partition_begin != 0 || cfg.partition_end != cfg.partitions) {
+            return fail(NEO_B200_ERR_UNSUPPORTED, "sparse filters: diagonal topology, direct form (frame_blocks = 0), unsharded partitions");
+        }
+        size_t const P = size_t(parts), B = size_t(m);
+        nseg           = int((B + 31) / 32);
+        std::vector<uint2> meta(filters * size_t(nseg) * P, make_uint2(0U, 0U));
+        std::vector<unsigned long long> base(filters + 1, 0ULL);
+        std::vector<cx<T>> vals;
+        for (size_t f = 0; f < filters; ++f) {
+            std::uint64_t const* const rows = row_ptr + f * (P + 1);
+            std::uint64_t const* const fc   = cols + filter_base[f];
+            cx<T> const* const fv           = values + filter_base[f];
+            uint2* const fm                 = meta.data() + f * size_t(nseg) * P;
+            if (filter_base[f] + rows[P] != filter_base[f + 1]) { return fail(NEO_B200_ERR_INVALID, "CSR filter %zu: row_ptr and filter_base disagree", f); }
+            // presence bits; column B (Nyquist) shares packed element 0 with column 0
+            for (size_t p = 0; p < P; ++p) {
+                if (rows[p] > rows[p + 1]) { return fail(NEO_B200_ERR_INVALID, "CSR filter %zu: row_ptr not ascending", f); }
+                for (std::uint64_t i = rows[p]; i < rows[p + 1]; ++i) {
+                    if (fc[i] > B) { return fail(NEO_B200_ERR_INVALID, "CSR filter %zu: column %llu out of range", f, static_cast<unsigned long long>(fc[i])); }
+                    size_t const k = fc[i] == B ? 0 : size_t(fc[i]);
+                    fm[(k >> 5) * P + p].x |= 1U << (k & 31U);
+                }
+            }
+            // value offsets in (segment, partition) order, then the values themselves
+            base[f]           = vals.size();
+            std::uint64_t run = 0;
+            for (size_t sgm = 0; sgm < size_t(nseg); ++sgm) {
+                for (size_t p = 0; p < P; ++p) {
+                    fm[sgm * P + p].y = unsigned(run);
+                    run += std::uint64_t(__builtin_popcount(fm[sgm * P + p].x));
+                }
+            }
+            if (run > 0xffffffffULL) { return fail(NEO_B200_ERR_UNSUPPORTED, "CSR filter %zu: more than 2^32 stored elements", f); }
+            vals.resize(vals.size() + size_t(run), mk<T>(T(0), T(0)));
+            cx<T>* const out = vals.data() + base[f];
+            for (size_t p = 0; p < P; ++p) {
+                for (std::uint64_t i = rows[p]; i < rows[p + 1]; ++i) {
+                    size_t const k   = fc[i] == B ? 0 : size_t(fc[i]);
+                    uint2 const w    = fm[(k >> 5) * P + p];
+                    cx<T>& dst       = out[w.y + unsigned(__builtin_popcount(w.x & ((1U << (k & 31U)) - 1U)))];
+                    if (fc[i] == B) { dst.y = fv[i].x; }        // packed element 0 = (Re H[0], Re H[B]), as pack_filter_kernel
+                    else if (fc[i] == 0) { dst.x = fv[i].x; }
+                    else { dst = fv[i]; }
+                }
+            }
+        }
+        base[filters] = vals.size();
+        NEO_TRY(sp_meta.reserve(meta.size() * sizeof(uint2)));
+        NEO_TRY(sp_vals.reserve(std::max<size_t>(1, vals.size()) * sizeof(cx<T>)));
+        NEO_TRY(sp_base.reserve(base.size() * sizeof(unsigned long long)));
+        NEO_CUDA_TRY(cudaMemcpyAsync(sp_meta.ptr, meta.data(), meta.size() * sizeof(uint2), cudaMemcpyHostToDevice, stream));
+        if (!vals.empty()) { NEO_CUDA_TRY(cudaMemcpyAsync(sp_vals.ptr, vals.data(), vals.size() * sizeof(cx<T>), cudaMemcpyHostToDevice, stream)); }
+        NEO_CUDA_TRY(cudaMemcpyAsync(sp_base.ptr, base.data(), base.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice, stream));
+        NEO_CUDA_TRY(cudaStreamSynchronize(stream));
+        filter.release();  // the dense layout is not kept: the stored elements are all the filter bytes there are
+        sparse = true;
+        return finish_filter(stream);
     }
 
     int finish_filter(cudaStream_t stream)
@@ -599,6 +675,17 @@ struct conv_engine
 
         size_t tau = 0;
         NEO_TRY(mark_begin(1, stream));
+        if (sparse) {  // one launch per block: every stored element is used once, as in the streaming kernel
+            dim3 const grid(unsigned((nseg + 3) / 4), unsigned(nout));
+            for (; tau < blocks; ++tau) {
+                g.tau0 = int(tau);
+                g.wp   = int((write_pos + tau) % size_t(ring));
+                fdl_mac_sparse_kernel<T><<<grid, 128, 0, stream>>>(fdl.template as<cx<T>>(), sp_meta.template as<uint2>(), sp_vals.template as<cx<T>>(),
+                                                                  sp_base.template as<unsigned long long>(), acc_w(), g, nseg);
+                NEO_TRY(check_launch("fdl_mac_sparse_kernel"));
+                ++mac_launches;
+            }
+        }
         while (tau < blocks) {
             size_t const left = blocks - tau;
             g.tau0            = int(tau);
@@ -883,6 +970,21 @@ int neo_b200_conv_set_filter(neo_b200_conv* conv, void const* H, int memspace)
     if (conv == nullptr || H == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
     NEO_CUDA_TRY(cudaSetDevice(conv->device));
     NEO_TRY(NEO_CONV_ENGINE(conv, set_filter(H, memspace, conv->stream.stream)));
+    NEO_CUDA_TRY(cudaStreamSynchronize(conv->stream.stream));
+    return NEO_B200_OK;
+}
+
+int neo_b200_conv_set_filter_csr(neo_b200_conv* conv, void const* values, uint64_t const* cols, uint64_t const* row_ptr, uint64_t const* filter_base)
+{
+    if (conv == nullptr || cols == nullptr || row_ptr == nullptr || filter_base == nullptr || (values == nullptr && filter_base[conv->cfg.outputs] != 0)) {
+        return fail(NEO_B200_ERR_INVALID, "null argument");
+    }
+    NEO_CUDA_TRY(cudaSetDevice(conv->device));
+    if (conv->cfg.dtype == NEO_B200_F32) {
+        NEO_TRY(conv->f32.set_filter_csr(static_cast<float2 const*>(values), cols, row_ptr, filter_base, conv->stream.stream));
+    } else {
+        NEO_TRY(conv->f64.set_filter_csr(static_cast<double2 const*>(values), cols, row_ptr, filter_base, conv->stream.stream));
+    }
     NEO_CUDA_TRY(cudaStreamSynchronize(conv->stream.stream));
     return NEO_B200_OK;
 }

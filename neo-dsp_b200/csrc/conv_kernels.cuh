@@ -894,6 +894,75 @@ struct stft_r2c_io
     }
 };
 
+// ---- sparse filters (neo::convolution::sparse_filter, sparse_filter.hpp:16-38; CSR multiply_add, algorithm/multiply_add.hpp:306-324)
+// The reference keeps each channel's partitions as a CSR matrix (rows = partitions, columns = bins) and touches only the stored
+// elements. A GPU wants the bins of a warp side by side, so the device layout is a BITMAP form of the same matrix: the row of B packed
+// bins is cut into segments of 32 bins; per (filter, segment, partition) one word of presence bits and the offset of the segment's
+// stored values, which lie packed in (segment, partition, bin) order -- the order one warp walks them in:
+//     meta [filters][nseg][parts]  uint2 {mask, offset into the filter's run of values}
+//     vals [filters' runs]         complex, fbase[f] = first value of filter f
+// One warp = one segment of one channel: it reads 32 partitions' meta words in one coalesced load, hands them round by shuffle, SKIPS
+// a partition whose segment is empty (no filter bytes, no delay-line bytes), and otherwise gathers the stored values (a contiguous
+// run) and the delay-line row segment. Bytes per block and channel: 8 P nseg of meta + 8 nnz + the delay-line segments touched,
+// against 16 P B for the dense stream. Same products in the same order (partition 0 first) as the dense kernels: stored elements
+// give the reference's sum, dropped ones add nothing. Diagonal topology, T = 1 per launch, packed bin 0 = (Re X[0], Re X[B]).
+template<typename T>
+__global__ void __launch_bounds__(128)
+    fdl_mac_sparse_kernel(cx<T> const* __restrict__ fdl, uint2 const* __restrict__ meta, cx<T> const* __restrict__ vals,
+                          unsigned long long const* __restrict__ fbase, cx<T>* __restrict__ acc, mac_geom g, int nseg)
+{
+    using C          = cx<T>;
+    constexpr int U  = 4;  // partitions gathered together
+    int const lane   = int(threadIdx.x) & 31;
+    int const seg    = blockIdx.x * 4 + (int(threadIdx.x) >> 5);
+    int const out    = blockIdx.y + g.out0;
+    if (seg >= nseg) { return; }
+    int const k      = seg * 32 + lane;
+    bool const mine  = k < g.m;
+    bool const edge  = k == 0 && g.packed_edge != 0;
+    unsigned const below = (1U << lane) - 1U;
+    uint2 const* const mrow = meta + (size_t(out) * nseg + seg) * g.parts;
+    C const* const vrow     = vals + fbase[out];
+    size_t const xbase      = tiled_offset(size_t(out), g.nt, g.logw, size_t(g.ring), 0, mine ? k : 0);
+
+    C a = mk<T>(T(0), T(0));
+    for (int p0 = 0; p0 < g.parts; p0 += 32) {
+        uint2 const word = p0 + lane < g.parts ? mrow[p0 + lane] : make_uint2(0U, 0U);
+        int const count  = min(32, g.parts - p0);
+        for (int j0 = 0; j0 < count; j0 += U) {
+            C h[U], x[U];
+            bool on[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                unsigned const mask = __shfl_sync(0xffffffffU, word.x, (j0 + u) & 31);
+                unsigned const off  = __shfl_sync(0xffffffffU, word.y, (j0 + u) & 31);
+                on[u]               = j0 + u < count && ((mask >> lane) & 1U) != 0U;
+                if (on[u]) {
+                    int slot = (g.wp - g.age0 - (p0 + j0 + u)) % g.ring;
+                    slot += slot < 0 ? g.ring : 0;
+                    h[u] = vrow[off + __popc(mask & below)];
+                    x[u] = fdl[xbase + (size_t(slot) << g.logw)];
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                if (on[u]) {
+                    if (edge) {
+                        a.x = fma(x[u].x, h[u].x, a.x);
+                        a.y = fma(x[u].y, h[u].y, a.y);
+                    } else {
+                        a.x = fma(x[u].x, h[u].x, a.x);
+                        a.x = fma(-x[u].y, h[u].y, a.x);
+                        a.y = fma(x[u].x, h[u].y, a.y);
+                        a.y = fma(x[u].y, h[u].x, a.y);
+                    }
+                }
+            }
+        }
+    }
+    if (mine) { acc[(size_t(out) * g.blocks + g.tau0) * g.m + k] = a; }
+}
+
 // reference layout H[f][P][B+1] -> convolver layout [f][parts][B] for partitions [part0, part0+parts)
 template<typename T>
 __global__ void __launch_bounds__(256)

@@ -129,6 +129,16 @@ for real, tag in ((np.float32, "f32"), (np.float64, "f64")):
     g[f"conv/{tag}/upola_v2_chunk96"] = r.convolve_blocks(4, H, sig, chunk=96)
 g["conv/block"] = np.array([B, L, NB], dtype=np.int64)
 
+# sparse convolvers (convolution/sparse_convolver.hpp:14-22) on the f32 case above: csr_matrix containers of channel 0 and the outputs,
+# predicate |re| > threshold or |im| > threshold
+THRESH = 0.25
+H32 = g["conv/f32/H"]
+rows, cols, vals = r.csr_build(H32[0], THRESH)
+g["sparse/threshold"] = np.array([THRESH], dtype=np.float32)
+g["sparse/csr_rows"], g["sparse/csr_cols"], g["sparse/csr_vals"] = rows, cols, vals
+g["sparse/upols"] = r.convolve_blocks_sparse(5, H32, g["conv/f32/signal"], THRESH)
+g["sparse/upola"] = r.convolve_blocks_sparse(6, H32, g["conv/f32/signal"], THRESH)
+
 # overlap policies with an identity callback (convolution/overlap_test.cpp:21-64)
 sig = r.noise(128 * 6, 3, np.float32)
 g["overlap/signal"] = sig

@@ -161,11 +161,13 @@ static double oracle_canonical_f64(oracle_mt19937* g)
 #define R_SIN sinf
 #define R_SQRT sqrtf
 #define R_FMA fmaf
+#define R_LROUND lroundf
 #include "neo_oracle_impl.inc"
 #undef REAL
 #undef SUF
 #undef R_COS
 #undef R_FMA
+#undef R_LROUND
 #undef R_SIN
 #undef R_SQRT
 
@@ -175,10 +177,12 @@ static double oracle_canonical_f64(oracle_mt19937* g)
 #define R_SIN sin
 #define R_SQRT sqrt
 #define R_FMA fma
+#define R_LROUND lround
 #include "neo_oracle_impl.inc"
 #undef REAL
 #undef SUF
 #undef R_COS
 #undef R_FMA
+#undef R_LROUND
 #undef R_SIN
 #undef R_SQRT

@@ -34,6 +34,11 @@ void oracle_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, 
     void oracle_conv_destroy_##S(struct oracle_conv_##S* c);                                                           \
     void oracle_conv_filter_##S(struct oracle_conv_##S* c, REAL const* h, size_t parts, size_t bins);                  \
     void oracle_conv_process_##S(struct oracle_conv_##S* c, REAL* inout, size_t num_samples);                          \
+    void oracle_compress_row_##S(REAL const* in, size_t n, int bits, int16_t* out);                                    \
+    void oracle_decompress_row_##S(int16_t const* in, size_t n, int bits, REAL* out);                                  \
+    size_t oracle_csr_build_##S(REAL const* h, size_t rows, size_t cols, REAL threshold, uint64_t* row_ptr, uint64_t* col_idx,      \
+                                REAL* values);                                                                         \
+    void oracle_conv_filter_sparse_##S(struct oracle_conv_##S* c, REAL const* h, size_t parts, size_t bins, REAL threshold);       \
     void oracle_direct_convolve_##S(REAL const* sig, size_t sig_len, REAL const* ir, size_t ir_len, REAL* out, size_t out_len); \
     void oracle_fft_convolve_##S(REAL const* sig, size_t sig_len, REAL const* patch, size_t patch_len, REAL* out);      \
     void oracle_noise_##S(size_t n, uint32_t seed, REAL* out);

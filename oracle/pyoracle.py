@@ -221,6 +221,48 @@ class _Checker:
     def convolver(self, kind: int, dtype=np.float32) -> "_Convolver":
         return _Convolver(self, kind, np.dtype(dtype))
 
+    def compressed_fdl_roundtrip(self, row: np.ndarray, bits: int) -> np.ndarray:
+        """compressed_fdl<complex<float>, scalar_complex<intN>>: insert(row, 0) then operator[](0) (compressed_fdl.hpp:26-48)"""
+        row = np.ascontiguousarray(row, dtype=np.complex64)
+        out = np.zeros_like(row)
+        if self.prefix == "ref_":
+            self._fn("compressed_fdl_roundtrip_f32", None, [_vp, _sz, _i, _vp])(_ptr(row), row.size, bits, _ptr(out))
+        else:
+            q = self.compress_row(row, bits)
+            self._fn("decompress_row_f32", None, [_vp, _sz, _i, _vp])(_ptr(q), row.size, bits, _ptr(out))
+        return out
+
+    def compress_row(self, row: np.ndarray, bits: int) -> np.ndarray:
+        """the stored integers of compressed_fdl::insert: int16 [n][2] (int8 values sign-extended). Oracle only."""
+        row = np.ascontiguousarray(row)
+        q = np.zeros((row.size, 2), dtype=np.int16)
+        self._fn("compress_row_" + _SUF[np.dtype(_REAL[row.dtype])], None, [_vp, _sz, _i, _vp])(_ptr(row), row.size, bits, _ptr(q))
+        return q
+
+    def csr_build(self, H: np.ndarray, threshold: float):
+        """neo::csr_matrix(H, predicate) (container/csr_matrix.hpp:64-98), predicate |re| > threshold or |im| > threshold:
+        (row_ptr [P+1] uint64, cols [nnz] uint64, values [nnz] complex). float32 only."""
+        H = np.ascontiguousarray(H, dtype=np.complex64)
+        fn = self._fn("csr_build_f32", _sz, [_vp, _sz, _sz, C.c_float, _vp, _vp, _vp])
+        rows = np.zeros(H.shape[0] + 1, dtype=np.uint64)
+        nnz = int(fn(_ptr(H), H.shape[0], H.shape[1], threshold, _ptr(rows), None, None))
+        cols, vals = np.zeros(max(nnz, 1), dtype=np.uint64), np.zeros(max(nnz, 1), dtype=np.complex64)
+        fn(_ptr(H), H.shape[0], H.shape[1], threshold, _ptr(rows), _ptr(cols), _ptr(vals))
+        return rows, cols[:nnz], vals[:nnz]
+
+    def convolve_blocks_sparse(self, kind: int, H: np.ndarray, signal: np.ndarray, threshold: float) -> np.ndarray:
+        """convolve_blocks with sparse_upols (kind 5) / sparse_upola (kind 6) convolvers"""
+        real = np.dtype(_REAL[H.dtype])
+        out = np.ascontiguousarray(signal, dtype=real).copy()
+        block = H.shape[-1] - 1
+        for c in range(out.shape[0]):
+            conv = self.convolver(kind, real)
+            conv.filter_sparse(H[c], threshold)
+            for s in range(0, out.shape[1], block):
+                conv.process(out[c, s : s + block])
+            conv.close()
+        return out
+
     def convolve_blocks(self, kind: int, H: np.ndarray, signal: np.ndarray, chunk: int | None = None) -> np.ndarray:
         """Run one convolver per channel over signal[C][n] (n multiple of B) and return the output.
         H: [C][P][K] (own filter per channel)."""
@@ -247,6 +289,12 @@ class _Convolver:
     def filter(self, H: np.ndarray) -> None:
         H = np.ascontiguousarray(H, dtype=_CPLX[self.dtype])
         self.chk._fn("conv_filter_" + self.suf, None, [_vp, _vp, _sz, _sz])(self.h, _ptr(H), H.shape[0], H.shape[1])
+
+    def filter_sparse(self, H: np.ndarray, threshold: float) -> None:
+        """sparse_filter::filter(H, sparsity) with the predicate |re| > threshold or |im| > threshold (kinds 5, 6)"""
+        H = np.ascontiguousarray(H, dtype=_CPLX[self.dtype])
+        thr = C.c_float if self.dtype == np.float32 else C.c_double
+        self.chk._fn("conv_filter_sparse_" + self.suf, None, [_vp, _vp, _sz, _sz, thr])(self.h, _ptr(H), H.shape[0], H.shape[1], threshold)
 
     def process(self, block: np.ndarray) -> None:
         assert block.dtype == self.dtype and block.flags.c_contiguous

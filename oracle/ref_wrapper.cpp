@@ -113,7 +113,9 @@ struct convolver_box
         neo::convolution::upola_convolver<Complex>,
         neo::convolution::split_upols_convolver<Complex>,
         neo::convolution::split_upola_convolver<Complex>,
-        neo::convolution::upola_convolver_v2<Complex>>
+        neo::convolution::upola_convolver_v2<Complex>,
+        neo::convolution::sparse_upols_convolver<Complex>,
+        neo::convolution::sparse_upola_convolver<Complex>>
         impl;
 
     explicit convolver_box(int kind)
@@ -123,6 +125,8 @@ struct convolver_box
             case 1: impl.template emplace<1>(); break;
             case 2: impl.template emplace<2>(); break;
             case 3: impl.template emplace<3>(); break;
+            case 5: impl.template emplace<5>(); break;
+            case 6: impl.template emplace<6>(); break;
             default: impl.template emplace<4>(); break;
         }
     }
@@ -130,7 +134,27 @@ struct convolver_box
     auto filter(Float const* h, std::size_t parts, std::size_t bins) -> void
     {
         auto view = mat_view<Complex const>{reinterpret_cast<Complex const*>(h), parts, bins};
-        std::visit([&](auto& c) { c.filter(view); }, impl);
+        std::visit(
+            [&](auto& c) {
+                using conv_t = std::remove_cvref_t<decltype(c)>;
+                if constexpr (!std::is_same_v<conv_t, neo::convolution::sparse_upols_convolver<Complex>>
+                              && !std::is_same_v<conv_t, neo::convolution::sparse_upola_convolver<Complex>>) {
+                    c.filter(view);
+                }
+            },
+            impl
+        );
+    }
+
+    // sparse_filter::filter(input, sparsity) (sparse_filter.hpp:25-28); predicate: comparisons only (see neo_oracle_impl.inc)
+    auto filter_sparse(Float const* h, std::size_t parts, std::size_t bins, Float threshold) -> void
+    {
+        auto view       = mat_view<Complex const>{reinterpret_cast<Complex const*>(h), parts, bins};
+        auto const keep = [threshold](auto /*row*/, auto /*col*/, Complex v) {
+            return std::abs(v.real()) > threshold || std::abs(v.imag()) > threshold;
+        };
+        if (auto* c = std::get_if<5>(&impl)) { c->filter(view, keep); }
+        if (auto* c = std::get_if<6>(&impl)) { c->filter(view, keep); }
     }
 
     auto process(Float* block, std::size_t n) -> void
@@ -354,6 +378,49 @@ void ref_conv_filter_f32(void* h, float const* f, std::size_t parts, std::size_t
 void ref_conv_filter_f64(void* h, double const* f, std::size_t parts, std::size_t bins)
 {
     static_cast<convolver_box<double>*>(h)->filter(f, parts, bins);
+}
+// compressed_fdl<complex<float>, scalar_complex<int8/int16>> (convolution/compressed_fdl.hpp:17-52): insert `in` [n] as row 0 of a
+// 2-row delay line and read it back through operator[] (the compressed_accessor): out [n] complex
+void ref_compressed_fdl_roundtrip_f32(float const* in, std::size_t n, int bits, float* out)
+{
+    using C       = std::complex<float>;
+    auto const go = [&](auto fdl) {
+        fdl.insert(vec_view<C const>{reinterpret_cast<C const*>(in), n}, 0);
+        auto const row = fdl[0];
+        for (std::size_t i = 0; i < n; ++i) {
+            C const v      = row[i];
+            out[2 * i]     = v.real();
+            out[2 * i + 1] = v.imag();
+        }
+    };
+    auto const ext = Kokkos::dextents<std::size_t, 2>{2, n};
+    if (bits == 8) { go(neo::convolution::compressed_fdl<C, neo::scalar_complex<std::int8_t>>{ext}); }
+    else { go(neo::convolution::compressed_fdl<C, neo::scalar_complex<std::int16_t>>{ext}); }
+}
+void ref_conv_filter_sparse_f32(void* h, float const* f, std::size_t parts, std::size_t bins, float threshold)
+{
+    static_cast<convolver_box<float>*>(h)->filter_sparse(f, parts, bins, threshold);
+}
+void ref_conv_filter_sparse_f64(void* h, double const* f, std::size_t parts, std::size_t bins, double threshold)
+{
+    static_cast<convolver_box<double>*>(h)->filter_sparse(f, parts, bins, threshold);
+}
+// neo::csr_matrix(matrix, filter) (container/csr_matrix.hpp:64-98) with the same predicate: its three containers, copied out
+std::size_t ref_csr_build_f32(float const* h, std::size_t rows, std::size_t cols, float threshold, std::uint64_t* row_ptr,
+                              std::uint64_t* col_idx, float* values)
+{
+    using C   = std::complex<float>;
+    auto view = mat_view<C const>{reinterpret_cast<C const*>(h), rows, cols};
+    auto csr  = neo::csr_matrix<C>{view, [threshold](auto, auto, C v) {
+                                      return std::abs(v.real()) > threshold || std::abs(v.imag()) > threshold;
+                                  }};
+    auto const& r = csr.row_container();
+    auto const& c = csr.column_container();
+    auto const& v = csr.value_container();
+    if (row_ptr != nullptr) { std::copy(r.begin(), r.end(), row_ptr); }
+    if (col_idx != nullptr) { std::copy(c.begin(), c.end(), col_idx); }
+    if (values != nullptr) { std::memcpy(values, v.data(), v.size() * sizeof(C)); }
+    return v.size();
 }
 void ref_conv_process_f32(void* h, float* block, std::size_t n) { static_cast<convolver_box<float>*>(h)->process(block, n); }
 void ref_conv_process_f64(void* h, double* block, std::size_t n)

@@ -255,6 +255,33 @@ static auto test_sparse_convolver() -> void
     for (std::size_t b = 0; b < nblocks; ++b) { oracle_conv_process_f32(o, want.data() + b * block, block); }
     oracle_conv_destroy_f32(o);
     REQUIRE(rel_l2(got, want) <= 1e-5);
+    // the CSR containers handed to the device are the reference's (csr_matrix.hpp:64-98, restated in the oracle), and the device
+    // holds fewer bytes than with the dense layout of the same filter
+    {
+        float const thr      = 0.3F;
+        auto const threshold = [thr](std::size_t, std::size_t, Complex v) { return std::abs(v.real()) > thr || std::abs(v.imag()) > thr; };
+        auto rows            = std::vector<std::uint64_t>(parts + 1);
+        auto const nnz       = oracle_csr_build_f32(reinterpret_cast<float const*>(h.data()), parts, block + 1, thr, rows.data(), nullptr, nullptr);
+        auto cols            = std::vector<std::uint64_t>(nnz + 1);
+        auto vals            = std::vector<Complex>(nnz + 1);
+        oracle_csr_build_f32(reinterpret_cast<float const*>(h.data()), parts, block + 1, thr, rows.data(), cols.data(), reinterpret_cast<float*>(vals.data()));
+        cols.resize(nnz);
+        auto sparse = neo::b200::sparse_upola_convolver<Complex>{};
+        sparse.filter(mat<Complex const>{h.data(), parts, block + 1}, threshold);
+        REQUIRE(sparse.csr_row_container() == rows);
+        REQUIRE(sparse.csr_column_container() == cols);
+        auto dense = neo::b200::upola_convolver<Complex>{};
+        dense.filter(mat<Complex const>{h.data(), parts, block + 1});
+        REQUIRE(nnz < parts * (block + 1));
+        REQUIRE(sparse.device_bytes() < dense.device_bytes());
+        auto y = sig, ref = sig;
+        for (std::size_t b = 0; b < nblocks; ++b) { sparse(vec<float>{y.data() + b * block, block}); }
+        auto* so = oracle_conv_create_f32(6);
+        oracle_conv_filter_sparse_f32(so, reinterpret_cast<float const*>(h.data()), parts, block + 1, thr);
+        for (std::size_t b = 0; b < nblocks; ++b) { oracle_conv_process_f32(so, ref.data() + b * block, block); }
+        oracle_conv_destroy_f32(so);
+        REQUIRE(rel_l2(y, ref) <= 1e-5);
+    }
     // identity filter with an all-pass predicate (uniform_partitioned_convolver_test.cpp:57-61)
     auto id = std::vector<Complex>(3 * (block + 1), Complex{});
     for (std::size_t k = 0; k <= block; ++k) { id[k] = {1, 0}; }

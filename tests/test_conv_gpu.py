@@ -123,6 +123,52 @@ def test_impulse_entry_equals_filter_entry(gpu, orc):
     assert rel_l2(yb, ya) <= 2e-6
 
 
+@pytest.mark.parametrize("block,taps,channels,thr", [(128, 1000, 3, 0.05), (16, 16 * 41 - 3, 2, 0.2), (1024, 1024 * 6, 2, 0.02), (4, 40, 2, 0.3)])
+def test_sparse_filters_csr_device_layout(gpu, orc, golden, block, taps, channels, thr):
+    # sparse_upols / sparse_upola (sparse_convolver.hpp:14-22): the CSR matrices of neo::csr_matrix go to the device, which keeps
+    # and multiplies only the stored elements (multiply_add.hpp:306-324). Oracle = the reference's sparse convolvers (kinds 5, 6).
+    ir, sig = make_case(orc, channels, taps, block, 13)
+    H = orc.uniform_partition(ir, block)
+    keep = (np.abs(H.real) > thr) | (np.abs(H.imag) > thr)
+    assert 0 < keep.sum() < keep.size
+    for kind in (0, 1):
+        want = orc.convolve_blocks_sparse(5 + kind, H, sig, thr)
+        for pattern in ([1], [3, 1, 4]):
+            conv = gpu.Convolver(kind, np.float32, gpu.DIAGONAL, max_blocks=4)
+            conv.filter_sparse(H, keep)
+            # the containers handed over are the reference's own, bit for bit (channel 0 checked against the oracle's csr_matrix)
+            rows, cols, vals = orc.csr_build(H[0], thr)
+            n0 = int(rows[-1])
+            assert np.array_equal(conv.csr[0][0], rows) and np.array_equal(conv.csr[1][:n0], cols) and np.array_equal(conv.csr[2][:n0], vals)
+            got = run_bank(conv, sig, block, pattern)
+            assert rel_l2(got, want) <= 1e-5, (kind, pattern, rel_l2(got, want))
+            sparse_bytes = conv.device_bytes()
+            conv.filter(H)  # a dense filter replaces the sparse one (and the other way round)
+            assert rel_l2(run_bank(conv, sig, block, pattern), orc.convolve_blocks(kind, H, sig)) <= 1e-5
+            if keep.mean() < 0.8 and block >= 128:
+                assert sparse_bytes < conv.device_bytes()
+            conv.close()
+    # float64, and a filter whose predicate keeps nothing in some channels / everything in others
+    ir64, sig64 = make_case(orc, 2, 300, 32, 9, np.float64)
+    H64 = orc.uniform_partition(ir64, 32)
+    keep64 = np.ones(H64.shape, dtype=bool)
+    keep64[1] = False
+    conv = gpu.Convolver(gpu.UPOLS, np.float64, gpu.DIAGONAL, max_blocks=2)
+    conv.filter_sparse(H64, keep64)
+    got = run_bank(conv, sig64, 32, [2, 1])
+    conv.close()
+    want = orc.convolve_blocks(0, H64, sig64)
+    assert rel_l2(got[0], want[0]) <= 1e-12 and not got[1].any()
+    # the golden vectors of the compiled reference
+    gthr = float(golden["sparse/threshold"][0])
+    Hg, sg = golden["conv/f32/H"], golden["conv/f32/signal"]
+    for kind, name in ((0, "upols"), (1, "upola")):
+        conv = gpu.Convolver(kind, np.float32, gpu.DIAGONAL)
+        conv.filter_sparse(Hg, (np.abs(Hg.real) > gthr) | (np.abs(Hg.imag) > gthr))
+        assert rel_l2(run_bank(conv, sg, 32, [1]), golden[f"sparse/{name}"]) <= 1e-5
+        conv.close()
+
+
 def test_filter_swap_and_reset(gpu, orc):
     ir, sig = make_case(orc, 2, 500, 32, 10)
     ir2, _ = make_case(orc, 2, 300, 32, 10, seed=50)

@@ -272,6 +272,23 @@ def test_partition_and_convolvers_match_reference_golden(orc, golden, tag, tol):
     assert rel_l2(orc.convolve_blocks(4, H, sig, chunk=96), golden[f"conv/{tag}/upola_v2_chunk96"]) <= tol
 
 
+def test_sparse_filter_csr_and_sparse_convolvers_golden(orc, golden):
+    # csr_matrix(partitions, predicate) (container/csr_matrix.hpp:64-98): index containers BIT-EXACT; sparse_upols / sparse_upola
+    # (sparse_convolver.hpp:14-22) bit-identical to the compiled reference in float
+    thr = float(golden["sparse/threshold"][0])
+    H, sig = golden["conv/f32/H"], golden["conv/f32/signal"]
+    rows, cols, vals = orc.csr_build(H[0], thr)
+    assert np.array_equal(rows, golden["sparse/csr_rows"]) and np.array_equal(cols, golden["sparse/csr_cols"])
+    assert np.array_equal(vals, golden["sparse/csr_vals"])
+    assert 0 < rows[-1] < H[0].size  # the predicate drops something and keeps something
+    for kind, name in ((5, "upols"), (6, "upola")):
+        got = orc.convolve_blocks_sparse(kind, H, sig, thr)
+        assert np.array_equal(got, golden[f"sparse/{name}"]), name
+        # multiply_add over the stored elements only (algorithm/multiply_add.hpp:306-324) = the dense sum with the others zeroed
+        Hz = np.where((np.abs(H.real) > thr) | (np.abs(H.imag) > thr), H, 0).astype(np.complex64)
+        assert np.array_equal(got, orc.convolve_blocks(kind - 5, Hz, sig))
+
+
 def test_uniform_partition_shapes(orc):
     # convolution/uniform_partition_test.cpp:8-38
     for L in (4096, 4095):
