@@ -171,6 +171,18 @@ NEO_B200_API int neo_b200_digitrev_perm(size_t radix, size_t size, uint32_t* out
 /* fdl_index (convolution/fdl_index.hpp:24-36): for each of `calls` blocks the write position and the `parts`
  * (fdl row, filter row) pairs; evaluated with the indexer the MAC kernel uses. pairs: [calls][parts][2] */
 NEO_B200_API int neo_b200_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, uint32_t* pairs);
+/* neo::convolution::compressed_fdl<FloatComplex, IntComplex> (convolution/compressed_fdl.hpp:17-52): a delay line of `rows` rows
+ * of `cols` complex bins kept on the device as int8 or int16 complex (bits = 8 / 16; a quarter / half of the float32 bytes).
+ * insert (:36-48) stores (int) lround(part * (float) max) for every real and imaginary part, max = 127 / 32767 -- the reference's
+ * integers, bit for bit (parts are expected in [-1, 1], as there); row = `fdl[index]` through compressed_accessor
+ * (container/compressed_accessor.hpp:27-45): (Float) q * (1 / max). dtype: NEO_B200_F32 / F64 of the complex rows handed in and out;
+ * raw: the stored integers of a row ([cols][2] int8_t or int16_t) to HOST memory. */
+typedef struct neo_b200_compressed_fdl neo_b200_compressed_fdl;
+NEO_B200_API int neo_b200_compressed_fdl_create(neo_b200_compressed_fdl** fdl, size_t rows, size_t cols, int dtype, int bits);
+NEO_B200_API void neo_b200_compressed_fdl_destroy(neo_b200_compressed_fdl* fdl);
+NEO_B200_API int neo_b200_compressed_fdl_insert(neo_b200_compressed_fdl* fdl, void const* row, size_t index, int memspace);
+NEO_B200_API int neo_b200_compressed_fdl_row(neo_b200_compressed_fdl* fdl, size_t index, void* out, int memspace);
+NEO_B200_API int neo_b200_compressed_fdl_raw(neo_b200_compressed_fdl* fdl, size_t index, void* out_host);
 /* number of partitions of an L-tap impulse response at block size B (fft/stft.hpp:21-25, overlap 0): ceil(L/B) */
 NEO_B200_API size_t neo_b200_num_partitions(size_t taps, size_t block);
 /* fft/order.hpp:33-39 */

@@ -829,6 +829,69 @@ using upola_convolver_v2 = overlap_add_convolver<Complex>;
 /// neo::convolution::split_upols_convolver / split_upola_convolver (dense_convolver.hpp:32-41) differ from the dense aliases only
 /// in how the reference lays its FDL and filter out in host memory (split re/im planes for its SIMD loops); interface and results
 /// are the same (golden vectors: tests/test_conv_gpu.py), and the device layout is this library's own either way.
+/// neo::convolution::compressed_fdl<FloatComplex, IntComplex> (compressed_fdl.hpp:17-52) with the rows on the device as int8 / int16
+/// complex. `insert(row, index)` as there; `operator[](index)` returns the row as the reference's compressed_accessor would read it
+/// (a materialised copy instead of a lazily converting view); `raw(index)` the stored integers.
+template<typename FloatComplex, typename IntComplex>
+struct compressed_fdl
+{
+    using value_type      = FloatComplex;
+    using compressed_type = IntComplex;
+    using real_type       = typename FloatComplex::value_type;
+    using int_type        = typename IntComplex::value_type;
+    static_assert(sizeof(int_type) == 1 || sizeof(int_type) == 2, "int8 or int16 parts");
+
+    compressed_fdl() = default;
+    compressed_fdl(std::size_t rows, std::size_t cols) : _rows{rows}, _cols{cols}
+    {
+        detail::check(neo_b200_compressed_fdl_create(&_fdl, rows, cols, detail::dtype_of<real_type>, int(8 * sizeof(int_type))));
+    }
+    /// the reference's constructor takes `stdex::dextents<size_t, 2>` (compressed_fdl.hpp:24)
+    template<typename Extents, typename = decltype(std::declval<Extents const&>().extent(0))>
+    explicit compressed_fdl(Extents const& e) : compressed_fdl{static_cast<std::size_t>(e.extent(0)), static_cast<std::size_t>(e.extent(1))}
+    {}
+    compressed_fdl(compressed_fdl const&)                    = delete;
+    auto operator=(compressed_fdl const&) -> compressed_fdl& = delete;
+    compressed_fdl(compressed_fdl&& o) noexcept : _fdl{std::exchange(o._fdl, nullptr)}, _rows{o._rows}, _cols{o._cols} {}
+    auto operator=(compressed_fdl&& o) noexcept -> compressed_fdl&
+    {
+        if (this != &o) {
+            neo_b200_compressed_fdl_destroy(_fdl);
+            _fdl  = std::exchange(o._fdl, nullptr);
+            _rows = o._rows;
+            _cols = o._cols;
+        }
+        return *this;
+    }
+    ~compressed_fdl() { neo_b200_compressed_fdl_destroy(_fdl); }
+
+    template<typename Vec>
+    auto insert(Vec input, std::size_t index) -> void
+    {
+        auto row = std::vector<std::complex<real_type>>(_cols);
+        for (std::size_t i = 0; i < _cols && i < static_cast<std::size_t>(input.extent(0)); ++i) { row[i] = {input[i].real(), input[i].imag()}; }
+        detail::check(neo_b200_compressed_fdl_insert(_fdl, row.data(), index, NEO_B200_HOST));
+    }
+    [[nodiscard]] auto operator[](std::size_t index) const -> std::vector<FloatComplex>
+    {
+        auto row = std::vector<std::complex<real_type>>(_cols);
+        detail::check(neo_b200_compressed_fdl_row(_fdl, index, row.data(), NEO_B200_HOST));
+        auto out = std::vector<FloatComplex>(_cols);
+        for (std::size_t i = 0; i < _cols; ++i) { out[i] = FloatComplex{row[i].real(), row[i].imag()}; }
+        return out;
+    }
+    [[nodiscard]] auto raw(std::size_t index) const -> std::vector<int_type>
+    {
+        auto out = std::vector<int_type>(2 * _cols);
+        detail::check(neo_b200_compressed_fdl_raw(_fdl, index, out.data()));
+        return out;
+    }
+
+private:
+    neo_b200_compressed_fdl* _fdl{nullptr};
+    std::size_t _rows{0}, _cols{0};
+};
+
 /// neo::convolution::sparse_upols_convolver / sparse_upola_convolver (sparse_convolver.hpp:14-22): `filter(H, sparsity)` builds the
 /// reference's CSR matrix on the host and the device keeps only its stored elements (neo_b200_conv_set_filter_csr).
 template<typename Complex>

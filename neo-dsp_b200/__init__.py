@@ -127,6 +127,11 @@ SIGNATURES = {
     "neo_b200_conv_destroy": (None, [_vp]),
     "neo_b200_conv_set_filter": (_i, [_vp, _vp, _i]),
     "neo_b200_conv_set_filter_csr": (_i, [_vp, _vp, _vp, _vp, _vp]),
+    "neo_b200_compressed_fdl_create": (_i, [C.POINTER(_vp), _sz, _sz, _i, _i]),
+    "neo_b200_compressed_fdl_destroy": (None, [_vp]),
+    "neo_b200_compressed_fdl_insert": (_i, [_vp, _vp, _sz, _i]),
+    "neo_b200_compressed_fdl_row": (_i, [_vp, _sz, _vp, _i]),
+    "neo_b200_compressed_fdl_raw": (_i, [_vp, _sz, _vp]),
     "neo_b200_conv_set_impulse": (_i, [_vp, _vp, _sz, _i]),
     "neo_b200_conv_reset": (_i, [_vp]),
     "neo_b200_conv_process": (_i, [_vp, _vp, _vp, _sz, _i]),
@@ -526,6 +531,44 @@ def normalize_impulse(ir):
         raise ValueError("impulse response must be [channels][taps]")
     _check(library().neo_b200_normalize_impulse(_ptr(ir), int(ir.shape[0]), int(ir.shape[1]), _DTYPE_CODE[_dtype_name(ir)], _space(ir)))
     return ir
+
+
+class CompressedFDL:
+    """neo::convolution::compressed_fdl<FloatComplex, IntComplex> (compressed_fdl.hpp:17-52) on the device: `rows` rows of `cols`
+    complex bins stored as int8 / int16 complex. insert(row, index) / row(index) (= operator[]) / raw(index) (the stored integers)."""
+
+    def __init__(self, rows: int, cols: int, dtype="float32", bits: int = 16):
+        self.real = np.dtype(dtype).name
+        self.rows, self.cols, self.bits = int(rows), int(cols), int(bits)
+        self._h = _vp()
+        _check(library().neo_b200_compressed_fdl_create(C.byref(self._h), self.rows, self.cols, _DTYPE_CODE[self.real], self.bits))
+
+    def insert(self, row, index: int) -> None:
+        want = "complex64" if self.real == "float32" else "complex128"
+        if _dtype_name(row) != want or int(row.shape[-1]) != self.cols:
+            raise ValueError("row shape/dtype mismatch")
+        _check(library().neo_b200_compressed_fdl_insert(self._h, _ptr(row), int(index), _space(row)))
+
+    def row(self, index: int) -> np.ndarray:
+        out = np.zeros(self.cols, dtype=np.complex64 if self.real == "float32" else np.complex128)
+        _check(library().neo_b200_compressed_fdl_row(self._h, int(index), _ptr(out), HOST))
+        return out
+
+    def raw(self, index: int) -> np.ndarray:
+        out = np.zeros((self.cols, 2), dtype=np.int8 if self.bits == 8 else np.int16)
+        _check(library().neo_b200_compressed_fdl_raw(self._h, int(index), _ptr(out)))
+        return out
+
+    def close(self) -> None:
+        if self._h:
+            library().neo_b200_compressed_fdl_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Convolver:

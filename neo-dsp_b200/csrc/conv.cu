@@ -1567,6 +1567,106 @@ int neo_b200_digitrev_perm(size_t radix, size_t size, uint32_t* out)
     return table_to_host(buf, out, size);
 }
 
+}  // extern "C"
+
+// compressed delay line: [rows][cols] int8 / int16 complex on the device
+struct neo_b200_compressed_fdl
+{
+    int device{0};
+    int dtype{NEO_B200_F32};
+    int bits{16};
+    size_t rows{0}, cols{0};
+    device_buffer store, stage;
+
+    size_t part_bytes() const { return bits == 8 ? 1 : 2; }
+    template<typename T, typename I>
+    int insert(void const* row, size_t index, int memspace)
+    {
+        size_t const n = 2 * cols;
+        T const* src   = static_cast<T const*>(row);
+        if (memspace == NEO_B200_HOST) {
+            NEO_TRY(stage.reserve(n * sizeof(double)));
+            NEO_CUDA_TRY(cudaMemcpy(stage.ptr, row, n * sizeof(T), cudaMemcpyHostToDevice));
+            src = stage.as<T>();
+        }
+        compress_parts_kernel<T, I><<<unsigned((n + 255) / 256), 256>>>(src, store.as<I>() + index * n, n);
+        NEO_TRY(check_launch("compress_parts_kernel"));
+        NEO_CUDA_TRY(cudaDeviceSynchronize());
+        return NEO_B200_OK;
+    }
+    template<typename T, typename I>
+    int read(size_t index, void* out, int memspace)
+    {
+        size_t const n = 2 * cols;
+        T* dst         = static_cast<T*>(out);
+        if (memspace == NEO_B200_HOST) {
+            NEO_TRY(stage.reserve(n * sizeof(double)));
+            dst = stage.as<T>();
+        }
+        decompress_parts_kernel<T, I><<<unsigned((n + 255) / 256), 256>>>(store.as<I>() + index * n, dst, n);
+        NEO_TRY(check_launch("decompress_parts_kernel"));
+        if (memspace == NEO_B200_HOST) { NEO_CUDA_TRY(cudaMemcpy(out, stage.ptr, n * sizeof(T), cudaMemcpyDeviceToHost)); }
+        else { NEO_CUDA_TRY(cudaDeviceSynchronize()); }
+        return NEO_B200_OK;
+    }
+};
+
+extern "C" {
+
+int neo_b200_compressed_fdl_create(neo_b200_compressed_fdl** fdl, size_t rows, size_t cols, int dtype, int bits)
+{
+    if (fdl == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    *fdl = nullptr;
+    if ((dtype != NEO_B200_F32 && dtype != NEO_B200_F64) || (bits != 8 && bits != 16) || rows == 0 || cols == 0) {
+        return fail(NEO_B200_ERR_INVALID, "compressed_fdl: dtype F32/F64, bits 8/16, rows and cols > 0");
+    }
+    NEO_TRY(require_device());
+    auto h = std::make_unique<neo_b200_compressed_fdl>();
+    cudaGetDevice(&h->device);
+    h->dtype = dtype;
+    h->bits  = bits;
+    h->rows  = rows;
+    h->cols  = cols;
+    NEO_TRY(h->store.reserve(rows * cols * 2 * h->part_bytes()));
+    NEO_CUDA_TRY(cudaMemset(h->store.ptr, 0, h->store.bytes));  // the reference's mdarray is value-initialised
+    *fdl = h.release();
+    return NEO_B200_OK;
+}
+
+void neo_b200_compressed_fdl_destroy(neo_b200_compressed_fdl* fdl) { delete fdl; }
+
+int neo_b200_compressed_fdl_insert(neo_b200_compressed_fdl* fdl, void const* row, size_t index, int memspace)
+{
+    if (fdl == nullptr || row == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (index >= fdl->rows) { return fail(NEO_B200_ERR_INVALID, "compressed_fdl: row %zu of %zu", index, fdl->rows); }
+    NEO_CUDA_TRY(cudaSetDevice(fdl->device));
+    if (fdl->dtype == NEO_B200_F32) {
+        return fdl->bits == 8 ? fdl->insert<float, std::int8_t>(row, index, memspace) : fdl->insert<float, std::int16_t>(row, index, memspace);
+    }
+    return fdl->bits == 8 ? fdl->insert<double, std::int8_t>(row, index, memspace) : fdl->insert<double, std::int16_t>(row, index, memspace);
+}
+
+int neo_b200_compressed_fdl_row(neo_b200_compressed_fdl* fdl, size_t index, void* out, int memspace)
+{
+    if (fdl == nullptr || out == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (index >= fdl->rows) { return fail(NEO_B200_ERR_INVALID, "compressed_fdl: row %zu of %zu", index, fdl->rows); }
+    NEO_CUDA_TRY(cudaSetDevice(fdl->device));
+    if (fdl->dtype == NEO_B200_F32) {
+        return fdl->bits == 8 ? fdl->read<float, std::int8_t>(index, out, memspace) : fdl->read<float, std::int16_t>(index, out, memspace);
+    }
+    return fdl->bits == 8 ? fdl->read<double, std::int8_t>(index, out, memspace) : fdl->read<double, std::int16_t>(index, out, memspace);
+}
+
+int neo_b200_compressed_fdl_raw(neo_b200_compressed_fdl* fdl, size_t index, void* out_host)
+{
+    if (fdl == nullptr || out_host == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }
+    if (index >= fdl->rows) { return fail(NEO_B200_ERR_INVALID, "compressed_fdl: row %zu of %zu", index, fdl->rows); }
+    NEO_CUDA_TRY(cudaSetDevice(fdl->device));
+    size_t const bytes = 2 * fdl->cols * fdl->part_bytes();
+    NEO_CUDA_TRY(cudaMemcpy(out_host, static_cast<char const*>(fdl->store.ptr) + index * bytes, bytes, cudaMemcpyDeviceToHost));
+    return NEO_B200_OK;
+}
+
 int neo_b200_fdl_index_sequence(size_t parts, size_t calls, uint32_t* write_pos, uint32_t* pairs)
 {
     if (write_pos == nullptr || pairs == nullptr) { return fail(NEO_B200_ERR_INVALID, "null argument"); }

@@ -1013,6 +1013,30 @@ __global__ void __launch_bounds__(256) scale_by_min_factor_kernel(T* __restrict_
     for (size_t i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) { ir[i] = ir[i] * scale; }
 }
 
+// ---- compressed delay line (neo::convolution::compressed_fdl, compressed_fdl.hpp:17-52): rows stored as int8 / int16 complex ----
+// insert (:36-48): q = (int_type) lround(val * (float) max); read through compressed_accessor (compressed_accessor.hpp:27-45):
+// (Float) q * (Float(1) / Float(max)). One thread per real or imaginary part; the device stores exactly the reference's integers.
+template<typename T, typename I>
+__global__ void __launch_bounds__(256) compress_parts_kernel(T const* __restrict__ in, I* __restrict__ out, size_t n)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    constexpr float max_val = sizeof(I) == 1 ? 127.0F : 32767.0F;
+    long long q;
+    if constexpr (sizeof(T) == 4) { q = llroundf(in[i] * max_val); }
+    else { q = llround(in[i] * double(max_val)); }
+    out[i] = static_cast<I>(q);
+}
+
+template<typename T, typename I>
+__global__ void __launch_bounds__(256) decompress_parts_kernel(I const* __restrict__ in, T* __restrict__ out, size_t n)
+{
+    size_t const i = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (i >= n) { return; }
+    constexpr T inv_scale = T(1) / T(sizeof(I) == 1 ? 127 : 32767);
+    out[i]                = static_cast<T>(in[i]) * inv_scale;
+}
+
 __global__ void fdl_index_kernel(unsigned parts, unsigned calls, unsigned* write_pos, unsigned* pairs);
 __global__ void bitrev_table_kernel(unsigned order, unsigned* out);
 

@@ -139,6 +139,15 @@ g["sparse/csr_rows"], g["sparse/csr_cols"], g["sparse/csr_vals"] = rows, cols, v
 g["sparse/upols"] = r.convolve_blocks_sparse(5, H32, g["conv/f32/signal"], THRESH)
 g["sparse/upola"] = r.convolve_blocks_sparse(6, H32, g["conv/f32/signal"], THRESH)
 
+# compressed_fdl (convolution/compressed_fdl.hpp:17-52): the known-answer row of compressed_fdl_test.cpp:31-41 and noise in (-1, 1),
+# inserted and read back through the reference's accessor, int8 and int16
+kat = np.array([0 + 0.125j, 0.25 + 0.333j, 0.5 + 0.666j, 0.75 + 1j, -0.0 - 0.125j, -0.25 - 0.333j, -0.5 - 0.666j, -0.75 - 1j], dtype=np.complex64)
+cn = r.noise(257, 77, np.complex64)
+g["cfdl/kat_in"], g["cfdl/noise_in"] = kat, cn
+for bits in (8, 16):
+    g[f"cfdl/{bits}/kat_out"] = r.compressed_fdl_roundtrip(kat, bits)
+    g[f"cfdl/{bits}/noise_out"] = r.compressed_fdl_roundtrip(cn, bits)
+
 # overlap policies with an identity callback (convolution/overlap_test.cpp:21-64)
 sig = r.noise(128 * 6, 3, np.float32)
 g["overlap/signal"] = sig

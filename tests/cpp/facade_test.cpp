@@ -229,6 +229,37 @@ static auto test_dft_plan() -> void
     }
 }
 
+// compressed_fdl_test.cpp:14-76 against the facade: the reference's known-answer row, int8 and int16 parts
+template<typename Int>
+static auto test_compressed_fdl() -> void
+{
+    using FloatComplex = std::complex<float>;
+    struct IntComplex
+    {
+        using value_type = Int;
+    };
+    double const tolerance = sizeof(Int) == 1 ? 0.005 : 0.0001;
+    auto input = std::vector<FloatComplex>{{+0.000F, +0.125F}, {+0.250F, +0.333F}, {+0.500F, +0.666F}, {+0.750F, +1.000F},
+                                           {-0.000F, -0.125F}, {-0.250F, -0.333F}, {-0.500F, -0.666F}, {-0.750F, -1.000F}};
+    auto fdl   = neo::b200::compressed_fdl<FloatComplex, IntComplex>{4, 8};
+    fdl.insert(vec<FloatComplex const>{input.data(), input.size()}, 0);
+    auto const compressed = fdl[0];
+    REQUIRE(compressed.size() == 8);
+    auto ints = std::vector<std::int16_t>(16);
+    oracle_compress_row_f32(reinterpret_cast<float const*>(input.data()), 8, int(8 * sizeof(Int)), ints.data());
+    auto const raw = fdl.raw(0);
+    for (std::size_t i = 0; i < 8; ++i) {
+        REQUIRE(std::abs(double(compressed[i].real()) - double(input[i].real())) <= tolerance);
+        REQUIRE(std::abs(double(compressed[i].imag()) - double(input[i].imag())) <= tolerance);
+        REQUIRE(raw[2 * i] == Int(ints[2 * i]));          // the reference's integers, bit for bit
+        REQUIRE(raw[2 * i + 1] == Int(ints[2 * i + 1]));
+    }
+    // neo::add(compressed, output, output) with output = (1, 2) (:66-74)
+    REQUIRE(std::abs(double(compressed[1].real()) + 1.0 - 1.250) <= tolerance);
+    REQUIRE(std::abs(double(compressed[1].imag()) + 2.0 - 2.333) <= tolerance);
+    for (auto v : fdl[3]) { REQUIRE(v == FloatComplex{}); }
+}
+
 // sparse_upols_convolver (sparse_convolver.hpp:14-17): filter(H, sparsity) == the dense convolver on H with the rejected bins zeroed
 static auto test_sparse_convolver() -> void
 {
@@ -433,6 +464,8 @@ int main()
     test_convolver<float, neo::b200::split_upola_convolver, 1>();
     test_overlap_add_convolver();
     test_sparse_convolver();
+    test_compressed_fdl<std::int8_t>();
+    test_compressed_fdl<std::int16_t>();
     test_multi_gpu_bank();
     std::printf(failures == 0 ? "facade_test: all passed\n" : "facade_test: %d FAILED\n", failures);
     return failures == 0 ? 0 : 1;

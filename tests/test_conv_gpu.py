@@ -169,6 +169,34 @@ def test_sparse_filters_csr_device_layout(gpu, orc, golden, block, taps, channel
         conv.close()
 
 
+@pytest.mark.parametrize("bits", [8, 16])
+def test_compressed_fdl_on_the_device(gpu, orc, golden, bits):
+    # compressed_fdl (compressed_fdl.hpp:17-52): the device stores the reference's integers (bit-exact) and reads rows back as its
+    # compressed_accessor does; golden = the compiled reference's read-back
+    fdl = gpu.CompressedFDL(4, 257, "float32", bits)
+    x = golden["cfdl/noise_in"]
+    fdl.insert(x, 2)
+    assert np.array_equal(fdl.raw(2), orc.compress_row(x, bits).astype(fdl.raw(2).dtype))
+    assert np.array_equal(fdl.row(2), golden[f"cfdl/{bits}/noise_out"])
+    assert not fdl.raw(0).any() and not fdl.row(3).any()  # untouched rows are zero, like the reference's value-initialised storage
+    fdl.close()
+    kat = gpu.CompressedFDL(4, 8, "float32", bits)
+    kat.insert(golden["cfdl/kat_in"], 0)
+    assert np.array_equal(kat.row(0), golden[f"cfdl/{bits}/kat_out"])
+    kat.close()
+    # double-precision rows: val * (float) max is a double product there
+    xd = (orc.noise(100, 5, np.complex128) * 0.999).astype(np.complex128)
+    fd = gpu.CompressedFDL(2, 100, "float64", bits)
+    fd.insert(xd, 1)
+    q = orc.compress_row(xd, bits)
+    assert np.array_equal(fd.raw(1), q.astype(fd.raw(1).dtype))
+    top = 127 if bits == 8 else 32767
+    assert np.array_equal(fd.row(1).view(np.float64).reshape(-1, 2), q.astype(np.float64) * (1.0 / top))
+    with pytest.raises(RuntimeError):
+        fd.insert(xd, 2)  # past the last row
+    fd.close()
+
+
 def test_filter_swap_and_reset(gpu, orc):
     ir, sig = make_case(orc, 2, 500, 32, 10)
     ir2, _ = make_case(orc, 2, 300, 32, 10, seed=50)

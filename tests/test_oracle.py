@@ -289,6 +289,24 @@ def test_sparse_filter_csr_and_sparse_convolvers_golden(orc, golden):
         assert np.array_equal(got, orc.convolve_blocks(kind - 5, Hz, sig))
 
 
+def test_compressed_fdl_rows_golden_and_known_answer(orc, golden):
+    # compressed_fdl::insert + operator[] (compressed_fdl.hpp:26-48, compressed_accessor.hpp:27-45): the restatement reads back what
+    # the compiled reference reads back, bit for bit; tolerances of compressed_fdl_test.cpp:24-29 on its known-answer row
+    for bits, tol in ((8, 0.005), (16, 0.0001)):
+        for name in ("kat", "noise"):
+            x = golden[f"cfdl/{name}_in"]
+            got = orc.compressed_fdl_roundtrip(x, bits)
+            assert np.array_equal(got, golden[f"cfdl/{bits}/{name}_out"]), (bits, name)
+            if name == "kat":
+                assert np.abs((got - x).view(np.float32)).max() <= tol  # per part, as the reference's WithinAbs checks
+        q = orc.compress_row(golden["cfdl/kat_in"], bits)
+        top = 127 if bits == 8 else 32767
+        assert q[3, 1] == top and q[7, 1] == -top and q[0, 0] == 0 and q[2, 0] == (64 if bits == 8 else 16384)  # lround: half away from zero
+        # the stored integers are what the read-back values say they are
+        assert np.array_equal(np.rint(golden[f"cfdl/{bits}/noise_out"].view(np.float32).astype(np.float64) * top).astype(np.int16).reshape(-1, 2),
+                              orc.compress_row(golden["cfdl/noise_in"], bits))
+
+
 def test_uniform_partition_shapes(orc):
     # convolution/uniform_partition_test.cpp:8-38
     for L in (4096, 4095):
