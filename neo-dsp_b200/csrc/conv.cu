@@ -676,7 +676,7 @@ struct conv_engine
         size_t tau = 0;
         NEO_TRY(mark_begin(1, stream));
         if (sparse) {  // one launch per block: every stored element is used once, as in the streaming kernel
-            dim3 const grid(unsigned((nseg + 3) / 4), unsigned(nout));
+            dim3 const grid{unsigned(nseg), unsigned(nout), 1U};
             for (; tau < blocks; ++tau) {
                 g.tau0 = int(tau);
                 g.wp   = int((write_pos + tau) % size_t(ring));

@@ -901,22 +901,24 @@ struct stft_r2c_io
 // stored values, which lie packed in (segment, partition, bin) order -- the order one warp walks them in:
 //     meta [filters][nseg][parts]  uint2 {mask, offset into the filter's run of values}
 //     vals [filters' runs]         complex, fbase[f] = first value of filter f
-// One warp = one segment of one channel: it reads 32 partitions' meta words in one coalesced load, hands them round by shuffle, SKIPS
-// a partition whose segment is empty (no filter bytes, no delay-line bytes), and otherwise gathers the stored values (a contiguous
-// run) and the delay-line row segment. Bytes per block and channel: 8 P nseg of meta + 8 nnz + the delay-line segments touched,
-// against 16 P B for the dense stream. Same products in the same order (partition 0 first) as the dense kernels: stored elements
-// give the reference's sum, dropped ones add nothing. Diagonal topology, T = 1 per launch, packed bin 0 = (Re X[0], Re X[B]).
+// One CTA = one segment of one channel, its four warps taking 32-partition chunks in turn: a warp reads 32 partitions' meta words in
+// one coalesced load, hands them round by shuffle, SKIPS what is empty (no filter bytes, no delay-line bytes), and otherwise
+// gathers the stored values (a contiguous run) and the delay-line row segment. Bytes per block and channel: 8 P nseg of meta + 8 nnz + the delay-line segments touched,
+// against 16 P B for the dense stream. Stored elements give the reference's sum, dropped ones add nothing; the four warps' partial
+// sums are added in a fixed order. Diagonal topology, T = 1 per launch, packed bin 0 = (Re X[0], Re X[B]).
 template<typename T>
 __global__ void __launch_bounds__(128)
     fdl_mac_sparse_kernel(cx<T> const* __restrict__ fdl, uint2 const* __restrict__ meta, cx<T> const* __restrict__ vals,
                           unsigned long long const* __restrict__ fbase, cx<T>* __restrict__ acc, mac_geom g, int nseg)
 {
-    using C          = cx<T>;
-    constexpr int U  = 4;  // partitions gathered together
+    using C             = cx<T>;
+    constexpr int U     = 8;  // partitions gathered together
+    constexpr int WARPS = 4;  // warps of a CTA share one segment: they take the 32-partition chunks in turn (a bank of few channels
+                              // would otherwise leave most warp slots empty and every warp a long dependent walk)
     int const lane   = int(threadIdx.x) & 31;
-    int const seg    = blockIdx.x * 4 + (int(threadIdx.x) >> 5);
+    int const warp   = int(threadIdx.x) >> 5;
+    int const seg    = blockIdx.x;
     int const out    = blockIdx.y + g.out0;
-    if (seg >= nseg) { return; }
     int const k      = seg * 32 + lane;
     bool const mine  = k < g.m;
     bool const edge  = k == 0 && g.packed_edge != 0;
@@ -926,9 +928,12 @@ __global__ void __launch_bounds__(128)
     size_t const xbase      = tiled_offset(size_t(out), g.nt, g.logw, size_t(g.ring), 0, mine ? k : 0);
 
     C a = mk<T>(T(0), T(0));
-    for (int p0 = 0; p0 < g.parts; p0 += 32) {
+    for (int p0 = 32 * warp; p0 < g.parts; p0 += 32 * WARPS) {
         uint2 const word = p0 + lane < g.parts ? mrow[p0 + lane] : make_uint2(0U, 0U);
         int const count  = min(32, g.parts - p0);
+        int sbase        = (g.wp - g.age0 - p0) % g.ring;  // ring slot of partition p0; the following ones lie below it
+        sbase += sbase < 0 ? g.ring : 0;
+        if (__ballot_sync(0xffffffffU, word.x != 0U) == 0U) { continue; }  // 32 partitions with nothing stored in this segment
         for (int j0 = 0; j0 < count; j0 += U) {
             C h[U], x[U];
             bool on[U];
@@ -938,10 +943,10 @@ __global__ void __launch_bounds__(128)
                 unsigned const off  = __shfl_sync(0xffffffffU, word.y, (j0 + u) & 31);
                 on[u]               = j0 + u < count && ((mask >> lane) & 1U) != 0U;
                 if (on[u]) {
-                    int slot = (g.wp - g.age0 - (p0 + j0 + u)) % g.ring;
+                    int slot = sbase - (j0 + u);
                     slot += slot < 0 ? g.ring : 0;
-                    h[u] = vrow[off + __popc(mask & below)];
-                    x[u] = fdl[xbase + (size_t(slot) << g.logw)];
+                    h[u] = __ldcs(vrow + off + __popc(mask & below));
+                    x[u] = __ldcs(fdl + xbase + (size_t(slot) << g.logw));
                 }
             }
 #pragma unroll
@@ -960,7 +965,18 @@ __global__ void __launch_bounds__(128)
             }
         }
     }
-    if (mine) { acc[(size_t(out) * g.blocks + g.tau0) * g.m + k] = a; }
+    // the warps' partial sums, added in warp order (deterministic)
+    __shared__ C partial[WARPS][32];
+    partial[warp][lane] = a;
+    __syncthreads();
+    if (warp == 0 && mine) {
+#pragma unroll
+        for (int w = 1; w < WARPS; ++w) {
+            a.x += partial[w][lane].x;
+            a.y += partial[w][lane].y;
+        }
+        acc[(size_t(out) * g.blocks + g.tau0) * g.m + k] = a;
+    }
 }
 
 // reference layout H[f][P][B+1] -> convolver layout [f][parts][B] for partitions [part0, part0+parts)
