@@ -18,11 +18,12 @@ direct form (--frame 0 --blocks T) reuses every filter partition T times in the 
   fft_sweep    batched rfft/irfft float32 N=2^10..2^16 (BASELINE config 2), GB/s against the same HBM peak, CPU pair beside it
   configs      BASELINE configs 1, 3, 4 (c2c N=1024 batch 1; stereo reverb; 64x64 matrix) with the reference CPU figure beside each
 
-N > 1 (torchrun, one rank per GPU): the bank lives in the LIBRARY (neo_b200_bank_*, NCCL transport). Layout Gc x Gp: Gc channel
-groups, inside a group the partitions of every impulse response are sharded Gp ways and the partial spectra are summed with one
-ncclReduceScatter over NVLink (BASELINE config 5: "partitions sharded across GPUs with NVLink NCCL reduce of partial spectra"); every
-rank moves only 1/N of the input and output rows over its own host link and the shards of a group exchange input rows with
-ncclAllGather. Default Gp = 2. Total work is fixed: "scaling": "strong". The line also carries the no-collective layout (Gc = N),
+N > 1 (torchrun, one rank per GPU): the bank lives in the LIBRARY (neo_b200_bank_*). Layout Gc x Gp: Gc channel groups, inside a
+group the partitions of every impulse response are sharded Gp ways and the partial spectra are summed over NVLink (BASELINE config 5:
+"partitions sharded across GPUs with NVLink NCCL reduce of partial spectra" -- NEO_B200_BANK_EXCHANGE=collective does it with
+ncclReduceScatter; the default moves the rows with the copy engines and sums them inside the c2r kernel, which measured faster); every
+rank moves only 1/N of the input and output rows over its own host link and the shards of a group exchange input rows over NVLink.
+Default Gp = 2. Total work is fixed: "scaling": "strong". The line also carries the no-collective layout (Gc = N),
 BASELINE config 4 sharded by output channel, the FFT batch split over the ranks, and `parity_rel_l2`: rank 0's rows of a multi-step
 run compared with a single direct-form handle on the same inputs, outside the timed region (the run fails above 1e-5).
 """
@@ -948,8 +949,13 @@ def run_sharded(args, pkg, torch, dist, emit, rank, world, local, peak, peak_src
             "data": "synthetic",
             "config": {
                 "workload": WORKLOAD, "blocks_per_call": T, "mode": main["mode"],
-                "sharding": f"library bank (neo_b200_bank_*, NCCL transport): {main['layout']}; partial spectra of a group summed by "
-                            "ncclReduceScatter over NVLink, input rows of a group exchanged by ncclAllGather, three steps in flight",
+                "sharding": f"library bank (neo_b200_bank_*, one rank per process): {main['layout']}; exchange = "
+                            + {"dma": "copy engines over NVLink (CUDA IPC mappings): input rows into the other shards' rings, partial spectra into "
+                                      "the owner's inbox, summed inside the owner's c2r kernel; one-word ncclAllGather per step as the gate",
+                               "kernel": "peer stores from inside the fused frame kernel into the owner's inbox, summed inside its c2r kernel",
+                               "collective": "ncclAllGather of the input rows, ncclReduceScatter of the partial spectra"}.get(
+                                   os.environ.get("NEO_B200_BANK_EXCHANGE", "dma"), "see NEO_B200_BANK_EXCHANGE")
+                            + "; three steps in flight",
                 "layout": {"channel_groups": layout[0], "partition_shards": layout[1]},
                 "l2": "working set per rank and step (filter + delay line, several GB) exceeds the 126 MB L2; 4 rotating input buffers",
                 "realtime_x_aggregate_48k": main["value"] * 1e6 / 48000.0, "realtime_x_wall_1024ch_48k": main["realtime_x_wall_1024ch_48k"],
