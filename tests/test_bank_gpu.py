@@ -62,6 +62,25 @@ def test_bank_layouts_match_oracle(gpu, orc, layout, frame):
     bank.close()
 
 
+@pytest.mark.parametrize("exchange", ["dma", "kernel"])
+def test_bank_long_frames_partition_shards_take_the_32_point_fused_kernel(gpu, orc, monkeypatch, exchange):
+    # BASELINE config 5's sharded geometry in small: T = 256 (L = 512 frame transforms), P = 1024 over two partition shards = two
+    # second-level partitions per shard, shard 1 on a delayed input -- the case the 32-points-per-thread fused frame kernel is taken
+    # for (conv_frame.cuh); enough steps for shard 1's delayed history to reach the output
+    monkeypatch.setenv("NEO_B200_BANK_EXCHANGE", exchange)
+    C, B, P, T, steps = 4, 16, 1024, 256, 6
+    ir, sig = make_case(orc, C, B * P - 3, B, T * steps)
+    want = orc.convolve_blocks(0, orc.uniform_partition(ir, B), sig)
+    bank = gpu.Bank(gpu.UPOLS, np.float32, gpu.DIAGONAL, C, C, B, P, max_blocks=T, frame_blocks=T, layout=(2, 2), devices=devices_for(gpu, 4))
+    assert bank.ranks[1]["delay_blocks"] == 512
+    bank.impulse_global(ir)
+    got = run_bank_steps(bank, sig, B, T, pipelined=True)
+    bank.close()
+    for s in range(steps):
+        sl = slice(s * T * B, (s + 1) * T * B)
+        assert rel_l2(got[:, sl], want[:, sl]) <= 2e-5, s
+
+
 @pytest.mark.parametrize("real", [np.float32, np.float64])
 @pytest.mark.parametrize("kind", [0, 1])
 def test_bank_upola_and_f64(gpu, orc, real, kind):
