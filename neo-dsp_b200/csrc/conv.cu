@@ -76,6 +76,9 @@ struct conv_engine
     // takes the wide kernel only with NEO_B200_CONV_WIDE_R2C.
     wide_tables<10, 3, 3> wide10;
     bool use_wide{false}, use_wide_r2c{false};
+    // resident CTAs the wide kernels are compiled for (NEO_B200_CONV_WIDE_R2C / _C2R = 4, 5, 6 -> 128 / 96 / 80 registers). Measured (C5, frame
+    // mode T = 256, ms per step, r2c / c2r): 4: 0.704 / 0.636, 5: 0.672 / 0.611, 6: 0.756 / 0.743 (spills), cta_fft r2c 0.689
+    int wide_minb_r2c{5}, wide_minb_c2r{5};
     device_buffer filter, fdl, prev[2], tail, acc, acc_alt, ola_y, stage_in, stage_out, stage_filter, tickets;
     // sparse filters (set_filter_csr): bitmap form of the reference's CSR matrices (conv_kernels.cuh, fdl_mac_sparse_kernel); the
     // dense filter buffer is released while they are in place
@@ -217,6 +220,8 @@ struct conv_engine
             use_wide = logb == 10 && std::getenv("NEO_B200_CONV_NO_WIDE") == nullptr;
             if (use_wide) { NEO_TRY(wide10.build(stream)); }
             use_wide_r2c = use_wide && std::getenv("NEO_B200_CONV_WIDE_R2C") != nullptr;
+            if (char const* v = std::getenv("NEO_B200_CONV_WIDE_R2C")) { wide_minb_r2c = std::max(4, std::min(6, std::atoi(v))); }
+            if (char const* v = std::getenv("NEO_B200_CONV_WIDE_C2R")) { wide_minb_c2r = std::max(4, std::min(6, std::atoi(v))); }
         }
 
         size_t const csz = sizeof(cx<T>);
@@ -483,7 +488,7 @@ struct conv_engine
         if constexpr (sizeof(T) == 4 && LOGM == 10) {
             if (wide) {
                 return launch_r2c_wide_io<10, 3, 3>(io, wide10.ta.template as<float2>(), wide10.tb_fwd.template as<float2>(),
-                                                    wide10.rtw.template as<float2>(), batch, stream);
+                                                    wide10.rtw.template as<float2>(), batch, stream, wide_minb_r2c);
             }
         }
         return launch_r2c<T, LOGM>(io, tables.tw(), tables.rtw(), batch, stream);
@@ -495,7 +500,7 @@ struct conv_engine
         if constexpr (sizeof(T) == 4 && LOGM == 10) {
             if (wide) {
                 return launch_c2r_wide_io<10, 3, 3>(io, wide10.ta.template as<float2>(), wide10.tb_bwd.template as<float2>(),
-                                                    wide10.rtw.template as<float2>(), batch, stream);
+                                                    wide10.rtw.template as<float2>(), batch, stream, wide_minb_c2r);
             }
         }
         return launch_c2r<T, LOGM>(io, tables.tw(), tables.rtw(), batch, stream);

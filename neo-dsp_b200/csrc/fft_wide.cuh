@@ -958,8 +958,8 @@ __global__ void __launch_bounds__(wide_cfg<LOGM2, LOGR1, LOGR2>::NT, 1)
 // store phases drift apart and overlap. Policies provide (besides open / store / store_edges / load / load_edges of the narrow
 // kernels) the 128-bit accesses of the real side: load_pair<HI>(row, j), keep_pair(row, j, v), store_pair<HI>(row, j, z0, z1) with j
 // an even index inside the lower (HI = false) or upper half of the real row's complex pairs.
-template<int LOGM, int LOGR1, int LOGR2, int G, class IO>
-__global__ void __launch_bounds__(32 * G, 512 / (32 * G))
+template<int LOGM, int LOGR1, int LOGR2, int G, class IO, int MINB = 512 / (32 * G)>
+__global__ void __launch_bounds__(32 * G, MINB)
     r2c_wide_io_kernel(IO io, float2 const* __restrict__ ta, float2 const* __restrict__ tb, float2 const* __restrict__ rtw, size_t batch)
 {
     using W   = wide_fft<LOGM, LOGR1, LOGR2>;
@@ -1035,8 +1035,8 @@ __global__ void __launch_bounds__(32 * G, 512 / (32 * G))
     }
 }
 
-template<int LOGM, int LOGR1, int LOGR2, int G, class IO>
-__global__ void __launch_bounds__(32 * G, 512 / (32 * G))
+template<int LOGM, int LOGR1, int LOGR2, int G, class IO, int MINB = 512 / (32 * G)>
+__global__ void __launch_bounds__(32 * G, MINB)
     c2r_wide_io_kernel(IO io, float2 const* __restrict__ ta, float2 const* __restrict__ tb, float2 const* __restrict__ rtw, size_t batch)
 {
     using W   = wide_fft<LOGM, LOGR1, LOGR2>;
@@ -1098,28 +1098,38 @@ __global__ void __launch_bounds__(32 * G, 512 / (32 * G))
     }
 }
 
+// minb: resident CTAs per SM the kernel is compiled for (4 = 128 registers, 5 = 96, 6 = 80: more warps to hide the loads behind, at the
+// price of spills) -- a measured choice per direction, see conv_engine
 template<int LOGM, int LOGR1, int LOGR2, class IO>
-int launch_r2c_wide_io(IO const& io, float2 const* ta, float2 const* tb, float2 const* rtw, size_t batch, cudaStream_t stream)
+int launch_r2c_wide_io(IO const& io, float2 const* ta, float2 const* tb, float2 const* rtw, size_t batch, cudaStream_t stream, int minb = 4)
 {
     using cfg       = wide_cfg<LOGM, LOGR1, LOGR2>;
     constexpr int G = 4;
     if (batch == 0) { return NEO_B200_OK; }
-    auto kernel = r2c_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO>;
-    NEO_TRY(enable_smem(kernel, G * cfg::SMEM));
-    kernel<<<unsigned((batch + G - 1) / G), 32 * G, G * cfg::SMEM, stream>>>(io, ta, tb, rtw, batch);
-    return check_launch("r2c_wide_io_kernel");
+    auto const go = [&](auto kernel) {
+        NEO_TRY(enable_smem(kernel, G * cfg::SMEM));
+        kernel<<<unsigned((batch + G - 1) / G), 32 * G, G * cfg::SMEM, stream>>>(io, ta, tb, rtw, batch);
+        return check_launch("r2c_wide_io_kernel");
+    };
+    if (minb == 5) { return go(r2c_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO, 5>); }
+    if (minb == 6) { return go(r2c_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO, 6>); }
+    return go(r2c_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO, 4>);
 }
 
 template<int LOGM, int LOGR1, int LOGR2, class IO>
-int launch_c2r_wide_io(IO const& io, float2 const* ta, float2 const* tb, float2 const* rtw, size_t batch, cudaStream_t stream)
+int launch_c2r_wide_io(IO const& io, float2 const* ta, float2 const* tb, float2 const* rtw, size_t batch, cudaStream_t stream, int minb = 4)
 {
     using cfg       = wide_cfg<LOGM, LOGR1, LOGR2>;
     constexpr int G = 4;
     if (batch == 0) { return NEO_B200_OK; }
-    auto kernel = c2r_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO>;
-    NEO_TRY(enable_smem(kernel, G * cfg::SMEM));
-    kernel<<<unsigned((batch + G - 1) / G), 32 * G, G * cfg::SMEM, stream>>>(io, ta, tb, rtw, batch);
-    return check_launch("c2r_wide_io_kernel");
+    auto const go = [&](auto kernel) {
+        NEO_TRY(enable_smem(kernel, G * cfg::SMEM));
+        kernel<<<unsigned((batch + G - 1) / G), 32 * G, G * cfg::SMEM, stream>>>(io, ta, tb, rtw, batch);
+        return check_launch("c2r_wide_io_kernel");
+    };
+    if (minb == 5) { return go(c2r_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO, 5>); }
+    if (minb == 6) { return go(c2r_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO, 6>); }
+    return go(c2r_wide_io_kernel<LOGM, LOGR1, LOGR2, G, IO, 4>);
 }
 
 // ---- tables + launchers --------------------------------------------------------------------------------------------------------------
