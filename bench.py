@@ -468,7 +468,7 @@ def build_conv(pkg, torch, stream, T, frame, channels=CHANNELS, first=0):
     return conv
 
 
-def host_link_probe(torch, hx, hy, iters: int = 3):
+def host_link_probe(torch, hx, hy, iters: int = 8):
     """GB/s per direction of pinned H2D + D2H copies running at the same time (the bound of every e2e number here)"""
     dx, dy = torch.empty(hx.shape, dtype=hx.dtype, device="cuda"), torch.empty(hy.shape, dtype=hy.dtype, device="cuda")
     s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
@@ -550,8 +550,9 @@ def run_single(args, pkg, torch, emit, peak, peak_src):
     # what bounds it: the host link with both directions busy (plain pinned copies of the same buffers, no kernels)
     link = host_link_probe(torch, hx, hy)
     e2e["host_link"] = {"both_directions_gbs_each": link, "achieved_gbs_each": e2e_pinned * 1e6 * 4 / 1e9,
-                        "what": "cudaMemcpyAsync H2D and D2H of the step's 1 GiB buffers on two streams at once, GB/s per direction; "
-                                "e2e moves the same bytes, so achieved / both_directions is its fraction of the link"}
+                        "what": "cudaMemcpyAsync H2D and D2H of the step's 1 GiB buffers on two streams at once, GB/s per direction, best of 8 "
+                                "(a momentary figure: the host side is shared with the box's other GPUs); e2e moves the same bytes, so achieved / "
+                                "both_directions is its fraction of the link"}
     del hx, hy, px, py
 
     # ---- roofline of the dominant kernel (spectral MAC), from the event-timed launches inside the timed region ----
