@@ -148,6 +148,25 @@ def test_sparse_filters_csr_device_layout(gpu, orc, golden, block, taps, channel
             if keep.mean() < 0.8 and block >= 128:
                 assert sparse_bytes < conv.device_bytes()
             conv.close()
+    # a wide bank through the host pipeline (channel groups, T = 4 per call) and with device buffers
+    irw, sigw = make_case(orc, 48, 32 * 5, 32, 8)
+    Hw = orc.uniform_partition(irw, 32)
+    keepw = (np.abs(Hw.real) > 0.1) | (np.abs(Hw.imag) > 0.1)
+    wantw = orc.convolve_blocks_sparse(5, Hw, sigw, 0.1)
+    conv = gpu.Convolver(gpu.UPOLS, np.float32, gpu.DIAGONAL, max_blocks=4)
+    conv.filter_sparse(Hw, keepw)
+    assert rel_l2(run_bank(conv, sigw, 32, [4]), wantw) <= 1e-5
+    conv.reset()
+    import torch
+
+    x = torch.from_numpy(sigw).cuda()
+    y = torch.empty_like(x[:, : 4 * 32])
+    outs = []
+    for s in range(2):
+        conv(x[:, s * 128 : (s + 1) * 128].contiguous(), out=y)
+        outs.append(y.cpu().numpy())
+    conv.close()
+    assert rel_l2(np.concatenate(outs, axis=1), wantw) <= 1e-5
     # float64, and a filter whose predicate keeps nothing in some channels / everything in others
     ir64, sig64 = make_case(orc, 2, 300, 32, 9, np.float64)
     H64 = orc.uniform_partition(ir64, 32)
