@@ -926,8 +926,15 @@ def run_sharded(args, pkg, torch, dist, emit, rank, world, local, peak, peak_src
         frame = min(frame, PARTS // layout[1])  # a shard starts on a frame boundary of the partition axis
     T = frame if frame > 0 else args.blocks
     main = measure_layout(args, pkg, torch, dist, rank, world, local, layout, T, frame, args.steps)
-    alt = c4 = sweep = None
+    alt = c4 = sweep = f512 = None
     if not args.no_modes:
+        # the same layout at 512 blocks per call (the longest frame): fewer second-level partitions per shard, the best absolute throughput
+        if 0 < frame < 512 and PARTS // layout[1] >= 512:
+            try:
+                f512 = measure_layout(args, pkg, torch, dist, rank, world, local, layout, 512, 512, max(5, min(args.steps, 10)),
+                                      want_e2e=False, want_parity=True)
+            except Exception as exc:  # an extra: never let it take the line down (every rank raises or none does: same code, same sizes)
+                f512 = {"error": f"{type(exc).__name__}: {exc}"}
         # the no-collective layout of the same workload, same code path with Gp = 1
         if layout[1] != 1:
             alt = measure_layout(args, pkg, torch, dist, rank, world, local, (world, 1), args.frame or args.blocks, args.frame,
@@ -966,6 +973,10 @@ def run_sharded(args, pkg, torch, dist, emit, rank, world, local, peak, peak_src
             "parity_rel_l2": main["parity_rel_l2"], "parity_tolerance": PARITY_TOL,
             "device_bytes_per_rank": main["device_bytes_per_rank"],
         }
+        if f512 is not None:
+            line["modes"] = {"frame512": f512}
+            if "parity_rel_l2" in f512:
+                worst = max(worst, f512["parity_rel_l2"])
         if alt is not None:
             line["channel_sharded"] = alt
             worst = max(worst, alt["parity_rel_l2"])
