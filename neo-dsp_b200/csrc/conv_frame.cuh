@@ -31,6 +31,17 @@
 
 #include <cstdlib>
 
+// MAC staging of the 32-points-per-thread fused frame kernel: chunk = E / CHDIV points, NP stages outside the exchange tile (the others
+// lie inside it). Both shapes that leave two CTAs resident at L = 512 were measured (C5 geometry, ms per fused step at T=256 Q=4 / T=256 Q=2 /
+// T=512 Q=2): 4-point chunks, 2 + 4 stages: 7.29 / 4.44 / 9.09 (shipped); 8-point chunks, 1 + 2 stages (EXTRA="-DNEO_B200_FRAME32_CHDIV=4
+// -DNEO_B200_FRAME32_NP=1"): 7.48 / 4.49 / 9.02 -- the chunk size is not what this form waits for.
+#ifndef NEO_B200_FRAME32_CHDIV
+#define NEO_B200_FRAME32_CHDIV 8
+#endif
+#ifndef NEO_B200_FRAME32_NP
+#define NEO_B200_FRAME32_NP 2
+#endif
+
 namespace neo_b200 {
 
 // bins (independent sequences) per CTA: enough adjacent bins to fill a 128-byte segment, and at least 128 threads
@@ -350,14 +361,16 @@ template<typename T, int LOGL, int LOGG, int LOGE_F>
 struct frame_async_cfg
 {
     using cfg                      = frame_cfg<T, LOGL, LOGG, LOGE_F>;
-    // points per thread and chunk: half a thread's points; 4 with 32 points per thread, so that tile + two stages stay under half an
-    // SM's shared memory and two CTAs are resident
-    static constexpr int CH        = cfg::E >= 32 ? 4 : cfg::E >= 2 ? cfg::E / 2 : 1;
+    // points per thread and chunk: half a thread's points; an eighth with 32 points per thread
+    static constexpr int CH        = cfg::E >= 32 ? cfg::E / NEO_B200_FRAME32_CHDIV : cfg::E >= 2 ? cfg::E / 2 : 1;
+    // stages outside the exchange tile (they can be filled while the forward transform runs): two. With 32 points per thread tile +
+    // private stages must stay under half an SM's shared memory, so that two CTAs are resident
+    static constexpr int NP        = cfg::E >= 32 ? NEO_B200_FRAME32_NP : 2;
     static constexpr int NH        = cfg::E / CH;                                                  // chunks per partition
     static constexpr int OPERAND   = CH * cfg::TN * cfg::G * int(sizeof(cx<T>));                   // bytes of one operand of a chunk
     static constexpr int STAGE     = 2 * OPERAND;                                                  // <= the exchange tile
-    static constexpr int NS        = 2 + int(cfg::SMEM) / STAGE;                                   // stages: two private + those the idle tile holds
-    static constexpr size_t SMEM   = cfg::SMEM + 2 * size_t(STAGE);
+    static constexpr int NS        = NP + int(cfg::SMEM) / STAGE;                                  // stages: the private ones + those the idle tile holds
+    static constexpr size_t SMEM   = cfg::SMEM + NP * size_t(STAGE);
     static constexpr int PER_THREAD = OPERAND / 16 / cfg::THREADS;                                 // 16-byte pieces per thread
     static constexpr int ROW_PIECES = cfg::G * int(sizeof(cx<T>)) / 16;                            // pieces per group of bins
     static_assert(STAGE <= int(cfg::SMEM), "a stage must fit the exchange tile");
@@ -402,9 +415,9 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
 
     // ---- ASYNC: chunk c = (partition q = c / NH, half eh = c % NH of the thread's points); stage = c % 3 ----
     using ac = frame_async_cfg<T, LOGL, LOGG, LOGE_F>;
-    auto const stage_ptr = [&](int c) -> unsigned char* {  // stages 2 .. NS-1 lie in the exchange tile
+    auto const stage_ptr = [&](int c) -> unsigned char* {  // stages NP .. NS-1 lie in the exchange tile
         int const st = c % ac::NS;
-        return st >= 2 ? smem_raw + (st - 2) * ac::STAGE : smem_raw + cfg::SMEM + st * ac::STAGE;
+        return st >= ac::NP ? smem_raw + (st - ac::NP) * ac::STAGE : smem_raw + cfg::SMEM + st * ac::STAGE;
     };
     int const nchunks = io.parts2 * ac::NH;
     // Warp-private staging: a warp copies exactly the rows its own threads will read (its TW = 32/G values of t, all CH points u of
@@ -457,8 +470,10 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
         int const row  = half * g.frame + t + (e % (E / 2)) * TN;
         v[e]           = src[size_t(row) << g.logb];
     }
-    issue(0);
-    issue(1);
+    if constexpr (ASYNC) {
+#pragma unroll
+        for (int c = 0; c < ac::NP; ++c) { issue(c); }
+    }
 #pragma unroll
     for (int e = 0; e < E; ++e) {
         if constexpr (NYQ) { v[e] = mk<T>(v[e].y, T(0)); }
@@ -467,7 +482,7 @@ __global__ void __launch_bounds__(frame_cfg<T, LOGL, LOGG, LOGE_F>::THREADS, fra
     cta_fft<T, LOGL, -1, LOGE_F>::run(v, sm, tw, t);
     if constexpr (ASYNC) {  // the exchange tile is free until the inverse transform
 #pragma unroll
-        for (int c = 2; c < ac::NS; ++c) { issue(c); }
+        for (int c = ac::NP; c < ac::NS; ++c) { issue(c); }
     }
     if (live) {
 #pragma unroll
