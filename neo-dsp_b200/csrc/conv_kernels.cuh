@@ -930,37 +930,40 @@ __global__ void __launch_bounds__(128)
     C a = mk<T>(T(0), T(0));
     for (int p0 = 32 * warp; p0 < g.parts; p0 += 32 * WARPS) {
         uint2 const word = p0 + lane < g.parts ? mrow[p0 + lane] : make_uint2(0U, 0U);
-        int const count  = min(32, g.parts - p0);
         int sbase        = (g.wp - g.age0 - p0) % g.ring;  // ring slot of partition p0; the following ones lie below it
         sbase += sbase < 0 ? g.ring : 0;
-        if (__ballot_sync(0xffffffffU, word.x != 0U) == 0U) { continue; }  // 32 partitions with nothing stored in this segment
-        for (int j0 = 0; j0 < count; j0 += U) {
+        // the partitions of this chunk that store anything in this segment, U at a time. The body is branch-free (every lane loads:
+        // a lane without a stored bin re-reads the segment's first value and multiplies by zero; a turn with fewer than U partitions
+        // left repeats the last one with an empty mask), so all 2 U loads of a turn are in flight together -- with a branch per
+        // partition the walk was one dependent load after the other (ncu: 80 % of the stall samples on the gathers' addresses)
+        unsigned todo = __ballot_sync(0xffffffffU, word.x != 0U);
+        while (todo != 0U) {
             C h[U], x[U];
-            bool on[U];
+            int j = 0;
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                unsigned const mask = __shfl_sync(0xffffffffU, word.x, (j0 + u) & 31);
-                unsigned const off  = __shfl_sync(0xffffffffU, word.y, (j0 + u) & 31);
-                on[u]               = j0 + u < count && ((mask >> lane) & 1U) != 0U;
-                if (on[u]) {
-                    int slot = sbase - (j0 + u);
-                    slot += slot < 0 ? g.ring : 0;
-                    h[u] = __ldcs(vrow + off + __popc(mask & below));
-                    x[u] = __ldcs(fdl + xbase + (size_t(slot) << g.logw));
-                }
+                bool const live = todo != 0U;
+                j               = live ? __ffs(int(todo)) - 1 : j;
+                todo &= todo - 1U;  // 0 stays 0
+                unsigned const mask = live ? __shfl_sync(0xffffffffU, word.x, j) : 0U;
+                unsigned const off  = __shfl_sync(0xffffffffU, word.y, j);
+                bool const on       = ((mask >> lane) & 1U) != 0U;
+                int slot            = sbase - j;
+                slot += slot < 0 ? g.ring : 0;
+                C const hv = vrow[off + (on ? __popc(mask & below) : 0)];
+                x[u]       = fdl[xbase + (size_t(slot) << g.logw)];
+                h[u]       = on ? hv : mk<T>(T(0), T(0));
             }
 #pragma unroll
             for (int u = 0; u < U; ++u) {
-                if (on[u]) {
-                    if (edge) {
-                        a.x = fma(x[u].x, h[u].x, a.x);
-                        a.y = fma(x[u].y, h[u].y, a.y);
-                    } else {
-                        a.x = fma(x[u].x, h[u].x, a.x);
-                        a.x = fma(-x[u].y, h[u].y, a.x);
-                        a.y = fma(x[u].x, h[u].y, a.y);
-                        a.y = fma(x[u].y, h[u].x, a.y);
-                    }
+                if (edge) {
+                    a.x = fma(x[u].x, h[u].x, a.x);
+                    a.y = fma(x[u].y, h[u].y, a.y);
+                } else {
+                    a.x = fma(x[u].x, h[u].x, a.x);
+                    a.x = fma(-x[u].y, h[u].y, a.x);
+                    a.y = fma(x[u].x, h[u].y, a.y);
+                    a.y = fma(x[u].y, h[u].x, a.y);
                 }
             }
         }
